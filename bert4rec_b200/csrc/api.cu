@@ -1,0 +1,736 @@
+// C ABI (include/b4r.h): parameter layout, session (workspace carving + the kernel schedule of one
+// forward / backward / optimizer step), ranking entry points.  Host-side only: every function enqueues on the
+// caller's stream and returns.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b4r.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace b4r;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" int b4r_version(void) { return B4R_VERSION; }
+extern "C" const char* b4r_last_error(void) { return g_err; }
+extern "C" int b4r_device_check(int device) {
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10) return fail("device %d is sm_%d%d; libb4r is built for sm_100a (B200) only", device, p.major, p.minor);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ layout
+namespace {
+struct Seg { std::string name; int64_t off, numel; int rows, cols, group; };
+struct Layout {
+  std::vector<Seg> segs;
+  int64_t n_decay = 0, n_train = 0, n_total = 0;
+  int64_t find(const std::string& n) const {
+    for (auto& s : segs) if (s.name == n) return s.off;
+    return -1;
+  }
+};
+static int64_t pad8(int64_t x) { return (x + 7) / 8 * 8; }
+
+static int check_cfg(const b4r_config* c) {
+  if (!c) return fail("null config");
+  const int H = c->hidden_size;
+  if (H != 64 && H != 128 && H != 256) return fail("hidden_size %d unsupported (64, 128, 256)", H);
+  if (c->num_heads <= 0 || H % c->num_heads) return fail("hidden_size %d not divisible by num_heads %d", H, c->num_heads);
+  const int D = H / c->num_heads;
+  if (D != 32 && D != 64) return fail("head dim %d unsupported (32, 64)", D);
+  if (c->inner_dim <= 0 || c->inner_dim % 8) return fail("inner_dim %d must be a positive multiple of 8", c->inner_dim);
+  if (c->vocab_size < 3) return fail("vocab_size %d too small", c->vocab_size);
+  if (c->max_seq_len < 1 || c->max_seq_len > 256) return fail("max_seq_len %d unsupported (1..256)", c->max_seq_len);
+  if (c->num_layers < 1 || c->num_layers > 64) return fail("num_layers %d unsupported", c->num_layers);
+  if (c->output_dropout < 0.f || c->output_dropout >= 1.f || c->attention_dropout < 0.f || c->attention_dropout >= 1.f)
+    return fail("dropout rates must be in [0,1)");
+  return 0;
+}
+
+static Layout make_layout(const b4r_config& c) {
+  Layout L;
+  int64_t off = 0;
+  auto add = [&](const std::string& n, int rows, int cols, int group) {
+    int64_t numel = (int64_t)rows * (cols ? cols : 1);
+    L.segs.push_back({n, off, numel, rows, cols, group});
+    off += pad8(numel);
+  };
+  const int V = c.vocab_size, H = c.hidden_size, I = c.inner_dim, Lyr = c.num_layers;
+  add("word_embeddings", V, H, 0);
+  add("position_embedding", c.max_seq_len, H, 0);
+  for (int l = 0; l < Lyr; ++l) {
+    std::string p = "layer_" + std::to_string(l) + "/";
+    add(p + "wqkv", H, 3 * H, 0);
+    add(p + "wo", H, H, 0);
+    add(p + "w1", H, I, 0);
+    add(p + "w2", I, H, 0);
+  }
+  add("head/wt", H, H, 0);
+  L.n_decay = off;
+  add("emb_ln/gamma", H, 0, 1);
+  add("emb_ln/beta", H, 0, 1);
+  for (int l = 0; l < Lyr; ++l) {
+    std::string p = "layer_" + std::to_string(l) + "/";
+    add(p + "bqkv", 3 * H, 0, 1);
+    add(p + "bo", H, 0, 1);
+    add(p + "ln1/gamma", H, 0, 1);
+    add(p + "ln1/beta", H, 0, 1);
+    add(p + "b1", I, 0, 1);
+    add(p + "b2", H, 0, 1);
+    add(p + "ln2/gamma", H, 0, 1);
+    add(p + "ln2/beta", H, 0, 1);
+  }
+  add("head/bt", H, 0, 1);
+  add("head/ln/gamma", H, 0, 1);
+  add("head/ln/beta", H, 0, 1);
+  add("head/output_bias", V, 0, 1);
+  L.n_train = off;
+  add("pooler/w", H, H, 2);
+  add("pooler/b", H, 0, 2);
+  L.n_total = off;
+  return L;
+}
+}  // namespace
+
+extern "C" int b4r_param_entries(const b4r_config* cfg, b4r_param_entry* out, int cap) {
+  if (check_cfg(cfg)) return -1;
+  Layout L = make_layout(*cfg);
+  int n = (int)L.segs.size();
+  if (out) {
+    for (int i = 0; i < n && i < cap; ++i) {
+      memset(&out[i], 0, sizeof(out[i]));
+      snprintf(out[i].name, sizeof(out[i].name), "%s", L.segs[i].name.c_str());
+      out[i].offset = L.segs[i].off; out[i].numel = L.segs[i].numel;
+      out[i].rows = L.segs[i].rows; out[i].cols = L.segs[i].cols; out[i].group = L.segs[i].group;
+    }
+  }
+  return n;
+}
+extern "C" int b4r_param_counts(const b4r_config* cfg, int64_t* n_decay, int64_t* n_trainable, int64_t* n_total) {
+  if (check_cfg(cfg)) return 1;
+  Layout L = make_layout(*cfg);
+  if (n_decay) *n_decay = L.n_decay;
+  if (n_trainable) *n_trainable = L.n_train;
+  if (n_total) *n_total = L.n_total;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ session
+namespace {
+struct LayerBuf {
+  bf16 *qkv, *ctx, *a_pre, *y, *h_pre, *h, *o_pre, *out;
+  float *lse, *mean1, *rstd1, *mean2, *rstd2;
+  uint64_t* keep;
+  // parameter offsets
+  int64_t wqkv, wo, w1, w2, bqkv, bo, g1, be1, b1, b2, g2, be2;
+  // gradient partial buffers
+  float *p_wqkv, *p_wo, *p_w1, *p_w2, *p_ln2, *p_ln1, *p_b1, *p_bqkv;
+  int s_wqkv, s_wo, s_w1, s_w2;
+};
+struct Bump {
+  char* base; size_t off, cap; bool dry;
+  template <class T> T* take(size_t n) {
+    off = (off + 255) / 256 * 256;
+    T* p = dry ? nullptr : reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+}  // namespace
+
+struct b4r_session {
+  b4r_config cfg;
+  int B, S, P, T, Mcap, H, I, V, N, Vp;
+  float* params; bf16* shadow; float* grads;
+  Layout lay;
+  bf16* x0;
+  std::vector<LayerBuf> layers;
+  // head
+  int *rows, *labels, *row_mult, *counts; float* row_w;
+  bf16 *t_pre, *t_act, *t; float *hmean, *hrstd;
+  float *ce_part, *lse, *lab, *stats, *step_stats;
+  int vsplits;
+  bf16* dlogits; int dl_rows;
+  float* dt_part; int dt_splits;
+  bf16* d_tpre;
+  float *p_head_ln, *p_wt, *p_vbias; int s_wt, vb_splits;
+  // backward scratch
+  float *dxa, *dxb; bf16 *d_branch, *dh, *dctx, *dqkv;
+  float *p_dpos, *p_embln; int emb_bsplits;
+  ReduceJob* d_jobs; int n_jobs, jobs_max_len;
+  ReduceJob* d_vb_jobs;  // [2]: first chunk (assign), later chunks (accumulate)
+  const int64_t *ids, *mask;
+  int select_mode;
+  int launches;
+};
+
+static int wgrad_splits(int M, int N, int T) {
+  int tiles = ((M + 63) / 64) * ((N + 63) / 64);
+  int s = (2 * 148 + tiles - 1) / tiles;
+  int cap = T / 256;
+  if (cap < 1) cap = 1;
+  if (s > cap) s = cap;
+  if (s < 1) s = 1;
+  return s;
+}
+
+static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<ReduceJob>* jobs) {
+  Bump b{reinterpret_cast<char*>(ws), 0, cap, dry};
+  const int T = s->T, H = s->H, I = s->I, V = s->V, N = s->N, B = s->B, S = s->S, Mcap = s->Mcap;
+  const int W = attn_mask_words(S);
+  auto off = [&](const std::string& n) { return s->lay.find(n); };
+  auto job = [&](float* src, int64_t dst_off, int nparts, int len, long long stride) {
+    if (jobs && s->grads) jobs->push_back(ReduceJob{src, s->grads + dst_off, nparts, len, stride, 0});
+  };
+  s->x0 = b.take<bf16>((size_t)T * H);
+  s->layers.resize(s->cfg.num_layers);
+  const int ln_parts = ln_bwd_parts(T);
+  const int mt128 = (T + gemm_block_m() - 1) / gemm_block_m();
+  for (int l = 0; l < s->cfg.num_layers; ++l) {
+    LayerBuf& L = s->layers[l];
+    std::string p = "layer_" + std::to_string(l) + "/";
+    L.wqkv = off(p + "wqkv"); L.wo = off(p + "wo"); L.w1 = off(p + "w1"); L.w2 = off(p + "w2");
+    L.bqkv = off(p + "bqkv"); L.bo = off(p + "bo"); L.g1 = off(p + "ln1/gamma"); L.be1 = off(p + "ln1/beta");
+    L.b1 = off(p + "b1"); L.b2 = off(p + "b2"); L.g2 = off(p + "ln2/gamma"); L.be2 = off(p + "ln2/beta");
+    L.qkv = b.take<bf16>((size_t)T * 3 * H);
+    L.ctx = b.take<bf16>((size_t)T * H);
+    L.a_pre = b.take<bf16>((size_t)T * H);
+    L.y = b.take<bf16>((size_t)T * H);
+    L.h_pre = b.take<bf16>((size_t)T * I);
+    L.h = b.take<bf16>((size_t)T * I);
+    L.o_pre = b.take<bf16>((size_t)T * H);
+    L.out = b.take<bf16>((size_t)T * H);
+    L.lse = b.take<float>((size_t)B * N * S);
+    L.mean1 = b.take<float>(T); L.rstd1 = b.take<float>(T); L.mean2 = b.take<float>(T); L.rstd2 = b.take<float>(T);
+    L.keep = b.take<uint64_t>((size_t)B * N * S * W);
+    L.s_wqkv = wgrad_splits(H, 3 * H, T); L.s_wo = wgrad_splits(H, H, T);
+    L.s_w1 = wgrad_splits(H, I, T); L.s_w2 = wgrad_splits(I, H, T);
+    L.p_wqkv = b.take<float>((size_t)L.s_wqkv * H * 3 * H);
+    L.p_wo = b.take<float>((size_t)L.s_wo * H * H);
+    L.p_w1 = b.take<float>((size_t)L.s_w1 * H * I);
+    L.p_w2 = b.take<float>((size_t)L.s_w2 * I * H);
+    L.p_ln2 = b.take<float>((size_t)ln_parts * 3 * H);
+    L.p_ln1 = b.take<float>((size_t)ln_parts * 3 * H);
+    L.p_b1 = b.take<float>((size_t)mt128 * I);
+    L.p_bqkv = b.take<float>((size_t)8 * 3 * H);
+    job(L.p_wqkv, L.wqkv, L.s_wqkv, H * 3 * H, (long long)H * 3 * H);
+    job(L.p_wo, L.wo, L.s_wo, H * H, (long long)H * H);
+    job(L.p_w1, L.w1, L.s_w1, H * I, (long long)H * I);
+    job(L.p_w2, L.w2, L.s_w2, I * H, (long long)I * H);
+    job(L.p_ln2, L.g2, ln_parts, H, 3 * H);
+    job(L.p_ln2 + H, L.be2, ln_parts, H, 3 * H);
+    job(L.p_ln2 + 2 * H, L.b2, ln_parts, H, 3 * H);
+    job(L.p_ln1, L.g1, ln_parts, H, 3 * H);
+    job(L.p_ln1 + H, L.be1, ln_parts, H, 3 * H);
+    job(L.p_ln1 + 2 * H, L.bo, ln_parts, H, 3 * H);
+    job(L.p_b1, L.b1, mt128, I, I);
+    job(L.p_bqkv, L.bqkv, 8, 3 * H, 3 * H);
+  }
+  // head
+  s->rows = b.take<int>(Mcap); s->labels = b.take<int>(Mcap); s->row_mult = b.take<int>(Mcap);
+  s->row_w = b.take<float>(Mcap); s->counts = b.take<int>(8);
+  s->t_pre = b.take<bf16>((size_t)Mcap * H); s->t_act = b.take<bf16>((size_t)Mcap * H); s->t = b.take<bf16>((size_t)Mcap * H);
+  s->hmean = b.take<float>(Mcap); s->hrstd = b.take<float>(Mcap);
+  {
+    int mtiles = (Mcap + ce_block_m() - 1) / ce_block_m();
+    int vtiles = (V + 127) / 128;
+    int vs = (2 * 148 + mtiles - 1) / mtiles;
+    if (vs > vtiles) vs = vtiles;
+    if (vs < 1) vs = 1;
+    if (vs > 64) vs = 64;
+    s->vsplits = vs;
+  }
+  s->ce_part = b.take<float>((size_t)s->vsplits * Mcap * 6);
+  s->lse = b.take<float>(Mcap); s->lab = b.take<float>(Mcap);
+  s->stats = b.take<float>(8); s->step_stats = b.take<float>(8);
+  {
+    // dlogits chunk: at most ~256 MB so that it stays close to the L2 / small in HBM
+    size_t max_rows = ((size_t)256 << 20) / ((size_t)s->Vp * 2);
+    max_rows = max_rows / 64 * 64;
+    if (max_rows < 64) max_rows = 64;
+    s->dl_rows = (int)((size_t)((Mcap + 63) / 64 * 64) < max_rows ? (size_t)((Mcap + 63) / 64 * 64) : max_rows);
+  }
+  s->dlogits = b.take<bf16>((size_t)s->dl_rows * s->Vp);
+  {
+    int mtiles = (Mcap + gemm_block_m() - 1) / gemm_block_m();
+    int sp = (2 * 148 + mtiles - 1) / mtiles;
+    int cap2 = s->Vp / 256;
+    if (sp > cap2) sp = cap2;
+    if (sp < 1) sp = 1;
+    if (sp > 32) sp = 32;
+    s->dt_splits = sp;
+  }
+  s->dt_part = b.take<float>((size_t)s->dt_splits * Mcap * H);
+  s->d_tpre = b.take<bf16>((size_t)Mcap * H);
+  const int head_parts = ln_bwd_parts(Mcap);
+  s->p_head_ln = b.take<float>((size_t)head_parts * 3 * H);
+  s->s_wt = wgrad_splits(H, H, Mcap);
+  s->p_wt = b.take<float>((size_t)s->s_wt * H * H);
+  s->vb_splits = 8;
+  s->p_vbias = b.take<float>((size_t)s->vb_splits * V);
+  job(s->p_head_ln, off("head/ln/gamma"), head_parts, H, 3 * H);
+  job(s->p_head_ln + H, off("head/ln/beta"), head_parts, H, 3 * H);
+  job(s->p_head_ln + 2 * H, off("head/bt"), head_parts, H, 3 * H);
+  job(s->p_wt, off("head/wt"), s->s_wt, H * H, (long long)H * H);
+  // backward scratch
+  s->dxa = b.take<float>((size_t)T * H); s->dxb = b.take<float>((size_t)T * H);
+  s->d_branch = b.take<bf16>((size_t)T * H); s->dh = b.take<bf16>((size_t)T * I);
+  s->dctx = b.take<bf16>((size_t)T * H); s->dqkv = b.take<bf16>((size_t)T * 3 * H);
+  s->emb_bsplits = embed_bwd_bsplits(B);
+  s->p_dpos = b.take<float>((size_t)s->emb_bsplits * S * H);
+  s->p_embln = b.take<float>((size_t)s->emb_bsplits * S * 2 * H);
+  job(s->p_dpos, off("position_embedding"), s->emb_bsplits, S * H, (long long)S * H);
+  job(s->p_embln, off("emb_ln/gamma"), s->emb_bsplits * S, H, 2 * H);
+  job(s->p_embln + H, off("emb_ln/beta"), s->emb_bsplits * S, H, 2 * H);
+  s->d_jobs = b.take<ReduceJob>(256);
+  s->d_vb_jobs = b.take<ReduceJob>(2);
+  return b.off + 256;
+}
+
+static b4r_session* make_session_shell(const b4r_config* cfg, int batch, int seq_len, int max_pred) {
+  b4r_session* s = new b4r_session();
+  s->cfg = *cfg;
+  s->B = batch; s->S = seq_len; s->P = max_pred; s->T = batch * seq_len;
+  s->Mcap = batch * max_pred + batch;
+  s->H = cfg->hidden_size; s->I = cfg->inner_dim; s->V = cfg->vocab_size; s->N = cfg->num_heads;
+  s->Vp = (cfg->vocab_size + 127) / 128 * 128;
+  s->lay = make_layout(*cfg);
+  s->params = nullptr; s->shadow = nullptr; s->grads = nullptr;
+  s->launches = 0; s->select_mode = 0; s->ids = nullptr; s->mask = nullptr;
+  return s;
+}
+
+static int check_dims(const b4r_config* cfg, int batch, int seq_len, int max_pred) {
+  if (check_cfg(cfg)) return 1;
+  if (batch < 1 || seq_len < 1 || max_pred < 0) return fail("bad session dims batch=%d seq_len=%d max_pred=%d", batch, seq_len, max_pred);
+  if (seq_len > cfg->max_seq_len) return fail("seq_len %d exceeds max_sequence_length %d", seq_len, cfg->max_seq_len);
+  if ((int64_t)batch * seq_len > (int64_t)1 << 30) return fail("batch*seq_len too large");
+  return 0;
+}
+
+extern "C" size_t b4r_session_workspace_bytes(const b4r_config* cfg, int batch, int seq_len, int max_pred) {
+  if (check_dims(cfg, batch, seq_len, max_pred)) return 0;
+  b4r_session* s = make_session_shell(cfg, batch, seq_len, max_pred);
+  size_t n = carve(s, nullptr, 0, true, nullptr);
+  delete s;
+  return n;
+}
+
+extern "C" int b4r_session_create(const b4r_config* cfg, int batch, int seq_len, int max_pred, float* params,
+                                  void* shadow_bf16, float* grads, void* workspace, size_t workspace_bytes,
+                                  b4r_session** out) {
+  if (!out) return fail("null out");
+  if (check_dims(cfg, batch, seq_len, max_pred)) return 1;
+  if (!params || !shadow_bf16 || !workspace) return fail("null buffer");
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (b4r_device_check(dev)) return 1;
+  if (((uintptr_t)params & 31) || ((uintptr_t)shadow_bf16 & 15) || ((uintptr_t)workspace & 255) || ((uintptr_t)grads & 31))
+    return fail("buffers must be aligned (params/grads 32 B, shadow 16 B, workspace 256 B)");
+  b4r_session* s = make_session_shell(cfg, batch, seq_len, max_pred);
+  s->params = params; s->shadow = reinterpret_cast<bf16*>(shadow_bf16); s->grads = grads;
+  std::vector<ReduceJob> jobs;
+  size_t need = carve(s, workspace, workspace_bytes, false, &jobs);
+  if (need > workspace_bytes) { delete s; return fail("workspace too small: need %zu bytes, got %zu", need, workspace_bytes); }
+  if (jobs.size() > 256) { delete s; return fail("too many reduce jobs"); }
+  s->n_jobs = (int)jobs.size();
+  s->jobs_max_len = 0;
+  for (auto& j : jobs) if (j.len > s->jobs_max_len) s->jobs_max_len = j.len;
+  CK(cudaMemcpy(s->d_jobs, jobs.data(), jobs.size() * sizeof(ReduceJob), cudaMemcpyHostToDevice));
+  ReduceJob vb[2];
+  vb[0] = ReduceJob{s->p_vbias, grads ? grads + s->lay.find("head/output_bias") : nullptr, s->vb_splits, s->V, (long long)s->V, 0};
+  vb[1] = vb[0]; vb[1].accumulate = 1;
+  CK(cudaMemcpy(s->d_vb_jobs, vb, sizeof(vb), cudaMemcpyHostToDevice));
+  CK(cudaMemset(s->stats, 0, 8 * sizeof(float)));
+  CK(cudaMemset(s->step_stats, 0, 8 * sizeof(float)));
+  CK(cudaMemset(s->counts, 0, 8 * sizeof(int)));
+  *out = s;
+  return 0;
+}
+
+extern "C" void b4r_session_destroy(b4r_session* s) { delete s; }
+
+extern "C" int b4r_sync_shadow(b4r_session* s, void* stream) {
+  if (!s) return fail("null session");
+  CK(launch_cast_bf16(s->params, s->shadow, s->lay.n_total, (cudaStream_t)stream));
+  s->launches++;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+extern "C" int b4r_encode(b4r_session* s, const int64_t* ids, const int64_t* mask, int training, uint64_t seed,
+                          uint32_t step, void* stream) {
+  if (!s || !ids || !mask) return fail("null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = s->T, H = s->H, I = s->I;
+  const float od = training ? s->cfg.output_dropout : 0.f, ad = training ? s->cfg.attention_dropout : 0.f;
+  const float* P = s->params;
+  const bf16* W = s->shadow;
+  s->ids = ids; s->mask = mask;
+  CK(launch_embed_ln_fwd(ids, W + s->lay.find("word_embeddings"), W + s->lay.find("position_embedding"),
+                         P + s->lay.find("emb_ln/gamma"), P + s->lay.find("emb_ln/beta"), s->x0, s->B, s->S, H, s->V, od,
+                         seed, step, st));
+  s->launches++;
+  const bf16* x = s->x0;
+  for (int l = 0; l < s->cfg.num_layers; ++l) {
+    LayerBuf& L = s->layers[l];
+    GemmArgs g{};
+    g.A = x; g.lda = H; g.B = W + L.wqkv; g.ldb = 3 * H; g.b_trans = true; g.M = T; g.N = 3 * H; g.K = H;
+    g.bias = P + L.bqkv; g.out_bf16 = L.qkv; g.ld_out = 3 * H;
+    CK(launch_gemm(EPI_BIAS_BF16, g, st));
+    AttnArgs a{};
+    a.qkv = L.qkv; a.mask = mask; a.ctx = L.ctx; a.lse = L.lse; a.keep_bits = L.keep; a.B = s->B; a.S = s->S; a.H = H; a.N = s->N;
+    a.drop_rate = ad; a.seed = seed; a.site = site_id(SITE_ATTN_PROBS, l); a.step = step;
+    CK(launch_attn_fwd(a, st));
+    RowLnArgs r{};
+    r.A = L.ctx; r.lda = H; r.W = W + L.wo; r.M = T; r.K = H; r.H = H; r.bias = P + L.bo; r.gamma = P + L.g1; r.beta = P + L.be1;
+    r.residual = x; r.pre = L.a_pre; r.y = L.y; r.mean = L.mean1; r.rstd = L.rstd1;
+    r.drop_rate = od; r.seed = seed; r.site = site_id(SITE_ATTN_OUT, l); r.step = step;
+    CK(launch_gemm_rowln(ROW_RES_DROP_LN, r, st));
+    GemmArgs f{};
+    f.A = L.y; f.lda = H; f.B = W + L.w1; f.ldb = I; f.b_trans = true; f.M = T; f.N = I; f.K = H;
+    f.bias = P + L.b1; f.out_bf16 = L.h_pre; f.out2_bf16 = L.h; f.ld_out = I;
+    CK(launch_gemm(EPI_BIAS_GELU, f, st));
+    RowLnArgs r2{};
+    r2.A = L.h; r2.lda = I; r2.W = W + L.w2; r2.M = T; r2.K = I; r2.H = H; r2.bias = P + L.b2; r2.gamma = P + L.g2; r2.beta = P + L.be2;
+    r2.residual = L.y; r2.pre = L.o_pre; r2.y = L.out; r2.mean = L.mean2; r2.rstd = L.rstd2;
+    r2.drop_rate = od; r2.seed = seed; r2.site = site_id(SITE_FFN_OUT, l); r2.step = step;
+    CK(launch_gemm_rowln(ROW_RES_DROP_LN, r2, st));
+    s->launches += 5;
+    x = L.out;
+  }
+  return 0;
+}
+
+extern "C" int b4r_mlm_select(b4r_session* s, const int64_t* positions, const int64_t* ids, const int64_t* weights,
+                              int mode, int want_aux, void* stream) {
+  if (!s || !positions) return fail("null argument");
+  if (mode == 0 && !ids) return fail("mode 0 needs masked_lm_ids");
+  if (mode == 1 && !weights) return fail("mode 1 needs masked_lm_weights");
+  if (s->P < 1) return fail("session was created with max_pred = 0");
+  // mode 2 (all slots): reuse the weights path with a null test -> handled by passing positions as weights of ones
+  s->select_mode = mode;
+  const int64_t* id_src = ids ? ids : positions;
+  if (mode == 2) {
+    // all slots valid: weights := non-null pointer whose values are irrelevant -> use use_weights = 2
+    CK(launch_mlm_select(positions, id_src, nullptr, 2, s->B, s->S, s->P, 0, s->rows, s->labels, s->row_w, s->row_mult, s->counts, (cudaStream_t)stream));
+  } else {
+    CK(launch_mlm_select(positions, id_src, weights, mode, s->B, s->S, s->P, want_aux, s->rows, s->labels, s->row_w, s->row_mult, s->counts, (cudaStream_t)stream));
+  }
+  s->launches++;
+  return 0;
+}
+
+extern "C" int b4r_mlm_transform(b4r_session* s, void* stream) {
+  if (!s) return fail("null session");
+  const int H = s->H;
+  const bf16* x = s->layers.back().out;
+  RowLnArgs r{};
+  r.A = x; r.lda = H; r.a_rows = s->rows; r.W = s->shadow + s->lay.find("head/wt"); r.M = s->Mcap; r.K = H; r.H = H;
+  r.d_M = s->counts + 1;
+  r.bias = s->params + s->lay.find("head/bt"); r.gamma = s->params + s->lay.find("head/ln/gamma"); r.beta = s->params + s->lay.find("head/ln/beta");
+  r.pre = s->t_pre; r.act = s->t_act; r.y = s->t; r.mean = s->hmean; r.rstd = s->hrstd;
+  CK(launch_gemm_rowln(ROW_GELU_LN, r, (cudaStream_t)stream));
+  s->launches++;
+  return 0;
+}
+
+static CeArgs ce_args(b4r_session* s) {
+  CeArgs c{};
+  c.t = s->t; c.ldt = s->H; c.E = s->shadow + s->lay.find("word_embeddings"); c.vbias = s->params + s->lay.find("head/output_bias");
+  c.labels = s->labels; c.row_w = s->row_w; c.row_mult = s->row_mult; c.d_counts = s->counts;
+  c.M_cap = s->Mcap; c.H = s->H; c.V = s->V; c.v_begin = 0; c.v_end = s->V; c.vsplits = s->vsplits;
+  c.part = s->ce_part; c.lse = s->lse; c.lab_out = s->lab; c.stats = s->stats; c.step_stats = s->step_stats;
+  c.dlogits = s->dlogits; c.ld_dl = s->Vp;
+  return c;
+}
+
+extern "C" int b4r_mlm_loss(b4r_session* s, void* stream) {
+  if (!s) return fail("null session");
+  CeArgs c = ce_args(s);
+  CK(launch_ce_fwd(c, (cudaStream_t)stream));
+  CK(launch_ce_finalize(c, (cudaStream_t)stream));
+  s->launches += 2;
+  return 0;
+}
+
+extern "C" int b4r_mlm_logits(b4r_session* s, float* out, void* stream) {
+  if (!s || !out) return fail("null argument");
+  GemmArgs g{};
+  g.A = s->t; g.lda = s->H; g.B = s->shadow + s->lay.find("word_embeddings"); g.ldb = s->H; g.b_trans = false;
+  g.M = s->Mcap; g.N = s->V; g.K = s->H; g.d_M = s->counts + 1;
+  g.bias = s->params + s->lay.find("head/output_bias"); g.out_f32 = out; g.ld_f32 = s->V;
+  CK(launch_gemm(EPI_BIAS_F32, g, (cudaStream_t)stream));
+  s->launches++;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, void* stream) {
+  if (!s || !s->grads) return fail("session has no gradient buffer");
+  if (!s->ids) return fail("b4r_encode must run before b4r_backward");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = s->T, H = s->H, I = s->I, V = s->V, Mcap = s->Mcap;
+  const float* P = s->params;
+  const bf16* W = s->shadow;
+  float* G = s->grads;
+  const float od = s->cfg.output_dropout;
+  const int64_t oE = s->lay.find("word_embeddings");
+  // gradient accumulators that are scatter / accumulate targets
+  CK(cudaMemsetAsync(G + oE, 0, (size_t)V * H * sizeof(float), st));
+  CK(cudaMemsetAsync(s->dxa, 0, (size_t)T * H * sizeof(float), st));
+  // ---- CE backward, chunked over rows
+  CeArgs c = ce_args(s);
+  int chunk = 0;
+  for (int r0 = 0; r0 < Mcap; r0 += s->dl_rows, ++chunk) {
+    const int rc = (Mcap - r0) < s->dl_rows ? (Mcap - r0) : s->dl_rows;
+    c.row_begin = r0; c.row_count = rc;
+    CK(launch_ce_dlogits(c, st));
+    CK(launch_colsum_bf16(s->dlogits, s->Vp, rc, V, s->counts + 1, r0, s->p_vbias, s->vb_splits, st));
+    CK(launch_grad_reduce(s->d_vb_jobs + (chunk > 0 ? 1 : 0), 1, V, st));
+    GemmArgs g{};
+    g.A = s->dlogits; g.lda = s->Vp; g.B = W + oE; g.ldb = H; g.b_trans = true; g.M = rc; g.N = H; g.K = s->Vp;
+    g.a_kmax = s->Vp; g.b_kmax = V; g.d_M = s->counts + 1; g.d_M_off = r0; g.splits = s->dt_splits;
+    g.out_f32 = s->dt_part + (size_t)r0 * H; g.ld_f32 = H; g.split_stride = (size_t)Mcap * H;
+    CK(launch_gemm(EPI_F32_PARTIAL, g, st));
+    WgradArgs w{};
+    w.X = s->dlogits; w.ldx = s->Vp; w.dY = s->t + (size_t)r0 * H; w.ldy = H; w.M = V; w.N = H; w.T = rc;
+    w.d_T = s->counts + 1; w.d_T_off = r0; w.splits = 1; w.out = G + oE; w.ld_out = H; w.accumulate = 1; w.x_mmax = s->Vp;
+    CK(launch_wgrad(w, st));
+    s->launches += 5;
+  }
+  // ---- MLM transform backward
+  CK(launch_head_bwd_rows(s->dt_part, s->dt_splits, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
+                          P + s->lay.find("head/ln/gamma"), s->d_tpre, s->p_head_ln, Mcap, s->counts, H, st));
+  const bf16* xL = s->layers.back().out;
+  {
+    WgradArgs w{};
+    w.X = xL; w.ldx = H; w.x_rows = s->rows; w.dY = s->d_tpre; w.ldy = H; w.M = H; w.N = H; w.T = Mcap;
+    w.d_T = s->counts + 1; w.splits = s->s_wt; w.out = s->p_wt; w.split_stride = (size_t)H * H; w.ld_out = H;
+    CK(launch_wgrad(w, st));
+    GemmArgs g{};
+    g.A = s->d_tpre; g.lda = H; g.B = W + s->lay.find("head/wt"); g.ldb = H; g.b_trans = false; g.M = Mcap; g.N = H; g.K = H;
+    g.d_M = s->counts;  // n_valid only: aux rows carry no gradient and may alias position 0 of a valid slot
+    g.out_f32 = s->dxa; g.ld_f32 = H; g.scatter_rows = s->rows;
+    CK(launch_gemm(EPI_SCATTER_F32, g, st));
+    s->launches += 3;
+  }
+  // ---- encoder layers, last to first.  d_out lives in dxa at the top of every iteration.
+  for (int l = s->cfg.num_layers - 1; l >= 0; --l) {
+    LayerBuf& L = s->layers[l];
+    const bf16* x_in = l == 0 ? s->x0 : s->layers[l - 1].out;
+    CK(launch_ln_bwd(s->dxa, L.o_pre, L.mean2, L.rstd2, P + L.g2, s->dxb, s->d_branch, L.p_ln2, T, H, od, seed,
+                     site_id(SITE_FFN_OUT, l), step, st));
+    {
+      WgradArgs w{};
+      w.X = L.h; w.ldx = I; w.dY = s->d_branch; w.ldy = H; w.M = I; w.N = H; w.T = T; w.splits = L.s_w2;
+      w.out = L.p_w2; w.split_stride = (size_t)I * H; w.ld_out = H;
+      CK(launch_wgrad(w, st));
+    }
+    {
+      GemmArgs g{};
+      g.A = s->d_branch; g.lda = H; g.B = W + L.w2; g.ldb = H; g.b_trans = false; g.M = T; g.N = I; g.K = H;
+      g.aux_bf16 = L.h_pre; g.ld_aux = I; g.out_bf16 = s->dh; g.ld_out = I; g.colsum_part = L.p_b1;
+      CK(launch_gemm(EPI_GELU_GRAD, g, st));
+    }
+    {
+      WgradArgs w{};
+      w.X = L.y; w.ldx = H; w.dY = s->dh; w.ldy = I; w.M = H; w.N = I; w.T = T; w.splits = L.s_w1;
+      w.out = L.p_w1; w.split_stride = (size_t)H * I; w.ld_out = I;
+      CK(launch_wgrad(w, st));
+    }
+    {
+      GemmArgs g{};
+      g.A = s->dh; g.lda = I; g.B = W + L.w1; g.ldb = I; g.b_trans = false; g.M = T; g.N = H; g.K = I;
+      g.res_f32 = s->dxb; g.out_f32 = s->dxa; g.ld_f32 = H;
+      CK(launch_gemm(EPI_F32_RES, g, st));
+    }
+    CK(launch_ln_bwd(s->dxa, L.a_pre, L.mean1, L.rstd1, P + L.g1, s->dxb, s->d_branch, L.p_ln1, T, H, od, seed,
+                     site_id(SITE_ATTN_OUT, l), step, st));
+    {
+      WgradArgs w{};
+      w.X = L.ctx; w.ldx = H; w.dY = s->d_branch; w.ldy = H; w.M = H; w.N = H; w.T = T; w.splits = L.s_wo;
+      w.out = L.p_wo; w.split_stride = (size_t)H * H; w.ld_out = H;
+      CK(launch_wgrad(w, st));
+    }
+    {
+      GemmArgs g{};
+      g.A = s->d_branch; g.lda = H; g.B = W + L.wo; g.ldb = H; g.b_trans = false; g.M = T; g.N = H; g.K = H;
+      g.out_bf16 = s->dctx; g.ld_out = H;
+      CK(launch_gemm(EPI_BF16, g, st));
+    }
+    {
+      AttnArgs a{};
+      a.qkv = L.qkv; a.mask = s->mask; a.ctx = L.ctx; a.lse = L.lse; a.keep_bits = L.keep; a.B = s->B; a.S = s->S; a.H = H; a.N = s->N;
+      a.drop_rate = s->cfg.attention_dropout; a.dctx = s->dctx; a.dqkv = s->dqkv;
+      CK(launch_attn_bwd(a, st));
+    }
+    CK(launch_colsum_bf16(s->dqkv, 3 * H, T, 3 * H, nullptr, 0, L.p_bqkv, 8, st));
+    {
+      WgradArgs w{};
+      w.X = x_in; w.ldx = H; w.dY = s->dqkv; w.ldy = 3 * H; w.M = H; w.N = 3 * H; w.T = T; w.splits = L.s_wqkv;
+      w.out = L.p_wqkv; w.split_stride = (size_t)H * 3 * H; w.ld_out = 3 * H;
+      CK(launch_wgrad(w, st));
+    }
+    {
+      GemmArgs g{};
+      g.A = s->dqkv; g.lda = 3 * H; g.B = W + L.wqkv; g.ldb = 3 * H; g.b_trans = false; g.M = T; g.N = H; g.K = 3 * H;
+      g.res_f32 = s->dxb; g.out_f32 = s->dxa; g.ld_f32 = H;
+      CK(launch_gemm(EPI_F32_RES, g, st));
+    }
+    s->launches += 12;
+  }
+  CK(launch_embed_bwd(s->ids, W + oE, W + s->lay.find("position_embedding"), P + s->lay.find("emb_ln/gamma"), s->dxa,
+                      G + oE, s->p_dpos, s->p_embln, s->B, s->S, H, V, od, seed, step, s->emb_bsplits, st));
+  CK(launch_grad_reduce(s->d_jobs, s->n_jobs, s->jobs_max_len, st));
+  s->launches += 2;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ pooler
+__global__ void pooler_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                              float* __restrict__ out, int B, int S, int H) {
+  const int bi = blockIdx.x;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    float acc = b[j];
+    for (int k = 0; k < H; ++k) acc += __bfloat162float(x[(size_t)bi * S * H + k]) * w[(size_t)k * H + j];
+    out[(size_t)bi * H + j] = tanhf(acc);
+  }
+}
+extern "C" int b4r_pooled_output(b4r_session* s, float* out, void* stream) {
+  if (!s || !out) return fail("null argument");
+  pooler_kernel<<<s->B, 128, 0, (cudaStream_t)stream>>>(s->layers.back().out, s->params + s->lay.find("pooler/w"),
+                                                       s->params + s->lay.find("pooler/b"), out, s->B, s->S, s->H);
+  CK(cudaGetLastError());
+  s->launches++;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ optimizer
+static const int kSqParts = 296;
+extern "C" size_t b4r_adamw_scratch_floats(void) { return kSqParts; }
+extern "C" int b4r_adamw_step(float* params, void* shadow_bf16, const float* grads, float* m, float* v, int64_t n_decay,
+                              int64_t n_trainable, const b4r_adamw_hparams* hp, const float* count, float grad_scale,
+                              int64_t* step_counter, float* scratch, float* lr_out, void* stream) {
+  if (!params || !shadow_bf16 || !grads || !m || !v || !hp || !step_counter || !scratch) return fail("null argument");
+  if ((n_decay & 7) || (n_trainable & 7)) return fail("segment sizes must be multiples of 8");
+  AdamWArgs a{};
+  a.p = params; a.shadow = reinterpret_cast<bf16*>(shadow_bf16); a.g = grads; a.m = m; a.v = v;
+  a.n_decay = n_decay; a.n = n_trainable; a.sq_part = scratch; a.n_sq_part = kSqParts; a.d_count = count; a.grad_scale = grad_scale;
+  a.d_step = reinterpret_cast<const long long*>(step_counter); a.d_step_out = reinterpret_cast<long long*>(step_counter);
+  a.init_lr = hp->init_lr; a.end_lr = hp->end_lr; a.num_train_steps = hp->num_train_steps; a.num_warmup_steps = hp->num_warmup_steps;
+  a.wd = hp->weight_decay_rate; a.beta1 = hp->beta_1; a.beta2 = hp->beta_2; a.eps = hp->epsilon; a.clip = hp->clip_norm;
+  a.d_lr_out = lr_out;
+  CK(launch_adamw(a, (cudaStream_t)stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ ranking
+extern "C" int b4r_rank_candidates(b4r_session* s, const int64_t* cand, const int64_t* gt, int n_slots, int C,
+                                   int64_t* ranking_out, float* scores_out, int32_t* rank_out, uint64_t* hist,
+                                   void* stream) {
+  if (!s || !cand) return fail("null argument");
+  if (C < 1 || C > 2048) return fail("candidate count %d unsupported (1..2048)", C);
+  if (n_slots > s->Mcap) return fail("n_slots %d exceeds session capacity %d", n_slots, s->Mcap);
+  CK(launch_rank_candidates(s->t, s->H, s->shadow + s->lay.find("word_embeddings"), s->params + s->lay.find("head/output_bias"),
+                            cand, gt, n_slots, C, s->H, reinterpret_cast<int64_t*>(ranking_out), scores_out, rank_out,
+                            reinterpret_cast<unsigned long long*>(hist), (cudaStream_t)stream));
+  s->launches++;
+  return 0;
+}
+
+extern "C" int b4r_rank_full(b4r_session* s, int v_begin, int v_end, int32_t* beat_out, void* stream) {
+  if (!s || !beat_out) return fail("null argument");
+  if (v_begin < 0 || v_end > s->V || v_begin >= v_end) return fail("bad vocabulary shard [%d, %d)", v_begin, v_end);
+  // ground-truth scores: label logit of the fused CE pass over the FULL vocabulary (b4r_mlm_loss must have run)
+  CeArgs c = ce_args(s);
+  c.v_begin = v_begin; c.v_end = v_end;
+  CK(launch_ce_count(c, s->lab, beat_out, (cudaStream_t)stream));
+  s->launches++;
+  return 0;
+}
+
+extern "C" int b4r_metrics_from_hist(const uint64_t* hist, int max_rank, const int32_t* ks, int nk, double* out, void* stream) {
+  if (!hist || !ks || !out || nk < 0 || nk > 16) return fail("bad argument");
+  CK(launch_metrics_from_hist(reinterpret_cast<const unsigned long long*>(hist), max_rank, ks, nk, out, (cudaStream_t)stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ introspection
+extern "C" const void* b4r_sequence_output(b4r_session* s, int layer) {
+  if (!s) return nullptr;
+  int L = s->cfg.num_layers;
+  if (layer < 0) layer += L;
+  if (layer < 0 || layer >= L) return nullptr;
+  return s->layers[layer].out;
+}
+extern "C" const void* b4r_mlm_hidden(b4r_session* s) { return s ? s->t : nullptr; }
+extern "C" const int32_t* b4r_mlm_counts(b4r_session* s) { return s ? s->counts : nullptr; }
+extern "C" const int32_t* b4r_mlm_rows(b4r_session* s) { return s ? s->rows : nullptr; }
+extern "C" float* b4r_stats(b4r_session* s) { return s ? s->stats : nullptr; }
+extern "C" float* b4r_step_stats(b4r_session* s) { return s ? s->step_stats : nullptr; }
+extern "C" const uint64_t* b4r_attn_keep_bits(b4r_session* s, int layer, int* words_per_row) {
+  if (!s || layer < 0 || layer >= s->cfg.num_layers) return nullptr;
+  if (words_per_row) *words_per_row = attn_mask_words(s->S);
+  return s->layers[layer].keep;
+}
+extern "C" int b4r_launch_count(b4r_session* s) { return s ? s->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ test helpers
+extern "C" int b4r_dropout_keep_mask(uint8_t* out, int rows, int cols, float rate, uint64_t seed, int site, int layer,
+                                     uint32_t step, void* stream) {
+  if (!out) return fail("null argument");
+  CK(launch_dropout_mask_dump(out, rows, cols, rate, seed, site_id((uint32_t)site, (uint32_t)layer), step, (cudaStream_t)stream));
+  return 0;
+}
+extern "C" int b4r_embed_ln_fwd(const int64_t* ids, const void* table, const void* pos, const float* gamma, const float* beta,
+                                void* out, int batch, int seq_len, int hidden, int vocab, void* stream) {
+  if (!ids || !table || !pos || !gamma || !beta || !out) return fail("null argument");
+  CK(launch_embed_ln_fwd(ids, (const bf16*)table, (const bf16*)pos, gamma, beta, (bf16*)out, batch, seq_len, hidden, vocab,
+                         0.f, 0, 0, (cudaStream_t)stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ DLPack adapter
+namespace {
+struct DLDevice_ { int32_t device_type; int32_t device_id; };
+struct DLDataType_ { uint8_t code; uint8_t bits; uint16_t lanes; };
+struct DLTensor_ { void* data; DLDevice_ device; int32_t ndim; DLDataType_ dtype; int64_t* shape; int64_t* strides; uint64_t byte_offset; };
+struct DLManagedTensor_ { DLTensor_ dl_tensor; void* manager_ctx; void (*deleter)(DLManagedTensor_*); };
+}  // namespace
+extern "C" int b4r_dl_view_of(const void* dl_managed_tensor, b4r_dl_view* out) {
+  if (!dl_managed_tensor || !out) return fail("null argument");
+  const DLTensor_& t = reinterpret_cast<const DLManagedTensor_*>(dl_managed_tensor)->dl_tensor;
+  if (t.device.device_type != 2 /* kDLCUDA */) return fail("tensor is not on a CUDA device (device_type %d)", t.device.device_type);
+  if (t.ndim < 0 || t.ndim > 4) return fail("ndim %d unsupported", t.ndim);
+  if (t.dtype.lanes != 1) return fail("vector dtypes unsupported");
+  int64_t expect = 1;
+  for (int i = t.ndim - 1; i >= 0; --i) {
+    if (t.strides && t.shape[i] > 1 && t.strides[i] != expect) return fail("tensor is not contiguous row-major");
+    expect *= t.shape[i];
+  }
+  out->data = reinterpret_cast<char*>(t.data) + t.byte_offset;
+  out->device_type = t.device.device_type; out->device_id = t.device.device_id; out->ndim = t.ndim;
+  out->dtype_code = t.dtype.code; out->dtype_bits = t.dtype.bits;
+  for (int i = 0; i < 4; ++i) out->shape[i] = i < t.ndim ? t.shape[i] : 1;
+  return 0;
+}

@@ -1,0 +1,188 @@
+// Host-callable launchers for every kernel of the path.  Raw device pointers, explicit stream, no allocation,
+// no hidden synchronisation.  All launchers return cudaError_t from the launch (cudaGetLastError()).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b4r {
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------ generic GEMM (k_gemm.cu)
+enum Epi : int {
+  EPI_BIAS_BF16 = 0,   // out_bf16 = acc + bias
+  EPI_BIAS_GELU = 1,   // out_bf16 = acc + bias (pre-activation) ; out2_bf16 = gelu(pre)
+  EPI_GELU_GRAD = 2,   // out_bf16 = acc * gelu'(aux_bf16) ; per-CTA column sums -> colsum_part[mtile][N]
+  EPI_BF16 = 3,        // out_bf16 = acc
+  EPI_F32_RES = 4,     // out_f32 = acc + res_f32
+  EPI_SCATTER_F32 = 5, // out_f32[scatter_rows[m]] = acc
+  EPI_F32_PARTIAL = 6, // out_f32[split][m][n] = acc   (split-K partials)
+  EPI_BIAS_F32 = 7,    // out_f32 = acc + bias          (materialised logits for the API / tests)
+};
+
+struct GemmArgs {
+  // operands (see gemm.cuh)
+  const bf16* A; int lda; const int* a_rows; bool a_trans;
+  const bf16* B; int ldb; bool b_trans;
+  int M, N, K;            // logical problem; K is the loop bound (multiple of 8)
+  int a_kmax, b_kmax;     // valid k extents of each operand (<= K); 0 -> K
+  const int* d_M;         // optional device-side dynamic row count (rows >= *d_M - d_M_off are skipped)
+  int d_M_off;
+  int splits;             // split-K factor (EPI_F32_PARTIAL only), >= 1
+  // epilogue
+  const float* bias;
+  bf16* out_bf16; int ld_out;
+  bf16* out2_bf16;
+  const bf16* aux_bf16; int ld_aux;
+  float* out_f32; int ld_f32;
+  const float* res_f32;
+  const int* scatter_rows;
+  float* colsum_part;     // [ceil(M/BM)][N]
+  size_t split_stride;
+};
+cudaError_t launch_gemm(int epi, const GemmArgs& a, cudaStream_t st);
+int gemm_block_m();  // BM of the generic kernel (for sizing colsum_part)
+
+// GEMM with a full-row epilogue (N == H in {64,128,256}), k_gemm.cu
+enum RowMode : int {
+  ROW_RES_DROP_LN = 0,  // v = drop(acc+bias) + residual ; pre=v ; y = LN(v)
+  ROW_GELU_LN = 1,      // pre = acc+bias ; act = gelu(pre) ; y = LN(act)
+};
+struct RowLnArgs {
+  const bf16* A; int lda; const int* a_rows;   // A [M][K] (optionally row-gathered)
+  const bf16* W;                               // [K][H] row-major (TF kernel layout)
+  int M, K, H;
+  const int* d_M;
+  const float* bias; const float* gamma; const float* beta;
+  const bf16* residual;                        // [M][H] (ROW_RES_DROP_LN)
+  bf16* pre;                                   // [M][H] pre-LN value (RES mode) / pre-activation (GELU mode)
+  bf16* act;                                   // [M][H] gelu(pre) (GELU mode only)
+  bf16* y;                                     // [M][H] LN output
+  float* mean; float* rstd;                    // [M]
+  // dropout
+  float drop_rate; uint64_t seed; uint32_t site; uint32_t step;
+};
+cudaError_t launch_gemm_rowln(int mode, const RowLnArgs& a, cudaStream_t st);
+
+// Weight-gradient GEMM: out[split][M][N] = sum_{t in split} X[t][m] * dY[t][n]   (both operands "transposed")
+struct WgradArgs {
+  const bf16* X; int ldx; const int* x_rows;   // [T][M] (rows optionally gathered)
+  const bf16* dY; int ldy;                     // [T][N]
+  int M, N, T;
+  const int* d_T; int d_T_off;                 // optional dynamic contraction length: min(T, *d_T - d_T_off)
+  int splits;
+  float* out; size_t split_stride;             // partials (accumulate==0) or final (splits==1, accumulate==1: out += )
+  int ld_out; int accumulate;
+  int x_mmax;                                  // valid columns of X (multiple of 8; defaults to M rounded up)
+};
+cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t st);
+
+// ------------------------------------------------------------------ embedding (k_embed.cu)
+cudaError_t launch_embed_ln_fwd(const int64_t* ids, const bf16* table, const bf16* pos, const float* gamma,
+                                const float* beta, bf16* out, int B, int S, int H, int V, float drop_rate,
+                                uint64_t seed, uint32_t step, cudaStream_t st);
+// d_out fp32 [T][H] -> dE (atomic scatter-add into grad_table fp32 [V][H]), dpos partials [bsplits][S*H],
+// dgamma/dbeta partials [nparts][2H]
+cudaError_t launch_embed_bwd(const int64_t* ids, const bf16* table, const bf16* pos, const float* gamma,
+                             const float* d_out, float* grad_table, float* dpos_part, float* dln_part, int B, int S,
+                             int H, int V, float drop_rate, uint64_t seed, uint32_t step, int bsplits,
+                             cudaStream_t st);
+int embed_bwd_bsplits(int B);
+
+// ------------------------------------------------------------------ attention (k_attn.cu)
+struct AttnArgs {
+  const bf16* qkv;        // [B*S][3H]  (q | k | v), head n occupies columns n*D..n*D+D-1 of each part
+  const int64_t* mask;    // [B][S] input_mask (1 = valid key)
+  bf16* ctx;              // [B*S][H]
+  float* lse;             // [B][N][S]
+  uint64_t* keep_bits;    // [B][N][S][words] dropout keep bits (training only)
+  int B, S, H, N;
+  float drop_rate; uint64_t seed; uint32_t site; uint32_t step;
+  // backward
+  const bf16* dctx;       // [B*S][H]
+  bf16* dqkv;             // [B*S][3H]
+};
+cudaError_t launch_attn_fwd(const AttnArgs& a, cudaStream_t st);
+cudaError_t launch_attn_bwd(const AttnArgs& a, cudaStream_t st);
+int attn_mask_words(int S);
+
+// ------------------------------------------------------------------ row kernels (k_rows.cu)
+// LayerNorm backward over rows (+ dropout of the branch gradient):
+//   d_pre = LNbwd(d_out) ; d_branch = drop(d_pre) (bf16) ; partials[cta] = {dgamma[H], dbeta[H], dbranch_colsum[H]}
+cudaError_t launch_ln_bwd(const float* d_out, const bf16* pre, const float* mean, const float* rstd,
+                          const float* gamma, float* d_pre, bf16* d_branch, float* partials, int M, int H,
+                          float drop_rate, uint64_t seed, uint32_t site, uint32_t step, cudaStream_t st);
+int ln_bwd_parts(int M);
+
+struct ReduceJob { const float* src; float* dst; int nparts; int len; long long part_stride; int accumulate; };
+cudaError_t launch_grad_reduce(const ReduceJob* d_jobs, int njobs, int max_len, cudaStream_t st);
+
+// squared L2 norm partials of g[0..n) -> out_part[nblocks] ; deterministic two-stage
+cudaError_t launch_sqnorm(const float* g, long long n, float* out_part, int nblocks, cudaStream_t st);
+struct AdamWArgs {
+  float* p; bf16* shadow; const float* g; float* m; float* v;
+  long long n_decay, n;        // [0,n_decay) decayed, [n_decay,n) not decayed
+  const float* sq_part; int n_sq_part;   // squared-norm partials of g (before scaling)
+  const float* d_count;        // optional device scalar: gradient is divided by max(*d_count,1) (loss normaliser)
+  float grad_scale;            // extra host-side scale (e.g. 1/world_size)
+  const long long* d_step;     // device step counter (optimizer.iterations) ; incremented by the kernel's last block
+  long long* d_step_out;
+  float init_lr, end_lr; long long num_train_steps, num_warmup_steps;
+  float wd, beta1, beta2, eps, clip;
+  float* d_lr_out;             // optional: lr used, global norm (2 floats)
+};
+cudaError_t launch_adamw(const AdamWArgs& a, cudaStream_t st);
+cudaError_t launch_colsum_bf16(const bf16* src, int ld, int M, int N, const int* d_M, int d_M_off, float* part,
+                               int splits, cudaStream_t st);
+cudaError_t launch_cast_bf16(const float* src, bf16* dst, long long n, cudaStream_t st);
+
+// ------------------------------------------------------------------ MLM head + CE (k_ce.cu)
+// Compact the valid masked slots: rows[m] = b*S + pos, labels[m]; then one aux row per sequence that has padded
+// slots (label 0, weight 0, mult = #padded slots) for SparseCategoricalAccuracy parity.
+// counts = {n_valid, n_rows_total}
+cudaError_t launch_mlm_select(const int64_t* positions, const int64_t* ids, const int64_t* weights, int use_weights,
+                              int B, int S, int P, int want_aux, int* rows, int* labels, float* row_w, int* row_mult,
+                              int* counts, cudaStream_t st);
+struct CeArgs {
+  const bf16* t; int ldt;            // [M][H] transformed hidden rows
+  const bf16* E;                     // [V][H] tied table (bf16 shadow)
+  const float* vbias;                // [V]
+  const int* labels; const float* row_w; const int* row_mult;
+  const int* d_counts;               // {n_valid, n_rows}
+  int M_cap, H, V;
+  int v_begin, v_end;                // vocabulary shard handled here (whole vocab: 0, V)
+  int vsplits;
+  float* part;                       // [vsplits][M_cap][6] partial (max, sum, label_logit, best_val, best_idx, unused)
+  float* lse;                        // [M_cap]
+  float* lab_out;                    // optional [M_cap]: logit of the label column (ground-truth score)
+  float* stats;                      // accumulators: {loss_sum, n_valid, n_correct_masked, n_correct_all, n_all}
+  float* step_stats;                 // this step only (same layout)
+  // backward
+  bf16* dlogits; int ld_dl;          // [rows_chunk][Vp]
+  int row_begin, row_count;          // chunk of rows for dlogits
+};
+cudaError_t launch_ce_fwd(const CeArgs& a, cudaStream_t st);
+cudaError_t launch_ce_finalize(const CeArgs& a, cudaStream_t st);
+cudaError_t launch_ce_dlogits(const CeArgs& a, cudaStream_t st);
+// full-catalogue rank counting (see k_ce.cu): beat[m] += #items of the shard that rank ahead of the ground truth
+cudaError_t launch_ce_count(const CeArgs& a, const float* s_gt, int* beat, cudaStream_t st);
+int ce_block_m();
+// MLM transform backward over rows: dt = sum_s dt_part[s] ; LN bwd ; gelu bwd -> d_tpre (bf16) ; partials {dgamma,dbeta,dbias}
+cudaError_t launch_head_bwd_rows(const float* dt_part, int nsplit, size_t split_stride, const bf16* t_pre,
+                                 const bf16* act, const float* mean, const float* rstd, const float* gamma,
+                                 bf16* d_tpre, float* partials, int M_cap, const int* d_counts, int H,
+                                 cudaStream_t st);
+
+// ------------------------------------------------------------------ ranking (k_rank.cu)
+// scores[m][c] = t[m] . E[cand[m][c]] + vbias[cand[m][c]] ; ranking = stable descending order (lower index first on ties)
+// rank[m] = 1 + position of the first candidate equal to gt[m] ; hist[r] += 1
+cudaError_t launch_rank_candidates(const bf16* t, int ldt, const bf16* E, const float* vbias, const int64_t* cand,
+                                   const int64_t* gt, int M, int C, int H, int64_t* ranking, float* scores,
+                                   int* rank, unsigned long long* hist, cudaStream_t st);
+// metric sums from a rank histogram: out = {n, ndcg@k.., hr@k.., map} in fp64
+cudaError_t launch_metrics_from_hist(const unsigned long long* hist, int max_rank, const int* ks, int nk,
+                                     double* out, cudaStream_t st);
+// keep-mask dump for tests: out[r][c] = keep ? 1 : 0 for the elementwise dropout sites
+cudaError_t launch_dropout_mask_dump(uint8_t* out, int rows, int cols, float rate, uint64_t seed, uint32_t site,
+                                     uint32_t step, cudaStream_t st);
+}  // namespace b4r

@@ -1,0 +1,128 @@
+/* libb4r -- C ABI of the B200-native BERT4Rec train + ranking path.
+ *
+ * The reference (maneymarkus/BERT4Rec) is pure Python over TensorFlow and has no FFI seam of its own; the boundary
+ * below is the set of entry points its Python classes would bind for this path.  Each entry cites the reference
+ * interface it replaces.  Conventions:
+ *   - every function returns 0 on success, non-zero on error; b4r_last_error() (thread-local) describes the failure;
+ *   - all pointers are plain device pointers (cudaMalloc'ed memory, e.g. a torch tensor's data_ptr) unless the name
+ *     says host; no torch / DLPack types cross the boundary except in b4r_dl_view (the optional DLPack adapter);
+ *   - every compute call takes a cudaStream_t (as void*) and only ENQUEUES work: no allocation, no hidden sync;
+ *   - integer model inputs are int64, row-major, exactly the reference's batch dict (bert4rec_model.py:15-22).
+ */
+#ifndef B4R_H_
+#define B4R_H_
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B4R_VERSION 100
+
+/* Bert4RecEncoder(vocab_size, hidden_size, num_layers, num_attention_heads, max_sequence_length, inner_dim,
+ * output_dropout, attention_dropout) -- bert4rec_encoder.py:62-80 (post-LN, exact-erf GELU, LN eps 1e-12). */
+typedef struct b4r_config {
+  int32_t vocab_size, hidden_size, num_layers, num_heads, max_seq_len, inner_dim;
+  float output_dropout, attention_dropout;
+} b4r_config;
+
+typedef struct b4r_param_entry {
+  char name[48];      /* internal segment name, e.g. "word_embeddings", "layer_0/wqkv" */
+  int64_t offset;     /* element offset inside the flat parameter buffer */
+  int64_t numel;
+  int32_t rows, cols; /* 2-D view (cols == 0 for vectors) */
+  int32_t group;      /* 0 = weight-decayed, 1 = not decayed (bias / LayerNorm), 2 = frozen (pooler: no gradient) */
+} b4r_param_entry;
+
+typedef struct b4r_adamw_hparams {  /* optimizers.create_adam_w_optimizer defaults, optimizers/__init__.py:7-15 */
+  float init_lr, end_lr;
+  int64_t num_train_steps, num_warmup_steps;
+  float weight_decay_rate, beta_1, beta_2, epsilon, clip_norm;
+} b4r_adamw_hparams;
+
+typedef struct b4r_session b4r_session;
+
+/* ---- library / device ---------------------------------------------------------------------------------- */
+int b4r_version(void);
+const char* b4r_last_error(void);
+int b4r_device_check(int device);   /* fails unless the device is sm_100 (B200) */
+
+/* ---- flat parameter layout (replaces keras variable creation, bert4rec_encoder.py:102-153, bert4rec_model.py:76-81) */
+int b4r_param_entries(const b4r_config* cfg, b4r_param_entry* out, int cap);          /* returns #entries (or <0) */
+int b4r_param_counts(const b4r_config* cfg, int64_t* n_decay, int64_t* n_trainable, int64_t* n_total);
+
+/* ---- session: static shapes (batch, seq_len, max_predictions_per_seq) + caller-owned buffers ------------ */
+size_t b4r_session_workspace_bytes(const b4r_config* cfg, int batch, int seq_len, int max_pred);
+int b4r_session_create(const b4r_config* cfg, int batch, int seq_len, int max_pred, float* params, void* shadow_bf16,
+                       float* grads, void* workspace, size_t workspace_bytes, b4r_session** out);
+void b4r_session_destroy(b4r_session* s);
+int b4r_sync_shadow(b4r_session* s, void* stream);   /* shadow_bf16 = bf16(params) after a host-side weight load */
+
+/* Bert4RecEncoder.call, bert4rec_encoder.py:186-231.  ids/mask: int64 [batch, seq_len]. */
+int b4r_encode(b4r_session* s, const int64_t* input_word_ids, const int64_t* input_mask, int training, uint64_t seed,
+               uint32_t step, void* stream);
+/* tfm MaskedLM._gather_indexes (bert4rec_model.py:141-143) + tf.boolean_mask of the loss (trainer_utils.py:19-20).
+ * mode 0: slots with masked_lm_ids != 0 (training); 1: slots with masked_lm_weights != 0 (rank_items,
+ * bert4rec_model.py:218-220); 2: all batch*max_pred slots (BERT4RecModel.call). want_aux adds one row per sequence
+ * with padded slots so that SparseCategoricalAccuracy over ALL slots stays exact. */
+int b4r_mlm_select(b4r_session* s, const int64_t* masked_lm_positions, const int64_t* masked_lm_ids,
+                   const int64_t* masked_lm_weights, int mode, int want_aux, void* stream);
+/* MaskedLM transform (dense+gelu+LayerNorm) on the selected rows. */
+int b4r_mlm_transform(b4r_session* s, void* stream);
+/* tied projection x online-softmax CE + accuracies (trainer_utils.py:12-23,49-60). Accumulates into stats. */
+int b4r_mlm_loss(b4r_session* s, void* stream);
+/* materialised logits [n_rows, vocab] fp32 for BERT4RecModel.call()'s "mlm_logits" (bert4rec_model.py:139-147) */
+int b4r_mlm_logits(b4r_session* s, float* out, void* stream);
+/* tape.gradient of the SUM loss over all trainable variables (bert4rec_model.py:166-167) -> grads (flat, fp32). */
+int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, void* stream);
+/* tanh pooler on token 0 (bert4rec_encoder.py:224-226) -> out fp32 [batch, hidden] */
+int b4r_pooled_output(b4r_session* s, float* out, void* stream);
+
+/* AdamWeightDecay.apply_gradients (adam_w_optimizer.py:100-136): clip_by_global_norm, WarmUp/PolynomialDecay lr,
+ * decoupled decay, Adam; also refreshes shadow_bf16.  The gradient is first multiplied by grad_scale / max(*count,1)
+ * (count = number of valid masked slots, the loss normaliser of trainer_utils.py:22).  step_counter: device int64
+ * (optimizer.iterations), incremented by the call.  lr_out (optional): device float[2] = {lr, global_norm}. */
+size_t b4r_adamw_scratch_floats(void);
+int b4r_adamw_step(float* params, void* shadow_bf16, const float* grads, float* m, float* v, int64_t n_decay,
+                   int64_t n_trainable, const b4r_adamw_hparams* hp, const float* count, float grad_scale,
+                   int64_t* step_counter, float* scratch, float* lr_out, void* stream);
+
+/* BERT4RecModel.rank_items with per-slot candidate lists (bert4rec_model.py:224-234) + rank lookup
+ * (bert4rec_evaluator.py:112-117).  cand: int64 [n_slots, C]; gt: int64 [n_slots] or NULL.
+ * ranking_out int64 [n_slots, C] (optional), scores_out fp32 [n_slots, C] (optional), rank_out int32 [n_slots]
+ * (1-based, 0 if gt absent), hist: uint64 [C+1] rank histogram, accumulated (optional). */
+int b4r_rank_candidates(b4r_session* s, const int64_t* cand, const int64_t* gt, int n_slots, int C,
+                        int64_t* ranking_out, float* scores_out, int32_t* rank_out, uint64_t* hist, void* stream);
+/* rank_items(items=None) for evaluation: 1-based rank of the label of every selected row over the vocabulary shard
+ * [v_begin, v_end): beat_out[i] += #items ranking ahead (caller zeroes; sum over shards + 1 = rank). */
+int b4r_rank_full(b4r_session* s, int v_begin, int v_end, int32_t* beat_out, void* stream);
+/* HR@k / NDCG@k / MAP from a rank histogram (evaluation_metrics.py:47-112): out fp64 [2 + 2*nk] =
+ * {n, NDCG@k..., HR@k..., MAP}; ks: device int32 [nk]. */
+int b4r_metrics_from_hist(const uint64_t* hist, int max_rank, const int32_t* ks, int nk, double* out, void* stream);
+
+/* ---- introspection (device pointers into the workspace; valid for the session lifetime) ------------------ */
+const void* b4r_sequence_output(b4r_session* s, int layer);  /* bf16 [batch*seq_len, hidden]; layer -1 = last */
+const void* b4r_mlm_hidden(b4r_session* s);                  /* bf16 [n_rows, hidden] transformed rows */
+const int32_t* b4r_mlm_counts(b4r_session* s);               /* int32[2] = {n_valid, n_rows} */
+const int32_t* b4r_mlm_rows(b4r_session* s);                 /* int32 [n_rows] flat row index b*seq_len+pos */
+float* b4r_stats(b4r_session* s);       /* float[8] running {loss_sum, n_valid, correct_masked, correct_all, n_all} */
+float* b4r_step_stats(b4r_session* s);  /* float[8] same, last step only */
+const uint64_t* b4r_attn_keep_bits(b4r_session* s, int layer, int* words_per_row);
+int b4r_launch_count(b4r_session* s);   /* kernels launched through this session so far */
+
+/* ---- test helpers ------------------------------------------------------------------------------------------ */
+/* keep mask (1 byte / element) of an elementwise dropout site: site 1 = embedding, 2 = attention output, 3 = FFN output */
+int b4r_dropout_keep_mask(uint8_t* out, int rows, int cols, float rate, uint64_t seed, int site, int layer, uint32_t step,
+                          void* stream);
+/* standalone kernels for unit parity tests */
+int b4r_embed_ln_fwd(const int64_t* ids, const void* table_bf16, const void* pos_bf16, const float* gamma,
+                     const float* beta, void* out_bf16, int batch, int seq_len, int hidden, int vocab, void* stream);
+
+/* ---- optional DLPack adapter: validates a (borrowed) DLManagedTensor and returns its device pointer ---------- */
+typedef struct b4r_dl_view { void* data; int32_t device_type, device_id, ndim, dtype_code, dtype_bits; int64_t shape[4]; } b4r_dl_view;
+int b4r_dl_view_of(const void* dl_managed_tensor, b4r_dl_view* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B4R_H_ */
