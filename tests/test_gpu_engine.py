@@ -105,10 +105,219 @@ def test_backward_grads(name):
     n_valid = float(sess.step_stats()[1])
     got = store.grad_dict()
     bad = []
+    gmax = max(float(g.norm()) for g in ref.values())
     for k, g in ref.items():
-        e = rel_l2(got[k] / n_valid, g)
-        if not e < 4e-2:
-            bad.append((k, e, float(g.norm())))
+        # key biases have an exactly-zero true gradient (softmax shift invariance): absolute floor
+        err = float((got[k].double() / n_valid - g.double()).norm())
+        if not err < 4e-2 * float(g.norm()) + 1e-5 * gmax:
+            bad.append((k, err, float(g.norm())))
     assert not bad, f"gradient mismatches (name, rel l2, ref norm): {bad}"
     for k in ("pooler_transform/kernel", "pooler_transform/bias"):
         assert float(got[k].abs().max()) == 0.0
+
+
+def _hp(**kw):
+    from bert4rec_b200 import _lib
+    d = dict(init_lr=1e-4, end_lr=0.0, num_train_steps=400000, num_warmup_steps=100, weight_decay_rate=0.01,
+             beta_1=0.9, beta_2=0.999, epsilon=1e-6, clip_norm=5.0)
+    d.update(kw)
+    return _lib.AdamWHParams(**d), d
+
+
+def test_adamw_matches_oracle():
+    """Fused clip + AdamW(+warm-up/decay) vs the oracle's AdamWeightDecay restatement on random gradients."""
+    from oracle import model as om
+    store, kw, B, S, P = build("h64_s50")
+    store.ensure_training_buffers()
+    hp, d = _hp(init_lr=1e-2, num_warmup_steps=2, num_train_steps=10)
+    params = {k: v.clone() for k, v in store.state_dict().items()}
+    trainable = [k for k in params if not k.startswith("pooler")]
+    opt = om.AdamW({k: params[k] for k in trainable}, init_lr=1e-2, num_train_steps=10, num_warmup_steps=2)
+    g = torch.Generator().manual_seed(9)
+    count = torch.tensor([7.0], device="cuda:0")
+    for it in range(5):
+        grads = {k: torch.randn(params[k].shape, generator=g) * (3.0 if it == 1 else 0.05) for k in trainable}
+        with torch.no_grad():
+            store.grads.zero_()
+            for k, v in store.tf_views(store.grads).items():
+                if k in grads:
+                    v.copy_((grads[k] * 7.0).to(v.device))      # kernel divides by count
+        store.adamw_step(hp, count=count)
+        opt.apply({k: params[k] for k in trainable}, grads)
+        torch.cuda.synchronize()
+        lr_gn = store.lr_out.cpu()
+        assert abs(float(lr_gn[0]) - om.lr_schedule(it, 1e-2, 10, 2)) < 1e-9
+    got = store.state_dict()
+    for k in trainable:
+        assert torch.allclose(got[k], params[k], rtol=2e-5, atol=2e-7), (k, float((got[k] - params[k]).abs().max()))
+    for k in ("pooler_transform/kernel", "pooler_transform/bias"):
+        assert torch.equal(got[k], params[k])
+    # shadow = bf16(params)
+    assert torch.equal(store.shadow.float().cpu()[: store.n_trainable], store.params.cpu()[: store.n_trainable].to(torch.bfloat16).float())
+    assert int(store.step_counter.item()) == 5
+
+
+@pytest.mark.parametrize("name", ["h64_s50", "h256_d64"])
+def test_training_mode_dropout_parity(name):
+    """Training-mode forward/backward with dropout ON: the oracle replays the CUDA path's Philox keep masks."""
+    from oracle import model as om
+    from bert4rec_b200.engine import dropout_keep_mask
+    rate = 0.25
+    store, kw, B, S, P = build(name, dropout=rate)
+    store.ensure_training_buffers()
+    batch = make_batch(B, S, P, kw["vocab_size"], seed=11)
+    cb = to_cuda(batch)
+    seed, step = 1234567, 3
+    sess = store.session(B, S, P)
+    sess.encode(cb["input_word_ids"], cb["input_mask"], training=True, seed=seed, step=step)
+    sess.select(cb["masked_lm_positions"], cb["masked_lm_ids"], cb["masked_lm_weights"], mode=0, want_aux=True)
+    sess.transform(); sess.loss(); sess.backward(seed=seed, step=step)
+    torch.cuda.synchronize()
+    H = kw["hidden_size"]
+    masks = {"emb": dropout_keep_mask(B * S, H, rate, seed, 1, 0, step, "cuda:0").cpu().reshape(B, S, H)}
+    for l in range(kw["num_layers"]):
+        masks[f"l{l}.attn_out"] = dropout_keep_mask(B * S, H, rate, seed, 2, l, step, "cuda:0").cpu().reshape(B, S, H)
+        masks[f"l{l}.ffn_out"] = dropout_keep_mask(B * S, H, rate, seed, 3, l, step, "cuda:0").cpu().reshape(B, S, H)
+        masks[f"l{l}.attn"] = sess.attn_keep_mask(l).cpu()
+    for k, m in masks.items():
+        frac = float(m.float().mean())
+        assert abs(frac - (1 - rate)) < 0.03, (k, frac)
+    sd = {k: v.to(torch.bfloat16).float() if (k.endswith("kernel") or k.endswith("embeddings")) else v
+          for k, v in store.state_dict().items()}
+    cfg = oracle_cfg(kw)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = om.model_forward(leaves, cfg, batch, training=True, keep_masks=masks)
+    y = batch["masked_lm_ids"]
+    loss = om.masked_sparse_ce(y, out["mlm_logits"])
+    st = sess.step_stats().cpu()
+    got_loss = float(st[0] / st[1])
+    assert abs(got_loss - float(loss)) / float(loss) < 2e-3, (got_loss, float(loss))
+    seq = sess.sequence_output().float().cpu()
+    assert (seq - out["sequence_output"].detach()).abs().max().item() < 8e-2
+    names = list(leaves)
+    gs = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    ref = {k: g for k, g in zip(names, gs) if g is not None}
+    got = store.grad_dict()
+    gmax = max(float(g.norm()) for g in ref.values())
+    bad = []
+    for k, g in ref.items():
+        err = float((got[k].double() / float(st[1]) - g.double()).norm())
+        if not err < 5e-2 * float(g.norm()) + 1e-5 * gmax:
+            bad.append((k, err, float(g.norm())))
+    assert not bad, bad
+
+
+def test_backward_deterministic_except_scatter():
+    """Two identical steps give bit-identical gradients for everything that does not go through the
+    floating-point scatter-add (the item table's gather part)."""
+    store, kw, B, S, P = build("h64_s50", dropout=0.1)
+    store.ensure_training_buffers()
+    batch = to_cuda(make_batch(B, S, P, kw["vocab_size"], seed=2))
+    sess = store.session(B, S, P)
+    outs = []
+    for _ in range(2):
+        sess.encode(batch["input_word_ids"], batch["input_mask"], training=True, seed=5, step=1)
+        sess.select(batch["masked_lm_positions"], batch["masked_lm_ids"], batch["masked_lm_weights"], mode=0, want_aux=True)
+        sess.transform(); sess.loss(); sess.backward(seed=5, step=1)
+        torch.cuda.synchronize()
+        outs.append(store.grad_dict())
+    for k in outs[0]:
+        if k == "word_embeddings/embeddings":
+            assert torch.allclose(outs[0][k], outs[1][k], rtol=1e-4, atol=1e-6)
+        else:
+            assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+@pytest.mark.parametrize("name,C", [("h64_s50", 101), ("h128_s37", 37), ("h256_d64", 300)])
+def test_rank_candidates_bit_exact(name, C):
+    """Ranks / rankings are bit-exact w.r.t. the oracle's stable-descending sort applied to the kernel's own scores,
+    and agree with the fp32 oracle's ranks except at bf16 near-ties."""
+    from oracle import host_ops, model as om
+    store, kw, B, S, P = build(name)
+    V = kw["vocab_size"]
+    batch = make_batch(B, S, P, V, seed=21, eval_mode=True)
+    cb = to_cuda(batch)
+    sess = store.session(B, S, P)
+    sess.encode(cb["input_word_ids"], cb["input_mask"], training=False)
+    sess.select(cb["masked_lm_positions"], cb["masked_lm_ids"], cb["masked_lm_weights"], mode=1)
+    sess.transform()
+    n = int(sess.counts()[0])
+    assert n == B
+    rng = np.random.RandomState(0)
+    gt = batch["masked_lm_ids"][:, 0].numpy()
+    cand = np.zeros((n, C), dtype=np.int64)
+    for i in range(n):
+        pool = np.setdiff1d(np.arange(3, V), [gt[i]])
+        cand[i, :C - 1] = rng.choice(pool, C - 1, replace=False)
+        cand[i, C - 1] = gt[i]
+    cand[0, 5] = cand[0, 9]  # duplicated candidate -> exact tie inside the list
+    hist = torch.zeros(C + 1, dtype=torch.int64, device="cuda:0")
+    ranking, scores, rank = sess.rank_candidates(torch.from_numpy(cand).cuda(), torch.from_numpy(gt).cuda(),
+                                                 want_ranking=True, want_scores=True, hist=hist)
+    ranking, scores, rank = ranking.cpu().numpy(), scores.cpu().numpy(), rank.cpu().numpy()
+    for i in range(n):
+        order = host_ops.stable_desc_argsort(scores[i])
+        assert np.array_equal(ranking[i], cand[i][order])
+        assert rank[i] == host_ops.rank_of(ranking[i], gt[i])
+    assert int(hist.sum()) == n and np.array_equal(np.bincount(rank, minlength=C + 1), hist.cpu().numpy())
+    # against the fp32 oracle: same ranks up to bf16 near-ties
+    ref_rank = []
+    logits = om.model_forward(store.state_dict(), oracle_cfg(kw), batch, training=False)["mlm_logits"]
+    for i in range(n):
+        ref_rank.append(host_ops.rank_of(host_ops.rank_candidates(logits[i, 0].numpy(), cand[i]), gt[i]))
+    assert np.mean(np.abs(np.array(ref_rank) - rank) <= 2) > 0.9
+    # device-side metrics from the histogram vs the reference's sequential accumulation
+    from bert4rec_b200 import _lib
+    import ctypes as Ct
+    ks = torch.tensor([1, 5, 10], dtype=torch.int32, device="cuda:0")
+    out = torch.zeros(8, dtype=torch.float64, device="cuda:0")
+    _lib.check(_lib.load().b4r_metrics_from_hist(Ct.c_void_p(hist.data_ptr()), C, Ct.c_void_p(ks.data_ptr()), 3,
+                                                 Ct.c_void_p(out.data_ptr()), Ct.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    acc = host_ops.MetricAccumulator()
+    for r in rank:
+        acc.update(int(r))
+    res = acc.results()
+    o = out.cpu().numpy()
+    assert o[0] == n
+    for j, k in enumerate((1, 5, 10)):
+        assert abs(o[1 + j] - res[f"NDCG@{k}"]) < 1e-12 and abs(o[4 + j] - res[f"HR@{k}"]) < 1e-12
+    assert abs(o[7] - res["MAP"]) < 1e-12
+
+
+def test_rank_full_catalogue():
+    from oracle import model as om
+    store, kw, B, S, P = build("h64_s50")
+    V = kw["vocab_size"]
+    batch = make_batch(B, S, P, V, seed=23, eval_mode=True)
+    cb = to_cuda(batch)
+    sess = store.session(B, S, P)
+    sess.encode(cb["input_word_ids"], cb["input_mask"], training=False)
+    sess.select(cb["masked_lm_positions"], cb["masked_lm_ids"], cb["masked_lm_weights"], mode=1)
+    sess.transform(); sess.loss()
+    n = int(sess.counts()[1])
+    beat = sess.rank_full(n).cpu().numpy()
+    # sharded = unsharded (the vocab-sharded multi-GPU path sums shard counts)
+    b2 = (sess.rank_full(n, 0, 500) + sess.rank_full(n, 500, V)).cpu().numpy()
+    assert np.array_equal(beat, b2)
+    own = sess.logits(n).cpu()
+    gt = batch["masked_lm_ids"][:, 0]
+    for i in range(n):
+        s = own[i]
+        sg = s[gt[i]]
+        ref = int((s > sg).sum()) + int(((s == sg) & (torch.arange(V) < gt[i])).sum())
+        assert abs(int(beat[i]) - ref) <= 1, (i, beat[i], ref)   # separate GEMM launch: allow one near-tie flip
+
+
+def test_mlm_select_matches_boolean_mask():
+    store, kw, B, S, P = build("h64_s50")
+    batch = make_batch(B, S, P, kw["vocab_size"], seed=31)
+    cb = to_cuda(batch)
+    sess = store.session(B, S, P)
+    sess.select(cb["masked_lm_positions"], cb["masked_lm_ids"], cb["masked_lm_weights"], mode=0, want_aux=True)
+    counts = sess.counts().cpu().numpy()
+    rows = sess.rows().cpu().numpy()
+    y = batch["masked_lm_ids"].numpy(); pos = batch["masked_lm_positions"].numpy()
+    exp = [b * S + pos[b, p] for b in range(B) for p in range(P) if y[b, p] != 0]
+    assert counts[0] == len(exp) and np.array_equal(rows[:counts[0]], np.array(exp))
+    aux = [b * S for b in range(B) if (y[b] != 0).sum() < P]
+    assert counts[1] == len(exp) + len(aux) and np.array_equal(rows[counts[0]:counts[1]], np.array(aux))
