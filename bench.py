@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- train masked-seq/s (+ 100-negative eval seq/s) of the BERT4Rec hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2]
+
+Contract (see the task statement): one JSON line on stdout from rank 0.  ``value`` = whole-job train
+masked-seq/s with the step's inputs already resident in HBM; ``e2e`` = the same metric through the public API
+(``BERT4RecModel.train_step``) with HOST (pinned) input buffers, the H2D copy and a D2H read of the loss inside the
+timed region.  ``--impl reference`` times the CPU restatement of the reference's TF2 path (``oracle/``; TensorFlow
+itself is not installable here) on the host cores for the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# workload table: BASELINE.json configs (SURVEY.md section 8 sizes)
+WORKLOADS = {
+    # C1: the reference's CPU-runnable case (ml-1m_64.json)
+    "c1": dict(name="C1 ML-1m shape", vocab_size=3709, hidden_size=64, num_layers=2, num_attention_heads=2,
+               max_sequence_length=200, inner_dim=256, output_dropout=0.2, attention_dropout=0.2,
+               batch=256, seq_len=200, max_pred=40, mask_prob=0.2),
+    # C2: Beauty shape (beauty_64.json; masked_lm_prob 0.15 per BASELINE.json) -- the headline single-GPU config
+    "c2": dict(name="C2 Beauty shape", vocab_size=12004, hidden_size=64, num_layers=2, num_attention_heads=2,
+               max_sequence_length=50, inner_dim=64, output_dropout=0.5, attention_dropout=0.2,
+               batch=256, seq_len=50, max_pred=30, mask_prob=0.15),
+    # C3: ML-20m shape, per-GPU batch 256 (data-parallel runs)
+    "c3": dict(name="C3 ML-20m shape", vocab_size=26732, hidden_size=64, num_layers=2, num_attention_heads=2,
+               max_sequence_length=200, inner_dim=256, output_dropout=0.1, attention_dropout=0.1,
+               batch=256, seq_len=200, max_pred=40, mask_prob=0.2),
+    # C4: scaled model
+    "c4": dict(name="C4 scaled H256 L4", vocab_size=13047, hidden_size=256, num_layers=4, num_attention_heads=4,
+               max_sequence_length=200, inner_dim=1024, output_dropout=0.1, attention_dropout=0.1,
+               batch=1024, seq_len=200, max_pred=40, mask_prob=0.2),
+}
+ENC_KEYS = ("vocab_size", "hidden_size", "num_layers", "num_attention_heads", "max_sequence_length", "inner_dim",
+            "output_dropout", "attention_dropout")
+
+
+def synth_batches(w, n_batches, seed=0, eval_mode=False):
+    """Seeded synthetic batches: item ids ~ truncated Zipf(1.1) over [3, V), dense (full-length) sequences, Cloze
+    masking by the product's bit-exact restatement of apply_dynamic_masking_task (seed = sequence index)."""
+    import torch
+    from bert4rec_b200.dataloaders import dataloader_utils as du
+    rng = np.random.RandomState(seed)
+    V, S, P, B = w["vocab_size"], w["seq_len"], w["max_pred"], w["batch"]
+    out = []
+    for nb in range(n_batches):
+        feats = {k: [] for k in ("labels", "input_word_ids", "input_mask", "masked_lm_ids", "masked_lm_positions", "masked_lm_weights")}
+        for b in range(B):
+            seq = ((rng.zipf(1.1, size=S) - 1) % (V - 3) + 3).astype(np.int64)
+            labels = seq.copy()
+            if eval_mode:
+                ids, pos, lab = du.mask_last_token_only(seq.copy(), 1)
+            else:
+                ids, pos, lab = du.apply_dynamic_masking_task(seq, P, 1, [2, 0], V, selection_rate=w["mask_prob"],
+                                                              mask_token_rate=1.0, random_token_rate=0.0,
+                                                              seed=nb * B + b)
+            k = P - len(lab)
+            feats["labels"].append(labels)
+            feats["input_word_ids"].append(ids)
+            feats["input_mask"].append(np.ones(S, dtype=np.int64))
+            feats["masked_lm_ids"].append(np.pad(lab, (0, k)))
+            feats["masked_lm_positions"].append(np.pad(pos, (0, k)))
+            feats["masked_lm_weights"].append(np.pad(np.ones_like(lab), (0, k)))
+        out.append({k: torch.from_numpy(np.stack(v).astype(np.int64)) for k, v in feats.items()})
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def train_flops(w, m_valid):
+    """Algorithmic FLOPs of one train step: 3 x (encoder + MLM transform + tied projection)."""
+    T = w["batch"] * w["seq_len"]
+    H, I, S, L, V = w["hidden_size"], w["inner_dim"], w["seq_len"], w["num_layers"], w["vocab_size"]
+    fwd = L * T * (8 * H * H + 4 * S * H + 4 * H * I) + 2 * m_valid * H * H + 2 * m_valid * H * V
+    return 3 * fwd
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference(w, steps, warmup, sample_batch=None):
+    """The reference's TF2 path restated on the CPU (oracle/model.py), fp32, all host threads."""
+    import torch
+    from oracle import model as om
+    torch.set_num_threads(os.cpu_count())
+    b = dict(w)
+    if sample_batch:
+        b["batch"] = sample_batch
+    cfg = om.Config(**{k: w[k] for k in ENC_KEYS})
+    params = om.init_params(cfg, 0)
+    opt = om.AdamW({k: v for k, v in params.items() if not k.startswith("pooler")})
+    batches = synth_batches(b, 2, seed=0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        om.train_step(params, cfg, batches[i % 2], opt, training=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = float(np.mean(times) * 1e3)
+    return b["batch"] / (ms / 1e3), ms, b["batch"]
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    sample = min(w["batch"], 64) if w["seq_len"] >= 200 else w["batch"]
+    value, ms, bs = cpu_reference(w, args.steps, args.warmup, sample_batch=sample)
+    line = {"impl": "reference", "metric": "train masked-seq/s", "value": value, "unit": "seq/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], **{k: w[k] for k in ENC_KEYS}, "batch": w["batch"], "seq_len": w["seq_len"],
+                       "max_pred": w["max_pred"], "mask_prob": w["mask_prob"]},
+            "cpu_baseline": {"value": value, "unit": "seq/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} train steps of batch {bs} (CPU restatement of the TF2 path, torch fp32, {cores} threads)"},
+            "e2e": {"value": value, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args, w):
+    import torch
+    import torch.distributed as dist
+    from bert4rec_b200 import trainers
+    from bert4rec_b200.models import BERT4RecModel
+    from bert4rec_b200.models.components import networks
+    from bert4rec_b200.evaluation import BERT4RecEvaluator
+    from bert4rec_b200.dataloaders import samplers
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    enc = networks.Bert4RecEncoder(**{k: w[k] for k in ENC_KEYS}, device=dev, seed=0)
+    model = BERT4RecModel(enc)
+    trainer = trainers.get("bert4rec", model=model)
+    trainer.initialize_model()  # AdamW defaults, masked CE, [sparse_categorical_accuracy, masked_accuracy]
+    n_b = 4
+    host_batches = synth_batches(w, n_b, seed=rank)
+    for b in host_batches:
+        for k in b:
+            b[k] = b[k].pin_memory()
+    dev_batches = [{k: v.to(dev) for k, v in b.items()} for b in host_batches]
+    m_valid = int((host_batches[0]["masked_lm_ids"] != 0).sum())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    B, S, P = w["batch"], w["seq_len"], w["max_pred"]
+    sess = model.store.session(B, S, P)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(batches, read_loss):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.warmup):
+            r = model.train_step(batches[i % n_b])
+            if read_loss:
+                _ = r["loss"]
+        barrier()
+        l0 = sess.launch_count()
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)  # L2 flush between timed steps (untimed)
+            ev[i][0].record()
+            r = model.train_step(batches[i % n_b])
+            if read_loss:
+                _ = r["loss"]  # D2H read of the running loss (synchronises)
+            ev[i][1].record()
+        barrier()
+        launches = sess.launch_count() - l0 + 2 * args.steps  # + sqnorm and adamw kernels per step
+        total_ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    total_ms, launches = timed(dev_batches, read_loss=False)
+    clk = clocks.stop() if rank == 0 else None
+    e2e_ms, _ = timed(host_batches, read_loss=True)
+    value = world * B * args.steps / (total_ms / 1e3)
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+
+    # ---- 100-negative evaluation (leave-one-out, RandomSampler negatives built once on the host)
+    eval_batches = synth_batches(w, 2, seed=1000 + rank, eval_mode=True)
+    V = w["vocab_size"]
+    rng = np.random.RandomState(5)
+    ev_items = []
+    for b in eval_batches:
+        gt = b["masked_lm_ids"][:, 0].numpy()
+        cand = rng.randint(3, V, size=(B, 101)).astype(np.int64)
+        cand[:, 100] = gt
+        ev_items.append((b, {k: v.to(dev) for k, v in b.items()}, torch.from_numpy(cand).pin_memory(),
+                         torch.from_numpy(cand).to(dev), torch.from_numpy(gt.astype(np.int64)).pin_memory(),
+                         torch.from_numpy(gt.astype(np.int64)).to(dev)))
+    def eval_timed(use_dev):
+        for i in range(args.warmup):
+            hb, db, hc, dc, hg, dg = ev_items[i % 2]
+            model.rank_candidates(db if use_dev else hb, dc if use_dev else hc, dg if use_dev else hg)[1].cpu()
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.steps):
+            hb, db, hc, dc, hg, dg = ev_items[i % 2]
+            flush.fill_(i & 0xFF)
+            ev[i][0].record()
+            _, rk = model.rank_candidates(db if use_dev else hb, dc if use_dev else hc, dg if use_dev else hg)
+            if not use_dev:
+                rk.cpu()
+            ev[i][1].record()
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * B * args.steps / (float(t.item()) / 1e3)
+    eval_value = eval_timed(True)
+    eval_e2e = eval_timed(False)
+
+    if rank == 0:
+        hbm, tf_burst, tf_sus, src = peaks()
+        flops = train_flops(w, m_valid)
+        step_ms = total_ms / args.steps
+        achieved_tf = flops / (step_ms / 1e3) / 1e12
+        line = {
+            "metric": "train masked-seq/s", "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": w["name"], **{k: w[k] for k in ENC_KEYS}, "batch_per_gpu": B, "seq_len": S,
+                       "max_pred": P, "mask_prob": w["mask_prob"], "valid_masked_slots_per_batch": m_valid,
+                       "sequences": "dense (full length), Zipf(1.1) item ids", "parallelism": f"dp{world}",
+                       "l2": "256 MiB buffer written between timed steps (untimed); per-step CUDA events summed"},
+            "e2e": {"value": e2e_value, "unit": "seq/s",
+                    "h2d_bytes_per_step": BERT4RecModel._bytes_of(("input_word_ids", "input_mask", "masked_lm_positions", "masked_lm_ids", "masked_lm_weights"), host_batches[0]),
+                    "d2h_bytes_per_step": 64},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "eval": {"metric": "100-neg eval seq/s", "value": eval_value, "e2e": eval_e2e, "unit": "seq/s"},
+            "step_flops": {"algorithmic_flops_per_step": flops, "achieved_tflops": achieved_tf,
+                           "frac_of_bf16_sustained": achieved_tf / tf_sus, "peak_source": src},
+        }
+        line["roofline"] = roofline_block(model, sess, w, dev_batches, args, hbm, tf_burst, src)
+        if world == 1 and not args.no_cpu_baseline:
+            sample = min(B, 64) if S >= 200 else B
+            v, ms, bs = cpu_reference(w, 3, 1, sample_batch=sample)
+            line["cpu_baseline"] = {"value": v, "unit": "seq/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"3 train steps of batch {bs} after 1 warm-up (CPU restatement of the TF2 path, torch fp32, {os.cpu_count()} threads), {ms:.0f} ms/step"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_work(tag, w, n_rows):
+    """Algorithmic (flops, bytes, bound) of ONE launch of the kernel behind a profile tag."""
+    B, S, H, I, V, N = w["batch"], w["seq_len"], w["hidden_size"], w["inner_dim"], w["vocab_size"], w["num_attention_heads"]
+    T, M, Vp, e = B * S, n_rows, (V + 127) // 128 * 128, 2
+    t = {
+        "embed_ln_fwd": (0, T * (8 + 2 * H * e), "hbm"),
+        "embed_bwd": (0, T * (8 + H * e + H * 4) + T * H * 4, "hbm"),
+        "gemm:qkv": (2 * T * H * 3 * H, T * H * e + 3 * H * H * e + T * 3 * H * e, "tensor"),
+        "attn_fwd": (4 * T * S * H, T * 3 * H * e + T * H * e + T * N * 4, "tensor"),
+        "rowln:attn_out": (2 * T * H * H, 3 * T * H * e + H * H * e + T * H * e, "tensor"),
+        "gemm:ffn1_gelu": (2 * T * H * I, T * H * e + H * I * e + 2 * T * I * e, "tensor"),
+        "rowln:ffn2": (2 * T * I * H, T * I * e + I * H * e + 3 * T * H * e, "tensor"),
+        "rowln:mlm_transform": (2 * M * H * H, 4 * M * H * e + H * H * e, "tensor"),
+        "ce_fwd": (2 * M * H * V, M * H * e + V * H * e + V * 4 + 3 * M * 4, "tensor"),
+        "ce_dlogits": (2 * M * H * V, M * H * e + V * H * e + V * 4 + M * Vp * e, "hbm"),
+        "gemm:ce_dT": (2 * M * V * H, M * Vp * e + V * H * e + M * H * 4, "hbm"),
+        "wgrad:ce_dE": (2 * M * V * H, M * Vp * e + M * H * e + 2 * V * H * 4, "hbm"),
+        "colsum:vbias": (0, M * Vp * e + V * 4, "hbm"),
+        "ln_bwd": (0, T * H * (4 + e + 4 + e), "hbm"),
+        "attn_bwd": (10 * T * S * H, T * 3 * H * e * 2 + 2 * T * H * e, "tensor"),
+        "wgrad:w2": (2 * T * I * H, T * I * e + T * H * e, "hbm"),
+        "wgrad:w1": (2 * T * I * H, T * I * e + T * H * e, "hbm"),
+        "wgrad:wo": (2 * T * H * H, 2 * T * H * e, "hbm"),
+        "wgrad:wqkv": (2 * T * H * 3 * H, T * H * e + T * 3 * H * e, "hbm"),
+        "gemm:ffn2_dgrad_gelu": (2 * T * H * I, T * H * e + 2 * T * I * e + I * H * e, "tensor"),
+        "gemm:ffn1_dgrad": (2 * T * I * H, T * I * e + 2 * T * H * 4, "tensor"),
+        "gemm:attn_out_dgrad": (2 * T * H * H, 2 * T * H * e, "tensor"),
+        "gemm:qkv_dgrad": (2 * T * 3 * H * H, T * 3 * H * e + 2 * T * H * 4, "tensor"),
+        "colsum:bqkv": (0, T * 3 * H * e, "hbm"),
+    }
+    return t.get(tag, (0, 0, "hbm"))
+
+
+def roofline_block(model, sess, w, dev_batches, args, hbm, tf_burst, src):
+    """Per-kernel CUDA-event timing (events recorded on the launching stream around every launch of the session,
+    b4r_profile_*) over a profiled pass of train steps; the dominant kernel's roofline entry + the breakdown."""
+    import torch
+    n = max(args.steps, 10)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_batches[0]["input_word_ids"].device)
+    for i in range(3):
+        model.train_step(dev_batches[i % len(dev_batches)])
+    torch.cuda.synchronize()
+    sess.profile(True)
+    for i in range(n):
+        flush.fill_(i & 0xFF)
+        model.train_step(dev_batches[i % len(dev_batches)])
+    rep = sess.profile_report()
+    sess.profile(False)
+    n_rows = int(sess.counts()[1])
+    rows = sorted(((tag, cnt, tot) for tag, (cnt, tot) in rep.items()), key=lambda r: -r[2])
+    total = sum(r[2] for r in rows)
+    breakdown = []
+    for tag, cnt, tot in rows[:12]:
+        fl, by, bound = kernel_work(tag, w, n_rows)
+        ms = tot / cnt
+        breakdown.append({"kernel": tag, "launches_per_step": cnt / n, "avg_ms": ms, "share": tot / total,
+                          "tflops": fl / (ms / 1e3) / 1e12 if fl else 0.0, "gbs": by / (ms / 1e3) / 1e9 if by else 0.0})
+    tag, cnt, tot = rows[0]
+    fl, by, bound = kernel_work(tag, w, n_rows)
+    ms = tot / cnt
+    if bound == "tensor":
+        ach, peak, unit = fl / (ms / 1e3) / 1e12, tf_burst, "TFLOP/s"
+    else:
+        ach, peak, unit = by / (ms / 1e3) / 1e9, hbm, "GB/s"
+    return {"kernel": tag, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+            "traffic": None, "peak_source": src, "launch_ms": ms, "share_of_step": tot / total,
+            "algorithmic_flops": fl, "algorithmic_bytes": by, "kernel_ms_per_step": total / n, "breakdown": breakdown}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_b200(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,7 +50,7 @@ _SIGNATURES = {
     "b4r_encode": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint64, C.c_uint32, _P]),
     "b4r_mlm_select": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "b4r_mlm_transform": (C.c_int, [_P, _P]),
-    "b4r_mlm_loss": (C.c_int, [_P, _P]),
+    "b4r_mlm_loss": (C.c_int, [_P, _P, _P]),
     "b4r_mlm_logits": (C.c_int, [_P, _P, _P]),
     "b4r_backward": (C.c_int, [_P, C.c_uint64, C.c_uint32, _P]),
     "b4r_pooled_output": (C.c_int, [_P, _P, _P]),
@@ -63,10 +63,11 @@ _SIGNATURES = {
     "b4r_mlm_hidden": (_P, [_P]),
     "b4r_mlm_counts": (_P, [_P]),
     "b4r_mlm_rows": (_P, [_P]),
-    "b4r_stats": (_P, [_P]),
     "b4r_step_stats": (_P, [_P]),
     "b4r_attn_keep_bits": (_P, [_P, C.c_int, C.POINTER(C.c_int)]),
     "b4r_launch_count": (C.c_int, [_P]),
+    "b4r_profile_enable": (C.c_int, [_P, C.c_int]),
+    "b4r_profile_report": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "b4r_dropout_keep_mask": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_int, C.c_int, C.c_uint32, _P]),
     "b4r_embed_ln_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "b4r_dl_view_of": (C.c_int, [_P, C.POINTER(DLView)]),

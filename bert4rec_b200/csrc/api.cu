@@ -28,6 +28,17 @@ static int fail(const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// kernel launch through a session: counts the launch and, when profiling is on, brackets it with CUDA events
+#define KL(tag, expr)                                                                   \
+  do {                                                                                  \
+    cudaEvent_t e0__ = nullptr, e1__ = nullptr;                                         \
+    if (s->prof_on) { cudaEventCreate(&e0__); cudaEventCreate(&e1__); cudaEventRecord(e0__, st); } \
+    CK(expr);                                                                           \
+    s->launches++;                                                                      \
+    if (s->prof_on) { cudaEventRecord(e1__, st); s->prof.push_back(ProfRec{tag, e0__, e1__}); }    \
+  } while (0)
+struct ProfRec { const char* tag; cudaEvent_t a, b; };
+
 extern "C" int b4r_version(void) { return B4R_VERSION; }
 extern "C" const char* b4r_last_error(void) { return g_err; }
 extern "C" int b4r_device_check(int device) {
@@ -181,6 +192,8 @@ struct b4r_session {
   const int64_t *ids, *mask;
   int select_mode;
   int launches;
+  bool prof_on = false;
+  std::vector<ProfRec> prof;
 };
 
 static int wgrad_splits(int M, int N, int T) {
@@ -370,9 +383,9 @@ extern "C" int b4r_session_create(const b4r_config* cfg, int batch, int seq_len,
 extern "C" void b4r_session_destroy(b4r_session* s) { delete s; }
 
 extern "C" int b4r_sync_shadow(b4r_session* s, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
   if (!s) return fail("null session");
-  CK(launch_cast_bf16(s->params, s->shadow, s->lay.n_total, (cudaStream_t)stream));
-  s->launches++;
+  KL("cast_bf16", launch_cast_bf16(s->params, s->shadow, s->lay.n_total, st));
   return 0;
 }
 
@@ -386,36 +399,34 @@ extern "C" int b4r_encode(b4r_session* s, const int64_t* ids, const int64_t* mas
   const float* P = s->params;
   const bf16* W = s->shadow;
   s->ids = ids; s->mask = mask;
-  CK(launch_embed_ln_fwd(ids, W + s->lay.find("word_embeddings"), W + s->lay.find("position_embedding"),
+  KL("embed_ln_fwd", launch_embed_ln_fwd(ids, W + s->lay.find("word_embeddings"), W + s->lay.find("position_embedding"),
                          P + s->lay.find("emb_ln/gamma"), P + s->lay.find("emb_ln/beta"), s->x0, s->B, s->S, H, s->V, od,
                          seed, step, st));
-  s->launches++;
   const bf16* x = s->x0;
   for (int l = 0; l < s->cfg.num_layers; ++l) {
     LayerBuf& L = s->layers[l];
     GemmArgs g{};
     g.A = x; g.lda = H; g.B = W + L.wqkv; g.ldb = 3 * H; g.b_trans = true; g.M = T; g.N = 3 * H; g.K = H;
     g.bias = P + L.bqkv; g.out_bf16 = L.qkv; g.ld_out = 3 * H;
-    CK(launch_gemm(EPI_BIAS_BF16, g, st));
+    KL("gemm:qkv", launch_gemm(EPI_BIAS_BF16, g, st));
     AttnArgs a{};
     a.qkv = L.qkv; a.mask = mask; a.ctx = L.ctx; a.lse = L.lse; a.keep_bits = L.keep; a.B = s->B; a.S = s->S; a.H = H; a.N = s->N;
     a.drop_rate = ad; a.seed = seed; a.site = site_id(SITE_ATTN_PROBS, l); a.step = step;
-    CK(launch_attn_fwd(a, st));
+    KL("attn_fwd", launch_attn_fwd(a, st));
     RowLnArgs r{};
     r.A = L.ctx; r.lda = H; r.W = W + L.wo; r.M = T; r.K = H; r.H = H; r.bias = P + L.bo; r.gamma = P + L.g1; r.beta = P + L.be1;
     r.residual = x; r.pre = L.a_pre; r.y = L.y; r.mean = L.mean1; r.rstd = L.rstd1;
     r.drop_rate = od; r.seed = seed; r.site = site_id(SITE_ATTN_OUT, l); r.step = step;
-    CK(launch_gemm_rowln(ROW_RES_DROP_LN, r, st));
+    KL("rowln:attn_out", launch_gemm_rowln(ROW_RES_DROP_LN, r, st));
     GemmArgs f{};
     f.A = L.y; f.lda = H; f.B = W + L.w1; f.ldb = I; f.b_trans = true; f.M = T; f.N = I; f.K = H;
     f.bias = P + L.b1; f.out_bf16 = L.h_pre; f.out2_bf16 = L.h; f.ld_out = I;
-    CK(launch_gemm(EPI_BIAS_GELU, f, st));
+    KL("gemm:ffn1_gelu", launch_gemm(EPI_BIAS_GELU, f, st));
     RowLnArgs r2{};
     r2.A = L.h; r2.lda = I; r2.W = W + L.w2; r2.M = T; r2.K = I; r2.H = H; r2.bias = P + L.b2; r2.gamma = P + L.g2; r2.beta = P + L.be2;
     r2.residual = L.y; r2.pre = L.o_pre; r2.y = L.out; r2.mean = L.mean2; r2.rstd = L.rstd2;
     r2.drop_rate = od; r2.seed = seed; r2.site = site_id(SITE_FFN_OUT, l); r2.step = step;
-    CK(launch_gemm_rowln(ROW_RES_DROP_LN, r2, st));
-    s->launches += 5;
+    KL("rowln:ffn2", launch_gemm_rowln(ROW_RES_DROP_LN, r2, st));
     x = L.out;
   }
   return 0;
@@ -423,6 +434,7 @@ extern "C" int b4r_encode(b4r_session* s, const int64_t* ids, const int64_t* mas
 
 extern "C" int b4r_mlm_select(b4r_session* s, const int64_t* positions, const int64_t* ids, const int64_t* weights,
                               int mode, int want_aux, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
   if (!s || !positions) return fail("null argument");
   if (mode == 0 && !ids) return fail("mode 0 needs masked_lm_ids");
   if (mode == 1 && !weights) return fail("mode 1 needs masked_lm_weights");
@@ -432,15 +444,15 @@ extern "C" int b4r_mlm_select(b4r_session* s, const int64_t* positions, const in
   const int64_t* id_src = ids ? ids : positions;
   if (mode == 2) {
     // all slots valid: weights := non-null pointer whose values are irrelevant -> use use_weights = 2
-    CK(launch_mlm_select(positions, id_src, nullptr, 2, s->B, s->S, s->P, 0, s->rows, s->labels, s->row_w, s->row_mult, s->counts, (cudaStream_t)stream));
+    KL("mlm_select", launch_mlm_select(positions, id_src, nullptr, 2, s->B, s->S, s->P, 0, s->rows, s->labels, s->row_w, s->row_mult, s->counts, st));
   } else {
-    CK(launch_mlm_select(positions, id_src, weights, mode, s->B, s->S, s->P, want_aux, s->rows, s->labels, s->row_w, s->row_mult, s->counts, (cudaStream_t)stream));
+    KL("mlm_select", launch_mlm_select(positions, id_src, weights, mode, s->B, s->S, s->P, want_aux, s->rows, s->labels, s->row_w, s->row_mult, s->counts, st));
   }
-  s->launches++;
   return 0;
 }
 
 extern "C" int b4r_mlm_transform(b4r_session* s, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
   if (!s) return fail("null session");
   const int H = s->H;
   const bf16* x = s->layers.back().out;
@@ -449,8 +461,7 @@ extern "C" int b4r_mlm_transform(b4r_session* s, void* stream) {
   r.d_M = s->counts + 1;
   r.bias = s->params + s->lay.find("head/bt"); r.gamma = s->params + s->lay.find("head/ln/gamma"); r.beta = s->params + s->lay.find("head/ln/beta");
   r.pre = s->t_pre; r.act = s->t_act; r.y = s->t; r.mean = s->hmean; r.rstd = s->hrstd;
-  CK(launch_gemm_rowln(ROW_GELU_LN, r, (cudaStream_t)stream));
-  s->launches++;
+  KL("rowln:mlm_transform", launch_gemm_rowln(ROW_GELU_LN, r, st));
   return 0;
 }
 
@@ -458,29 +469,30 @@ static CeArgs ce_args(b4r_session* s) {
   CeArgs c{};
   c.t = s->t; c.ldt = s->H; c.E = s->shadow + s->lay.find("word_embeddings"); c.vbias = s->params + s->lay.find("head/output_bias");
   c.labels = s->labels; c.row_w = s->row_w; c.row_mult = s->row_mult; c.d_counts = s->counts;
-  c.M_cap = s->Mcap; c.H = s->H; c.V = s->V; c.v_begin = 0; c.v_end = s->V; c.vsplits = s->vsplits;
-  c.part = s->ce_part; c.lse = s->lse; c.lab_out = s->lab; c.stats = s->stats; c.step_stats = s->step_stats;
+  c.M_cap = s->Mcap; c.H = s->H; c.V = s->V; c.v_begin = 0; c.v_end = s->V; c.vsplits = s->vsplits; c.batch = s->B;
+  c.part = s->ce_part; c.lse = s->lse; c.lab_out = s->lab; c.stats = nullptr; c.step_stats = s->step_stats;
   c.dlogits = s->dlogits; c.ld_dl = s->Vp;
   return c;
 }
 
-extern "C" int b4r_mlm_loss(b4r_session* s, void* stream) {
+extern "C" int b4r_mlm_loss(b4r_session* s, float* stats, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
   if (!s) return fail("null session");
   CeArgs c = ce_args(s);
-  CK(launch_ce_fwd(c, (cudaStream_t)stream));
-  CK(launch_ce_finalize(c, (cudaStream_t)stream));
-  s->launches += 2;
+  c.stats = stats;
+  KL("ce_fwd", launch_ce_fwd(c, st));
+  KL("ce_finalize", launch_ce_finalize(c, st));
   return 0;
 }
 
 extern "C" int b4r_mlm_logits(b4r_session* s, float* out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
   if (!s || !out) return fail("null argument");
   GemmArgs g{};
   g.A = s->t; g.lda = s->H; g.B = s->shadow + s->lay.find("word_embeddings"); g.ldb = s->H; g.b_trans = false;
   g.M = s->Mcap; g.N = s->V; g.K = s->H; g.d_M = s->counts + 1;
   g.bias = s->params + s->lay.find("head/output_bias"); g.out_f32 = out; g.ld_f32 = s->V;
-  CK(launch_gemm(EPI_BIAS_F32, g, (cudaStream_t)stream));
-  s->launches++;
+  KL("gemm:logits", launch_gemm(EPI_BIAS_F32, g, st));
   return 0;
 }
 
@@ -504,105 +516,101 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, void* 
   for (int r0 = 0; r0 < Mcap; r0 += s->dl_rows, ++chunk) {
     const int rc = (Mcap - r0) < s->dl_rows ? (Mcap - r0) : s->dl_rows;
     c.row_begin = r0; c.row_count = rc;
-    CK(launch_ce_dlogits(c, st));
-    CK(launch_colsum_bf16(s->dlogits, s->Vp, rc, V, s->counts + 1, r0, s->p_vbias, s->vb_splits, st));
-    CK(launch_grad_reduce(s->d_vb_jobs + (chunk > 0 ? 1 : 0), 1, V, st));
+    KL("ce_dlogits", launch_ce_dlogits(c, st));
+    KL("colsum:vbias", launch_colsum_bf16(s->dlogits, s->Vp, rc, V, s->counts + 1, r0, s->p_vbias, s->vb_splits, st));
+    KL("grad_reduce:vbias", launch_grad_reduce(s->d_vb_jobs + (chunk > 0 ? 1 : 0), 1, V, st));
     GemmArgs g{};
     g.A = s->dlogits; g.lda = s->Vp; g.B = W + oE; g.ldb = H; g.b_trans = true; g.M = rc; g.N = H; g.K = s->Vp;
     g.a_kmax = s->Vp; g.b_kmax = V; g.d_M = s->counts + 1; g.d_M_off = r0; g.splits = s->dt_splits;
     g.out_f32 = s->dt_part + (size_t)r0 * H; g.ld_f32 = H; g.split_stride = (size_t)Mcap * H;
-    CK(launch_gemm(EPI_F32_PARTIAL, g, st));
+    KL("gemm:ce_dT", launch_gemm(EPI_F32_PARTIAL, g, st));
     WgradArgs w{};
     w.X = s->dlogits; w.ldx = s->Vp; w.dY = s->t + (size_t)r0 * H; w.ldy = H; w.M = V; w.N = H; w.T = rc;
     w.d_T = s->counts + 1; w.d_T_off = r0; w.splits = 1; w.out = G + oE; w.ld_out = H; w.accumulate = 1; w.x_mmax = s->Vp;
-    CK(launch_wgrad(w, st));
-    s->launches += 5;
+    KL("wgrad:ce_dE", launch_wgrad(w, st));
   }
   // ---- MLM transform backward
-  CK(launch_head_bwd_rows(s->dt_part, s->dt_splits, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
+  KL("head_bwd_rows", launch_head_bwd_rows(s->dt_part, s->dt_splits, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
                           P + s->lay.find("head/ln/gamma"), s->d_tpre, s->p_head_ln, Mcap, s->counts, H, st));
   const bf16* xL = s->layers.back().out;
   {
     WgradArgs w{};
     w.X = xL; w.ldx = H; w.x_rows = s->rows; w.dY = s->d_tpre; w.ldy = H; w.M = H; w.N = H; w.T = Mcap;
     w.d_T = s->counts + 1; w.splits = s->s_wt; w.out = s->p_wt; w.split_stride = (size_t)H * H; w.ld_out = H;
-    CK(launch_wgrad(w, st));
+    KL("wgrad:head_wt", launch_wgrad(w, st));
     GemmArgs g{};
     g.A = s->d_tpre; g.lda = H; g.B = W + s->lay.find("head/wt"); g.ldb = H; g.b_trans = false; g.M = Mcap; g.N = H; g.K = H;
     g.d_M = s->counts;  // n_valid only: aux rows carry no gradient and may alias position 0 of a valid slot
     g.out_f32 = s->dxa; g.ld_f32 = H; g.scatter_rows = s->rows;
-    CK(launch_gemm(EPI_SCATTER_F32, g, st));
-    s->launches += 3;
+    KL("gemm:head_dx_scatter", launch_gemm(EPI_SCATTER_F32, g, st));
   }
   // ---- encoder layers, last to first.  d_out lives in dxa at the top of every iteration.
   for (int l = s->cfg.num_layers - 1; l >= 0; --l) {
     LayerBuf& L = s->layers[l];
     const bf16* x_in = l == 0 ? s->x0 : s->layers[l - 1].out;
-    CK(launch_ln_bwd(s->dxa, L.o_pre, L.mean2, L.rstd2, P + L.g2, s->dxb, s->d_branch, L.p_ln2, T, H, od, seed,
+    KL("ln_bwd", launch_ln_bwd(s->dxa, L.o_pre, L.mean2, L.rstd2, P + L.g2, s->dxb, s->d_branch, L.p_ln2, T, H, od, seed,
                      site_id(SITE_FFN_OUT, l), step, st));
     {
       WgradArgs w{};
       w.X = L.h; w.ldx = I; w.dY = s->d_branch; w.ldy = H; w.M = I; w.N = H; w.T = T; w.splits = L.s_w2;
       w.out = L.p_w2; w.split_stride = (size_t)I * H; w.ld_out = H;
-      CK(launch_wgrad(w, st));
+      KL("wgrad:w2", launch_wgrad(w, st));
     }
     {
       GemmArgs g{};
       g.A = s->d_branch; g.lda = H; g.B = W + L.w2; g.ldb = H; g.b_trans = false; g.M = T; g.N = I; g.K = H;
       g.aux_bf16 = L.h_pre; g.ld_aux = I; g.out_bf16 = s->dh; g.ld_out = I; g.colsum_part = L.p_b1;
-      CK(launch_gemm(EPI_GELU_GRAD, g, st));
+      KL("gemm:ffn2_dgrad_gelu", launch_gemm(EPI_GELU_GRAD, g, st));
     }
     {
       WgradArgs w{};
       w.X = L.y; w.ldx = H; w.dY = s->dh; w.ldy = I; w.M = H; w.N = I; w.T = T; w.splits = L.s_w1;
       w.out = L.p_w1; w.split_stride = (size_t)H * I; w.ld_out = I;
-      CK(launch_wgrad(w, st));
+      KL("wgrad:w1", launch_wgrad(w, st));
     }
     {
       GemmArgs g{};
       g.A = s->dh; g.lda = I; g.B = W + L.w1; g.ldb = I; g.b_trans = false; g.M = T; g.N = H; g.K = I;
       g.res_f32 = s->dxb; g.out_f32 = s->dxa; g.ld_f32 = H;
-      CK(launch_gemm(EPI_F32_RES, g, st));
+      KL("gemm:ffn1_dgrad", launch_gemm(EPI_F32_RES, g, st));
     }
-    CK(launch_ln_bwd(s->dxa, L.a_pre, L.mean1, L.rstd1, P + L.g1, s->dxb, s->d_branch, L.p_ln1, T, H, od, seed,
+    KL("ln_bwd", launch_ln_bwd(s->dxa, L.a_pre, L.mean1, L.rstd1, P + L.g1, s->dxb, s->d_branch, L.p_ln1, T, H, od, seed,
                      site_id(SITE_ATTN_OUT, l), step, st));
     {
       WgradArgs w{};
       w.X = L.ctx; w.ldx = H; w.dY = s->d_branch; w.ldy = H; w.M = H; w.N = H; w.T = T; w.splits = L.s_wo;
       w.out = L.p_wo; w.split_stride = (size_t)H * H; w.ld_out = H;
-      CK(launch_wgrad(w, st));
+      KL("wgrad:wo", launch_wgrad(w, st));
     }
     {
       GemmArgs g{};
       g.A = s->d_branch; g.lda = H; g.B = W + L.wo; g.ldb = H; g.b_trans = false; g.M = T; g.N = H; g.K = H;
       g.out_bf16 = s->dctx; g.ld_out = H;
-      CK(launch_gemm(EPI_BF16, g, st));
+      KL("gemm:attn_out_dgrad", launch_gemm(EPI_BF16, g, st));
     }
     {
       AttnArgs a{};
       a.qkv = L.qkv; a.mask = s->mask; a.ctx = L.ctx; a.lse = L.lse; a.keep_bits = L.keep; a.B = s->B; a.S = s->S; a.H = H; a.N = s->N;
       a.drop_rate = s->cfg.attention_dropout; a.dctx = s->dctx; a.dqkv = s->dqkv;
-      CK(launch_attn_bwd(a, st));
+      KL("attn_bwd", launch_attn_bwd(a, st));
     }
-    CK(launch_colsum_bf16(s->dqkv, 3 * H, T, 3 * H, nullptr, 0, L.p_bqkv, 8, st));
+    KL("colsum:bqkv", launch_colsum_bf16(s->dqkv, 3 * H, T, 3 * H, nullptr, 0, L.p_bqkv, 8, st));
     {
       WgradArgs w{};
       w.X = x_in; w.ldx = H; w.dY = s->dqkv; w.ldy = 3 * H; w.M = H; w.N = 3 * H; w.T = T; w.splits = L.s_wqkv;
       w.out = L.p_wqkv; w.split_stride = (size_t)H * 3 * H; w.ld_out = 3 * H;
-      CK(launch_wgrad(w, st));
+      KL("wgrad:wqkv", launch_wgrad(w, st));
     }
     {
       GemmArgs g{};
       g.A = s->dqkv; g.lda = 3 * H; g.B = W + L.wqkv; g.ldb = 3 * H; g.b_trans = false; g.M = T; g.N = H; g.K = 3 * H;
       g.res_f32 = s->dxb; g.out_f32 = s->dxa; g.ld_f32 = H;
-      CK(launch_gemm(EPI_F32_RES, g, st));
+      KL("gemm:qkv_dgrad", launch_gemm(EPI_F32_RES, g, st));
     }
-    s->launches += 12;
   }
-  CK(launch_embed_bwd(s->ids, W + oE, W + s->lay.find("position_embedding"), P + s->lay.find("emb_ln/gamma"), s->dxa,
+  KL("embed_bwd", launch_embed_bwd(s->ids, W + oE, W + s->lay.find("position_embedding"), P + s->lay.find("emb_ln/gamma"), s->dxa,
                       G + oE, s->p_dpos, s->p_embln, s->B, s->S, H, V, od, seed, step, s->emb_bsplits, st));
-  CK(launch_grad_reduce(s->d_jobs, s->n_jobs, s->jobs_max_len, st));
-  s->launches += 2;
+  KL("grad_reduce:all", launch_grad_reduce(s->d_jobs, s->n_jobs, s->jobs_max_len, st));
   return 0;
 }
 
@@ -618,10 +626,10 @@ __global__ void pooler_kernel(const bf16* __restrict__ x, const float* __restric
 }
 extern "C" int b4r_pooled_output(b4r_session* s, float* out, void* stream) {
   if (!s || !out) return fail("null argument");
-  pooler_kernel<<<s->B, 128, 0, (cudaStream_t)stream>>>(s->layers.back().out, s->params + s->lay.find("pooler/w"),
+  cudaStream_t st = (cudaStream_t)stream;
+  pooler_kernel<<<s->B, 128, 0, st>>>(s->layers.back().out, s->params + s->lay.find("pooler/w"),
                                                        s->params + s->lay.find("pooler/b"), out, s->B, s->S, s->H);
   CK(cudaGetLastError());
-  s->launches++;
   return 0;
 }
 
@@ -648,24 +656,24 @@ extern "C" int b4r_adamw_step(float* params, void* shadow_bf16, const float* gra
 extern "C" int b4r_rank_candidates(b4r_session* s, const int64_t* cand, const int64_t* gt, int n_slots, int C,
                                    int64_t* ranking_out, float* scores_out, int32_t* rank_out, uint64_t* hist,
                                    void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
   if (!s || !cand) return fail("null argument");
   if (C < 1 || C > 2048) return fail("candidate count %d unsupported (1..2048)", C);
   if (n_slots > s->Mcap) return fail("n_slots %d exceeds session capacity %d", n_slots, s->Mcap);
-  CK(launch_rank_candidates(s->t, s->H, s->shadow + s->lay.find("word_embeddings"), s->params + s->lay.find("head/output_bias"),
+  KL("rank_candidates", launch_rank_candidates(s->t, s->H, s->shadow + s->lay.find("word_embeddings"), s->params + s->lay.find("head/output_bias"),
                             cand, gt, n_slots, C, s->H, reinterpret_cast<int64_t*>(ranking_out), scores_out, rank_out,
-                            reinterpret_cast<unsigned long long*>(hist), (cudaStream_t)stream));
-  s->launches++;
+                            reinterpret_cast<unsigned long long*>(hist), st));
   return 0;
 }
 
 extern "C" int b4r_rank_full(b4r_session* s, int v_begin, int v_end, int32_t* beat_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
   if (!s || !beat_out) return fail("null argument");
   if (v_begin < 0 || v_end > s->V || v_begin >= v_end) return fail("bad vocabulary shard [%d, %d)", v_begin, v_end);
   // ground-truth scores: label logit of the fused CE pass over the FULL vocabulary (b4r_mlm_loss must have run)
   CeArgs c = ce_args(s);
   c.v_begin = v_begin; c.v_end = v_end;
-  CK(launch_ce_count(c, s->lab, beat_out, (cudaStream_t)stream));
-  s->launches++;
+  KL("ce_count", launch_ce_count(c, s->lab, beat_out, st));
   return 0;
 }
 
@@ -686,7 +694,6 @@ extern "C" const void* b4r_sequence_output(b4r_session* s, int layer) {
 extern "C" const void* b4r_mlm_hidden(b4r_session* s) { return s ? s->t : nullptr; }
 extern "C" const int32_t* b4r_mlm_counts(b4r_session* s) { return s ? s->counts : nullptr; }
 extern "C" const int32_t* b4r_mlm_rows(b4r_session* s) { return s ? s->rows : nullptr; }
-extern "C" float* b4r_stats(b4r_session* s) { return s ? s->stats : nullptr; }
 extern "C" float* b4r_step_stats(b4r_session* s) { return s ? s->step_stats : nullptr; }
 extern "C" const uint64_t* b4r_attn_keep_bits(b4r_session* s, int layer, int* words_per_row) {
   if (!s || layer < 0 || layer >= s->cfg.num_layers) return nullptr;
@@ -694,6 +701,36 @@ extern "C" const uint64_t* b4r_attn_keep_bits(b4r_session* s, int layer, int* wo
   return s->layers[layer].keep;
 }
 extern "C" int b4r_launch_count(b4r_session* s) { return s ? s->launches : 0; }
+extern "C" int b4r_profile_enable(b4r_session* s, int on) {
+  if (!s) return fail("null session");
+  s->prof_on = on != 0;
+  return 0;
+}
+// Synchronises the device, aggregates the recorded per-launch event times by kernel tag, writes lines
+// "tag count total_ms" into buf, and clears the records.
+extern "C" int b4r_profile_report(b4r_session* s, char* buf, int cap) {
+  if (!s || !buf || cap < 1) return fail("bad argument");
+  CK(cudaDeviceSynchronize());
+  std::vector<std::string> tags; std::vector<int> cnt; std::vector<double> tot;
+  for (auto& r : s->prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    size_t i = 0;
+    for (; i < tags.size(); ++i) if (tags[i] == r.tag) break;
+    if (i == tags.size()) { tags.push_back(r.tag); cnt.push_back(0); tot.push_back(0.0); }
+    cnt[i]++; tot[i] += ms;
+  }
+  s->prof.clear();
+  std::string out;
+  for (size_t i = 0; i < tags.size(); ++i) {
+    char line[160];
+    snprintf(line, sizeof(line), "%s %d %.6f\n", tags[i].c_str(), cnt[i], tot[i]);
+    out += line;
+  }
+  snprintf(buf, cap, "%s", out.c_str());
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------ test helpers
 extern "C" int b4r_dropout_keep_mask(uint8_t* out, int rows, int cols, float rate, uint64_t seed, int site, int layer,

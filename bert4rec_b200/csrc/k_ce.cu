@@ -109,7 +109,7 @@ int ce_block_m() { return CE_BM; }
 struct CeDev {
   const bf16* t; int ldt; const bf16* E; const float* vbias;
   const int* labels; const float* row_w; const int* row_mult; const int* d_counts;
-  int M_cap, V, v_begin, v_end, vsplits;
+  int M_cap, V, v_begin, v_end, vsplits, batch;
   float* part; float* lse; float* lab_out; float* stats; float* step_stats;
   bf16* dlogits; int ld_dl; int row_begin, row_count;
 };
@@ -305,11 +305,22 @@ __global__ void __launch_bounds__(1024) ce_finalize_kernel(CeDev a) {
     if (lane == 0) s_red[warp][k] = v;
   }
   __syncthreads();
+  __shared__ float s_tot[5];
   if (tid < 5) {
     float v = 0.f;
     for (int w = 0; w < 32; ++w) v += s_red[w][tid];
+    s_tot[tid] = v;
     a.step_stats[tid] = v;
     if (a.stats) a.stats[tid] += v;
+  }
+  __syncthreads();
+  if (tid == 0 && a.stats) {
+    // Keras running means: loss = Mean(batch loss, weight = batch size); masked_accuracy = Mean over batches
+    const float nv = fmaxf(s_tot[1], 1.f);
+    a.stats[5] += (s_tot[0] / nv) * (float)a.batch;
+    a.stats[6] += (float)a.batch;
+    a.stats[7] += s_tot[2] / nv;
+    a.stats[8] += 1.f;
   }
 }
 
@@ -462,7 +473,7 @@ static CeDev to_dev(const CeArgs& a) {
   CeDev d;
   d.t = a.t; d.ldt = a.ldt; d.E = a.E; d.vbias = a.vbias; d.labels = a.labels; d.row_w = a.row_w; d.row_mult = a.row_mult;
   d.d_counts = a.d_counts; d.M_cap = a.M_cap; d.V = a.V; d.v_begin = a.v_begin; d.v_end = a.v_end;
-  d.vsplits = a.vsplits > 0 ? a.vsplits : 1;
+  d.vsplits = a.vsplits > 0 ? a.vsplits : 1; d.batch = a.batch;
   d.part = a.part; d.lse = a.lse; d.lab_out = a.lab_out; d.stats = a.stats; d.step_stats = a.step_stats; d.dlogits = a.dlogits; d.ld_dl = a.ld_dl;
   d.row_begin = a.row_begin; d.row_count = a.row_count;
   return d;

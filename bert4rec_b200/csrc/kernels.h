@@ -152,10 +152,12 @@ struct CeArgs {
   int M_cap, H, V;
   int v_begin, v_end;                // vocabulary shard handled here (whole vocab: 0, V)
   int vsplits;
+  int batch;                         // batch size (weight of the per-batch loss in the running mean)
   float* part;                       // [vsplits][M_cap][6] partial (max, sum, label_logit, best_val, best_idx, unused)
   float* lse;                        // [M_cap]
   float* lab_out;                    // optional [M_cap]: logit of the label column (ground-truth score)
-  float* stats;                      // accumulators: {loss_sum, n_valid, n_correct_masked, n_correct_all, n_all}
+  float* stats;                      // optional float[16] running accumulators: {loss_sum, n_valid, n_correct_masked,
+                                     // n_correct_all, n_all, sum(batch_loss*batch), sum(batch), sum(batch_masked_acc), n_steps}
   float* step_stats;                 // this step only (same layout)
   // backward
   bf16* dlogits; int ld_dl;          // [rows_chunk][Vp]

@@ -229,8 +229,8 @@ class Session:
     def transform(self):
         check(self.lib.b4r_mlm_transform(self.h, _stream()))
 
-    def loss(self):
-        check(self.lib.b4r_mlm_loss(self.h, _stream()))
+    def loss(self, stats=None):
+        check(self.lib.b4r_mlm_loss(self.h, _ptr(stats), _stream()))
 
     def logits(self, n_rows):
         out = torch.empty(n_rows, self.store.V, dtype=torch.float32, device=self.store.device)
@@ -282,9 +282,6 @@ class Session:
     def rows(self):
         return self._view(self.lib.b4r_mlm_rows(self.h), (self.Mcap,), torch.int32)
 
-    def stats(self):
-        return self._view(self.lib.b4r_stats(self.h), (8,), torch.float32)
-
     def step_stats(self):
         return self._view(self.lib.b4r_step_stats(self.h), (8,), torch.float32)
 
@@ -300,6 +297,19 @@ class Session:
 
     def launch_count(self):
         return self.lib.b4r_launch_count(self.h)
+
+    def profile(self, on=True):
+        check(self.lib.b4r_profile_enable(self.h, int(on)))
+
+    def profile_report(self):
+        """{tag: (count, total_ms)} of every kernel launched through the session since profiling was enabled."""
+        buf = C.create_string_buffer(1 << 16)
+        check(self.lib.b4r_profile_report(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            tag, cnt, ms = line.rsplit(" ", 2)
+            out[tag] = (int(cnt), float(ms))
+        return out
 
 
 def dropout_keep_mask(rows, cols, rate, seed, site, layer, step, device):

@@ -1,0 +1,430 @@
+"""BERT4RecModel on the B200 path: encoder + tied-embedding masked-item head, custom train/test step, ranking.
+
+Mirrors the reference's ``BERT4RecModel`` (bert4rec/models/bert4rec_model.py:27-240): same constructor, same batch
+dict keys (:15-22), same output dict keys (:117-149), ``compile`` / ``train_step`` / ``test_step`` / ``fit`` /
+``rank_items``.  Differences that follow from the B200 design: the [B,P,V] logits are only materialised
+when ``__call__`` is asked for them; ``train_step`` never builds them (fused projection + softmax-CE), keeps the
+running metrics on the device and returns a lazy mapping (reading a value synchronises); ``rank_items`` scores only
+the candidate ids (fused gather-dot) instead of the whole vocabulary.
+"""
+import collections.abc
+import copy
+import ctypes as C
+import pathlib
+import time
+
+import numpy as np
+import torch
+
+from bert4rec_b200 import _lib
+from bert4rec_b200.models.components import networks
+
+_ENCODER_CONFIG_FILE_NAME = "encoder_config.json"
+_META_CONFIG_FILE_NAME = "meta_config.json"
+_TOKENIZER_VOCAB_FILE_NAME = "vocab.txt"
+_MODEL_WEIGHTS_FILES_PREFIX = "model_weights"
+
+# PAD, MASK, UNK -- BERT4RecDataloader(0, 0)._SPECIAL_TOKEN_IDS in the reference (bert4rec_dataloader.py:35-43)
+SPECIAL_TOKEN_IDS = [0, 1, 2]
+BATCH_KEYS = ("labels", "input_word_ids", "input_mask", "masked_lm_ids", "masked_lm_positions", "masked_lm_weights")
+_STAGED_KEYS = ("input_word_ids", "input_mask", "masked_lm_positions", "masked_lm_ids", "masked_lm_weights")
+
+
+class History:
+    """keras.callbacks.History stand-in: ``history`` maps metric name -> list of per-epoch values."""
+
+    def __init__(self):
+        self.history = {}
+        self.epoch = []
+        self.params = {}
+
+    def _append(self, epoch, logs):
+        self.epoch.append(epoch)
+        for k, v in logs.items():
+            self.history.setdefault(k, []).append(v)
+
+
+class StepMetrics(collections.abc.Mapping):
+    """Lazy view of the device-side running metrics (Keras ``{m.name: m.result()}``, bert4rec_model.py:173).
+    Values are read from the device (one small D2H copy, synchronising) on first access."""
+
+    def __init__(self, stats, names):
+        self._stats, self._names, self._cache = stats, names, None
+
+    def _load(self):
+        if self._cache is None:
+            s = self._stats.detach().cpu().tolist()
+            vals = {"loss": s[5] / s[6] if s[6] else 0.0,
+                    "sparse_categorical_accuracy": s[3] / s[4] if s[4] else 0.0,
+                    "masked_accuracy": s[7] / s[8] if s[8] else 0.0}
+            self._cache = {k: vals[k] for k in self._names}
+        return self._cache
+
+    def __getitem__(self, k):
+        return self._load()[k]
+
+    def __iter__(self):
+        return iter(self._names)
+
+    def __len__(self):
+        return len(self._names)
+
+    def __repr__(self):
+        return repr(self._load())
+
+
+class BERT4RecModel:
+    def __init__(self,
+                 encoder: networks.Bert4RecEncoder,
+                 customized_masked_lm=None,
+                 mlm_activation="gelu",
+                 mlm_initializer="glorot_uniform",
+                 name: str = "bert4rec",
+                 special_token_ids: list = SPECIAL_TOKEN_IDS,
+                 **kwargs):
+        if customized_masked_lm is not None:
+            raise NotImplementedError("customized_masked_lm: only the tied-embedding MaskedLM head is implemented")
+        if mlm_activation != "gelu":
+            raise NotImplementedError("mlm_activation: only exact-erf 'gelu'")
+        self.name = name
+        self._config = {"encoder": encoder, "customized_masked_lm": customized_masked_lm,
+                        "mlm_activation": mlm_activation, "mlm_initializer": mlm_initializer, "name": name}
+        self.encoder = encoder
+        self.store = encoder.store
+        self.vocab_size = encoder.get_config()["vocab_size"]
+        self.prediction_mask = None  # the reference builds a special-token mask and then disables it (:101-102)
+        self.inputs = dict(encoder.inputs, masked_lm_positions=None)
+        self.optimizer = None
+        self.loss = None
+        self.compiled_metrics = None
+        self._metric_names = ("loss",)
+        self._want_sca = False
+        self._stats = {}
+        self._staging = {}
+        self._seed = 0x5EEDB4A7
+        self._host_step = 0
+        self.stop_training = False
+        self.distributed = False
+        self._timers = None
+
+    @property
+    def identifier(self):
+        return "bert4rec"
+
+    @property
+    def device(self):
+        return self.store.device
+
+    # ------------------------------------------------------------------ input staging
+    def _stage(self, inputs, keys):
+        """Moves the int64 input tensors named by ``keys`` to the device.  Host tensors are packed into ONE pinned
+        staging buffer and copied with a single async H2D copy; device tensors are used in place."""
+        vals = [inputs[k] for k in keys]
+        if all(torch.is_tensor(v) and v.is_cuda for v in vals):
+            return {k: (v if v.dtype == torch.int64 and v.is_contiguous() else v.to(torch.int64).contiguous())
+                    for k, v in zip(keys, vals)}
+        arrs = [torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v).to(torch.int64).reshape(-1).cpu()
+                if not (torch.is_tensor(v) and v.dtype == torch.int64 and not v.is_cuda) else v.reshape(-1)
+                for v in vals]
+        shapes = [tuple(torch.as_tensor(v).shape) if not torch.is_tensor(v) else tuple(v.shape) for v in vals]
+        sizes = [a.numel() for a in arrs]
+        total = sum(sizes)
+        key = (keys, tuple(shapes))
+        st = self._staging.get(key)
+        if st is None:
+            host = torch.empty(total, dtype=torch.int64).pin_memory()
+            dev = torch.empty(total, dtype=torch.int64, device=self.device)
+            st = self._staging[key] = (host, dev)
+        host, dev = st
+        off = 0
+        for a, n in zip(arrs, sizes):
+            host[off:off + n].copy_(a)
+            off += n
+        dev.copy_(host, non_blocking=True)
+        out, off = {}, 0
+        for k, shp, n in zip(keys, shapes, sizes):
+            out[k] = dev[off:off + n].view(shp)
+            off += n
+        return out
+
+    @staticmethod
+    def _bytes_of(keys, inputs):
+        return sum(int(np.prod(tuple(inputs[k].shape))) * 8 for k in keys)
+
+    # ------------------------------------------------------------------ forward (API parity)
+    def __call__(self, inputs, training=None, mask=None):
+        return self.call(inputs, training=training, mask=mask)
+
+    def call(self, inputs, training=None, mask=None):
+        if isinstance(inputs, (list, tuple)):
+            names = ["input_word_ids", "input_mask", "masked_lm_positions"]
+            inputs = dict(zip(names, inputs))
+        if not isinstance(inputs, dict):
+            raise ValueError("inputs should be a dict with keys input_word_ids, input_mask[, masked_lm_positions]")
+        keys = ("input_word_ids", "input_mask") + (("masked_lm_positions",) if "masked_lm_positions" in inputs else ())
+        d = self._stage(inputs, keys)
+        B, S = d["input_word_ids"].shape
+        P = d["masked_lm_positions"].shape[1] if "masked_lm_positions" in d else 0
+        sess = self.store.session(B, S, P)
+        sess.encode(d["input_word_ids"], d["input_mask"], training=bool(training),
+                    seed=self._seed, step=self._host_step)
+        L = self.store.L
+        outs = [sess.sequence_output(l).float() for l in range(L)]
+        outputs = dict(sequence_output=outs[-1], pooled_output=sess.pooled_output(), encoder_outputs=outs)
+        if P:
+            sess.select(d["masked_lm_positions"], None, None, mode=2)
+            sess.transform()
+            outputs["mlm_logits"] = sess.logits(B * P).view(B, P, self.vocab_size)
+        return outputs
+
+    # ------------------------------------------------------------------ compile / steps
+    def compile(self, optimizer=None, loss=None, metrics=None, **kwargs):
+        from bert4rec_b200.trainers import optimizers as _opt, trainer_utils
+        if optimizer is None or isinstance(optimizer, str):
+            optimizer = _opt.get(optimizer or "adamw")
+        if not isinstance(optimizer, _opt.AdamWeightDecay):
+            raise NotImplementedError("only the AdamWeightDecay optimizer is implemented on the B200 path")
+        if loss is None:
+            loss = trainer_utils.MaskedSparseCategoricalCrossentropy()
+        if not isinstance(loss, trainer_utils.MaskedSparseCategoricalCrossentropy) or loss.pad_token != 0:
+            raise NotImplementedError("only MaskedSparseCategoricalCrossentropy(pad_token=0) is fused into the step")
+        names = ["loss"]
+        for m in (metrics or []):
+            n = getattr(m, "name", None) or getattr(m, "__name__", None) or str(m)
+            if n in ("sparse_categorical_accuracy", "masked_accuracy"):
+                names.append(n)
+            else:
+                raise NotImplementedError(f"metric {n!r} is not computed by the fused step")
+        groups = {k: (2 if k.startswith("pooler_transform") else (0 if k.endswith(("kernel", "embeddings")) else 1))
+                  for k in self.store.tf_views()}
+        optimizer.check_layout(groups)
+        self.optimizer, self.loss, self.compiled_metrics = optimizer, loss, list(metrics or [])
+        self._metric_names = tuple(names)
+        self._want_sca = "sparse_categorical_accuracy" in names
+        self.store.ensure_training_buffers()
+        self._hp = optimizer.hparams_struct()
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            self.distributed = True
+            self._count = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    @property
+    def metrics_names(self):
+        return list(self._metric_names)
+
+    def _stats_buf(self, phase):
+        b = self._stats.get(phase)
+        if b is None:
+            b = self._stats[phase] = torch.zeros(16, dtype=torch.float32, device=self.device)
+        return b
+
+    def reset_metrics(self, phase=None):
+        for k, b in self._stats.items():
+            if phase is None or k == phase:
+                b.zero_()
+
+    def train_step(self, inputs):
+        """fwd(training) -> fused CE -> backward -> [NCCL allreduce] -> clip + AdamW (bert4rec_model.py:151-173)."""
+        if self.optimizer is None:
+            raise RuntimeError("compile() the model (or trainer.initialize_model()) before train_step")
+        d = self._stage(inputs, _STAGED_KEYS)
+        B, S = d["input_word_ids"].shape
+        P = d["masked_lm_positions"].shape[1]
+        sess = self.store.session(B, S, P)
+        step = self._host_step
+        self._host_step += 1
+        stats = self._stats_buf("train")
+        sess.encode(d["input_word_ids"], d["input_mask"], training=True, seed=self._seed, step=step)
+        sess.select(d["masked_lm_positions"], d["masked_lm_ids"], d["masked_lm_weights"], mode=0, want_aux=self._want_sca)
+        sess.transform()
+        sess.loss(stats)
+        sess.backward(seed=self._seed, step=step)
+        count = sess.step_stats()[1:2]
+        scale = 1.0
+        if self.distributed:
+            # batch data-parallel: SUM gradients of the SUM loss and the valid-slot counts over ranks (NCCL), so that
+            # the normaliser is the GLOBAL number of valid masked slots (trainer_utils.py:22)
+            self._count.copy_(count)
+            torch.distributed.all_reduce(self.store.grads[: self.store.n_trainable])
+            torch.distributed.all_reduce(self._count)
+            count = self._count
+        self.store.adamw_step(self._hp, count=count, grad_scale=scale)
+        return StepMetrics(stats, self._metric_names)
+
+    def test_step(self, inputs):
+        """fwd(inference) -> fused CE + accuracies, no update (bert4rec_model.py:175-192)."""
+        d = self._stage(inputs, _STAGED_KEYS)
+        B, S = d["input_word_ids"].shape
+        P = d["masked_lm_positions"].shape[1]
+        sess = self.store.session(B, S, P)
+        stats = self._stats_buf("test")
+        sess.encode(d["input_word_ids"], d["input_mask"], training=False)
+        sess.select(d["masked_lm_positions"], d["masked_lm_ids"], d["masked_lm_weights"], mode=0, want_aux=self._want_sca)
+        sess.transform()
+        sess.loss(stats)
+        return StepMetrics(stats, self._metric_names)
+
+    def evaluate(self, x, steps=None, return_dict=True):
+        self.reset_metrics("test")
+        res = None
+        for i, batch in enumerate(x):
+            if steps is not None and i >= steps:
+                break
+            res = self.test_step(batch)
+        out = dict(res) if res is not None else {}
+        return out if return_dict else [out[k] for k in self._metric_names]
+
+    def fit(self, x=None, validation_data=None, epochs=1, callbacks=None, steps_per_epoch=None,
+            validation_steps=None, verbose=0, initial_epoch=0, **kwargs):
+        """Minimal keras ``Model.fit``: per epoch reset metrics, run train_step over ``x``, evaluate
+        ``validation_data`` (metrics prefixed ``val_``), call the callbacks, return a History."""
+        history = History()
+        callbacks = list(callbacks or [])
+        for cb in callbacks:
+            if hasattr(cb, "set_model"):
+                cb.set_model(self)
+        self.stop_training = False
+        for cb in callbacks:
+            getattr(cb, "on_train_begin", lambda logs=None: None)()
+        for epoch in range(initial_epoch, epochs):
+            for cb in callbacks:
+                getattr(cb, "on_epoch_begin", lambda e, logs=None: None)(epoch)
+            self.reset_metrics("train")
+            t0 = time.time()
+            last, n = None, 0
+            for i, batch in enumerate(x):
+                if steps_per_epoch is not None and i >= steps_per_epoch:
+                    break
+                last = self.train_step(batch)
+                n += 1
+            logs = dict(last) if last is not None else {}
+            if validation_data is not None:
+                val = self.evaluate(validation_data, steps=validation_steps)
+                logs.update({f"val_{k}": v for k, v in val.items()})
+            history._append(epoch, logs)
+            if verbose:
+                print(f"Epoch {epoch + 1}/{epochs} - {n} steps - {time.time() - t0:.2f}s - "
+                      + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()), flush=True)
+            for cb in callbacks:
+                getattr(cb, "on_epoch_end", lambda e, logs=None: None)(epoch, logs)
+            if self.stop_training:
+                break
+        for cb in callbacks:
+            getattr(cb, "on_train_end", lambda logs=None: None)()
+        self.history = history
+        return history
+
+    # ------------------------------------------------------------------ ranking
+    def _encode_for_ranking(self, encoder_input):
+        keys = ("input_word_ids", "input_mask", "masked_lm_positions") + \
+               (("masked_lm_weights",) if "masked_lm_weights" in encoder_input else ())
+        d = self._stage(encoder_input, keys)
+        B, S = d["input_word_ids"].shape
+        P = d["masked_lm_positions"].shape[1]
+        sess = self.store.session(B, S, P)
+        sess.encode(d["input_word_ids"], d["input_mask"], training=False)
+        if "masked_lm_weights" in d:
+            sess.select(d["masked_lm_positions"], None, d["masked_lm_weights"], mode=1)
+        else:
+            sess.select(d["masked_lm_positions"], None, None, mode=2)
+        sess.transform()
+        return sess, d
+
+    def rank_candidates(self, encoder_input, candidates, ground_truth=None, want_ranking=False, hist=None):
+        """Fast path of ``rank_items`` for rectangular candidate lists: ``candidates`` int64 [n_slots, C] (row order =
+        row-major order of the slots with weight 1), ``ground_truth`` int64 [n_slots].  Returns (ranking or None,
+        ranks int32 [n_slots]) as device tensors."""
+        sess, _ = self._encode_for_ranking(encoder_input)
+        cand = torch.as_tensor(candidates)
+        if not cand.is_cuda:
+            cand = cand.to(torch.int64).pin_memory().to(self.device, non_blocking=True)
+        gt = None
+        if ground_truth is not None:
+            gt = torch.as_tensor(ground_truth)
+            if not gt.is_cuda:
+                gt = gt.to(torch.int64).pin_memory().to(self.device, non_blocking=True)
+        ranking, _, rank = sess.rank_candidates(cand.contiguous(), gt, want_ranking=want_ranking, hist=hist)
+        return ranking, rank
+
+    def rank_items(self, encoder_input: dict, items: list = None):
+        """Reference semantics (bert4rec_model.py:203-240): one ranking per slot whose ``masked_lm_weights`` is 1;
+        with ``items`` (list per sequence of list per slot of candidate ids) the candidates sorted by descending
+        logit (stable: lower list index first on ties); without, the whole vocabulary sorted by logit."""
+        sess, d = self._encode_for_ranking(encoder_input)
+        B = d["input_word_ids"].shape[0]
+        counts = sess.counts().cpu()
+        n = int(counts[0])
+        if "masked_lm_weights" in d:
+            per_seq = (d["masked_lm_weights"] != 0).sum(1).cpu().tolist()
+        else:
+            per_seq = [d["masked_lm_positions"].shape[1]] * B
+        flat_rankings = [None] * n
+        if items is not None and len(items) and type(items[0]) is list:
+            flat = [items[b][j] for b in range(B) for j in range(per_seq[b])]
+            by_len = {}
+            for i, lst in enumerate(flat):
+                by_len.setdefault(len(lst), []).append(i)
+            hidden = sess.mlm_hidden()
+            for Cn, idxs in by_len.items():
+                cand = torch.tensor([flat[i] for i in idxs], dtype=torch.int64)
+                if len(idxs) == n:
+                    ranking, _, _ = sess.rank_candidates(cand.to(self.device), None, want_ranking=True)
+                else:  # ragged candidate lists: score each length group on a compacted copy of the hidden rows
+                    ranking = self._rank_rows(sess, hidden, idxs, cand)
+                ranking = ranking.cpu()
+                for r, i in enumerate(idxs):
+                    flat_rankings[i] = ranking[r]
+        else:
+            order = self._full_ranking(sess, n)
+            for i in range(n):
+                flat_rankings[i] = order[i]
+        out, k = [], 0
+        for b in range(B):
+            out.append(flat_rankings[k:k + per_seq[b]])
+            k += per_seq[b]
+        return out
+
+    def _rank_rows(self, sess, hidden, idxs, cand):
+        sel = torch.tensor(idxs, device=self.device)
+        saved = hidden[: len(idxs)].clone()
+        hidden[: len(idxs)] = hidden[sel]
+        ranking, _, _ = sess.rank_candidates(cand.to(self.device), None, want_ranking=True)
+        hidden[: len(idxs)] = saved
+        return ranking
+
+    def _full_ranking(self, sess, n):
+        """items=None: argsort of the whole vocabulary per slot.  Off the measured path: materialises the logits with
+        the GEMM kernel and orders them with a stable descending sort on the device."""
+        logits = sess.logits(n)
+        return torch.sort(logits, dim=-1, descending=True, stable=True).indices.cpu()
+
+    # ------------------------------------------------------------------ config / weights
+    def get_config(self):
+        return dict(self._config)
+
+    @classmethod
+    def from_config(cls, config, custom_object=None):
+        return cls(**config)
+
+    def state_dict(self):
+        return self.store.state_dict()
+
+    def load_state_dict(self, sd):
+        self.store.load_state_dict(sd)
+
+    def save_weights(self, path):
+        path = pathlib.Path(str(path))
+        path.parent.mkdir(parents=True, exist_ok=True)
+        target = path if path.suffix == ".npz" else path.with_name(path.name + ".npz")
+        np.savez(target, **{k: v.numpy() for k, v in self.state_dict().items()})
+        return target
+
+    def load_weights(self, path):
+        path = pathlib.Path(str(path))
+        target = path if path.suffix == ".npz" else path.with_name(path.name + ".npz")
+        with np.load(target) as z:
+            self.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files})
+        return self
+
+    @property
+    def trainable_variables(self):
+        return [v for k, v in self.store.tf_views().items() if not k.startswith("pooler_transform")]

@@ -69,8 +69,10 @@ int b4r_mlm_select(b4r_session* s, const int64_t* masked_lm_positions, const int
                    const int64_t* masked_lm_weights, int mode, int want_aux, void* stream);
 /* MaskedLM transform (dense+gelu+LayerNorm) on the selected rows. */
 int b4r_mlm_transform(b4r_session* s, void* stream);
-/* tied projection x online-softmax CE + accuracies (trainer_utils.py:12-23,49-60). Accumulates into stats. */
-int b4r_mlm_loss(b4r_session* s, void* stream);
+/* tied projection x online-softmax CE + accuracies (trainer_utils.py:12-23,49-60).  stats: optional device float[16]
+ * of running accumulators {loss_sum, n_valid, correct_masked, correct_all, n_all, sum(batch_loss*batch), sum(batch),
+ * sum(batch_masked_accuracy), n_steps} (the Keras Mean metrics of train_step, bert4rec_model.py:171-173). */
+int b4r_mlm_loss(b4r_session* s, float* stats, void* stream);
 /* materialised logits [n_rows, vocab] fp32 for BERT4RecModel.call()'s "mlm_logits" (bert4rec_model.py:139-147) */
 int b4r_mlm_logits(b4r_session* s, float* out, void* stream);
 /* tape.gradient of the SUM loss over all trainable variables (bert4rec_model.py:166-167) -> grads (flat, fp32). */
@@ -105,10 +107,13 @@ const void* b4r_sequence_output(b4r_session* s, int layer);  /* bf16 [batch*seq_
 const void* b4r_mlm_hidden(b4r_session* s);                  /* bf16 [n_rows, hidden] transformed rows */
 const int32_t* b4r_mlm_counts(b4r_session* s);               /* int32[2] = {n_valid, n_rows} */
 const int32_t* b4r_mlm_rows(b4r_session* s);                 /* int32 [n_rows] flat row index b*seq_len+pos */
-float* b4r_stats(b4r_session* s);       /* float[8] running {loss_sum, n_valid, correct_masked, correct_all, n_all} */
-float* b4r_step_stats(b4r_session* s);  /* float[8] same, last step only */
+float* b4r_step_stats(b4r_session* s);  /* float[8] {loss_sum, n_valid, correct_masked, correct_all, n_all} of the last step */
 const uint64_t* b4r_attn_keep_bits(b4r_session* s, int layer, int* words_per_row);
 int b4r_launch_count(b4r_session* s);   /* kernels launched through this session so far */
+/* per-kernel CUDA-event timing of everything launched through the session (events on the launching stream);
+ * report: lines "tag count total_ms", synchronises, clears the records. */
+int b4r_profile_enable(b4r_session* s, int on);
+int b4r_profile_report(b4r_session* s, char* buf, int cap);
 
 /* ---- test helpers ------------------------------------------------------------------------------------------ */
 /* keep mask (1 byte / element) of an elementwise dropout site: site 1 = embedding, 2 = attention output, 3 = FFN output */
