@@ -214,6 +214,14 @@ def run_b200(args, w):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # launches per step: counted once on an eager (non-graph) step; a graph replay re-issues the same kernels
+    model.use_cuda_graph = False
+    model.train_step(dev_batches[0])
+    l_a = sess.launch_count()
+    model.train_step(dev_batches[0])
+    launches_per_step = sess.launch_count() - l_a + 2   # + sqnorm and adamw kernels
+    model.use_cuda_graph = not args.no_graph
+
     def timed(batches, read_loss):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         for i in range(args.warmup):
@@ -221,7 +229,6 @@ def run_b200(args, w):
             if read_loss:
                 _ = r["loss"]
         barrier()
-        l0 = sess.launch_count()
         for i in range(args.steps):
             flush.fill_(i & 0xFF)  # L2 flush between timed steps (untimed)
             ev[i][0].record()
@@ -230,7 +237,7 @@ def run_b200(args, w):
                 _ = r["loss"]  # D2H read of the running loss (synchronises)
             ev[i][1].record()
         barrier()
-        launches = sess.launch_count() - l0 + 2 * args.steps  # + sqnorm and adamw kernels per step
+        launches = launches_per_step * args.steps
         total_ms = sum(a.elapsed_time(b) for a, b in ev)
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -292,7 +299,8 @@ def run_b200(args, w):
             "config": {"workload": w["name"], **{k: w[k] for k in ENC_KEYS}, "batch_per_gpu": B, "seq_len": S,
                        "max_pred": P, "mask_prob": w["mask_prob"], "valid_masked_slots_per_batch": m_valid,
                        "sequences": "dense (full length), Zipf(1.1) item ids", "parallelism": f"dp{world}",
-                       "l2": "256 MiB buffer written between timed steps (untimed); per-step CUDA events summed"},
+                       "l2": "256 MiB buffer written between timed steps (untimed); per-step CUDA events summed",
+                       "cuda_graph": not args.no_graph},
             "e2e": {"value": e2e_value, "unit": "seq/s",
                     "h2d_bytes_per_step": BERT4RecModel._bytes_of(("input_word_ids", "input_mask", "masked_lm_positions", "masked_lm_ids", "masked_lm_weights"), host_batches[0]),
                     "d2h_bytes_per_step": 64},
@@ -352,6 +360,7 @@ def roofline_block(model, sess, w, dev_batches, args, hbm, tf_burst, src):
     import torch
     n = max(args.steps, 10)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_batches[0]["input_word_ids"].device)
+    model.use_cuda_graph = False   # per-launch events cannot be recorded inside a graph replay
     for i in range(3):
         model.train_step(dev_batches[i % len(dev_batches)])
     torch.cuda.synchronize()
@@ -361,6 +370,7 @@ def roofline_block(model, sess, w, dev_batches, args, hbm, tf_burst, src):
         model.train_step(dev_batches[i % len(dev_batches)])
     rep = sess.profile_report()
     sess.profile(False)
+    model.use_cuda_graph = True
     n_rows = int(sess.counts()[1])
     rows = sorted(((tag, cnt, tot) for tag, (cnt, tot) in rep.items()), key=lambda r: -r[2])
     total = sum(r[2] for r in rows)
@@ -390,6 +400,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

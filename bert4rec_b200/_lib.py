@@ -47,12 +47,12 @@ _SIGNATURES = {
     "b4r_session_create": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_size_t, C.POINTER(_P)]),
     "b4r_session_destroy": (None, [_P]),
     "b4r_sync_shadow": (C.c_int, [_P, _P]),
-    "b4r_encode": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint64, C.c_uint32, _P]),
+    "b4r_encode": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint64, C.c_uint32, _P, _P]),
     "b4r_mlm_select": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "b4r_mlm_transform": (C.c_int, [_P, _P]),
     "b4r_mlm_loss": (C.c_int, [_P, _P, _P]),
     "b4r_mlm_logits": (C.c_int, [_P, _P, _P]),
-    "b4r_backward": (C.c_int, [_P, C.c_uint64, C.c_uint32, _P]),
+    "b4r_backward": (C.c_int, [_P, C.c_uint64, C.c_uint32, _P, _P]),
     "b4r_pooled_output": (C.c_int, [_P, _P, _P]),
     "b4r_adamw_scratch_floats": (C.c_size_t, []),
     "b4r_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.POINTER(AdamWHParams), _P, C.c_float, _P, _P, _P, _P]),

@@ -196,6 +196,7 @@ struct b4r_session {
   std::vector<ProfRec> prof;
 };
 
+static const int kColsumSplits = 64;
 static int wgrad_splits(int M, int N, int T) {
   int tiles = ((M + 63) / 64) * ((N + 63) / 64);
   int s = (2 * 148 + tiles - 1) / tiles;
@@ -244,7 +245,7 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
     L.p_ln2 = b.take<float>((size_t)ln_parts * 3 * H);
     L.p_ln1 = b.take<float>((size_t)ln_parts * 3 * H);
     L.p_b1 = b.take<float>((size_t)mt128 * I);
-    L.p_bqkv = b.take<float>((size_t)8 * 3 * H);
+    L.p_bqkv = b.take<float>((size_t)kColsumSplits * 3 * H);
     job(L.p_wqkv, L.wqkv, L.s_wqkv, H * 3 * H, (long long)H * 3 * H);
     job(L.p_wo, L.wo, L.s_wo, H * H, (long long)H * H);
     job(L.p_w1, L.w1, L.s_w1, H * I, (long long)H * I);
@@ -256,7 +257,7 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
     job(L.p_ln1 + H, L.be1, ln_parts, H, 3 * H);
     job(L.p_ln1 + 2 * H, L.bo, ln_parts, H, 3 * H);
     job(L.p_b1, L.b1, mt128, I, I);
-    job(L.p_bqkv, L.bqkv, 8, 3 * H, 3 * H);
+    job(L.p_bqkv, L.bqkv, kColsumSplits, 3 * H, 3 * H);
   }
   // head
   s->rows = b.take<int>(Mcap); s->labels = b.take<int>(Mcap); s->row_mult = b.take<int>(Mcap);
@@ -298,7 +299,7 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
   s->p_head_ln = b.take<float>((size_t)head_parts * 3 * H);
   s->s_wt = wgrad_splits(H, H, Mcap);
   s->p_wt = b.take<float>((size_t)s->s_wt * H * H);
-  s->vb_splits = 8;
+  s->vb_splits = 16;
   s->p_vbias = b.take<float>((size_t)s->vb_splits * V);
   job(s->p_head_ln, off("head/ln/gamma"), head_parts, H, 3 * H);
   job(s->p_head_ln + H, off("head/ln/beta"), head_parts, H, 3 * H);
@@ -391,7 +392,8 @@ extern "C" int b4r_sync_shadow(b4r_session* s, void* stream) {
 
 // ------------------------------------------------------------------------------------------------ forward
 extern "C" int b4r_encode(b4r_session* s, const int64_t* ids, const int64_t* mask, int training, uint64_t seed,
-                          uint32_t step, void* stream) {
+                          uint32_t step, const int64_t* step_counter, void* stream) {
+  const long long* d_step = reinterpret_cast<const long long*>(step_counter);
   if (!s || !ids || !mask) return fail("null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int T = s->T, H = s->H, I = s->I;
@@ -401,7 +403,7 @@ extern "C" int b4r_encode(b4r_session* s, const int64_t* ids, const int64_t* mas
   s->ids = ids; s->mask = mask;
   KL("embed_ln_fwd", launch_embed_ln_fwd(ids, W + s->lay.find("word_embeddings"), W + s->lay.find("position_embedding"),
                          P + s->lay.find("emb_ln/gamma"), P + s->lay.find("emb_ln/beta"), s->x0, s->B, s->S, H, s->V, od,
-                         seed, step, st));
+                         seed, step, d_step, st));
   const bf16* x = s->x0;
   for (int l = 0; l < s->cfg.num_layers; ++l) {
     LayerBuf& L = s->layers[l];
@@ -411,12 +413,12 @@ extern "C" int b4r_encode(b4r_session* s, const int64_t* ids, const int64_t* mas
     KL("gemm:qkv", launch_gemm(EPI_BIAS_BF16, g, st));
     AttnArgs a{};
     a.qkv = L.qkv; a.mask = mask; a.ctx = L.ctx; a.lse = L.lse; a.keep_bits = L.keep; a.B = s->B; a.S = s->S; a.H = H; a.N = s->N;
-    a.drop_rate = ad; a.seed = seed; a.site = site_id(SITE_ATTN_PROBS, l); a.step = step;
+    a.drop_rate = ad; a.seed = seed; a.site = site_id(SITE_ATTN_PROBS, l); a.step = step; a.d_step = d_step;
     KL("attn_fwd", launch_attn_fwd(a, st));
     RowLnArgs r{};
     r.A = L.ctx; r.lda = H; r.W = W + L.wo; r.M = T; r.K = H; r.H = H; r.bias = P + L.bo; r.gamma = P + L.g1; r.beta = P + L.be1;
     r.residual = x; r.pre = L.a_pre; r.y = L.y; r.mean = L.mean1; r.rstd = L.rstd1;
-    r.drop_rate = od; r.seed = seed; r.site = site_id(SITE_ATTN_OUT, l); r.step = step;
+    r.drop_rate = od; r.seed = seed; r.site = site_id(SITE_ATTN_OUT, l); r.step = step; r.d_step = d_step;
     KL("rowln:attn_out", launch_gemm_rowln(ROW_RES_DROP_LN, r, st));
     GemmArgs f{};
     f.A = L.y; f.lda = H; f.B = W + L.w1; f.ldb = I; f.b_trans = true; f.M = T; f.N = I; f.K = H;
@@ -425,7 +427,7 @@ extern "C" int b4r_encode(b4r_session* s, const int64_t* ids, const int64_t* mas
     RowLnArgs r2{};
     r2.A = L.h; r2.lda = I; r2.W = W + L.w2; r2.M = T; r2.K = I; r2.H = H; r2.bias = P + L.b2; r2.gamma = P + L.g2; r2.beta = P + L.be2;
     r2.residual = L.y; r2.pre = L.o_pre; r2.y = L.out; r2.mean = L.mean2; r2.rstd = L.rstd2;
-    r2.drop_rate = od; r2.seed = seed; r2.site = site_id(SITE_FFN_OUT, l); r2.step = step;
+    r2.drop_rate = od; r2.seed = seed; r2.site = site_id(SITE_FFN_OUT, l); r2.step = step; r2.d_step = d_step;
     KL("rowln:ffn2", launch_gemm_rowln(ROW_RES_DROP_LN, r2, st));
     x = L.out;
   }
@@ -497,7 +499,8 @@ extern "C" int b4r_mlm_logits(b4r_session* s, float* out, void* stream) {
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, void* stream) {
+extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const int64_t* step_counter, void* stream) {
+  const long long* d_step = reinterpret_cast<const long long*>(step_counter);
   if (!s || !s->grads) return fail("session has no gradient buffer");
   if (!s->ids) return fail("b4r_encode must run before b4r_backward");
   cudaStream_t st = (cudaStream_t)stream;
@@ -549,7 +552,7 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, void* 
     LayerBuf& L = s->layers[l];
     const bf16* x_in = l == 0 ? s->x0 : s->layers[l - 1].out;
     KL("ln_bwd", launch_ln_bwd(s->dxa, L.o_pre, L.mean2, L.rstd2, P + L.g2, s->dxb, s->d_branch, L.p_ln2, T, H, od, seed,
-                     site_id(SITE_FFN_OUT, l), step, st));
+                     site_id(SITE_FFN_OUT, l), step, d_step, st));
     {
       WgradArgs w{};
       w.X = L.h; w.ldx = I; w.dY = s->d_branch; w.ldy = H; w.M = I; w.N = H; w.T = T; w.splits = L.s_w2;
@@ -575,7 +578,7 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, void* 
       KL("gemm:ffn1_dgrad", launch_gemm(EPI_F32_RES, g, st));
     }
     KL("ln_bwd", launch_ln_bwd(s->dxa, L.a_pre, L.mean1, L.rstd1, P + L.g1, s->dxb, s->d_branch, L.p_ln1, T, H, od, seed,
-                     site_id(SITE_ATTN_OUT, l), step, st));
+                     site_id(SITE_ATTN_OUT, l), step, d_step, st));
     {
       WgradArgs w{};
       w.X = L.ctx; w.ldx = H; w.dY = s->d_branch; w.ldy = H; w.M = H; w.N = H; w.T = T; w.splits = L.s_wo;
@@ -594,7 +597,7 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, void* 
       a.drop_rate = s->cfg.attention_dropout; a.dctx = s->dctx; a.dqkv = s->dqkv;
       KL("attn_bwd", launch_attn_bwd(a, st));
     }
-    KL("colsum:bqkv", launch_colsum_bf16(s->dqkv, 3 * H, T, 3 * H, nullptr, 0, L.p_bqkv, 8, st));
+    KL("colsum:bqkv", launch_colsum_bf16(s->dqkv, 3 * H, T, 3 * H, nullptr, 0, L.p_bqkv, kColsumSplits, st));
     {
       WgradArgs w{};
       w.X = x_in; w.ldx = H; w.dY = s->dqkv; w.ldy = 3 * H; w.M = H; w.N = 3 * H; w.T = T; w.splits = L.s_wqkv;
@@ -609,7 +612,7 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, void* 
     }
   }
   KL("embed_bwd", launch_embed_bwd(s->ids, W + oE, W + s->lay.find("position_embedding"), P + s->lay.find("emb_ln/gamma"), s->dxa,
-                      G + oE, s->p_dpos, s->p_embln, s->B, s->S, H, V, od, seed, step, s->emb_bsplits, st));
+                      G + oE, s->p_dpos, s->p_embln, s->B, s->S, H, V, od, seed, step, d_step, s->emb_bsplits, st));
   KL("grad_reduce:all", launch_grad_reduce(s->d_jobs, s->n_jobs, s->jobs_max_len, st));
   return 0;
 }
@@ -743,7 +746,7 @@ extern "C" int b4r_embed_ln_fwd(const int64_t* ids, const void* table, const voi
                                 void* out, int batch, int seq_len, int hidden, int vocab, void* stream) {
   if (!ids || !table || !pos || !gamma || !beta || !out) return fail("null argument");
   CK(launch_embed_ln_fwd(ids, (const bf16*)table, (const bf16*)pos, gamma, beta, (bf16*)out, batch, seq_len, hidden, vocab,
-                         0.f, 0, 0, (cudaStream_t)stream));
+                         0.f, 0, 0, nullptr, (cudaStream_t)stream));
   return 0;
 }
 

@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
                                                        bf16* __restrict__ ctx, float* __restrict__ lse,
                                                        uint64_t* __restrict__ keep_bits, int S, int H, int N,
                                                        uint32_t thr16, float inv_keep, uint64_t seed, uint32_t site,
-                                                       uint32_t step) {
+                                                       uint32_t step, const long long* __restrict__ d_step) {
+  if (d_step) step += (uint32_t)(*d_step);
   constexpr int LD = D + 8;
   constexpr int KD = D / 16;  // k-steps over the head dim
   constexpr int ND = D / 8;   // output n-tiles
@@ -197,12 +198,13 @@ cudaError_t launch_attn_fwd(const AttnArgs& a, cudaStream_t st) {
   float inv_keep = 1.0f / (1.0f - (float)thr / 65536.0f);
   dim3 grid((a.S + 63) / 64, a.B * a.N);
   size_t smem = attn_fwd_smem(a.S, D);
+  static size_t cap32 = 0, cap64 = 0;
   if (D == 32) {
-    cudaFuncSetAttribute(attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attn_fwd_kernel<32><<<grid, 128, smem, st>>>(a.qkv, a.mask, a.ctx, a.lse, a.keep_bits, a.S, a.H, a.N, thr, inv_keep, a.seed, a.site, a.step);
+    if (smem > cap32) { cudaFuncSetAttribute(attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cap32 = smem; }
+    attn_fwd_kernel<32><<<grid, 128, smem, st>>>(a.qkv, a.mask, a.ctx, a.lse, a.keep_bits, a.S, a.H, a.N, thr, inv_keep, a.seed, a.site, a.step, a.d_step);
   } else {
-    cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attn_fwd_kernel<64><<<grid, 128, smem, st>>>(a.qkv, a.mask, a.ctx, a.lse, a.keep_bits, a.S, a.H, a.N, thr, inv_keep, a.seed, a.site, a.step);
+    if (smem > cap64) { cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cap64 = smem; }
+    attn_fwd_kernel<64><<<grid, 128, smem, st>>>(a.qkv, a.mask, a.ctx, a.lse, a.keep_bits, a.S, a.H, a.N, thr, inv_keep, a.seed, a.site, a.step, a.d_step);
   }
   return cudaGetLastError();
 }
@@ -447,11 +449,12 @@ cudaError_t launch_attn_bwd(const AttnArgs& a, cudaStream_t st) {
   uint32_t thr = drop_threshold16(a.drop_rate);
   float inv_keep = 1.0f / (1.0f - (float)thr / 65536.0f);
   size_t smem = attn_bwd_smem(a.S, D);
+  static size_t cap32 = 0, cap64 = 0;
   if (D == 32) {
-    cudaFuncSetAttribute(attn_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > cap32) { cudaFuncSetAttribute(attn_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cap32 = smem; }
     attn_bwd_kernel<32><<<a.B * a.N, 128, smem, st>>>(a.qkv, a.mask, a.ctx, a.dctx, a.lse, a.keep_bits, a.dqkv, a.S, a.H, a.N, thr, inv_keep);
   } else {
-    cudaFuncSetAttribute(attn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > cap64) { cudaFuncSetAttribute(attn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cap64 = smem; }
     attn_bwd_kernel<64><<<a.B * a.N, 128, smem, st>>>(a.qkv, a.mask, a.ctx, a.dctx, a.lse, a.keep_bits, a.dqkv, a.S, a.H, a.N, thr, inv_keep);
   }
   return cudaGetLastError();

@@ -496,7 +496,8 @@ cudaError_t launch_ce_fwd(const CeArgs& a, cudaStream_t st) {
 #define B4R_CE(HH)                                                                                         \
   case HH: {                                                                                               \
     size_t smem = ce_fwd_smem<HH>();                                                                       \
-    cudaFuncSetAttribute(ce_fwd_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+    static bool done_##HH = false;                                                                         \
+    if (!done_##HH) { cudaFuncSetAttribute(ce_fwd_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done_##HH = true; }        \
     ce_fwd_kernel<HH><<<grid, 256, smem, st>>>(d);                                                         \
     break;                                                                                                 \
   }
@@ -516,7 +517,8 @@ cudaError_t launch_ce_count(const CeArgs& a, const float* s_gt, int* beat, cudaS
 #define B4R_CC(HH)                                                                                         \
   case HH: {                                                                                               \
     size_t smem = ce_fwd_smem<HH>();                                                                       \
-    cudaFuncSetAttribute(ce_count_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    static bool done_##HH = false;                                                                         \
+    if (!done_##HH) { cudaFuncSetAttribute(ce_count_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done_##HH = true; }      \
     ce_count_kernel<HH><<<grid, 256, smem, st>>>(d, s_gt, beat);                                           \
     break;                                                                                                 \
   }
@@ -541,7 +543,8 @@ cudaError_t launch_ce_dlogits(const CeArgs& a, cudaStream_t st) {
 #define B4R_DL(HH)                                                                                         \
   case HH: {                                                                                               \
     size_t smem = ce_dl_smem<HH>();                                                                        \
-    cudaFuncSetAttribute(ce_dlogits_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    static bool done_##HH = false;                                                                         \
+    if (!done_##HH) { cudaFuncSetAttribute(ce_dlogits_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done_##HH = true; }    \
     ce_dlogits_kernel<HH><<<grid, 256, smem, st>>>(d);                                                     \
     break;                                                                                                 \
   }

@@ -12,7 +12,8 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __rest
                                                            const bf16* __restrict__ pos, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, bf16* __restrict__ out, int T,
                                                            int S, int V, uint32_t thr16, float inv_keep, uint64_t seed,
-                                                           uint32_t step) {
+                                                           uint32_t step, const long long* __restrict__ d_step) {
+  if (d_step) step += (uint32_t)(*d_step);
   constexpr int LPR = H / 8;       // lanes per row (16 B each)
   constexpr int RPW = 32 / LPR;    // rows per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __rest
 
 cudaError_t launch_embed_ln_fwd(const int64_t* ids, const bf16* table, const bf16* pos, const float* gamma,
                                 const float* beta, bf16* out, int B, int S, int H, int V, float drop_rate,
-                                uint64_t seed, uint32_t step, cudaStream_t st) {
+                                uint64_t seed, uint32_t step, const long long* d_step, cudaStream_t st) {
   const int T = B * S;
   uint32_t thr = drop_threshold16(drop_rate);
   float inv_keep = 1.0f / (1.0f - (float)thr / 65536.0f);
@@ -70,7 +71,7 @@ cudaError_t launch_embed_ln_fwd(const int64_t* ids, const bf16* table, const bf1
   case HH: {                                                                                                   \
     int rows_per_cta = 8 * (32 / (HH / 8));                                                                    \
     embed_ln_fwd_kernel<HH><<<(T + rows_per_cta - 1) / rows_per_cta, 256, 0, st>>>(ids, table, pos, gamma, beta, out, T, S, \
-                                                                                   V, thr, inv_keep, seed, step);  \
+                                                                                   V, thr, inv_keep, seed, step, d_step);  \
     break;                                                                                                     \
   }
   switch (H) {
@@ -95,7 +96,8 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restric
                                                         const float* __restrict__ d_out, float* __restrict__ grad_table,
                                                         float* __restrict__ dpos_part, float* __restrict__ dln_part, int B,
                                                         int S, int V, uint32_t thr16, float inv_keep, uint64_t seed,
-                                                        uint32_t step) {
+                                                        uint32_t step, const long long* __restrict__ d_step) {
+  if (d_step) step += (uint32_t)(*d_step);
   constexpr int LPR = H / 8, RPW = 32 / LPR, RPC = 8 * RPW;  // rows per CTA pass
   __shared__ float s_red[3][RPC][H + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -193,15 +195,15 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restric
 
 cudaError_t launch_embed_bwd(const int64_t* ids, const bf16* table, const bf16* pos, const float* gamma,
                              const float* d_out, float* grad_table, float* dpos_part, float* dln_part, int B, int S,
-                             int H, int V, float drop_rate, uint64_t seed, uint32_t step, int bsplits,
-                             cudaStream_t st) {
+                             int H, int V, float drop_rate, uint64_t seed, uint32_t step, const long long* d_step,
+                             int bsplits, cudaStream_t st) {
   uint32_t thr = drop_threshold16(drop_rate);
   float inv_keep = 1.0f / (1.0f - (float)thr / 65536.0f);
   dim3 grid(S, bsplits);
   switch (H) {
-    case 64: embed_bwd_kernel<64><<<grid, 256, 0, st>>>(ids, table, pos, gamma, d_out, grad_table, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step); break;
-    case 128: embed_bwd_kernel<128><<<grid, 256, 0, st>>>(ids, table, pos, gamma, d_out, grad_table, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step); break;
-    case 256: embed_bwd_kernel<256><<<grid, 256, 0, st>>>(ids, table, pos, gamma, d_out, grad_table, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step); break;
+    case 64: embed_bwd_kernel<64><<<grid, 256, 0, st>>>(ids, table, pos, gamma, d_out, grad_table, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
+    case 128: embed_bwd_kernel<128><<<grid, 256, 0, st>>>(ids, table, pos, gamma, d_out, grad_table, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
+    case 256: embed_bwd_kernel<256><<<grid, 256, 0, st>>>(ids, table, pos, gamma, d_out, grad_table, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

@@ -188,7 +188,7 @@ struct RowLnDev {
   int M, H;
   const float* bias; const float* gamma; const float* beta;
   const bf16* residual; bf16* pre; bf16* act; bf16* y; float* mean; float* rstd;
-  uint32_t thr16; float inv_keep; uint64_t seed; uint32_t site; uint32_t step;
+  uint32_t thr16; float inv_keep; uint64_t seed; uint32_t site; uint32_t step; const long long* d_step;
 };
 
 template <int H, int MODE>
@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(256) gemm_rowln_kernel(GemmOperands op, RowLnD
   if (d_M) M = min(M, *d_M);
   const int m0 = blockIdx.x * T::BM;
   if (m0 >= M) return;
+  if (ep.d_step) ep.step += (uint32_t)(*ep.d_step);
   op.a_mmax = min(op.a_mmax, M);
 
   float acc[T::MI][T::NI][4];
@@ -308,7 +309,7 @@ static cudaError_t launch_rowln_t(const RowLnArgs& a, cudaStream_t st) {
   ep.pre = a.pre; ep.act = a.act; ep.y = a.y; ep.mean = a.mean; ep.rstd = a.rstd;
   ep.thr16 = drop_threshold16(a.drop_rate);
   ep.inv_keep = 1.0f / (1.0f - (float)ep.thr16 / 65536.0f);
-  ep.seed = a.seed; ep.site = a.site; ep.step = a.step;
+  ep.seed = a.seed; ep.site = a.site; ep.step = a.step; ep.d_step = a.d_step;
   size_t smem = RowTile<H>::SMEM;
   static bool attr_done = false;
   if (!attr_done) {

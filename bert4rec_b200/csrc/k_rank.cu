@@ -76,7 +76,7 @@ cudaError_t launch_rank_candidates(const bf16* t, int ldt, const bf16* E, const 
   int grid = (M + 3) / 4;
 #define B4R_RK(HH)                                                                                            \
   case HH:                                                                                                    \
-    cudaFuncSetAttribute(rank_candidates_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    { static size_t cap_##HH = 0; if (smem > cap_##HH) { cudaFuncSetAttribute(rank_candidates_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cap_##HH = smem; } } \
     rank_candidates_kernel<HH><<<grid, 128, smem, st>>>(t, ldt, E, vbias, cand, gt, M, C, ranking, scores, rank, hist); \
     break;
   switch (H) {

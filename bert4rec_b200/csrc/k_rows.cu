@@ -22,8 +22,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      bf16* __restrict__ d_branch, float* __restrict__ partials, int M,
                                                      uint32_t thr16, float inv_keep, uint64_t seed, uint32_t site,
                                                      uint32_t step, int nsplit, size_t split_stride,
-                                                     const bf16* __restrict__ t_pre, const int* __restrict__ d_M) {
+                                                     const bf16* __restrict__ t_pre, const int* __restrict__ d_M,
+                                                     const long long* __restrict__ d_step) {
   if (d_M) M = min(M, *d_M);
+  if (d_step) step += (uint32_t)(*d_step);
   constexpr int LPR = H / 8, RPW = 32 / LPR, RPC = 8 * RPW;
   __shared__ float s_red[3][RPC][H + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -112,14 +114,15 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 
 cudaError_t launch_ln_bwd(const float* d_out, const bf16* pre, const float* mean, const float* rstd,
                           const float* gamma, float* d_pre, bf16* d_branch, float* partials, int M, int H,
-                          float drop_rate, uint64_t seed, uint32_t site, uint32_t step, cudaStream_t st) {
+                          float drop_rate, uint64_t seed, uint32_t site, uint32_t step, const long long* d_step,
+                          cudaStream_t st) {
   uint32_t thr = drop_threshold16(drop_rate);
   float inv_keep = 1.0f / (1.0f - (float)thr / 65536.0f);
   int grid = ln_bwd_parts(M);
   switch (H) {
-    case 64: ln_bwd_kernel<64, false><<<grid, 256, 0, st>>>(d_out, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr); break;
-    case 128: ln_bwd_kernel<128, false><<<grid, 256, 0, st>>>(d_out, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr); break;
-    case 256: ln_bwd_kernel<256, false><<<grid, 256, 0, st>>>(d_out, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr); break;
+    case 64: ln_bwd_kernel<64, false><<<grid, 256, 0, st>>>(d_out, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr, d_step); break;
+    case 128: ln_bwd_kernel<128, false><<<grid, 256, 0, st>>>(d_out, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr, d_step); break;
+    case 256: ln_bwd_kernel<256, false><<<grid, 256, 0, st>>>(d_out, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr, d_step); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -132,9 +135,9 @@ cudaError_t launch_head_bwd_rows(const float* dt_part, int nsplit, size_t split_
   int grid = ln_bwd_parts(M_cap);
   const int* d_M = d_counts ? d_counts + 1 : nullptr;
   switch (H) {
-    case 64: ln_bwd_kernel<64, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M); break;
-    case 128: ln_bwd_kernel<128, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M); break;
-    case 256: ln_bwd_kernel<256, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M); break;
+    case 64: ln_bwd_kernel<64, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr); break;
+    case 128: ln_bwd_kernel<128, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr); break;
+    case 256: ln_bwd_kernel<256, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

@@ -61,6 +61,7 @@ struct RowLnArgs {
   float* mean; float* rstd;                    // [M]
   // dropout
   float drop_rate; uint64_t seed; uint32_t site; uint32_t step;
+  const long long* d_step;                     // optional device counter added to step (CUDA-graph replays)
 };
 cudaError_t launch_gemm_rowln(int mode, const RowLnArgs& a, cudaStream_t st);
 
@@ -80,13 +81,13 @@ cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t st);
 // ------------------------------------------------------------------ embedding (k_embed.cu)
 cudaError_t launch_embed_ln_fwd(const int64_t* ids, const bf16* table, const bf16* pos, const float* gamma,
                                 const float* beta, bf16* out, int B, int S, int H, int V, float drop_rate,
-                                uint64_t seed, uint32_t step, cudaStream_t st);
+                                uint64_t seed, uint32_t step, const long long* d_step, cudaStream_t st);
 // d_out fp32 [T][H] -> dE (atomic scatter-add into grad_table fp32 [V][H]), dpos partials [bsplits][S*H],
 // dgamma/dbeta partials [nparts][2H]
 cudaError_t launch_embed_bwd(const int64_t* ids, const bf16* table, const bf16* pos, const float* gamma,
                              const float* d_out, float* grad_table, float* dpos_part, float* dln_part, int B, int S,
-                             int H, int V, float drop_rate, uint64_t seed, uint32_t step, int bsplits,
-                             cudaStream_t st);
+                             int H, int V, float drop_rate, uint64_t seed, uint32_t step, const long long* d_step,
+                             int bsplits, cudaStream_t st);
 int embed_bwd_bsplits(int B);
 
 // ------------------------------------------------------------------ attention (k_attn.cu)
@@ -97,7 +98,7 @@ struct AttnArgs {
   float* lse;             // [B][N][S]
   uint64_t* keep_bits;    // [B][N][S][words] dropout keep bits (training only)
   int B, S, H, N;
-  float drop_rate; uint64_t seed; uint32_t site; uint32_t step;
+  float drop_rate; uint64_t seed; uint32_t site; uint32_t step; const long long* d_step;
   // backward
   const bf16* dctx;       // [B*S][H]
   bf16* dqkv;             // [B*S][3H]
@@ -111,7 +112,8 @@ int attn_mask_words(int S);
 //   d_pre = LNbwd(d_out) ; d_branch = drop(d_pre) (bf16) ; partials[cta] = {dgamma[H], dbeta[H], dbranch_colsum[H]}
 cudaError_t launch_ln_bwd(const float* d_out, const bf16* pre, const float* mean, const float* rstd,
                           const float* gamma, float* d_pre, bf16* d_branch, float* partials, int M, int H,
-                          float drop_rate, uint64_t seed, uint32_t site, uint32_t step, cudaStream_t st);
+                          float drop_rate, uint64_t seed, uint32_t site, uint32_t step, const long long* d_step,
+                          cudaStream_t st);
 int ln_bwd_parts(int M);
 
 struct ReduceJob { const float* src; float* dst; int nparts; int len; long long part_stride; int accumulate; };

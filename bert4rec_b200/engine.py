@@ -216,11 +216,12 @@ class Session:
             pass
 
     # ---- steps (all enqueue on torch's current stream)
-    def encode(self, ids, mask, training=False, seed=0, step=0):
+    def encode(self, ids, mask, training=False, seed=0, step=0, step_counter=None):
         assert ids.dtype == torch.int64 and mask.dtype == torch.int64 and ids.is_contiguous() and mask.is_contiguous()
         assert tuple(ids.shape) == (self.B, self.S), (ids.shape, self.B, self.S)
         self._keep = [ids, mask]
-        check(self.lib.b4r_encode(self.h, _ptr(ids), _ptr(mask), int(bool(training)), int(seed), int(step), _stream()))
+        check(self.lib.b4r_encode(self.h, _ptr(ids), _ptr(mask), int(bool(training)), int(seed), int(step),
+                                  _ptr(step_counter), _stream()))
 
     def select(self, positions, ids=None, weights=None, mode=0, want_aux=False):
         self._keep += [positions, ids, weights]
@@ -237,8 +238,8 @@ class Session:
         check(self.lib.b4r_mlm_logits(self.h, _ptr(out), _stream()))
         return out
 
-    def backward(self, seed=0, step=0):
-        check(self.lib.b4r_backward(self.h, int(seed), int(step), _stream()))
+    def backward(self, seed=0, step=0, step_counter=None):
+        check(self.lib.b4r_backward(self.h, int(seed), int(step), _ptr(step_counter), _stream()))
 
     def pooled_output(self):
         out = torch.empty(self.B, self.store.H, dtype=torch.float32, device=self.store.device)

@@ -105,7 +105,8 @@ class BERT4RecModel:
         self._host_step = 0
         self.stop_training = False
         self.distributed = False
-        self._timers = None
+        self.use_cuda_graph = True
+        self._graphs = {}
 
     @property
     def identifier(self):
@@ -116,18 +117,18 @@ class BERT4RecModel:
         return self.store.device
 
     # ------------------------------------------------------------------ input staging
-    def _stage(self, inputs, keys):
+    def _stage(self, inputs, keys, persistent=False):
         """Moves the int64 input tensors named by ``keys`` to the device.  Host tensors are packed into ONE pinned
-        staging buffer and copied with a single async H2D copy; device tensors are used in place."""
-        vals = [inputs[k] for k in keys]
-        if all(torch.is_tensor(v) and v.is_cuda for v in vals):
+        staging buffer and copied with a single async H2D copy.  Device tensors are used in place unless
+        ``persistent`` (CUDA-graph replays need fixed addresses): then they are gathered into the same persistent
+        device buffer with one D2D copy kernel."""
+        vals = [v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v)) for v in (inputs[k] for k in keys)]
+        all_cuda = all(v.is_cuda for v in vals)
+        if all_cuda and not persistent:
             return {k: (v if v.dtype == torch.int64 and v.is_contiguous() else v.to(torch.int64).contiguous())
                     for k, v in zip(keys, vals)}
-        arrs = [torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v).to(torch.int64).reshape(-1).cpu()
-                if not (torch.is_tensor(v) and v.dtype == torch.int64 and not v.is_cuda) else v.reshape(-1)
-                for v in vals]
-        shapes = [tuple(torch.as_tensor(v).shape) if not torch.is_tensor(v) else tuple(v.shape) for v in vals]
-        sizes = [a.numel() for a in arrs]
+        shapes = [tuple(v.shape) for v in vals]
+        sizes = [v.numel() for v in vals]
         total = sum(sizes)
         key = (keys, tuple(shapes))
         st = self._staging.get(key)
@@ -136,11 +137,14 @@ class BERT4RecModel:
             dev = torch.empty(total, dtype=torch.int64, device=self.device)
             st = self._staging[key] = (host, dev)
         host, dev = st
-        off = 0
-        for a, n in zip(arrs, sizes):
-            host[off:off + n].copy_(a)
-            off += n
-        dev.copy_(host, non_blocking=True)
+        if all_cuda:
+            torch.cat([v.reshape(-1).to(torch.int64) for v in vals], out=dev)
+        else:
+            off = 0
+            for v, n in zip(vals, sizes):
+                host[off:off + n].copy_(v.reshape(-1))   # dtype-converting host copy into the pinned buffer
+                off += n
+            dev.copy_(host, non_blocking=True)
         out, off = {}, 0
         for k, shp, n in zip(keys, shapes, sizes):
             out[k] = dev[off:off + n].view(shp)
@@ -226,18 +230,37 @@ class BERT4RecModel:
         """fwd(training) -> fused CE -> backward -> [NCCL allreduce] -> clip + AdamW (bert4rec_model.py:151-173)."""
         if self.optimizer is None:
             raise RuntimeError("compile() the model (or trainer.initialize_model()) before train_step")
-        d = self._stage(inputs, _STAGED_KEYS)
+        d = self._stage(inputs, _STAGED_KEYS, persistent=self.use_cuda_graph)
         B, S = d["input_word_ids"].shape
         P = d["masked_lm_positions"].shape[1]
         sess = self.store.session(B, S, P)
-        step = self._host_step
-        self._host_step += 1
         stats = self._stats_buf("train")
-        sess.encode(d["input_word_ids"], d["input_mask"], training=True, seed=self._seed, step=step)
+        if not self.use_cuda_graph:
+            self._train_body(sess, d, stats)
+        else:
+            g = self._graphs.get((B, S, P))
+            if g is None:
+                # first step of this shape runs eagerly (lazy one-time initialisation), then the same launch
+                # sequence is captured once and replayed for every later step
+                self._train_body(sess, d, stats)
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._train_body(sess, d, stats)
+                self._graphs[(B, S, P)] = g
+            else:
+                g.replay()
+        return StepMetrics(stats, self._metric_names)
+
+    def _train_body(self, sess, d, stats):
+        """The launch sequence of one optimisation step (all on torch's current stream; CUDA-graph capturable:
+        the dropout counter and the learning-rate schedule read the device-side iteration counter)."""
+        ctr = self.store.step_counter
+        sess.encode(d["input_word_ids"], d["input_mask"], training=True, seed=self._seed, step=0, step_counter=ctr)
         sess.select(d["masked_lm_positions"], d["masked_lm_ids"], d["masked_lm_weights"], mode=0, want_aux=self._want_sca)
         sess.transform()
         sess.loss(stats)
-        sess.backward(seed=self._seed, step=step)
+        sess.backward(seed=self._seed, step=0, step_counter=ctr)
         count = sess.step_stats()[1:2]
         scale = 1.0
         if self.distributed:
@@ -248,7 +271,6 @@ class BERT4RecModel:
             torch.distributed.all_reduce(self._count)
             count = self._count
         self.store.adamw_step(self._hp, count=count, grad_scale=scale)
-        return StepMetrics(stats, self._metric_names)
 
     def test_step(self, inputs):
         """fwd(inference) -> fused CE + accuracies, no update (bert4rec_model.py:175-192)."""

@@ -60,7 +60,9 @@ int b4r_sync_shadow(b4r_session* s, void* stream);   /* shadow_bf16 = bf16(param
 
 /* Bert4RecEncoder.call, bert4rec_encoder.py:186-231.  ids/mask: int64 [batch, seq_len]. */
 int b4r_encode(b4r_session* s, const int64_t* input_word_ids, const int64_t* input_mask, int training, uint64_t seed,
-               uint32_t step, void* stream);
+               uint32_t step, const int64_t* step_counter, void* stream);
+/* Dropout masks are Philox(seed; row, col, site, step + *step_counter): step_counter (optional device int64, e.g. the
+ * optimizer's iteration counter) lets a captured CUDA graph draw fresh masks on every replay. */
 /* tfm MaskedLM._gather_indexes (bert4rec_model.py:141-143) + tf.boolean_mask of the loss (trainer_utils.py:19-20).
  * mode 0: slots with masked_lm_ids != 0 (training); 1: slots with masked_lm_weights != 0 (rank_items,
  * bert4rec_model.py:218-220); 2: all batch*max_pred slots (BERT4RecModel.call). want_aux adds one row per sequence
@@ -76,7 +78,7 @@ int b4r_mlm_loss(b4r_session* s, float* stats, void* stream);
 /* materialised logits [n_rows, vocab] fp32 for BERT4RecModel.call()'s "mlm_logits" (bert4rec_model.py:139-147) */
 int b4r_mlm_logits(b4r_session* s, float* out, void* stream);
 /* tape.gradient of the SUM loss over all trainable variables (bert4rec_model.py:166-167) -> grads (flat, fp32). */
-int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, void* stream);
+int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const int64_t* step_counter, void* stream);
 /* tanh pooler on token 0 (bert4rec_encoder.py:224-226) -> out fp32 [batch, hidden] */
 int b4r_pooled_output(b4r_session* s, float* out, void* stream);
 
