@@ -361,6 +361,7 @@ def roofline_block(model, sess, w, dev_batches, args, hbm, tf_burst, src):
     n = max(args.steps, 10)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_batches[0]["input_word_ids"].device)
     model.use_cuda_graph = False   # per-launch events cannot be recorded inside a graph replay
+    model.distributed = False      # rank-0-only profiling pass: no collective (the other ranks are not stepping)
     for i in range(3):
         model.train_step(dev_batches[i % len(dev_batches)])
     torch.cuda.synchronize()

@@ -236,24 +236,55 @@ class BERT4RecModel:
         sess = self.store.session(B, S, P)
         stats = self._stats_buf("train")
         if not self.use_cuda_graph:
-            self._train_body(sess, d, stats)
+            self._fwd_bwd(sess, d, stats)
+            self._reduce_and_update(sess)
         else:
             g = self._graphs.get((B, S, P))
             if g is None:
                 # first step of this shape runs eagerly (lazy one-time initialisation), then the same launch
-                # sequence is captured once and replayed for every later step
-                self._train_body(sess, d, stats)
+                # sequence is captured once and replayed for every later step.  Single GPU: one graph for the
+                # whole step.  Data-parallel: forward+backward graph, eager NCCL all-reduce, optimizer graph.
+                self._fwd_bwd(sess, d, stats)
+                self._reduce_and_update(sess)
                 torch.cuda.synchronize(self.device)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._train_body(sess, d, stats)
-                self._graphs[(B, S, P)] = g
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    self._fwd_bwd(sess, d, stats)
+                    if not self.distributed:
+                        self._reduce_and_update(sess)
+                g2 = None
+                if self.distributed:
+                    g2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g2):
+                        self._update(self._count)
+                self._graphs[(B, S, P)] = (g1, g2)
             else:
-                g.replay()
+                g1, g2 = g
+                g1.replay()
+                if g2 is not None:
+                    self._all_reduce(sess)
+                    g2.replay()
         return StepMetrics(stats, self._metric_names)
 
-    def _train_body(self, sess, d, stats):
-        """The launch sequence of one optimisation step (all on torch's current stream; CUDA-graph capturable:
+    def _all_reduce(self, sess):
+        # batch data-parallel: SUM gradients of the SUM loss and the valid-slot counts over ranks (NCCL), so that
+        # the normaliser is the GLOBAL number of valid masked slots (trainer_utils.py:22)
+        self._count.copy_(sess.step_stats()[1:2])
+        torch.distributed.all_reduce(self.store.grads[: self.store.n_trainable])
+        torch.distributed.all_reduce(self._count)
+
+    def _update(self, count):
+        self.store.adamw_step(self._hp, count=count, grad_scale=1.0)
+
+    def _reduce_and_update(self, sess):
+        if self.distributed:
+            self._all_reduce(sess)
+            self._update(self._count)
+        else:
+            self._update(sess.step_stats()[1:2])
+
+    def _fwd_bwd(self, sess, d, stats):
+        """The launch sequence of forward + backward (all on torch's current stream; CUDA-graph capturable:
         the dropout counter and the learning-rate schedule read the device-side iteration counter)."""
         ctr = self.store.step_counter
         sess.encode(d["input_word_ids"], d["input_mask"], training=True, seed=self._seed, step=0, step_counter=ctr)
@@ -261,16 +292,6 @@ class BERT4RecModel:
         sess.transform()
         sess.loss(stats)
         sess.backward(seed=self._seed, step=0, step_counter=ctr)
-        count = sess.step_stats()[1:2]
-        scale = 1.0
-        if self.distributed:
-            # batch data-parallel: SUM gradients of the SUM loss and the valid-slot counts over ranks (NCCL), so that
-            # the normaliser is the GLOBAL number of valid masked slots (trainer_utils.py:22)
-            self._count.copy_(count)
-            torch.distributed.all_reduce(self.store.grads[: self.store.n_trainable])
-            torch.distributed.all_reduce(self._count)
-            count = self._count
-        self.store.adamw_step(self._hp, count=count, grad_scale=scale)
 
     def test_step(self, inputs):
         """fwd(inference) -> fused CE + accuracies, no update (bert4rec_model.py:175-192)."""
