@@ -3,6 +3,7 @@
 // caller's stream and returns.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -179,7 +180,9 @@ struct b4r_session {
   int *rows, *labels, *row_mult, *counts; float* row_w;
   bf16 *t_pre, *t_act, *t; float *hmean, *hrstd;
   float *ce_part, *lse, *lab, *stats, *step_stats;
-  int vsplits;
+  int vsplits, vsplits_umma;
+  bool use_umma = false;
+  CeUmmaMaps umaps;
   bf16* dlogits; int dl_rows;
   float* dt_part; int dt_splits;
   bf16* d_tpre;
@@ -273,7 +276,16 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
     if (vs > 64) vs = 64;
     s->vsplits = vs;
   }
-  s->ce_part = b.take<float>((size_t)s->vsplits * Mcap * 6);
+  {
+    int mtiles = (Mcap + ce_umma_block_m() - 1) / ce_umma_block_m();
+    int vtiles = (V + 127) / 128;
+    int vs = (2 * 148 + mtiles - 1) / mtiles;
+    if (vs > vtiles) vs = vtiles;
+    if (vs < 1) vs = 1;
+    if (vs > 64) vs = 64;
+    s->vsplits_umma = vs;
+  }
+  s->ce_part = b.take<float>((size_t)(s->vsplits > s->vsplits_umma ? s->vsplits : s->vsplits_umma) * Mcap * 6);
   s->lse = b.take<float>(Mcap); s->lab = b.take<float>(Mcap);
   s->stats = b.take<float>(8); s->step_stats = b.take<float>(8);
   {
@@ -376,6 +388,8 @@ extern "C" int b4r_session_create(const b4r_config* cfg, int batch, int seq_len,
   CK(cudaMemcpy(s->d_vb_jobs, vb, sizeof(vb), cudaMemcpyHostToDevice));
   CK(cudaMemset(s->stats, 0, 8 * sizeof(float)));
   CK(cudaMemset(s->step_stats, 0, 8 * sizeof(float)));
+  s->use_umma = ce_umma_make_maps(&s->umaps, s->t, s->Mcap, s->shadow + s->lay.find("word_embeddings"), s->V, s->H) &&
+                getenv("B4R_DISABLE_UMMA") == nullptr;
   CK(cudaMemset(s->counts, 0, 8 * sizeof(int)));
   *out = s;
   return 0;
@@ -482,7 +496,12 @@ extern "C" int b4r_mlm_loss(b4r_session* s, float* stats, void* stream) {
   if (!s) return fail("null session");
   CeArgs c = ce_args(s);
   c.stats = stats;
-  KL("ce_fwd", launch_ce_fwd(c, st));
+  if (s->use_umma) {
+    c.vsplits = s->vsplits_umma;
+    KL("ce_fwd_umma", launch_ce_fwd_umma(s->umaps, c, st));
+  } else {
+    KL("ce_fwd", launch_ce_fwd(c, st));
+  }
   KL("ce_finalize", launch_ce_finalize(c, st));
   return 0;
 }
@@ -704,6 +723,11 @@ extern "C" const uint64_t* b4r_attn_keep_bits(b4r_session* s, int layer, int* wo
   return s->layers[layer].keep;
 }
 extern "C" int b4r_launch_count(b4r_session* s) { return s ? s->launches : 0; }
+extern "C" int b4r_session_set_flag(b4r_session* s, int flag, int value) {
+  if (!s) return fail("null session");
+  if (flag == 1) { s->use_umma = value != 0; return 0; }
+  return fail("unknown flag %d", flag);
+}
 extern "C" int b4r_profile_enable(b4r_session* s, int on) {
   if (!s) return fail("null session");
   s->prof_on = on != 0;

@@ -1,0 +1,229 @@
+// Generation 2 of the fused tied-projection x online-softmax cross-entropy forward:
+// tcgen05.mma (bf16 -> fp32 accumulators in TMEM) fed by TMA (128-byte-swizzled K-major tiles), warp-specialised:
+//   warp 0    : TMA producer (t tile once, then the stream of E tiles through a STAGES-deep smem ring)
+//   warp 1    : TMEM allocator + single-thread MMA issuer (double-buffered 128x128 fp32 accumulators)
+//   warps 2-5 : epilogue, one thread per accumulator row: tcgen05.ld 32 columns at a time, + bias, online
+//               (max, sum-exp, label logit, first arg-max) entirely thread-local -- no shuffles, logits never leave chip.
+// Same partial format / finalize kernel as generation 1 (k_ce.cu); reference ops replaced: tfm MaskedLM projection +
+// SparseSoftmaxCrossEntropyWithLogits + argmax metrics (bert4rec_model.py:143, trainer_utils.py:12-23,49-60).
+#include "common.cuh"
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace b4r {
+
+constexpr int UM_BM = 128, UM_BN = 128;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct CeUmmaDev {
+  const float* vbias; const int* labels; const int* d_counts;
+  int M_cap, v_begin, v_end, vsplits;
+  float* part;
+};
+
+template <int H>
+struct CeUmmaCfg {
+  static constexpr int KB = H / 64;                         // 64-column (128-byte) k-blocks
+  static constexpr int STAGES = H == 64 ? 4 : (H == 128 ? 3 : 2);
+  static constexpr int A_BYTES = KB * UM_BM * 128;
+  static constexpr int B_STAGE_BYTES = KB * UM_BN * 128;
+  static constexpr int SMEM = A_BYTES + STAGES * B_STAGE_BYTES + 2 * UM_BN * 4 + 256 + 1024;  // + bias x2, barriers, align slack
+};
+
+template <int H>
+__global__ void __launch_bounds__(192, 1) ce_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB, CeUmmaDev a) {
+  using Cfg = CeUmmaCfg<H>;
+  constexpr int KB = Cfg::KB, STAGES = Cfg::STAGES;
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment for the 128B-swizzled tiles
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + Cfg::A_BYTES;
+  float* sBias = reinterpret_cast<float*>(sB + STAGES * Cfg::B_STAGE_BYTES);  // [2][UM_BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * UM_BN);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint64_t* afull = tempty + 2;          // [1]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(afull + 1);
+
+  const int n_rows = min(a.M_cap, a.d_counts[1]);
+  const int m0 = blockIdx.y * UM_BM;
+  if (m0 >= n_rows) return;  // uniform: before any barrier / TMEM allocation
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int ntiles = (a.v_end - a.v_begin + UM_BN - 1) / UM_BN;
+  const int tps = (ntiles + a.vsplits - 1) / a.vsplits;
+  const int tile_lo = blockIdx.x * tps, tile_hi = min(ntiles, tile_lo + tps);
+  const int my_tiles = max(0, tile_hi - tile_lo);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { umma::mbar_init(full + i, 1); umma::mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(tfull + i, 1); umma::mbar_init(tempty + i, 128); }
+    umma::mbar_init(afull, 1);
+    umma::fence_barrier_init();
+    umma::prefetch_tensormap(&tmA);
+    umma::prefetch_tensormap(&tmB);
+  }
+  if (warp == 1) umma::tmem_alloc<256>(tmem_holder);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0 && my_tiles > 0) {
+      umma::mbar_expect_tx(afull, Cfg::A_BYTES);
+      for (int kb = 0; kb < KB; ++kb) umma::tma_load_2d(sA + kb * UM_BM * 128, &tmA, kb * 64, m0, afull);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int stage = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        umma::mbar_wait(empty + stage, ph ^ 1);
+        umma::mbar_expect_tx(full + stage, Cfg::B_STAGE_BYTES);
+        const int v0 = a.v_begin + (tile_lo + i) * UM_BN;
+        for (int kb = 0; kb < KB; ++kb)
+          umma::tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES + kb * UM_BN * 128, &tmB, kb * 64, v0, full + stage);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0 && my_tiles > 0) {
+      constexpr uint32_t idesc = umma::make_idesc_bf16(UM_BM, UM_BN);
+      umma::mbar_wait(afull, 0);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int stage = i % STAGES, acc = i & 1;
+        umma::mbar_wait(tempty + acc, ((i >> 1) & 1) ^ 1);
+        umma::mbar_wait(full + stage, (i / STAGES) & 1);
+        umma::fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * UM_BN;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint32_t a_addr = umma::smem_addr(sA + kb * UM_BM * 128);
+          const uint32_t b_addr = umma::smem_addr(sB + stage * Cfg::B_STAGE_BYTES + kb * UM_BN * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma::mma_bf16_ss(d_tmem, umma::make_desc_k_sw128(a_addr + k * 32), umma::make_desc_k_sw128(b_addr + k * 32), idesc,
+                              (kb | k) ? 1u : 0u);
+        }
+        umma::mma_commit(empty + stage);  // smem stage reusable once these MMAs have read it
+        umma::mma_commit(tfull + acc);    // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    const int row = m0 + row_in_tile;
+    const int et = threadIdx.x - 64;           // 0..127 index among the epilogue threads
+    const int label = row < n_rows ? a.labels[row] : -1;
+    float run_max = -INFINITY, run_sum = 0.f, lab_logit = -INFINITY, best_v = -INFINITY;
+    int best_i = 0x7fffffff;
+    constexpr float LOG2E = 1.4426950408889634f;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int acc = i & 1;
+      const int v0 = a.v_begin + (tile_lo + i) * UM_BN;
+      {
+        const int v = v0 + et;
+        sBias[acc * UM_BN + et] = v < a.v_end ? a.vbias[v] : -INFINITY;  // -inf masks the out-of-range columns
+      }
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      umma::mbar_wait(tfull + acc, (i >> 1) & 1);
+      umma::fence_after_sync();
+      const float* bias = sBias + acc * UM_BN;
+#pragma unroll 1
+      for (int c = 0; c < UM_BN / 32; ++c) {
+        uint32_t r[32];
+        umma::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * UM_BN + c * 32, r);
+        umma::tmem_ld_wait();
+        float v[32];
+        float cmax = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __uint_as_float(r[j]) + bias[c * 32 + j];
+          cmax = fmaxf(cmax, v[j]);
+        }
+        const int col0 = v0 + c * 32;
+        if (cmax > best_v) {  // first maximum wins (columns are visited in increasing order)
+          best_v = cmax;
+#pragma unroll
+          for (int j = 31; j >= 0; --j)
+            if (v[j] == cmax) best_i = col0 + j;
+        }
+        if (label >= col0 && label < col0 + 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j == label) lab_logit = v[j];
+        }
+        if (cmax > run_max) {
+          run_sum *= ex2_approx((run_max - cmax) * LOG2E);  // ex2(-inf) = 0 on the first chunk
+          run_max = cmax;
+        }
+        if (run_max != -INFINITY) {
+          const float ms = run_max * LOG2E;
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s += ex2_approx(fmaf(v[j], LOG2E, -ms));
+          run_sum += s;
+        }
+      }
+      umma::fence_before_sync();
+      umma::mbar_arrive(tempty + acc);
+    }
+    if (row < n_rows) {
+      float* out = a.part + ((size_t)blockIdx.x * a.M_cap + row) * 6;
+      out[0] = run_max; out[1] = run_sum; out[2] = lab_logit; out[3] = best_v; out[4] = __int_as_float(best_i); out[5] = 0.f;
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    umma::fence_after_sync();
+    umma::tmem_dealloc<256>(tmem_base);
+  }
+}
+
+bool ce_umma_make_maps(CeUmmaMaps* maps, const bf16* t, int M_cap, const bf16* E, int V, int H) {
+  static_assert(sizeof(CUtensorMap) == sizeof(maps->a), "CUtensorMap size");
+  bool ok = make_tmap_bf16_sw128(reinterpret_cast<CUtensorMap*>(maps->a), t, (uint64_t)M_cap, (uint64_t)H, (uint64_t)H, UM_BM);
+  ok = ok && make_tmap_bf16_sw128(reinterpret_cast<CUtensorMap*>(maps->b), E, (uint64_t)V, (uint64_t)H, (uint64_t)H, UM_BN);
+  return ok;
+}
+
+int ce_umma_block_m() { return UM_BM; }
+
+cudaError_t launch_ce_fwd_umma(const CeUmmaMaps& maps, const CeArgs& a, cudaStream_t st) {
+  CeUmmaDev d;
+  d.vbias = a.vbias; d.labels = a.labels; d.d_counts = a.d_counts; d.M_cap = a.M_cap; d.v_begin = a.v_begin; d.v_end = a.v_end;
+  d.vsplits = a.vsplits > 0 ? a.vsplits : 1; d.part = a.part;
+  dim3 grid(d.vsplits, (a.M_cap + UM_BM - 1) / UM_BM);
+  const CUtensorMap& tmA = *reinterpret_cast<const CUtensorMap*>(maps.a);
+  const CUtensorMap& tmB = *reinterpret_cast<const CUtensorMap*>(maps.b);
+#define B4R_UM(HH)                                                                                                  \
+  case HH: {                                                                                                        \
+    static bool done_##HH = false;                                                                                  \
+    if (!done_##HH) {                                                                                               \
+      cudaFuncSetAttribute(ce_fwd_umma_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, CeUmmaCfg<HH>::SMEM); \
+      done_##HH = true;                                                                                             \
+    }                                                                                                               \
+    ce_fwd_umma_kernel<HH><<<grid, 192, CeUmmaCfg<HH>::SMEM, st>>>(tmA, tmB, d);                                    \
+    break;                                                                                                          \
+  }
+  switch (a.H) {
+    B4R_UM(64)
+    B4R_UM(128)
+    B4R_UM(256)
+    default: return cudaErrorInvalidValue;
+  }
+#undef B4R_UM
+  return cudaGetLastError();
+}
+
+}  // namespace b4r

@@ -171,6 +171,11 @@ cudaError_t launch_ce_dlogits(const CeArgs& a, cudaStream_t st);
 // full-catalogue rank counting (see k_ce.cu): beat[m] += #items of the shard that rank ahead of the ground truth
 cudaError_t launch_ce_count(const CeArgs& a, const float* s_gt, int* beat, cudaStream_t st);
 int ce_block_m();
+// generation 2 (tcgen05 + TMA) forward; maps are created once per session on the host
+struct CeUmmaMaps { alignas(64) unsigned char a[128]; alignas(64) unsigned char b[128]; };
+bool ce_umma_make_maps(CeUmmaMaps* maps, const bf16* t, int M_cap, const bf16* E, int V, int H);
+cudaError_t launch_ce_fwd_umma(const CeUmmaMaps& maps, const CeArgs& a, cudaStream_t st);
+int ce_umma_block_m();
 // MLM transform backward over rows: dt = sum_s dt_part[s] ; LN bwd ; gelu bwd -> d_tpre (bf16) ; partials {dgamma,dbeta,dbias}
 cudaError_t launch_head_bwd_rows(const float* dt_part, int nsplit, size_t split_stride, const bf16* t_pre,
                                  const bf16* act, const float* mean, const float* rstd, const float* gamma,

@@ -299,6 +299,9 @@ class Session:
     def launch_count(self):
         return self.lib.b4r_launch_count(self.h)
 
+    def set_flag(self, flag, value):
+        check(self.lib.b4r_session_set_flag(self.h, int(flag), int(value)))
+
     def profile(self, on=True):
         check(self.lib.b4r_profile_enable(self.h, int(on)))
 

@@ -411,3 +411,26 @@ def test_model_call_output_contract():
     assert "mlm_logits" not in no_mlm
     with pytest.raises(ValueError):
         model.encoder("not a dict")
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_ce_forward_tcgen05_matches_mma_sync_generation(name):
+    """Generation 2 (tcgen05 + TMEM + TMA) of the fused projection/CE forward against generation 1 (mma.sync) on the
+    same transformed rows: same loss / lse / label logits to fp32 summation-order noise, same arg-max counts."""
+    store, kw, B, S, P = build(name)
+    batch = to_cuda(make_batch(B, S, P, kw["vocab_size"], seed=41))
+    sess = store.session(B, S, P)
+    sess.encode(batch["input_word_ids"], batch["input_mask"], training=False)
+    sess.select(batch["masked_lm_positions"], batch["masked_lm_ids"], batch["masked_lm_weights"], mode=0, want_aux=True)
+    sess.transform()
+    res = []
+    for flag in (0, 1):
+        sess.set_flag(1, flag)
+        sess.loss()
+        torch.cuda.synchronize()
+        res.append(sess.step_stats().cpu().clone())
+    sess.set_flag(1, 1)
+    a, b = res
+    assert float(a[1]) == float(b[1]) and float(a[4]) == float(b[4])
+    assert abs(float(a[0]) - float(b[0])) / float(a[0]) < 1e-5, (a, b)
+    assert abs(float(a[2]) - float(b[2])) <= 1 and abs(float(a[3]) - float(b[3])) <= 1
