@@ -279,10 +279,9 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
   {
     int mtiles = (Mcap + ce_umma_block_m() - 1) / ce_umma_block_m();
     int vtiles = (V + 127) / 128;
-    int vs = (2 * 148 + mtiles - 1) / mtiles;
-    if (vs > vtiles) vs = vtiles;
+    (void)mtiles;
+    int vs = vtiles < 64 ? vtiles : 64;   // capacity of the partial buffer; the actual split count is chosen on the device
     if (vs < 1) vs = 1;
-    if (vs > 64) vs = 64;
     s->vsplits_umma = vs;
   }
   s->ce_part = b.take<float>((size_t)(s->vsplits > s->vsplits_umma ? s->vsplits : s->vsplits_umma) * Mcap * 6);
@@ -497,8 +496,9 @@ extern "C" int b4r_mlm_loss(b4r_session* s, float* stats, void* stream) {
   CeArgs c = ce_args(s);
   c.stats = stats;
   if (s->use_umma) {
-    c.vsplits = s->vsplits_umma;
+    c.target_ctas = 2 * 148; c.max_splits = s->vsplits_umma;
     KL("ce_fwd_umma", launch_ce_fwd_umma(s->umaps, c, st));
+    c.vsplits = -1;  // finalize re-derives the device-side split count
   } else {
     KL("ce_fwd", launch_ce_fwd(c, st));
   }
@@ -723,6 +723,7 @@ extern "C" const uint64_t* b4r_attn_keep_bits(b4r_session* s, int layer, int* wo
   return s->layers[layer].keep;
 }
 extern "C" int b4r_launch_count(b4r_session* s) { return s ? s->launches : 0; }
+extern "C" const void* b4r_debug_buffer(b4r_session* s) { return s ? (const void*)(s->ce_part + (size_t)(s->vsplits_umma - 1) * s->Mcap * 6) : nullptr; }
 extern "C" int b4r_session_set_flag(b4r_session* s, int flag, int value) {
   if (!s) return fail("null session");
   if (flag == 1) { s->use_umma = value != 0; return 0; }

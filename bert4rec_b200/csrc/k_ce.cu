@@ -109,7 +109,7 @@ int ce_block_m() { return CE_BM; }
 struct CeDev {
   const bf16* t; int ldt; const bf16* E; const float* vbias;
   const int* labels; const float* row_w; const int* row_mult; const int* d_counts;
-  int M_cap, V, v_begin, v_end, vsplits, batch;
+  int M_cap, V, v_begin, v_end, vsplits, batch, target_ctas, max_splits;
   float* part; float* lse; float* lab_out; float* stats; float* step_stats;
   bf16* dlogits; int ld_dl; int row_begin, row_count;
 };
@@ -273,6 +273,15 @@ __global__ void __launch_bounds__(1024) ce_finalize_kernel(CeDev a) {
   __shared__ float s_red[32][5];
   const int n_rows = min(a.M_cap, a.d_counts[1]);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (a.vsplits < 0) {  // generation-2 forward: same device-side split formula as ce_fwd_umma_kernel (128-row tiles)
+    const int ntiles = (a.v_end - a.v_begin + 127) / 128;
+    int mt = (n_rows + 127) / 128; if (mt < 1) mt = 1;
+    int vs = a.target_ctas / mt;
+    if (vs > ntiles) vs = ntiles;
+    if (vs > a.max_splits) vs = a.max_splits;
+    if (vs < 1) vs = 1;
+    a.vsplits = vs;
+  }
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // loss_sum, n_valid, correct_masked, correct_all, n_all
   for (int r = tid; r < n_rows; r += 1024) {
     float mn = -INFINITY, l = 0.f, lab = -INFINITY, bv = -INFINITY;
@@ -473,7 +482,7 @@ static CeDev to_dev(const CeArgs& a) {
   CeDev d;
   d.t = a.t; d.ldt = a.ldt; d.E = a.E; d.vbias = a.vbias; d.labels = a.labels; d.row_w = a.row_w; d.row_mult = a.row_mult;
   d.d_counts = a.d_counts; d.M_cap = a.M_cap; d.V = a.V; d.v_begin = a.v_begin; d.v_end = a.v_end;
-  d.vsplits = a.vsplits > 0 ? a.vsplits : 1; d.batch = a.batch;
+  d.vsplits = a.vsplits != 0 ? a.vsplits : 1; d.batch = a.batch; d.target_ctas = a.target_ctas; d.max_splits = a.max_splits;
   d.part = a.part; d.lse = a.lse; d.lab_out = a.lab_out; d.stats = a.stats; d.step_stats = a.step_stats; d.dlogits = a.dlogits; d.ld_dl = a.ld_dl;
   d.row_begin = a.row_begin; d.row_count = a.row_count;
   return d;

@@ -6,6 +6,7 @@
 //               (max, sum-exp, label logit, first arg-max) entirely thread-local -- no shuffles, logits never leave chip.
 // Same partial format / finalize kernel as generation 1 (k_ce.cu); reference ops replaced: tfm MaskedLM projection +
 // SparseSoftmaxCrossEntropyWithLogits + argmax metrics (bert4rec_model.py:143, trainer_utils.py:12-23,49-60).
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 #include "umma.cuh"
@@ -22,7 +23,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 struct CeUmmaDev {
   const float* vbias; const int* labels; const int* d_counts;
-  int M_cap, v_begin, v_end, vsplits;
+  int M_cap, v_begin, v_end, target_ctas, max_splits, debug;
   float* part;
 };
 
@@ -32,11 +33,24 @@ struct CeUmmaCfg {
   static constexpr int STAGES = H == 64 ? 4 : (H == 128 ? 3 : 2);
   static constexpr int A_BYTES = KB * UM_BM * 128;
   static constexpr int B_STAGE_BYTES = KB * UM_BN * 128;
-  static constexpr int SMEM = A_BYTES + STAGES * B_STAGE_BYTES + 2 * UM_BN * 4 + 256 + 1024;  // + bias x2, barriers, align slack
+  static constexpr int SMEM = A_BYTES + STAGES * B_STAGE_BYTES + 2 * UM_BN * 4 + 128 * 5 * 4 + 8 + 256 + 1024;  // + bias x2, merge, barriers, align slack
 };
 
+// Work decomposition is decided ON THE DEVICE from the actual row count (the grid is sized for the capacity):
+//   mtiles = ceil(n_rows/128), vsplits = clamp(ceil(target_ctas / mtiles), 1, min(max_splits, ntiles)),
+//   CTA id -> (m-tile = id / vsplits, split = id % vsplits).  ce_finalize uses the same formula.
+__host__ __device__ inline int ce_umma_dyn_splits(int n_rows, int ntiles, int target_ctas, int max_splits) {
+  int mt = (n_rows + UM_BM - 1) / UM_BM;
+  if (mt < 1) mt = 1;
+  int vs = target_ctas / mt;   // floor: (m-tiles x splits) fits in one wave of target_ctas resident CTAs
+  if (vs > ntiles) vs = ntiles;
+  if (vs > max_splits) vs = max_splits;
+  if (vs < 1) vs = 1;
+  return vs;
+}
+
 template <int H>
-__global__ void __launch_bounds__(192, 1) ce_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(320, 2) ce_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, CeUmmaDev a) {
   using Cfg = CeUmmaCfg<H>;
   constexpr int KB = Cfg::KB, STAGES = Cfg::STAGES;
@@ -46,7 +60,8 @@ __global__ void __launch_bounds__(192, 1) ce_fwd_umma_kernel(const __grid_consta
   unsigned char* sA = smem;
   unsigned char* sB = smem + Cfg::A_BYTES;
   float* sBias = reinterpret_cast<float*>(sB + STAGES * Cfg::B_STAGE_BYTES);  // [2][UM_BN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * UM_BN);
+  float* sMerge = sBias + 2 * UM_BN;                                          // [128][5] second column half's result
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMerge + 128 * 5 + 2);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + STAGES;       // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;   // [2]
@@ -55,18 +70,20 @@ __global__ void __launch_bounds__(192, 1) ce_fwd_umma_kernel(const __grid_consta
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(afull + 1);
 
   const int n_rows = min(a.M_cap, a.d_counts[1]);
-  const int m0 = blockIdx.y * UM_BM;
+  const int ntiles = (a.v_end - a.v_begin + UM_BN - 1) / UM_BN;
+  const int vsplits = ce_umma_dyn_splits(n_rows, ntiles, a.target_ctas, a.max_splits);
+  const int mtile = blockIdx.x / vsplits, split = blockIdx.x % vsplits;
+  const int m0 = mtile * UM_BM;
   if (m0 >= n_rows) return;  // uniform: before any barrier / TMEM allocation
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int ntiles = (a.v_end - a.v_begin + UM_BN - 1) / UM_BN;
-  const int tps = (ntiles + a.vsplits - 1) / a.vsplits;
-  const int tile_lo = blockIdx.x * tps, tile_hi = min(ntiles, tile_lo + tps);
+  const int tps = (ntiles + vsplits - 1) / vsplits;
+  const int tile_lo = split * tps, tile_hi = min(ntiles, tile_lo + tps);
   const int my_tiles = max(0, tile_hi - tile_lo);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { umma::mbar_init(full + i, 1); umma::mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(tfull + i, 1); umma::mbar_init(tempty + i, 128); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(tfull + i, 1); umma::mbar_init(tempty + i, 8); }
     umma::mbar_init(afull, 1);
     umma::fence_barrier_init();
     umma::prefetch_tensormap(&tmA);
@@ -77,6 +94,10 @@ __global__ void __launch_bounds__(192, 1) ce_fwd_umma_kernel(const __grid_consta
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem_base = *tmem_holder;
+  // debug timestamps (B4R_CE_DEBUG & 8): CTA 0 only, first 16 tiles, into the unused tail of the partial buffer
+  long long* dbg = reinterpret_cast<long long*>(a.part + (size_t)(a.max_splits - 1) * a.M_cap * 6);
+  const bool dbg_on = (a.debug & 8) && blockIdx.x == 0;
+#define DBG_T(role, i, slot) do { if (dbg_on && (i) < 16) dbg[((role) * 16 + (i)) * 8 + (slot)] = clock64(); } while (0)
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -87,6 +108,7 @@ __global__ void __launch_bounds__(192, 1) ce_fwd_umma_kernel(const __grid_consta
         const int stage = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
         umma::mbar_wait(empty + stage, ph ^ 1);
+        DBG_T(0, i, 0);
         umma::mbar_expect_tx(full + stage, Cfg::B_STAGE_BYTES);
         const int v0 = a.v_begin + (tile_lo + i) * UM_BN;
         for (int kb = 0; kb < KB; ++kb)
@@ -101,7 +123,9 @@ __global__ void __launch_bounds__(192, 1) ce_fwd_umma_kernel(const __grid_consta
       for (int i = 0; i < my_tiles; ++i) {
         const int stage = i % STAGES, acc = i & 1;
         umma::mbar_wait(tempty + acc, ((i >> 1) & 1) ^ 1);
+        DBG_T(1, i, 0);
         umma::mbar_wait(full + stage, (i / STAGES) & 1);
+        DBG_T(1, i, 1);
         umma::fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * UM_BN;
 #pragma unroll
@@ -110,47 +134,67 @@ __global__ void __launch_bounds__(192, 1) ce_fwd_umma_kernel(const __grid_consta
           const uint32_t b_addr = umma::smem_addr(sB + stage * Cfg::B_STAGE_BYTES + kb * UM_BN * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma::mma_bf16_ss(d_tmem, umma::make_desc_k_sw128(a_addr + k * 32), umma::make_desc_k_sw128(b_addr + k * 32), idesc,
+            if (!(a.debug & 4)) umma::mma_bf16_ss(d_tmem, umma::make_desc_k_sw128(a_addr + k * 32), umma::make_desc_k_sw128(b_addr + k * 32), idesc,
                               (kb | k) ? 1u : 0u);
         }
         umma::mma_commit(empty + stage);  // smem stage reusable once these MMAs have read it
         umma::mma_commit(tfull + acc);    // accumulator ready for the epilogue
+        DBG_T(1, i, 2);
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
-    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    // ===================================================================== epilogue (warps 2..9)
+    // 2 warps per TMEM lane quadrant; warp pair member `half` owns columns [half*64, half*64+64) of every tile
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = quad * 32 + lane;
     const int row = m0 + row_in_tile;
-    const int et = threadIdx.x - 64;           // 0..127 index among the epilogue threads
+    const int et = threadIdx.x - 64;           // 0..255 index among the epilogue threads
     const int label = row < n_rows ? a.labels[row] : -1;
     float run_max = -INFINITY, run_sum = 0.f, lab_logit = -INFINITY, best_v = -INFINITY;
     int best_i = 0x7fffffff;
     constexpr float LOG2E = 1.4426950408889634f;
+    // bias of tile 0 -> smem; later tiles are prefetched one tile ahead into a register
+    float bias_next = 0.f;
+    if (et < UM_BN && my_tiles > 0) {
+      const int v = a.v_begin + tile_lo * UM_BN + et;
+      sBias[et] = v < a.v_end ? a.vbias[v] : -INFINITY;  // -inf masks the out-of-range columns
+    }
     for (int i = 0; i < my_tiles; ++i) {
       const int acc = i & 1;
       const int v0 = a.v_begin + (tile_lo + i) * UM_BN;
-      {
-        const int v = v0 + et;
-        sBias[acc * UM_BN + et] = v < a.v_end ? a.vbias[v] : -INFINITY;  // -inf masks the out-of-range columns
+      if (et < UM_BN && i + 1 < my_tiles) {
+        const int v = v0 + UM_BN + et;
+        bias_next = v < a.v_end ? a.vbias[v] : -INFINITY;
       }
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      if (et == 0) DBG_T(2, i, 0);
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");  // bias of tile i visible; buffer (i+1)&1 no longer read
+      if (et == 0) DBG_T(2, i, 1);
       umma::mbar_wait(tfull + acc, (i >> 1) & 1);
+      if (et == 0) DBG_T(2, i, 2);
       umma::fence_after_sync();
-      const float* bias = sBias + acc * UM_BN;
+      const float* bias = sBias + acc * UM_BN + half * 64;
 #pragma unroll 1
-      for (int c = 0; c < UM_BN / 32; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        umma::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * UM_BN + c * 32, r);
-        umma::tmem_ld_wait();
-        float v[32];
-        float cmax = -INFINITY;
+        if (!(a.debug & 2)) {
+          umma::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * UM_BN + half * 64 + c * 32, r);
+          umma::tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = __uint_as_float(r[j]) + bias[c * 32 + j];
-          cmax = fmaxf(cmax, v[j]);
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint((float)(j + c));
         }
-        const int col0 = v0 + c * 32;
+        float v[32];
+        float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 32 + j);
+          v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+          cm[0] = fmaxf(cm[0], v[j]); cm[1] = fmaxf(cm[1], v[j + 1]); cm[2] = fmaxf(cm[2], v[j + 2]); cm[3] = fmaxf(cm[3], v[j + 3]);
+        }
+        const float cmax = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
+        const int col0 = v0 + half * 64 + c * 32;
         if (cmax > best_v) {  // first maximum wins (columns are visited in increasing order)
           best_v = cmax;
 #pragma unroll
@@ -166,20 +210,36 @@ __global__ void __launch_bounds__(192, 1) ce_fwd_umma_kernel(const __grid_consta
           run_sum *= ex2_approx((run_max - cmax) * LOG2E);  // ex2(-inf) = 0 on the first chunk
           run_max = cmax;
         }
-        if (run_max != -INFINITY) {
+        if (run_max != -INFINITY && !(a.debug & 1)) {
           const float ms = run_max * LOG2E;
-          float s = 0.f;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s += ex2_approx(fmaf(v[j], LOG2E, -ms));
-          run_sum += s;
+          for (int j = 0; j < 32; ++j) s4[j & 3] += ex2_approx(fmaf(v[j], LOG2E, -ms));
+          run_sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
         }
       }
+      if (et == 0) DBG_T(2, i, 3);
       umma::fence_before_sync();
-      umma::mbar_arrive(tempty + acc);
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(tempty + acc);
+      if (et == 0) DBG_T(2, i, 4);
+      if (et < UM_BN && i + 1 < my_tiles) sBias[((i + 1) & 1) * UM_BN + et] = bias_next;
     }
-    if (row < n_rows) {
-      float* out = a.part + ((size_t)blockIdx.x * a.M_cap + row) * 6;
-      out[0] = run_max; out[1] = run_sum; out[2] = lab_logit; out[3] = best_v; out[4] = __int_as_float(best_i); out[5] = 0.f;
+    // merge the two column halves of each row (half 1 -> smem -> half 0)
+    if (half == 1) {
+      float* d = sMerge + row_in_tile * 5;
+      d[0] = run_max; d[1] = run_sum; d[2] = lab_logit; d[3] = best_v; d[4] = __int_as_float(best_i);
+    }
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    if (half == 0 && row < n_rows) {
+      const float* o = sMerge + row_in_tile * 5;
+      const float mn = fmaxf(run_max, o[0]);
+      float l = 0.f;
+      if (mn != -INFINITY) l = run_sum * ex2_approx((run_max - mn) * LOG2E) + o[1] * ex2_approx((o[0] - mn) * LOG2E);
+      const int bi1 = __float_as_int(o[4]);
+      if (o[3] > best_v || (o[3] == best_v && bi1 < best_i)) { best_v = o[3]; best_i = bi1; }
+      float* out = a.part + ((size_t)split * a.M_cap + row) * 6;
+      out[0] = mn; out[1] = l; out[2] = fmaxf(lab_logit, o[2]); out[3] = best_v; out[4] = __int_as_float(best_i); out[5] = 0.f;
     }
   }
   umma::fence_before_sync();
@@ -198,12 +258,15 @@ bool ce_umma_make_maps(CeUmmaMaps* maps, const bf16* t, int M_cap, const bf16* E
 }
 
 int ce_umma_block_m() { return UM_BM; }
+int ce_umma_splits(int n_rows, int ntiles, int target_ctas, int max_splits) { return ce_umma_dyn_splits(n_rows, ntiles, target_ctas, max_splits); }
 
 cudaError_t launch_ce_fwd_umma(const CeUmmaMaps& maps, const CeArgs& a, cudaStream_t st) {
   CeUmmaDev d;
   d.vbias = a.vbias; d.labels = a.labels; d.d_counts = a.d_counts; d.M_cap = a.M_cap; d.v_begin = a.v_begin; d.v_end = a.v_end;
-  d.vsplits = a.vsplits > 0 ? a.vsplits : 1; d.part = a.part;
-  dim3 grid(d.vsplits, (a.M_cap + UM_BM - 1) / UM_BM);
+  d.target_ctas = a.target_ctas; d.max_splits = a.max_splits; d.part = a.part;
+  { const char* e = getenv("B4R_CE_DEBUG"); d.debug = e ? atoi(e) : 0; }
+  // capacity grid: enough CTAs for every (m-tile, split) pair any row count can produce
+  dim3 grid(a.target_ctas + (a.M_cap + UM_BM - 1) / UM_BM);
   const CUtensorMap& tmA = *reinterpret_cast<const CUtensorMap*>(maps.a);
   const CUtensorMap& tmB = *reinterpret_cast<const CUtensorMap*>(maps.b);
 #define B4R_UM(HH)                                                                                                  \
@@ -213,7 +276,7 @@ cudaError_t launch_ce_fwd_umma(const CeUmmaMaps& maps, const CeArgs& a, cudaStre
       cudaFuncSetAttribute(ce_fwd_umma_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, CeUmmaCfg<HH>::SMEM); \
       done_##HH = true;                                                                                             \
     }                                                                                                               \
-    ce_fwd_umma_kernel<HH><<<grid, 192, CeUmmaCfg<HH>::SMEM, st>>>(tmA, tmB, d);                                    \
+    ce_fwd_umma_kernel<HH><<<grid, 320, CeUmmaCfg<HH>::SMEM, st>>>(tmA, tmB, d);                                    \
     break;                                                                                                          \
   }
   switch (a.H) {

@@ -154,6 +154,7 @@ struct CeArgs {
   int M_cap, H, V;
   int v_begin, v_end;                // vocabulary shard handled here (whole vocab: 0, V)
   int vsplits;
+  int target_ctas, max_splits;       // generation 2: device-side split choice (vsplits < 0 in finalize = dynamic)
   int batch;                         // batch size (weight of the per-batch loss in the running mean)
   float* part;                       // [vsplits][M_cap][6] partial (max, sum, label_logit, best_val, best_idx, unused)
   float* lse;                        // [M_cap]
