@@ -184,7 +184,9 @@ struct b4r_session {
   bool use_umma = false;
   CeUmmaMaps umaps;
   bf16* dlogits; int dl_rows;
-  float* dt_part; int dt_splits;
+  float* dt_part; int dt_splits, dt_max_splits;
+  float *p_dE, *p_dbias2; int me_splits;
+  ReduceJob* d_ce_jobs;
   bf16* d_tpre;
   float *p_head_ln, *p_wt, *p_vbias; int s_wt, vb_splits;
   // backward scratch
@@ -304,7 +306,19 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
     if (sp > 32) sp = 32;
     s->dt_splits = sp;
   }
-  s->dt_part = b.take<float>((size_t)s->dt_splits * Mcap * H);
+  {
+    int vtiles = (V + 127) / 128;
+    s->dt_max_splits = vtiles < 24 ? vtiles : 24;
+    int ms = (2 * 148) / vtiles;
+    if (ms < 1) ms = 1;
+    if (ms > 8) ms = 8;
+    s->me_splits = ms;
+  }
+  const bool bwd_umma = ce_bwd_umma_supported(H);
+  s->dt_part = b.take<float>((size_t)(bwd_umma && s->dt_max_splits > s->dt_splits ? s->dt_max_splits : s->dt_splits) * Mcap * H);
+  s->p_dE = b.take<float>(bwd_umma ? (size_t)s->me_splits * V * H : 8);
+  s->p_dbias2 = b.take<float>(bwd_umma ? (size_t)s->me_splits * V : 8);
+  s->d_ce_jobs = b.take<ReduceJob>(2);
   s->d_tpre = b.take<bf16>((size_t)Mcap * H);
   const int head_parts = ln_bwd_parts(Mcap);
   s->p_head_ln = b.take<float>((size_t)head_parts * 3 * H);
@@ -385,6 +399,10 @@ extern "C" int b4r_session_create(const b4r_config* cfg, int batch, int seq_len,
   vb[0] = ReduceJob{s->p_vbias, grads ? grads + s->lay.find("head/output_bias") : nullptr, s->vb_splits, s->V, (long long)s->V, 0};
   vb[1] = vb[0]; vb[1].accumulate = 1;
   CK(cudaMemcpy(s->d_vb_jobs, vb, sizeof(vb), cudaMemcpyHostToDevice));
+  ReduceJob cj[2];
+  cj[0] = ReduceJob{s->p_dE, grads ? grads + s->lay.find("word_embeddings") : nullptr, s->me_splits, s->V * s->H, (long long)s->V * s->H, 0};
+  cj[1] = ReduceJob{s->p_dbias2, grads ? grads + s->lay.find("head/output_bias") : nullptr, s->me_splits, s->V, (long long)s->V, 0};
+  CK(cudaMemcpy(s->d_ce_jobs, cj, sizeof(cj), cudaMemcpyHostToDevice));
   CK(cudaMemset(s->stats, 0, 8 * sizeof(float)));
   CK(cudaMemset(s->step_stats, 0, 8 * sizeof(float)));
   s->use_umma = ce_umma_make_maps(&s->umaps, s->t, s->Mcap, s->shadow + s->lay.find("word_embeddings"), s->V, s->H) &&
@@ -529,13 +547,25 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
   float* G = s->grads;
   const float od = s->cfg.output_dropout;
   const int64_t oE = s->lay.find("word_embeddings");
+  const bool bwd_umma = s->use_umma && ce_bwd_umma_supported(H);
   // gradient accumulators that are scatter / accumulate targets
-  CK(cudaMemsetAsync(G + oE, 0, (size_t)V * H * sizeof(float), st));
+  if (!bwd_umma) CK(cudaMemsetAsync(G + oE, 0, (size_t)V * H * sizeof(float), st));
   CK(cudaMemsetAsync(s->dxa, 0, (size_t)T * H * sizeof(float), st));
-  // ---- CE backward, chunked over rows
   CeArgs c = ce_args(s);
+  if (bwd_umma) {
+    // ---- CE backward, generation 2: two tcgen05 passes that recompute the logits tile, nothing [M,V]-sized in memory
+    CeBwdArgs ba{};
+    ba.vbias = c.vbias; ba.lse = s->lse; ba.row_w = s->row_w; ba.labels = s->labels; ba.d_counts = s->counts;
+    ba.M_cap = Mcap; ba.V = V; ba.H = H; ba.target_ctas = 2 * 148; ba.max_splits = s->dt_max_splits; ba.msplits = s->me_splits;
+    ba.out = s->dt_part; ba.dbias_out = nullptr;
+    KL("ce_bwd_umma:dT", launch_ce_bwd_umma(s->umaps, ba, true, st));
+    ba.out = s->p_dE; ba.dbias_out = s->p_dbias2;
+    KL("ce_bwd_umma:dE", launch_ce_bwd_umma(s->umaps, ba, false, st));
+    KL("grad_reduce:ce", launch_grad_reduce(s->d_ce_jobs, 2, V * H, st));
+  }
+  // ---- CE backward, generation 1: dlogits materialised in bf16, chunked over rows
   int chunk = 0;
-  for (int r0 = 0; r0 < Mcap; r0 += s->dl_rows, ++chunk) {
+  for (int r0 = 0; r0 < (bwd_umma ? 0 : Mcap); r0 += s->dl_rows, ++chunk) {
     const int rc = (Mcap - r0) < s->dl_rows ? (Mcap - r0) : s->dl_rows;
     c.row_begin = r0; c.row_count = rc;
     KL("ce_dlogits", launch_ce_dlogits(c, st));
@@ -553,7 +583,8 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
   }
   // ---- MLM transform backward
   KL("head_bwd_rows", launch_head_bwd_rows(s->dt_part, s->dt_splits, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
-                          P + s->lay.find("head/ln/gamma"), s->d_tpre, s->p_head_ln, Mcap, s->counts, H, st));
+                          P + s->lay.find("head/ln/gamma"), s->d_tpre, s->p_head_ln, Mcap, s->counts, H, st,
+                          bwd_umma ? (V + 127) / 128 : 0, bwd_umma ? 2 * 148 : 0, bwd_umma ? s->dt_max_splits : 0));
   const bf16* xL = s->layers.back().out;
   {
     WgradArgs w{};

@@ -23,8 +23,17 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      uint32_t thr16, float inv_keep, uint64_t seed, uint32_t site,
                                                      uint32_t step, int nsplit, size_t split_stride,
                                                      const bf16* __restrict__ t_pre, const int* __restrict__ d_M,
-                                                     const long long* __restrict__ d_step) {
+                                                     const long long* __restrict__ d_step, int dyn_vtiles = 0,
+                                                     int dyn_target = 0, int dyn_max = 0) {
   if (d_M) M = min(M, *d_M);
+  if (HEAD && dyn_max > 0) {  // split count chosen on the device by the generation-2 dT pass (same formula)
+    int mt = (M + 127) / 128; if (mt < 1) mt = 1;
+    int vs = dyn_target / mt;
+    if (vs > dyn_vtiles) vs = dyn_vtiles;
+    if (vs > dyn_max) vs = dyn_max;
+    if (vs < 1) vs = 1;
+    nsplit = vs;
+  }
   if (d_step) step += (uint32_t)(*d_step);
   constexpr int LPR = H / 8, RPW = 32 / LPR, RPC = 8 * RPW;
   __shared__ float s_red[3][RPC][H + 1];
@@ -131,13 +140,13 @@ cudaError_t launch_ln_bwd(const float* d_out, const bf16* pre, const float* mean
 cudaError_t launch_head_bwd_rows(const float* dt_part, int nsplit, size_t split_stride, const bf16* t_pre,
                                  const bf16* act, const float* mean, const float* rstd, const float* gamma,
                                  bf16* d_tpre, float* partials, int M_cap, const int* d_counts, int H,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, int dyn_vtiles, int dyn_target, int dyn_max) {
   int grid = ln_bwd_parts(M_cap);
   const int* d_M = d_counts ? d_counts + 1 : nullptr;
   switch (H) {
-    case 64: ln_bwd_kernel<64, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr); break;
-    case 128: ln_bwd_kernel<128, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr); break;
-    case 256: ln_bwd_kernel<256, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr); break;
+    case 64: ln_bwd_kernel<64, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
+    case 128: ln_bwd_kernel<128, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
+    case 256: ln_bwd_kernel<256, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

@@ -177,11 +177,21 @@ struct CeUmmaMaps { alignas(64) unsigned char a[128]; alignas(64) unsigned char 
 bool ce_umma_make_maps(CeUmmaMaps* maps, const bf16* t, int M_cap, const bf16* E, int V, int H);
 cudaError_t launch_ce_fwd_umma(const CeUmmaMaps& maps, const CeArgs& a, cudaStream_t st);
 int ce_umma_block_m();
+// generation 2 backward (k_ce_bwd_umma.cu): row_is_m = true -> dT partials, false -> dE partials + d(output bias)
+struct CeBwdArgs {
+  const float* vbias; const float* lse; const float* row_w; const int* labels; const int* d_counts;
+  int M_cap, V, H;
+  int target_ctas, max_splits;   // dT pass: device-side vocabulary split choice
+  int msplits;                   // dE pass: static row splits
+  float* out; float* dbias_out;
+};
+bool ce_bwd_umma_supported(int H);
+cudaError_t launch_ce_bwd_umma(const CeUmmaMaps& maps, const CeBwdArgs& a, bool row_is_m, cudaStream_t st);
 // MLM transform backward over rows: dt = sum_s dt_part[s] ; LN bwd ; gelu bwd -> d_tpre (bf16) ; partials {dgamma,dbeta,dbias}
 cudaError_t launch_head_bwd_rows(const float* dt_part, int nsplit, size_t split_stride, const bf16* t_pre,
                                  const bf16* act, const float* mean, const float* rstd, const float* gamma,
                                  bf16* d_tpre, float* partials, int M_cap, const int* d_counts, int H,
-                                 cudaStream_t st);
+                                 cudaStream_t st, int dyn_vtiles = 0, int dyn_target = 0, int dyn_max = 0);
 
 // ------------------------------------------------------------------ ranking (k_rank.cu)
 // scores[m][c] = t[m] . E[cand[m][c]] + vbias[cand[m][c]] ; ranking = stable descending order (lower index first on ties)

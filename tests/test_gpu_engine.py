@@ -434,3 +434,30 @@ def test_ce_forward_tcgen05_matches_mma_sync_generation(name):
     assert float(a[1]) == float(b[1]) and float(a[4]) == float(b[4])
     assert abs(float(a[0]) - float(b[0])) / float(a[0]) < 1e-5, (a, b)
     assert abs(float(a[2]) - float(b[2])) <= 1 and abs(float(a[3]) - float(b[3])) <= 1
+
+
+@pytest.mark.parametrize("name", ["h64_s50", "h64_s200", "h128_s37"])
+def test_ce_backward_tcgen05_matches_materialised_generation(name):
+    """Generation 2 CE backward (two tcgen05 recompute passes, nothing [M,V]-sized in memory) against generation 1
+    (bf16 dlogits materialised + mma.sync GEMMs): all parameter gradients agree to bf16 noise."""
+    store, kw, B, S, P = build(name)
+    store.ensure_training_buffers()
+    batch = to_cuda(make_batch(B, S, P, kw["vocab_size"], seed=43))
+    sess = store.session(B, S, P)
+    grads = []
+    for flag in (0, 1):
+        sess.set_flag(1, flag)
+        sess.encode(batch["input_word_ids"], batch["input_mask"], training=True)
+        sess.select(batch["masked_lm_positions"], batch["masked_lm_ids"], batch["masked_lm_weights"], mode=0, want_aux=True)
+        sess.transform(); sess.loss(); sess.backward()
+        torch.cuda.synchronize()
+        grads.append(store.grad_dict())
+    sess.set_flag(1, 1)
+    g1, g2 = grads
+    gmax = max(float(v.norm()) for v in g1.values())
+    bad = []
+    for k in g1:
+        err = float((g1[k].double() - g2[k].double()).norm())
+        if not err < 1e-2 * float(g1[k].norm()) + 1e-5 * gmax:
+            bad.append((k, err, float(g1[k].norm())))
+    assert not bad, bad
