@@ -179,7 +179,7 @@ struct b4r_session {
   // head
   int *rows, *labels, *row_mult, *counts; float* row_w;
   bf16 *t_pre, *t_act, *t; float *hmean, *hrstd;
-  float *ce_part, *lse, *lab, *stats, *step_stats;
+  float *ce_part, *lse, *lab, *stats, *step_stats, *fin_part; int* ticket;
   int vsplits, vsplits_umma;
   bool use_umma = false;
   CeUmmaMaps umaps;
@@ -289,6 +289,7 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
   s->ce_part = b.take<float>((size_t)(s->vsplits > s->vsplits_umma ? s->vsplits : s->vsplits_umma) * Mcap * 6);
   s->lse = b.take<float>(Mcap); s->lab = b.take<float>(Mcap);
   s->stats = b.take<float>(8); s->step_stats = b.take<float>(8);
+  s->fin_part = b.take<float>(64 * 5); s->ticket = b.take<int>(4);
   {
     // dlogits chunk: at most ~256 MB so that it stays close to the L2 / small in HBM
     size_t max_rows = ((size_t)256 << 20) / ((size_t)s->Vp * 2);
@@ -405,6 +406,7 @@ extern "C" int b4r_session_create(const b4r_config* cfg, int batch, int seq_len,
   CK(cudaMemcpy(s->d_ce_jobs, cj, sizeof(cj), cudaMemcpyHostToDevice));
   CK(cudaMemset(s->stats, 0, 8 * sizeof(float)));
   CK(cudaMemset(s->step_stats, 0, 8 * sizeof(float)));
+  CK(cudaMemset(s->ticket, 0, 4 * sizeof(int)));
   s->use_umma = ce_umma_make_maps(&s->umaps, s->t, s->Mcap, s->shadow + s->lay.find("word_embeddings"), s->V, s->H) &&
                 getenv("B4R_DISABLE_UMMA") == nullptr;
   CK(cudaMemset(s->counts, 0, 8 * sizeof(int)));
@@ -504,6 +506,7 @@ static CeArgs ce_args(b4r_session* s) {
   c.labels = s->labels; c.row_w = s->row_w; c.row_mult = s->row_mult; c.d_counts = s->counts;
   c.M_cap = s->Mcap; c.H = s->H; c.V = s->V; c.v_begin = 0; c.v_end = s->V; c.vsplits = s->vsplits; c.batch = s->B;
   c.part = s->ce_part; c.lse = s->lse; c.lab_out = s->lab; c.stats = nullptr; c.step_stats = s->step_stats;
+  c.fin_part = s->fin_part; c.ticket = s->ticket;
   c.dlogits = s->dlogits; c.ld_dl = s->Vp;
   return c;
 }

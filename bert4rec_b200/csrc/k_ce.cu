@@ -268,9 +268,11 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(CeDev a) {
   }
 }
 
-// Single CTA: merge the vsplits partials per row, emit lse, accumulate the step statistics in a fixed order.
-__global__ void __launch_bounds__(1024) ce_finalize_kernel(CeDev a) {
-  __shared__ float s_red[32][5];
+// Multi-CTA: merge the vsplits partials per row, emit lse; per-CTA partial statistics; the LAST CTA to finish (atomic
+// ticket) sums them in CTA-index order (deterministic) and accumulates the step / running statistics.
+__global__ void __launch_bounds__(256) ce_finalize_kernel(CeDev a, float* __restrict__ fin_part, int* __restrict__ ticket) {
+  __shared__ float s_red[8][5];
+  __shared__ int s_last;
   const int n_rows = min(a.M_cap, a.d_counts[1]);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (a.vsplits < 0) {  // generation-2 forward: same device-side split formula as ce_fwd_umma_kernel (128-row tiles)
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(1024) ce_finalize_kernel(CeDev a) {
     a.vsplits = vs;
   }
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // loss_sum, n_valid, correct_masked, correct_all, n_all
-  for (int r = tid; r < n_rows; r += 1024) {
+  for (int r = blockIdx.x * 256 + tid; r < n_rows; r += gridDim.x * 256) {
     float mn = -INFINITY, l = 0.f, lab = -INFINITY, bv = -INFINITY;
     int bi = 0x7fffffff;
     for (int s = 0; s < a.vsplits; ++s) {
@@ -317,11 +319,23 @@ __global__ void __launch_bounds__(1024) ce_finalize_kernel(CeDev a) {
   __shared__ float s_tot[5];
   if (tid < 5) {
     float v = 0.f;
-    for (int w = 0; w < 32; ++w) v += s_red[w][tid];
+    for (int w = 0; w < 8; ++w) v += s_red[w][tid];
+    fin_part[blockIdx.x * 5 + tid] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < 5) {
+    float v = 0.f;
+    for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(fin_part + b * 5 + tid);
     s_tot[tid] = v;
     a.step_stats[tid] = v;
     if (a.stats) a.stats[tid] += v;
   }
+  if (tid == 0) *ticket = 0;
   __syncthreads();
   if (tid == 0 && a.stats) {
     // Keras running means: loss = Mean(batch loss, weight = batch size); masked_accuracy = Mean over batches
@@ -542,7 +556,9 @@ cudaError_t launch_ce_count(const CeArgs& a, const float* s_gt, int* beat, cudaS
 }
 
 cudaError_t launch_ce_finalize(const CeArgs& a, cudaStream_t st) {
-  ce_finalize_kernel<<<1, 1024, 0, st>>>(to_dev(a));
+  int blocks = (a.M_cap + 255) / 256;
+  if (blocks > 64) blocks = 64;
+  ce_finalize_kernel<<<blocks, 256, 0, st>>>(to_dev(a), a.fin_part, a.ticket);
   return cudaGetLastError();
 }
 

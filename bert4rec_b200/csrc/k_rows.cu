@@ -158,34 +158,55 @@ cudaError_t launch_head_bwd_rows(const float* dt_part, int nsplit, size_t split_
 __global__ void __launch_bounds__(256) grad_reduce_kernel(const ReduceJob* __restrict__ jobs) {
   __shared__ float s[8][33];
   const ReduceJob job = jobs[blockIdx.y];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + tx;
-  if (blockIdx.x * 32 >= job.len) return;
-  float acc = 0.f;
-  if (col < job.len) {
-    const float* p = job.src + col;
-    int k = ty;
-    for (; k + 24 < job.nparts; k += 32) {
-      float a = p[(size_t)k * job.part_stride], b = p[(size_t)(k + 8) * job.part_stride];
-      float c = p[(size_t)(k + 16) * job.part_stride], d = p[(size_t)(k + 24) * job.part_stride];
-      acc += a; acc += b; acc += c; acc += d;
-    }
-    for (; k < job.nparts; k += 8) acc += p[(size_t)k * job.part_stride];
-  }
-  s[ty][tx] = acc;
-  __syncthreads();
-  if (ty == 0 && col < job.len) {
-    float v = 0.f;
+  const int c0 = blockIdx.x * 1024;  // every block owns 1024 consecutive columns of its job
+  if (c0 >= job.len) return;
+  if (job.nparts <= 8) {
+    // few, long partials (split-K weight gradients, vocabulary-sized buffers): one thread per column, coalesced
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v += s[r][tx];
-    if (job.accumulate) v += job.dst[col];
-    job.dst[col] = v;
+    for (int k = 0; k < 4; ++k) {
+      const int col = c0 + k * 256 + threadIdx.x;
+      if (col < job.len) {
+        float v = 0.f;
+        for (int p = 0; p < job.nparts; ++p) v += job.src[(size_t)p * job.part_stride + col];
+        if (job.accumulate) v += job.dst[col];
+        job.dst[col] = v;
+      }
+    }
+    return;
+  }
+  // many short partials (per-CTA bias / LayerNorm sums): 32 columns x 8 part-lanes per pass
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int sub = 0; sub < 32; ++sub) {
+    const int cb = c0 + sub * 32;
+    if (cb >= job.len) break;  // uniform
+    const int col = cb + tx;
+    float acc = 0.f;
+    if (col < job.len) {
+      const float* p = job.src + col;
+      int k = ty;
+      for (; k + 24 < job.nparts; k += 32) {
+        float a = p[(size_t)k * job.part_stride], b = p[(size_t)(k + 8) * job.part_stride];
+        float c = p[(size_t)(k + 16) * job.part_stride], d = p[(size_t)(k + 24) * job.part_stride];
+        acc += a; acc += b; acc += c; acc += d;
+      }
+      for (; k < job.nparts; k += 8) acc += p[(size_t)k * job.part_stride];
+    }
+    s[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && col < job.len) {
+      float v = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v += s[r][tx];
+      if (job.accumulate) v += job.dst[col];
+      job.dst[col] = v;
+    }
+    __syncthreads();
   }
 }
 
 cudaError_t launch_grad_reduce(const ReduceJob* d_jobs, int njobs, int max_len, cudaStream_t st) {
   if (njobs <= 0) return cudaSuccess;
-  dim3 grid((max_len + 31) / 32, njobs);
+  dim3 grid((max_len + 1023) / 1024, njobs);
   grad_reduce_kernel<<<grid, 256, 0, st>>>(d_jobs);
   return cudaGetLastError();
 }

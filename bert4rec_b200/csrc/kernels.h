@@ -159,6 +159,7 @@ struct CeArgs {
   float* part;                       // [vsplits][M_cap][6] partial (max, sum, label_logit, best_val, best_idx, unused)
   float* lse;                        // [M_cap]
   float* lab_out;                    // optional [M_cap]: logit of the label column (ground-truth score)
+  float* fin_part; int* ticket;      // finalize scratch: [64][5] floats + one zero-initialised int
   float* stats;                      // optional float[16] running accumulators: {loss_sum, n_valid, n_correct_masked,
                                      // n_correct_all, n_all, sum(batch_loss*batch), sum(batch), sum(batch_masked_acc), n_steps}
   float* step_stats;                 // this step only (same layout)
