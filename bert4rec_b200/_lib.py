@@ -65,6 +65,7 @@ _SIGNATURES = {
     "b4r_mlm_rows": (_P, [_P]),
     "b4r_step_stats": (_P, [_P]),
     "b4r_attn_keep_bits": (_P, [_P, C.c_int, C.POINTER(C.c_int)]),
+    "b4r_layer_tensor": (_P, [_P, C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b4r_launch_count": (C.c_int, [_P]),
     "b4r_session_set_flag": (C.c_int, [_P, C.c_int, C.c_int]),
     "b4r_debug_buffer": (_P, [_P]),

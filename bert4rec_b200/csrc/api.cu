@@ -183,6 +183,8 @@ struct b4r_session {
   int vsplits, vsplits_umma;
   bool use_umma = false;
   CeUmmaMaps umaps;
+  bool use_fused = false;   // whole-encoder forward in one tcgen05 launch (k_enc_fused.cu)
+  void* d_enc_tables = nullptr;
   bf16* dlogits; int dl_rows;
   float* dt_part; int dt_splits, dt_max_splits;
   float *p_dE, *p_dbias2; int me_splits;
@@ -343,6 +345,7 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
   job(s->p_embln + H, off("emb_ln/beta"), s->emb_bsplits * S, H, 2 * H);
   s->d_jobs = b.take<ReduceJob>(256);
   s->d_vb_jobs = b.take<ReduceJob>(2);
+  s->d_enc_tables = b.take<unsigned char>(enc_fused_table_bytes(s->cfg.num_layers));
   return b.off + 256;
 }
 
@@ -410,6 +413,23 @@ extern "C" int b4r_session_create(const b4r_config* cfg, int batch, int seq_len,
   s->use_umma = ce_umma_make_maps(&s->umaps, s->t, s->Mcap, s->shadow + s->lay.find("word_embeddings"), s->V, s->H) &&
                 getenv("B4R_DISABLE_UMMA") == nullptr;
   CK(cudaMemset(s->counts, 0, 8 * sizeof(int)));
+  if (enc_fused_supported(s->H, s->N, s->S, s->I)) {
+    const int Ln = s->cfg.num_layers;
+    std::vector<EncFusedLayerHost> lh(Ln);
+    std::vector<const bf16*> wp((size_t)Ln * 4);
+    for (int l = 0; l < Ln; ++l) {
+      LayerBuf& L = s->layers[l];
+      const float* P = s->params;
+      lh[l] = EncFusedLayerHost{P + L.bqkv, P + L.bo, P + L.g1, P + L.be1, P + L.b1, P + L.b2, P + L.g2, P + L.be2,
+                                L.qkv, L.ctx, L.a_pre, L.y, L.h_pre, L.h, L.o_pre, L.out, L.lse, L.mean1, L.rstd1, L.mean2, L.rstd2, L.keep};
+      wp[l * 4 + 0] = s->shadow + L.wqkv; wp[l * 4 + 1] = s->shadow + L.wo; wp[l * 4 + 2] = s->shadow + L.w1; wp[l * 4 + 3] = s->shadow + L.w2;
+    }
+    std::vector<unsigned char> host(enc_fused_table_bytes(Ln));
+    if (enc_fused_build_tables(lh.data(), Ln, s->I, wp.data(), host.data(), s->d_enc_tables)) {
+      CK(cudaMemcpy(s->d_enc_tables, host.data(), host.size(), cudaMemcpyHostToDevice));
+      s->use_fused = true;
+    }
+  }
   *out = s;
   return 0;
 }
@@ -434,6 +454,15 @@ extern "C" int b4r_encode(b4r_session* s, const int64_t* ids, const int64_t* mas
   const float* P = s->params;
   const bf16* W = s->shadow;
   s->ids = ids; s->mask = mask;
+  if (s->use_fused) {
+    EncFusedArgs f{};
+    f.ids = ids; f.mask = mask; f.table = W + s->lay.find("word_embeddings"); f.pos = W + s->lay.find("position_embedding");
+    f.emb_g = P + s->lay.find("emb_ln/gamma"); f.emb_b = P + s->lay.find("emb_ln/beta"); f.x0 = s->x0; f.dev_tables = s->d_enc_tables;
+    f.B = s->B; f.S = s->S; f.V = s->V; f.L = s->cfg.num_layers; f.I = I; f.training = training;
+    f.out_drop = od; f.attn_drop = ad; f.seed = seed; f.step = step; f.d_step = d_step;
+    KL("enc_fwd_fused", launch_enc_fwd_fused(f, st));
+    return 0;
+  }
   KL("embed_ln_fwd", launch_embed_ln_fwd(ids, W + s->lay.find("word_embeddings"), W + s->lay.find("position_embedding"),
                          P + s->lay.find("emb_ln/gamma"), P + s->lay.find("emb_ln/beta"), s->x0, s->B, s->S, H, s->V, od,
                          seed, step, d_step, st));
@@ -756,11 +785,41 @@ extern "C" const uint64_t* b4r_attn_keep_bits(b4r_session* s, int layer, int* wo
   if (words_per_row) *words_per_row = attn_mask_words(s->S);
   return s->layers[layer].keep;
 }
+// saved activation of one encoder layer by name (bf16 [T, cols] unless *is_f32): development / parity-test aid
+extern "C" const void* b4r_layer_tensor(b4r_session* s, int layer, const char* name, int* cols, int* is_f32) {
+  if (!s || !name || layer < 0 || layer >= s->cfg.num_layers) return nullptr;
+  const LayerBuf& L = s->layers[layer];
+  const std::string n(name);
+  int c = s->H, f = 0;
+  const void* p = nullptr;
+  if (n == "x0") p = s->x0;
+  else if (n == "qkv") { p = L.qkv; c = 3 * s->H; }
+  else if (n == "ctx") p = L.ctx;
+  else if (n == "a_pre") p = L.a_pre;
+  else if (n == "y") p = L.y;
+  else if (n == "h_pre") { p = L.h_pre; c = s->I; }
+  else if (n == "h") { p = L.h; c = s->I; }
+  else if (n == "o_pre") p = L.o_pre;
+  else if (n == "out") p = L.out;
+  else if (n == "mean1") { p = L.mean1; c = 1; f = 1; }
+  else if (n == "rstd1") { p = L.rstd1; c = 1; f = 1; }
+  else if (n == "mean2") { p = L.mean2; c = 1; f = 1; }
+  else if (n == "rstd2") { p = L.rstd2; c = 1; f = 1; }
+  else if (n == "lse") { p = L.lse; c = 1; f = 1; }
+  if (cols) *cols = c;
+  if (is_f32) *is_f32 = f;
+  return p;
+}
 extern "C" int b4r_launch_count(b4r_session* s) { return s ? s->launches : 0; }
 extern "C" const void* b4r_debug_buffer(b4r_session* s) { return s ? (const void*)(s->ce_part + (size_t)(s->vsplits_umma - 1) * s->Mcap * 6) : nullptr; }
 extern "C" int b4r_session_set_flag(b4r_session* s, int flag, int value) {
   if (!s) return fail("null session");
   if (flag == 1) { s->use_umma = value != 0; return 0; }
+  if (flag == 2) {
+    if (value && !s->d_enc_tables) return fail("fused encoder unavailable");
+    s->use_fused = value != 0 && enc_fused_supported(s->H, s->N, s->S, s->I);
+    return 0;
+  }
   return fail("unknown flag %d", flag);
 }
 extern "C" int b4r_profile_enable(b4r_session* s, int on) {

@@ -107,6 +107,29 @@ cudaError_t launch_attn_fwd(const AttnArgs& a, cudaStream_t st);
 cudaError_t launch_attn_bwd(const AttnArgs& a, cudaStream_t st);
 int attn_mask_words(int S);
 
+// ------------------------------------------------------------------ fused encoder forward (k_enc_fused.cu)
+// Whole encoder stack in one launch (tcgen05 + TMEM + TMA), hidden 64 / 2 heads / seq_len <= 128 / inner_dim % 64 == 0.
+struct EncFusedLayerHost {
+  const float *bqkv, *bo, *g1, *be1, *b1, *b2, *g2, *be2;
+  bf16 *qkv, *ctx, *a_pre, *y, *h_pre, *h, *o_pre, *out;
+  float *lse, *mean1, *rstd1, *mean2, *rstd2;
+  uint64_t* keep;
+};
+struct EncFusedArgs {
+  const int64_t* ids; const int64_t* mask;
+  const bf16* table; const bf16* pos; const float* emb_g; const float* emb_b;
+  bf16* x0;
+  const void* dev_tables;   // device block built by enc_fused_build_tables
+  int B, S, V, L, I, training;
+  float out_drop, attn_drop; uint64_t seed; uint32_t step; const long long* d_step;
+};
+bool enc_fused_supported(int H, int N, int S, int I);
+size_t enc_fused_smem_bytes(int I);
+size_t enc_fused_table_bytes(int L);
+// w_ptrs: [L][4] bf16 device pointers (wqkv, wo, w1, w2); host: staging buffer of enc_fused_table_bytes(L)
+bool enc_fused_build_tables(const EncFusedLayerHost* layers, int L, int I, const bf16* const* w_ptrs, void* host, void* dev_base);
+cudaError_t launch_enc_fwd_fused(const EncFusedArgs& a, cudaStream_t st);
+
 // ------------------------------------------------------------------ row kernels (k_rows.cu)
 // LayerNorm backward over rows (+ dropout of the branch gradient):
 //   d_pre = LNbwd(d_out) ; d_branch = drop(d_pre) (bf16) ; partials[cta] = {dgamma[H], dbeta[H], dbranch_colsum[H]}

@@ -296,6 +296,15 @@ class Session:
         m = ((words.unsqueeze(-1) >> bits) & 1).reshape(self.B, N, S, W * 64)[..., :S]
         return m.to(torch.uint8)
 
+    def layer_tensor(self, layer, name):
+        """Saved activation of one encoder layer (see b4r_layer_tensor); zero-copy view over the workspace."""
+        cols, f32 = C.c_int(), C.c_int()
+        p = self.lib.b4r_layer_tensor(self.h, layer, name.encode(), C.byref(cols), C.byref(f32))
+        if not p:
+            raise KeyError(name)
+        rows = self.B * self.S * (self.store.N if name == "lse" else 1)
+        return self._view(p, (rows, cols.value), torch.float32 if f32.value else torch.bfloat16)
+
     def launch_count(self):
         return self.lib.b4r_launch_count(self.h)
 

@@ -111,8 +111,12 @@ const int32_t* b4r_mlm_counts(b4r_session* s);               /* int32[2] = {n_va
 const int32_t* b4r_mlm_rows(b4r_session* s);                 /* int32 [n_rows] flat row index b*seq_len+pos */
 float* b4r_step_stats(b4r_session* s);  /* float[8] {loss_sum, n_valid, correct_masked, correct_all, n_all} of the last step */
 const uint64_t* b4r_attn_keep_bits(b4r_session* s, int layer, int* words_per_row);
+/* saved activation of encoder layer `layer` by name ("x0","qkv","ctx","a_pre","y","h_pre","h","o_pre","out": bf16
+ * [batch*seq_len, *cols]; "mean1","rstd1","mean2","rstd2": fp32 [batch*seq_len]; "lse": fp32 [batch*heads*seq_len]) */
+const void* b4r_layer_tensor(b4r_session* s, int layer, const char* name, int* cols, int* is_f32);
 int b4r_launch_count(b4r_session* s);   /* kernels launched through this session so far */
-/* flag 1: tcgen05/TMA generation of the tied-projection kernels (1, default) or the mma.sync generation (0) */
+/* flag 1: tcgen05/TMA generation of the tied-projection kernels (1, default) or the mma.sync generation (0);
+ * flag 2: whole-encoder fused tcgen05 forward (1, default where the shape allows) or the layered kernels (0) */
 int b4r_session_set_flag(b4r_session* s, int flag, int value);
 const void* b4r_debug_buffer(b4r_session* s);  /* kernel-internal timestamps when B4R_CE_DEBUG&8 (development aid) */
 /* per-kernel CUDA-event timing of everything launched through the session (events on the launching stream);

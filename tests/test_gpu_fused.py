@@ -1,0 +1,101 @@
+"""The whole-encoder fused tcgen05 forward (k_enc_fused.cu) against the layered kernels it replaces, tensor by
+tensor, and through a full training step.  Run with `-m gpu` on a B200."""
+import pytest
+import torch
+
+from tests.helpers import make_batch, to_cuda
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = {
+    # name: (B, S, P, inner_dim, layers)   hidden 64, 2 heads
+    "s50_two_per_tile": (25, 50, 8, 64, 2),       # odd batch: the last tile holds one sequence
+    "s20_six_per_tile": (13, 20, 4, 128, 3),
+    "s128_one_per_tile": (3, 128, 20, 64, 1),
+    "s64_i256": (5, 64, 10, 256, 2),
+    "s7_tiny": (40, 7, 2, 64, 1),
+}
+SAVED = ("x0", "qkv", "ctx", "a_pre", "y", "h_pre", "h", "o_pre", "out", "mean1", "rstd1", "mean2", "rstd2", "lse")
+
+
+def _store(S, I, L, dropout):
+    from bert4rec_b200.engine import ParamStore
+    store = ParamStore(vocab_size=977, hidden_size=64, num_layers=L, num_attention_heads=2, max_sequence_length=S,
+                       inner_dim=I, output_dropout=dropout, attention_dropout=dropout, device="cuda:0")
+    store.init_weights(3)
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for k, v in store.tf_views().items():
+            if k.endswith("bias") or k.endswith("beta"):
+                v.copy_((torch.randn(v.shape, generator=g) * 0.05).to(v.device))
+            elif k.endswith("gamma"):
+                v.copy_((1.0 + torch.randn(v.shape, generator=g) * 0.1).to(v.device))
+    store.sync_shadow()
+    return store
+
+
+def _run(sess, cb, fused, training, backward, store):
+    sess.set_flag(2, int(fused))
+    sess.encode(cb["input_word_ids"], cb["input_mask"], training=training, seed=99, step=7)
+    out = {}
+    L = store.L
+    for l in range(L):
+        names = SAVED if training else ("out",)
+        for n in names:
+            if n == "x0" and l > 0:
+                continue
+            out[f"{l}.{n}"] = sess.layer_tensor(l, n).float().clone()
+        if training and store.cfg.attention_dropout > 0:
+            out[f"{l}.keep"] = sess.attn_keep_mask(l).clone()
+    if backward:
+        sess.select(cb["masked_lm_positions"], cb["masked_lm_ids"], cb["masked_lm_weights"], mode=0, want_aux=True)
+        sess.transform(); sess.loss(); sess.backward(seed=99, step=7)
+        torch.cuda.synchronize()
+        out["loss"] = sess.step_stats().clone()[:2]
+        out["grads"] = {k: v.clone() for k, v in store.grad_dict().items()}
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+@pytest.mark.parametrize("dropout", [0.0, 0.3])
+def test_fused_forward_matches_layered(name, dropout):
+    B, S, P, I, L = SHAPES[name]
+    store = _store(S, I, L, dropout)
+    store.ensure_training_buffers()
+    cb = to_cuda(make_batch(B, S, P, 977, seed=17))
+    sess = store.session(B, S, P)
+    sess.set_flag(2, 1)   # raises if the fused kernel does not support the shape
+    for training in (False, True):
+        ref = _run(sess, cb, False, training, training, store)
+        got = _run(sess, cb, True, training, training, store)
+        for k in ref:
+            if k in ("grads", "loss"):
+                continue
+            if k.endswith(".keep"):
+                assert torch.equal(ref[k], got[k]), f"{name}: attention keep bits differ in {k}"
+                continue
+            a, b = got[k], ref[k]
+            scale = float(b.abs().max()) + 1e-6
+            err = float((a - b).abs().max())
+            # same math, different summation order: a bf16 ulp or two of the tensor's range
+            assert err <= 2.5e-2 * scale, f"{name} training={training}: {k} max abs diff {err} (range {scale})"
+            assert float((a - b).norm() / (b.norm() + 1e-20)) < 4e-3, (name, k)
+        if training:
+            assert torch.allclose(ref["loss"], got["loss"], rtol=2e-3)
+            for k, g in ref["grads"].items():
+                d = float((got["grads"][k] - g).norm())
+                assert d <= 2e-2 * float(g.norm()) + 1e-6 * max(float(x.norm()) for x in ref["grads"].values()), (name, k, d)
+
+
+def test_fused_is_default_for_beauty_shape_and_counts_one_launch():
+    store = _store(50, 64, 2, 0.1)
+    sess = store.session(16, 50, 5)
+    cb = to_cuda(make_batch(16, 50, 5, 977, seed=1))
+    n0 = sess.launch_count()
+    sess.encode(cb["input_word_ids"], cb["input_mask"], training=False)
+    assert sess.launch_count() - n0 == 1
+    sess.set_flag(2, 0)
+    n0 = sess.launch_count()
+    sess.encode(cb["input_word_ids"], cb["input_mask"], training=False)
+    assert sess.launch_count() - n0 == 1 + 5 * 2
