@@ -325,7 +325,16 @@ def kernel_work(tag, w, n_rows):
     """Algorithmic (flops, bytes, bound) of ONE launch of the kernel behind a profile tag."""
     B, S, H, I, V, N = w["batch"], w["seq_len"], w["hidden_size"], w["inner_dim"], w["vocab_size"], w["num_attention_heads"]
     T, M, Vp, e = B * S, n_rows, (V + 127) // 128 * 128, 2
+    L = w["num_layers"]
+    saved = T * e * (H + L * (3 * H + 5 * H + 2 * I))   # activations the fused forward writes for backward
     t = {
+        # fused encoder forward: FLOPs of SURVEY 8d's encoder formula; bytes = ids + every saved activation once
+        "enc_fwd_fused": (L * T * (8 * H * H + 4 * S * H + 4 * H * I), T * 8 + saved + L * 4 * T * 4, "hbm"),
+        "ce_fwd_umma": (2 * M * H * V, M * H * e + V * H * e + V * 4 + 3 * M * 4, "tensor"),
+        # recompute passes: only the useful GEMM (dT = dl E, dE = dl^T t) is counted, not the recomputed logits
+        "ce_bwd_umma:dT": (2 * M * H * V, M * H * e + V * H * e + V * 4 + M * H * 4, "tensor"),
+        "ce_bwd_umma:dE": (2 * M * H * V, M * H * e + V * H * e + V * H * 4 + V * 4, "tensor"),
+        "sqnorm+adamw": (0, 32 * (V * H + 64 * H + L * (4 * H * H + 2 * H * I) + H * H + V), "hbm"),
         "embed_ln_fwd": (0, T * (8 + 2 * H * e), "hbm"),
         "embed_bwd": (0, T * (8 + H * e + H * 4) + T * H * 4, "hbm"),
         "gemm:qkv": (2 * T * H * 3 * H, T * H * e + 3 * H * H * e + T * 3 * H * e, "tensor"),
@@ -354,34 +363,49 @@ def kernel_work(tag, w, n_rows):
     return t.get(tag, (0, 0, "hbm"))
 
 
+def profile_steps(model, sess, batches, n, flush=None):
+    """Per-kernel device times of n train steps INSIDE the CUDA graph: the step is re-captured with profiling on, so
+    every launch is bracketed by external event-record nodes and each replay re-times it (b4r_profile_*).
+    Returns {tag: (launches, total_ms)} summed over the n replays."""
+    import torch
+    model.use_cuda_graph = True
+    model._graphs.clear()
+    sess.profile(True)
+    model.train_step(batches[0])          # eager pass + capture (with event nodes)
+    torch.cuda.synchronize()
+    sess.profile_report()                 # discard the eager records
+    agg = {}
+    for i in range(n):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        model.train_step(batches[i % len(batches)])
+        for tag, (cnt, ms) in sess.profile_report().items():
+            c0, m0 = agg.get(tag, (0, 0.0))
+            agg[tag] = (c0 + cnt, m0 + ms)
+    sess.profile(False)
+    model._graphs.clear()                 # the profiled graph references destroyed events: never replay it again
+    return agg
+
+
 def roofline_block(model, sess, w, dev_batches, args, hbm, tf_burst, src):
-    """Per-kernel CUDA-event timing (events recorded on the launching stream around every launch of the session,
-    b4r_profile_*) over a profiled pass of train steps; the dominant kernel's roofline entry + the breakdown."""
+    """Per-kernel CUDA-event timing inside graph replays (profile_steps); the roofline entry is the kernel with the
+    largest share of the step among those with a stated algorithmic workload (kernel_work), + the breakdown."""
     import torch
     n = max(args.steps, 10)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_batches[0]["input_word_ids"].device)
-    model.use_cuda_graph = False   # per-launch events cannot be recorded inside a graph replay
     model.distributed = False      # rank-0-only profiling pass: no collective (the other ranks are not stepping)
-    for i in range(3):
-        model.train_step(dev_batches[i % len(dev_batches)])
-    torch.cuda.synchronize()
-    sess.profile(True)
-    for i in range(n):
-        flush.fill_(i & 0xFF)
-        model.train_step(dev_batches[i % len(dev_batches)])
-    rep = sess.profile_report()
-    sess.profile(False)
-    model.use_cuda_graph = True
+    rep = profile_steps(model, sess, dev_batches, n, flush)
     n_rows = int(sess.counts()[1])
     rows = sorted(((tag, cnt, tot) for tag, (cnt, tot) in rep.items()), key=lambda r: -r[2])
     total = sum(r[2] for r in rows)
     breakdown = []
-    for tag, cnt, tot in rows[:12]:
+    for tag, cnt, tot in rows[:14]:
         fl, by, bound = kernel_work(tag, w, n_rows)
         ms = tot / cnt
         breakdown.append({"kernel": tag, "launches_per_step": cnt / n, "avg_ms": ms, "share": tot / total,
                           "tflops": fl / (ms / 1e3) / 1e12 if fl else 0.0, "gbs": by / (ms / 1e3) / 1e9 if by else 0.0})
-    tag, cnt, tot = rows[0]
+    known = [r for r in rows if kernel_work(r[0], w, n_rows)[0] or kernel_work(r[0], w, n_rows)[1]]
+    tag, cnt, tot = (known or rows)[0]
     fl, by, bound = kernel_work(tag, w, n_rows)
     ms = tot / cnt
     if bound == "tensor":
@@ -389,8 +413,14 @@ def roofline_block(model, sess, w, dev_batches, args, hbm, tf_burst, src):
     else:
         ach, peak, unit = by / (ms / 1e3) / 1e9, hbm, "GB/s"
     return {"kernel": tag, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-            "traffic": None, "peak_source": src, "launch_ms": ms, "share_of_step": tot / total,
-            "algorithmic_flops": fl, "algorithmic_bytes": by, "kernel_ms_per_step": total / n, "breakdown": breakdown}
+            "traffic": NCU_TRAFFIC.get(tag), "peak_source": src, "launch_ms": ms, "share_of_step": tot / total,
+            "algorithmic_flops": fl, "algorithmic_bytes": by, "kernel_ms_per_step": total / n,
+            "timing": "CUDA events recorded as graph nodes around every launch, averaged over %d replays" % n,
+            "breakdown": breakdown}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+NCU_TRAFFIC = {}
 
 
 def main():

@@ -69,6 +69,7 @@ _SIGNATURES = {
     "b4r_launch_count": (C.c_int, [_P]),
     "b4r_session_set_flag": (C.c_int, [_P, C.c_int, C.c_int]),
     "b4r_debug_buffer": (_P, [_P]),
+    "b4r_debug_buffer2": (_P, [_P]),
     "b4r_profile_enable": (C.c_int, [_P, C.c_int]),
     "b4r_profile_report": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "b4r_dropout_keep_mask": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_int, C.c_int, C.c_uint32, _P]),

@@ -29,16 +29,31 @@ static int fail(const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
-// kernel launch through a session: counts the launch and, when profiling is on, brackets it with CUDA events
-#define KL(tag, expr)                                                                   \
+// Kernel launch through the C ABI: counts the launch and, when profiling is on, brackets it with CUDA events on the
+// launching stream.  Inside a stream capture the events become external event-record NODES of the graph, so every
+// replay re-times every kernel in place (durations inside the graph, not at eager launch rate).
+struct ProfRec { const char* tag; cudaEvent_t a, b; bool in_graph; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static void prof_record(cudaEvent_t e, cudaStream_t st, bool capturing) {
+  if (capturing) cudaEventRecordWithFlags(e, st, cudaEventRecordExternal);
+  else cudaEventRecord(e, st);
+}
+#define KL_(counter, tag, expr)                                                          \
   do {                                                                                  \
     cudaEvent_t e0__ = nullptr, e1__ = nullptr;                                         \
-    if (s->prof_on) { cudaEventCreate(&e0__); cudaEventCreate(&e1__); cudaEventRecord(e0__, st); } \
+    bool cap__ = false;                                                                 \
+    if (g_prof_on) {                                                                    \
+      cudaStreamCaptureStatus cs__ = cudaStreamCaptureStatusNone;                       \
+      cudaStreamIsCapturing(st, &cs__);                                                 \
+      cap__ = cs__ == cudaStreamCaptureStatusActive;                                    \
+      cudaEventCreate(&e0__); cudaEventCreate(&e1__); prof_record(e0__, st, cap__);     \
+    }                                                                                   \
     CK(expr);                                                                           \
-    s->launches++;                                                                      \
-    if (s->prof_on) { cudaEventRecord(e1__, st); s->prof.push_back(ProfRec{tag, e0__, e1__}); }    \
+    counter;                                                                            \
+    if (g_prof_on) { prof_record(e1__, st, cap__); g_prof.push_back(ProfRec{tag, e0__, e1__, cap__}); } \
   } while (0)
-struct ProfRec { const char* tag; cudaEvent_t a, b; };
+#define KL(tag, expr) KL_(s->launches++, tag, expr)
 
 extern "C" int b4r_version(void) { return B4R_VERSION; }
 extern "C" const char* b4r_last_error(void) { return g_err; }
@@ -185,6 +200,7 @@ struct b4r_session {
   CeUmmaMaps umaps;
   bool use_fused = false;   // whole-encoder forward in one tcgen05 launch (k_enc_fused.cu)
   void* d_enc_tables = nullptr;
+  unsigned long long* dbg_buf = nullptr;
   bf16* dlogits; int dl_rows;
   float* dt_part; int dt_splits, dt_max_splits;
   float *p_dE, *p_dbias2; int me_splits;
@@ -199,8 +215,6 @@ struct b4r_session {
   const int64_t *ids, *mask;
   int select_mode;
   int launches;
-  bool prof_on = false;
-  std::vector<ProfRec> prof;
 };
 
 static const int kColsumSplits = 64;
@@ -346,6 +360,7 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
   s->d_jobs = b.take<ReduceJob>(256);
   s->d_vb_jobs = b.take<ReduceJob>(2);
   s->d_enc_tables = b.take<unsigned char>(enc_fused_table_bytes(s->cfg.num_layers));
+  s->dbg_buf = b.take<unsigned long long>(512);
   return b.off + 256;
 }
 
@@ -397,7 +412,7 @@ extern "C" int b4r_session_create(const b4r_config* cfg, int batch, int seq_len,
   if (jobs.size() > 256) { delete s; return fail("too many reduce jobs"); }
   s->n_jobs = (int)jobs.size();
   s->jobs_max_len = 0;
-  for (auto& j : jobs) if (j.len > s->jobs_max_len) s->jobs_max_len = j.len;
+  for (auto& j : jobs) { int nb = grad_reduce_blocks(j.nparts, j.len); if (nb > s->jobs_max_len) s->jobs_max_len = nb; }
   CK(cudaMemcpy(s->d_jobs, jobs.data(), jobs.size() * sizeof(ReduceJob), cudaMemcpyHostToDevice));
   ReduceJob vb[2];
   vb[0] = ReduceJob{s->p_vbias, grads ? grads + s->lay.find("head/output_bias") : nullptr, s->vb_splits, s->V, (long long)s->V, 0};
@@ -460,6 +475,7 @@ extern "C" int b4r_encode(b4r_session* s, const int64_t* ids, const int64_t* mas
     f.emb_g = P + s->lay.find("emb_ln/gamma"); f.emb_b = P + s->lay.find("emb_ln/beta"); f.x0 = s->x0; f.dev_tables = s->d_enc_tables;
     f.B = s->B; f.S = s->S; f.V = s->V; f.L = s->cfg.num_layers; f.I = I; f.training = training;
     f.out_drop = od; f.attn_drop = ad; f.seed = seed; f.step = step; f.d_step = d_step;
+    f.dbg = getenv("B4R_FUSED_DEBUG") ? (void*)s->dbg_buf : nullptr;
     KL("enc_fwd_fused", launch_enc_fwd_fused(f, st));
     return 0;
   }
@@ -593,7 +609,7 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
     KL("ce_bwd_umma:dT", launch_ce_bwd_umma(s->umaps, ba, true, st));
     ba.out = s->p_dE; ba.dbias_out = s->p_dbias2;
     KL("ce_bwd_umma:dE", launch_ce_bwd_umma(s->umaps, ba, false, st));
-    KL("grad_reduce:ce", launch_grad_reduce(s->d_ce_jobs, 2, V * H, st));
+    KL("grad_reduce:ce", launch_grad_reduce(s->d_ce_jobs, 2, grad_reduce_blocks(s->me_splits, V * H), st));
   }
   // ---- CE backward, generation 1: dlogits materialised in bf16, chunked over rows
   int chunk = 0;
@@ -602,7 +618,7 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
     c.row_begin = r0; c.row_count = rc;
     KL("ce_dlogits", launch_ce_dlogits(c, st));
     KL("colsum:vbias", launch_colsum_bf16(s->dlogits, s->Vp, rc, V, s->counts + 1, r0, s->p_vbias, s->vb_splits, st));
-    KL("grad_reduce:vbias", launch_grad_reduce(s->d_vb_jobs + (chunk > 0 ? 1 : 0), 1, V, st));
+    KL("grad_reduce:vbias", launch_grad_reduce(s->d_vb_jobs + (chunk > 0 ? 1 : 0), 1, grad_reduce_blocks(s->vb_splits, V), st));
     GemmArgs g{};
     g.A = s->dlogits; g.lda = s->Vp; g.B = W + oE; g.ldb = H; g.b_trans = true; g.M = rc; g.N = H; g.K = s->Vp;
     g.a_kmax = s->Vp; g.b_kmax = V; g.d_M = s->counts + 1; g.d_M_off = r0; g.splits = s->dt_splits;
@@ -733,7 +749,8 @@ extern "C" int b4r_adamw_step(float* params, void* shadow_bf16, const float* gra
   a.init_lr = hp->init_lr; a.end_lr = hp->end_lr; a.num_train_steps = hp->num_train_steps; a.num_warmup_steps = hp->num_warmup_steps;
   a.wd = hp->weight_decay_rate; a.beta1 = hp->beta_1; a.beta2 = hp->beta_2; a.eps = hp->epsilon; a.clip = hp->clip_norm;
   a.d_lr_out = lr_out;
-  CK(launch_adamw(a, (cudaStream_t)stream));
+  cudaStream_t st = (cudaStream_t)stream;
+  KL_((void)0, "sqnorm+adamw", launch_adamw(a, st));
   return 0;
 }
 
@@ -812,6 +829,7 @@ extern "C" const void* b4r_layer_tensor(b4r_session* s, int layer, const char* n
 }
 extern "C" int b4r_launch_count(b4r_session* s) { return s ? s->launches : 0; }
 extern "C" const void* b4r_debug_buffer(b4r_session* s) { return s ? (const void*)(s->ce_part + (size_t)(s->vsplits_umma - 1) * s->Mcap * 6) : nullptr; }
+extern "C" const void* b4r_debug_buffer2(b4r_session* s) { return s ? (const void*)s->dbg_buf : nullptr; }
 extern "C" int b4r_session_set_flag(b4r_session* s, int flag, int value) {
   if (!s) return fail("null session");
   if (flag == 1) { s->use_umma = value != 0; return 0; }
@@ -823,26 +841,36 @@ extern "C" int b4r_session_set_flag(b4r_session* s, int flag, int value) {
   return fail("unknown flag %d", flag);
 }
 extern "C" int b4r_profile_enable(b4r_session* s, int on) {
-  if (!s) return fail("null session");
-  s->prof_on = on != 0;
+  (void)s;
+  g_prof_on = on != 0;
+  if (!g_prof_on) {  // switching off drops every record, including the ones living in captured graphs
+    cudaDeviceSynchronize();
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+  }
   return 0;
 }
-// Synchronises the device, aggregates the recorded per-launch event times by kernel tag, writes lines
-// "tag count total_ms" into buf, and clears the records.
+// Synchronises the device, aggregates the recorded per-launch event times by kernel tag and writes lines
+// "tag count total_ms" into buf.  Eager records are consumed; records captured into a CUDA graph persist (they are
+// re-timed by every replay) until profiling is switched off.
 extern "C" int b4r_profile_report(b4r_session* s, char* buf, int cap) {
-  if (!s || !buf || cap < 1) return fail("bad argument");
+  (void)s;
+  if (!buf || cap < 1) return fail("bad argument");
   CK(cudaDeviceSynchronize());
   std::vector<std::string> tags; std::vector<int> cnt; std::vector<double> tot;
-  for (auto& r : s->prof) {
+  std::vector<ProfRec> keep;
+  for (auto& r : g_prof) {
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, r.a, r.b);
-    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); ms = -1.f; }
+    if (r.in_graph) keep.push_back(r);
+    else { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    if (ms < 0.f) continue;   // a captured record that no replay has timed yet
     size_t i = 0;
     for (; i < tags.size(); ++i) if (tags[i] == r.tag) break;
     if (i == tags.size()) { tags.push_back(r.tag); cnt.push_back(0); tot.push_back(0.0); }
     cnt[i]++; tot[i] += ms;
   }
-  s->prof.clear();
+  g_prof.swap(keep);
   std::string out;
   for (size_t i = 0; i < tags.size(); ++i) {
     char line[160];

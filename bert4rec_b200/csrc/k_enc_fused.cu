@@ -28,6 +28,7 @@ constexpr int FT = 128;                 // rows per CTA tile
 constexpr int FH = 64;                  // hidden size
 constexpr int FNH = 2, FD = 32;         // heads, head dim
 constexpr int TILE_B = FT * 128;        // bytes of one [128][64] bf16 tile
+constexpr int NTHR = 512;               // 16 warps: TMEM lane quadrant (warp & 3) x column quarter (warp >> 2)
 
 // shared-memory map (byte offsets from the 1024-aligned base)
 constexpr int OFF_X = 0;                        // layer input / residual
@@ -36,10 +37,13 @@ constexpr int OFF_K = OFF_Q + TILE_B;           // K ; later y = LN1 output
 constexpr int OFF_V = OFF_K + TILE_B;           // V
 constexpr int OFF_P = OFF_V + TILE_B;           // probabilities: FNH x [128][128] ; later h = gelu(FFN1) [128][I]
 constexpr int OFF_WA = OFF_P + FNH * 2 * TILE_B;  // Wqkv (3 x 8 KB) + Wo (8 KB)
-constexpr int OFF_WB = OFF_WA + 4 * 8192;       // W1 (I/64 x 8 KB) + W2 (I x 128 B)
+constexpr int OFF_WB = OFF_WA + 4 * 8192;       // W1 (I/64 x 8 KB) + W2 (I x 128 B), then the small arrays (see kernel)
+// per-layer parameter block, in floats (the flat layout keeps these 8 vectors contiguous: api.cu make_layout)
+constexpr int PB_BQKV = 0, PB_BO = 192, PB_G1 = 256, PB_BE1 = 320, PB_B1 = 384;   // then b2, g2, be2 at 384+I, 448+I, 512+I
+__host__ __device__ constexpr int par_floats(int I) { return 576 + I; }
 
 struct LayerDev {
-  const float *bqkv, *bo, *g1, *be1, *b1, *b2, *g2, *be2;
+  const float* pblock;    // bqkv | bo | ln1 gamma | ln1 beta | b1 | b2 | ln2 gamma | ln2 beta
   bf16 *qkv, *ctx, *a_pre, *y, *h_pre, *h, *o_pre, *out;
   float *lse, *mean1, *rstd1, *mean2, *rstd2;
   unsigned long long* keep;
@@ -65,36 +69,63 @@ __device__ __forceinline__ void tmem_ld_f32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
-// 32 bf16 (16 packed words) of one row -> 4 consecutive 16-byte chunks (chunk0..chunk0+3) of a swizzled tile row
-__device__ __forceinline__ void st_tile(unsigned char* tile, int row, int chunk0, const uint32_t (&pk)[16]) {
+__device__ __forceinline__ void tmem_ld_f16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  umma::tmem_ld16(taddr, r);
+  umma::tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+// NC consecutive 16-byte chunks (chunk0..) of one row of a 128-byte-swizzled [128][64] bf16 tile
+template <int NC>
+__device__ __forceinline__ void st_tile(unsigned char* tile, int row, int chunk0, const uint32_t (&pk)[4 * NC]) {
   unsigned char* rp = tile + row * 128;
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < NC; ++q)
     *reinterpret_cast<uint4*>(rp + (((chunk0 + q) ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
 }
-__device__ __forceinline__ void ld_tile(const unsigned char* tile, int row, int chunk0, float (&v)[32]) {
+template <int NC>
+__device__ __forceinline__ void ld_tile(const unsigned char* tile, int row, int chunk0, float (&v)[8 * NC]) {
   const unsigned char* rp = tile + row * 128;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < NC; ++q) {
     const uint4 u = *reinterpret_cast<const uint4*>(rp + (((chunk0 + q) ^ (row & 7)) << 4));
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf162(w[i]); v[8 * q + 2 * i] = f.x; v[8 * q + 2 * i + 1] = f.y; }
   }
 }
-__device__ __forceinline__ void st_global32(bf16* dst, const uint32_t (&pk)[16]) {
+template <int NW>
+__device__ __forceinline__ void st_global(bf16* dst, const uint32_t (&pk)[NW]) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < NW / 4; ++q)
     *reinterpret_cast<uint4*>(dst + 8 * q) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
 }
-__device__ __forceinline__ void pack32(const float (&v)[32], uint32_t (&pk)[16]) {
+template <int N>
+__device__ __forceinline__ void pack_n(const float (&v)[N], uint32_t (&pk)[N / 2]) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) pk[i] = pack_bf162(v[2 * i], v[2 * i + 1]);
+  for (int i = 0; i < N / 2; ++i) pk[i] = pack_bf162(v[2 * i], v[2 * i + 1]);
 }
-__device__ __forceinline__ void round32(float (&v)[32], uint32_t (&pk)[16]) {  // v := bf16-rounded v, pk := packed
-  pack32(v, pk);
+template <int N>
+__device__ __forceinline__ void round_n(float (&v)[N], uint32_t (&pk)[N / 2]) {  // v := bf16-rounded v, pk := packed
+  pack_n<N>(v, pk);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { const float2 f = unpack_bf162(pk[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  for (int i = 0; i < N / 2; ++i) { const float2 f = unpack_bf162(pk[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <int N>
+__device__ __forceinline__ void zero_if(bool z, uint32_t (&pk)[N]) {
+  if (z) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) pk[i] = 0u;
+  }
+}
+template <int N>
+__device__ __forceinline__ void add_vec(float (&v)[N], const float* sp) {   // sp: 16-byte aligned shared-memory vector
+#pragma unroll
+  for (int i = 0; i < N; i += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(sp + i);
+    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+  }
 }
 }  // namespace
 
@@ -104,13 +135,14 @@ struct EncFusedDev {
   bf16* x0;
   const LayerDev* layers;
   const CUtensorMap* maps;  // [L][4]: wqkv, wo, w1, w2
-  int B, S, V, L, G, I;
+  int B, S, V, L, slot, I;  // slot = rows reserved per sequence (32 / 64 / 128)
   int training;
   uint32_t thr_out, thr_attn; float inv_keep_out, inv_keep_attn;
   unsigned long long seed; uint32_t step; const long long* d_step;
+  unsigned long long* dbg;   // optional: phase timestamps of CTA 0 + start/end of every CTA (development aid)
 };
 
-__global__ void __launch_bounds__(256, 1) enc_fwd_fused_kernel(EncFusedDev a) {
+__global__ void __launch_bounds__(NTHR, 1) enc_fwd_fused_kernel(EncFusedDev a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sX = smem + OFF_X;
@@ -124,39 +156,44 @@ __global__ void __launch_bounds__(256, 1) enc_fwd_fused_kernel(EncFusedDev a) {
   unsigned char* sWA = smem + OFF_WA;
   unsigned char* sWB = smem + OFF_WB;
   const int I = a.I;
-  float* sMask = reinterpret_cast<float*>(sWB + I * 256);   // [128] additive key mask of the tile rows
-  float* sRed = reinterpret_cast<float*>(sP);               // [2][2][128] pair-exchange buffers: P / h are dead in every LN phase
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + FT);
+  const int PF = par_floats(I);
+  float* sPar = reinterpret_cast<float*>(sWB + I * 256);    // [2][PF] parameter blocks of two consecutive layers
+  float* sEmb = sPar + 2 * PF;                              // [128] embedding LN gamma | beta
+  float* sMask = sEmb + 128;                                // [128] additive key mask of the tile rows
+  float* sRed = sMask + FT;                                 // [2][4][128] exchange buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 8 * FT);
   uint64_t* barA = bars;        // Wqkv + Wo landed
   uint64_t* barB = bars + 1;    // W1 + W2 landed
   uint64_t* barM = bars + 2;    // MMA batch complete
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* barP = bars + 3;    // [2] parameter block landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, half = warp >> 2;
+  const int quad = warp & 3, part = warp >> 2;
   const int row = quad * 32 + lane;
-  const int S = a.S, T = a.B * S;
-  const int R = a.G * S;                       // rows of the tile in use
-  const int t0 = blockIdx.x * R;               // first token of the tile
-  const int t = t0 + row;
-  const bool valid = row < R && t < T;
-  const int c0 = half * 32;                    // this thread's 32 columns of a 64-wide row
+  const int S = a.S, SLOT = a.slot, G = FT / SLOT;
+  const int g = row / SLOT, pos = row - g * SLOT;       // g is warp-uniform (SLOT >= 32)
+  const int seq = blockIdx.x * G + g;
+  const bool valid = pos < S && seq < a.B;
+  const int t = seq * S + pos;
+  const int cq = part * 16;                             // this thread's 16 columns of a 64-wide row
   const uint32_t step = a.step + (a.d_step ? (uint32_t)(*a.d_step) : 0u);
   const Philox ph(a.seed);
   const bool train = a.training != 0;
 
-  if (tid == 0) {
-    umma::mbar_init(barA, 1); umma::mbar_init(barB, 1); umma::mbar_init(barM, 1);
-    umma::fence_barrier_init();
+  int dbg_i = 0;
+  auto stamp = [&]() {
+    if (a.dbg && blockIdx.x == 0 && tid == 0) {
+      unsigned long long tns;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+      a.dbg[dbg_i++] = tns;
+    }
+  };
+  if (a.dbg && tid == 0 && blockIdx.x < 128) {
+    unsigned long long tns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+    a.dbg[256 + 2 * blockIdx.x] = tns;
   }
-  if (warp == 1) umma::tmem_alloc<512>(tmem_holder);
-  umma::fence_before_sync();
-  __syncthreads();
-  umma::fence_after_sync();
-  const uint32_t tmem = *tmem_holder;
-  const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
-  uint32_t parM = 0;
-  int red_sel = 0;
 
   auto load_A = [&](int l) {   // thread 0: Wqkv + Wo of layer l
     const CUtensorMap* m = a.maps + l * 4;
@@ -170,53 +207,78 @@ __global__ void __launch_bounds__(256, 1) enc_fwd_fused_kernel(EncFusedDev a) {
     for (int n = 0; n < I / 64; ++n) umma::tma_load_2d(sWB + n * 8192, m + 2, n * 64, 0, barB);
     umma::tma_load_2d(sWB + I * 128, m + 3, 0, 0, barB);
   };
-  if (tid == 0) { load_A(0); load_B(0); }
-
-  // pair exchange: sum of a per-thread value over the two column halves of a row
-  auto pair_sum = [&](float v) -> float {
-    float* buf = sRed + red_sel * 2 * FT;
-    buf[half * FT + row] = v;
-    __syncthreads();
-    const float o = buf[(half ^ 1) * FT + row];
-    red_sel ^= 1;
-    return v + o;
+  auto load_P = [&](int l) {   // thread 0: parameter block of layer l -> buffer l & 1
+    umma::mbar_expect_tx(barP + (l & 1), (uint32_t)PF * 4);
+    umma::bulk_load_1d(sPar + (l & 1) * PF, a.layers[l].pblock, (uint32_t)PF * 4, barP + (l & 1));
   };
-  // LayerNorm of a 64-wide row held as two 32-column halves; v must already be the bf16-rounded pre-LN value
-  auto layer_norm = [&](float (&v)[32], const float* gamma, const float* beta, float& mean, float& rstd) {
+
+  if (tid == 0) {
+    umma::mbar_init(barA, 1); umma::mbar_init(barB, 1); umma::mbar_init(barM, 1);
+    umma::mbar_init(barP, 1); umma::mbar_init(barP + 1, 1);
+    umma::fence_barrier_init();
+    load_P(0);
+    if (a.L > 1) load_P(1);
+    load_A(0); load_B(0);
+  }
+  if (tid < 128) sEmb[tid] = tid < 64 ? a.emb_g[tid] : a.emb_b[tid - 64];
+  if (part == 0) sMask[row] = valid ? (a.mask[t] != 0 ? 0.f : -1e9f) : 0.f;
+  if (warp == 1) umma::tmem_alloc<512>(tmem_holder);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+  uint32_t parM = 0;
+  int red_sel = 0;
+  stamp();
+
+  // exchange of one float between the 4 column-quarter threads of a row
+  auto quad_sum = [&](float v) -> float {
+    float* buf = sRed + red_sel * 4 * FT;
+    buf[part * FT + row] = v;
+    __syncthreads();
+    const float r = (buf[row] + buf[FT + row]) + (buf[2 * FT + row] + buf[3 * FT + row]);
+    red_sel ^= 1;
+    return r;
+  };
+  auto pair_other = [&](float v) -> float {   // value of the thread owning the other key half of the same (row, head)
+    float* buf = sRed + red_sel * 4 * FT;
+    buf[part * FT + row] = v;
+    __syncthreads();
+    const float o = buf[(part ^ 1) * FT + row];
+    red_sel ^= 1;
+    return o;
+  };
+  // LayerNorm of a 64-wide row held as four 16-column quarters; v must already be the bf16-rounded pre-LN value
+  auto layer_norm = [&](float (&v)[16], const float* gamma, const float* beta, float& mean, float& rstd) {
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) s += v[i];
-    mean = pair_sum(s) * (1.0f / FH);
+    for (int i = 0; i < 16; ++i) s += v[i];
+    mean = quad_sum(s) * (1.0f / FH);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; q += d * d; }
-    rstd = rsqrtf(pair_sum(q) * (1.0f / FH) + kLnEps);
+    for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; q += d * d; }
+    rstd = rsqrtf(quad_sum(q) * (1.0f / FH) + kLnEps);
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0 + i));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c0 + i));
-      v[i] = (v[i] - mean) * rstd * g.x + b.x; v[i + 1] = (v[i + 1] - mean) * rstd * g.y + b.y;
-      v[i + 2] = (v[i + 2] - mean) * rstd * g.z + b.z; v[i + 3] = (v[i + 3] - mean) * rstd * g.w + b.w;
+    for (int i = 0; i < 16; i += 4) {
+      const float4 gm = *reinterpret_cast<const float4*>(gamma + cq + i);
+      const float4 bt = *reinterpret_cast<const float4*>(beta + cq + i);
+      v[i] = (v[i] - mean) * rstd * gm.x + bt.x; v[i + 1] = (v[i + 1] - mean) * rstd * gm.y + bt.y;
+      v[i + 2] = (v[i + 2] - mean) * rstd * gm.z + bt.z; v[i + 3] = (v[i + 3] - mean) * rstd * gm.w + bt.w;
     }
   };
-  auto add_bias = [&](float (&v)[32], const float* bias) {
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + i));
-      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-    }
-  };
-  auto drop32 = [&](float (&v)[32], uint32_t site) {   // elementwise dropout of columns c0..c0+31 of token row t
+  auto drop16 = [&](float (&v)[16], uint32_t site) {   // elementwise dropout of columns cq..cq+15 of token row t
     if (a.thr_out == 0 || !train) return;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t bits = keep_bits8(ph, (uint32_t)t, (uint32_t)(c0 / 8 + q), site, step, a.thr_out);
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t bits = keep_bits8(ph, (uint32_t)t, (uint32_t)(cq / 8 + q), site, step, a.thr_out);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[8 * q + i] = ((bits >> i) & 1u) ? v[8 * q + i] * a.inv_keep_out : 0.f;
     }
   };
   // every thread: previous epilogue's smem writes / TMEM reads are ordered before the next MMA batch
   auto phase_sync = [&]() {
+    stamp();
     umma::fence_before_sync();
     umma::fence_proxy_async();
     __syncthreads();
@@ -226,21 +288,43 @@ __global__ void __launch_bounds__(256, 1) enc_fwd_fused_kernel(EncFusedDev a) {
     umma::mbar_wait(barM, parM);
     parM ^= 1;
     umma::fence_after_sync();
+    stamp();
+  };
+  // shared epilogue of the two residual + LayerNorm phases (attention output, FFN output)
+  auto res_ln_epilogue = [&](uint32_t acc_col, const float* bias, uint32_t site, const unsigned char* res_tile, const float* gamma,
+                             const float* beta, bf16* pre_out, unsigned char* dst_tile, bf16* y_out, bool y_always, float* mean_out,
+                             float* rstd_out) {
+    float v[16], res[16];
+    tmem_ld_f16(tlane + acc_col + cq, v);
+    add_vec<16>(v, bias + cq);
+    drop16(v, site);
+    ld_tile<2>(res_tile, row, part * 2, res);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += res[i];
+    uint32_t pk[8];
+    round_n<16>(v, pk);                            // LN statistics on the bf16 value backward re-reads
+    if (valid && train) st_global<8>(pre_out + (size_t)t * FH + cq, pk);
+    float mean, rstd;
+    layer_norm(v, gamma, beta, mean, rstd);
+    pack_n<16>(v, pk);
+    zero_if<8>(!valid, pk);
+    st_tile<2>(dst_tile, row, part * 2, pk);
+    if (valid && (train || y_always)) st_global<8>(y_out + (size_t)t * FH + cq, pk);
+    if (valid && train && part == 0) { mean_out[t] = mean; rstd_out[t] = rstd; }
   };
 
   // ------------------------------------------------------------------ phase 0: embedding + LN + dropout -> sX
   {
-    sMask[row] = valid ? (a.mask[t] != 0 ? 0.f : -1e9f) : 0.f;   // (both halves write the same value)
-    float v[32];
+    float v[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
     if (valid) {
       long long id = a.ids[t];
       id = id < 0 ? 0 : (id >= a.V ? a.V - 1 : id);
-      const bf16* e = a.table + (size_t)id * FH + c0;
-      const bf16* p = a.pos + (size_t)(row % S) * FH + c0;
+      const bf16* e = a.table + (size_t)id * FH + cq;
+      const bf16* p = a.pos + (size_t)pos * FH + cq;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 2; ++q) {
         const uint4 eu = __ldg(reinterpret_cast<const uint4*>(e + 8 * q));
         const uint4 pu = __ldg(reinterpret_cast<const uint4*>(p + 8 * q));
         const uint32_t ew[4] = {eu.x, eu.y, eu.z, eu.w}, pw[4] = {pu.x, pu.y, pu.z, pu.w};
@@ -252,26 +336,24 @@ __global__ void __launch_bounds__(256, 1) enc_fwd_fused_kernel(EncFusedDev a) {
       }
     }
     float mean, rstd;
-    layer_norm(v, a.emb_g, a.emb_b, mean, rstd);
-    drop32(v, site_id(SITE_EMB, 0));
-    uint32_t pk[16];
-    pack32(v, pk);
-    if (!valid) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) pk[i] = 0u;
-    }
-    st_tile(sX, row, half * 4, pk);
-    if (valid && train) st_global32(a.x0 + (size_t)t * FH + c0, pk);
+    layer_norm(v, sEmb, sEmb + 64, mean, rstd);
+    drop16(v, site_id(SITE_EMB, 0));
+    uint32_t pk[8];
+    pack_n<16>(v, pk);
+    zero_if<8>(!valid, pk);
+    st_tile<2>(sX, row, part * 2, pk);
+    if (valid && train) st_global<8>(a.x0 + (size_t)t * FH + cq, pk);
   }
 
   const float scale = rsqrtf((float)FD);
-  const int R16 = (R + 15) & ~15;
   for (int l = 0; l < a.L; ++l) {
     const LayerDev& Ly = a.layers[l];
+    const float* par = sPar + (l & 1) * PF;
     // ---------------------------------------------------------------- phase 1: QKV = X Wqkv + b
     phase_sync();
     if (tid == 0) {
       umma::fence_after_sync();
+      if (l >= 1 && l + 1 < a.L) load_P(l + 1);     // buffer (l+1)&1 was last read by layer l-1
       umma::mbar_wait(barA, l & 1);
       const uint32_t xa = umma::smem_addr(sX), wa = umma::smem_addr(sWA);
 #pragma unroll
@@ -279,22 +361,20 @@ __global__ void __launch_bounds__(256, 1) enc_fwd_fused_kernel(EncFusedDev a) {
         umma::mma_bf16_ss(tmem, umma::make_desc_k_sw128(xa + k * 32), desc_mn_sw128(wa + k * 2048, 8192), idesc_bmn(FT, 192), k ? 1u : 0u);
       umma::mma_commit(barM);
     }
+    umma::mbar_wait(barP + (l & 1), (l >> 1) & 1);  // this layer's biases / LN parameters are in shared memory
     wait_mma();
 #pragma unroll 1
-    for (int j = 0; j < 3; ++j) {
-      const int c = half * 3 + j;            // 32-column chunk of the 192-wide row: Q Q K K V V
-      float v[32];
-      tmem_ld_f32(tlane + c * 32, v);
-      add_bias(v, Ly.bqkv + c * 32);
-      uint32_t pk[16];
-      pack32(v, pk);
-      if (!valid) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = 0u;
-      }
-      unsigned char* tile = (c >> 1) == 0 ? sQ : ((c >> 1) == 1 ? sK : sV);
-      st_tile(tile, row, (c & 1) * 4, pk);
-      if (valid && train) st_global32(Ly.qkv + (size_t)t * 192 + c * 32, pk);
+    for (int i = 0; i < 3; ++i) {
+      const int j = part * 3 + i;            // 16-column chunk of the 192-wide row: Q Q Q Q K K K K V V V V
+      float v[16];
+      tmem_ld_f16(tlane + j * 16, v);
+      add_vec<16>(v, par + PB_BQKV + j * 16);
+      uint32_t pk[8];
+      pack_n<16>(v, pk);
+      zero_if<8>(!valid, pk);
+      unsigned char* tile = (j >> 2) == 0 ? sQ : ((j >> 2) == 1 ? sK : sV);
+      st_tile<2>(tile, row, (j & 3) * 2, pk);
+      if (valid && train) st_global<8>(Ly.qkv + (size_t)t * 192 + j * 16, pk);
     }
     // ---------------------------------------------------------------- phase 2: scores per head + softmax -> P
     phase_sync();
@@ -312,82 +392,95 @@ __global__ void __launch_bounds__(256, 1) enc_fwd_fused_kernel(EncFusedDev a) {
     wait_mma();
     float inv_l = 0.f;
     {
-      const int hd = half;                       // this warpgroup's head
-      const int g = valid ? row / S : 0;
-      const int ks = g * S, ke = ks + S;         // this row's keys (tile columns)
-      // chunks of 32 score columns any lane of this warp needs (tcgen05.ld is warp-collective)
-      int c_lo = 1, c_hi = 0;
-      if (quad * 32 < R) {
-        const int wr_hi = min(R - 1, quad * 32 + 31);
-        c_lo = ((quad * 32 / S) * S) >> 5;
-        c_hi = ((wr_hi / S + 1) * S - 1) >> 5;
-      }
-      float m = -INFINITY;
-      for (int c = c_lo; c <= c_hi; ++c) {
-        float s[32];
-        tmem_ld_f32(tlane + hd * 128 + c * 32, s);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int key = c * 32 + j;
-          const bool in = valid && key >= ks && key < ke;
-          m = fmaxf(m, in ? s[j] * scale + sMask[key] : -INFINITY);
-        }
-      }
-      // attention-prob dropout keep bits, identical stream to attn_fwd_kernel (k_attn.cu)
-      unsigned long long kw0 = ~0ull, kw1 = ~0ull;
+      // thread = (row, head, key half): of the four 32-key chunks of the score row it owns chunks kh and kh+2; only
+      // the chunks inside the row's own slot carry data, the others are zero-filled (foreign sequences)
+      const int hd = part >> 1, kh = part & 1;
+      const int CPS = SLOT >> 5;                 // 32-key chunks per slot
+      const int colbase = g * SLOT;
       const bool drop = train && a.thr_attn > 0;
-      const int bn = (t / S) * FNH + hd, qi = row % S, W = (S + 63) >> 6;
-      if (drop && valid) {
-        const uint32_t grow = (uint32_t)(bn * S + qi);
-        const uint32_t site = site_id(SITE_ATTN_PROBS, l);
-        for (int kb = 0; kb < W; ++kb) {
-          unsigned long long word = 0ull;
+      const int bn = seq * FNH + hd, W = (S + 63) >> 6;
+      bool dat[2]; int jl0[2];
 #pragma unroll
-          for (int o = 0; o < 8; ++o) {
-            const uint4 r = ph(grow, (uint32_t)(kb * 8 + o), site, step);
-            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int bit = ((o & 1) * 4 + i) * 8 + (o >> 1) * 2;
-              word |= (unsigned long long)((w[i] & 0xFFFFu) >= a.thr_attn ? 1u : 0u) << bit;
-              word |= (unsigned long long)((w[i] >> 16) >= a.thr_attn ? 1u : 0u) << (bit + 1);
-            }
-          }
-          if (kb == 0) kw0 = word; else kw1 = word;
-          Ly.keep[((size_t)bn * S + qi) * W + kb] = word;
-        }
+      for (int c = 0; c < 2; ++c) {
+        const int cc = kh + 2 * c;
+        dat[c] = (cc / CPS) == g;
+        jl0[c] = (cc % CPS) * 32;
       }
-      float lsum = 0.f;
-      unsigned char* pt = sP + hd * 2 * TILE_B;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-        if (c >= c_lo && c <= c_hi) {
+      const int keepc = dat[0] ? 0 : 1;
+      float sk[32];
+      float mloc = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (dat[c]) {
           float s[32];
-          tmem_ld_f32(tlane + hd * 128 + c * 32, s);
+          tmem_ld_f32(tlane + hd * 128 + (kh + 2 * c) * 32, s);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int key = c * 32 + j;
-            const bool in = valid && key >= ks && key < ke;
-            float p = in ? __expf(s[j] * scale + sMask[key] - m) : 0.f;
-            lsum += p;
-            if (drop) {
-              const int jl = key - ks;
-              const bool keep = (((jl < 64 ? kw0 : kw1) >> (jl & 63)) & 1ull) != 0ull;
-              p = keep ? p * a.inv_keep_attn : 0.f;
-            }
-            s[j] = p;
+            const int jl = jl0[c] + j;
+            const float v = (valid && jl < S) ? s[j] * scale + sMask[colbase + jl] : -INFINITY;
+            mloc = fmaxf(mloc, v);
+            if (c == keepc) sk[j] = v;
           }
-          pack32(s, pk);
+        }
+      }
+      const float m = fmaxf(mloc, pair_other(mloc));
+      float lsum = 0.f;
+      unsigned char* pt = sP + hd * 2 * TILE_B;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int cc = kh + 2 * c;
+        uint32_t pk[16];
+        if (dat[c]) {
+          float v[32];
+          if (c == keepc) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = sk[j];
+          } else {
+            tmem_ld_f32(tlane + hd * 128 + cc * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int jl = jl0[c] + j;
+              v[j] = (valid && jl < S) ? v[j] * scale + sMask[colbase + jl] : -INFINITY;
+            }
+          }
+          // attention-prob dropout keep bits of this chunk: identical stream to attn_fwd_kernel (k_attn.cu)
+          uint32_t bits = 0xFFFFFFFFu;
+          if (drop && valid) {
+            const int ci = jl0[c] >> 5, kb = ci >> 1, hf = ci & 1;
+            const uint32_t grow = (uint32_t)(bn * S + pos), site = site_id(SITE_ATTN_PROBS, l);
+            bits = 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int o = hf + 2 * u;
+              const uint4 r = ph(grow, (uint32_t)(kb * 8 + o), site, step);
+              const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int bit = i * 8 + u * 2;
+                bits |= ((w[i] & 0xFFFFu) >= a.thr_attn ? 1u : 0u) << bit;
+                bits |= ((w[i] >> 16) >= a.thr_attn ? 1u : 0u) << (bit + 1);
+              }
+            }
+            reinterpret_cast<uint32_t*>(Ly.keep)[(((size_t)bn * S + pos) * W + kb) * 2 + hf] = bits;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float p = v[j] == -INFINITY ? 0.f : __expf(v[j] - m);
+            lsum += p;
+            if (drop) p = ((bits >> j) & 1u) ? p * a.inv_keep_attn : 0.f;
+            v[j] = p;
+          }
+          pack_n<32>(v, pk);
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) pk[i] = 0u;
         }
-        st_tile(pt + (c >> 1) * TILE_B, row, (c & 1) * 4, pk);
+        st_tile<4>(pt + (cc >> 1) * TILE_B, row, (cc & 1) * 4, pk);
       }
+      const float lall = lsum + pair_other(lsum);
       if (valid) {
-        inv_l = 1.0f / lsum;
-        if (train) Ly.lse[(size_t)bn * S + qi] = m + __logf(lsum);
+        inv_l = 1.0f / lall;
+        if (train && kh == 0) Ly.lse[(size_t)bn * S + pos] = m + __logf(lall);
       }
     }
     // ---------------------------------------------------------------- phase 3: ctx = P V per head
@@ -396,26 +489,24 @@ __global__ void __launch_bounds__(256, 1) enc_fwd_fused_kernel(EncFusedDev a) {
       umma::fence_after_sync();
       const uint32_t pa = umma::smem_addr(sP), va = umma::smem_addr(sV);
       for (int hd = 0; hd < FNH; ++hd)
-        for (int kk = 0; kk < R16 / 16; ++kk)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
           umma::mma_bf16_ss(tmem + 256 + hd * 64, umma::make_desc_k_sw128(pa + hd * 2 * TILE_B + (kk >> 2) * TILE_B + (kk & 3) * 32),
                             desc_mn_sw128(va + kk * 2048, 8192), idesc_bmn(FT, 64), kk ? 1u : 0u);
       umma::mma_commit(barM);
     }
     wait_mma();
     {
-      const int hd = half;
-      float v[32];
-      tmem_ld_f32(tlane + 256 + hd * 64 + hd * FD, v);   // head hd's 32 columns of its own accumulator
+      const int hd = part >> 1;
+      float v[16];
+      tmem_ld_f16(tlane + 256 + hd * 64 + cq, v);   // head hd's columns of its own accumulator (cq = hd*32 + kh*16)
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] *= inv_l;
-      uint32_t pk[16];
-      pack32(v, pk);
-      if (!valid) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = 0u;
-      }
-      st_tile(sCtx, row, hd * 4, pk);
-      if (valid && train) st_global32(Ly.ctx + (size_t)t * FH + hd * FD, pk);
+      for (int i = 0; i < 16; ++i) v[i] *= inv_l;
+      uint32_t pk[8];
+      pack_n<16>(v, pk);
+      zero_if<8>(!valid, pk);
+      st_tile<2>(sCtx, row, part * 2, pk);
+      if (valid && train) st_global<8>(Ly.ctx + (size_t)t * FH + cq, pk);
     }
     // ---------------------------------------------------------------- phase 4: a = x + drop(ctx Wo + bo) ; y = LN1(a)
     phase_sync();
@@ -429,30 +520,7 @@ __global__ void __launch_bounds__(256, 1) enc_fwd_fused_kernel(EncFusedDev a) {
     }
     wait_mma();
     if (tid == 0 && l + 1 < a.L) load_A(l + 1);   // Wqkv / Wo of the next layer stream in behind the epilogue
-    {
-      float v[32], res[32];
-      tmem_ld_f32(tlane + 384 + c0, v);
-      add_bias(v, Ly.bo + c0);
-      drop32(v, site_id(SITE_ATTN_OUT, l));
-      ld_tile(sX, row, half * 4, res);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += res[i];
-      uint32_t pk[16];
-      round32(v, pk);                              // LN statistics on the bf16 value backward re-reads
-      if (valid && train) st_global32(Ly.a_pre + (size_t)t * FH + c0, pk);
-      float mean, rstd;
-      layer_norm(v, Ly.g1, Ly.be1, mean, rstd);
-      pack32(v, pk);
-      if (!valid) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = 0u;
-      }
-      st_tile(sY, row, half * 4, pk);
-      if (valid && train) {
-        st_global32(Ly.y + (size_t)t * FH + c0, pk);
-        if (half == 0) { Ly.mean1[t] = mean; Ly.rstd1[t] = rstd; }
-      }
-    }
+    res_ln_epilogue(384, par + PB_BO, site_id(SITE_ATTN_OUT, l), sX, par + PB_G1, par + PB_BE1, Ly.a_pre, sY, Ly.y, false, Ly.mean1, Ly.rstd1);
     // ---------------------------------------------------------------- phase 5: h = gelu(y W1 + b1)
     phase_sync();
     if (tid == 0) {
@@ -467,23 +535,20 @@ __global__ void __launch_bounds__(256, 1) enc_fwd_fused_kernel(EncFusedDev a) {
     }
     wait_mma();
 #pragma unroll 1
-    for (int j = 0; j < I / 64; ++j) {
-      const int c = half * (I / 64) + j;      // 32-column chunk of the I-wide row
-      float v[32];
-      tmem_ld_f32(tlane + c * 32, v);
-      add_bias(v, Ly.b1 + c * 32);
-      uint32_t pk[16];
-      round32(v, pk);                          // GELU of the bf16 pre-activation backward re-reads
-      if (valid && train) st_global32(Ly.h_pre + (size_t)t * I + c * 32, pk);
+    for (int i = 0; i < I / 64; ++i) {
+      const int j = part * (I / 64) + i;      // 16-column chunk of the I-wide row
+      float v[16];
+      tmem_ld_f16(tlane + j * 16, v);
+      add_vec<16>(v, par + PB_B1 + j * 16);
+      uint32_t pk[8];
+      round_n<16>(v, pk);                      // GELU of the bf16 pre-activation backward re-reads
+      if (valid && train) st_global<8>(Ly.h_pre + (size_t)t * I + j * 16, pk);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-      pack32(v, pk);
-      if (!valid) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = 0u;
-      }
-      st_tile(sHh + (c >> 1) * TILE_B, row, (c & 1) * 4, pk);
-      if (valid && train) st_global32(Ly.h + (size_t)t * I + c * 32, pk);
+      for (int k = 0; k < 16; ++k) v[k] = gelu_erf(v[k]);
+      pack_n<16>(v, pk);
+      zero_if<8>(!valid, pk);
+      st_tile<2>(sHh + (j >> 2) * TILE_B, row, (j & 3) * 2, pk);
+      if (valid && train) st_global<8>(Ly.h + (size_t)t * I + j * 16, pk);
     }
     // ---------------------------------------------------------------- phase 6: o = y + drop(h W2 + b2) ; out = LN2(o)
     phase_sync();
@@ -497,36 +562,20 @@ __global__ void __launch_bounds__(256, 1) enc_fwd_fused_kernel(EncFusedDev a) {
     }
     wait_mma();
     if (tid == 0 && l + 1 < a.L) load_B(l + 1);
-    {
-      float v[32], res[32];
-      tmem_ld_f32(tlane + 448 + c0, v);
-      add_bias(v, Ly.b2 + c0);
-      drop32(v, site_id(SITE_FFN_OUT, l));
-      ld_tile(sY, row, half * 4, res);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += res[i];
-      uint32_t pk[16];
-      round32(v, pk);
-      if (valid && train) st_global32(Ly.o_pre + (size_t)t * FH + c0, pk);
-      float mean, rstd;
-      layer_norm(v, Ly.g2, Ly.be2, mean, rstd);
-      pack32(v, pk);
-      if (!valid) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = 0u;
-      }
-      st_tile(sX, row, half * 4, pk);
-      if (valid) {
-        st_global32(Ly.out + (size_t)t * FH + c0, pk);
-        if (train && half == 0) { Ly.mean2[t] = mean; Ly.rstd2[t] = rstd; }
-      }
-    }
+    res_ln_epilogue(448, par + PB_B1 + I, site_id(SITE_FFN_OUT, l), sY, par + PB_B1 + I + 64, par + PB_B1 + I + 128, Ly.o_pre, sX, Ly.out, true,
+                    Ly.mean2, Ly.rstd2);
   }
+  stamp();
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 1) {
     umma::fence_after_sync();
     umma::tmem_dealloc<512>(tmem);
+  }
+  if (a.dbg && tid == 0 && blockIdx.x < 128) {
+    unsigned long long tns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+    a.dbg[257 + 2 * blockIdx.x] = tns;
   }
 }
 
@@ -537,7 +586,7 @@ bool enc_fused_supported(int H, int N, int S, int I) {
   if (I < 64 || I > 256 || (I % 64)) return false;
   return enc_fused_smem_bytes(I) <= 232448;
 }
-size_t enc_fused_smem_bytes(int I) { return (size_t)OFF_WB + (size_t)I * 256 + FT * 4 + 64 + 1024; }
+size_t enc_fused_smem_bytes(int I) { return (size_t)OFF_WB + (size_t)I * 256 + 2 * (size_t)par_floats(I) * 4 + 128 * 4 + FT * 4 + 8 * FT * 4 + 64 + 1024; }
 size_t enc_fused_table_bytes(int L) { return (size_t)L * sizeof(LayerDev) + 128 + (size_t)L * 4 * sizeof(CUtensorMap); }
 
 // Fills the device-side layer table + tensor maps (host staging buffer `host`, same size as the device block).
@@ -546,7 +595,11 @@ bool enc_fused_build_tables(const EncFusedLayerHost* layers, int L, int I, const
   LayerDev* ld = reinterpret_cast<LayerDev*>(host);
   for (int l = 0; l < L; ++l) {
     const EncFusedLayerHost& h = layers[l];
-    ld[l] = LayerDev{h.bqkv, h.bo, h.g1, h.be1, h.b1, h.b2, h.g2, h.be2, h.qkv, h.ctx, h.a_pre, h.y, h.h_pre, h.h, h.o_pre, h.out,
+    // the kernel bulk-copies the eight per-layer vectors as ONE block: they must be contiguous in this order
+    if (h.bo != h.bqkv + 192 || h.g1 != h.bo + 64 || h.be1 != h.g1 + 64 || h.b1 != h.be1 + 64 || h.b2 != h.b1 + I || h.g2 != h.b2 + 64 ||
+        h.be2 != h.g2 + 64 || ((uintptr_t)h.bqkv & 15))
+      return false;
+    ld[l] = LayerDev{h.bqkv, h.qkv, h.ctx, h.a_pre, h.y, h.h_pre, h.h, h.o_pre, h.out,
                      h.lse, h.mean1, h.rstd1, h.mean2, h.rstd2, reinterpret_cast<unsigned long long*>(h.keep)};
   }
   size_t moff = ((size_t)L * sizeof(LayerDev) + 127) / 128 * 128;
@@ -570,11 +623,11 @@ cudaError_t launch_enc_fwd_fused(const EncFusedArgs& a, cudaStream_t st) {
   d.layers = reinterpret_cast<const LayerDev*>(a.dev_tables);
   size_t moff = ((size_t)a.L * sizeof(LayerDev) + 127) / 128 * 128;
   d.maps = reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const char*>(a.dev_tables) + moff);
-  d.B = a.B; d.S = a.S; d.V = a.V; d.L = a.L; d.G = FT / a.S; d.I = a.I; d.training = a.training;
+  d.B = a.B; d.S = a.S; d.V = a.V; d.L = a.L; d.slot = a.S <= 32 ? 32 : (a.S <= 64 ? 64 : 128); d.I = a.I; d.training = a.training;
   d.thr_out = drop_threshold16(a.out_drop); d.thr_attn = drop_threshold16(a.attn_drop);
   d.inv_keep_out = 1.0f / (1.0f - (float)d.thr_out / 65536.0f);
   d.inv_keep_attn = 1.0f / (1.0f - (float)d.thr_attn / 65536.0f);
-  d.seed = a.seed; d.step = a.step; d.d_step = a.d_step;
+  d.seed = a.seed; d.step = a.step; d.d_step = a.d_step; d.dbg = reinterpret_cast<unsigned long long*>(a.dbg);
   const size_t smem = enc_fused_smem_bytes(a.I);
   static size_t cap = 0;
   if (smem > cap) {
@@ -582,8 +635,9 @@ cudaError_t launch_enc_fwd_fused(const EncFusedArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     cap = smem;
   }
-  const int grid = (a.B + d.G - 1) / d.G;
-  enc_fwd_fused_kernel<<<grid, 256, smem, st>>>(d);
+  const int G = FT / d.slot;
+  const int grid = (a.B + G - 1) / G;
+  enc_fwd_fused_kernel<<<grid, NTHR, smem, st>>>(d);
   return cudaGetLastError();
 }
 

@@ -158,10 +158,11 @@ cudaError_t launch_head_bwd_rows(const float* dt_part, int nsplit, size_t split_
 __global__ void __launch_bounds__(256) grad_reduce_kernel(const ReduceJob* __restrict__ jobs) {
   __shared__ float s[8][33];
   const ReduceJob job = jobs[blockIdx.y];
-  const int c0 = blockIdx.x * 1024;  // every block owns 1024 consecutive columns of its job
-  if (c0 >= job.len) return;
   if (job.nparts <= 8) {
-    // few, long partials (split-K weight gradients, vocabulary-sized buffers): one thread per column, coalesced
+    // few, long partials (split-K weight gradients, vocabulary-sized buffers): 1024 columns per block, one thread per
+    // column, coalesced
+    const int c0 = blockIdx.x * 1024;
+    if (c0 >= job.len) return;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int col = c0 + k * 256 + threadIdx.x;
@@ -174,39 +175,38 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const ReduceJob* __res
     }
     return;
   }
-  // many short partials (per-CTA bias / LayerNorm sums): 32 columns x 8 part-lanes per pass
+  // many partials (per-CTA bias / LayerNorm sums, token-split weight gradients): 32 columns x 8 part-lanes per block
+  const int cb = blockIdx.x * 32;
+  if (cb >= job.len) return;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int sub = 0; sub < 32; ++sub) {
-    const int cb = c0 + sub * 32;
-    if (cb >= job.len) break;  // uniform
-    const int col = cb + tx;
-    float acc = 0.f;
-    if (col < job.len) {
-      const float* p = job.src + col;
-      int k = ty;
-      for (; k + 24 < job.nparts; k += 32) {
-        float a = p[(size_t)k * job.part_stride], b = p[(size_t)(k + 8) * job.part_stride];
-        float c = p[(size_t)(k + 16) * job.part_stride], d = p[(size_t)(k + 24) * job.part_stride];
-        acc += a; acc += b; acc += c; acc += d;
-      }
-      for (; k < job.nparts; k += 8) acc += p[(size_t)k * job.part_stride];
+  const int col = cb + tx;
+  float acc = 0.f;
+  if (col < job.len) {
+    const float* p = job.src + col;
+    int k = ty;
+    for (; k + 24 < job.nparts; k += 32) {
+      float a = p[(size_t)k * job.part_stride], b = p[(size_t)(k + 8) * job.part_stride];
+      float c = p[(size_t)(k + 16) * job.part_stride], d = p[(size_t)(k + 24) * job.part_stride];
+      acc += a; acc += b; acc += c; acc += d;
     }
-    s[ty][tx] = acc;
-    __syncthreads();
-    if (ty == 0 && col < job.len) {
-      float v = 0.f;
+    for (; k < job.nparts; k += 8) acc += p[(size_t)k * job.part_stride];
+  }
+  s[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && col < job.len) {
+    float v = 0.f;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) v += s[r][tx];
-      if (job.accumulate) v += job.dst[col];
-      job.dst[col] = v;
-    }
-    __syncthreads();
+    for (int r = 0; r < 8; ++r) v += s[r][tx];
+    if (job.accumulate) v += job.dst[col];
+    job.dst[col] = v;
   }
 }
 
-cudaError_t launch_grad_reduce(const ReduceJob* d_jobs, int njobs, int max_len, cudaStream_t st) {
+int grad_reduce_blocks(int nparts, int len) { return nparts <= 8 ? (len + 1023) / 1024 : (len + 31) / 32; }
+
+cudaError_t launch_grad_reduce(const ReduceJob* d_jobs, int njobs, int max_blocks, cudaStream_t st) {
   if (njobs <= 0) return cudaSuccess;
-  dim3 grid((max_len + 1023) / 1024, njobs);
+  dim3 grid(max_blocks, njobs);
   grad_reduce_kernel<<<grid, 256, 0, st>>>(d_jobs);
   return cudaGetLastError();
 }

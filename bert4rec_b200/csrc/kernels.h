@@ -122,6 +122,7 @@ struct EncFusedArgs {
   const void* dev_tables;   // device block built by enc_fused_build_tables
   int B, S, V, L, I, training;
   float out_drop, attn_drop; uint64_t seed; uint32_t step; const long long* d_step;
+  void* dbg;                // optional device uint64[256]: phase timestamps of CTA 0
 };
 bool enc_fused_supported(int H, int N, int S, int I);
 size_t enc_fused_smem_bytes(int I);
@@ -140,7 +141,8 @@ cudaError_t launch_ln_bwd(const float* d_out, const bf16* pre, const float* mean
 int ln_bwd_parts(int M);
 
 struct ReduceJob { const float* src; float* dst; int nparts; int len; long long part_stride; int accumulate; };
-cudaError_t launch_grad_reduce(const ReduceJob* d_jobs, int njobs, int max_len, cudaStream_t st);
+cudaError_t launch_grad_reduce(const ReduceJob* d_jobs, int njobs, int max_blocks, cudaStream_t st);
+int grad_reduce_blocks(int nparts, int len);  // blocks (grid.x) one job needs; pass the max over the jobs of a launch
 
 // squared L2 norm partials of g[0..n) -> out_part[nblocks] ; deterministic two-stage
 cudaError_t launch_sqnorm(const float* g, long long n, float* out_part, int nblocks, cudaStream_t st);

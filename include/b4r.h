@@ -118,7 +118,8 @@ int b4r_launch_count(b4r_session* s);   /* kernels launched through this session
 /* flag 1: tcgen05/TMA generation of the tied-projection kernels (1, default) or the mma.sync generation (0);
  * flag 2: whole-encoder fused tcgen05 forward (1, default where the shape allows) or the layered kernels (0) */
 int b4r_session_set_flag(b4r_session* s, int flag, int value);
-const void* b4r_debug_buffer(b4r_session* s);  /* kernel-internal timestamps when B4R_CE_DEBUG&8 (development aid) */
+const void* b4r_debug_buffer(b4r_session* s);
+const void* b4r_debug_buffer2(b4r_session* s); /* uint64[512]: fused-kernel phase timestamps (ns) when B4R_FUSED_DEBUG is set */  /* kernel-internal timestamps when B4R_CE_DEBUG&8 (development aid) */
 /* per-kernel CUDA-event timing of everything launched through the session (events on the launching stream);
  * report: lines "tag count total_ms", synchronises, clears the records. */
 int b4r_profile_enable(b4r_session* s, int on);

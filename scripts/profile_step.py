@@ -25,17 +25,10 @@ for i in range(n):
     model.train_step(batches[i % 2])
 ev1.record(); torch.cuda.synchronize()
 print(f"{wl}: {ev0.elapsed_time(ev1) / n * 1e3:.1f} us/step back-to-back (no flush), {w['batch'] * n / ev0.elapsed_time(ev1) * 1e3:.0f} seq/s")
-model.use_cuda_graph = False
-for i in range(3):
-    model.train_step(batches[i % 2])
-sess.profile(True)
-for i in range(n):
-    model.train_step(batches[i % 2])
-rep = sess.profile_report()
-sess.profile(False)
+rep = bench.profile_steps(model, sess, batches, n)
 rows = sorted(rep.items(), key=lambda kv: -kv[1][1])
 tot = sum(v[1] for v in rep.values())
-print(f"sum of kernel event times: {tot / n * 1e3:.1f} us/step over {sum(v[0] for v in rep.values()) / n:.0f} launches")
+print(f"sum of kernel times inside the graph: {tot / n * 1e3:.1f} us/step over {sum(v[0] for v in rep.values()) / n:.0f} launches")
 n_rows = int(sess.counts()[1])
 for tag, (cnt, ms) in rows:
     fl, by, bound = bench.kernel_work(tag, w, n_rows)

@@ -12,7 +12,8 @@ SHAPES = {
     "s50_two_per_tile": (25, 50, 8, 64, 2),       # odd batch: the last tile holds one sequence
     "s20_six_per_tile": (13, 20, 4, 128, 3),
     "s128_one_per_tile": (3, 128, 20, 64, 1),
-    "s64_i256": (5, 64, 10, 256, 2),
+    "s64_i192": (5, 64, 10, 192, 2),
+    "s33_slot64": (9, 33, 6, 64, 2),
     "s7_tiny": (40, 7, 2, 64, 1),
 }
 SAVED = ("x0", "qkv", "ctx", "a_pre", "y", "h_pre", "h", "o_pre", "out", "mean1", "rstd1", "mean2", "rstd2", "lse")
