@@ -199,6 +199,9 @@ struct b4r_session {
   bool use_umma = false;
   CeUmmaMaps umaps;
   bool use_fused = false;   // whole-encoder forward in one tcgen05 launch (k_enc_fused.cu)
+  bool use_fused_bwd = false, fused_bwd_ok = false;   // ... and the backward (k_enc_fused_bwd.cu)
+  float *enc_wpart = nullptr, *enc_bpart = nullptr;
+  ReduceJob* d_jobs_f = nullptr; int n_jobs_f = 0, jobs_f_blocks = 0;   // reduce jobs when the fused backward produced the partials
   void* d_enc_tables = nullptr;
   unsigned long long* dbg_buf = nullptr;
   bf16* dlogits; int dl_rows;
@@ -228,18 +231,21 @@ static int wgrad_splits(int M, int N, int T) {
   return s;
 }
 
-static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<ReduceJob>* jobs) {
+static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<ReduceJob>* jobs, std::vector<ReduceJob>* jobs_f = nullptr) {
   Bump b{reinterpret_cast<char*>(ws), 0, cap, dry};
   const int T = s->T, H = s->H, I = s->I, V = s->V, N = s->N, B = s->B, S = s->S, Mcap = s->Mcap;
   const int W = attn_mask_words(S);
   auto off = [&](const std::string& n) { return s->lay.find(n); };
+  bool in_layers = false;   // jobs pushed inside the layer loop belong to the layered backward only
   auto job = [&](float* src, int64_t dst_off, int nparts, int len, long long stride) {
     if (jobs && s->grads) jobs->push_back(ReduceJob{src, s->grads + dst_off, nparts, len, stride, 0});
+    if (jobs_f && s->grads && !in_layers) jobs_f->push_back(ReduceJob{src, s->grads + dst_off, nparts, len, stride, 0});
   };
   s->x0 = b.take<bf16>((size_t)T * H);
   s->layers.resize(s->cfg.num_layers);
   const int ln_parts = ln_bwd_parts(T);
   const int mt128 = (T + gemm_block_m() - 1) / gemm_block_m();
+  in_layers = true;
   for (int l = 0; l < s->cfg.num_layers; ++l) {
     LayerBuf& L = s->layers[l];
     std::string p = "layer_" + std::to_string(l) + "/";
@@ -279,6 +285,19 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
     job(L.p_ln1 + 2 * H, L.bo, ln_parts, H, 3 * H);
     job(L.p_b1, L.b1, mt128, I, I);
     job(L.p_bqkv, L.bqkv, kColsumSplits, 3 * H, 3 * H);
+  }
+  in_layers = false;
+  s->fused_bwd_ok = enc_bwd_fused_supported(H, N, S, I);
+  if (s->fused_bwd_ok) {
+    const int nc = enc_fused_ctas(B, S), Ln = s->cfg.num_layers;
+    const size_t WPn = enc_bwd_wpart_floats(I), PFn = enc_bwd_bpart_floats(I);
+    s->enc_wpart = b.take<float>((size_t)Ln * nc * WPn);
+    s->enc_bpart = b.take<float>((size_t)Ln * nc * PFn);
+    for (int l = 0; l < Ln && jobs_f && s->grads; ++l) {
+      // the four kernels of a layer (and its eight bias / LayerNorm vectors) are contiguous in the flat layout
+      jobs_f->push_back(ReduceJob{s->enc_wpart + (size_t)l * nc * WPn, s->grads + s->layers[l].wqkv, nc, (int)WPn, (long long)WPn, 0});
+      jobs_f->push_back(ReduceJob{s->enc_bpart + (size_t)l * nc * PFn, s->grads + s->layers[l].bqkv, nc, (int)PFn, (long long)PFn, 0});
+    }
   }
   // head
   s->rows = b.take<int>(Mcap); s->labels = b.take<int>(Mcap); s->row_mult = b.take<int>(Mcap);
@@ -358,6 +377,7 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
   job(s->p_embln, off("emb_ln/gamma"), s->emb_bsplits * S, H, 2 * H);
   job(s->p_embln + H, off("emb_ln/beta"), s->emb_bsplits * S, H, 2 * H);
   s->d_jobs = b.take<ReduceJob>(256);
+  s->d_jobs_f = b.take<ReduceJob>(256);
   s->d_vb_jobs = b.take<ReduceJob>(2);
   s->d_enc_tables = b.take<unsigned char>(enc_fused_table_bytes(s->cfg.num_layers));
   s->dbg_buf = b.take<unsigned long long>(512);
@@ -406,14 +426,18 @@ extern "C" int b4r_session_create(const b4r_config* cfg, int batch, int seq_len,
     return fail("buffers must be aligned (params/grads 32 B, shadow 16 B, workspace 256 B)");
   b4r_session* s = make_session_shell(cfg, batch, seq_len, max_pred);
   s->params = params; s->shadow = reinterpret_cast<bf16*>(shadow_bf16); s->grads = grads;
-  std::vector<ReduceJob> jobs;
-  size_t need = carve(s, workspace, workspace_bytes, false, &jobs);
+  std::vector<ReduceJob> jobs, jobs_f;
+  size_t need = carve(s, workspace, workspace_bytes, false, &jobs, &jobs_f);
   if (need > workspace_bytes) { delete s; return fail("workspace too small: need %zu bytes, got %zu", need, workspace_bytes); }
   if (jobs.size() > 256) { delete s; return fail("too many reduce jobs"); }
   s->n_jobs = (int)jobs.size();
   s->jobs_max_len = 0;
   for (auto& j : jobs) { int nb = grad_reduce_blocks(j.nparts, j.len); if (nb > s->jobs_max_len) s->jobs_max_len = nb; }
   CK(cudaMemcpy(s->d_jobs, jobs.data(), jobs.size() * sizeof(ReduceJob), cudaMemcpyHostToDevice));
+  if (jobs_f.size() > 256) { delete s; return fail("too many reduce jobs"); }
+  s->n_jobs_f = (int)jobs_f.size();
+  for (auto& j : jobs_f) { int nb = grad_reduce_blocks(j.nparts, j.len); if (nb > s->jobs_f_blocks) s->jobs_f_blocks = nb; }
+  if (!jobs_f.empty()) CK(cudaMemcpy(s->d_jobs_f, jobs_f.data(), jobs_f.size() * sizeof(ReduceJob), cudaMemcpyHostToDevice));
   ReduceJob vb[2];
   vb[0] = ReduceJob{s->p_vbias, grads ? grads + s->lay.find("head/output_bias") : nullptr, s->vb_splits, s->V, (long long)s->V, 0};
   vb[1] = vb[0]; vb[1].accumulate = 1;
@@ -443,6 +467,7 @@ extern "C" int b4r_session_create(const b4r_config* cfg, int batch, int seq_len,
     if (enc_fused_build_tables(lh.data(), Ln, s->I, wp.data(), host.data(), s->d_enc_tables)) {
       CK(cudaMemcpy(s->d_enc_tables, host.data(), host.size(), cudaMemcpyHostToDevice));
       s->use_fused = true;
+      s->use_fused_bwd = s->fused_bwd_ok && s->grads != nullptr;
     }
   }
   *out = s;
@@ -646,7 +671,16 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
     KL("gemm:head_dx_scatter", launch_gemm(EPI_SCATTER_F32, g, st));
   }
   // ---- encoder layers, last to first.  d_out lives in dxa at the top of every iteration.
-  for (int l = s->cfg.num_layers - 1; l >= 0; --l) {
+  const bool fbwd = s->use_fused_bwd && s->use_fused;   // the fused backward assumes the fused forward's tables
+  if (fbwd) {
+    EncBwdArgs f{};
+    f.mask = s->mask; f.x0 = s->x0; f.dev_tables = s->d_enc_tables; f.dx = s->dxa; f.wpart = s->enc_wpart; f.bpart = s->enc_bpart;
+    f.B = s->B; f.S = s->S; f.L = s->cfg.num_layers; f.I = I;
+    f.out_drop = od; f.attn_drop = s->cfg.attention_dropout; f.seed = seed; f.step = step; f.d_step = d_step;
+    f.dbg = getenv("B4R_FUSED_DEBUG") ? (void*)s->dbg_buf : nullptr;
+    KL("enc_bwd_fused", launch_enc_bwd_fused(f, st));
+  }
+  for (int l = s->cfg.num_layers - 1; l >= 0 && !fbwd; --l) {
     LayerBuf& L = s->layers[l];
     const bf16* x_in = l == 0 ? s->x0 : s->layers[l - 1].out;
     KL("ln_bwd", launch_ln_bwd(s->dxa, L.o_pre, L.mean2, L.rstd2, P + L.g2, s->dxb, s->d_branch, L.p_ln2, T, H, od, seed,
@@ -711,7 +745,8 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
   }
   KL("embed_bwd", launch_embed_bwd(s->ids, W + oE, W + s->lay.find("position_embedding"), P + s->lay.find("emb_ln/gamma"), s->dxa,
                       G + oE, s->p_dpos, s->p_embln, s->B, s->S, H, V, od, seed, step, d_step, s->emb_bsplits, st));
-  KL("grad_reduce:all", launch_grad_reduce(s->d_jobs, s->n_jobs, s->jobs_max_len, st));
+  if (fbwd) KL("grad_reduce:all", launch_grad_reduce(s->d_jobs_f, s->n_jobs_f, s->jobs_f_blocks, st));
+  else KL("grad_reduce:all", launch_grad_reduce(s->d_jobs, s->n_jobs, s->jobs_max_len, st));
   return 0;
 }
 
@@ -833,6 +868,11 @@ extern "C" const void* b4r_debug_buffer2(b4r_session* s) { return s ? (const voi
 extern "C" int b4r_session_set_flag(b4r_session* s, int flag, int value) {
   if (!s) return fail("null session");
   if (flag == 1) { s->use_umma = value != 0; return 0; }
+  if (flag == 3) {
+    if (value && !s->fused_bwd_ok) return fail("fused encoder backward unavailable for this shape");
+    s->use_fused_bwd = value != 0;
+    return 0;
+  }
   if (flag == 2) {
     if (value && !s->d_enc_tables) return fail("fused encoder unavailable");
     s->use_fused = value != 0 && enc_fused_supported(s->H, s->N, s->S, s->I);

@@ -9,7 +9,8 @@
 namespace b4r {
 
 // ------------------------------------------------------------------------------------------------ compaction
-// Single CTA.  Order of the compacted rows = row-major (b, p) order of the valid slots (= tf.boolean_mask order).
+// Single CTA, 4 consecutive slots per thread per pass.  Order of the compacted rows = row-major (b, p) order of the
+// valid slots (= tf.boolean_mask order).
 __global__ void __launch_bounds__(1024) mlm_select_kernel(const int64_t* __restrict__ positions, const int64_t* __restrict__ ids,
                                                           const int64_t* __restrict__ weights, int use_weights, int B, int S,
                                                           int P, int want_aux, int* __restrict__ rows, int* __restrict__ labels,
@@ -21,15 +22,12 @@ __global__ void __launch_bounds__(1024) mlm_select_kernel(const int64_t* __restr
   if (tid == 0) s_carry = 0;
   __syncthreads();
   const int n = B * P;
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + tid;
-    int valid = 0;
-    if (i < n) valid = use_weights == 2 ? 1 : (use_weights ? (weights[i] != 0) : (ids[i] != 0));
-    // block exclusive scan
-    int x = valid;
+  // block exclusive scan of one int per thread; returns the exclusive prefix, *total = block total
+  auto block_scan = [&](int x, int* total) -> int {
+    int incl = x;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) s_warp[warp] = x;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     if (warp == 0) {
       int w = s_warp[lane];
@@ -38,57 +36,70 @@ __global__ void __launch_bounds__(1024) mlm_select_kernel(const int64_t* __restr
       s_warp[lane] = w;
     }
     __syncthreads();
-    const int carry = s_carry;
-    const int excl = carry + (warp > 0 ? s_warp[warp - 1] : 0) + x - valid;
-    if (valid) {
-      const int b = i / P;
-      long long pos = positions[i];
-      pos = pos < 0 ? 0 : (pos >= S ? S - 1 : pos);
-      rows[excl] = b * S + (int)pos;
-      labels[excl] = (int)ids[i];
-      row_w[excl] = ids[i] != 0 ? 1.f : 0.f;
-      row_mult[excl] = 1;
-    }
+    const int excl = (warp > 0 ? s_warp[warp - 1] : 0) + incl - x;
+    *total = s_warp[31];
     __syncthreads();
-    if (tid == 1023) s_carry = carry + s_warp[31];
+    return excl;
+  };
+  for (int base = 0; base < n; base += 4096) {
+    const int i0 = base + tid * 4;
+    long long idv[4];
+    int val[4], cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k;
+      const bool ok = i < n;
+      idv[k] = ok ? ids[i] : 0;
+      val[k] = !ok ? 0 : (use_weights == 2 ? 1 : (use_weights ? (weights[i] != 0) : (idv[k] != 0)));
+      cnt += val[k];
+    }
+    int total;
+    const int carry = s_carry;   // read before the scan's barriers; thread 0 updates it after them
+    int excl = carry + block_scan(cnt, &total);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (val[k]) {
+        const int i = i0 + k;
+        long long pos = positions[i];
+        pos = pos < 0 ? 0 : (pos >= S ? S - 1 : pos);
+        rows[excl] = (i / P) * S + (int)pos;
+        labels[excl] = (int)idv[k];
+        row_w[excl] = idv[k] != 0 ? 1.f : 0.f;
+        row_mult[excl] = 1;
+        ++excl;
+      }
+    }
+    if (tid == 0) s_carry += total;
     __syncthreads();
   }
   const int n_valid = s_carry;
-  __syncthreads();
   if (want_aux) {
     // one aux row per sequence with padded slots: logits of (b, position 0) against label 0, for
-    // SparseCategoricalAccuracy over ALL slots (bert4rec_trainer.py:30)
+    // SparseCategoricalAccuracy over ALL slots (bert4rec_trainer.py:30).  One thread per sequence, independent loads.
     for (int base = 0; base < B; base += 1024) {
-      const int b = base + tid;
       int npad = 0;
-      if (b < B) {
+      if (base + tid < B) {
+        const int64_t* src = (use_weights ? weights : ids) + (size_t)(base + tid) * P;
         int nv = 0;
-        for (int p = 0; p < P; ++p) nv += use_weights == 2 ? 1 : (use_weights ? (weights[b * P + p] != 0) : (ids[b * P + p] != 0));
+        if (use_weights == 2) nv = P;
+        else {
+#pragma unroll 8
+          for (int p = 0; p < P; ++p) nv += src[p] != 0;
+        }
         npad = P - nv;
       }
-      const int has = npad > 0;
-      int x = has;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-      if (lane == 31) s_warp[warp] = x;
-      __syncthreads();
-      if (warp == 0) {
-        int w = s_warp[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
-        s_warp[lane] = w;
-      }
-      __syncthreads();
+      const int b = base + tid;
+      const int has = (b < B && npad > 0) ? 1 : 0;
+      int total;
       const int carry = s_carry;
-      const int excl = carry + (warp > 0 ? s_warp[warp - 1] : 0) + x - has;
+      const int excl = carry + block_scan(has, &total);
       if (has) {
         rows[excl] = b * S;
         labels[excl] = 0;
         row_w[excl] = 0.f;
         row_mult[excl] = npad;
       }
-      __syncthreads();
-      if (tid == 1023) s_carry = carry + s_warp[31];
+      if (tid == 0) s_carry += total;
       __syncthreads();
     }
   }
@@ -285,30 +296,48 @@ __global__ void __launch_bounds__(256) ce_finalize_kernel(CeDev a, float* __rest
     a.vsplits = vs;
   }
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // loss_sum, n_valid, correct_masked, correct_all, n_all
-  for (int r = blockIdx.x * 256 + tid; r < n_rows; r += gridDim.x * 256) {
+  // 8 lanes per row: lane q merges splits q, q+8, ...; the 8 lanes are then merged by an xor butterfly (fixed order)
+  const int q = lane & 7, rsub = lane >> 3;
+  for (int r0 = blockIdx.x * 32; r0 < n_rows; r0 += gridDim.x * 32) {
+    const int r = r0 + warp * 4 + rsub;
     float mn = -INFINITY, l = 0.f, lab = -INFINITY, bv = -INFINITY;
     int bi = 0x7fffffff;
-    for (int s = 0; s < a.vsplits; ++s) {
-      const float* p = a.part + ((size_t)s * a.M_cap + r) * 6;
-      const float m2 = p[0], l2 = p[1];
+    if (r < n_rows) {
+      for (int s = q; s < a.vsplits; s += 8) {
+        const float2* p = reinterpret_cast<const float2*>(a.part + ((size_t)s * a.M_cap + r) * 6);
+        const float2 p01 = p[0], p23 = p[1], p45 = p[2];
+        const float m3 = fmaxf(mn, p01.x);
+        if (m3 != -INFINITY) l = l * __expf(mn - m3) + p01.y * __expf(p01.x - m3);
+        mn = m3;
+        lab = fmaxf(lab, p23.x);
+        const int bi2 = __float_as_int(p45.x);
+        if (p23.y > bv || (p23.y == bv && bi2 < bi)) { bv = p23.y; bi = bi2; }
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, mn, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
+      const float lab2 = __shfl_xor_sync(0xffffffffu, lab, o), bv2 = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int bi2 = __shfl_xor_sync(0xffffffffu, bi, o);
       const float m3 = fmaxf(mn, m2);
       if (m3 != -INFINITY) l = l * __expf(mn - m3) + l2 * __expf(m2 - m3);
       mn = m3;
-      lab = fmaxf(lab, p[2]);
-      const int bi2 = __float_as_int(p[4]);
-      if (p[3] > bv || (p[3] == bv && bi2 < bi)) { bv = p[3]; bi = bi2; }
+      lab = fmaxf(lab, lab2);
+      if (bv2 > bv || (bv2 == bv && bi2 < bi)) { bv = bv2; bi = bi2; }
     }
-    const float lse = mn + logf(l);
-    a.lse[r] = lse;
-    if (a.lab_out) a.lab_out[r] = lab;
-    const float w = a.row_w[r];
-    const int mult = a.row_mult[r];
-    const int correct = (bi == a.labels[r]);
-    if (w > 0.f) acc[0] += (lse - lab);
-    acc[1] += w;
-    acc[2] += (w > 0.f && correct) ? 1.f : 0.f;
-    acc[3] += correct ? (float)mult : 0.f;
-    acc[4] += (float)mult;
+    if (q == 0 && r < n_rows) {
+      const float lse = mn + logf(l);
+      a.lse[r] = lse;
+      if (a.lab_out) a.lab_out[r] = lab;
+      const float w = a.row_w[r];
+      const int mult = a.row_mult[r];
+      const int correct = (bi == a.labels[r]);
+      if (w > 0.f) acc[0] += (lse - lab);
+      acc[1] += w;
+      acc[2] += (w > 0.f && correct) ? 1.f : 0.f;
+      acc[3] += correct ? (float)mult : 0.f;
+      acc[4] += (float)mult;
+    }
   }
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
@@ -556,7 +585,7 @@ cudaError_t launch_ce_count(const CeArgs& a, const float* s_gt, int* beat, cudaS
 }
 
 cudaError_t launch_ce_finalize(const CeArgs& a, cudaStream_t st) {
-  int blocks = (a.M_cap + 255) / 256;
+  int blocks = (a.M_cap + 31) / 32;
   if (blocks > 64) blocks = 64;
   ce_finalize_kernel<<<blocks, 256, 0, st>>>(to_dev(a), a.fin_part, a.ticket);
   return cudaGetLastError();

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     for (int i = 0; i < 8; ++i) { dy[i] = 0.f; xh[i] = 0.f; }
     float rs = 0.f;
     if (ok) {
+#pragma unroll 4
       for (int sp = 0; sp < (HEAD ? nsplit : 1); ++sp) {
         const float* src = d_out + sp * split_stride + (size_t)m * H + c0;
         const float4 d0 = *reinterpret_cast<const float4*>(src);
@@ -236,8 +237,41 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
     if (c < N) part[(size_t)blockIdx.y * N + c] = v;
   }
 }
+// N <= 2048, N % 8 == 0: one thread per 8 consecutive columns (16-byte loads), RL row lanes per block
+__global__ void __launch_bounds__(256) colsum8_bf16_kernel(const bf16* __restrict__ src, int ld, int M, int N,
+                                                           const int* __restrict__ d_M, int d_M_off, float* __restrict__ part) {
+  extern __shared__ float s_cs[];   // [RL][N]
+  if (d_M) M = min(M, *d_M - d_M_off);
+  const int groups = N >> 3, RL = 256 / groups;
+  const int gi = threadIdx.x % groups, rl = threadIdx.x / groups;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rl < RL) {
+    const int rows_per_block = (M + gridDim.y - 1) / gridDim.y;
+    const int r_begin = blockIdx.y * rows_per_block, r_end = min(M, r_begin + rows_per_block);
+#pragma unroll 4
+    for (int r = r_begin + rl; r < r_end; r += RL) {
+      const uint4 u = *reinterpret_cast<const uint4*>(src + (size_t)r * ld + gi * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf162(w[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_cs[rl * N + gi * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < N; c += 256) {
+    float v = 0.f;
+    for (int r = 0; r < RL; ++r) v += s_cs[r * N + c];
+    part[(size_t)blockIdx.y * N + c] = v;
+  }
+}
 cudaError_t launch_colsum_bf16(const bf16* src, int ld, int M, int N, const int* d_M, int d_M_off, float* part,
                                int splits, cudaStream_t st) {
+  if (N % 8 == 0 && N <= 2048 && ld % 8 == 0) {
+    const int groups = N / 8, RL = 256 / groups;
+    colsum8_bf16_kernel<<<dim3(1, splits), 256, (size_t)RL * N * sizeof(float), st>>>(src, ld, M, N, d_M, d_M_off, part);
+    return cudaGetLastError();
+  }
   dim3 grid((N + 63) / 64, splits);
   colsum_bf16_kernel<<<grid, 256, 0, st>>>(src, ld, M, N, d_M, d_M_off, part);
   return cudaGetLastError();

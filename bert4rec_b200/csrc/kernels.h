@@ -131,6 +131,22 @@ size_t enc_fused_table_bytes(int L);
 bool enc_fused_build_tables(const EncFusedLayerHost* layers, int L, int I, const bf16* const* w_ptrs, void* host, void* dev_base);
 cudaError_t launch_enc_fwd_fused(const EncFusedArgs& a, cudaStream_t st);
 
+// fused encoder backward (k_enc_fused_bwd.cu): all layers in one launch, same tile ownership as the fused forward
+struct EncBwdArgs {
+  const int64_t* mask; const bf16* x0;
+  const void* dev_tables;   // the forward's device block (layer table + weight tensor maps)
+  float* dx;                // [T][64] fp32 in/out
+  float* wpart; float* bpart;
+  int B, S, L, I;
+  float out_drop, attn_drop; uint64_t seed; uint32_t step; const long long* d_step;
+  void* dbg;
+};
+bool enc_bwd_fused_supported(int H, int N, int S, int I);
+int enc_fused_ctas(int B, int S);            // CTAs (= partial buffers) of the fused kernels
+size_t enc_bwd_wpart_floats(int I);          // per (layer, CTA): wqkv | wo | w1 | w2
+size_t enc_bwd_bpart_floats(int I);          // per (layer, CTA): the layer's bias / LayerNorm block
+cudaError_t launch_enc_bwd_fused(const EncBwdArgs& a, cudaStream_t st);
+
 // ------------------------------------------------------------------ row kernels (k_rows.cu)
 // LayerNorm backward over rows (+ dropout of the branch gradient):
 //   d_pre = LNbwd(d_out) ; d_branch = drop(d_pre) (bf16) ; partials[cta] = {dgamma[H], dbeta[H], dbranch_colsum[H]}

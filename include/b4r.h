@@ -116,7 +116,8 @@ const uint64_t* b4r_attn_keep_bits(b4r_session* s, int layer, int* words_per_row
 const void* b4r_layer_tensor(b4r_session* s, int layer, const char* name, int* cols, int* is_f32);
 int b4r_launch_count(b4r_session* s);   /* kernels launched through this session so far */
 /* flag 1: tcgen05/TMA generation of the tied-projection kernels (1, default) or the mma.sync generation (0);
- * flag 2: whole-encoder fused tcgen05 forward (1, default where the shape allows) or the layered kernels (0) */
+ * flag 2: whole-encoder fused tcgen05 forward (1, default where the shape allows) or the layered kernels (0);
+ * flag 3: whole-encoder fused tcgen05 backward (needs flag 2) or the layered backward kernels (0) */
 int b4r_session_set_flag(b4r_session* s, int flag, int value);
 const void* b4r_debug_buffer(b4r_session* s);
 const void* b4r_debug_buffer2(b4r_session* s); /* uint64[512]: fused-kernel phase timestamps (ns) when B4R_FUSED_DEBUG is set */  /* kernel-internal timestamps when B4R_CE_DEBUG&8 (development aid) */

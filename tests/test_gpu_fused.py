@@ -100,3 +100,41 @@ def test_fused_is_default_for_beauty_shape_and_counts_one_launch():
     n0 = sess.launch_count()
     sess.encode(cb["input_word_ids"], cb["input_mask"], training=False)
     assert sess.launch_count() - n0 == 1 + 5 * 2
+
+
+BWD_SHAPES = {
+    "s50_two_per_tile": (25, 50, 8, 64, 2),
+    "s20_four_per_tile": (13, 20, 4, 128, 3),
+    "s128_one_per_tile": (3, 128, 20, 64, 1),
+    "s33_slot64_i128": (9, 33, 6, 128, 2),
+}
+
+
+@pytest.mark.parametrize("name", list(BWD_SHAPES))
+@pytest.mark.parametrize("dropout", [0.0, 0.3])
+def test_fused_backward_matches_layered(name, dropout):
+    """Same fused forward, then the one-launch tcgen05 backward against the 12-launches-per-layer backward."""
+    B, S, P, I, L = BWD_SHAPES[name]
+    store = _store(S, I, L, dropout)
+    store.ensure_training_buffers()
+    cb = to_cuda(make_batch(B, S, P, 977, seed=23))
+    sess = store.session(B, S, P)
+    sess.set_flag(2, 1)
+    outs = []
+    for fused_bwd in (0, 1):
+        sess.set_flag(3, fused_bwd)   # raises if unsupported
+        n0 = sess.launch_count()
+        sess.encode(cb["input_word_ids"], cb["input_mask"], training=True, seed=99, step=7)
+        sess.select(cb["masked_lm_positions"], cb["masked_lm_ids"], cb["masked_lm_weights"], mode=0, want_aux=True)
+        sess.transform(); sess.loss(); sess.backward(seed=99, step=7)
+        torch.cuda.synchronize()
+        outs.append(({k: v.clone() for k, v in store.grad_dict().items()}, sess.launch_count() - n0))
+    (ref, n_ref), (got, n_got) = outs
+    assert n_got == n_ref - 12 * L + 1, (n_ref, n_got)
+    gmax = max(float(g.norm()) for g in ref.values())
+    bad = []
+    for k, g in ref.items():
+        d = float((got[k] - g).norm())
+        if not d <= 2e-2 * float(g.norm()) + 1e-6 * gmax:
+            bad.append((k, d, float(g.norm())))
+    assert not bad, (name, bad)
