@@ -44,6 +44,27 @@ __host__ __device__ constexpr uint32_t idesc_bmn(int M, int N) {  // A K-major, 
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+__host__ __device__ constexpr uint32_t idesc_gen(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+// One lane of a converged warp (warp-uniform control flow around the single-thread tcgen05.mma issue)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// Descriptors of any tile / k-slice inside one CTA's shared memory differ from a base descriptor only in the 14-bit
+// start-address field ((byte address) >> 4, never carries out for addresses < 256 KB): desc(base + off) = desc(base) + (off >> 4).
+__device__ __forceinline__ uint64_t desc_at(uint64_t base_desc, uint32_t byte_off) { return base_desc + (uint64_t)(byte_off >> 4); }
+
 __device__ __forceinline__ void tmem_ld_f32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   umma::tmem_ld32(taddr, r);

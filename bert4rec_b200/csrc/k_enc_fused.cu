@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(NTHR, 1) enc_fwd_fused_kernel(EncFusedDev a) {
   };
 
   if (tid == 0) {
-    umma::mbar_init(barA, 1); umma::mbar_init(barB, 1); umma::mbar_init(barM, 1);
+    umma::mbar_init(barA, 1); umma::mbar_init(barB, 1); umma::mbar_init(barM, 4);   // 4 issuer warps commit per batch
     umma::mbar_init(barP, 1); umma::mbar_init(barP + 1, 1);
     umma::fence_barrier_init();
     load_P(0);
@@ -128,6 +128,23 @@ __global__ void __launch_bounds__(NTHR, 1) enc_fwd_fused_kernel(EncFusedDev a) {
   uint32_t parM = 0;
   int red_sel = 0;
   stamp();
+  // base descriptors (smem offset 0); every operand is base + (byte offset >> 4).  MN-major weights: 8 KB between
+  // 64-column blocks; V (one block) shares that base.
+  const uint64_t DK0 = umma::make_desc_k_sw128(umma::smem_addr(smem));
+  const uint64_t DMN0 = desc_mn_sw128(umma::smem_addr(smem), 8192);
+  auto dk = [&](int off) -> uint64_t { return desc_at(DK0, (uint32_t)off); };
+  auto dmn = [&](int off) -> uint64_t { return desc_at(DMN0, (uint32_t)off); };
+  // MMA issue: warps 0..3 (one per scheduler) each issue the accumulation chains `chain(w)` gives them and commit
+  auto issue = [&](auto&& chain) {
+    if (warp < 4) {
+      if (elect_one()) {
+        umma::fence_after_sync();
+        chain(warp);
+        umma::mma_commit(barM);
+      }
+      __syncwarp();
+    }
+  };
 
   // exchange of one float between the 4 column-quarter threads of a row
   auto quad_sum = [&](float v) -> float {
@@ -248,16 +265,14 @@ __global__ void __launch_bounds__(NTHR, 1) enc_fwd_fused_kernel(EncFusedDev a) {
     const float* par = sPar + (l & 1) * PF;
     // ---------------------------------------------------------------- phase 1: QKV = X Wqkv + b
     phase_sync();
-    if (tid == 0) {
-      umma::fence_after_sync();
-      if (l >= 1 && l + 1 < a.L) load_P(l + 1);     // buffer (l+1)&1 was last read by layer l-1
-      umma::mbar_wait(barA, l & 1);
-      const uint32_t xa = umma::smem_addr(sX), wa = umma::smem_addr(sWA);
+    if (tid == 0 && l >= 1 && l + 1 < a.L) load_P(l + 1);     // buffer (l+1)&1 was last read by layer l-1
+    issue([&](int w) {
+      if (w == 0) {
+        umma::mbar_wait(barA, l & 1);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma::mma_bf16_ss(tmem, umma::make_desc_k_sw128(xa + k * 32), desc_mn_sw128(wa + k * 2048, 8192), idesc_bmn(FT, 192), k ? 1u : 0u);
-      umma::mma_commit(barM);
-    }
+        for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(tmem, dk(OFF_X + k * 32), dmn(OFF_WA + k * 2048), idesc_bmn(FT, 192), k ? 1u : 0u);
+      }
+    });
     umma::mbar_wait(barP + (l & 1), (l >> 1) & 1);  // this layer's biases / LN parameters are in shared memory
     wait_mma();
 #pragma unroll 1
@@ -275,17 +290,13 @@ __global__ void __launch_bounds__(NTHR, 1) enc_fwd_fused_kernel(EncFusedDev a) {
     }
     // ---------------------------------------------------------------- phase 2: scores per head + softmax -> P
     phase_sync();
-    if (tid == 0) {
-      umma::fence_after_sync();
-      const uint32_t qa = umma::smem_addr(sQ), ka = umma::smem_addr(sK);
-#pragma unroll
-      for (int hd = 0; hd < FNH; ++hd)
+    issue([&](int w) {
+      if (w < FNH) {
 #pragma unroll
         for (int k = 0; k < FD / 16; ++k)
-          umma::mma_bf16_ss(tmem + hd * 128, umma::make_desc_k_sw128(qa + hd * FD * 2 + k * 32),
-                            umma::make_desc_k_sw128(ka + hd * FD * 2 + k * 32), umma::make_idesc_bf16(FT, 128), k ? 1u : 0u);
-      umma::mma_commit(barM);
-    }
+          umma::mma_bf16_ss(tmem + w * 128, dk(OFF_Q + w * FD * 2 + k * 32), dk(OFF_K + w * FD * 2 + k * 32), umma::make_idesc_bf16(FT, 128), k ? 1u : 0u);
+      }
+    });
     wait_mma();
     float inv_l = 0.f;
     {
@@ -382,16 +393,14 @@ __global__ void __launch_bounds__(NTHR, 1) enc_fwd_fused_kernel(EncFusedDev a) {
     }
     // ---------------------------------------------------------------- phase 3: ctx = P V per head
     phase_sync();
-    if (tid == 0) {
-      umma::fence_after_sync();
-      const uint32_t pa = umma::smem_addr(sP), va = umma::smem_addr(sV);
-      for (int hd = 0; hd < FNH; ++hd)
+    issue([&](int w) {
+      if (w < FNH) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma::mma_bf16_ss(tmem + 256 + hd * 64, umma::make_desc_k_sw128(pa + hd * 2 * TILE_B + (kk >> 2) * TILE_B + (kk & 3) * 32),
-                            desc_mn_sw128(va + kk * 2048, 8192), idesc_bmn(FT, 64), kk ? 1u : 0u);
-      umma::mma_commit(barM);
-    }
+          umma::mma_bf16_ss(tmem + 256 + w * 64, dk(OFF_P + w * 2 * TILE_B + (kk >> 2) * TILE_B + (kk & 3) * 32), dmn(OFF_V + kk * 2048),
+                            idesc_bmn(FT, 64), kk ? 1u : 0u);
+      }
+    });
     wait_mma();
     {
       const int hd = part >> 1;
@@ -407,29 +416,25 @@ __global__ void __launch_bounds__(NTHR, 1) enc_fwd_fused_kernel(EncFusedDev a) {
     }
     // ---------------------------------------------------------------- phase 4: a = x + drop(ctx Wo + bo) ; y = LN1(a)
     phase_sync();
-    if (tid == 0) {
-      umma::fence_after_sync();
-      const uint32_t ca = umma::smem_addr(sCtx), wo = umma::smem_addr(sWA + 3 * 8192);
+    issue([&](int w) {
+      if (w == 0) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma::mma_bf16_ss(tmem + 384, umma::make_desc_k_sw128(ca + k * 32), desc_mn_sw128(wo + k * 2048, 8192), idesc_bmn(FT, 64), k ? 1u : 0u);
-      umma::mma_commit(barM);
-    }
+        for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(tmem + 384, dk(OFF_Q + k * 32), dmn(OFF_WA + 3 * 8192 + k * 2048), idesc_bmn(FT, 64), k ? 1u : 0u);
+      }
+    });
     wait_mma();
     if (tid == 0 && l + 1 < a.L) load_A(l + 1);   // Wqkv / Wo of the next layer stream in behind the epilogue
     res_ln_epilogue(384, par + PB_BO, site_id(SITE_ATTN_OUT, l), sX, par + PB_G1, par + PB_BE1, Ly.a_pre, sY, Ly.y, false, Ly.mean1, Ly.rstd1);
     // ---------------------------------------------------------------- phase 5: h = gelu(y W1 + b1)
     phase_sync();
-    if (tid == 0) {
-      umma::fence_after_sync();
-      umma::mbar_wait(barB, l & 1);
-      const uint32_t ya = umma::smem_addr(sY), w1 = umma::smem_addr(sWB);
-      const uint32_t id1 = idesc_bmn(FT, I);
+    issue([&](int w) {
+      if (w == 0) {
+        umma::mbar_wait(barB, l & 1);
+        const uint32_t id1 = idesc_bmn(FT, I);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma::mma_bf16_ss(tmem, umma::make_desc_k_sw128(ya + k * 32), desc_mn_sw128(w1 + k * 2048, 8192), id1, k ? 1u : 0u);
-      umma::mma_commit(barM);
-    }
+        for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(tmem, dk(OFF_K + k * 32), dmn(OFF_WB + k * 2048), id1, k ? 1u : 0u);
+      }
+    });
     wait_mma();
 #pragma unroll 1
     for (int i = 0; i < I / 64; ++i) {
@@ -449,14 +454,12 @@ __global__ void __launch_bounds__(NTHR, 1) enc_fwd_fused_kernel(EncFusedDev a) {
     }
     // ---------------------------------------------------------------- phase 6: o = y + drop(h W2 + b2) ; out = LN2(o)
     phase_sync();
-    if (tid == 0) {
-      umma::fence_after_sync();
-      const uint32_t ha = umma::smem_addr(sHh), w2 = umma::smem_addr(sWB + I * 128);
-      for (int kk = 0; kk < I / 16; ++kk)
-        umma::mma_bf16_ss(tmem + 448, umma::make_desc_k_sw128(ha + (kk >> 2) * TILE_B + (kk & 3) * 32), desc_mn_sw128(w2 + kk * 2048, 8192),
-                          idesc_bmn(FT, 64), kk ? 1u : 0u);
-      umma::mma_commit(barM);
-    }
+    issue([&](int w) {
+      if (w == 0) {
+        for (int kk = 0; kk < I / 16; ++kk)
+          umma::mma_bf16_ss(tmem + 448, dk(OFF_P + (kk >> 2) * TILE_B + (kk & 3) * 32), dmn(OFF_WB + I * 128 + kk * 2048), idesc_bmn(FT, 64), kk ? 1u : 0u);
+      }
+    });
     wait_mma();
     if (tid == 0 && l + 1 < a.L) load_B(l + 1);
     res_ln_epilogue(448, par + PB_B1 + I, site_id(SITE_FFN_OUT, l), sY, par + PB_B1 + I + 64, par + PB_B1 + I + 128, Ly.o_pre, sX, Ly.out, true,

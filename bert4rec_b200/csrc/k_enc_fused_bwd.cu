@@ -38,11 +38,6 @@ constexpr int T_H = 0, T_DB2 = 2, T_DH = 3, T_Y = 5, T_DB1 = 6, T_C = 7, T_W2 = 
 constexpr int T_Q = 0, T_K = 1, T_V = 2, T_DC = 3, T_PD = 4, T_DS = 8;       // P_drop: 4..7, dS: 8..11 (head-major, 2 tiles each)
 constexpr int T_DQ = 4, T_XIN = 7, T_WQKV = 8;                                // dQ|dK|dV: 4,5,6
 
-__host__ __device__ constexpr uint32_t idesc_gen(int M, int N, int a_mn, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
-}
-
 // Column sums over the 32 rows of a warp of a [32 rows x 16 cols] register block (recursive halving, 16 shuffles).
 // On return every lane with (lane & 1) == 0 holds in `out` the sum of column `col`.
 __device__ __forceinline__ void warp_colsum16(const float (&v)[16], int lane, float& out, int& col) {
@@ -155,7 +150,7 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
   };
 
   if (tid == 0) {
-    umma::mbar_init(barWa, 1); umma::mbar_init(barWq, 1); umma::mbar_init(barM, 1);
+    umma::mbar_init(barWa, 1); umma::mbar_init(barWq, 1); umma::mbar_init(barM, 4);   // 4 issuer warps commit per batch
     umma::mbar_init(barP, 1); umma::mbar_init(barP + 1, 1);
     umma::fence_barrier_init();
     load_P(a.L - 1);
@@ -172,6 +167,22 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
   uint32_t parM = 0;
   int red_sel = 0;
   stamp();
+  // base descriptors of arena tile 0; every operand is DK / DMN + (byte offset >> 4)
+  const uint64_t DK0 = umma::make_desc_k_sw128(umma::smem_addr(smem));
+  const uint64_t DMN0 = desc_mn_sw128(umma::smem_addr(smem), TILE_B);
+  auto dk = [&](int tile_i, int off) -> uint64_t { return desc_at(DK0, (uint32_t)(tile_i * TILE_B + off)); };
+  auto dmn = [&](int tile_i, int off) -> uint64_t { return desc_at(DMN0, (uint32_t)(tile_i * TILE_B + off)); };
+  // MMA issue: warps 0..3 (one per scheduler) each issue the accumulation chains `chain(w)` gives them and commit
+  auto issue = [&](auto&& chain) {
+    if (warp < 4) {
+      if (elect_one()) {
+        umma::fence_after_sync();
+        chain(warp);
+        umma::mma_commit(barM);
+      }
+      __syncwarp();
+    }
+  };
 
   // sums of two per-thread values over the 4 column-quarter threads of a row (one barrier)
   auto quad_sum2 = [&](float& x, float& y) {
@@ -221,21 +232,11 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
     }
   };
   // LayerNorm backward of one row (four 16-column quarters): dy -> d(pre), + column sums for gamma / beta
-  auto ln_bwd = [&](float (&dy)[16], const bf16* pre_g, const float* mean_g, const float* rstd_g, const float* gamma, int off_g, int off_b) {
+  auto ln_bwd = [&](float (&dy)[16], const uint32_t (&pre_pk)[8], float mu, float rs, const float* gamma, int off_g, int off_b) {
     float xh[16];
-    float rs = 0.f;
-    if (valid) {
-      uint32_t pk[8];
-      ld_global16(pre_g + (size_t)t * FH + cq, pk);
-      unpack16(pk, xh);
-      const float mu = mean_g[t];
-      rs = rstd_g[t];
+    unpack16(pre_pk, xh);   // padding rows were prefetched as zeros with rs = 0
 #pragma unroll
-      for (int i = 0; i < 16; ++i) xh[i] = (xh[i] - mu) * rs;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) xh[i] = 0.f;
-    }
+    for (int i = 0; i < 16; ++i) xh[i] = (xh[i] - mu) * rs;
     float tmp[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) tmp[i] = dy[i] * xh[i];
@@ -255,14 +256,14 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
     for (int i = 0; i < 16; ++i) dy[i] = rs * (dy[i] - s1 - xh[i] * s2);
   };
   // one row x 16 columns of a saved [T][ld] bf16 activation -> two 16-byte chunks of a tile (zeros for padding rows)
-  auto load_act = [&](const bf16* src, int ld, int col, unsigned char* dst_tile, int chunk) {
-    uint32_t pk[8];
+  // prefetch of one row x 16 columns of a saved [T][ld] bf16 activation (zeros for padding rows); issued BEFORE the wait
+  // on the tensor-core batch so that the L2 latency hides behind it
+  auto pf = [&](const bf16* src, int ld, int col, uint32_t (&pk)[8]) {
     if (valid) ld_global16(src + (size_t)t * ld + col, pk);
     else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) pk[i] = 0u;
     }
-    st_tile<2>(dst_tile, row, chunk, pk);
   };
 
   // gradient with respect to the output of the layer being processed: this thread's row x 16 columns
@@ -278,6 +279,17 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
   }
   const float scale = rsqrtf((float)FD);
   const int hd = part >> 1, kh = part & 1;
+  // prefetch registers (saved activations of the NEXT epilogue phase)
+  uint32_t pfA[8], pfB[8], pfC[8];
+  float pf_mu = 0.f, pf_rs = 0.f;
+  auto prefetch_e0 = [&](const LayerDev& Ln) {   // o_pre row chunk, LN2 statistics, h chunk(s)
+    pf(Ln.o_pre, FH, cq, pfA);
+    pf(Ln.h, I, part * IC * 16, pfB);
+    if (IC > 1) pf(Ln.h, I, (part * IC + 1) * 16, pfC);
+    pf_mu = valid ? Ln.mean2[t] : 0.f;
+    pf_rs = valid ? Ln.rstd2[t] : 0.f;
+  };
+  prefetch_e0(a.layers[a.L - 1]);
 
   for (int l = a.L - 1, it = 0; l >= 0; --l, ++it) {
     const LayerDev& Ly = a.layers[l];
@@ -288,7 +300,7 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
     // ================================================================ E0: LN2 backward -> d_branch2 ; h
     float dres[16];
     {
-      ln_bwd(dO, Ly.o_pre, Ly.mean2, Ly.rstd2, par + OFF_G2, OFF_G2, OFF_BE2);
+      ln_bwd(dO, pfA, pf_mu, pf_rs, par + OFF_G2, OFF_G2, OFF_BE2);
 #pragma unroll
       for (int i = 0; i < 16; ++i) dres[i] = dO[i];
       drop16(dO, site_id(SITE_FFN_OUT, l));
@@ -298,24 +310,26 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
       st_tile<2>(tile(T_DB2), row, part * 2, pk);
       for (int i = 0; i < IC; ++i) {
         const int j = part * IC + i;
-        load_act(Ly.h, I, j * 16, tile(T_H + (j >> 2)), (j & 3) * 2);
+        if (i == 0) st_tile<2>(tile(T_H + (j >> 2)), row, (j & 3) * 2, pfB);
+        else st_tile<2>(tile(T_H + (j >> 2)), row, (j & 3) * 2, pfC);
       }
     }
     // ================================================================ M1: dW2 = h^T db2 | dh = db2 W2^T
     phase_sync();
-    if (tid == 0) {
-      umma::fence_after_sync();
-      umma::mbar_wait(barWa, it & 1);
-      const uint32_t th = umma::smem_addr(tile(T_H)), tb = umma::smem_addr(tile(T_DB2)), w2 = umma::smem_addr(tile(T_W2));
+    issue([&](int w) {
+      if (w == 0) {
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk)
-        umma::mma_bf16_ss(tmem, desc_mn_sw128(th + kk * 2048, TILE_B), desc_mn_sw128(tb + kk * 2048, TILE_B), idesc_gen(128, 64, 1, 1), kk ? 1u : 0u);
-      const uint32_t id = idesc_gen(128, I, 0, 0);
+        for (int kk = 0; kk < 8; ++kk) umma::mma_bf16_ss(tmem, dmn(T_H, kk * 2048), dmn(T_DB2, kk * 2048), idesc_gen(128, 64, 1, 1), kk ? 1u : 0u);
+      } else if (w == 1) {
+        umma::mbar_wait(barWa, it & 1);
+        const uint32_t id = idesc_gen(128, I, 0, 0);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma::mma_bf16_ss(tmem + 64, umma::make_desc_k_sw128(tb + k * 32), umma::make_desc_k_sw128(w2 + k * 32), id, k ? 1u : 0u);
-      umma::mma_commit(barM);
-    }
+        for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(tmem + 64, dk(T_DB2, k * 32), dk(T_W2, k * 32), id, k ? 1u : 0u);
+      }
+    });
+    pf(Ly.h_pre, I, part * IC * 16, pfB);
+    if (IC > 1) pf(Ly.h_pre, I, (part * IC + 1) * 16, pfC);
+    pf(Ly.y, FH, cq, pfA);
     wait_mma();
     // ================================================================ E1: drain dW2 ; dh * gelu' -> dh_pre ; y
     {
@@ -329,9 +343,7 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
         float v[16], hp[16];
         tmem_ld_f16(tlane + 64 + j * 16, v);
         if (valid) {
-          uint32_t pk[8];
-          ld_global16(Ly.h_pre + (size_t)t * I + j * 16, pk);
-          unpack16(pk, hp);
+          if (i == 0) unpack16(pfB, hp); else unpack16(pfC, hp);
 #pragma unroll
           for (int k = 0; k < 16; ++k) v[k] *= gelu_erf_grad(hp[k]);
         } else {
@@ -347,22 +359,25 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
         }
         st_tile<2>(tile(T_DH + (j >> 2)), row, (j & 3) * 2, pk);
       }
-      load_act(Ly.y, FH, cq, tile(T_Y), part * 2);
+      st_tile<2>(tile(T_Y), row, part * 2, pfA);
     }
     // ================================================================ M2: dW1 = y^T dh_pre | dy = dh_pre W1^T
     phase_sync();
-    if (tid == 0) {
-      umma::fence_after_sync();
-      const uint32_t ty = umma::smem_addr(tile(T_Y)), td = umma::smem_addr(tile(T_DH)), w1 = umma::smem_addr(tile(T_W1));
-      const uint32_t id = idesc_gen(128, I, 1, 1);
+    issue([&](int w) {
+      if (w == 0) {
+        const uint32_t id = idesc_gen(128, I, 1, 1);
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk)
-        umma::mma_bf16_ss(tmem, desc_mn_sw128(ty + kk * 2048, TILE_B), desc_mn_sw128(td + kk * 2048, TILE_B), id, kk ? 1u : 0u);
-      for (int kk = 0; kk < I / 16; ++kk)
-        umma::mma_bf16_ss(tmem + 256, umma::make_desc_k_sw128(td + (kk >> 2) * TILE_B + (kk & 3) * 32),
-                          umma::make_desc_k_sw128(w1 + (kk >> 2) * 8192 + (kk & 3) * 32), idesc_gen(128, 64, 0, 0), kk ? 1u : 0u);
-      umma::mma_commit(barM);
-    }
+        for (int kk = 0; kk < 8; ++kk) umma::mma_bf16_ss(tmem, dmn(T_Y, kk * 2048), dmn(T_DH, kk * 2048), id, kk ? 1u : 0u);
+      } else if (w == 1) {
+        for (int kk = 0; kk < I / 16; ++kk)
+          umma::mma_bf16_ss(tmem + 256, dk(T_DH, (kk >> 2) * TILE_B + (kk & 3) * 32), dk(T_W1, (kk >> 2) * 8192 + (kk & 3) * 32),
+                            idesc_gen(128, 64, 0, 0), kk ? 1u : 0u);
+      }
+    });
+    pf(Ly.a_pre, FH, cq, pfA);
+    pf(Ly.ctx, FH, cq, pfB);
+    pf_mu = valid ? Ly.mean1[t] : 0.f;
+    pf_rs = valid ? Ly.rstd1[t] : 0.f;
     wait_mma();
     // ================================================================ E2: drain dW1 ; LN1 backward -> d_branch1 ; ctx
     {
@@ -378,7 +393,7 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
       tmem_ld_f16(tlane + 256 + cq, v);
 #pragma unroll
       for (int i = 0; i < 16; ++i) dO[i] = valid ? v[i] + dres[i] : 0.f;
-      ln_bwd(dO, Ly.a_pre, Ly.mean1, Ly.rstd1, par + PB_G1, PB_G1, PB_BE1);
+      ln_bwd(dO, pfA, pf_mu, pf_rs, par + PB_G1, PB_G1, PB_BE1);
 #pragma unroll
       for (int i = 0; i < 16; ++i) dres[i] = dO[i];
       drop16(dO, site_id(SITE_ATTN_OUT, l));
@@ -386,21 +401,22 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
       round_n<16>(dO, pk);
       colsum(dO, PB_BO);
       st_tile<2>(tile(T_DB1), row, part * 2, pk);
-      load_act(Ly.ctx, FH, cq, tile(T_C), part * 2);
+      st_tile<2>(tile(T_C), row, part * 2, pfB);
     }
     // ================================================================ M3: dWo = ctx^T db1 | dctx = db1 Wo^T
     phase_sync();
-    if (tid == 0) {
-      umma::fence_after_sync();
-      const uint32_t tc = umma::smem_addr(tile(T_C)), tb = umma::smem_addr(tile(T_DB1)), wo = umma::smem_addr(tile(T_WO));
+    issue([&](int w) {
+      if (w == 0) {
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk)
-        umma::mma_bf16_ss(tmem, desc_mn_sw128(tc + kk * 2048, TILE_B), desc_mn_sw128(tb + kk * 2048, TILE_B), idesc_gen(128, 64, 1, 1), kk ? 1u : 0u);
+        for (int kk = 0; kk < 8; ++kk) umma::mma_bf16_ss(tmem, dmn(T_C, kk * 2048), dmn(T_DB1, kk * 2048), idesc_gen(128, 64, 1, 1), kk ? 1u : 0u);
+      } else if (w == 1) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma::mma_bf16_ss(tmem + 64, umma::make_desc_k_sw128(tb + k * 32), umma::make_desc_k_sw128(wo + k * 32), idesc_gen(128, 64, 0, 0), k ? 1u : 0u);
-      umma::mma_commit(barM);
-    }
+        for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(tmem + 64, dk(T_DB1, k * 32), dk(T_WO, k * 32), idesc_gen(128, 64, 0, 0), k ? 1u : 0u);
+      }
+    });
+    pf(Ly.qkv, 192, cq, pfA);
+    pf(Ly.qkv, 192, 64 + cq, pfB);
+    pf(Ly.qkv, 192, 128 + cq, pfC);
     wait_mma();
     // ================================================================ E3: drain dWo ; dctx, delta ; Q K V
     float delta = 0.f;
@@ -423,48 +439,48 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
       }
       delta = dl + pair_other(dl);     // the pair (part, part ^ 1) covers the 32 columns of head part >> 1
       st_tile<2>(tile(T_DC), row, part * 2, pk);
-      load_act(Ly.qkv, 192, cq, tile(T_Q), part * 2);
-      load_act(Ly.qkv, 192, 64 + cq, tile(T_K), part * 2);
-      load_act(Ly.qkv, 192, 128 + cq, tile(T_V), part * 2);
+      st_tile<2>(tile(T_Q), row, part * 2, pfA);
+      st_tile<2>(tile(T_K), row, part * 2, pfB);
+      st_tile<2>(tile(T_V), row, part * 2, pfC);
     }
     // ================================================================ M4: S = Q K^T | dP = dctx V^T   (both heads)
     phase_sync();
-    if (tid == 0) {
-      umma::fence_after_sync();
-      const uint32_t tq = umma::smem_addr(tile(T_Q)), tk = umma::smem_addr(tile(T_K)), tv = umma::smem_addr(tile(T_V)),
-                     tdc = umma::smem_addr(tile(T_DC));
-#pragma unroll
-      for (int h = 0; h < FNH; ++h) {
+    issue([&](int w) {   // chain w: head w >> 1 ; even = scores, odd = dP
+      const int h = w >> 1;
+      if (!(w & 1)) {
 #pragma unroll
         for (int k = 0; k < FD / 16; ++k)
-          umma::mma_bf16_ss(tmem + h * 128, umma::make_desc_k_sw128(tq + h * FD * 2 + k * 32), umma::make_desc_k_sw128(tk + h * FD * 2 + k * 32),
-                            idesc_gen(128, 128, 0, 0), k ? 1u : 0u);
+          umma::mma_bf16_ss(tmem + h * 128, dk(T_Q, h * FD * 2 + k * 32), dk(T_K, h * FD * 2 + k * 32), idesc_gen(128, 128, 0, 0), k ? 1u : 0u);
+      } else {
 #pragma unroll
         for (int k = 0; k < FD / 16; ++k)
-          umma::mma_bf16_ss(tmem + 256 + h * 128, umma::make_desc_k_sw128(tdc + h * FD * 2 + k * 32),
-                            umma::make_desc_k_sw128(tv + h * FD * 2 + k * 32), idesc_gen(128, 128, 0, 0), k ? 1u : 0u);
+          umma::mma_bf16_ss(tmem + 256 + h * 128, dk(T_DC, h * FD * 2 + k * 32), dk(T_V, h * FD * 2 + k * 32), idesc_gen(128, 128, 0, 0), k ? 1u : 0u);
       }
-      umma::mma_commit(barM);
+    });
+    const int CPS = SLOT >> 5, colbase = g * SLOT;
+    const bool drop = a.thr_attn > 0;
+    const int bn = seq * FNH + hd, W = (S + 63) >> 6;
+    const float lse = valid ? Ly.lse[(size_t)bn * S + pos] : 0.f;
+    uint32_t kbits[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int cc = kh + 2 * c;
+      if ((cc / CPS) == g && drop && valid) {
+        const int ci = cc % CPS;
+        kbits[c] = reinterpret_cast<const uint32_t*>(Ly.keep)[(((size_t)bn * S + pos) * W + (ci >> 1)) * 2 + (ci & 1)];
+      }
     }
     wait_mma();
     // ================================================================ E4: P, dS (recomputed from lse) -> bf16 tiles
     {
-      const int CPS = SLOT >> 5, colbase = g * SLOT;
-      const bool drop = a.thr_attn > 0;
-      const int bn = seq * FNH + hd, W = (S + 63) >> 6;
-      const float lse = valid ? Ly.lse[(size_t)bn * S + pos] : 0.f;
       unsigned char* tpd = tile(T_PD + hd * 2);
       unsigned char* tds = tile(T_DS + hd * 2);
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int cc = kh + 2 * c;
         const bool dat = (cc / CPS) == g;
         const int jl0 = (cc % CPS) * 32;
-        uint32_t bits = 0xFFFFFFFFu;
-        if (dat && drop && valid) {
-          const int ci = jl0 >> 5;
-          bits = reinterpret_cast<const uint32_t*>(Ly.keep)[(((size_t)bn * S + pos) * W + (ci >> 1)) * 2 + (ci & 1)];
-        }
+        const uint32_t bits = kbits[c];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {       // two 16-column halves of the 32-key chunk
           uint32_t pkp[8], pkd[8];
@@ -499,25 +515,23 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
     }
     // ================================================================ M5: dV = Pd^T dctx | dK = dS^T Q | dQ = dS K
     phase_sync();
-    if (tid == 0) {
-      umma::fence_after_sync();
-      const uint32_t tq = umma::smem_addr(tile(T_Q)), tk = umma::smem_addr(tile(T_K)), tdc = umma::smem_addr(tile(T_DC));
-      for (int h = 0; h < FNH; ++h) {
-        const uint32_t tp = umma::smem_addr(tile(T_PD + h * 2)), ts = umma::smem_addr(tile(T_DS + h * 2));
-        const uint32_t base = tmem + h * 192;
+    issue([&](int w) {   // six chains over four issuers: w0: dV0 dK0 ; w1: dQ0 ; w2: dV1 dK1 ; w3: dQ1
+      const int h = w >> 1;
+      const uint32_t base = tmem + h * 192;
+      if (!(w & 1)) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma::mma_bf16_ss(base, desc_mn_sw128(tp + kk * 2048, TILE_B), desc_mn_sw128(tdc + kk * 2048, TILE_B), idesc_gen(128, 64, 1, 1), kk ? 1u : 0u);
+          umma::mma_bf16_ss(base, dmn(T_PD + h * 2, kk * 2048), dmn(T_DC, kk * 2048), idesc_gen(128, 64, 1, 1), kk ? 1u : 0u);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma::mma_bf16_ss(base + 64, desc_mn_sw128(ts + kk * 2048, TILE_B), desc_mn_sw128(tq + kk * 2048, TILE_B), idesc_gen(128, 64, 1, 1), kk ? 1u : 0u);
+          umma::mma_bf16_ss(base + 64, dmn(T_DS + h * 2, kk * 2048), dmn(T_Q, kk * 2048), idesc_gen(128, 64, 1, 1), kk ? 1u : 0u);
+      } else {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma::mma_bf16_ss(base + 128, umma::make_desc_k_sw128(ts + (kk >> 2) * TILE_B + (kk & 3) * 32), desc_mn_sw128(tk + kk * 2048, TILE_B),
-                            idesc_gen(128, 64, 0, 1), kk ? 1u : 0u);
+          umma::mma_bf16_ss(base + 128, dk(T_DS + h * 2, (kk >> 2) * TILE_B + (kk & 3) * 32), dmn(T_K, kk * 2048), idesc_gen(128, 64, 0, 1), kk ? 1u : 0u);
       }
-      umma::mma_commit(barM);
-    }
+    });
+    pf(l == 0 ? a.x0 : a.layers[l - 1].out, FH, cq, pfA);
     wait_mma();
     if (tid == 0) load_Wq(l);     // dS tiles are dead: Wqkv streams into T8.. behind the epilogue
     // ================================================================ E5: dQ | dK | dV tiles ; x_in
@@ -543,23 +557,23 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
       round_n<16>(v, pk);
       colsum(v, PB_BQKV + 128);
       st_tile<2>(tile(T_DQ + 2), row, part * 2, pk);
-      load_act(l == 0 ? a.x0 : a.layers[l - 1].out, FH, cq, tile(T_XIN), part * 2);
+      st_tile<2>(tile(T_XIN), row, part * 2, pfA);
     }
     // ================================================================ M6: dWqkv = x^T dqkv | dx = dqkv Wqkv^T
     phase_sync();
-    if (tid == 0) {
-      umma::fence_after_sync();
-      umma::mbar_wait(barWq, it & 1);
-      const uint32_t tx = umma::smem_addr(tile(T_XIN)), tdq = umma::smem_addr(tile(T_DQ)), wq = umma::smem_addr(tile(T_WQKV));
+    issue([&](int w) {
+      if (w == 0) {
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk)
-        umma::mma_bf16_ss(tmem, desc_mn_sw128(tx + kk * 2048, TILE_B), desc_mn_sw128(tdq + kk * 2048, TILE_B), idesc_gen(128, 192, 1, 1), kk ? 1u : 0u);
+        for (int kk = 0; kk < 8; ++kk) umma::mma_bf16_ss(tmem, dmn(T_XIN, kk * 2048), dmn(T_DQ, kk * 2048), idesc_gen(128, 192, 1, 1), kk ? 1u : 0u);
+      } else if (w == 1) {
+        umma::mbar_wait(barWq, it & 1);
 #pragma unroll
-      for (int kk = 0; kk < 12; ++kk)
-        umma::mma_bf16_ss(tmem + 256, umma::make_desc_k_sw128(tdq + (kk >> 2) * TILE_B + (kk & 3) * 32),
-                          umma::make_desc_k_sw128(wq + (kk >> 2) * 8192 + (kk & 3) * 32), idesc_gen(128, 64, 0, 0), kk ? 1u : 0u);
-      umma::mma_commit(barM);
-    }
+        for (int kk = 0; kk < 12; ++kk)
+          umma::mma_bf16_ss(tmem + 256, dk(T_DQ, (kk >> 2) * TILE_B + (kk & 3) * 32), dk(T_WQKV, (kk >> 2) * 8192 + (kk & 3) * 32),
+                            idesc_gen(128, 64, 0, 0), kk ? 1u : 0u);
+      }
+    });
+    if (l > 0) prefetch_e0(a.layers[l - 1]);
     wait_mma();
     if (tid == 0 && l > 0) load_Wa(l - 1);   // next layer's W2 / W1 / Wo
     // ================================================================ E6: drain dWqkv ; d(residual) for the next layer

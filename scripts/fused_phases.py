@@ -15,8 +15,14 @@ store.init_weights(0)
 store.ensure_training_buffers()
 b = {k: v.cuda() for k, v in bench.synth_batches(w, 1, seed=0)[0].items()}
 sess = store.session(w["batch"], w["seq_len"], w["max_pred"])
+which = sys.argv[3] if len(sys.argv) > 3 else "fwd"
 for it in range(3):
     sess.encode(b["input_word_ids"], b["input_mask"], training=train, seed=1, step=it)
+    if which == "bwd":
+        torch.cuda.synchronize()
+        sess._view(store.lib.b4r_debug_buffer2(sess.h), (512,), torch.int64).zero_()
+        sess.select(b["masked_lm_positions"], b["masked_lm_ids"], b["masked_lm_weights"], mode=0, want_aux=True)
+        sess.transform(); sess.loss(); sess.backward(seed=1, step=it)
 torch.cuda.synchronize()
 p = store.lib.b4r_debug_buffer2(sess.h)
 ts = sess._view(p, (512,), torch.int64).cpu().tolist()
