@@ -200,7 +200,7 @@ struct b4r_session {
   CeUmmaMaps umaps;
   bool use_fused = false;   // whole-encoder forward in one tcgen05 launch (k_enc_fused.cu)
   bool use_fused_bwd = false, fused_bwd_ok = false;   // ... and the backward (k_enc_fused_bwd.cu)
-  float *enc_wpart = nullptr, *enc_bpart = nullptr;
+  float *enc_wpart = nullptr, *enc_bpart = nullptr, *enc_dpos = nullptr, *enc_embln = nullptr;
   ReduceJob* d_jobs_f = nullptr; int n_jobs_f = 0, jobs_f_blocks = 0;   // reduce jobs when the fused backward produced the partials
   void* d_enc_tables = nullptr;
   unsigned long long* dbg_buf = nullptr;
@@ -373,9 +373,20 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
   s->emb_bsplits = embed_bwd_bsplits(B);
   s->p_dpos = b.take<float>((size_t)s->emb_bsplits * S * H);
   s->p_embln = b.take<float>((size_t)s->emb_bsplits * S * 2 * H);
+  in_layers = true;   // the fused backward reduces its own embedding partials (below)
   job(s->p_dpos, off("position_embedding"), s->emb_bsplits, S * H, (long long)S * H);
   job(s->p_embln, off("emb_ln/gamma"), s->emb_bsplits * S, H, 2 * H);
   job(s->p_embln + H, off("emb_ln/beta"), s->emb_bsplits * S, H, 2 * H);
+  in_layers = false;
+  if (s->fused_bwd_ok) {
+    const int nc = enc_fused_ctas(B, S);
+    s->enc_dpos = b.take<float>((size_t)nc * S * H);
+    s->enc_embln = b.take<float>((size_t)nc * 128);
+    if (jobs_f && s->grads) {
+      jobs_f->push_back(ReduceJob{s->enc_dpos, s->grads + off("position_embedding"), nc, S * H, (long long)S * H, 0});
+      jobs_f->push_back(ReduceJob{s->enc_embln, s->grads + off("emb_ln/gamma"), nc, 2 * H, (long long)2 * H, 0});
+    }
+  }
   s->d_jobs = b.take<ReduceJob>(256);
   s->d_jobs_f = b.take<ReduceJob>(256);
   s->d_vb_jobs = b.take<ReduceJob>(2);
@@ -662,7 +673,8 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
   {
     WgradArgs w{};
     w.X = xL; w.ldx = H; w.x_rows = s->rows; w.dY = s->d_tpre; w.ldy = H; w.M = H; w.N = H; w.T = Mcap;
-    w.d_T = s->counts + 1; w.splits = s->s_wt; w.out = s->p_wt; w.split_stride = (size_t)H * H; w.ld_out = H;
+    w.d_T = s->counts;   // n_valid rows only: aux rows carry no gradient
+    w.splits = s->s_wt; w.out = s->p_wt; w.split_stride = (size_t)H * H; w.ld_out = H;
     KL("wgrad:head_wt", launch_wgrad(w, st));
     GemmArgs g{};
     g.A = s->d_tpre; g.lda = H; g.B = W + s->lay.find("head/wt"); g.ldb = H; g.b_trans = false; g.M = Mcap; g.N = H; g.K = H;
@@ -678,6 +690,8 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
     f.B = s->B; f.S = s->S; f.L = s->cfg.num_layers; f.I = I;
     f.out_drop = od; f.attn_drop = s->cfg.attention_dropout; f.seed = seed; f.step = step; f.d_step = d_step;
     f.dbg = getenv("B4R_FUSED_DEBUG") ? (void*)s->dbg_buf : nullptr;
+    f.ids = s->ids; f.table = W + oE; f.pos = W + s->lay.find("position_embedding"); f.emb_g = P + s->lay.find("emb_ln/gamma");
+    f.grad_table = G + oE; f.dpos_part = s->enc_dpos; f.embln_part = s->enc_embln; f.V = V;
     KL("enc_bwd_fused", launch_enc_bwd_fused(f, st));
   }
   for (int l = s->cfg.num_layers - 1; l >= 0 && !fbwd; --l) {
@@ -743,7 +757,7 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
       KL("gemm:qkv_dgrad", launch_gemm(EPI_F32_RES, g, st));
     }
   }
-  KL("embed_bwd", launch_embed_bwd(s->ids, W + oE, W + s->lay.find("position_embedding"), P + s->lay.find("emb_ln/gamma"), s->dxa,
+  if (!fbwd) KL("embed_bwd", launch_embed_bwd(s->ids, W + oE, W + s->lay.find("position_embedding"), P + s->lay.find("emb_ln/gamma"), s->dxa,
                       G + oE, s->p_dpos, s->p_embln, s->B, s->S, H, V, od, seed, step, d_step, s->emb_bsplits, st));
   if (fbwd) KL("grad_reduce:all", launch_grad_reduce(s->d_jobs_f, s->n_jobs_f, s->jobs_f_blocks, st));
   else KL("grad_reduce:all", launch_grad_reduce(s->d_jobs, s->n_jobs, s->jobs_max_len, st));

@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(320, 2) ce_bwd_umma_kernel(const __grid_consta
   uint64_t* acc_full = dl_empty + 1;  // all MMA2 done
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
 
-  const int n_rows = min(a.M_cap, a.d_counts[1]);
+  // rows with a gradient = the valid masked slots; the zero-weight aux rows behind them (metric parity only) are skipped
+  const int n_rows = min(a.M_cap, a.d_counts[0]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // ---- work assignment
   int r0, x_lo, x_hi, split;  // R tile start row, streamed tile range [x_lo, x_hi), partial slot

@@ -87,6 +87,12 @@ struct EncBwdDev {
   float* dx;                 // [T][64] fp32: in = d(loss)/d(last layer output), out = d(loss)/d(embedding output)
   float* wpart;              // [L][nCTA][WP] weight-gradient partials: wqkv | wo | w1 | w2
   float* bpart;              // [L][nCTA][PF] bias / LayerNorm gradient partials, laid out like the parameter block
+  // embedding stage backward (fused tail): LN backward + dropout', scatter-add into the item-table gradient
+  const int64_t* ids; const bf16* table; const bf16* pos; const float* emb_g;
+  float* grad_table;         // [V][64] fp32 (already holds the tied-projection part)
+  float* dpos_part;          // [nCTA][S][64]
+  float* embln_part;         // [nCTA][128] gamma | beta
+  int V;
   int B, S, L, slot, I;
   uint32_t thr_out, thr_attn; float inv_keep_out, inv_keep_attn;
   unsigned long long seed; uint32_t step; const long long* d_step;
@@ -601,7 +607,109 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
     }
     if (tid == 0 && l >= 2) load_P(l - 2);   // buffer l & 1 is free again (all threads are past their last read of it)
   }
-  if (valid) st_f32x16(a.dx + (size_t)t * FH + cq, dO);
+  // ================================================================== embedding stage backward (k_embed.cu semantics)
+  {
+    // dO = d(loss)/d(x0).  x0 = drop(LN(E[id] + pos)): recompute the LN input (gather again), LN backward, scatter.
+    if (a.thr_out > 0) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t bits = keep_bits8(ph, (uint32_t)t, (uint32_t)(cq / 8 + q), site_id(SITE_EMB, 0), step, a.thr_out);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dO[8 * q + i] = ((bits >> i) & 1u) ? dO[8 * q + i] * a.inv_keep_out : 0.f;
+      }
+    }
+    float x[16];
+    long long id = 0;
+    if (valid) {
+      id = a.ids[t];
+      id = id < 0 ? 0 : (id >= a.V ? a.V - 1 : id);
+      uint32_t e[8], p[8];
+      ld_global16(a.table + (size_t)id * FH + cq, e);
+      ld_global16(a.pos + (size_t)pos * FH + cq, p);
+      float pv[16];
+      unpack16(e, x);
+      unpack16(p, pv);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] += pv[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { x[i] = 0.f; dO[i] = 0.f; }
+    }
+    float sm = 0.f, zero = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sm += x[i];
+    quad_sum2(sm, zero);
+    const float mean = sm * (1.0f / FH);
+    float q2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float d = x[i] - mean; q2 += d * d; }
+    zero = 0.f;
+    quad_sum2(q2, zero);
+    const float rstd = valid ? rsqrtf(q2 * (1.0f / FH) + kLnEps) : 0.f;
+    float tmp[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { x[i] = (x[i] - mean) * rstd; tmp[i] = dO[i] * x[i]; }
+    // column sums -> sCol (gamma at [0,64), beta at [64,128) of quad block)
+    {
+      float sv; int c;
+      warp_colsum16(tmp, lane, sv, c);
+      if (!(lane & 1)) sCol[quad * PF + cq + c] = sv;
+      warp_colsum16(dO, lane, sv, c);
+      if (!(lane & 1)) sCol[quad * PF + 64 + cq + c] = sv;
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(a.emb_g + cq + i));
+      dO[i] *= gm.x; dO[i + 1] *= gm.y; dO[i + 2] *= gm.z; dO[i + 3] *= gm.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { s1 += dO[i]; s2 += dO[i] * x[i]; }
+    quad_sum2(s1, s2);
+    s1 *= (1.0f / FH); s2 *= (1.0f / FH);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dO[i] = rstd * (dO[i] - s1 - x[i] * s2);
+    // stage dx rows (fp32) and the item ids of the tile in the (dead) arena
+    float* sDx = reinterpret_cast<float*>(smem);                 // [128 rows][64]
+    int* sIds = reinterpret_cast<int*>(smem + 2 * TILE_B);       // [128]
+    umma::fence_before_sync();
+    __syncthreads();                                             // every MMA / tile read of the last layer is complete
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(sDx + row * FH + cq + i) = make_float4(dO[i], dO[i + 1], dO[i + 2], dO[i + 3]);
+    if (part == 0) sIds[row] = valid ? (int)id : -1;
+    __syncthreads();
+    // item-table gradient: rows of the tile with the same item are summed here first (popular items repeat), then ONE
+    // vector reduction per distinct item of the tile goes to the table
+    {
+      const int my = valid ? (int)id : -2;
+      bool leader = valid;
+      for (int r = 0; r < row && leader; ++r) leader = sIds[r] != my;
+      if (leader) {
+        for (int r = row + 1; r < FT; ++r) {
+          if (sIds[r] == my) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 o = *reinterpret_cast<const float4*>(sDx + r * FH + cq + i);
+              dO[i] += o.x; dO[i + 1] += o.y; dO[i + 2] += o.z; dO[i + 3] += o.w;
+            }
+          }
+        }
+        float* gt = a.grad_table + (size_t)id * FH + cq;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(gt + i), "f"(dO[i]), "f"(dO[i + 1]), "f"(dO[i + 2]), "f"(dO[i + 3]) : "memory");
+      }
+    }
+    // position gradient: sum over the G sequences of the tile (fixed order), one partial per CTA
+    float* dp = a.dpos_part + (size_t)blockIdx.x * S * FH;
+    for (int e = tid; e < S * FH; e += NTHR) {
+      const int pp = e / FH, c = e % FH;
+      float v = 0.f;
+      for (int gg = 0; gg < G; ++gg) v += sDx[(gg * SLOT + pp) * FH + c];
+      dp[e] = v;
+    }
+    if (tid < 128) a.embln_part[(size_t)blockIdx.x * 128 + tid] = (sCol[tid] + sCol[PF + tid]) + (sCol[2 * PF + tid] + sCol[3 * PF + tid]);
+  }
   stamp();
   umma::fence_before_sync();
   __syncthreads();
@@ -636,6 +744,8 @@ cudaError_t launch_enc_bwd_fused(const EncBwdArgs& a, cudaStream_t st) {
   size_t moff = ((size_t)a.L * sizeof(LayerDev) + 127) / 128 * 128;
   d.maps = reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const char*>(a.dev_tables) + moff);
   d.dx = a.dx; d.wpart = a.wpart; d.bpart = a.bpart;
+  d.ids = a.ids; d.table = a.table; d.pos = a.pos; d.emb_g = a.emb_g; d.grad_table = a.grad_table; d.dpos_part = a.dpos_part;
+  d.embln_part = a.embln_part; d.V = a.V;
   d.B = a.B; d.S = a.S; d.L = a.L; d.slot = a.S <= 32 ? 32 : (a.S <= 64 ? 64 : 128); d.I = a.I;
   d.thr_out = drop_threshold16(a.out_drop); d.thr_attn = drop_threshold16(a.attn_drop);
   d.inv_keep_out = 1.0f / (1.0f - (float)d.thr_out / 65536.0f);

@@ -143,7 +143,7 @@ cudaError_t launch_head_bwd_rows(const float* dt_part, int nsplit, size_t split_
                                  bf16* d_tpre, float* partials, int M_cap, const int* d_counts, int H,
                                  cudaStream_t st, int dyn_vtiles, int dyn_target, int dyn_max) {
   int grid = ln_bwd_parts(M_cap);
-  const int* d_M = d_counts ? d_counts + 1 : nullptr;
+  const int* d_M = d_counts;   // n_valid: aux rows carry no gradient
   switch (H) {
     case 64: ln_bwd_kernel<64, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
     case 128: ln_bwd_kernel<128, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;

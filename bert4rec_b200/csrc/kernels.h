@@ -137,6 +137,9 @@ struct EncBwdArgs {
   const void* dev_tables;   // the forward's device block (layer table + weight tensor maps)
   float* dx;                // [T][64] fp32 in/out
   float* wpart; float* bpart;
+  // embedding stage backward (fused tail)
+  const int64_t* ids; const bf16* table; const bf16* pos; const float* emb_g;
+  float* grad_table; float* dpos_part; float* embln_part; int V;
   int B, S, L, I;
   float out_drop, attn_drop; uint64_t seed; uint32_t step; const long long* d_step;
   void* dbg;
