@@ -321,6 +321,14 @@ def run_b200(args, w):
         dist.destroy_process_group()
 
 
+def enc_ctas(w):
+    """CTAs of the fused encoder kernels: 128-row tiles of whole sequences in 32/64/128-row slots."""
+    S = w["seq_len"]
+    slot = 32 if S <= 32 else (64 if S <= 64 else 128)
+    g = 128 // slot
+    return (w["batch"] + g - 1) // g
+
+
 def kernel_work(tag, w, n_rows):
     """Algorithmic (flops, bytes, bound) of ONE launch of the kernel behind a profile tag."""
     B, S, H, I, V, N = w["batch"], w["seq_len"], w["hidden_size"], w["inner_dim"], w["vocab_size"], w["num_attention_heads"]
@@ -330,6 +338,10 @@ def kernel_work(tag, w, n_rows):
     t = {
         # fused encoder forward: FLOPs of SURVEY 8d's encoder formula; bytes = ids + every saved activation once
         "enc_fwd_fused": (L * T * (8 * H * H + 4 * S * H + 4 * H * I), T * 8 + saved + L * 4 * T * 4, "hbm"),
+        # fused encoder backward (+ embedding backward): 2x the forward FLOPs; bytes = saved activations read once +
+        # d(out) in + per-CTA weight/bias gradient partials out + item-table reduction
+        "enc_bwd_fused": (2 * L * T * (8 * H * H + 4 * S * H + 4 * H * I),
+                          saved + 2 * T * H * 4 + L * enc_ctas(w) * (4 * H * H + 2 * H * I + 9 * H + I) * 4 + L * 4 * T * 4, "hbm"),
         "ce_fwd_umma": (2 * M * H * V, M * H * e + V * H * e + V * 4 + 3 * M * 4, "tensor"),
         # recompute passes: only the useful GEMM (dT = dl E, dE = dl^T t) is counted, not the recomputed logits
         "ce_bwd_umma:dT": (2 * M * H * V, M * H * e + V * H * e + V * 4 + M * H * 4, "tensor"),
@@ -413,14 +425,19 @@ def roofline_block(model, sess, w, dev_batches, args, hbm, tf_burst, src):
     else:
         ach, peak, unit = by / (ms / 1e3) / 1e9, hbm, "GB/s"
     return {"kernel": tag, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-            "traffic": NCU_TRAFFIC.get(tag), "peak_source": src, "launch_ms": ms, "share_of_step": tot / total,
+            "traffic": NCU_TRAFFIC.get(tag) if w["name"].startswith("C2") else None, "peak_source": src, "launch_ms": ms, "share_of_step": tot / total,
             "algorithmic_flops": fl, "algorithmic_bytes": by, "kernel_ms_per_step": total / n,
             "timing": "CUDA events recorded as graph nodes around every launch, averaged over %d replays" % n,
             "breakdown": breakdown}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {   # bytes per launch at C2, profiles/r01_ncu_full_c2.md (cold-cache capture; the step itself runs L2-warm)
+    "enc_bwd_fused": 41_417_728 + 1_213_440,
+    "enc_fwd_fused": 1_033_984 + 58_624,
+    "ce_bwd_umma:dT": 1_946_624 + 86_528,
+    "ce_bwd_umma:dE": 1_867_264 + 2_560,
+}
 
 
 def main():
