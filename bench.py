@@ -126,6 +126,18 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+def workload_config(w, world, m_valid, sample_note=None):
+    """The `config` object both arms report (same workload keys; the arm-specific notes are extra keys)."""
+    c = {"workload": w["name"], **{k: w[k] for k in ENC_KEYS}, "batch_per_gpu": w["batch"], "seq_len": w["seq_len"],
+         "max_pred": w["max_pred"], "mask_prob": w["mask_prob"],
+         "sequences": "dense (full length), Zipf(1.1) item ids", "parallelism": f"dp{world}"}
+    if m_valid is not None:
+        c["valid_masked_slots_per_batch"] = m_valid
+    if sample_note:
+        c["sample"] = sample_note
+    return c
+
+
 def train_flops(w, m_valid):
     """Algorithmic FLOPs of one train step: 3 x (encoder + MLM transform + tied projection)."""
     T = w["batch"] * w["seq_len"]
@@ -168,12 +180,11 @@ def run_reference(args, w):
     line = {"impl": "reference", "metric": "train masked-seq/s", "value": value, "unit": "seq/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], **{k: w[k] for k in ENC_KEYS}, "batch": w["batch"], "seq_len": w["seq_len"],
-                       "max_pred": w["max_pred"], "mask_prob": w["mask_prob"]},
+            "config": workload_config(w, args.gpus, None, sample_note=f"CPU arm: bounded sample, batch {bs} per step on rank 0"),
             "cpu_baseline": {"value": value, "unit": "seq/s", "cores": cores, "kind": "port",
                              "sample": f"{args.steps} train steps of batch {bs} (CPU restatement of the TF2 path, torch fp32, {cores} threads)"},
             "e2e": {"value": value, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -296,9 +307,7 @@ def run_b200(args, w):
             "metric": "train masked-seq/s", "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": w["name"], **{k: w[k] for k in ENC_KEYS}, "batch_per_gpu": B, "seq_len": S,
-                       "max_pred": P, "mask_prob": w["mask_prob"], "valid_masked_slots_per_batch": m_valid,
-                       "sequences": "dense (full length), Zipf(1.1) item ids", "parallelism": f"dp{world}",
+            "config": {**workload_config(w, world, m_valid),
                        "l2": "256 MiB buffer written between timed steps (untimed); per-step CUDA events summed",
                        "cuda_graph": not args.no_graph},
             "e2e": {"value": e2e_value, "unit": "seq/s",
@@ -316,7 +325,7 @@ def run_b200(args, w):
             v, ms, bs = cpu_reference(w, 3, 1, sample_batch=sample)
             line["cpu_baseline"] = {"value": v, "unit": "seq/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"3 train steps of batch {bs} after 1 warm-up (CPU restatement of the TF2 path, torch fp32, {os.cpu_count()} threads), {ms:.0f} ms/step"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -440,7 +449,26 @@ NCU_TRAFFIC = {   # bytes per launch at C2, profiles/r01_ncu_full_c2.md (cold-ca
 }
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, torch warnings) may write to fd 1; the contract is ONE JSON line on stdout.
+    fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
