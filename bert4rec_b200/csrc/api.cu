@@ -356,9 +356,10 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
   s->p_dbias2 = b.take<float>(bwd_umma ? (size_t)s->me_splits * V : 8);
   s->d_ce_jobs = b.take<ReduceJob>(2);
   s->d_tpre = b.take<bf16>((size_t)Mcap * H);
-  const int head_parts = ln_bwd_parts(Mcap);
+  const bool head_fused = head_bwd_fused_supported(H);
+  const int head_parts = head_fused ? head_bwd_fused_ctas() : ln_bwd_parts(Mcap);
   s->p_head_ln = b.take<float>((size_t)head_parts * 3 * H);
-  s->s_wt = wgrad_splits(H, H, Mcap);
+  s->s_wt = head_fused ? head_bwd_fused_ctas() : wgrad_splits(H, H, Mcap);
   s->p_wt = b.take<float>((size_t)s->s_wt * H * H);
   s->vb_splits = 16;
   s->p_vbias = b.take<float>((size_t)s->vb_splits * V);
@@ -666,10 +667,16 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
     KL("wgrad:ce_dE", launch_wgrad(w, st));
   }
   // ---- MLM transform backward
+  const bf16* xL = s->layers.back().out;
+  if (head_bwd_fused_supported(H)) {
+    KL("head_bwd_fused", launch_head_bwd_fused(s->dt_part, s->dt_splits, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
+                             P + s->lay.find("head/ln/gamma"), W + s->lay.find("head/wt"), xL, s->rows, s->counts, Mcap, s->dxa,
+                             s->p_head_ln, s->p_wt, st, bwd_umma ? (V + 127) / 128 : 0, bwd_umma ? 2 * 148 : 0,
+                             bwd_umma ? s->dt_max_splits : 0));
+  } else {
   KL("head_bwd_rows", launch_head_bwd_rows(s->dt_part, s->dt_splits, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
                           P + s->lay.find("head/ln/gamma"), s->d_tpre, s->p_head_ln, Mcap, s->counts, H, st,
                           bwd_umma ? (V + 127) / 128 : 0, bwd_umma ? 2 * 148 : 0, bwd_umma ? s->dt_max_splits : 0));
-  const bf16* xL = s->layers.back().out;
   {
     WgradArgs w{};
     w.X = xL; w.ldx = H; w.x_rows = s->rows; w.dY = s->d_tpre; w.ldy = H; w.M = H; w.N = H; w.T = Mcap;
@@ -681,6 +688,7 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
     g.d_M = s->counts;  // n_valid only: aux rows carry no gradient and may alias position 0 of a valid slot
     g.out_f32 = s->dxa; g.ld_f32 = H; g.scatter_rows = s->rows;
     KL("gemm:head_dx_scatter", launch_gemm(EPI_SCATTER_F32, g, st));
+  }
   }
   // ---- encoder layers, last to first.  d_out lives in dxa at the top of every iteration.
   const bool fbwd = s->use_fused_bwd && s->use_fused;   // the fused backward assumes the fused forward's tables

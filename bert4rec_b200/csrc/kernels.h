@@ -238,6 +238,14 @@ cudaError_t launch_head_bwd_rows(const float* dt_part, int nsplit, size_t split_
                                  bf16* d_tpre, float* partials, int M_cap, const int* d_counts, int H,
                                  cudaStream_t st, int dyn_vtiles = 0, int dyn_target = 0, int dyn_max = 0);
 
+// MLM transform backward in one launch (k_head.cu, hidden 64): dt partial sum + LN/GELU backward + dx scatter + dWt partials
+bool head_bwd_fused_supported(int H);
+int head_bwd_fused_ctas();   // number of per-CTA partials: p_ln [ctas][3H] = {dgamma, dbeta, dbias}, p_wt [ctas][H*H]
+cudaError_t launch_head_bwd_fused(const float* dt_part, int nsplit, size_t split_stride, const bf16* t_pre, const bf16* t_act,
+                                  const float* mean, const float* rstd, const float* gamma, const bf16* wt, const bf16* x,
+                                  const int* rows, const int* d_counts, int M_cap, float* dx_out, float* p_ln, float* p_wt,
+                                  cudaStream_t st, int dyn_vtiles = 0, int dyn_target = 0, int dyn_max = 0);
+
 // ------------------------------------------------------------------ ranking (k_rank.cu)
 // scores[m][c] = t[m] . E[cand[m][c]] + vbias[cand[m][c]] ; ranking = stable descending order (lower index first on ties)
 // rank[m] = 1 + position of the first candidate equal to gt[m] ; hist[r] += 1
