@@ -140,10 +140,13 @@ class BERT4RecModel:
         if all_cuda:
             torch.cat([v.reshape(-1).to(torch.int64) for v in vals], out=dev)
         else:
-            off = 0
-            for v, n in zip(vals, sizes):
-                host[off:off + n].copy_(v.reshape(-1))   # dtype-converting host copy into the pinned buffer
-                off += n
+            if all(v.dtype == torch.int64 for v in vals):
+                torch.cat([v.reshape(-1) for v in vals], out=host)   # one packed host copy into the pinned buffer
+            else:
+                off = 0
+                for v, n in zip(vals, sizes):
+                    host[off:off + n].copy_(v.reshape(-1))           # dtype-converting host copy
+                    off += n
             dev.copy_(host, non_blocking=True)
         out, off = {}, 0
         for k, shp, n in zip(keys, shapes, sizes):
@@ -230,7 +233,21 @@ class BERT4RecModel:
         """fwd(training) -> fused CE -> backward -> [NCCL allreduce] -> clip + AdamW (bert4rec_model.py:151-173)."""
         if self.optimizer is None:
             raise RuntimeError("compile() the model (or trainer.initialize_model()) before train_step")
-        d = self._stage(inputs, _STAGED_KEYS, persistent=self.use_cuda_graph)
+        # Device-resident int64 inputs are consumed IN PLACE: the captured graph is keyed by their addresses (a training
+        # loop cycling over a cached, device-resident dataset replays with no copy at all).  Host inputs, and device
+        # inputs once more than 8 address sets have been seen, go through the persistent staging buffer.
+        vals = [inputs[k] for k in _STAGED_KEYS]
+        in_place = self.use_cuda_graph and all(torch.is_tensor(v) and v.is_cuda and v.dtype == torch.int64 and v.is_contiguous()
+                                               for v in vals)
+        gkey_ptrs = tuple(v.data_ptr() for v in vals) if in_place else ()
+        if in_place and (vals[0].shape[0], vals[0].shape[1], vals[2].shape[1]) + gkey_ptrs not in self._graphs \
+                and sum(1 for k in self._graphs if len(k) > 3) >= 8:
+            in_place, gkey_ptrs = False, ()
+        if in_place:
+            d = dict(zip(_STAGED_KEYS, vals))
+            self._graph_inputs = getattr(self, "_graph_inputs", {})
+        else:
+            d = self._stage(inputs, _STAGED_KEYS, persistent=self.use_cuda_graph)
         B, S = d["input_word_ids"].shape
         P = d["masked_lm_positions"].shape[1]
         sess = self.store.session(B, S, P)
@@ -239,7 +256,10 @@ class BERT4RecModel:
             self._fwd_bwd(sess, d, stats)
             self._reduce_and_update(sess)
         else:
-            g = self._graphs.get((B, S, P))
+            gkey = (B, S, P) + gkey_ptrs
+            if in_place:
+                self._graph_inputs[gkey] = vals   # keep the captured tensors alive as long as the graph
+            g = self._graphs.get(gkey)
             if g is None:
                 # first step of this shape runs eagerly (lazy one-time initialisation), then the same launch
                 # sequence is captured once and replayed for every later step.  Single GPU: one graph for the
@@ -257,7 +277,7 @@ class BERT4RecModel:
                     g2 = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g2):
                         self._update(self._count)
-                self._graphs[(B, S, P)] = (g1, g2)
+                self._graphs[gkey] = (g1, g2)
             else:
                 g1, g2 = g
                 g1.replay()
