@@ -16,34 +16,38 @@ __global__ void __launch_bounds__(128) rank_candidates_kernel(const bf16* __rest
                                                               const int64_t* __restrict__ gt, int M, int C,
                                                               int64_t* __restrict__ ranking, float* __restrict__ scores,
                                                               int* __restrict__ rank, unsigned long long* __restrict__ hist) {
-  constexpr int LPR = H / 8, CPP = 32 / LPR;  // lanes per row, candidates per pass
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x * 4 + warp;
   if (m >= M) return;
   long long* s_id = reinterpret_cast<long long*>(smem_raw) + (size_t)warp * C;
   float* s_sc = reinterpret_cast<float*>(reinterpret_cast<long long*>(smem_raw) + (size_t)4 * C) + (size_t)warp * C;
-  const int sub = lane / LPR, l = lane % LPR;
-  float tv[8];
-  {
-    const uint4 v = *reinterpret_cast<const uint4*>(t + (size_t)m * ldt + l * 8);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 f = unpack_bf162(w[i]); tv[2 * i] = f.x; tv[2 * i + 1] = f.y; }
+  // the slot's hidden row, fp32, in shared memory (read as a broadcast by every lane)
+  float* s_t = reinterpret_cast<float*>(reinterpret_cast<long long*>(smem_raw) + (size_t)4 * C) + (size_t)4 * C + (size_t)warp * H;
+  for (int k = lane * 2; k < H; k += 64) {
+    const float2 f = unpack_bf162(*reinterpret_cast<const uint32_t*>(t + (size_t)m * ldt + k));
+    s_t[k] = f.x; s_t[k + 1] = f.y;
   }
-  for (int c0 = 0; c0 < C; c0 += CPP) {
-    const int c = c0 + sub;
-    float acc = 0.f;
-    long long id = 0;
-    if (c < C) {
-      id = cand[(size_t)m * C + c];
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(E + (size_t)id * H + l * 8));
+  __syncwarp();
+  // one candidate per lane: its whole table row is fetched with independent 16-byte loads (no cross-lane reduction, all
+  // gathers of the slot in flight at once)
+  for (int c = lane; c < C; c += 32) {
+    const long long id = cand[(size_t)m * C + c];
+    const uint4* row = reinterpret_cast<const uint4*>(E + (size_t)id * H);
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains; summed in a fixed order
+#pragma unroll
+    for (int j = 0; j < H / 8; ++j) {
+      const uint4 v = __ldg(row + j);
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { float2 f = unpack_bf162(w[i]); acc = fmaf(tv[2 * i], f.x, acc); acc = fmaf(tv[2 * i + 1], f.y, acc); }
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf162(w[i]);
+        a4[i] = fmaf(s_t[j * 8 + 2 * i], f.x, a4[i]);
+        a4[i] = fmaf(s_t[j * 8 + 2 * i + 1], f.y, a4[i]);
+      }
     }
-    acc = group_sum<LPR>(acc);
-    if (c < C && l == 0) { s_sc[c] = acc + vbias[id]; s_id[c] = id; }
+    s_sc[c] = ((a4[0] + a4[1]) + (a4[2] + a4[3])) + vbias[id];
+    s_id[c] = id;
   }
   __syncwarp();
   const long long g = gt ? gt[m] : -1;
@@ -72,7 +76,7 @@ cudaError_t launch_rank_candidates(const bf16* t, int ldt, const bf16* E, const 
                                    const int64_t* gt, int M, int C, int H, int64_t* ranking, float* scores,
                                    int* rank, unsigned long long* hist, cudaStream_t st) {
   if (M <= 0) return cudaSuccess;
-  size_t smem = (size_t)4 * C * (sizeof(long long) + sizeof(float));
+  size_t smem = (size_t)4 * C * (sizeof(long long) + sizeof(float)) + (size_t)4 * H * sizeof(float);
   int grid = (M + 3) / 4;
 #define B4R_RK(HH)                                                                                            \
   case HH:                                                                                                    \

@@ -241,7 +241,7 @@ class BERT4RecModel:
                                                for v in vals)
         gkey_ptrs = tuple(v.data_ptr() for v in vals) if in_place else ()
         if in_place and (vals[0].shape[0], vals[0].shape[1], vals[2].shape[1]) + gkey_ptrs not in self._graphs \
-                and sum(1 for k in self._graphs if len(k) > 3) >= 8:
+                and sum(1 for k in self._graphs if len(k) > 3 and k[0] != "rank") >= 8:
             in_place, gkey_ptrs = False, ()
         if in_place:
             d = dict(zip(_STAGED_KEYS, vals))
@@ -392,21 +392,68 @@ class BERT4RecModel:
         sess.transform()
         return sess, d
 
+    def _stage_aux(self, name, t):
+        """int64 auxiliary input (candidate lists, ground truth): device tensors in place, host tensors through a
+        persistent pinned + device buffer pair (stable addresses for graph replays)."""
+        t = torch.as_tensor(t)
+        if t.is_cuda:
+            return t if (t.dtype == torch.int64 and t.is_contiguous()) else t.to(torch.int64).contiguous()
+        key = (name, tuple(t.shape))
+        st = self._staging.get(key)
+        if st is None:
+            st = self._staging[key] = (torch.empty(tuple(t.shape), dtype=torch.int64).pin_memory(),
+                                       torch.empty(tuple(t.shape), dtype=torch.int64, device=self.device))
+        host, dev = st
+        host.copy_(t)
+        dev.copy_(host, non_blocking=True)
+        return dev
+
     def rank_candidates(self, encoder_input, candidates, ground_truth=None, want_ranking=False, hist=None):
         """Fast path of ``rank_items`` for rectangular candidate lists: ``candidates`` int64 [n_slots, C] (row order =
         row-major order of the slots with weight 1), ``ground_truth`` int64 [n_slots].  Returns (ranking or None,
-        ranks int32 [n_slots]) as device tensors."""
-        sess, _ = self._encode_for_ranking(encoder_input)
-        cand = torch.as_tensor(candidates)
-        if not cand.is_cuda:
-            cand = cand.to(torch.int64).pin_memory().to(self.device, non_blocking=True)
-        gt = None
-        if ground_truth is not None:
-            gt = torch.as_tensor(ground_truth)
-            if not gt.is_cuda:
-                gt = gt.to(torch.int64).pin_memory().to(self.device, non_blocking=True)
-        ranking, _, rank = sess.rank_candidates(cand.contiguous(), gt, want_ranking=want_ranking, hist=hist)
-        return ranking, rank
+        ranks int32 [n_slots]) as device tensors.  The launch sequence (encoder forward, slot selection, MLM
+        transform, fused gather-dot + rank) is captured per set of input buffers and replayed; the returned tensors
+        are the graph's output buffers, valid until the next call with the same buffers."""
+        keys = ("input_word_ids", "input_mask", "masked_lm_positions") + \
+               (("masked_lm_weights",) if "masked_lm_weights" in encoder_input else ())
+        d = self._stage(encoder_input, keys)
+        cand = self._stage_aux("cand", candidates)
+        gt = self._stage_aux("gt", ground_truth) if ground_truth is not None else None
+        B, S = d["input_word_ids"].shape
+        P = d["masked_lm_positions"].shape[1]
+        sess = self.store.session(B, S, P)
+
+        def run():
+            sess.encode(d["input_word_ids"], d["input_mask"], training=False)
+            if "masked_lm_weights" in d:
+                sess.select(d["masked_lm_positions"], None, d["masked_lm_weights"], mode=1)
+            else:
+                sess.select(d["masked_lm_positions"], None, None, mode=2)
+            sess.transform()
+            ranking, _, rank = sess.rank_candidates(cand, gt, want_ranking=want_ranking, hist=hist)
+            return ranking, rank
+
+        if not self.use_cuda_graph:
+            return run()
+        gkey = ("rank", B, S, P, tuple(cand.shape), bool(want_ranking), hist.data_ptr() if hist is not None else 0,
+                cand.data_ptr(), gt.data_ptr() if gt is not None else 0) + tuple(d[k].data_ptr() for k in keys)
+        g = self._graphs.get(gkey)
+        if g is None:
+            if sum(1 for k in self._graphs if k and k[0] == "rank") >= 8:
+                return run()          # too many distinct buffer sets: stay eager
+            eager_out = run()         # this call's result (and its histogram update) comes from the eager pass
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = run()
+            self._graphs[gkey] = (graph, out, [d, cand, gt, hist])
+            return eager_out
+        return self._replay_rank(gkey)
+
+    def _replay_rank(self, gkey):
+        graph, out, _ = self._graphs[gkey]
+        graph.replay()
+        return out
 
     def rank_items(self, encoder_input: dict, items: list = None):
         """Reference semantics (bert4rec_model.py:203-240): one ranking per slot whose ``masked_lm_weights`` is 1;
