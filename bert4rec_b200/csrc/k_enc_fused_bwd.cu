@@ -131,10 +131,10 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
 
   int dbg_i = 0;
   auto stamp = [&]() {
-    if (a.dbg && blockIdx.x == 0 && tid == 0) {
+    if (a.dbg && blockIdx.x == 0 && lane == 0 && dbg_i < 32) {   // every warp of CTA 0: dbg[warp][32]
       unsigned long long tns;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
-      a.dbg[dbg_i++] = tns;
+      a.dbg[warp * 32 + dbg_i++] = tns;
     }
   };
 

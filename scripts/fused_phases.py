@@ -34,5 +34,13 @@ if cta:
     t0 = min(c[0] for c in cta)
     print("CTAs", len(cta), "start spread us", (max(c[0] for c in cta) - t0) / 1e3, "last end us", (max(c[1] for c in cta) - t0) / 1e3,
           "mean dur us", sum(c[1] - c[0] for c in cta) / len(cta) / 1e3)
+if which == "bwd":
+    allts = sess._view(p, (512,), torch.int64).cpu().tolist()
+    t0 = min(v for v in allts if v)
+    print("per-warp phase stamps (us since first stamp), CTA 0: rows = warps (quad = w & 3, part = w >> 2)")
+    for w in range(16):
+        r = [v for v in allts[w * 32:(w + 1) * 32] if v]
+        print(f"w{w:2d} " + " ".join(f"{(v - t0) / 1e3:6.2f}" for v in r[:14]))
+    sys.exit(0)
 print("stamps", n, "total us", (ts[-1] - ts[0]) / 1e3)
 print(" ".join(f"{(ts[i + 1] - ts[i]) / 1e3:.2f}" for i in range(n - 1)))
