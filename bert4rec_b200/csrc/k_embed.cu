@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restric
   if (d_step) step += (uint32_t)(*d_step);
   constexpr int LPR = H / 8, RPW = 32 / LPR, RPC = 8 * RPW;  // rows per CTA pass
   __shared__ float s_red[3][RPC][H + 1];
+  __shared__ float s_dx[RPC][H];   // dx rows of one pass, for the in-CTA aggregation of repeated items
+  __shared__ int s_id[RPC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, l = lane % LPR, c0 = l * 8;
   const int s = blockIdx.x, z = blockIdx.y, nz = gridDim.y;
@@ -162,8 +164,10 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restric
     }
     s1 = group_sum<LPR>(s1) * (1.0f / H);
     s2 = group_sum<LPR>(s2) * (1.0f / H);
+    float dx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dx[i] = 0.f;
     if (ok) {
-      float dx[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         dx[i] = rstd * (dxh[i] - s1 - xh[i] * s2);
@@ -171,10 +175,31 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restric
         a_g[i] += dy[i] * xh[i];
         a_b[i] += dy[i];
       }
-      float* g = grad_table + (size_t)id * H + c0;
-      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(g), "f"(dx[0]), "f"(dx[1]), "f"(dx[2]), "f"(dx[3]) : "memory");
-      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(g + 4), "f"(dx[4]), "f"(dx[5]), "f"(dx[6]), "f"(dx[7]) : "memory");
     }
+    // Rows of this pass that gather the same item (popular items repeat) are summed in shared memory first; one vector
+    // reduction per distinct item of the pass goes to the table (the hot rows otherwise serialise in L2).
+    *reinterpret_cast<float4*>(&s_dx[slot][c0]) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+    *reinterpret_cast<float4*>(&s_dx[slot][c0 + 4]) = make_float4(dx[4], dx[5], dx[6], dx[7]);
+    if (l == 0) s_id[slot] = ok ? (int)id : -1;
+    __syncthreads();
+    if (ok) {
+      const int my = (int)id;
+      bool leader = true;
+      for (int r = 0; r < slot && leader; ++r) leader = s_id[r] != my;
+      if (leader) {
+        for (int r = slot + 1; r < RPC; ++r) {
+          if (s_id[r] == my) {
+            const float4 o0 = *reinterpret_cast<const float4*>(&s_dx[r][c0]);
+            const float4 o1 = *reinterpret_cast<const float4*>(&s_dx[r][c0 + 4]);
+            dx[0] += o0.x; dx[1] += o0.y; dx[2] += o0.z; dx[3] += o0.w; dx[4] += o1.x; dx[5] += o1.y; dx[6] += o1.z; dx[7] += o1.w;
+          }
+        }
+        float* g = grad_table + (size_t)id * H + c0;
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(g), "f"(dx[0]), "f"(dx[1]), "f"(dx[2]), "f"(dx[3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(g + 4), "f"(dx[4]), "f"(dx[5]), "f"(dx[6]), "f"(dx[7]) : "memory");
+      }
+    }
+    __syncthreads();
   }
   // CTA reduction over the RPC row slots (fixed order -> deterministic for dpos / dgamma / dbeta)
 #pragma unroll
