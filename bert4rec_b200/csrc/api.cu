@@ -793,7 +793,7 @@ extern "C" int b4r_pooled_output(b4r_session* s, float* out, void* stream) {
 
 // ------------------------------------------------------------------------------------------------ optimizer
 static const int kSqParts = 296;
-extern "C" size_t b4r_adamw_scratch_floats(void) { return kSqParts; }
+extern "C" size_t b4r_adamw_scratch_floats(void) { return kSqParts + 16; }   // partials + coefficients + ticket (zero-initialised by the caller)
 extern "C" int b4r_adamw_step(float* params, void* shadow_bf16, const float* grads, float* m, float* v, int64_t n_decay,
                               int64_t n_trainable, const b4r_adamw_hparams* hp, const float* count, float grad_scale,
                               int64_t* step_counter, float* scratch, float* lr_out, void* stream) {

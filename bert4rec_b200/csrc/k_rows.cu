@@ -278,17 +278,31 @@ cudaError_t launch_colsum_bf16(const bf16* src, int ld, int M, int N, const int*
 }
 
 // ------------------------------------------------------------------------------------------------ norm + AdamW
-__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, long long n, float* __restrict__ out_part,
-                                                     long long* step_counter) {
+struct AdamWDev {
+  float* p; bf16* shadow; const float* g; float* m; float* v;
+  long long n_decay, n;
+  float* sq_part; int n_sq_part;   // [n_sq_part] partial squared norms, then coef[4] = {gscale*clip, lr, alpha, -} and the ticket
+  const float* d_count; float grad_scale;
+  long long* d_step;
+  float init_lr, end_lr; float num_train_steps, num_warmup_steps;
+  float wd, beta1, beta2, eps, clip;
+  float* d_lr_out;
+};
+
+// Stage 1: squared-norm partials of the gradient.  The LAST block to finish (atomic ticket) sums them in a fixed order,
+// advances optimizer.iterations and evaluates the step coefficients ONCE (global-norm clip scale, warm-up / decayed
+// learning rate, Adam bias correction in double precision) -- not per block of the update kernel.
+__global__ void __launch_bounds__(256) sqnorm_kernel(AdamWDev a, int with_coef) {
   __shared__ float s[8];
+  __shared__ int s_last;
   float acc = 0.f;
-  const long long n4 = n >> 2;
-  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const long long n4 = a.n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(a.g);
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     float4 v = g4[i];
     acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
-  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { float v = g[(n4 << 2) + threadIdx.x]; acc += v * v; }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) { float v = a.g[(n4 << 2) + threadIdx.x]; acc += v * v; }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -296,40 +310,29 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g
     float v = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) v += s[i];
-    out_part[blockIdx.x] = v;
-    if (blockIdx.x == 0 && step_counter) *step_counter += 1;  // optimizer.iterations -> t = iterations + 1
+    a.sq_part[blockIdx.x] = v;
   }
-}
-
-cudaError_t launch_sqnorm(const float* g, long long n, float* out_part, int nblocks, cudaStream_t st) {
-  sqnorm_kernel<<<nblocks, 256, 0, st>>>(g, n, out_part, nullptr);
-  return cudaGetLastError();
-}
-
-struct AdamWDev {
-  float* p; bf16* shadow; const float* g; float* m; float* v;
-  long long n_decay, n;
-  const float* sq_part; int n_sq_part;
-  const float* d_count; float grad_scale;
-  const long long* d_step;
-  float init_lr, end_lr; float num_train_steps, num_warmup_steps;
-  float wd, beta1, beta2, eps, clip;
-  float* d_lr_out;
-};
-
-__global__ void __launch_bounds__(256) adamw_kernel(AdamWDev a) {
-  __shared__ float s_coef[4];  // gscale, lr, alpha, (unused)
+  if (!with_coef) return;
+  int* ticket = reinterpret_cast<int*>(a.sq_part + a.n_sq_part + 4);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   if (threadIdx.x < 32) {
-    float acc = 0.f;
-    for (int i = threadIdx.x; i < a.n_sq_part; i += 32) acc += a.sq_part[i];
-    acc = warp_sum(acc);
+    float tot = 0.f;
+    for (int i = threadIdx.x; i < a.n_sq_part; i += 32) tot += __ldcg(a.sq_part + i);
+    tot = warp_sum(tot);
     if (threadIdx.x == 0) {
+      *ticket = 0;
+      const long long t = *a.d_step + 1;   // optimizer.iterations -> t = iterations + 1
+      *a.d_step = t;
       float gscale = a.grad_scale;
       if (a.d_count) gscale /= fmaxf(*a.d_count, 1.0f);
-      const float gn = sqrtf(acc) * gscale;  // global norm of the (normalised) gradient
+      const float gn = sqrtf(tot) * gscale;  // global norm of the (normalised) gradient
       float clip_scale = 1.0f;
       if (a.clip > 0.f) clip_scale = a.clip * fminf(1.0f / gn, 1.0f / a.clip);  // tf.clip_by_global_norm
-      const long long t = *a.d_step;        // already incremented for this step: t = iterations + 1
       const float it = (float)(t - 1);
       float lr;
       if (a.num_warmup_steps > 0.f && it < a.num_warmup_steps) {
@@ -340,12 +343,23 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamWDev a) {
       }
       const double b1p = pow((double)a.beta1, (double)t), b2p = pow((double)a.beta2, (double)t);
       const float alpha = (float)((double)lr * sqrt(1.0 - b2p) / (1.0 - b1p));
-      s_coef[0] = gscale * clip_scale; s_coef[1] = lr; s_coef[2] = alpha;
-      if (blockIdx.x == 0 && a.d_lr_out) { a.d_lr_out[0] = lr; a.d_lr_out[1] = gn; }
+      float* coef = a.sq_part + a.n_sq_part;
+      coef[0] = gscale * clip_scale; coef[1] = lr; coef[2] = alpha;
+      if (a.d_lr_out) { a.d_lr_out[0] = lr; a.d_lr_out[1] = gn; }
     }
   }
-  __syncthreads();
-  const float gs = s_coef[0], lr = s_coef[1], alpha = s_coef[2];
+}
+
+cudaError_t launch_sqnorm(const float* g, long long n, float* out_part, int nblocks, cudaStream_t st) {
+  AdamWDev d{};
+  d.g = g; d.n = n; d.sq_part = out_part; d.n_sq_part = nblocks;
+  sqnorm_kernel<<<nblocks, 256, 0, st>>>(d, 0);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(AdamWDev a) {
+  const float* coef = a.sq_part + a.n_sq_part;
+  const float gs = coef[0], lr = coef[1], alpha = coef[2];
   const float ob1 = 1.0f - a.beta1, ob2 = 1.0f - a.beta2;
   const long long n4 = a.n >> 2;  // segments are padded to multiples of 8 elements, so n % 4 == 0
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
@@ -373,16 +387,16 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamWDev a) {
 }
 
 cudaError_t launch_adamw(const AdamWArgs& a, cudaStream_t st) {
-  // stage 1: squared-norm partials (+ step counter increment), stage 2: update
-  sqnorm_kernel<<<a.n_sq_part, 256, 0, st>>>(a.g, a.n, const_cast<float*>(a.sq_part), a.d_step_out);
   AdamWDev d;
   d.p = a.p; d.shadow = a.shadow; d.g = a.g; d.m = a.m; d.v = a.v; d.n_decay = a.n_decay; d.n = a.n;
-  d.sq_part = a.sq_part; d.n_sq_part = a.n_sq_part; d.d_count = a.d_count; d.grad_scale = a.grad_scale;
-  d.d_step = a.d_step; d.init_lr = a.init_lr; d.end_lr = a.end_lr;
+  d.sq_part = const_cast<float*>(a.sq_part); d.n_sq_part = a.n_sq_part; d.d_count = a.d_count; d.grad_scale = a.grad_scale;
+  d.d_step = a.d_step_out; d.init_lr = a.init_lr; d.end_lr = a.end_lr;
   d.num_train_steps = (float)a.num_train_steps; d.num_warmup_steps = (float)a.num_warmup_steps;
   d.wd = a.wd; d.beta1 = a.beta1; d.beta2 = a.beta2; d.eps = a.eps; d.clip = a.clip; d.d_lr_out = a.d_lr_out;
+  // stage 1: squared-norm partials + (last block) step counter and coefficients ; stage 2: update
+  sqnorm_kernel<<<a.n_sq_part, 256, 0, st>>>(d, 1);
   long long n4 = a.n >> 2;
-  int blocks = (int)((n4 + 255) / 256);
+  int blocks = (int)((n4 + 1023) / 1024);   // 4 float4 per thread
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   adamw_kernel<<<blocks, 256, 0, st>>>(d);
