@@ -203,6 +203,17 @@ struct b4r_session {
   float *enc_wpart = nullptr, *enc_bpart = nullptr, *enc_dpos = nullptr, *enc_embln = nullptr;
   ReduceJob* d_jobs_f = nullptr; int n_jobs_f = 0, jobs_f_blocks = 0;   // reduce jobs when the fused backward produced the partials
   void* d_enc_tables = nullptr;
+  // internal side stream: kernels that do not depend on each other run as parallel branches (forked from / joined to the
+  // caller's stream with events, so the caller still sees ONE ordered stream; inside a capture they become graph branches)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sel = nullptr;
+  bool sel_pending = false, overlap_select = false;
+  ~b4r_session() {
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (ev_sel) cudaEventDestroy(ev_sel);
+    if (side) cudaStreamDestroy(side);
+  }
   unsigned long long* dbg_buf = nullptr;
   bf16* dlogits; int dl_rows;
   float* dt_part; int dt_splits, dt_max_splits;
@@ -464,6 +475,10 @@ extern "C" int b4r_session_create(const b4r_config* cfg, int batch, int seq_len,
   s->use_umma = ce_umma_make_maps(&s->umaps, s->t, s->Mcap, s->shadow + s->lay.find("word_embeddings"), s->V, s->H) &&
                 getenv("B4R_DISABLE_UMMA") == nullptr;
   CK(cudaMemset(s->counts, 0, 8 * sizeof(int)));
+  CK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&s->ev_sel, cudaEventDisableTiming));
   if (enc_fused_supported(s->H, s->N, s->S, s->I)) {
     const int Ln = s->cfg.num_layers;
     std::vector<EncFusedLayerHost> lh(Ln);
@@ -559,11 +574,30 @@ extern "C" int b4r_mlm_select(b4r_session* s, const int64_t* positions, const in
   // mode 2 (all slots): reuse the weights path with a null test -> handled by passing positions as weights of ones
   s->select_mode = mode;
   const int64_t* id_src = ids ? ids : positions;
+  cudaStream_t st_caller = st;
+  if (s->overlap_select) {   // the compaction depends on the inputs only: run it as a branch beside what the caller enqueues next
+    CK(cudaEventRecord(s->ev_fork, st_caller));
+    CK(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
+    st = s->side;
+  }
   if (mode == 2) {
     // all slots valid: weights := non-null pointer whose values are irrelevant -> use use_weights = 2
     KL("mlm_select", launch_mlm_select(positions, id_src, nullptr, 2, s->B, s->S, s->P, 0, s->rows, s->labels, s->row_w, s->row_mult, s->counts, st));
   } else {
     KL("mlm_select", launch_mlm_select(positions, id_src, weights, mode, s->B, s->S, s->P, want_aux, s->rows, s->labels, s->row_w, s->row_mult, s->counts, st));
+  }
+  if (s->overlap_select) {
+    CK(cudaEventRecord(s->ev_sel, s->side));
+    s->sel_pending = true;
+  }
+  return 0;
+}
+
+// joins a pending side-stream selection into the caller's stream (every consumer of rows / labels / counts calls this)
+static int join_select(b4r_session* s, cudaStream_t st) {
+  if (s->sel_pending) {
+    CK(cudaStreamWaitEvent(st, s->ev_sel, 0));
+    s->sel_pending = false;
   }
   return 0;
 }
@@ -571,6 +605,7 @@ extern "C" int b4r_mlm_select(b4r_session* s, const int64_t* positions, const in
 extern "C" int b4r_mlm_transform(b4r_session* s, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!s) return fail("null session");
+  if (join_select(s, st)) return 1;
   const int H = s->H;
   const bf16* x = s->layers.back().out;
   RowLnArgs r{};
@@ -596,6 +631,7 @@ static CeArgs ce_args(b4r_session* s) {
 extern "C" int b4r_mlm_loss(b4r_session* s, float* stats, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!s) return fail("null session");
+  if (join_select(s, st)) return 1;
   CeArgs c = ce_args(s);
   c.stats = stats;
   if (s->use_umma) {
@@ -612,6 +648,7 @@ extern "C" int b4r_mlm_loss(b4r_session* s, float* stats, void* stream) {
 extern "C" int b4r_mlm_logits(b4r_session* s, float* out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!s || !out) return fail("null argument");
+  if (join_select(s, st)) return 1;
   GemmArgs g{};
   g.A = s->t; g.lda = s->H; g.B = s->shadow + s->lay.find("word_embeddings"); g.ldb = s->H; g.b_trans = false;
   g.M = s->Mcap; g.N = s->V; g.K = s->H; g.d_M = s->counts + 1;
@@ -637,6 +674,8 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
   if (!bwd_umma) CK(cudaMemsetAsync(G + oE, 0, (size_t)V * H * sizeof(float), st));
   CK(cudaMemsetAsync(s->dxa, 0, (size_t)T * H * sizeof(float), st));
   CeArgs c = ce_args(s);
+  bool head_done = false;
+  if (join_select(s, st)) return 1;
   if (bwd_umma) {
     // ---- CE backward, generation 2: two tcgen05 passes that recompute the logits tile, nothing [M,V]-sized in memory
     CeBwdArgs ba{};
@@ -644,9 +683,24 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
     ba.M_cap = Mcap; ba.V = V; ba.H = H; ba.target_ctas = 2 * 148; ba.max_splits = s->dt_max_splits; ba.msplits = s->me_splits;
     ba.out = s->dt_part; ba.dbias_out = nullptr;
     KL("ce_bwd_umma:dT", launch_ce_bwd_umma(s->umaps, ba, true, st));
+    if (head_bwd_fused_supported(H)) {
+      // the MLM-transform backward needs dT only: it runs as a branch beside the dE pass and its reduction
+      CK(cudaEventRecord(s->ev_fork, st));
+      CK(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
+      {
+        cudaStream_t st_main = st; (void)st_main;
+        cudaStream_t st = s->side;
+        KL("head_bwd_fused", launch_head_bwd_fused(s->dt_part, s->dt_splits, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
+                                 P + s->lay.find("head/ln/gamma"), W + s->lay.find("head/wt"), s->layers.back().out, s->rows, s->counts,
+                                 Mcap, s->dxa, s->p_head_ln, s->p_wt, st, (V + 127) / 128, 2 * 148, s->dt_max_splits));
+      }
+      CK(cudaEventRecord(s->ev_join, s->side));
+      head_done = true;
+    }
     ba.out = s->p_dE; ba.dbias_out = s->p_dbias2;
     KL("ce_bwd_umma:dE", launch_ce_bwd_umma(s->umaps, ba, false, st));
     KL("grad_reduce:ce", launch_grad_reduce(s->d_ce_jobs, 2, grad_reduce_blocks(s->me_splits, V * H), st));
+    if (head_done) CK(cudaStreamWaitEvent(st, s->ev_join, 0));
   }
   // ---- CE backward, generation 1: dlogits materialised in bf16, chunked over rows
   int chunk = 0;
@@ -668,7 +722,9 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
   }
   // ---- MLM transform backward
   const bf16* xL = s->layers.back().out;
-  if (head_bwd_fused_supported(H)) {
+  if (head_done) {
+    // already issued beside the dE pass
+  } else if (head_bwd_fused_supported(H)) {
     KL("head_bwd_fused", launch_head_bwd_fused(s->dt_part, s->dt_splits, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
                              P + s->lay.find("head/ln/gamma"), W + s->lay.find("head/wt"), xL, s->rows, s->counts, Mcap, s->dxa,
                              s->p_head_ln, s->p_wt, st, bwd_umma ? (V + 127) / 128 : 0, bwd_umma ? 2 * 148 : 0,
@@ -819,6 +875,7 @@ extern "C" int b4r_rank_candidates(b4r_session* s, const int64_t* cand, const in
   if (!s || !cand) return fail("null argument");
   if (C < 1 || C > 2048) return fail("candidate count %d unsupported (1..2048)", C);
   if (n_slots > s->Mcap) return fail("n_slots %d exceeds session capacity %d", n_slots, s->Mcap);
+  if (join_select(s, st)) return 1;
   KL("rank_candidates", launch_rank_candidates(s->t, s->H, s->shadow + s->lay.find("word_embeddings"), s->params + s->lay.find("head/output_bias"),
                             cand, gt, n_slots, C, s->H, reinterpret_cast<int64_t*>(ranking_out), scores_out, rank_out,
                             reinterpret_cast<unsigned long long*>(hist), st));
@@ -890,6 +947,7 @@ extern "C" const void* b4r_debug_buffer2(b4r_session* s) { return s ? (const voi
 extern "C" int b4r_session_set_flag(b4r_session* s, int flag, int value) {
   if (!s) return fail("null session");
   if (flag == 1) { s->use_umma = value != 0; return 0; }
+  if (flag == 4) { s->overlap_select = value != 0; return 0; }
   if (flag == 3) {
     if (value && !s->fused_bwd_ok) return fail("fused encoder backward unavailable for this shape");
     s->use_fused_bwd = value != 0;

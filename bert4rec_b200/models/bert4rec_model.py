@@ -135,8 +135,12 @@ class BERT4RecModel:
         if st is None:
             host = torch.empty(total, dtype=torch.int64).pin_memory()
             dev = torch.empty(total, dtype=torch.int64, device=self.device)
-            st = self._staging[key] = (host, dev)
-        host, dev = st
+            views, off = {}, 0
+            for k, shp, n in zip(keys, shapes, sizes):   # the per-key device views are fixed: built once
+                views[k] = dev[off:off + n].view(shp)
+                off += n
+            st = self._staging[key] = (host, dev, views)
+        host, dev, views = st
         if all_cuda:
             torch.cat([v.reshape(-1).to(torch.int64) for v in vals], out=dev)
         else:
@@ -148,11 +152,7 @@ class BERT4RecModel:
                     host[off:off + n].copy_(v.reshape(-1))           # dtype-converting host copy
                     off += n
             dev.copy_(host, non_blocking=True)   # ONE H2D copy (five separate small copies measured slower)
-        out, off = {}, 0
-        for k, shp, n in zip(keys, shapes, sizes):
-            out[k] = dev[off:off + n].view(shp)
-            off += n
-        return out
+        return views
 
     @staticmethod
     def _bytes_of(keys, inputs):
@@ -308,8 +308,11 @@ class BERT4RecModel:
         """The launch sequence of forward + backward (all on torch's current stream; CUDA-graph capturable:
         the dropout counter and the learning-rate schedule read the device-side iteration counter)."""
         ctr = self.store.step_counter
-        sess.encode(d["input_word_ids"], d["input_mask"], training=True, seed=self._seed, step=0, step_counter=ctr)
+        # the slot compaction depends on the inputs only: it is enqueued first, as a branch beside the encoder forward
+        sess.set_flag(4, 1)
         sess.select(d["masked_lm_positions"], d["masked_lm_ids"], d["masked_lm_weights"], mode=0, want_aux=self._want_sca)
+        sess.set_flag(4, 0)
+        sess.encode(d["input_word_ids"], d["input_mask"], training=True, seed=self._seed, step=0, step_counter=ctr)
         sess.transform()
         sess.loss(stats)
         sess.backward(seed=self._seed, step=0, step_counter=ctr)
@@ -427,11 +430,13 @@ class BERT4RecModel:
         sess = self.store.session(B, S, P)
 
         def run():
-            sess.encode(d["input_word_ids"], d["input_mask"], training=False)
+            sess.set_flag(4, 1)   # the slot selection runs as a branch beside the encoder forward
             if "masked_lm_weights" in d:
                 sess.select(d["masked_lm_positions"], None, d["masked_lm_weights"], mode=1)
             else:
                 sess.select(d["masked_lm_positions"], None, None, mode=2)
+            sess.set_flag(4, 0)
+            sess.encode(d["input_word_ids"], d["input_mask"], training=False)
             sess.transform()
             ranking, _, rank = sess.rank_candidates(cand, gt, want_ranking=want_ranking, hist=hist)
             return ranking, rank
