@@ -233,6 +233,7 @@ struct b4r_session {
 
 static const int kColsumSplits = 64;
 static int wgrad_splits(int M, int N, int T) {
+  if (twgrad_shape_ok(M, N, T)) return twgrad_splits(M, N, T);   // the tcgen05 kernel's own split count
   int tiles = ((M + 63) / 64) * ((N + 63) / 64);
   int s = (2 * 148 + tiles - 1) / tiles;
   int cap = T / 256;

@@ -157,6 +157,7 @@ static cudaError_t launch_gemm_t(const GemmArgs& a, cudaStream_t st) {
 
 cudaError_t launch_gemm(int epi, const GemmArgs& a, cudaStream_t st) {
   if (a.a_trans) return cudaErrorInvalidValue;
+  if (tgemm_supported(epi, a)) return launch_tgemm(epi, a, st);   // generation 2: tcgen05 + TMEM + TMA
 #define B4R_CASE(E)                                                          \
   case E:                                                                    \
     return a.b_trans ? launch_gemm_t<TileNN, E>(a, st) : launch_gemm_t<TileNT, E>(a, st);
@@ -374,6 +375,7 @@ __global__ void __launch_bounds__(TileWG::THREADS) wgrad_kernel(GemmOperands op,
 }
 
 cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t st) {
+  if (twgrad_supported(a)) return launch_twgrad(a, st);   // generation 2: tcgen05 + TMEM + TMA
   typedef TileWG T;
   GemmOperands op;
   op.A = a.X; op.lda = a.ldx; op.a_rows = a.x_rows; op.B = a.dY; op.ldb = a.ldy;

@@ -1,0 +1,429 @@
+// Generation 2 of the generic GEMM (k_gemm.cu gemm_kernel): C[M,N] = A[M,K] . B  with the same fused epilogues, on
+// tcgen05.mma + TMEM + TMA.  Persistent, warp-specialised:
+//   warp 0    : TMA producer -- A tile [128 rows][64 k] and B tile through a 4-stage shared-memory ring (SWIZZLE_128B)
+//   warp 1    : MMA issuer (one elected lane): 4 x (M128 N128 K16) per k-block into one of TWO 128-column fp32
+//               accumulators in TMEM, so the epilogue of tile i overlaps the main loop of tile i+1
+//   warps 2-9 : epilogue, thread = (accumulator row, 64-column half): tcgen05.ld 32 columns at a time -> bias / GELU /
+//               GELU' (+ per-tile column sums = bias gradient) / fp32 residual -> global
+// B is consumed in place in either layout: [K,N] row-major (forward: TF kernels are [in,out]) as an MN-major operand,
+// [N,K] row-major (data gradients read the SAME weights transposed) as a K-major operand -- no transposed copies.
+// Used for hidden sizes whose GEMMs are real GEMMs (K, N multiples of 64; e.g. C4: M = 204 800 tokens, K/N in
+// {256, 768, 1024}); reference ops: Keras EinsumDense projections of tfm TransformerEncoderBlock
+// (bert4rec_encoder.py:136-147) and their gradients.
+#include <cstdlib>
+#include "common.cuh"
+#include "kernels.h"
+#include "umma.cuh"
+#include "enc_fused.cuh"
+
+namespace b4r {
+using namespace encf;
+
+namespace {
+constexpr int TG_BM = 128, TG_BN = 128, TG_BK = 64, TG_STAGES = 4;
+constexpr int TG_A_BYTES = TG_BM * 128, TG_B_BYTES = TG_BN * 128, TG_STAGE = TG_A_BYTES + TG_B_BYTES;
+constexpr int TG_SMEM = TG_STAGES * TG_STAGE + 2 * 4 * TG_BN * 4 + 256 + 1024;   // ring + column-sum scratch + barriers + align
+
+struct TGemmDev {
+  int M, N, K;
+  const float* bias;
+  bf16* out_bf16; int ld_out;
+  bf16* out2_bf16;
+  const bf16* aux_bf16; int ld_aux;
+  float* out_f32; int ld_f32;
+  const float* res_f32;
+  float* colsum_part;
+};
+}  // namespace
+
+template <int EPI, bool B_MN>
+__global__ void __launch_bounds__(320, 1) tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                       TGemmDev a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* sCol = reinterpret_cast<float*>(smem + TG_STAGES * TG_STAGE);   // [2 acc][4 quads][128] column-sum partials
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + 2 * 4 * TG_BN);
+  uint64_t* full = bars;                       // [STAGES]
+  uint64_t* empty = bars + TG_STAGES;          // [STAGES]
+  uint64_t* tfull = bars + 2 * TG_STAGES;      // [2]
+  uint64_t* tempty = tfull + 2;                // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (a.M + TG_BM - 1) / TG_BM, tiles_n = (a.N + TG_BN - 1) / TG_BN;
+  const int n_tiles = tiles_m * tiles_n, kblocks = a.K / TG_BK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TG_STAGES; ++i) { umma::mbar_init(full + i, 1); umma::mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(tfull + i, 1); umma::mbar_init(tempty + i, 8); }
+    umma::fence_barrier_init();
+    umma::prefetch_tensormap(&tmA);
+    umma::prefetch_tensormap(&tmB);
+  }
+  if (warp == 1) umma::tmem_alloc<256>(tmem_holder);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int m0 = (t / tiles_n) * TG_BM, n0 = (t % tiles_n) * TG_BN;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int st = it % TG_STAGES;
+          umma::mbar_wait(empty + st, ((it / TG_STAGES) & 1) ^ 1);
+          umma::mbar_expect_tx(full + st, TG_STAGE);
+          unsigned char* sA = smem + st * TG_STAGE;
+          unsigned char* sB = sA + TG_A_BYTES;
+          umma::tma_load_2d(sA, &tmA, kb * TG_BK, m0, full + st);
+          if (B_MN) {   // B [K,N]: two [64 k-rows][64 n] blocks
+            umma::tma_load_2d(sB, &tmB, n0, kb * TG_BK, full + st);
+            umma::tma_load_2d(sB + 8192, &tmB, n0 + 64, kb * TG_BK, full + st);
+          } else {      // B [N,K]: [128 n-rows][64 k]
+            umma::tma_load_2d(sB, &tmB, kb * TG_BK, n0, full + st);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (elect_one()) {
+      const uint64_t DK0 = umma::make_desc_k_sw128(umma::smem_addr(smem));
+      const uint64_t DMN0 = desc_mn_sw128(umma::smem_addr(smem), 8192);
+      constexpr uint32_t idesc = idesc_gen(TG_BM, TG_BN, 0, B_MN ? 1 : 0);
+      int it = 0, ti = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+        const int acc = ti & 1;
+        umma::mbar_wait(tempty + acc, ((ti >> 1) & 1) ^ 1);
+        umma::fence_after_sync();
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int st = it % TG_STAGES;
+          umma::mbar_wait(full + st, (it / TG_STAGES) & 1);
+          umma::fence_after_sync();
+          const uint32_t offA = st * TG_STAGE, offB = offA + TG_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = desc_at(DK0, offA + k * 32);
+            const uint64_t db = B_MN ? desc_at(DMN0, offB + k * 2048) : desc_at(DK0, offB + k * 32);
+            umma::mma_bf16_ss(tmem + acc * TG_BN, da, db, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma::mma_commit(empty + st);
+        }
+        umma::mma_commit(tfull + acc);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue (warps 2..9)
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int row_in_tile = quad * 32 + lane;
+    int ti = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+      const int acc = ti & 1;
+      const int mt = t / tiles_n, m0 = mt * TG_BM, n0 = (t % tiles_n) * TG_BN;
+      const int m = m0 + row_in_tile;
+      const bool mok = m < a.M;
+      umma::mbar_wait(tfull + acc, (ti >> 1) & 1);
+      umma::fence_after_sync();
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int n = n0 + half * 64 + c * 32;           // first of this thread's 32 columns
+        float v[32];
+        tmem_ld_f32(tmem + ((uint32_t)(quad * 32) << 16) + acc * TG_BN + half * 64 + c * 32, v);
+        const bool nok = n < a.N;                         // N is a multiple of 32 on this path
+        if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU) {
+          if (nok) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n + i));
+              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+            }
+          }
+        }
+        if (EPI == EPI_BIAS_BF16 || EPI == EPI_BF16) {
+          uint32_t pk[16];
+          pack_n<32>(v, pk);
+          if (mok && nok) st_global<16>(a.out_bf16 + (size_t)m * a.ld_out + n, pk);
+        } else if (EPI == EPI_BIAS_GELU) {
+          uint32_t pk[16];
+          round_n<32>(v, pk);   // GELU of the bf16-rounded pre-activation backward re-reads
+          if (mok && nok) st_global<16>(a.out_bf16 + (size_t)m * a.ld_out + n, pk);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          pack_n<32>(v, pk);
+          if (mok && nok) st_global<16>(a.out2_bf16 + (size_t)m * a.ld_out + n, pk);
+        } else if (EPI == EPI_GELU_GRAD) {
+          uint32_t pk[16];
+          if (mok && nok) {
+            const bf16* ap = a.aux_bf16 + (size_t)m * a.ld_aux + n;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(ap + 8 * q));
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_bf162(w[i]);
+                v[8 * q + 2 * i] *= gelu_erf_grad(f.x); v[8 * q + 2 * i + 1] *= gelu_erf_grad(f.y);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          round_n<32>(v, pk);   // the bias gradient sums what the weight-gradient GEMM will see
+          if (mok && nok) st_global<16>(a.out_bf16 + (size_t)m * a.ld_out + n, pk);
+          if (a.colsum_part) {
+            // column sums over the 32 rows of this warp (recursive halving: 31 shuffles for 32 columns), then over the 4
+            // lane quadrants through smem
+            float a16[16], a8[8], a4[4], a2[2];
+            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float keep = h16 ? v[i + 16] : v[i], send = h16 ? v[i] : v[i + 16];
+              a16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float keep = h8 ? a16[i + 8] : a16[i], send = h8 ? a16[i] : a16[i + 8];
+              a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float keep = h4 ? a8[i + 4] : a8[i], send = h4 ? a8[i] : a8[i + 4];
+              a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float keep = h2 ? a4[i + 2] : a4[i], send = h2 ? a4[i] : a4[i + 2];
+              a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            const float keep = h1 ? a2[1] : a2[0], send = h1 ? a2[0] : a2[1];
+            const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            const int col = (h16 ? 16 : 0) + (h8 ? 8 : 0) + (h4 ? 4 : 0) + (h2 ? 2 : 0) + (h1 ? 1 : 0);   // == lane
+            sCol[(acc * 4 + quad) * TG_BN + half * 64 + c * 32 + col] = tot;
+          }
+        } else if (EPI == EPI_F32_RES) {
+          if (mok && nok) {
+            const float* rp = a.res_f32 + (size_t)m * a.ld_f32 + n;
+            float* op = a.out_f32 + (size_t)m * a.ld_f32 + n;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 r = *reinterpret_cast<const float4*>(rp + i);
+              *reinterpret_cast<float4*>(op + i) = make_float4(v[i] + r.x, v[i + 1] + r.y, v[i + 2] + r.z, v[i + 3] + r.w);
+            }
+          }
+        }
+      }
+      umma::fence_before_sync();
+      if (EPI == EPI_GELU_GRAD && a.colsum_part) {
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");   // the 8 epilogue warps: column partials of this tile complete
+        const int et = threadIdx.x - 64;
+        if (et < TG_BN && n0 + et < a.N) {
+          const float* sc = sCol + acc * 4 * TG_BN + et;
+          a.colsum_part[(size_t)mt * a.N + n0 + et] = (sc[0] + sc[TG_BN]) + (sc[2 * TG_BN] + sc[3 * TG_BN]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(tempty + acc);
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    umma::fence_after_sync();
+    umma::tmem_dealloc<256>(tmem);
+  }
+}
+
+bool tgemm_supported(int epi, const GemmArgs& a) {
+  if (getenv("B4R_DISABLE_TGEMM")) return false;
+  if (!(epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU || epi == EPI_GELU_GRAD || epi == EPI_BF16 || epi == EPI_F32_RES)) return false;
+  if (a.a_trans || a.a_rows || a.d_M || a.splits > 1) return false;
+  if (a.K % TG_BK || a.N % 64 || a.K < 128 || a.M < 256) return false;   // small / narrow problems stay on the portable kernel
+  if ((a.a_kmax && a.a_kmax != a.K) || (a.b_kmax && a.b_kmax != a.K)) return false;
+  if (a.lda % 8 || a.ldb % 8 || ((uintptr_t)a.A & 15) || ((uintptr_t)a.B & 15)) return false;
+  return true;
+}
+
+template <int EPI, bool B_MN>
+static cudaError_t launch_tgemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const TGemmDev& d, int grid, cudaStream_t st) {
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(tgemm_kernel<EPI, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
+    if (e != cudaSuccess) return e;
+    done = true;
+  }
+  tgemm_kernel<EPI, B_MN><<<grid, 320, TG_SMEM, st>>>(tmA, tmB, d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tgemm(int epi, const GemmArgs& a, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  if (!make_tmap_bf16_sw128(&tmA, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, TG_BM)) return cudaErrorInvalidValue;
+  const bool bmn = a.b_trans;   // b_trans: B memory is [K][N]
+  if (bmn ? !make_tmap_bf16_sw128(&tmB, a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64)
+          : !make_tmap_bf16_sw128(&tmB, a.B, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, TG_BN))
+    return cudaErrorInvalidValue;
+  TGemmDev d;
+  d.M = a.M; d.N = a.N; d.K = a.K; d.bias = a.bias; d.out_bf16 = a.out_bf16; d.ld_out = a.ld_out; d.out2_bf16 = a.out2_bf16;
+  d.aux_bf16 = a.aux_bf16; d.ld_aux = a.ld_aux; d.out_f32 = a.out_f32; d.ld_f32 = a.ld_f32; d.res_f32 = a.res_f32;
+  d.colsum_part = a.colsum_part;
+  const int tiles = ((a.M + TG_BM - 1) / TG_BM) * ((a.N + TG_BN - 1) / TG_BN);
+  const int grid = tiles < 148 ? tiles : 148;
+#define B4R_TG(E)                                                                                              \
+  case E:                                                                                                      \
+    return bmn ? launch_tgemm_t<E, true>(tmA, tmB, d, grid, st) : launch_tgemm_t<E, false>(tmA, tmB, d, grid, st);
+  switch (epi) {
+    B4R_TG(EPI_BIAS_BF16)
+    B4R_TG(EPI_BIAS_GELU)
+    B4R_TG(EPI_GELU_GRAD)
+    B4R_TG(EPI_BF16)
+    B4R_TG(EPI_F32_RES)
+  }
+#undef B4R_TG
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace b4r
+
+// ======================================================================================= weight gradient (generation 2)
+// dW[M,N] = X^T dY, contraction over the T token rows, for M, N multiples of 256 (hidden 256 models).  Both operands are
+// read in place as MN-major tiles ([64 token rows][64 features] TMA boxes); one CTA owns a 256 x 256 output tile (two
+// M = 128 accumulators of 256 TMEM columns each) and a contiguous range of token rows (split over T, deterministic fp32
+// partials summed by grad_reduce_kernel).  256 x 256 tiles read X N/256 times and dY M/256 times: HBM-bound by design.
+namespace b4r {
+using namespace encf;
+namespace {
+constexpr int TW_STAGES = 3, TW_STAGE = 2 * 64 * 256 * 2;   // 32 KB of X + 32 KB of dY per 64-token k-block
+constexpr int TW_SMEM = TW_STAGES * TW_STAGE + 256 + 1024;
+struct TWgradDev { int M, N, T, t_per_split, tiles_n; float* out; size_t split_stride; int ld_out; };
+}  // namespace
+
+__global__ void __launch_bounds__(320, 1) twgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                                                        TWgradDev a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TW_STAGES * TW_STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + TW_STAGES;
+  uint64_t* tfull = bars + 2 * TW_STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tfull + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, z = blockIdx.y;
+  const int m0 = (tile / a.tiles_n) * 256, n0 = (tile % a.tiles_n) * 256;
+  const int t_begin = z * a.t_per_split, t_end = min(a.T, t_begin + a.t_per_split);
+  const int kblocks = t_end > t_begin ? (t_end - t_begin + 63) / 64 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TW_STAGES; ++i) { umma::mbar_init(full + i, 1); umma::mbar_init(empty + i, 1); }
+    umma::mbar_init(tfull, 1);
+    umma::fence_barrier_init();
+    umma::prefetch_tensormap(&tmX);
+    umma::prefetch_tensormap(&tmY);
+  }
+  if (warp == 1) umma::tmem_alloc<512>(tmem_holder);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int st = kb % TW_STAGES;
+        umma::mbar_wait(empty + st, ((kb / TW_STAGES) & 1) ^ 1);
+        umma::mbar_expect_tx(full + st, TW_STAGE);
+        unsigned char* sA = smem + st * TW_STAGE;
+        unsigned char* sB = sA + TW_STAGE / 2;
+        const int t0 = t_begin + kb * 64;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          umma::tma_load_2d(sA + j * 8192, &tmX, m0 + j * 64, t0, full + st);
+          umma::tma_load_2d(sB + j * 8192, &tmY, n0 + j * 64, t0, full + st);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint64_t DMN0 = desc_mn_sw128(umma::smem_addr(smem), 8192);
+      constexpr uint32_t idesc = idesc_gen(128, 256, 1, 1);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int st = kb % TW_STAGES;
+        umma::mbar_wait(full + st, (kb / TW_STAGES) & 1);
+        umma::fence_after_sync();
+        const uint32_t offA = st * TW_STAGE, offB = offA + TW_STAGE / 2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            umma::mma_bf16_ss(tmem + h * 256, desc_at(DMN0, offA + h * 16384 + k * 2048), desc_at(DMN0, offB + k * 2048), idesc,
+                              (kb | k) ? 1u : 0u);
+        umma::mma_commit(empty + st);
+      }
+      umma::mma_commit(tfull);
+    }
+    __syncwarp();
+  } else {
+    // epilogue: warps 2..9 -> (lane quadrant, m-half); 256 fp32 columns per thread row
+    const int quad = warp & 3, h = (warp - 2) >> 2;
+    const int m = m0 + h * 128 + quad * 32 + lane;
+    float* dst = a.out + (size_t)z * a.split_stride + (size_t)m * a.ld_out + n0;
+    if (kblocks > 0) {
+      umma::mbar_wait(tfull, 0);
+      umma::fence_after_sync();
+    }
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      float v[32];
+      if (kblocks > 0) tmem_ld_f32(tmem + ((uint32_t)(quad * 32) << 16) + h * 256 + c * 32, v);
+      else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + c * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    umma::fence_after_sync();
+    umma::tmem_dealloc<512>(tmem);
+  }
+}
+
+bool twgrad_shape_ok(int M, int N, int T) { return !getenv("B4R_DISABLE_TGEMM") && M % 256 == 0 && N % 256 == 0 && T >= 4096; }
+int twgrad_splits(int M, int N, int T) {
+  const int tiles = (M / 256) * (N / 256);
+  int s = 148 / tiles;
+  const int cap = T / 512;   // at least 8 k-blocks per CTA
+  if (s > cap) s = cap;
+  return s < 1 ? 1 : s;
+}
+bool twgrad_supported(const WgradArgs& a) {
+  if (!twgrad_shape_ok(a.M, a.N, a.T)) return false;
+  if (a.x_rows || a.d_T || a.accumulate || a.splits < 1) return false;
+  if (a.ldx % 8 || a.ldy % 8 || ((uintptr_t)a.X & 15) || ((uintptr_t)a.dY & 15) || (a.ld_out % 4)) return false;
+  return true;
+}
+cudaError_t launch_twgrad(const WgradArgs& a, cudaStream_t st) {
+  CUtensorMap tmX, tmY;
+  if (!make_tmap_bf16_sw128(&tmX, a.X, (uint64_t)a.T, (uint64_t)a.M, (uint64_t)a.ldx, 64)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16_sw128(&tmY, a.dY, (uint64_t)a.T, (uint64_t)a.N, (uint64_t)a.ldy, 64)) return cudaErrorInvalidValue;
+  TWgradDev d;
+  d.M = a.M; d.N = a.N; d.T = a.T; d.tiles_n = a.N / 256; d.out = a.out; d.split_stride = a.split_stride; d.ld_out = a.ld_out;
+  d.t_per_split = ((a.T + a.splits - 1) / a.splits + 63) / 64 * 64;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(twgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM);
+    if (e != cudaSuccess) return e;
+    done = true;
+  }
+  dim3 grid((a.M / 256) * (a.N / 256), a.splits);
+  twgrad_kernel<<<grid, 320, TW_SMEM, st>>>(tmX, tmY, d);
+  return cudaGetLastError();
+}
+}  // namespace b4r

@@ -42,6 +42,9 @@ struct GemmArgs {
 };
 cudaError_t launch_gemm(int epi, const GemmArgs& a, cudaStream_t st);
 int gemm_block_m();  // BM of the generic kernel (for sizing colsum_part)
+// generation 2 (k_tgemm.cu): persistent tcgen05 GEMM with the same epilogues; launch_gemm dispatches to it when supported
+bool tgemm_supported(int epi, const GemmArgs& a);
+cudaError_t launch_tgemm(int epi, const GemmArgs& a, cudaStream_t st);
 
 // GEMM with a full-row epilogue (N == H in {64,128,256}), k_gemm.cu
 enum RowMode : int {
@@ -77,6 +80,11 @@ struct WgradArgs {
   int x_mmax;                                  // valid columns of X (multiple of 8; defaults to M rounded up)
 };
 cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t st);
+// generation 2 (k_tgemm.cu): tcgen05 weight gradient for M, N multiples of 256; launch_wgrad dispatches to it
+bool twgrad_shape_ok(int M, int N, int T);
+int twgrad_splits(int M, int N, int T);   // token-row splits (= partial buffers) the tcgen05 kernel wants
+bool twgrad_supported(const WgradArgs& a);
+cudaError_t launch_twgrad(const WgradArgs& a, cudaStream_t st);
 
 // ------------------------------------------------------------------ embedding (k_embed.cu)
 cudaError_t launch_embed_ln_fwd(const int64_t* ids, const bf16* table, const bf16* pos, const float* gamma,
