@@ -322,6 +322,7 @@ static cudaError_t launch_rowln_t(const RowLnArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_gemm_rowln(int mode, const RowLnArgs& a, cudaStream_t st) {
+  if (trowln_supported(mode, a)) return launch_trowln(a, st);   // generation 2: tcgen05 + TMEM + TMA
 #define B4R_ROW(HH)                                                                       \
   case HH:                                                                                \
     return mode == ROW_RES_DROP_LN ? launch_rowln_t<HH, ROW_RES_DROP_LN>(a, st) : launch_rowln_t<HH, ROW_GELU_LN>(a, st);

@@ -427,3 +427,213 @@ cudaError_t launch_twgrad(const WgradArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 }  // namespace b4r
+
+// ======================================================================================= GEMM + full-row epilogue (generation 2)
+// y = LayerNorm(drop(A W + bias) + residual) for hidden 256 (ROW_RES_DROP_LN of k_gemm.cu): one CTA tile = 128 whole
+// rows x 256 columns (a 256-column TMEM accumulator, double-buffered = all 512 columns), so the row statistics never
+// leave the CTA.  Epilogue thread = (row, 128-column half): pass 1 writes the bf16 pre-LN value and accumulates sum and
+// sum of squares, the two halves exchange them through shared memory, pass 2 re-reads the (L2-hot) pre-LN value and
+// normalises.  Same persistent producer / issuer / epilogue split as tgemm_kernel.
+namespace b4r {
+using namespace encf;
+namespace {
+constexpr int TR_STAGES = 4, TR_STAGE = 128 * 128 + 64 * 256 * 2;   // 16 KB of A + 32 KB of W per 64-wide k-block
+constexpr int TR_SMEM = TR_STAGES * TR_STAGE + 2 * 2 * 128 * 2 * 4 + 256 + 1024;
+struct TRowDev {
+  int M, K;
+  const float* bias; const float* gamma; const float* beta;
+  const bf16* residual; bf16* pre; bf16* y; float* mean; float* rstd;
+  uint32_t thr16; float inv_keep; unsigned long long seed; uint32_t site; uint32_t step; const long long* d_step;
+};
+}  // namespace
+
+__global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                                                        TRowDev a) {
+  constexpr int H = 256;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* sStat = reinterpret_cast<float*>(smem + TR_STAGES * TR_STAGE);   // [2 acc][2 halves][128 rows][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * 2 * 128 * 2);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + TR_STAGES;
+  uint64_t* tfull = bars + 2 * TR_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (a.M + 127) / 128, kblocks = a.K / 64;
+  const uint32_t step = a.step + (a.d_step ? (uint32_t)(*a.d_step) : 0u);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TR_STAGES; ++i) { umma::mbar_init(full + i, 1); umma::mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(tfull + i, 1); umma::mbar_init(tempty + i, 8); }
+    umma::fence_barrier_init();
+    umma::prefetch_tensormap(&tmA);
+    umma::prefetch_tensormap(&tmW);
+  }
+  if (warp == 1) umma::tmem_alloc<512>(tmem_holder);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int st = it % TR_STAGES;
+          umma::mbar_wait(empty + st, ((it / TR_STAGES) & 1) ^ 1);
+          umma::mbar_expect_tx(full + st, TR_STAGE);
+          unsigned char* sA = smem + st * TR_STAGE;
+          unsigned char* sB = sA + 128 * 128;
+          umma::tma_load_2d(sA, &tmA, kb * 64, t * 128, full + st);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) umma::tma_load_2d(sB + j * 8192, &tmW, j * 64, kb * 64, full + st);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint64_t DK0 = umma::make_desc_k_sw128(umma::smem_addr(smem));
+      const uint64_t DMN0 = desc_mn_sw128(umma::smem_addr(smem), 8192);
+      constexpr uint32_t idesc = idesc_gen(128, 256, 0, 1);
+      int it = 0, ti = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+        const int acc = ti & 1;
+        umma::mbar_wait(tempty + acc, ((ti >> 1) & 1) ^ 1);
+        umma::fence_after_sync();
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int st = it % TR_STAGES;
+          umma::mbar_wait(full + st, (it / TR_STAGES) & 1);
+          umma::fence_after_sync();
+          const uint32_t offA = st * TR_STAGE, offB = offA + 128 * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma::mma_bf16_ss(tmem + acc * 256, desc_at(DK0, offA + k * 32), desc_at(DMN0, offB + k * 2048), idesc, (kb | k) ? 1u : 0u);
+          umma::mma_commit(empty + st);
+        }
+        umma::mma_commit(tfull + acc);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int row_in_tile = quad * 32 + lane;
+    const Philox ph(a.seed);
+    int ti = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+      const int acc = ti & 1;
+      const int m = t * 128 + row_in_tile;
+      const bool mok = m < a.M;
+      umma::mbar_wait(tfull + acc, (ti >> 1) & 1);
+      umma::fence_after_sync();
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int n = half * 128 + c * 32;
+        float v[32];
+        tmem_ld_f32(tmem + ((uint32_t)(quad * 32) << 16) + acc * 256 + n, v);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n + i));
+          v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+        }
+        if (a.thr16 > 0 && mok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t bits = keep_bits8(ph, (uint32_t)m, (uint32_t)(n / 8 + q), a.site, step, a.thr16);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * q + i] = ((bits >> i) & 1u) ? v[8 * q + i] * a.inv_keep : 0.f;
+          }
+        }
+        if (mok) {
+          const bf16* rp = a.residual + (size_t)m * H + n;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + 8 * q));
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf162(w[i]); v[8 * q + 2 * i] += f.x; v[8 * q + 2 * i + 1] += f.y; }
+          }
+          uint32_t pk[16];
+          round_n<32>(v, pk);   // LN statistics are taken on the bf16-rounded value that backward will re-read
+          st_global<16>(a.pre + (size_t)m * H + n, pk);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 += v[i] * v[i]; }
+        }
+      }
+      // the accumulator has been read completely: hand it back to the MMA warp before the second pass
+      umma::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(tempty + acc);
+      float* st = sStat + ((acc * 2 + half) * 128 + row_in_tile) * 2;
+      st[0] = s1; st[1] = s2;
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      const float* so = sStat + ((acc * 2 + (half ^ 1)) * 128 + row_in_tile) * 2;
+      const float t1 = half == 0 ? s1 + so[0] : so[0] + s1, t2 = half == 0 ? s2 + so[1] : so[1] + s2;
+      const float mean = t1 * (1.0f / H);
+      const float var = fmaxf(t2 * (1.0f / H) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + kLnEps);
+      if (mok) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int n = half * 128 + c * 32;
+          const bf16* pp = a.pre + (size_t)m * H + n;
+          float v[32];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 u = *reinterpret_cast<const uint4*>(pp + 8 * q);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf162(w[i]); v[8 * q + 2 * i] = f.x; v[8 * q + 2 * i + 1] = f.y; }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma + n + i));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(a.beta + n + i));
+            v[i] = (v[i] - mean) * rstd * g.x + b.x; v[i + 1] = (v[i + 1] - mean) * rstd * g.y + b.y;
+            v[i + 2] = (v[i + 2] - mean) * rstd * g.z + b.z; v[i + 3] = (v[i + 3] - mean) * rstd * g.w + b.w;
+          }
+          uint32_t pk[16];
+          pack_n<32>(v, pk);
+          st_global<16>(a.y + (size_t)m * H + n, pk);
+        }
+        if (half == 0) { a.mean[m] = mean; a.rstd[m] = rstd; }
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    umma::fence_after_sync();
+    umma::tmem_dealloc<512>(tmem);
+  }
+}
+
+bool trowln_supported(int mode, const RowLnArgs& a) {
+  if (getenv("B4R_DISABLE_TGEMM")) return false;
+  if (mode != ROW_RES_DROP_LN || a.H != 256 || a.a_rows || a.d_M) return false;
+  if (a.K % 64 || a.K < 128 || a.M < 256 || a.lda % 8 || ((uintptr_t)a.A & 15) || ((uintptr_t)a.W & 15)) return false;
+  return true;
+}
+cudaError_t launch_trowln(const RowLnArgs& a, cudaStream_t st) {
+  CUtensorMap tmA, tmW;
+  if (!make_tmap_bf16_sw128(&tmA, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, 128)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16_sw128(&tmW, a.W, (uint64_t)a.K, 256, 256, 64)) return cudaErrorInvalidValue;
+  TRowDev d;
+  d.M = a.M; d.K = a.K; d.bias = a.bias; d.gamma = a.gamma; d.beta = a.beta; d.residual = a.residual; d.pre = a.pre; d.y = a.y;
+  d.mean = a.mean; d.rstd = a.rstd;
+  d.thr16 = drop_threshold16(a.drop_rate);
+  d.inv_keep = 1.0f / (1.0f - (float)d.thr16 / 65536.0f);
+  d.seed = a.seed; d.site = a.site; d.step = a.step; d.d_step = a.d_step;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(trowln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM);
+    if (e != cudaSuccess) return e;
+    done = true;
+  }
+  const int tiles = (a.M + 127) / 128;
+  trowln_kernel<<<tiles < 148 ? tiles : 148, 320, TR_SMEM, st>>>(tmA, tmW, d);
+  return cudaGetLastError();
+}
+}  // namespace b4r

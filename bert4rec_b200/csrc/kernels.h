@@ -67,6 +67,9 @@ struct RowLnArgs {
   const long long* d_step;                     // optional device counter added to step (CUDA-graph replays)
 };
 cudaError_t launch_gemm_rowln(int mode, const RowLnArgs& a, cudaStream_t st);
+// generation 2 (k_tgemm.cu): tcgen05 GEMM + residual/dropout/LayerNorm epilogue for hidden 256; launch_gemm_rowln dispatches
+bool trowln_supported(int mode, const RowLnArgs& a);
+cudaError_t launch_trowln(const RowLnArgs& a, cudaStream_t st);
 
 // Weight-gradient GEMM: out[split][M][N] = sum_{t in split} X[t][m] * dY[t][n]   (both operands "transposed")
 struct WgradArgs {
