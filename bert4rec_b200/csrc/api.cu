@@ -231,7 +231,7 @@ struct b4r_session {
   int launches;
 };
 
-static const int kColsumSplits = 64;
+static const int kColsumSplits = 296;   // CTAs (= partial rows) of the bias-gradient column sums: two per SM
 static int wgrad_splits(int M, int N, int T) {
   if (twgrad_shape_ok(M, N, T)) return twgrad_splits(M, N, T);   // the tcgen05 kernel's own split count
   int tiles = ((M + 63) / 64) * ((N + 63) / 64);
