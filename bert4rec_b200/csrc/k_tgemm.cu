@@ -3,7 +3,7 @@
 //   warp 0    : TMA producer -- A tile [128 rows][64 k] and B tile through a 4-stage shared-memory ring (SWIZZLE_128B)
 //   warp 1    : MMA issuer (one elected lane): 4 x (M128 N128 K16) per k-block into one of TWO 128-column fp32
 //               accumulators in TMEM, so the epilogue of tile i overlaps the main loop of tile i+1
-//   warps 2-9 : epilogue, thread = (accumulator row, 64-column half): tcgen05.ld 32 columns at a time -> bias / GELU /
+//   warps 2-17: epilogue, thread = (accumulator row, 32-column part): one tcgen05.ld of 32 columns -> bias / GELU /
 //               GELU' (+ per-tile column sums = bias gradient) / fp32 residual -> global
 // B is consumed in place in either layout: [K,N] row-major (forward: TF kernels are [in,out]) as an MN-major operand,
 // [N,K] row-major (data gradients read the SAME weights transposed) as a K-major operand -- no transposed copies.
@@ -21,6 +21,7 @@ using namespace encf;
 
 namespace {
 constexpr int TG_BM = 128, TG_BN = 128, TG_BK = 64, TG_STAGES = 4;
+constexpr int TG_EPI_WARPS = 16, TG_THREADS = 64 + 32 * TG_EPI_WARPS;   // producer + issuer + 16 epilogue warps
 constexpr int TG_A_BYTES = TG_BM * 128, TG_B_BYTES = TG_BN * 128, TG_STAGE = TG_A_BYTES + TG_B_BYTES;
 constexpr int TG_SMEM = TG_STAGES * TG_STAGE + 2 * 4 * TG_BN * 4 + 256 + 1024;   // ring + column-sum scratch + barriers + align
 
@@ -37,7 +38,7 @@ struct TGemmDev {
 }  // namespace
 
 template <int EPI, bool B_MN>
-__global__ void __launch_bounds__(320, 1) tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                        TGemmDev a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(320, 1) tgemm_kernel(const __grid_constant__ C
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TG_STAGES; ++i) { umma::mbar_init(full + i, 1); umma::mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(tfull + i, 1); umma::mbar_init(tempty + i, 8); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(tfull + i, 1); umma::mbar_init(tempty + i, TG_EPI_WARPS); }
     umma::fence_barrier_init();
     umma::prefetch_tensormap(&tmA);
     umma::prefetch_tensormap(&tmB);
@@ -117,8 +118,8 @@ __global__ void __launch_bounds__(320, 1) tgemm_kernel(const __grid_constant__ C
     }
     __syncwarp();
   } else {
-    // ===================================================================== epilogue (warps 2..9)
-    const int quad = warp & 3, half = (warp - 2) >> 2;
+    // ===================================================================== epilogue (warps 2..17): (lane quadrant, 32-column part)
+    const int quad = warp & 3, cpart = (warp - 2) >> 2;
     const int row_in_tile = quad * 32 + lane;
     int ti = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
@@ -128,11 +129,10 @@ __global__ void __launch_bounds__(320, 1) tgemm_kernel(const __grid_constant__ C
       const bool mok = m < a.M;
       umma::mbar_wait(tfull + acc, (ti >> 1) & 1);
       umma::fence_after_sync();
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        const int n = n0 + half * 64 + c * 32;           // first of this thread's 32 columns
+      {
+        const int n = n0 + cpart * 32;                   // first of this thread's 32 columns
         float v[32];
-        tmem_ld_f32(tmem + ((uint32_t)(quad * 32) << 16) + acc * TG_BN + half * 64 + c * 32, v);
+        tmem_ld_f32(tmem + ((uint32_t)(quad * 32) << 16) + acc * TG_BN + cpart * 32, v);
         const bool nok = n < a.N;                         // N is a multiple of 32 on this path
         if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU) {
           if (nok) {
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(320, 1) tgemm_kernel(const __grid_constant__ C
             const float keep = h1 ? a2[1] : a2[0], send = h1 ? a2[0] : a2[1];
             const float tot = keep + __shfl_xor_sync(0xffffffffu, send, 1);
             const int col = (h16 ? 16 : 0) + (h8 ? 8 : 0) + (h4 ? 4 : 0) + (h2 ? 2 : 0) + (h1 ? 1 : 0);   // == lane
-            sCol[(acc * 4 + quad) * TG_BN + half * 64 + c * 32 + col] = tot;
+            sCol[(acc * 4 + quad) * TG_BN + cpart * 32 + col] = tot;
           }
         } else if (EPI == EPI_F32_RES) {
           if (mok && nok) {
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(320, 1) tgemm_kernel(const __grid_constant__ C
       }
       umma::fence_before_sync();
       if (EPI == EPI_GELU_GRAD && a.colsum_part) {
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");   // the 8 epilogue warps: column partials of this tile complete
+        asm volatile("bar.sync 1, 512;\n" ::: "memory");   // the 16 epilogue warps: column partials of this tile complete
         const int et = threadIdx.x - 64;
         if (et < TG_BN && n0 + et < a.N) {
           const float* sc = sCol + acc * 4 * TG_BN + et;
@@ -256,7 +256,7 @@ static cudaError_t launch_tgemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB
     if (e != cudaSuccess) return e;
     done = true;
   }
-  tgemm_kernel<EPI, B_MN><<<grid, 320, TG_SMEM, st>>>(tmA, tmB, d);
+  tgemm_kernel<EPI, B_MN><<<grid, TG_THREADS, TG_SMEM, st>>>(tmA, tmB, d);
   return cudaGetLastError();
 }
 
