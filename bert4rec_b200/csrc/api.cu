@@ -356,8 +356,9 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
   }
   {
     int vtiles = (V + 127) / 128;
-    s->dt_max_splits = vtiles < 24 ? vtiles : 24;
-    int ms = (2 * 148) / vtiles;
+    const int xtiles = (V + ce_bwd_umma_xtile(H) - 1) / ce_bwd_umma_xtile(H);
+    s->dt_max_splits = xtiles < 24 ? xtiles : 24;
+    int ms = (ce_bwd_umma_xtile(H) == 64 ? 148 : 2 * 148) / vtiles;   // resident CTAs: two per SM, one at hidden 256
     if (ms < 1) ms = 1;
     if (ms > 8) ms = 8;
     s->me_splits = ms;
@@ -671,6 +672,7 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
   const float od = s->cfg.output_dropout;
   const int64_t oE = s->lay.find("word_embeddings");
   const bool bwd_umma = s->use_umma && ce_bwd_umma_supported(H);
+  const int ce_xt = ce_bwd_umma_xtile(H), ce_xtiles = (V + ce_xt - 1) / ce_xt, ce_ctas = ce_xt == 64 ? 148 : 2 * 148;
   // gradient accumulators that are scatter / accumulate targets
   if (!bwd_umma) CK(cudaMemsetAsync(G + oE, 0, (size_t)V * H * sizeof(float), st));
   CK(cudaMemsetAsync(s->dxa, 0, (size_t)T * H * sizeof(float), st));
@@ -681,7 +683,7 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
     // ---- CE backward, generation 2: two tcgen05 passes that recompute the logits tile, nothing [M,V]-sized in memory
     CeBwdArgs ba{};
     ba.vbias = c.vbias; ba.lse = s->lse; ba.row_w = s->row_w; ba.labels = s->labels; ba.d_counts = s->counts;
-    ba.M_cap = Mcap; ba.V = V; ba.H = H; ba.target_ctas = 2 * 148; ba.max_splits = s->dt_max_splits; ba.msplits = s->me_splits;
+    ba.M_cap = Mcap; ba.V = V; ba.H = H; ba.target_ctas = ce_ctas; ba.max_splits = s->dt_max_splits; ba.msplits = s->me_splits;
     ba.out = s->dt_part; ba.dbias_out = nullptr;
     KL("ce_bwd_umma:dT", launch_ce_bwd_umma(s->umaps, ba, true, st));
     if (head_bwd_fused_supported(H)) {
@@ -693,7 +695,7 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
         cudaStream_t st = s->side;
         KL("head_bwd_fused", launch_head_bwd_fused(s->dt_part, s->dt_splits, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
                                  P + s->lay.find("head/ln/gamma"), W + s->lay.find("head/wt"), s->layers.back().out, s->rows, s->counts,
-                                 Mcap, s->dxa, s->p_head_ln, s->p_wt, st, (V + 127) / 128, 2 * 148, s->dt_max_splits));
+                                 Mcap, s->dxa, s->p_head_ln, s->p_wt, st, ce_xtiles, ce_ctas, s->dt_max_splits));
       }
       CK(cudaEventRecord(s->ev_join, s->side));
       head_done = true;
@@ -728,12 +730,12 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
   } else if (head_bwd_fused_supported(H)) {
     KL("head_bwd_fused", launch_head_bwd_fused(s->dt_part, s->dt_splits, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
                              P + s->lay.find("head/ln/gamma"), W + s->lay.find("head/wt"), xL, s->rows, s->counts, Mcap, s->dxa,
-                             s->p_head_ln, s->p_wt, st, bwd_umma ? (V + 127) / 128 : 0, bwd_umma ? 2 * 148 : 0,
+                             s->p_head_ln, s->p_wt, st, bwd_umma ? ce_xtiles : 0, bwd_umma ? ce_ctas : 0,
                              bwd_umma ? s->dt_max_splits : 0));
   } else {
   KL("head_bwd_rows", launch_head_bwd_rows(s->dt_part, s->dt_splits, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
                           P + s->lay.find("head/ln/gamma"), s->d_tpre, s->p_head_ln, Mcap, s->counts, H, st,
-                          bwd_umma ? (V + 127) / 128 : 0, bwd_umma ? 2 * 148 : 0, bwd_umma ? s->dt_max_splits : 0));
+                          bwd_umma ? ce_xtiles : 0, bwd_umma ? ce_ctas : 0, bwd_umma ? s->dt_max_splits : 0));
   {
     WgradArgs w{};
     w.X = xL; w.ldx = H; w.x_rows = s->rows; w.dY = s->d_tpre; w.ldy = H; w.M = H; w.N = H; w.T = Mcap;

@@ -20,7 +20,7 @@
 
 namespace b4r {
 
-constexpr int CB_T = 128;  // tile edge (rows of R, rows of X)
+constexpr int CB_T = 128;  // rows of the resident tile R (and of X for hidden <= 128; hidden 256 streams 64-row X tiles)
 
 __device__ __forceinline__ float ex2f_approx(float x) {
   float y;
@@ -56,13 +56,15 @@ struct CeBwdDev {
 template <int H>
 struct CeBwdCfg {
   static constexpr int KB = H / 64;
+  static constexpr int XT = H <= 128 ? 128 : 64;           // rows of a streamed X tile (= columns of the S / dl tile)
   static constexpr int XSTAGES = H == 64 ? 3 : 2;
   static constexpr int R_BYTES = KB * CB_T * 128;
-  static constexpr int X_BYTES = KB * CB_T * 128;
-  static constexpr int DL_BYTES = 2 * CB_T * 128;          // [128][128] bf16 as two [128][64] sub-tiles
+  static constexpr int X_BYTES = KB * XT * 128;
+  static constexpr int DL_BYTES = (XT / 64) * CB_T * 128;  // [128][XT] bf16 as [128][64] sub-tiles
   static constexpr int VEC_BYTES = 2 * 3 * CB_T * 4;       // double-buffered per-column vectors (3 x 128 x 4 B)
   static constexpr int SMEM = R_BYTES + XSTAGES * X_BYTES + DL_BYTES + VEC_BYTES + 256 + 1024;
-  static constexpr int TMEM_COLS = 256;                    // S (128) + ACC (H <= 128)
+  static constexpr int TMEM_COLS = XT + H <= 256 ? 256 : 512;   // S (XT) + ACC (H)
+  static constexpr int CTAS_PER_SM = TMEM_COLS == 256 ? 2 : 1;
 };
 
 __host__ __device__ inline int ce_bwd_dyn_splits(int n_rows, int ntiles, int target_ctas, int max_splits) {
@@ -76,10 +78,10 @@ __host__ __device__ inline int ce_bwd_dyn_splits(int n_rows, int ntiles, int tar
 }
 
 template <int H, bool ROW_IS_M>
-__global__ void __launch_bounds__(320, 2) ce_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmT,
+__global__ void __launch_bounds__(320, CeBwdCfg<H>::CTAS_PER_SM) ce_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmT,
                                                              const __grid_constant__ CUtensorMap tmE, CeBwdDev a) {
   using Cfg = CeBwdCfg<H>;
-  constexpr int KB = Cfg::KB, XS = Cfg::XSTAGES;
+  constexpr int KB = Cfg::KB, XS = Cfg::XSTAGES, XT = Cfg::XT;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sR = smem;
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(320, 2) ce_bwd_umma_kernel(const __grid_consta
   // ---- work assignment
   int r0, x_lo, x_hi, split;  // R tile start row, streamed tile range [x_lo, x_hi), partial slot
   if (ROW_IS_M) {
-    const int ntiles = (a.V + CB_T - 1) / CB_T;
+    const int ntiles = (a.V + XT - 1) / XT;
     const int vs = ce_bwd_dyn_splits(n_rows, ntiles, a.target_ctas, a.max_splits);
     const int mtile = blockIdx.x / vs;
     split = blockIdx.x % vs;
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(320, 2) ce_bwd_umma_kernel(const __grid_consta
     const int vtile = blockIdx.x / a.msplits;
     split = blockIdx.x % a.msplits;
     r0 = vtile * CB_T;
-    const int mt = (n_rows + CB_T - 1) / CB_T;
+    const int mt = (n_rows + XT - 1) / XT;
     const int per = (mt + a.msplits - 1) / a.msplits;
     x_lo = split * per; x_hi = min(mt, x_lo + per);
     if (x_lo >= x_hi) {  // empty row range: this partial slot must still be defined
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(320, 2) ce_bwd_umma_kernel(const __grid_consta
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem_base = *tmem_holder;
-  const uint32_t tmem_s = tmem_base, tmem_acc = tmem_base + CB_T;
+  const uint32_t tmem_s = tmem_base, tmem_acc = tmem_base + XT;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -167,14 +169,14 @@ __global__ void __launch_bounds__(320, 2) ce_bwd_umma_kernel(const __grid_consta
         const int st = i % XS;
         umma::mbar_wait(xempty + st, ((i / XS) & 1) ^ 1);
         umma::mbar_expect_tx(xfull + st, Cfg::X_BYTES);
-        const int xr0 = (x_lo + i) * CB_T;
-        for (int kb = 0; kb < KB; ++kb) umma::tma_load_2d(sX + st * Cfg::X_BYTES + kb * CB_T * 128, mapX, kb * 64, xr0, xfull + st);
+        const int xr0 = (x_lo + i) * XT;
+        for (int kb = 0; kb < KB; ++kb) umma::tma_load_2d(sX + st * Cfg::X_BYTES + kb * XT * 128, mapX, kb * 64, xr0, xfull + st);
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0 && my_tiles > 0) {
-      constexpr uint32_t idesc1 = umma::make_idesc_bf16(CB_T, CB_T);
+      constexpr uint32_t idesc1 = umma::make_idesc_bf16(CB_T, XT);
       constexpr uint32_t idesc2 = make_idesc_bf16_bmn(CB_T, H);
       umma::mbar_wait(rfull, 0);
       for (int i = 0; i < my_tiles; ++i) {
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(320, 2) ce_bwd_umma_kernel(const __grid_consta
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma::mma_bf16_ss(tmem_s, umma::make_desc_k_sw128(r_addr + k * 32),
-                              umma::make_desc_k_sw128(x_addr + kb * CB_T * 128 + k * 32), idesc1, (kb | k) ? 1u : 0u);
+                              umma::make_desc_k_sw128(x_addr + kb * XT * 128 + k * 32), idesc1, (kb | k) ? 1u : 0u);
         }
         umma::mma_commit(s_full);
         // second MMA: ACC += dl (K-major, K = the 128 streamed rows) . X (MN-major: N = H feature columns)
@@ -197,9 +199,9 @@ __global__ void __launch_bounds__(320, 2) ce_bwd_umma_kernel(const __grid_consta
         umma::fence_after_sync();
         const uint32_t dl_addr = umma::smem_addr(sDl);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
+        for (int kk = 0; kk < XT / 16; ++kk)
           umma::mma_bf16_ss(tmem_acc, umma::make_desc_k_sw128(dl_addr + (kk >> 2) * CB_T * 128 + (kk & 3) * 32),
-                            make_desc_mn_sw128(x_addr + kk * 16 * 128, CB_T * 128), idesc2, (i | kk) ? 1u : 0u);
+                            make_desc_mn_sw128(x_addr + kk * 16 * 128, XT * 128), idesc2, (i | kk) ? 1u : 0u);
         umma::mma_commit(xempty + st);
         umma::mma_commit(dl_empty);
       }
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(320, 2) ce_bwd_umma_kernel(const __grid_consta
     //   else    : v0[c] = lse[m]*log2e, v1[c] = w[m] (0 beyond n_rows), v2[c] = label[m] (as int bits)
     float pre0 = 0.f, pre1 = 0.f, pre2 = 0.f;
     auto fetch = [&](int tile_idx) {
-      const int c = (x_lo + tile_idx) * CB_T + et;
+      const int c = (x_lo + tile_idx) * XT + et;
       if (ROW_IS_M) {
         pre0 = c < a.V ? a.vbias[c] * LOG2E : -INFINITY;
       } else {
@@ -242,20 +244,20 @@ __global__ void __launch_bounds__(320, 2) ce_bwd_umma_kernel(const __grid_consta
       d[et] = pre0;
       if (!ROW_IS_M) { d[CB_T + et] = pre1; d[2 * CB_T + et] = pre2; }
     };
-    if (et < CB_T && my_tiles > 0) { fetch(0); stash(0); }
+    if (et < XT && my_tiles > 0) { fetch(0); stash(0); }
     for (int i = 0; i < my_tiles; ++i) {
       const int buf = i & 1;
-      if (et < CB_T && i + 1 < my_tiles) fetch(i + 1);
+      if (et < XT && i + 1 < my_tiles) fetch(i + 1);
       asm volatile("bar.sync 1, 256;\n" ::: "memory");  // vectors of tile i visible; buffer buf^1 free
       umma::mbar_wait(s_full, i & 1);
       umma::fence_after_sync();
       umma::mbar_wait(dl_empty, (i & 1) ^ 1);           // MMA2 of the previous tile has consumed the dl tile
-      const float* vec = sVec + buf * 3 * CB_T + half * 64;
-      const int x0 = (x_lo + i) * CB_T + half * 64;     // first streamed row (= S column) of this thread's half
+      const float* vec = sVec + buf * 3 * CB_T + half * (XT / 2);
+      const int x0 = (x_lo + i) * XT + half * (XT / 2);   // first streamed row (= S column) of this thread's half
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < XT / 64; ++c) {
         uint32_t r[32];
-        umma::tmem_ld32(tmem_s + ((uint32_t)(quad * 32) << 16) + half * 64 + c * 32, r);
+        umma::tmem_ld32(tmem_s + ((uint32_t)(quad * 32) << 16) + half * (XT / 2) + c * 32, r);
         umma::tmem_ld_wait();
         uint32_t pk[16];
         if (ROW_IS_M) {
@@ -288,10 +290,11 @@ __global__ void __launch_bounds__(320, 2) ce_bwd_umma_kernel(const __grid_consta
           }
         }
         // row-contiguous store into the 128B-swizzled K-major sub-tile `half`: 16-byte chunk q -> q ^ (row & 7)
-        unsigned char* rowp = sDl + half * (CB_T * 128) + row_in_tile * 128;
+        const int dcol = half * (XT / 2) + c * 32;   // first dl column of this chunk: sub-tile dcol / 64, 16-byte chunk (dcol % 64) / 8
+        unsigned char* rowp = sDl + (dcol >> 6) * (CB_T * 128) + row_in_tile * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int chunk = (c * 4 + q) ^ (row_in_tile & 7);
+          const int chunk = (((dcol & 63) >> 3) + q) ^ (row_in_tile & 7);
           *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
       }
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(320, 2) ce_bwd_umma_kernel(const __grid_consta
       umma::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       __syncwarp();
       if (lane == 0) { umma::mbar_arrive(s_empty); umma::mbar_arrive(dl_full); }
-      if (et < CB_T && i + 1 < my_tiles) stash(buf ^ 1);
+      if (et < XT && i + 1 < my_tiles) stash(buf ^ 1);
     }
     // ---- accumulator -> global partial
     umma::mbar_wait(acc_full, 0);
@@ -336,9 +339,10 @@ __global__ void __launch_bounds__(320, 2) ce_bwd_umma_kernel(const __grid_consta
   }
 }
 
-bool ce_bwd_umma_supported(int H) { return H == 64 || H == 128; }
+bool ce_bwd_umma_supported(int H) { return H == 64 || H == 128 || H == 256; }
+int ce_bwd_umma_xtile(int H) { return H <= 128 ? 128 : 64; }
 int ce_bwd_umma_dt_splits(int n_rows, int V, int target_ctas, int max_splits) {
-  return ce_bwd_dyn_splits(n_rows, (V + CB_T - 1) / CB_T, target_ctas, max_splits);
+  return ce_bwd_dyn_splits(n_rows, (V + CB_T - 1) / CB_T, target_ctas, max_splits);   // (callers pass the X-tile count themselves)
 }
 
 template <int H, bool ROW_IS_M>
@@ -357,12 +361,15 @@ cudaError_t launch_ce_bwd_umma(const CeUmmaMaps& maps, const CeBwdArgs& a, bool 
   d.vbias = a.vbias; d.lse = a.lse; d.row_w = a.row_w; d.labels = a.labels; d.d_counts = a.d_counts;
   d.M_cap = a.M_cap; d.V = a.V; d.target_ctas = a.target_ctas; d.max_splits = a.max_splits; d.msplits = a.msplits;
   d.out = a.out; d.dbias_out = a.dbias_out;
-  const CUtensorMap& tmT = *reinterpret_cast<const CUtensorMap*>(maps.a);
-  const CUtensorMap& tmE = *reinterpret_cast<const CUtensorMap*>(maps.b);
+  // resident operand: 128-row boxes; streamed operand: XT-row boxes (64 for hidden 256)
+  const bool x64 = ce_bwd_umma_xtile(a.H) == 64;
+  const CUtensorMap& tmT = *reinterpret_cast<const CUtensorMap*>(row_is_m || !x64 ? maps.a : maps.a64);
+  const CUtensorMap& tmE = *reinterpret_cast<const CUtensorMap*>(!row_is_m || !x64 ? maps.b : maps.b64);
   const int mtiles_cap = (a.M_cap + CB_T - 1) / CB_T, vtiles = (a.V + CB_T - 1) / CB_T;
   const int grid = row_is_m ? a.target_ctas + mtiles_cap : vtiles * a.msplits;
   if (a.H == 64) return row_is_m ? launch_ce_bwd_t<64, true>(tmT, tmE, d, grid, st) : launch_ce_bwd_t<64, false>(tmT, tmE, d, grid, st);
   if (a.H == 128) return row_is_m ? launch_ce_bwd_t<128, true>(tmT, tmE, d, grid, st) : launch_ce_bwd_t<128, false>(tmT, tmE, d, grid, st);
+  if (a.H == 256) return row_is_m ? launch_ce_bwd_t<256, true>(tmT, tmE, d, grid, st) : launch_ce_bwd_t<256, false>(tmT, tmE, d, grid, st);
   return cudaErrorInvalidValue;
 }
 

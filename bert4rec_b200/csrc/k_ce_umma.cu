@@ -254,6 +254,8 @@ bool ce_umma_make_maps(CeUmmaMaps* maps, const bf16* t, int M_cap, const bf16* E
   static_assert(sizeof(CUtensorMap) == sizeof(maps->a), "CUtensorMap size");
   bool ok = make_tmap_bf16_sw128(reinterpret_cast<CUtensorMap*>(maps->a), t, (uint64_t)M_cap, (uint64_t)H, (uint64_t)H, UM_BM);
   ok = ok && make_tmap_bf16_sw128(reinterpret_cast<CUtensorMap*>(maps->b), E, (uint64_t)V, (uint64_t)H, (uint64_t)H, UM_BN);
+  ok = ok && make_tmap_bf16_sw128(reinterpret_cast<CUtensorMap*>(maps->a64), t, (uint64_t)M_cap, (uint64_t)H, (uint64_t)H, 64);
+  ok = ok && make_tmap_bf16_sw128(reinterpret_cast<CUtensorMap*>(maps->b64), E, (uint64_t)V, (uint64_t)H, (uint64_t)H, 64);
   return ok;
 }
 

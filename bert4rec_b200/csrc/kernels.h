@@ -229,7 +229,9 @@ cudaError_t launch_ce_dlogits(const CeArgs& a, cudaStream_t st);
 cudaError_t launch_ce_count(const CeArgs& a, const float* s_gt, int* beat, cudaStream_t st);
 int ce_block_m();
 // generation 2 (tcgen05 + TMA) forward; maps are created once per session on the host
-struct CeUmmaMaps { alignas(64) unsigned char a[128]; alignas(64) unsigned char b[128]; };
+struct CeUmmaMaps {   // a: t rows, b: E rows (128-row boxes); a64 / b64: 64-row boxes (streamed operand of the hidden-256 backward)
+  alignas(64) unsigned char a[128]; alignas(64) unsigned char b[128]; alignas(64) unsigned char a64[128]; alignas(64) unsigned char b64[128];
+};
 bool ce_umma_make_maps(CeUmmaMaps* maps, const bf16* t, int M_cap, const bf16* E, int V, int H);
 cudaError_t launch_ce_fwd_umma(const CeUmmaMaps& maps, const CeArgs& a, cudaStream_t st);
 int ce_umma_block_m();
@@ -242,6 +244,7 @@ struct CeBwdArgs {
   float* out; float* dbias_out;
 };
 bool ce_bwd_umma_supported(int H);
+int ce_bwd_umma_xtile(int H);   // rows of a streamed tile (128, or 64 for hidden 256): the unit of the vocabulary split count
 cudaError_t launch_ce_bwd_umma(const CeUmmaMaps& maps, const CeBwdArgs& a, bool row_is_m, cudaStream_t st);
 // MLM transform backward over rows: dt = sum_s dt_part[s] ; LN bwd ; gelu bwd -> d_tpre (bf16) ; partials {dgamma,dbeta,dbias}
 cudaError_t launch_head_bwd_rows(const float* dt_part, int nsplit, size_t split_stride, const bf16* t_pre,

@@ -436,7 +436,7 @@ def test_ce_forward_tcgen05_matches_mma_sync_generation(name):
     assert abs(float(a[2]) - float(b[2])) <= 1 and abs(float(a[3]) - float(b[3])) <= 1
 
 
-@pytest.mark.parametrize("name", ["h64_s50", "h64_s200", "h128_s37"])
+@pytest.mark.parametrize("name", ["h64_s50", "h64_s200", "h128_s37", "h256_d64"])
 def test_ce_backward_tcgen05_matches_materialised_generation(name):
     """Generation 2 CE backward (two tcgen05 recompute passes, nothing [M,V]-sized in memory) against generation 1
     (bf16 dlogits materialised + mma.sync GEMMs): all parameter gradients agree to bf16 noise."""
