@@ -192,6 +192,7 @@ static size_t attn_fwd_smem(int S, int D) {
 }
 
 cudaError_t launch_attn_fwd(const AttnArgs& a, cudaStream_t st) {
+  if (tattn_fwd_supported(a)) return launch_tattn_fwd(a, st);   // generation 2: tcgen05 + TMEM + TMA
   const int D = a.H / a.N;
   if (a.S > 256 || (D != 32 && D != 64)) return cudaErrorInvalidValue;
   uint32_t thr = drop_threshold16(a.drop_rate);

@@ -117,6 +117,9 @@ struct AttnArgs {
 cudaError_t launch_attn_fwd(const AttnArgs& a, cudaStream_t st);
 cudaError_t launch_attn_bwd(const AttnArgs& a, cudaStream_t st);
 int attn_mask_words(int S);
+// generation 2 forward (k_tattn.cu): tcgen05 + TMEM + TMA, seq_len <= 256; launch_attn_fwd dispatches to it
+bool tattn_fwd_supported(const AttnArgs& a);
+cudaError_t launch_tattn_fwd(const AttnArgs& a, cudaStream_t st);
 
 // ------------------------------------------------------------------ fused encoder forward (k_enc_fused.cu)
 // Whole encoder stack in one launch (tcgen05 + TMEM + TMA), hidden 64 / 2 heads / seq_len <= 128 / inner_dim % 64 == 0.

@@ -60,3 +60,47 @@ def test_tcgen05_gemm_matches_mma_sync_generation(name, kw, B, S, P, dropout):
         if not d <= 2e-2 * float(g.norm()) + 1e-6 * gmax:
             bad.append((k, d, float(g.norm())))
     assert not bad, (name, bad)
+
+
+@pytest.mark.parametrize("name,kw,B,S,P", [
+    ("h64_s200_two_key_tiles", dict(vocab_size=1203, hidden_size=64, num_layers=2, num_attention_heads=2, max_sequence_length=200,
+                                    inner_dim=256), 7, 200, 20),
+    ("h256_d64_s72", dict(vocab_size=2001, hidden_size=256, num_layers=1, num_attention_heads=4, max_sequence_length=72,
+                          inner_dim=512), 5, 72, 8),
+    ("h128_d32_s130", dict(vocab_size=515, hidden_size=128, num_layers=1, num_attention_heads=4, max_sequence_length=130,
+                           inner_dim=256), 4, 130, 9),
+])
+@pytest.mark.parametrize("dropout", [0.0, 0.25])
+def test_tcgen05_attention_forward_matches_mma_sync_generation(name, kw, B, S, P, dropout):
+    """Layered path: tcgen05 attention forward (k_tattn.cu) against attn_fwd_kernel: context, log-sum-exp, keep bits."""
+    from bert4rec_b200.engine import ParamStore
+    outs = []
+    for disable in (True, False):
+        if disable:
+            os.environ.pop("B4R_ENABLE_TATTN", None)
+        else:
+            os.environ["B4R_ENABLE_TATTN"] = "1"     # opt-in kernel (see k_tattn.cu)
+        os.environ["B4R_DISABLE_FUSED"] = "1"
+        try:
+            store = ParamStore(device="cuda:0", output_dropout=dropout, attention_dropout=dropout, **kw)
+            store.init_weights(11)
+            store.ensure_training_buffers()
+            cb = to_cuda(make_batch(B, S, P, kw["vocab_size"], seed=37))
+            sess = store.session(B, S, P)
+            sess.encode(cb["input_word_ids"], cb["input_mask"], training=True, seed=9, step=4)
+            torch.cuda.synchronize()
+            o = {"ctx": sess.layer_tensor(0, "ctx").float().clone(), "lse": sess.layer_tensor(0, "lse").float().clone(),
+                 "out": sess.sequence_output().float().clone()}
+            if dropout > 0:
+                o["keep"] = sess.attn_keep_mask(0).clone()
+            outs.append(o)
+        finally:
+            os.environ.pop("B4R_ENABLE_TATTN", None)
+            os.environ.pop("B4R_DISABLE_FUSED", None)
+    ref, got = outs
+    if dropout > 0:
+        assert torch.equal(ref["keep"], got["keep"])
+    for k in ("ctx", "lse", "out"):
+        scale = float(ref[k].abs().max()) + 1e-6
+        err = float((got[k] - ref[k]).abs().max())
+        assert err <= 2.5e-2 * scale, (name, k, err, scale)
