@@ -336,7 +336,7 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
   s->ce_part = b.take<float>((size_t)(s->vsplits > s->vsplits_umma ? s->vsplits : s->vsplits_umma) * Mcap * 6);
   s->lse = b.take<float>(Mcap); s->lab = b.take<float>(Mcap);
   s->stats = b.take<float>(8); s->step_stats = b.take<float>(8);
-  s->fin_part = b.take<float>((size_t)(Mcap / 128 + 64) * 5); s->ticket = b.take<int>(Mcap / 128 + 8);
+  s->fin_part = b.take<float>(64 * 5); s->ticket = b.take<int>(4);
   {
     // dlogits chunk: at most ~256 MB so that it stays close to the L2 / small in HBM
     size_t max_rows = ((size_t)256 << 20) / ((size_t)s->Vp * 2);
@@ -473,7 +473,7 @@ extern "C" int b4r_session_create(const b4r_config* cfg, int batch, int seq_len,
   CK(cudaMemcpy(s->d_ce_jobs, cj, sizeof(cj), cudaMemcpyHostToDevice));
   CK(cudaMemset(s->stats, 0, 8 * sizeof(float)));
   CK(cudaMemset(s->step_stats, 0, 8 * sizeof(float)));
-  CK(cudaMemset(s->ticket, 0, (size_t)(s->Mcap / 128 + 8) * sizeof(int)));
+  CK(cudaMemset(s->ticket, 0, 4 * sizeof(int)));
   s->use_umma = ce_umma_make_maps(&s->umaps, s->t, s->Mcap, s->shadow + s->lay.find("word_embeddings"), s->V, s->H) &&
                 getenv("B4R_DISABLE_UMMA") == nullptr;
   CK(cudaMemset(s->counts, 0, 8 * sizeof(int)));
@@ -638,12 +638,12 @@ extern "C" int b4r_mlm_loss(b4r_session* s, float* stats, void* stream) {
   c.stats = stats;
   if (s->use_umma) {
     c.target_ctas = 2 * 148; c.max_splits = s->vsplits_umma;
-    c.fuse_finalize = 1;   // partial merge + statistics inside the forward kernel (last CTA per row tile / last tile)
     KL("ce_fwd_umma", launch_ce_fwd_umma(s->umaps, c, st));
+    c.vsplits = -1;  // finalize re-derives the device-side split count
   } else {
     KL("ce_fwd", launch_ce_fwd(c, st));
-    KL("ce_finalize", launch_ce_finalize(c, st));
   }
+  KL("ce_finalize", launch_ce_finalize(c, st));
   return 0;
 }
 

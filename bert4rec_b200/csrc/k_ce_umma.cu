@@ -25,10 +25,6 @@ struct CeUmmaDev {
   const float* vbias; const int* labels; const int* d_counts;
   int M_cap, v_begin, v_end, target_ctas, max_splits, debug;
   float* part;
-  // fused finalize (the last CTA of a row tile merges its split partials; the last row tile sums the statistics)
-  const float* row_w; const int* row_mult; float* lse; float* lab_out; float* stats; float* step_stats;
-  float* fin_part; int* ticket;   // [mtiles][5] floats ; ticket[0] = grid ticket, ticket[1 + mtile] = per-tile tickets (zero-initialised)
-  int batch;
 };
 
 template <int H>
@@ -78,13 +74,7 @@ __global__ void __launch_bounds__(320, 2) ce_fwd_umma_kernel(const __grid_consta
   const int vsplits = ce_umma_dyn_splits(n_rows, ntiles, a.target_ctas, a.max_splits);
   const int mtile = blockIdx.x / vsplits, split = blockIdx.x % vsplits;
   const int m0 = mtile * UM_BM;
-  if (m0 >= n_rows) {        // uniform: before any barrier / TMEM allocation
-    if (n_rows == 0 && blockIdx.x == 0 && a.fin_part) {   // empty batch: the statistics of this step are zeros
-      if (threadIdx.x < 5) a.step_stats[threadIdx.x] = 0.f;
-      if (threadIdx.x == 0 && a.stats) { a.stats[6] += (float)a.batch; a.stats[8] += 1.f; }
-    }
-    return;
-  }
+  if (m0 >= n_rows) return;  // uniform: before any barrier / TMEM allocation
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int tps = (ntiles + vsplits - 1) / vsplits;
@@ -253,83 +243,10 @@ __global__ void __launch_bounds__(320, 2) ce_fwd_umma_kernel(const __grid_consta
     }
   }
   umma::fence_before_sync();
-  __threadfence();            // this CTA's partials are visible device-wide before its ticket
   __syncthreads();
   if (warp == 1) {
     umma::fence_after_sync();
     umma::tmem_dealloc<256>(tmem_base);
-  }
-  // ---------------------------------------------------------------- fused finalize (replaces ce_finalize_kernel on this path)
-  if (a.fin_part == nullptr) return;
-  __shared__ int s_flag;
-  __shared__ float s_red5[4][5];
-  if (threadIdx.x == 0) s_flag = (atomicAdd(a.ticket + 1 + mtile, 1) == vsplits - 1);
-  __syncthreads();
-  if (!s_flag) return;
-  __threadfence();
-  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // loss_sum, n_valid, correct_masked, correct_all, n_all
-  if (threadIdx.x < UM_BM) {
-    const int r = m0 + threadIdx.x;
-    if (r < n_rows) {
-      float mn = -INFINITY, l = 0.f, lab = -INFINITY, bv = -INFINITY;
-      int bi = 0x7fffffff;
-      for (int s = 0; s < vsplits; ++s) {      // fixed order over the splits: deterministic
-        const float2* p = reinterpret_cast<const float2*>(a.part + ((size_t)s * a.M_cap + r) * 6);
-        const float2 p01 = __ldcg(p), p23 = __ldcg(p + 1), p45 = __ldcg(p + 2);
-        const float m3 = fmaxf(mn, p01.x);
-        if (m3 != -INFINITY) l = l * __expf(mn - m3) + p01.y * __expf(p01.x - m3);
-        mn = m3;
-        lab = fmaxf(lab, p23.x);
-        const int bi2 = __float_as_int(p45.x);
-        if (p23.y > bv || (p23.y == bv && bi2 < bi)) { bv = p23.y; bi = bi2; }
-      }
-      const float lse = mn + logf(l);
-      a.lse[r] = lse;
-      if (a.lab_out) a.lab_out[r] = lab;
-      const float w = a.row_w[r];
-      const int mult = a.row_mult[r];
-      const int correct = (bi == a.labels[r]);
-      if (w > 0.f) acc[0] = lse - lab;
-      acc[1] = w;
-      acc[2] = (w > 0.f && correct) ? 1.f : 0.f;
-      acc[3] = correct ? (float)mult : 0.f;
-      acc[4] = (float)mult;
-    }
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const float v = warp_sum(acc[k]);
-      if (lane == 0) s_red5[warp][k] = v;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < 5) a.fin_part[mtile * 5 + threadIdx.x] = (s_red5[0][threadIdx.x] + s_red5[1][threadIdx.x]) + (s_red5[2][threadIdx.x] + s_red5[3][threadIdx.x]);
-  __threadfence();
-  __syncthreads();
-  const int mtiles = (n_rows + UM_BM - 1) / UM_BM;
-  if (threadIdx.x == 0) {
-    a.ticket[1 + mtile] = 0;
-    s_flag = (atomicAdd(a.ticket, 1) == mtiles - 1);
-  }
-  __syncthreads();
-  if (!s_flag) return;
-  __threadfence();
-  __shared__ float s_tot[5];
-  if (threadIdx.x < 5) {
-    float v = 0.f;
-    for (int t = 0; t < mtiles; ++t) v += __ldcg(a.fin_part + t * 5 + threadIdx.x);   // row-tile order: deterministic
-    s_tot[threadIdx.x] = v;
-    a.step_stats[threadIdx.x] = v;
-    if (a.stats) a.stats[threadIdx.x] += v;
-  }
-  if (threadIdx.x == 0) a.ticket[0] = 0;
-  __syncthreads();
-  if (threadIdx.x == 0 && a.stats) {
-    // Keras running means: loss = Mean(batch loss, weight = batch size); masked_accuracy = Mean over batches
-    const float nv = fmaxf(s_tot[1], 1.f);
-    a.stats[5] += (s_tot[0] / nv) * (float)a.batch;
-    a.stats[6] += (float)a.batch;
-    a.stats[7] += s_tot[2] / nv;
-    a.stats[8] += 1.f;
   }
 }
 
@@ -349,8 +266,6 @@ cudaError_t launch_ce_fwd_umma(const CeUmmaMaps& maps, const CeArgs& a, cudaStre
   CeUmmaDev d;
   d.vbias = a.vbias; d.labels = a.labels; d.d_counts = a.d_counts; d.M_cap = a.M_cap; d.v_begin = a.v_begin; d.v_end = a.v_end;
   d.target_ctas = a.target_ctas; d.max_splits = a.max_splits; d.part = a.part;
-  d.row_w = a.row_w; d.row_mult = a.row_mult; d.lse = a.lse; d.lab_out = a.lab_out; d.stats = a.stats; d.step_stats = a.step_stats;
-  d.fin_part = a.fuse_finalize ? a.fin_part : nullptr; d.ticket = a.ticket; d.batch = a.batch;
   { const char* e = getenv("B4R_CE_DEBUG"); d.debug = e ? atoi(e) : 0; }
   // capacity grid: enough CTAs for every (m-tile, split) pair any row count can produce
   dim3 grid(a.target_ctas + (a.M_cap + UM_BM - 1) / UM_BM);

@@ -217,8 +217,7 @@ struct CeArgs {
   float* part;                       // [vsplits][M_cap][6] partial (max, sum, label_logit, best_val, best_idx, unused)
   float* lse;                        // [M_cap]
   float* lab_out;                    // optional [M_cap]: logit of the label column (ground-truth score)
-  float* fin_part; int* ticket;      // finalize scratch: [max(64, row tiles)][5] floats ; ticket[0] grid ticket + ticket[1 + tile] (zero-initialised)
-  int fuse_finalize;                 // generation-2 forward: merge the partials + statistics inside the forward kernel (no ce_finalize launch)
+  float* fin_part; int* ticket;      // finalize scratch: [64][5] floats + one zero-initialised int
   float* stats;                      // optional float[16] running accumulators: {loss_sum, n_valid, n_correct_masked,
                                      // n_correct_all, n_all, sum(batch_loss*batch), sum(batch), sum(batch_masked_acc), n_steps}
   float* step_stats;                 // this step only (same layout)
