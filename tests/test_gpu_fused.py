@@ -138,3 +138,55 @@ def test_fused_backward_matches_layered(name, dropout):
         if not d <= 2e-2 * float(g.norm()) + 1e-6 * gmax:
             bad.append((k, d, float(g.norm())))
     assert not bad, (name, bad)
+
+
+def _edge_batch(kind, B, S, P, V=977):
+    """Hand-built batches for the corner cases of the reference's dataloader tests (empty / one-item sequences, no
+    masked slot, everything masked)."""
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(3, V, (B, S), generator=g)
+    mask = torch.ones(B, S, dtype=torch.int64)
+    pos = torch.zeros(B, P, dtype=torch.int64)
+    mids = torch.zeros(B, P, dtype=torch.int64)
+    if kind == "one_item_sequences":          # every sequence holds a single (masked) item, the rest is padding
+        ids[:, 1:] = 0; mask[:, 1:] = 0
+        mids[:, 0] = ids[:, 0]; ids[:, 0] = 1
+    elif kind == "fully_padded_rows":         # some sequences are entirely padding (input_mask all zero)
+        ids[::2] = 0; mask[::2] = 0
+        for b in range(1, B, 2):
+            mids[b, 0] = ids[b, S - 1]; pos[b, 0] = S - 1; ids[b, S - 1] = 1
+    elif kind == "no_masked_slot":            # nothing to predict: the loss has no valid slot
+        pass
+    elif kind == "all_slots_used":            # max_predictions_per_seq reached in every sequence
+        for b in range(B):
+            p = torch.randperm(S, generator=g)[:P].sort().values
+            pos[b] = p; mids[b] = ids[b, p]; ids[b, p] = 1
+    w = (mids != 0).to(torch.int64)
+    return {"labels": ids.clone(), "input_word_ids": ids, "input_mask": mask, "masked_lm_ids": mids,
+            "masked_lm_positions": pos, "masked_lm_weights": w}
+
+
+@pytest.mark.parametrize("kind,B,S,P", [("one_item_sequences", 9, 12, 1), ("fully_padded_rows", 6, 50, 4),
+                                          ("no_masked_slot", 4, 33, 3), ("all_slots_used", 1, 50, 30)])
+def test_fused_edge_cases_match_layered(kind, B, S, P):
+    store = _store(S, 64, 2, 0.2)
+    store.ensure_training_buffers()
+    cb = to_cuda(_edge_batch(kind, B, S, P))
+    sess = store.session(B, S, P)
+    outs = []
+    for fused in (0, 1):
+        sess.set_flag(2, fused); sess.set_flag(3, fused)
+        sess.encode(cb["input_word_ids"], cb["input_mask"], training=True, seed=3, step=1)
+        sess.select(cb["masked_lm_positions"], cb["masked_lm_ids"], cb["masked_lm_weights"], mode=0, want_aux=True)
+        sess.transform(); sess.loss(); sess.backward(seed=3, step=1)
+        torch.cuda.synchronize()
+        outs.append((sess.sequence_output().float().clone(), sess.step_stats().clone()[:5], sess.counts().clone(),
+                     {k: v.clone() for k, v in store.grad_dict().items()}))
+    (seq0, st0, c0, g0), (seq1, st1, c1, g1) = outs
+    assert torch.equal(c0, c1)
+    assert torch.isfinite(seq1).all() and all(torch.isfinite(v).all() for v in g1.values())
+    assert float((seq0 - seq1).abs().max()) <= 2.5e-2 * (float(seq0.abs().max()) + 1e-6)
+    assert torch.allclose(st0, st1, rtol=2e-3, atol=1e-4), (st0, st1)
+    gmax = max(float(v.norm()) for v in g0.values())
+    for k in g0:
+        assert float((g0[k] - g1[k]).norm()) <= 2e-2 * float(g0[k].norm()) + 1e-5 * gmax + 1e-7, k
