@@ -32,6 +32,23 @@ class BaseEvaluator(abc.ABC):
     def get_metrics(self):
         return self._metrics
 
+    def all_reduce_metrics(self, group=None, device=None) -> dict:
+        """Data-parallel evaluation: every rank evaluates its own sequences; ONE all-reduce(SUM) of the metrics'
+        float64 partial sums (counter, nominators, denominators) merges them, after which every rank holds the global
+        results.  ``device``: where the reduction buffer lives (a CUDA device for NCCL, None / "cpu" for gloo)."""
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return self.get_metrics_results()
+        parts = [m._partials() for m in self._metrics]
+        flat = torch.tensor([x for p in parts for x in p], dtype=torch.float64, device=device)
+        dist.all_reduce(flat, group=group)
+        vals, k = flat.cpu().tolist(), 0
+        for m, p in zip(self._metrics, parts):
+            m._set_partials(vals[k:k + len(p)])
+            k += len(p)
+        return self.get_metrics_results()
+
     def get_metrics_results(self) -> dict:
         return {m.name: m.result() for m in self._metrics}
 

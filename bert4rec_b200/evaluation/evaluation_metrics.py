@@ -30,6 +30,14 @@ class EvaluationMetric(abc.ABC):
     def result(self):
         return self._value
 
+    # ---- data-parallel evaluation: every rank evaluates its own sequences, the sums are merged at the end
+    def _partials(self):
+        """float64 partial sums that add across ranks."""
+        return [float(self._value)]
+
+    def _set_partials(self, p):
+        self._value = type(self._initial_value)(p[0]) if isinstance(self._initial_value, int) else p[0]
+
 
 class Counter(EvaluationMetric):
     """Counts update() calls (used as "Valid Ranks")."""
@@ -71,6 +79,13 @@ class RatioEvaluationMetric(EvaluationMetric):
         self._denominator += float(ranks.size)
         self._value = self._nominator / self._denominator
         return self._value
+
+    def _partials(self):
+        return [self._nominator, self._denominator]
+
+    def _set_partials(self, p):
+        self._nominator, self._denominator = float(p[0]), float(p[1])
+        self._value = self._nominator / self._denominator if self._denominator else self._initial_value
 
     def reset(self):
         super().reset()

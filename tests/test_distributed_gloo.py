@@ -87,3 +87,44 @@ def test_dp_gradients_and_vocab_sharded_ce_over_gloo():
     sg = full.gather(-1, yy[:, None])
     ref_beat = ((full > sg) | ((full == sg) & (torch.arange(157)[None, :] < yy[:, None]))).sum(-1)
     assert torch.equal(ret["beat"], ref_beat)
+
+
+def _eval_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bert4rec_b200.evaluation.bert4rec_evaluator import default_bert4rec_metrics
+    from bert4rec_b200.evaluation.base_evaluator import BaseEvaluator
+
+    class _E(BaseEvaluator):
+        def evaluate(self, model, test_data):
+            return self._metrics
+
+    import numpy as np
+    from bert4rec_b200.dataloaders import samplers
+    ev = _E(default_bert4rec_metrics(), samplers.get("random", sample_size=5, vocab=list(range(3, 50))))
+    ranks = np.random.RandomState(7).randint(1, 102, size=200)
+    mine = ranks[rank::world]                      # this rank's share of the sequences
+    for m in ev.get_metrics():
+        m.update_many(mine)
+    out = ev.all_reduce_metrics()
+    if rank == 0:
+        ret["merged"] = dict(out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_dp_evaluation_metrics_merge_over_gloo():
+    """Every rank ranks its own sequences; one all-reduce of the partial sums gives the single-process metrics."""
+    import numpy as np
+    from bert4rec_b200.evaluation.bert4rec_evaluator import default_bert4rec_metrics
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_eval_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    ranks = np.random.RandomState(7).randint(1, 102, size=200)
+    ref = default_bert4rec_metrics()
+    for m in ref:
+        m.reset()
+        m.update_many(ranks)
+    for m in ref:
+        assert abs(ret["merged"][m.name] - m.result()) < 1e-12, (m.name, ret["merged"][m.name], m.result())
