@@ -58,6 +58,7 @@ _SIGNATURES = {
     "b4r_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.POINTER(AdamWHParams), _P, C.c_float, _P, _P, _P, _P]),
     "b4r_rank_candidates": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "b4r_rank_full": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "b4r_rank_full_ext": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "b4r_metrics_from_hist": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P]),
     "b4r_sequence_output": (_P, [_P, C.c_int]),
     "b4r_mlm_hidden": (_P, [_P]),

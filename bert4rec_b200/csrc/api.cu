@@ -896,6 +896,21 @@ extern "C" int b4r_rank_full(b4r_session* s, int v_begin, int v_end, int32_t* be
   return 0;
 }
 
+// Same count for EXTERNAL rows (vocab-sharded evaluation over several GPUs: the hidden rows, labels and ground-truth scores
+// of every rank are all-gathered, each rank counts over ITS vocabulary shard, one all-reduce of the counts gives exact ranks).
+extern "C" int b4r_rank_full_ext(b4r_session* s, const void* t_rows, const int32_t* labels, const float* gt_scores,
+                                 const int32_t* counts2, int rows_cap, int v_begin, int v_end, int32_t* beat_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!s || !t_rows || !labels || !gt_scores || !counts2 || !beat_out) return fail("null argument");
+  if (v_begin < 0 || v_end > s->V || v_begin >= v_end) return fail("bad vocabulary shard [%d, %d)", v_begin, v_end);
+  if (rows_cap < 1) return fail("rows_cap %d", rows_cap);
+  CeArgs c = ce_args(s);
+  c.t = reinterpret_cast<const bf16*>(t_rows); c.labels = labels; c.d_counts = counts2; c.M_cap = rows_cap;
+  c.v_begin = v_begin; c.v_end = v_end;
+  KL("ce_count", launch_ce_count(c, gt_scores, beat_out, st));
+  return 0;
+}
+
 extern "C" int b4r_metrics_from_hist(const uint64_t* hist, int max_rank, const int32_t* ks, int nk, double* out, void* stream) {
   if (!hist || !ks || !out || nk < 0 || nk > 16) return fail("bad argument");
   CK(launch_metrics_from_hist(reinterpret_cast<const unsigned long long*>(hist), max_rank, ks, nk, out, (cudaStream_t)stream));

@@ -507,7 +507,8 @@ __global__ void __launch_bounds__(256) ce_count_kernel(CeDev a, const float* __r
         const int h = e >> 1;
         if (col < a.v_end) {
           const float v = acc[nt][e] + sBias[cl];
-          cnt[h] += (v > sg[h]) || (v == sg[h] && col < label[h]);
+          // the label column never competes with itself (its score here may differ from s_gt in the last bit)
+          cnt[h] += col != label[h] && ((v > sg[h]) || (v == sg[h] && col < label[h]));
         }
       }
   }

@@ -261,6 +261,13 @@ class Session:
         check(self.lib.b4r_rank_full(self.h, v_begin, self.store.V if v_end is None else v_end, _ptr(beat), _stream()))
         return beat[:n_rows]
 
+    def rank_full_ext(self, t_rows, labels, gt_scores, counts2, v_begin, v_end, beat):
+        """Items of the shard [v_begin, v_end) ranking ahead of each external row's ground truth, added into ``beat``."""
+        assert t_rows.dtype == torch.bfloat16 and labels.dtype == torch.int32 and gt_scores.dtype == torch.float32
+        assert counts2.dtype == torch.int32 and beat.dtype == torch.int32 and t_rows.is_contiguous()
+        check(self.lib.b4r_rank_full_ext(self.h, _ptr(t_rows), _ptr(labels), _ptr(gt_scores), _ptr(counts2), t_rows.shape[0],
+                                         int(v_begin), int(v_end), _ptr(beat), _stream()))
+
     # ---- introspection (zero-copy views over the workspace)
     def _view(self, ptr, shape, dtype):
         n = 1

@@ -483,6 +483,47 @@ class BERT4RecModel:
         graph.replay()
         return out
 
+    def full_catalogue_ranks(self, encoder_input, ground_truth, group=None):
+        """1-based rank of every slot's ground truth over the WHOLE catalogue (``rank_items(items=None)`` + the evaluator's
+        rank lookup, bert4rec_model.py:235-240, bert4rec_evaluator.py:112-117), without materialising any logits.
+        With an initialised process group the vocabulary is SHARDED over the ranks (large catalogues): the hidden
+        rows, labels and ground-truth scores of all ranks are all-gathered, every rank counts the items of its shard that
+        rank ahead (``b4r_rank_full_ext``), one all-reduce(SUM) of the counts gives the exact ranks."""
+        import torch.distributed as dist
+        sess, _ = self._encode_for_ranking(encoder_input)
+        gt = self._stage_aux("gt_full", ground_truth)
+        n = int(gt.shape[0])
+        cap = sess.Mcap
+        # ground-truth scores with the gather-dot kernel (one candidate per slot)
+        _, score, _ = sess.rank_candidates(gt.view(-1, 1).contiguous(), None, want_ranking=False, want_scores=True)
+        dev = self.device
+        t = torch.zeros(cap, self.store.H, dtype=torch.bfloat16, device=dev)
+        t[:n] = sess.mlm_hidden()[:n]
+        lab = torch.zeros(cap, dtype=torch.int32, device=dev); lab[:n] = gt.to(torch.int32)
+        sc = torch.zeros(cap, dtype=torch.float32, device=dev); sc[:n] = score.view(-1)
+        cnt = torch.tensor([n, n], dtype=torch.int32, device=dev)
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if world == 1:
+            beat = torch.zeros(cap, dtype=torch.int32, device=dev)
+            sess.rank_full_ext(t, lab, sc, cnt, 0, self.store.V, beat)
+            return beat[:n] + 1
+        me = dist.get_rank(group)
+        ts = [torch.empty_like(t) for _ in range(world)]
+        labs = [torch.empty_like(lab) for _ in range(world)]
+        scs = [torch.empty_like(sc) for _ in range(world)]
+        cnts = [torch.empty_like(cnt) for _ in range(world)]
+        dist.all_gather(ts, t, group=group); dist.all_gather(labs, lab, group=group)
+        dist.all_gather(scs, sc, group=group); dist.all_gather(cnts, cnt, group=group)
+        V = self.store.V
+        per = (V + world - 1) // world
+        v_lo, v_hi = me * per, min(V, (me + 1) * per)
+        beat = torch.zeros(world, cap, dtype=torch.int32, device=dev)
+        if v_lo < v_hi:
+            for q in range(world):
+                sess.rank_full_ext(ts[q], labs[q], scs[q], cnts[q], v_lo, v_hi, beat[q])
+        dist.all_reduce(beat, group=group)
+        return beat[me, :n] + 1
+
     def rank_items(self, encoder_input: dict, items: list = None):
         """Reference semantics (bert4rec_model.py:203-240): one ranking per slot whose ``masked_lm_weights`` is 1;
         with ``items`` (list per sequence of list per slot of candidate ids) the candidates sorted by descending

@@ -100,6 +100,11 @@ int b4r_rank_candidates(b4r_session* s, const int64_t* cand, const int64_t* gt, 
 /* rank_items(items=None) for evaluation: 1-based rank of the label of every selected row over the vocabulary shard
  * [v_begin, v_end): beat_out[i] += #items ranking ahead (caller zeroes; sum over shards + 1 = rank). */
 int b4r_rank_full(b4r_session* s, int v_begin, int v_end, int32_t* beat_out, void* stream);
+/* The same count for EXTERNAL rows: t_rows bf16 [rows_cap, hidden], labels int32 [rows_cap], gt_scores fp32 [rows_cap],
+ * counts2 device int32[2] (counts2[1] = number of rows).  Vocab-sharded evaluation over several GPUs all-gathers the rows
+ * of every rank, counts per shard here and all-reduces the counts (rank = 1 + sum over shards). */
+int b4r_rank_full_ext(b4r_session* s, const void* t_rows, const int32_t* labels, const float* gt_scores, const int32_t* counts2,
+                      int rows_cap, int v_begin, int v_end, int32_t* beat_out, void* stream);
 /* HR@k / NDCG@k / MAP from a rank histogram (evaluation_metrics.py:47-112): out fp64 [2 + 2*nk] =
  * {n, NDCG@k..., HR@k..., MAP}; ks: device int32 [nk]. */
 int b4r_metrics_from_hist(const uint64_t* hist, int max_rank, const int32_t* ks, int nk, double* out, void* stream);
