@@ -33,6 +33,7 @@ using namespace encf;
 
 namespace {
 constexpr int NT_ARENA = 12;   // 16 KB tiles
+constexpr int ONES_OFF = NT_ARENA * TILE_B, ONES_BYTES = 2048;   // 16 k-rows x 64 bf16 ones behind the arena (see `dmn_ones`)
 // arena tile indices by phase (see the liveness table in DESIGN.md section 4b)
 constexpr int T_H = 0, T_DB2 = 2, T_DH = 3, T_Y = 5, T_DB1 = 6, T_C = 7, T_W2 = 8, T_W1 = 9, T_WO = 10;
 constexpr int T_Q = 0, T_K = 1, T_V = 2, T_DC = 3, T_PD = 4, T_DS = 8;       // P_drop: 4..7, dS: 8..11 (head-major, 2 tiles each)
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
   auto tile = [&](int i) -> unsigned char* { return smem + i * TILE_B; };
   const int I = a.I, PF = par_floats(I), IC = I / 64;     // IC: 16-column chunks of an I-wide row per thread
   const int WP = 64 * 192 + 64 * 64 + 2 * 64 * I;
-  float* sPar = reinterpret_cast<float*>(smem + NT_ARENA * TILE_B);   // [2][PF]
+  float* sPar = reinterpret_cast<float*>(smem + ONES_OFF + ONES_BYTES);   // [2][PF]
   float* sCol = sPar + 2 * PF;                                        // [4 quads][PF] column-sum partials of this layer
   float* sMask = sCol + 4 * PF;                                       // [128]
   float* sRed = sMask + FT;                                           // [2][2][4][128]
@@ -164,6 +165,8 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
     load_Wa(a.L - 1);
   }
   if (part == 0) sMask[row] = valid ? (a.mask[t] != 0 ? 0.f : -1e9f) : 0.f;
+  if (tid < ONES_BYTES / 4) reinterpret_cast<uint32_t*>(smem + ONES_OFF)[tid] = 0x3F803F80u;   // bf16 1.0 pairs
+  for (int i = tid; i < 4 * PF; i += NTHR) sCol[i] = 0.f;
   if (warp == 1) umma::tmem_alloc<512>(tmem_holder);
   umma::fence_before_sync();
   __syncthreads();
@@ -178,6 +181,24 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
   const uint64_t DMN0 = desc_mn_sw128(umma::smem_addr(smem), TILE_B);
   auto dk = [&](int tile_i, int off) -> uint64_t { return desc_at(DK0, (uint32_t)(tile_i * TILE_B + off)); };
   auto dmn = [&](int tile_i, int off) -> uint64_t { return desc_at(DMN0, (uint32_t)(tile_i * TILE_B + off)); };
+  // A operand of a weight-gradient MMA (X^T, MN-major, M = 128 but only 64 real feature rows): the second 64-row block is
+  // pointed at the tile of ONES (leading-byte-offset chosen per k-step), so accumulator lane 64 = column sums of dY = the
+  // bias gradient, for free on the tensor core
+  const uint64_t DMN_NOLBO = DMN0 - ((uint64_t)(TILE_B >> 4) << 16);
+  auto dmn_ones = [&](int tile_i, int off) -> uint64_t {
+    const uint32_t a0 = (uint32_t)(tile_i * TILE_B + off);
+    return desc_at(DMN_NOLBO, a0) + ((uint64_t)((ONES_OFF - a0) >> 4) << 16);
+  };
+  // lane 64 of a weight-gradient accumulator (held by the quad-2 warps) -> sCol slot of quad 2 (the other quads' slots of these
+  // offsets stay zero), 16 columns per call
+  auto bias_lane = [&](uint32_t acc_col, int off) {
+    float v[16];
+    tmem_ld_f16(tlane + acc_col, v);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sCol[2 * PF + off + i] = v[i];
+    }
+  };
   // MMA issue: warps 0..3 (one per scheduler) each issue the accumulation chains `chain(w)` gives them and commit
   auto issue = [&](auto&& chain) {
     if (warp < 4) {
@@ -312,7 +333,7 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
       drop16(dO, site_id(SITE_FFN_OUT, l));
       uint32_t pk[8];
       round_n<16>(dO, pk);
-      colsum(dO, OFF_B2);
+      if (I != 64) colsum(dO, OFF_B2);   // I == 64: accumulator lane 64 of dW2 (ones block)
       st_tile<2>(tile(T_DB2), row, part * 2, pk);
       for (int i = 0; i < IC; ++i) {
         const int j = part * IC + i;
@@ -325,7 +346,8 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
     issue([&](int w) {
       if (w == 0) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma::mma_bf16_ss(tmem, dmn(T_H, kk * 2048), dmn(T_DB2, kk * 2048), idesc_gen(128, 64, 1, 1), kk ? 1u : 0u);
+        for (int kk = 0; kk < 8; ++kk)
+          umma::mma_bf16_ss(tmem, I == 64 ? dmn_ones(T_H, kk * 2048) : dmn(T_H, kk * 2048), dmn(T_DB2, kk * 2048), idesc_gen(128, 64, 1, 1), kk ? 1u : 0u);
       } else if (w == 1) {
         umma::mbar_wait(barWa, it & 1);
         const uint32_t id = idesc_gen(128, I, 0, 0);
@@ -344,6 +366,7 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
         tmem_ld_f16(tlane + cq, v);
         if (row < I) st_f32x16(wp + 64 * 192 + 64 * 64 + 64 * I + (size_t)row * 64 + cq, v);
       }
+      if (I == 64 && quad == 2) bias_lane(cq, OFF_B2 + cq);
       for (int i = 0; i < IC; ++i) {
         const int j = part * IC + i;
         float v[16], hp[16];
@@ -358,11 +381,6 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
         }
         uint32_t pk[8];
         round_n<16>(v, pk);
-        {
-          float s; int c;
-          warp_colsum16(v, lane, s, c);
-          if (!(lane & 1)) sCol[quad * PF + PB_B1 + j * 16 + c] = s;
-        }
         st_tile<2>(tile(T_DH + (j >> 2)), row, (j & 3) * 2, pk);
       }
       st_tile<2>(tile(T_Y), row, part * 2, pfA);
@@ -373,7 +391,7 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
       if (w == 0) {
         const uint32_t id = idesc_gen(128, I, 1, 1);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma::mma_bf16_ss(tmem, dmn(T_Y, kk * 2048), dmn(T_DH, kk * 2048), id, kk ? 1u : 0u);
+        for (int kk = 0; kk < 8; ++kk) umma::mma_bf16_ss(tmem, dmn_ones(T_Y, kk * 2048), dmn(T_DH, kk * 2048), id, kk ? 1u : 0u);
       } else if (w == 1) {
         for (int kk = 0; kk < I / 16; ++kk)
           umma::mma_bf16_ss(tmem + 256, dk(T_DH, (kk >> 2) * TILE_B + (kk & 3) * 32), dk(T_W1, (kk >> 2) * 8192 + (kk & 3) * 32),
@@ -395,6 +413,9 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
           st_f32x16(wp + 64 * 192 + 64 * 64 + (size_t)row * I + j * 16, v);
         }
       }
+      if (quad == 2) {
+        for (int i = 0; i < IC; ++i) bias_lane((part * IC + i) * 16, PB_B1 + (part * IC + i) * 16);
+      }
       float v[16];
       tmem_ld_f16(tlane + 256 + cq, v);
 #pragma unroll
@@ -405,7 +426,6 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
       drop16(dO, site_id(SITE_ATTN_OUT, l));
       uint32_t pk[8];
       round_n<16>(dO, pk);
-      colsum(dO, PB_BO);
       st_tile<2>(tile(T_DB1), row, part * 2, pk);
       st_tile<2>(tile(T_C), row, part * 2, pfB);
     }
@@ -414,7 +434,7 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
     issue([&](int w) {
       if (w == 0) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma::mma_bf16_ss(tmem, dmn(T_C, kk * 2048), dmn(T_DB1, kk * 2048), idesc_gen(128, 64, 1, 1), kk ? 1u : 0u);
+        for (int kk = 0; kk < 8; ++kk) umma::mma_bf16_ss(tmem, dmn_ones(T_C, kk * 2048), dmn(T_DB1, kk * 2048), idesc_gen(128, 64, 1, 1), kk ? 1u : 0u);
       } else if (w == 1) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma::mma_bf16_ss(tmem + 64, dk(T_DB1, k * 32), dk(T_WO, k * 32), idesc_gen(128, 64, 0, 0), k ? 1u : 0u);
@@ -432,6 +452,7 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
         tmem_ld_f16(tlane + cq, v);
         st_f32x16(wp + 64 * 192 + (size_t)row * 64 + cq, v);
       }
+      if (quad == 2) bias_lane(cq, PB_BO + cq);
       float v[16], c[16];
       tmem_ld_f16(tlane + 64 + cq, v);
       uint32_t pk[8];
@@ -549,19 +570,16 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = valid ? v[i] * scale : 0.f;
       round_n<16>(v, pk);
-      colsum(v, PB_BQKV);
       st_tile<2>(tile(T_DQ), row, part * 2, pk);
       tmem_ld_f16(base + 64, v);                     // dK
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = valid ? v[i] * scale : 0.f;
       round_n<16>(v, pk);
-      colsum(v, PB_BQKV + 64);
       st_tile<2>(tile(T_DQ + 1), row, part * 2, pk);
       tmem_ld_f16(base, v);                          // dV
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = valid ? v[i] : 0.f;
       round_n<16>(v, pk);
-      colsum(v, PB_BQKV + 128);
       st_tile<2>(tile(T_DQ + 2), row, part * 2, pk);
       st_tile<2>(tile(T_XIN), row, part * 2, pfA);
     }
@@ -570,7 +588,7 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
     issue([&](int w) {
       if (w == 0) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma::mma_bf16_ss(tmem, dmn(T_XIN, kk * 2048), dmn(T_DQ, kk * 2048), idesc_gen(128, 192, 1, 1), kk ? 1u : 0u);
+        for (int kk = 0; kk < 8; ++kk) umma::mma_bf16_ss(tmem, dmn_ones(T_XIN, kk * 2048), dmn(T_DQ, kk * 2048), idesc_gen(128, 192, 1, 1), kk ? 1u : 0u);
       } else if (w == 1) {
         umma::mbar_wait(barWq, it & 1);
 #pragma unroll
@@ -592,6 +610,10 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
           tmem_ld_f16(tlane + j * 16, v);
           st_f32x16(wp + (size_t)row * 192 + j * 16, v);
         }
+      }
+      if (quad == 2) {
+#pragma unroll 1
+        for (int i = 0; i < 3; ++i) bias_lane((part * 3 + i) * 16, PB_BQKV + (part * 3 + i) * 16);
       }
       float v[16];
       tmem_ld_f16(tlane + 256 + cq, v);
@@ -721,7 +743,7 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
 
 // ------------------------------------------------------------------------------------------------ host side
 size_t enc_bwd_fused_smem_bytes(int I) {
-  return (size_t)NT_ARENA * TILE_B + 2 * (size_t)par_floats(I) * 4 + 4 * (size_t)par_floats(I) * 4 + FT * 4 + 16 * FT * 4 + 64 + 1024;
+  return (size_t)NT_ARENA * TILE_B + ONES_BYTES + 2 * (size_t)par_floats(I) * 4 + 4 * (size_t)par_floats(I) * 4 + FT * 4 + 16 * FT * 4 + 64 + 1024;
 }
 bool enc_bwd_fused_supported(int H, int N, int S, int I) {
   if (getenv("B4R_DISABLE_FUSED") || getenv("B4R_DISABLE_FUSED_BWD")) return false;
