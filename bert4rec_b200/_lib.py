@@ -59,6 +59,20 @@ _SIGNATURES = {
     "b4r_rank_candidates": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "b4r_rank_full": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "b4r_rank_full_ext": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "b4r_backward_from_dt": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P, _P]),
+    "b4r_mlm_labels": (_P, [_P]),
+    "b4r_mlm_row_weights": (_P, [_P]),
+    "b4r_mlm_row_mult": (_P, [_P]),
+    "b4r_shard_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
+    "b4r_shard_create": (C.c_int, [C.c_int] * 6 + [_P, _P, _P, _P, _P, C.c_size_t, C.POINTER(_P)]),
+    "b4r_shard_destroy": (None, [_P]),
+    "b4r_shard_pack": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "b4r_shard_ce_partial": (C.c_int, [_P, _P, _P]),
+    "b4r_shard_ce_merge": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "b4r_shard_ce_backward": (C.c_int, [_P, _P, C.c_int, _P]),
+    "b4r_shard_step_stats": (_P, [_P]),
+    "b4r_shard_lse": (_P, [_P]),
+    "b4r_shard_counts": (_P, [_P]),
     "b4r_metrics_from_hist": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P]),
     "b4r_sequence_output": (_P, [_P, C.c_int]),
     "b4r_mlm_hidden": (_P, [_P]),

@@ -660,7 +660,10 @@ extern "C" int b4r_mlm_logits(b4r_session* s, float* out, void* stream) {
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const int64_t* step_counter, void* stream) {
+// ext_dt != nullptr: the gradient of the transformed rows comes from outside (vocabulary-sharded projection: the reduce-scattered
+// sum of every shard's partial dT, fp32 [Mcap][H] in this session's row order); the cross-entropy backward is skipped and the
+// table / output-bias gradients are left as the shard wrote them (the embedding backward accumulates on top).
+static int backward_impl(b4r_session* s, uint64_t seed, uint32_t step, const int64_t* step_counter, void* stream, const float* ext_dt) {
   const long long* d_step = reinterpret_cast<const long long*>(step_counter);
   if (!s || !s->grads) return fail("session has no gradient buffer");
   if (!s->ids) return fail("b4r_encode must run before b4r_backward");
@@ -671,10 +674,10 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
   float* G = s->grads;
   const float od = s->cfg.output_dropout;
   const int64_t oE = s->lay.find("word_embeddings");
-  const bool bwd_umma = s->use_umma && ce_bwd_umma_supported(H);
+  const bool bwd_umma = !ext_dt && s->use_umma && ce_bwd_umma_supported(H);
   const int ce_xt = ce_bwd_umma_xtile(H), ce_xtiles = (V + ce_xt - 1) / ce_xt, ce_ctas = ce_xt == 64 ? 148 : 2 * 148;
   // gradient accumulators that are scatter / accumulate targets
-  if (!bwd_umma) CK(cudaMemsetAsync(G + oE, 0, (size_t)V * H * sizeof(float), st));
+  if (!bwd_umma && !ext_dt) CK(cudaMemsetAsync(G + oE, 0, (size_t)V * H * sizeof(float), st));
   CK(cudaMemsetAsync(s->dxa, 0, (size_t)T * H * sizeof(float), st));
   CeArgs c = ce_args(s);
   bool head_done = false;
@@ -707,7 +710,7 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
   }
   // ---- CE backward, generation 1: dlogits materialised in bf16, chunked over rows
   int chunk = 0;
-  for (int r0 = 0; r0 < (bwd_umma ? 0 : Mcap); r0 += s->dl_rows, ++chunk) {
+  for (int r0 = 0; r0 < (bwd_umma || ext_dt ? 0 : Mcap); r0 += s->dl_rows, ++chunk) {
     const int rc = (Mcap - r0) < s->dl_rows ? (Mcap - r0) : s->dl_rows;
     c.row_begin = r0; c.row_count = rc;
     KL("ce_dlogits", launch_ce_dlogits(c, st));
@@ -725,15 +728,17 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
   }
   // ---- MLM transform backward
   const bf16* xL = s->layers.back().out;
+  const float* dt_src = ext_dt ? ext_dt : s->dt_part;
+  const int dt_n = ext_dt ? 1 : s->dt_splits;
   if (head_done) {
     // already issued beside the dE pass
   } else if (head_bwd_fused_supported(H)) {
-    KL("head_bwd_fused", launch_head_bwd_fused(s->dt_part, s->dt_splits, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
+    KL("head_bwd_fused", launch_head_bwd_fused(dt_src, dt_n, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
                              P + s->lay.find("head/ln/gamma"), W + s->lay.find("head/wt"), xL, s->rows, s->counts, Mcap, s->dxa,
                              s->p_head_ln, s->p_wt, st, bwd_umma ? ce_xtiles : 0, bwd_umma ? ce_ctas : 0,
                              bwd_umma ? s->dt_max_splits : 0));
   } else {
-  KL("head_bwd_rows", launch_head_bwd_rows(s->dt_part, s->dt_splits, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
+  KL("head_bwd_rows", launch_head_bwd_rows(dt_src, dt_n, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
                           P + s->lay.find("head/ln/gamma"), s->d_tpre, s->p_head_ln, Mcap, s->counts, H, st,
                           bwd_umma ? ce_xtiles : 0, bwd_umma ? ce_ctas : 0, bwd_umma ? s->dt_max_splits : 0));
   {
@@ -830,6 +835,193 @@ extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const 
   else KL("grad_reduce:all", launch_grad_reduce(s->d_jobs, s->n_jobs, s->jobs_max_len, st));
   return 0;
 }
+
+extern "C" int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const int64_t* step_counter, void* stream) {
+  return backward_impl(s, seed, step, step_counter, stream, nullptr);
+}
+extern "C" int b4r_backward_from_dt(b4r_session* s, const float* dt, uint64_t seed, uint32_t step, const int64_t* step_counter,
+                                    void* stream) {
+  if (!dt) return fail("null dt");
+  return backward_impl(s, seed, step, step_counter, stream, dt);
+}
+extern "C" const int32_t* b4r_mlm_labels(b4r_session* s) { return s ? s->labels : nullptr; }
+extern "C" const float* b4r_mlm_row_weights(b4r_session* s) { return s ? s->row_w : nullptr; }
+extern "C" const int32_t* b4r_mlm_row_mult(b4r_session* s) { return s ? s->row_mult : nullptr; }
+
+// ------------------------------------------------------------------------------------------------ vocabulary shard
+// The tied output projection of ONE rank's slice [v_begin, v_end) of the catalogue over the masked-slot rows of ALL ranks
+// (SURVEY 8e "large catalogue"; the reference computes the full [B,P,V] logits on one device, bert4rec_model.py:139-147).
+struct b4r_shard {
+  int H, V, v_begin, v_end, Vs, n_ranks, Mcap, cap;
+  const bf16* table; const float* vbias; float* g_table; float* g_bias;
+  bf16* rows; int *lab_local, *lab_global, *mult, *counts; float* w;
+  const int* counts_in;   // [n][2] of the last pack (device, caller-owned: must stay alive until the backward)
+  float *ce_part, *lse, *lab, *step_stats, *fin_part; int* ticket;
+  int fwd_max_splits, dt_max_splits, me_splits;
+  float *dt_part, *p_dE, *p_dbias;
+  ReduceJob* d_jobs;
+  CeUmmaMaps maps;
+};
+
+static size_t shard_carve(b4r_shard* s, void* ws, size_t ws_bytes, bool dry) {
+  Bump b{reinterpret_cast<char*>(ws), 0, ws_bytes, dry};
+  const int H = s->H, cap = s->cap, Vs = s->Vs;
+  const size_t budget = (size_t)1 << 30;   // partial buffers are capped at 1 GB each (large row counts need no splits anyway)
+  s->rows = b.take<bf16>((size_t)cap * H);
+  s->lab_local = b.take<int>(cap); s->lab_global = b.take<int>(cap); s->mult = b.take<int>(cap); s->w = b.take<float>(cap);
+  s->counts = b.take<int>(8);
+  const int vtiles = (Vs + 127) / 128;
+  {
+    size_t ms = budget / ((size_t)cap * 6 * sizeof(float));
+    int vs = vtiles < 64 ? vtiles : 64;
+    if ((size_t)vs > ms) vs = (int)ms;
+    s->fwd_max_splits = vs < 1 ? 1 : vs;
+  }
+  s->ce_part = b.take<float>((size_t)s->fwd_max_splits * cap * 6);
+  s->lse = b.take<float>(cap); s->lab = b.take<float>(cap);
+  s->step_stats = b.take<float>(8); s->fin_part = b.take<float>(64 * 5); s->ticket = b.take<int>(4);
+  {
+    const int xt = ce_bwd_umma_xtile(H), xtiles = (Vs + xt - 1) / xt;
+    size_t ms = budget / ((size_t)cap * H * sizeof(float));
+    int vs = xtiles < 24 ? xtiles : 24;
+    if ((size_t)vs > ms) vs = (int)ms;
+    s->dt_max_splits = vs < 1 ? 1 : vs;
+    int me = (xt == 64 ? 148 : 2 * 148) / vtiles;
+    if (me < 1) me = 1;
+    if (me > 8) me = 8;
+    s->me_splits = me;
+  }
+  s->dt_part = b.take<float>((size_t)s->dt_max_splits * cap * H);
+  s->p_dE = b.take<float>((size_t)s->me_splits * Vs * H);
+  s->p_dbias = b.take<float>((size_t)s->me_splits * Vs);
+  s->d_jobs = b.take<ReduceJob>(2);
+  return b.off;
+}
+
+static int shard_check(int hidden, int vocab, int n_ranks, int rows_per_rank, int v_begin, int v_end) {
+  if (hidden != 64 && hidden != 128 && hidden != 256) return fail("vocabulary shard: hidden %d not in {64, 128, 256}", hidden);
+  if (n_ranks < 1 || n_ranks > 64 || rows_per_rank < 1) return fail("vocabulary shard: bad row layout %d x %d", n_ranks, rows_per_rank);
+  if ((long long)n_ranks * rows_per_rank > (1ll << 30)) return fail("vocabulary shard: too many rows");
+  if (v_begin < 0 || v_end > vocab || v_begin >= v_end) return fail("bad vocabulary shard [%d, %d) of %d", v_begin, v_end, vocab);
+  return 0;
+}
+
+static b4r_shard* shard_shell(int hidden, int vocab, int n_ranks, int rows_per_rank, int v_begin, int v_end) {
+  b4r_shard* s = new b4r_shard();
+  s->H = hidden; s->V = vocab; s->v_begin = v_begin; s->v_end = v_end; s->Vs = v_end - v_begin;
+  s->n_ranks = n_ranks; s->Mcap = rows_per_rank; s->cap = n_ranks * rows_per_rank;
+  return s;
+}
+
+extern "C" size_t b4r_shard_workspace_bytes(int hidden, int vocab, int n_ranks, int rows_per_rank, int v_begin, int v_end) {
+  if (shard_check(hidden, vocab, n_ranks, rows_per_rank, v_begin, v_end)) return 0;
+  b4r_shard* s = shard_shell(hidden, vocab, n_ranks, rows_per_rank, v_begin, v_end);
+  const size_t n = shard_carve(s, nullptr, 0, true);
+  delete s;
+  return n;
+}
+
+extern "C" int b4r_shard_create(int hidden, int vocab, int n_ranks, int rows_per_rank, int v_begin, int v_end, const void* table_bf16,
+                                const float* output_bias, float* grad_table, float* grad_bias, void* workspace,
+                                size_t workspace_bytes, b4r_shard** out) {
+  if (!out) return fail("null out");
+  if (shard_check(hidden, vocab, n_ranks, rows_per_rank, v_begin, v_end)) return 1;
+  if (!table_bf16 || !output_bias || !grad_table || !grad_bias || !workspace) return fail("null buffer");
+  if ((uintptr_t)workspace & 255) return fail("workspace must be 256-byte aligned");
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (b4r_device_check(dev)) return 1;
+  b4r_shard* s = shard_shell(hidden, vocab, n_ranks, rows_per_rank, v_begin, v_end);
+  s->table = reinterpret_cast<const bf16*>(table_bf16); s->vbias = output_bias; s->g_table = grad_table; s->g_bias = grad_bias;
+  const size_t need = shard_carve(s, workspace, workspace_bytes, false);
+  if (need > workspace_bytes) { delete s; return fail("workspace too small: need %zu bytes", need); }
+  // zero once: rows behind the packed ones are read (never used) by the tile loads and must stay finite
+  if (cudaMemset(workspace, 0, need) != cudaSuccess) { delete s; return fail("cudaMemset failed"); }
+  ReduceJob j[2];
+  j[0] = ReduceJob{s->p_dE, grad_table + (size_t)v_begin * hidden, s->me_splits, s->Vs * hidden, (long long)s->Vs * hidden, 0};
+  j[1] = ReduceJob{s->p_dbias, grad_bias + v_begin, s->me_splits, s->Vs, (long long)s->Vs, 0};
+  if (cudaMemcpy(s->d_jobs, j, sizeof(j), cudaMemcpyHostToDevice) != cudaSuccess) { delete s; return fail("cudaMemcpy failed"); }
+  if (!ce_umma_make_maps(&s->maps, s->rows, s->cap, s->table + (size_t)v_begin * hidden, s->Vs, hidden)) {
+    delete s;
+    return fail("vocabulary shard: tensor maps could not be created");
+  }
+  *out = s;
+  return 0;
+}
+
+extern "C" void b4r_shard_destroy(b4r_shard* s) { delete s; }
+
+// rows_in bf16 [n][rows_per_rank][hidden], labels_in int32 / weights_in fp32 / mult_in int32 [n][rows_per_rank], counts_in int32 [n][2]
+// = every rank's {n_valid, n_rows}: the all-gathered b4r_mlm_hidden / labels / row_weights / row_mult / counts buffers.
+extern "C" int b4r_shard_pack(b4r_shard* s, const void* rows_in, const int32_t* labels_in, const float* weights_in,
+                              const int32_t* mult_in, const int32_t* counts_in, void* stream) {
+  if (!s || !rows_in || !labels_in || !weights_in || !mult_in || !counts_in) return fail("null argument");
+  s->counts_in = counts_in;
+  CK(launch_shard_pack(reinterpret_cast<const bf16*>(rows_in), labels_in, weights_in, mult_in, counts_in, s->n_ranks, s->Mcap, s->H,
+                       s->v_begin, s->rows, s->lab_local, s->lab_global, s->w, s->mult, s->counts, (cudaStream_t)stream));
+  return 0;
+}
+
+static CeArgs shard_ce_args(b4r_shard* s) {
+  CeArgs c{};
+  c.t = s->rows; c.ldt = s->H; c.E = s->table + (size_t)s->v_begin * s->H; c.vbias = s->vbias + s->v_begin;
+  c.labels = s->lab_local; c.row_w = s->w; c.row_mult = s->mult; c.d_counts = s->counts;
+  c.M_cap = s->cap; c.H = s->H; c.V = s->Vs; c.v_begin = 0; c.v_end = s->Vs;
+  c.part = s->ce_part; c.lse = s->lse; c.lab_out = s->lab; c.step_stats = s->step_stats; c.fin_part = s->fin_part; c.ticket = s->ticket;
+  c.target_ctas = 2 * 148; c.max_splits = s->fwd_max_splits;
+  return c;
+}
+
+// forward over the shard: part_out fp32 [n*rows_per_rank][6] = per packed row {max, sum exp(x - max), label logit (-inf when
+// the label lives in another shard), best logit, best GLOBAL index (int bits), 0}
+extern "C" int b4r_shard_ce_partial(b4r_shard* s, float* part_out, void* stream) {
+  if (!s || !part_out) return fail("null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CeArgs c = shard_ce_args(s);
+  CK(launch_ce_fwd_umma(s->maps, c, st));
+  CK(launch_shard_part_merge(s->ce_part, s->counts, s->cap, (s->Vs + 127) / 128, c.target_ctas, c.max_splits, s->v_begin, part_out, st));
+  return 0;
+}
+
+// parts fp32 [n_shards][n*rows_per_rank][6] (all-gathered b4r_shard_ce_partial outputs): log-sum-exp per row, loss / accuracy
+// sums of the GLOBAL batch into the shard's step statistics and (optional) the running stats (same layout as b4r_mlm_loss)
+extern "C" int b4r_shard_ce_merge(b4r_shard* s, const float* parts, int n_shards, int global_batch, float* stats, void* stream) {
+  if (!s || !parts || n_shards < 1) return fail("bad argument");
+  CeArgs c = shard_ce_args(s);
+  c.labels = s->lab_global;
+  c.part = const_cast<float*>(parts); c.vsplits = n_shards; c.batch = global_batch; c.stats = stats;
+  CK(launch_ce_finalize(c, (cudaStream_t)stream));
+  return 0;
+}
+
+// backward over the shard.  dt_out fp32 [n][rows_per_rank][hidden]: this shard's partial gradient of every rank's transformed
+// rows (reduce-scatter(SUM) over the shards gives each rank its dT for b4r_backward_from_dt).  The shard's slice of the table
+// and output-bias gradients is complete and is WRITTEN to grad_table / grad_bias; with zero_all the rest of both is zeroed
+// first, so that an all-reduce(SUM) over ranks assembles the whole projection gradient.
+extern "C" int b4r_shard_ce_backward(b4r_shard* s, float* dt_out, int zero_all, void* stream) {
+  if (!s || !dt_out) return fail("null argument");
+  if (!s->counts_in) return fail("b4r_shard_pack must run before b4r_shard_ce_backward");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = s->H, xt = ce_bwd_umma_xtile(H), xtiles = (s->Vs + xt - 1) / xt, ctas = xt == 64 ? 148 : 2 * 148;
+  if (zero_all) {
+    CK(cudaMemsetAsync(s->g_table, 0, (size_t)s->V * H * sizeof(float), st));
+    CK(cudaMemsetAsync(s->g_bias, 0, (size_t)s->V * sizeof(float), st));
+  }
+  CeBwdArgs ba{};
+  ba.vbias = s->vbias + s->v_begin; ba.lse = s->lse; ba.row_w = s->w; ba.labels = s->lab_local; ba.d_counts = s->counts;
+  ba.M_cap = s->cap; ba.V = s->Vs; ba.H = H; ba.target_ctas = ctas; ba.max_splits = s->dt_max_splits; ba.msplits = s->me_splits;
+  ba.out = s->dt_part; ba.dbias_out = nullptr;
+  CK(launch_ce_bwd_umma(s->maps, ba, true, st));
+  CK(launch_shard_dt_unpack(s->dt_part, s->counts, s->counts_in, s->n_ranks, s->Mcap, s->cap, H, xtiles, ctas, s->dt_max_splits,
+                            dt_out, st));
+  ba.out = s->p_dE; ba.dbias_out = s->p_dbias;
+  CK(launch_ce_bwd_umma(s->maps, ba, false, st));
+  CK(launch_grad_reduce(s->d_jobs, 2, grad_reduce_blocks(s->me_splits, s->Vs * H), st));
+  return 0;
+}
+extern "C" const float* b4r_shard_step_stats(b4r_shard* s) { return s ? s->step_stats : nullptr; }
+extern "C" const float* b4r_shard_lse(b4r_shard* s) { return s ? s->lse : nullptr; }
+extern "C" const int32_t* b4r_shard_counts(b4r_shard* s) { return s ? s->counts : nullptr; }
 
 // ------------------------------------------------------------------------------------------------ pooler
 __global__ void pooler_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,

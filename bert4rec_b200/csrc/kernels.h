@@ -249,6 +249,25 @@ struct CeBwdArgs {
 bool ce_bwd_umma_supported(int H);
 int ce_bwd_umma_xtile(int H);   // rows of a streamed tile (128, or 64 for hidden 256): the unit of the vocabulary split count
 cudaError_t launch_ce_bwd_umma(const CeUmmaMaps& maps, const CeBwdArgs& a, bool row_is_m, cudaStream_t st);
+// split count the generation-2 CE passes choose on the device (row tiles of 128): (row tiles x splits) fits one wave of target_ctas
+__host__ __device__ inline int ce_dyn_splits128(int n_rows, int ntiles, int target_ctas, int max_splits) {
+  int mt = (n_rows + 127) / 128;
+  if (mt < 1) mt = 1;
+  int vs = target_ctas / mt;
+  if (vs > ntiles) vs = ntiles;
+  if (vs > max_splits) vs = max_splits;
+  if (vs < 1) vs = 1;
+  return vs;
+}
+
+// ------------------------------------------------------------------ vocabulary-sharded projection, row-side helpers (k_shard.cu)
+cudaError_t launch_shard_pack(const bf16* rows_in, const int* labels_in, const float* w_in, const int* mult_in, const int* counts_in,
+                              int n, int M_cap, int H, int v_begin, bf16* rows, int* lab_local, int* lab_global, float* w, int* mult,
+                              int* counts, cudaStream_t st);
+cudaError_t launch_shard_part_merge(const float* part, const int* counts, int M_cap, int ntiles, int target_ctas, int max_splits,
+                                    int v_begin, float* out, cudaStream_t st);
+cudaError_t launch_shard_dt_unpack(const float* dt_part, const int* counts, const int* counts_in, int n, int M_cap, int cap, int H,
+                                   int xtiles, int target_ctas, int max_splits, float* out, cudaStream_t st);
 // MLM transform backward over rows: dt = sum_s dt_part[s] ; LN bwd ; gelu bwd -> d_tpre (bf16) ; partials {dgamma,dbeta,dbias}
 cudaError_t launch_head_bwd_rows(const float* dt_part, int nsplit, size_t split_stride, const bf16* t_pre,
                                  const bf16* act, const float* mean, const float* rstd, const float* gamma,

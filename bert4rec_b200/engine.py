@@ -241,6 +241,11 @@ class Session:
     def backward(self, seed=0, step=0, step_counter=None):
         check(self.lib.b4r_backward(self.h, int(seed), int(step), _ptr(step_counter), _stream()))
 
+    def backward_from_dt(self, dt, seed=0, step=0, step_counter=None):
+        """Backward from an externally supplied gradient of the transformed rows (vocabulary-sharded projection)."""
+        assert dt.dtype == torch.float32 and dt.is_contiguous() and tuple(dt.shape) == (self.Mcap, self.store.H)
+        check(self.lib.b4r_backward_from_dt(self.h, _ptr(dt), int(seed), int(step), _ptr(step_counter), _stream()))
+
     def pooled_output(self):
         out = torch.empty(self.B, self.store.H, dtype=torch.float32, device=self.store.device)
         check(self.lib.b4r_pooled_output(self.h, _ptr(out), _stream()))
@@ -293,6 +298,15 @@ class Session:
     def step_stats(self):
         return self._view(self.lib.b4r_step_stats(self.h), (8,), torch.float32)
 
+    def labels(self):
+        return self._view(self.lib.b4r_mlm_labels(self.h), (self.Mcap,), torch.int32)
+
+    def row_weights(self):
+        return self._view(self.lib.b4r_mlm_row_weights(self.h), (self.Mcap,), torch.float32)
+
+    def row_mult(self):
+        return self._view(self.lib.b4r_mlm_row_mult(self.h), (self.Mcap,), torch.int32)
+
     def attn_keep_mask(self, layer):
         """[B, N, S, S] uint8 keep mask of the attention-prob dropout of the last training forward."""
         w = C.c_int()
@@ -330,6 +344,90 @@ class Session:
             tag, cnt, ms = line.rsplit(" ", 2)
             out[tag] = (int(cnt), float(ms))
         return out
+
+
+def shard_range(vocab, world, rank):
+    """Catalogue rows [lo, hi) of the tied projection owned by ``rank`` (contiguous, equal ceil(V/world) slices)."""
+    per = (vocab + world - 1) // world
+    return min(vocab, rank * per), min(vocab, (rank + 1) * per)
+
+
+class VocabShard:
+    """One rank's slice [v_begin, v_end) of the tied output projection over the masked-slot rows of all ``n_ranks`` ranks
+    (SURVEY 8e large catalogues; b4r_shard_* in include/b4r.h).  The collectives stay with the caller."""
+
+    def __init__(self, store, n_ranks, rows_per_rank, v_begin, v_end):
+        self.store, self.lib = store, store.lib
+        self.n, self.Mcap, self.cap = n_ranks, rows_per_rank, n_ranks * rows_per_rank
+        self.v_begin, self.v_end = int(v_begin), int(v_end)
+        store.ensure_training_buffers()
+        H, V = store.H, store.V
+        nbytes = self.lib.b4r_shard_workspace_bytes(H, V, n_ranks, rows_per_rank, self.v_begin, self.v_end)
+        if nbytes == 0:
+            raise ValueError(self.lib.b4r_last_error().decode())
+        with torch.cuda.device(store.device):
+            self.ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=store.device)
+            off = (-self.ws.data_ptr()) % 256
+            h = C.c_void_p()
+            check(self.lib.b4r_shard_create(H, V, n_ranks, rows_per_rank, self.v_begin, self.v_end,
+                                            _ptr(store.seg("word_embeddings", store.shadow)), _ptr(store.seg("head/output_bias")),
+                                            _ptr(store.seg("word_embeddings", store.grads)),
+                                            _ptr(store.seg("head/output_bias", store.grads)),
+                                            C.c_void_p(self.ws.data_ptr() + off), nbytes, C.byref(h)))
+        self.h = h
+        self._keep = None
+
+    def close(self):
+        if self.h:
+            self.lib.b4r_shard_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def pack(self, rows, labels, weights, mult, counts):
+        """All-gathered session buffers: rows bf16 [n, Mcap, H]; labels/mult int32, weights fp32 [n, Mcap]; counts int32 [n, 2]."""
+        H = self.store.H
+        assert rows.dtype == torch.bfloat16 and rows.numel() == self.cap * H and rows.is_contiguous()
+        assert labels.dtype == torch.int32 and mult.dtype == torch.int32 and weights.dtype == torch.float32
+        assert labels.numel() == self.cap and mult.numel() == self.cap and weights.numel() == self.cap
+        assert counts.dtype == torch.int32 and counts.numel() == 2 * self.n and counts.is_contiguous()
+        self._keep = (rows, labels, weights, mult, counts)
+        check(self.lib.b4r_shard_pack(self.h, _ptr(rows), _ptr(labels), _ptr(weights), _ptr(mult), _ptr(counts), _stream()))
+
+    def partial(self, out=None):
+        if out is None:
+            out = torch.empty(self.cap, 6, dtype=torch.float32, device=self.store.device)
+        check(self.lib.b4r_shard_ce_partial(self.h, _ptr(out), _stream()))
+        return out
+
+    def merge(self, parts, global_batch, stats=None):
+        assert parts.dtype == torch.float32 and parts.is_contiguous() and parts.numel() % (self.cap * 6) == 0
+        check(self.lib.b4r_shard_ce_merge(self.h, _ptr(parts), parts.numel() // (self.cap * 6), int(global_batch), _ptr(stats),
+                                          _stream()))
+
+    def backward(self, dt_out=None, zero_all=True):
+        if dt_out is None:
+            dt_out = torch.empty(self.n, self.Mcap, self.store.H, dtype=torch.float32, device=self.store.device)
+        assert dt_out.dtype == torch.float32 and dt_out.is_contiguous() and dt_out.numel() == self.cap * self.store.H
+        check(self.lib.b4r_shard_ce_backward(self.h, _ptr(dt_out), int(bool(zero_all)), _stream()))
+        return dt_out
+
+    def _view(self, ptr, n, dtype):
+        off = ptr - self.ws.data_ptr()
+        return self.ws[off:off + n * torch.empty(0, dtype=dtype).element_size()].view(dtype)
+
+    def step_stats(self):
+        return self._view(self.lib.b4r_shard_step_stats(self.h), 8, torch.float32)
+
+    def lse(self):
+        return self._view(self.lib.b4r_shard_lse(self.h), self.cap, torch.float32)
+
+    def counts(self):
+        return self._view(self.lib.b4r_shard_counts(self.h), 2, torch.int32)
 
 
 def dropout_keep_mask(rows, cols, rate, seed, site, layer, step, device):

@@ -106,6 +106,8 @@ class BERT4RecModel:
         self._host_step = 0
         self.stop_training = False
         self.distributed = False
+        self.vocab_sharded = False
+        self._shards = {}
         self.use_cuda_graph = True
         self._graphs = {}
         # data-parallel step as ONE graph with the NCCL all-reduce captured inside: opt-in only (B4R_DP_SINGLE_GRAPH=1).  Measured
@@ -220,6 +222,8 @@ class BERT4RecModel:
             # flat gradient buffer (first element of the frozen pooler segment, which has no gradient)
             nt = self.store.n_trainable
             self._count = self.store.grads[nt:nt + 1]
+            # large catalogues: the tied output projection is sharded by vocabulary rows over the ranks
+            self.vocab_sharded = bool(kwargs.get("vocab_sharded", os.environ.get("B4R_VOCAB_SHARDED")))
 
     @property
     def metrics_names(self):
@@ -259,7 +263,12 @@ class BERT4RecModel:
         P = d["masked_lm_positions"].shape[1]
         sess = self.store.session(B, S, P)
         stats = self._stats_buf("train")
-        if not self.use_cuda_graph:
+        if self.distributed and self.vocab_sharded:
+            self._fwd_bwd_sharded(sess, d, stats)   # eager: five collectives inside the step
+            self._all_reduce(sess)
+            self._count.copy_(self._shard_of(sess).step_stats()[1:2])   # global valid slots (same on every rank)
+            self._update(self._count)
+        elif not self.use_cuda_graph:
             self._fwd_bwd(sess, d, stats)
             self._reduce_and_update(sess)
         else:
@@ -338,6 +347,55 @@ class BERT4RecModel:
         sess.backward(seed=self._seed, step=0, step_counter=ctr)
         if self.distributed:
             self._count.copy_(sess.step_stats()[1:2])   # inside the captured graph: rides along with the gradients
+
+    def _shard_of(self, sess):
+        import torch.distributed as dist
+        from bert4rec_b200.engine import VocabShard, shard_range
+        sh = self._shards.get(sess.Mcap)
+        if sh is None:
+            world, me = dist.get_world_size(), dist.get_rank()
+            lo, hi = shard_range(self.store.V, world, me)
+            if lo >= hi:
+                raise ValueError(f"vocabulary of {self.store.V} rows cannot be sharded over {world} ranks")
+            sh = self._shards[sess.Mcap] = VocabShard(self.store, world, sess.Mcap, lo, hi)
+            dev, H, n = self.device, self.store.H, world
+            sh.buf = {"rows": torch.empty(n, sess.Mcap, H, dtype=torch.bfloat16, device=dev),
+                      "meta_in": torch.empty(3 * sess.Mcap + 2, dtype=torch.int32, device=dev),
+                      "meta": torch.empty(n, 3 * sess.Mcap + 2, dtype=torch.int32, device=dev),
+                      "part": torch.empty(n * sess.Mcap, 6, dtype=torch.float32, device=dev),
+                      "parts": torch.empty(n, n * sess.Mcap, 6, dtype=torch.float32, device=dev),
+                      "dt_all": torch.empty(n, sess.Mcap, H, dtype=torch.float32, device=dev),
+                      "dt": torch.empty(sess.Mcap, H, dtype=torch.float32, device=dev)}
+        return sh
+
+    def _fwd_bwd_sharded(self, sess, d, stats):
+        """Forward + backward with the tied output projection SHARDED by vocabulary rows: all-gather the
+        transformed rows (+ labels / weights / counts) of every rank, score them against the local catalogue slice, exchange
+        and merge the per-row softmax partials, run the projection backward on the slice (its table-gradient slice is complete)
+        and reduce-scatter the partial row gradients back to the ranks that own the rows."""
+        import torch.distributed as dist
+        ctr = self.store.step_counter
+        sess.select(d["masked_lm_positions"], d["masked_lm_ids"], d["masked_lm_weights"], mode=0, want_aux=self._want_sca)
+        sess.encode(d["input_word_ids"], d["input_mask"], training=True, seed=self._seed, step=0, step_counter=ctr)
+        sess.transform()
+        sh = self._shard_of(sess)
+        b, M = sh.buf, sess.Mcap
+        torch.cat([sess.labels(), sess.row_weights().view(torch.int32), sess.row_mult(), sess.counts()], out=b["meta_in"])
+        dist.all_gather_into_tensor(b["rows"], sess.mlm_hidden())
+        dist.all_gather_into_tensor(b["meta"], b["meta_in"])
+        meta = b["meta"]
+        # the pack kernel wants each field contiguous over the ranks
+        labels = meta[:, :M].contiguous()
+        weights = meta[:, M:2 * M].contiguous().view(torch.float32)
+        mult = meta[:, 2 * M:3 * M].contiguous()
+        counts = meta[:, 3 * M:3 * M + 2].contiguous()
+        sh.pack(b["rows"], labels, weights, mult, counts)
+        sh.partial(b["part"])
+        dist.all_gather_into_tensor(b["parts"], b["part"])
+        sh.merge(b["parts"], sess.B * sh.n, stats)
+        sh.backward(b["dt_all"], zero_all=True)
+        dist.reduce_scatter_tensor(b["dt"], b["dt_all"])
+        sess.backward_from_dt(b["dt"], seed=self._seed, step=0, step_counter=ctr)
 
     def test_step(self, inputs):
         """fwd(inference) -> fused CE + accuracies, no update (bert4rec_model.py:175-192)."""

@@ -79,6 +79,10 @@ int b4r_mlm_loss(b4r_session* s, float* stats, void* stream);
 int b4r_mlm_logits(b4r_session* s, float* out, void* stream);
 /* tape.gradient of the SUM loss over all trainable variables (bert4rec_model.py:166-167) -> grads (flat, fp32). */
 int b4r_backward(b4r_session* s, uint64_t seed, uint32_t step, const int64_t* step_counter, void* stream);
+/* The same backward when the gradient of the transformed rows comes from OUTSIDE (vocabulary-sharded projection below):
+ * dt fp32 [batch*max_pred + batch, hidden] in this session's row order (rows behind n_valid are ignored).  The cross-entropy backward is skipped; the tied-table and
+ * output-bias gradients already in `grads` (written by b4r_shard_ce_backward) are kept and the embedding backward adds to them. */
+int b4r_backward_from_dt(b4r_session* s, const float* dt, uint64_t seed, uint32_t step, const int64_t* step_counter, void* stream);
 /* tanh pooler on token 0 (bert4rec_encoder.py:224-226) -> out fp32 [batch, hidden] */
 int b4r_pooled_output(b4r_session* s, float* out, void* stream);
 
@@ -105,6 +109,35 @@ int b4r_rank_full(b4r_session* s, int v_begin, int v_end, int32_t* beat_out, voi
  * of every rank, counts per shard here and all-reduces the counts (rank = 1 + sum over shards). */
 int b4r_rank_full_ext(b4r_session* s, const void* t_rows, const int32_t* labels, const float* gt_scores, const int32_t* counts2,
                       int rows_cap, int v_begin, int v_end, int32_t* beat_out, void* stream);
+/* ---- vocabulary-sharded tied projection for TRAINING (large catalogues; the reference builds the whole [B,P,V] logits on
+ * one device, bert4rec_model.py:139-147 + trainer_utils.py:12-23).  One b4r_shard per rank owns catalogue rows
+ * [v_begin, v_end) and works on the masked-slot rows of ALL n_ranks ranks (rows_per_rank = the session's row capacity,
+ * batch*max_pred + batch, identical on every rank):
+ *   all-gather {b4r_mlm_hidden, b4r_mlm_labels, b4r_mlm_row_weights, b4r_mlm_row_mult, b4r_mlm_counts}  -> b4r_shard_pack
+ *   b4r_shard_ce_partial -> all-gather the [rows][6] partials -> b4r_shard_ce_merge (loss / accuracy of the global batch)
+ *   b4r_shard_ce_backward -> reduce-scatter(SUM) dt_out -> b4r_backward_from_dt ; all-reduce(SUM) the flat gradients.
+ * The collectives are the caller's (torch.distributed / NCCL on the same stream).  table_bf16 / output_bias / grad_table /
+ * grad_bias point at the FULL [vocab, hidden] / [vocab] arrays of this rank. */
+typedef struct b4r_shard b4r_shard;
+size_t b4r_shard_workspace_bytes(int hidden, int vocab, int n_ranks, int rows_per_rank, int v_begin, int v_end);
+int b4r_shard_create(int hidden, int vocab, int n_ranks, int rows_per_rank, int v_begin, int v_end, const void* table_bf16,
+                     const float* output_bias, float* grad_table, float* grad_bias, void* workspace, size_t workspace_bytes,
+                     b4r_shard** out);
+void b4r_shard_destroy(b4r_shard* s);
+/* rows_in bf16 [n_ranks][rows_per_rank][hidden]; labels_in int32, weights_in fp32, mult_in int32 [n_ranks][rows_per_rank];
+ * counts_in int32 [n_ranks][2] = each rank's {n_valid, n_rows} (must stay alive until b4r_shard_ce_backward). */
+int b4r_shard_pack(b4r_shard* s, const void* rows_in, const int32_t* labels_in, const float* weights_in, const int32_t* mult_in,
+                   const int32_t* counts_in, void* stream);
+/* part_out fp32 [n_ranks*rows_per_rank][6] = {max, sum exp(x-max), label logit | -inf, best logit, best GLOBAL id (int bits), 0} */
+int b4r_shard_ce_partial(b4r_shard* s, float* part_out, void* stream);
+/* parts fp32 [n_shards][n_ranks*rows_per_rank][6]; stats: optional running statistics, layout of b4r_mlm_loss */
+int b4r_shard_ce_merge(b4r_shard* s, const float* parts, int n_shards, int global_batch, float* stats, void* stream);
+/* dt_out fp32 [n_ranks][rows_per_rank][hidden]; zero_all: zero the whole table / bias gradient before writing the shard's slice */
+int b4r_shard_ce_backward(b4r_shard* s, float* dt_out, int zero_all, void* stream);
+const float* b4r_shard_step_stats(b4r_shard* s);   /* float[8], layout of b4r_step_stats, GLOBAL batch */
+const float* b4r_shard_lse(b4r_shard* s);          /* fp32 [n_ranks*rows_per_rank] packed row order */
+const int32_t* b4r_shard_counts(b4r_shard* s);     /* int32[2] = {n_valid, n_rows} over all ranks */
+
 /* HR@k / NDCG@k / MAP from a rank histogram (evaluation_metrics.py:47-112): out fp64 [2 + 2*nk] =
  * {n, NDCG@k..., HR@k..., MAP}; ks: device int32 [nk]. */
 int b4r_metrics_from_hist(const uint64_t* hist, int max_rank, const int32_t* ks, int nk, double* out, void* stream);
@@ -114,6 +147,9 @@ const void* b4r_sequence_output(b4r_session* s, int layer);  /* bf16 [batch*seq_
 const void* b4r_mlm_hidden(b4r_session* s);                  /* bf16 [n_rows, hidden] transformed rows */
 const int32_t* b4r_mlm_counts(b4r_session* s);               /* int32[2] = {n_valid, n_rows} */
 const int32_t* b4r_mlm_rows(b4r_session* s);                 /* int32 [n_rows] flat row index b*seq_len+pos */
+const int32_t* b4r_mlm_labels(b4r_session* s);               /* int32 [n_rows] label id of the row */
+const float* b4r_mlm_row_weights(b4r_session* s);            /* fp32 [n_rows] masked_lm_weights of the row */
+const int32_t* b4r_mlm_row_mult(b4r_session* s);             /* int32 [n_rows] slots the row stands for (all-slot accuracy) */
 float* b4r_step_stats(b4r_session* s);  /* float[8] {loss_sum, n_valid, correct_masked, correct_all, n_all} of the last step */
 const uint64_t* b4r_attn_keep_bits(b4r_session* s, int layer, int* words_per_row);
 /* saved activation of encoder layer `layer` by name ("x0","qkv","ctx","a_pre","y","h_pre","h","o_pre","out": bf16

@@ -128,3 +128,15 @@ def test_dp_evaluation_metrics_merge_over_gloo():
         m.update_many(ranks)
     for m in ref:
         assert abs(ret["merged"][m.name] - m.result()) < 1e-12, (m.name, ret["merged"][m.name], m.result())
+
+
+def test_shard_range_partitions_the_catalogue():
+    """Host logic of the vocabulary-sharded projection: contiguous, disjoint, covering slices (engine.shard_range)."""
+    from bert4rec_b200.engine import shard_range
+    for V in (1, 7, 1203, 12004, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(V, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == V
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(lo <= hi for lo, hi in spans)
+            assert max(hi - lo for lo, hi in spans) == -(-V // world)
