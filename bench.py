@@ -320,6 +320,8 @@ def run_b200(args, w):
                            "frac_of_bf16_sustained": achieved_tf / tf_sus, "peak_source": src},
         }
         line["roofline"] = roofline_block(model, sess, w, dev_batches, args, hbm, tf_burst, src)
+        if world == 1:
+            line["host_path"] = host_path_block(w, model, eval_batches[0])
         if world == 1 and not args.no_cpu_baseline:
             sample = min(B, 64) if S >= 200 else B
             v, ms, bs = cpu_reference(w, 3, 1, sample_batch=sample)
@@ -328,6 +330,54 @@ def run_b200(args, w):
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def host_path_block(w, model, eval_batch):
+    """Host data path of the loop: Cloze masking and negative sampling on the C++ threads of libb4r.so, timed
+    on this box's cores next to the per-sequence Python (the product's restatement of the reference functions; the
+    reference's own list-scan versions are slower still), and the 100-negative evaluation INCLUDING the host sampling."""
+    import time
+    from bert4rec_b200.dataloaders import host_native as hn, dataloader_utils as du, samplers
+    from bert4rec_b200.evaluation import BERT4RecEvaluator
+    V, S, P, B = w["vocab_size"], w["seq_len"], w["max_pred"], w["batch"]
+    rng = np.random.RandomState(11)
+    n = 64 * B
+    vals = rng.randint(3, V, size=n * S).astype(np.int64)
+    off = np.arange(n + 1, dtype=np.int64) * S
+    seeds = np.arange(n, dtype=np.uint64)
+    args = (S, P, 1, [2, 0], V, w["mask_prob"], 1.0, 0.0)
+    hn.cloze_mask_batch((vals[:B * S], off[:B + 1]), *args, seeds=seeds[:B])
+    t0 = time.perf_counter(); hn.cloze_mask_batch((vals, off), *args, seeds=seeds); t_native = time.perf_counter() - t0
+    m = 2 * B
+    t0 = time.perf_counter()
+    for i in range(m):
+        du.apply_dynamic_masking_task(vals[i * S:(i + 1) * S], P, 1, [2, 0], V, w["mask_prob"], 1.0, 0.0, seed=i)
+    t_py = time.perf_counter() - t0
+    sm = samplers.get("random", vocab=list(range(3, V)), sample_size=100, seed=3)
+    ev = BERT4RecEvaluator(sampler=sm)
+    ev.build_candidates(eval_batch, as_array=True)
+    t0 = time.perf_counter()
+    for _ in range(4):
+        ev.build_candidates(eval_batch, as_array=True)
+    t_samp = (time.perf_counter() - t0) / 4
+    hist = eval_batch["labels"][0].tolist()
+    t0 = time.perf_counter()
+    for i in range(32):
+        sm.sample(without=hist + [5 + i])
+    t_samp_py = (time.perf_counter() - t0) / 32
+    ev.evaluate_batch(model, eval_batch)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        ev.evaluate_batch(model, eval_batch)
+    torch.cuda.synchronize()
+    t_eval = (time.perf_counter() - t0) / 4
+    return {"threads": os.cpu_count(),
+            "cloze_masking_seq_per_s": {"native_batch": n / t_native, "python_per_sequence": m / t_py},
+            "negative_sampling_seq_per_s": {"native_batch": B / t_samp, "python_per_sequence": 1.0 / t_samp_py,
+                                            "sampler": "RandomSampler(100 of V, without = history + [gt]), exact numpy legacy stream"},
+            "eval_with_host_sampling_seq_per_s": B / t_eval,
+            "note": "bit-exact with the reference's python `random` / np.random streams (tests/test_host_native.py)"}
 
 
 def enc_ctas(w):

@@ -23,6 +23,7 @@ static int fail(const char* fmt, ...) {
   va_end(ap);
   return 1;
 }
+namespace b4r { void set_last_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); } }   // host_data.cu
 #define CK(expr)                                                                                   \
   do {                                                                                             \
     cudaError_t e__ = (expr);                                                                      \

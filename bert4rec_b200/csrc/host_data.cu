@@ -1,0 +1,433 @@
+// Host data path of the hot loop: Cloze masking and negative sampling for a whole batch, in C++ threads,
+// BIT-EXACT with the reference's Python:
+//   * apply_dynamic_masking_task + process_element layout   (dataloader_utils.py:186-261, bert4rec_preprocessor.py:47-116)
+//     -- CPython's `random` module: MT19937 seeded by init_by_array(seed words), random() = 53-bit from two draws,
+//        shuffle / choice through _randbelow (rejection on getrandbits(bit_length(n)));
+//   * RandomSampler.sample / PopularSampler.sample / PopularRandomSampler.sample
+//     (random_sampler.py:63-79, popular_sampler.py:53-71, popular_random_sampler.py:77-117)
+//     -- numpy's LEGACY RandomState: np.random.seed(int) = init_genrand, choice(replace=False) = permutation(n)[:size] with the
+//        masked-rejection `random_interval`, choice(replace=True) = masked-rejection randint, choice(p=...) = cumsum / searchsorted.
+// No GPU involved; nothing here touches CUDA.  Errors mirror the ValueErrors of the Python code (b4r_last_error()).
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/b4r.h"
+
+namespace b4r { void set_last_error(const char* msg); }
+
+namespace {
+
+struct MT19937 {
+  uint32_t mt[624];
+  int pos;
+  void init_genrand(uint32_t s) {   // numpy mt19937_seed / reference MT init
+    mt[0] = s;
+    for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    pos = 624;
+  }
+  void init_by_array(const uint32_t* key, int len) {   // CPython random_seed for an int
+    init_genrand(19650218u);
+    int i = 1, j = 0;
+    for (int k = 624 > len ? 624 : len; k; --k) {
+      mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+      ++i; ++j;
+      if (i >= 624) { mt[0] = mt[623]; i = 1; }
+      if (j >= len) j = 0;
+    }
+    for (int k = 623; k; --k) {
+      mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+      ++i;
+      if (i >= 624) { mt[0] = mt[623]; i = 1; }
+    }
+    mt[0] = 0x80000000u;
+    pos = 624;
+  }
+  void refill() {
+    static const uint32_t mag[2] = {0u, 0x9908b0dfu};
+    int kk = 0;
+    for (; kk < 624 - 397; ++kk) {
+      const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+      mt[kk] = mt[kk + 397] ^ (y >> 1) ^ mag[y & 1u];
+    }
+    for (; kk < 623; ++kk) {
+      const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+      mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ mag[y & 1u];
+    }
+    const uint32_t y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+    mt[623] = mt[396] ^ (y >> 1) ^ mag[y & 1u];
+    pos = 0;
+  }
+  uint32_t next32() {
+    if (pos >= 624) refill();
+    uint32_t y = mt[pos++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+  double next_double() {   // CPython random() and numpy random_sample(): identical construction
+    const uint32_t a = next32() >> 5, b = next32() >> 6;
+    return (a * 67108864.0 + b) / 9007199254740992.0;
+  }
+};
+
+// ---- CPython `random`
+inline void py_seed(MT19937& g, uint64_t seed) {
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  g.init_by_array(key, key[1] ? 2 : 1);
+}
+inline int bit_length(uint64_t n) { return n ? 64 - __builtin_clzll(n) : 0; }
+inline uint64_t py_randbelow(MT19937& g, uint64_t n) {   // n >= 1, n < 2^32 here
+  const int k = bit_length(n);
+  uint64_t r;
+  if (k <= 32) {
+    do { r = g.next32() >> (32 - k); } while (r >= n);
+  } else {   // getrandbits(k) for 32 < k <= 64: low word first
+    do {
+      const uint64_t lo = g.next32();
+      const uint64_t hi = g.next32() >> (64 - k);
+      r = lo | (hi << 32);
+    } while (r >= n);
+  }
+  return r;
+}
+
+// ---- numpy legacy RandomState
+inline uint64_t np_interval(MT19937& g, uint64_t max) {   // random_interval: uniform on [0, max]
+  if (max == 0) return 0;
+  uint64_t mask = max;
+  mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16; mask |= mask >> 32;
+  uint64_t v;
+  if (max <= 0xffffffffull) {
+    while ((v = (g.next32() & mask)) > max) {}
+  } else {
+    while ((v = ((((uint64_t)g.next32()) << 32 | g.next32()) & mask)) > max) {}
+  }
+  return v;
+}
+
+template <class F>
+int run_parallel(int n, int n_threads, F&& body) {   // body(i) -> 0 or error; first error wins
+  if (n_threads < 1) n_threads = (int)std::thread::hardware_concurrency();
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > n) n_threads = n > 0 ? n : 1;
+  std::atomic<int> next(0), err(0);
+  auto worker = [&]() {
+    for (;;) {
+      const int i0 = next.fetch_add(16);
+      if (i0 >= n || err.load()) return;
+      const int i1 = i0 + 16 < n ? i0 + 16 : n;
+      for (int i = i0; i < i1; ++i) {
+        const int e = body(i);
+        if (e) { err.store(e); return; }
+      }
+    }
+  };
+  if (n_threads == 1) { worker(); return err.load(); }
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; ++t) th.emplace_back(worker);
+  for (auto& t : th) t.join();
+  return err.load();
+}
+
+// first error of a call (worker threads race for it); copied into the caller's thread-local b4r_last_error() at the end
+struct Err {
+  std::atomic<bool> set{false};
+  char msg[400];
+  int fail(const char* fmt, ...) {
+    char buf[400];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    bool expect = false;
+    if (set.compare_exchange_strong(expect, true)) memcpy(msg, buf, sizeof(buf));
+    return 1;
+  }
+  int finish(int rc) {
+    if (rc) b4r::set_last_error(set.load() ? msg : "host data path failed");
+    return rc;
+  }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ Cloze masking
+extern "C" int b4r_host_cloze_mask_batch(const int64_t* tokens, const int64_t* offsets, const uint64_t* seeds, int n, int max_seq_len,
+                                         int max_pred, int64_t mask_id, int64_t pad_id, const int64_t* special_ids, int n_special,
+                                         int64_t vocab_size, double selection_rate, double mask_token_rate, double random_token_rate,
+                                         int64_t* labels, int64_t* input_word_ids, int64_t* input_mask, int64_t* masked_lm_ids,
+                                         int64_t* masked_lm_positions, int64_t* masked_lm_weights, int n_threads) {
+  Err err;
+  if (!tokens || !offsets || !seeds || n < 0 || max_seq_len < 1 || max_pred < 1 || n_special < 0 || (n_special && !special_ids))
+    return err.finish(err.fail("b4r_host_cloze_mask_batch: bad argument"));
+  if (!labels || !input_word_ids || !input_mask || !masked_lm_ids || !masked_lm_positions || !masked_lm_weights)
+    return err.finish(err.fail("b4r_host_cloze_mask_batch: null output"));
+  // selectable vocab = [i for i in range(vocab_size) if i not in special]: k-th element by skipping the sorted specials
+  std::vector<int64_t> sp;
+  for (int i = 0; i < n_special; ++i)
+    if (special_ids[i] >= 0 && special_ids[i] < vocab_size) sp.push_back(special_ids[i]);
+  std::sort(sp.begin(), sp.end());
+  sp.erase(std::unique(sp.begin(), sp.end()), sp.end());
+  const int64_t n_selectable = vocab_size - (int64_t)sp.size();
+  const double threshold = mask_token_rate + random_token_rate;
+  const int S = max_seq_len, P = max_pred;
+  auto is_special = [&](int64_t v) {
+    for (int i = 0; i < n_special; ++i)
+      if (special_ids[i] == v) return true;
+    return false;
+  };
+  const int rc = run_parallel(n, n_threads, [&](int b) -> int {
+    const int64_t* seq = tokens + offsets[b];
+    const int64_t len64 = offsets[b + 1] - offsets[b];
+    if (len64 < 0 || len64 > S) return err.fail("sequence %d has %lld tokens, more than max_seq_len %d", b, (long long)len64, S);
+    const int len = (int)len64;
+    int64_t* lab = labels + (size_t)b * S; int64_t* ids = input_word_ids + (size_t)b * S; int64_t* msk = input_mask + (size_t)b * S;
+    int64_t* mid = masked_lm_ids + (size_t)b * P; int64_t* mpos = masked_lm_positions + (size_t)b * P;
+    int64_t* mw = masked_lm_weights + (size_t)b * P;
+    for (int i = 0; i < S; ++i) {
+      const bool in = i < len;
+      lab[i] = in ? seq[i] : pad_id; ids[i] = in ? seq[i] : pad_id; msk[i] = in ? 1 : pad_id;
+    }
+    for (int i = 0; i < P; ++i) { mid[i] = pad_id; mpos[i] = pad_id; mw[i] = pad_id; }
+    MT19937 g;
+    py_seed(g, seeds[b]);
+    int n_plain = 0;
+    for (int i = 0; i < len; ++i) n_plain += is_special(seq[i]) ? 0 : 1;
+    int n_pred = (int)((double)n_plain * selection_rate);   // int(len * rate): truncation of the double product
+    if (n_pred < 1) n_pred = 1;
+    if (n_pred > P) n_pred = P;
+    // random.shuffle(list(range(n_plain)))
+    int order_stack[512];
+    std::vector<int> order_heap;
+    int* order = order_stack;
+    if (n_plain > 512) { order_heap.resize(n_plain); order = order_heap.data(); }
+    for (int i = 0; i < n_plain; ++i) order[i] = i;
+    for (int i = n_plain - 1; i >= 1; --i) {
+      const int j = (int)py_randbelow(g, (uint64_t)i + 1);
+      const int t = order[i]; order[i] = order[j]; order[j] = t;
+    }
+    const int n_sel = n_pred < n_plain ? n_pred : n_plain;
+    std::sort(order, order + n_sel);
+    for (int k = 0; k < n_sel; ++k) {
+      const int idx = order[k];
+      const double rn = g.next_double();
+      int64_t token = seq[idx];
+      if (rn < threshold) {
+        if (n_selectable < 1) return err.fail("Cannot choose from an empty sequence (no selectable vocabulary)");
+        int64_t v = (int64_t)py_randbelow(g, (uint64_t)n_selectable);   // random.choice(selectable_vocab)
+        for (size_t s = 0; s < sp.size(); ++s) {
+          if (sp[s] <= v) ++v; else break;
+        }
+        token = v;
+      }
+      if (rn < mask_token_rate) token = mask_id;
+      ids[idx] = token;
+      mid[k] = seq[idx]; mpos[k] = idx; mw[k] = 1;
+    }
+    return 0;
+  });
+  return err.finish(rc);
+}
+
+// ------------------------------------------------------------------------------------------------ negative sampling
+namespace {
+// np.random.choice(pool, size, replace) without p, after np.random.seed(seed)
+int np_choice_uniform(Err& err, MT19937& g, const std::vector<int64_t>& pool, int size, bool replace, int64_t* out,
+                      std::vector<int64_t>& perm) {
+  const int64_t n = (int64_t)pool.size();
+  if (n == 0 && size > 0) return err.fail("'a' cannot be empty unless no samples are taken");
+  if (replace) {
+    for (int i = 0; i < size; ++i) out[i] = pool[(size_t)np_interval(g, (uint64_t)n - 1)];   // randint: masked rejection
+    return 0;
+  }
+  if (size > n) return err.fail("Cannot take a larger sample than population when 'replace=False'");
+  perm.resize((size_t)n);
+  for (int64_t i = 0; i < n; ++i) perm[(size_t)i] = i;
+  if (n - 1 <= 0xffffffffll) {
+    // legacy shuffle of arange(n): j = random_interval(i) = masked rejection on 32-bit draws; the mask (smallest 2^k - 1 >= i)
+    // only changes when i crosses a power of two, so it is carried instead of recomputed
+    uint32_t mask = 0;
+    for (uint64_t m = (uint64_t)(n - 1); m; m >>= 1) mask = (mask << 1) | 1u;
+    for (int64_t i = n - 1; i >= 1; --i) {
+      while ((mask >> 1) >= (uint64_t)i) mask >>= 1;
+      uint32_t j;
+      while ((j = (g.next32() & mask)) > (uint64_t)i) {}
+      const int64_t t = perm[(size_t)i]; perm[(size_t)i] = perm[j]; perm[j] = t;
+    }
+  } else {
+    for (int64_t i = n - 1; i >= 1; --i) {
+      const int64_t j = (int64_t)np_interval(g, (uint64_t)i);
+      const int64_t t = perm[(size_t)i]; perm[(size_t)i] = perm[(size_t)j]; perm[(size_t)j] = t;
+    }
+  }
+  for (int i = 0; i < size; ++i) out[i] = pool[(size_t)perm[(size_t)i]];
+  return 0;
+}
+}  // namespace
+
+// RandomSampler.sample(without=..., seed=...) for n requests: pool = vocab minus without (vocab order kept), one legacy choice.
+// out int64 [n][sample_size].
+extern "C" int b4r_host_sample_random_batch(const int64_t* vocab, int64_t n_vocab, const int64_t* without, const int64_t* without_off,
+                                            const uint32_t* seeds, int n, int sample_size, int allow_duplicates, int64_t* out,
+                                            int n_threads) {
+  Err err;
+  if (!vocab || n_vocab < 0 || !seeds || n < 0 || sample_size < 0 || !out || (without && !without_off))
+    return err.finish(err.fail("b4r_host_sample_random_batch: bad argument"));
+  if (!allow_duplicates && sample_size > n_vocab)
+    return err.finish(err.fail("When no duplicates are allowed in the final sample then the sample size (given sample size: %d)) can "
+                            "not be greater than the length length of the vocab (length of the vocab: %lld)", sample_size,
+                            (long long)n_vocab));
+  // small non-negative ids (the tokenizer's): exclusion by a per-thread mark array instead of a hash set
+  int64_t vmin = 0, vmax = -1;
+  for (int64_t i = 0; i < n_vocab; ++i) {
+    if (i == 0 || vocab[i] < vmin) vmin = vocab[i];
+    if (i == 0 || vocab[i] > vmax) vmax = vocab[i];
+  }
+  const bool dense = n_vocab > 0 && vmin >= 0 && vmax < (1ll << 26);
+  const int rc = run_parallel(n, n_threads, [&](int b) -> int {
+    thread_local std::vector<int64_t> pool, perm;
+    thread_local std::unordered_set<int64_t> ex;
+    thread_local std::vector<uint8_t> mark;
+    pool.clear();
+    if (without && without_off[b + 1] > without_off[b] && dense) {
+      if ((int64_t)mark.size() < vmax + 1) mark.assign((size_t)vmax + 1, 0);
+      for (int64_t k = without_off[b]; k < without_off[b + 1]; ++k)
+        if (without[k] >= 0 && without[k] <= vmax) mark[(size_t)without[k]] = 1;
+      pool.reserve((size_t)n_vocab);
+      for (int64_t i = 0; i < n_vocab; ++i)
+        if (!mark[(size_t)vocab[i]]) pool.push_back(vocab[i]);
+      for (int64_t k = without_off[b]; k < without_off[b + 1]; ++k)
+        if (without[k] >= 0 && without[k] <= vmax) mark[(size_t)without[k]] = 0;
+    } else if (without && without_off[b + 1] > without_off[b]) {
+      ex.clear();
+      ex.insert(without + without_off[b], without + without_off[b + 1]);
+      for (int64_t i = 0; i < n_vocab; ++i)
+        if (!ex.count(vocab[i])) pool.push_back(vocab[i]);
+    } else {
+      pool.assign(vocab, vocab + n_vocab);
+    }
+    MT19937 g;
+    g.init_genrand(seeds[b]);
+    return np_choice_uniform(err, g, pool, sample_size, allow_duplicates != 0, out + (size_t)b * sample_size, perm);
+  });
+  return err.finish(rc);
+}
+
+// PopularSampler.sample(without=...) with a pre-ranked source (set_source ranks by popularity once): the first sample_size items
+// of the ranked list that are not in `without`.  out int64 [n][sample_size], out_len int32 [n] (the list can run short).
+extern "C" int b4r_host_sample_popular_batch(const int64_t* ranked, int64_t n_ranked, const int64_t* without, const int64_t* without_off,
+                                             int n, int sample_size, int64_t* out, int32_t* out_len, int n_threads) {
+  Err err;
+  if (!ranked || n_ranked < 0 || n < 0 || sample_size < 0 || !out || !out_len || (without && !without_off))
+    return err.finish(err.fail("b4r_host_sample_popular_batch: bad argument"));
+  const int rc = run_parallel(n, n_threads, [&](int b) -> int {
+    thread_local std::unordered_set<int64_t> ex;
+    ex.clear();
+    if (without) ex.insert(without + without_off[b], without + without_off[b + 1]);
+    int k = 0;
+    int64_t* o = out + (size_t)b * sample_size;
+    for (int64_t i = 0; i < n_ranked && k < sample_size; ++i)
+      if (!ex.count(ranked[i])) o[k++] = ranked[i];
+    out_len[b] = k;
+    for (int i = k; i < sample_size; ++i) o[i] = 0;
+    return 0;
+  });
+  return err.finish(rc);
+}
+
+// PopularRandomSampler.sample(without=..., seed=...): np.random.choice(vocab, sample_size + |set(without)|, replace, p) then the
+// items of `without` are removed and the first sample_size kept (popular_random_sampler.py:96-117).  out_len: the list can
+// run short when removed items were drawn.  p: the sampler's probability_distribution (float64 [n_vocab]).
+extern "C" int b4r_host_sample_pop_random_batch(const int64_t* vocab, const double* p, int64_t n_vocab, const int64_t* without,
+                                                const int64_t* without_off, const uint32_t* seeds, int n, int sample_size,
+                                                int allow_duplicates, int64_t* out, int32_t* out_len, int n_threads) {
+  Err err;
+  if (!vocab || !p || n_vocab < 1 || !seeds || n < 0 || sample_size < 0 || !out || !out_len || (without && !without_off))
+    return err.finish(err.fail("b4r_host_sample_pop_random_batch: bad argument"));
+  // numpy's checks on p (mtrand.pyx choice): non-negative, no NaN, sums to 1 within sqrt(eps) (Kahan sum)
+  {
+    double sum = 0.0, c = 0.0;
+    for (int64_t i = 0; i < n_vocab; ++i) {
+      if (!(p[i] >= 0.0)) return err.finish(err.fail(p[i] != p[i] ? "probabilities contain NaN" : "probabilities are not non-negative"));
+      const double y = p[i] - c, t = sum + y;
+      c = (t - sum) - y; sum = t;
+    }
+    if (!(sum - 1.0 <= 1.4901161193847656e-08 && 1.0 - sum <= 1.4901161193847656e-08))
+      return err.finish(err.fail("probabilities do not sum to 1"));
+  }
+  int64_t nonzero = 0;
+  for (int64_t i = 0; i < n_vocab; ++i) nonzero += p[i] > 0.0;
+  const int rc = run_parallel(n, n_threads, [&](int b) -> int {
+    thread_local std::unordered_set<int64_t> ex;
+    thread_local std::vector<double> pw, cdf, x;
+    thread_local std::vector<int64_t> found;
+    thread_local std::vector<std::pair<int64_t, int>> uniq;
+    thread_local std::vector<std::pair<int, int64_t>> byidx;
+    ex.clear();
+    if (without) ex.insert(without + without_off[b], without + without_off[b + 1]);
+    const int64_t size = sample_size + (without ? (int64_t)ex.size() : 0);
+    if (!allow_duplicates && size > n_vocab)
+      return err.fail("The given without list (length: %d reduces the vocab (length: %lld) too much to take a sample of size %d "
+                       "(since no duplicates are allowed).", (int)ex.size(), (long long)n_vocab, sample_size);
+    MT19937 g;
+    g.init_genrand(seeds[b]);
+    found.assign((size_t)size, 0);
+    cdf.resize((size_t)n_vocab);
+    auto make_cdf = [&](const double* q) {
+      double acc = 0.0;
+      for (int64_t i = 0; i < n_vocab; ++i) { acc += q[i]; cdf[(size_t)i] = acc; }
+      const double last = cdf[(size_t)n_vocab - 1];
+      for (int64_t i = 0; i < n_vocab; ++i) cdf[(size_t)i] /= last;
+    };
+    if (allow_duplicates) {
+      make_cdf(p);
+      for (int64_t i = 0; i < size; ++i) {
+        const double u = g.next_double();
+        found[(size_t)i] = std::upper_bound(cdf.begin(), cdf.end(), u) - cdf.begin();   // searchsorted(side='right')
+      }
+    } else {
+      if (nonzero < size) return err.fail("Fewer non-zero entries in p than size");
+      pw.assign(p, p + n_vocab);
+      int64_t n_uniq = 0;
+      while (n_uniq < size) {
+        const int64_t m = size - n_uniq;
+        x.resize((size_t)m);
+        for (int64_t i = 0; i < m; ++i) x[(size_t)i] = g.next_double();
+        if (n_uniq > 0)
+          for (int64_t i = 0; i < n_uniq; ++i) pw[(size_t)found[(size_t)i]] = 0.0;
+        make_cdf(pw.data());
+        // new = searchsorted ; keep the FIRST occurrence of every value, in draw order (np.unique(return_index) + sort)
+        uniq.clear();
+        for (int64_t i = 0; i < m; ++i)
+          uniq.emplace_back((int64_t)(std::upper_bound(cdf.begin(), cdf.end(), x[(size_t)i]) - cdf.begin()), (int)i);
+        std::sort(uniq.begin(), uniq.end());
+        byidx.clear();
+        for (size_t i = 0; i < uniq.size(); ++i)
+          if (i == 0 || uniq[i].first != uniq[i - 1].first) byidx.emplace_back(uniq[i].second, uniq[i].first);
+        std::sort(byidx.begin(), byidx.end());
+        for (auto& e : byidx) found[(size_t)n_uniq++] = e.second;
+      }
+    }
+    int k = 0;
+    int64_t* o = out + (size_t)b * sample_size;
+    for (int64_t i = 0; i < size && k < sample_size; ++i) {
+      if (found[(size_t)i] >= n_vocab) return err.fail("internal: sampled index out of range");
+      const int64_t v = vocab[(size_t)found[(size_t)i]];
+      if (!ex.count(v)) o[k++] = v;
+    }
+    out_len[b] = k;
+    for (int i = k; i < sample_size; ++i) o[i] = 0;
+    return 0;
+  });
+  return err.finish(rc);
+}

@@ -63,6 +63,32 @@ class BERT4RecPreprocessor:
         return out
 
     @classmethod
+    def process_batch(cls, sequences, apply_mlm: bool = True, finetuning: bool = False, seeds=None, n_threads: int = 0) -> dict:
+        """``process_element`` for a list of raw sequences at once -> dict of int64 arrays ``[n, max_seq_len]`` /
+        ``[n, max_predictions_per_seq]``.  The Cloze-masking case (the per-epoch work of training) runs on the C++ threads
+        of libb4r.so (``b4r_host_cloze_mask_batch``): with ``seeds[i]`` it is bit-identical to
+        ``process_element(sequences[i], True, False, seed=seeds[i])``; ``seeds=None`` draws fresh entropy per sequence, which
+        is what the reference does (it never passes a seed, bert4rec_preprocessor.py:82-90)."""
+        if not (apply_mlm and not finetuning):
+            els = [cls.process_element(seq, apply_mlm, finetuning) for seq in sequences]
+            keys = els[0].keys() if els else ()
+            return {k: np.stack([np.asarray(e[k], dtype=np.int64) for e in els]) for k in keys}
+        from .. import host_native
+        S = cls.max_seq_len
+        windows = []
+        for seq in sequences:
+            tokens = cls.tokenizer.tokenize(seq)
+            if len(tokens) <= S:
+                windows.append(tokens)
+            else:
+                start = random.randint(0, len(tokens) - S)
+                windows.append(tokens[start:start + S])
+        return host_native.cloze_mask_batch(
+            windows, S, cls.max_predictions_per_seq, cls.mask_token_id, [cls.unk_token_id, cls.pad_token_id],
+            cls.tokenizer.get_vocab_size(), cls.masked_lm_rate, cls.mask_token_rate, cls.random_token_rate, seeds=seeds,
+            pad_token_id=cls.pad_token_id, n_threads=n_threads)
+
+    @classmethod
     def process_dataset(cls, ds, apply_mlm: bool, finetuning: bool):
         return [cls.process_element(seq, apply_mlm, finetuning) for seq in ds]
 

@@ -31,6 +31,37 @@ class BaseSampler(abc.ABC):
     def is_fully_prepared(self) -> bool:
         ...
 
+    def sample_batch(self, withouts: list, sample_size: int = None, as_array: bool = False):
+        """One ``sample(without=w)`` per entry of ``withouts`` (the evaluator's per-slot calls, bert4rec_evaluator.py:98-104).
+        The concrete samplers run the whole batch on the C++ threads of libb4r.so (bit-exact with the per-call results);
+        this generic version is the per-call loop.  ``as_array``: (int64 [n, sample_size] zero-padded, lengths [n])."""
+        if isinstance(withouts, tuple):
+            vals, off = withouts
+            withouts = [vals[off[i]:off[i + 1]].tolist() for i in range(len(off) - 1)]
+        outs = [self.sample(sample_size=sample_size, without=w) for w in withouts]
+        return self._pack(outs, sample_size) if as_array else outs
+
+    @staticmethod
+    def _withouts(withouts):
+        """list of exclusion lists (None = nothing excluded), or a ready CSR pair (values, offsets[n+1]) of numpy arrays"""
+        if isinstance(withouts, tuple):
+            return withouts
+        return [w if w is not None else [] for w in withouts]
+
+    def _pack(self, outs, sample_size):
+        import numpy as np
+        size = self.sample_size if sample_size is None else sample_size
+        arr = np.zeros((len(outs), size), dtype=np.int64)
+        lens = np.zeros(len(outs), dtype=np.int32)
+        for i, o in enumerate(outs):
+            arr[i, :len(o)] = o
+            lens[i] = len(o)
+        return arr, lens
+
+    @staticmethod
+    def _unpack(arr, lens, as_array):
+        return (arr, lens) if as_array else [arr[i, :lens[i]].tolist() for i in range(arr.shape[0])]
+
     def set_source(self, source: list):
         self.source = list(source)
 

@@ -65,6 +65,20 @@ class PopularRandomSampler(BaseSampler):
             drawn = [v for v in drawn if v not in excluded]
         return drawn[:sample_size]
 
+    def sample_batch(self, withouts: list, sample_size: int = None, as_array: bool = False, seed: int = None):
+        """Batch of ``sample(without=w)`` calls on the native host path (``b4r_host_sample_pop_random_batch``): the
+        weighted ``np.random.choice`` of the legacy RandomState restated in C++, bit-exact with the per-call method."""
+        from bert4rec_b200.dataloaders import host_native
+        src, vocab, sample_size = self._resolve(None, None, sample_size)
+        if src is None or vocab is None:
+            raise ValueError("The source and vocab arguments have to be given during the initialization of the sampler "
+                             "when working with the popular random sampler.")
+        if not self.probability_distribution:
+            self._determine_probability_distribution(src, vocab)
+        arr, lens = host_native.sample_pop_random_batch(vocab, self._p_array, self._withouts(withouts), sample_size,
+                                                        self.allow_duplicates, self.seed if seed is None else seed)
+        return self._unpack(arr, lens, as_array)
+
     def set_source(self, source: list):
         super().set_source(source)
         if self.vocab is not None:

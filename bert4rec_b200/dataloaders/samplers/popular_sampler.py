@@ -29,5 +29,14 @@ class PopularSampler(BaseSampler):
             ranked = dataloader_utils.rank_items_by_popularity(ranked)
         return ranked[:sample_size]
 
+    def sample_batch(self, withouts: list, sample_size: int = None, as_array: bool = False):
+        """Batch of ``sample(without=w)`` calls over the stored (already ranked) source on the native host path."""
+        from bert4rec_b200.dataloaders import host_native
+        src, _, sample_size = self._resolve(None, None, sample_size)
+        if src is None:
+            raise ValueError("The source argument has to be provided to the popular sampler but None was given.")
+        arr, lens = host_native.sample_popular_batch(src, self._withouts(withouts), sample_size)
+        return self._unpack(arr, lens, as_array)
+
     def set_source(self, source: list):
         self.source = dataloader_utils.rank_items_by_popularity(list(source))

@@ -39,5 +39,17 @@ class RandomSampler(BaseSampler):
             pool = [v for v in vocab if v not in excluded]
         return np.random.choice(pool, size=sample_size, replace=allow_duplicates).tolist()
 
+    def sample_batch(self, withouts: list, sample_size: int = None, as_array: bool = False, seed: int = None):
+        """Batch of ``sample(without=w)`` calls on the native host path (``b4r_host_sample_random_batch``): same pools, same
+        numpy legacy streams, same draws as the per-call method (every call re-seeds with the same seed; None = entropy)."""
+        from bert4rec_b200.dataloaders import host_native
+        _, vocab, sample_size = self._resolve(None, None, sample_size)
+        if vocab is None:
+            raise ValueError("No vocab or any other source has been given to the random sampler.")
+        arr = host_native.sample_random_batch(vocab, self._withouts(withouts), sample_size, self.allow_duplicates,
+                                              self.seed if seed is None else seed)
+        import numpy as np
+        return self._unpack(arr, np.full(arr.shape[0], arr.shape[1], dtype=np.int32), as_array)
+
     def set_source(self, source: list):
         super().set_source(source if self.allow_duplicates else list(set(source)))

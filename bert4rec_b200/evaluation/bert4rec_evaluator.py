@@ -45,30 +45,34 @@ class BERT4RecEvaluator(BaseEvaluator):
             self.evaluate_batch(model, batch)
         return self._metrics
 
-    def build_candidates(self, test_batch):
-        """Host side of evaluate_batch: returns (candidate lists in slot order, ground truths)."""
+    def build_candidates(self, test_batch, as_array=False):
+        """Host side of evaluate_batch: returns (candidate lists in slot order, ground truths).  All slots of the batch go
+        through ONE ``sampler.sample_batch`` call (C++ threads of libb4r.so for the shipped samplers, bit-exact with the
+        per-slot ``sample(without=history + [gt])`` calls of the reference).  ``as_array``: candidates as an int64
+        [n_slots, sample_size + 1] array when every list has the full length (else the lists)."""
         w = np.asarray(torch.as_tensor(test_batch["masked_lm_weights"]).cpu()) != 0
         ids = np.asarray(torch.as_tensor(test_batch["masked_lm_ids"]).cpu())
-        labels = np.asarray(torch.as_tensor(test_batch["labels"]).cpu())
-        cands, gts = [], []
-        for b in range(w.shape[0]):
-            history = labels[b].tolist()
-            for p in np.nonzero(w[b])[0]:
-                gt = int(ids[b, p])
-                negatives = self.sampler.sample(without=history + [gt])
-                negatives.append(gt)
-                cands.append(negatives)
-                gts.append(gt)
-        return cands, gts
+        labels = np.asarray(torch.as_tensor(test_batch["labels"]).cpu()).astype(np.int64)
+        bs, ps = np.nonzero(w)
+        if bs.size == 0:
+            return [], []
+        gts = ids[bs, ps].astype(np.int64)
+        n, S = bs.size, labels.shape[1]
+        without = np.concatenate([labels[bs], gts[:, None]], axis=1)          # history + [gt] per slot
+        arr, lens = self.sampler.sample_batch((without.reshape(-1), np.arange(n + 1, dtype=np.int64) * (S + 1)), as_array=True)
+        if as_array and bool((lens == arr.shape[1]).all()):
+            return np.concatenate([arr, gts[:, None]], axis=1), gts
+        cands = [arr[i, :lens[i]].tolist() + [int(gts[i])] for i in range(n)]
+        return cands, gts.tolist()
 
     def evaluate_batch(self, model, test_batch: dict):
-        cands, gts = self.build_candidates(test_batch)
-        if not cands:
+        cands, gts = self.build_candidates(test_batch, as_array=True)
+        if len(cands) == 0:
             return
-        lengths = {len(c) for c in cands}
+        lengths = {cands.shape[1]} if isinstance(cands, np.ndarray) else {len(c) for c in cands}
         if len(lengths) == 1:
-            cand = torch.tensor(cands, dtype=torch.int64)
-            _, rank = model.rank_candidates(test_batch, cand, torch.tensor(gts, dtype=torch.int64))
+            cand = torch.as_tensor(np.asarray(cands, dtype=np.int64))
+            _, rank = model.rank_candidates(test_batch, cand, torch.as_tensor(np.asarray(gts, dtype=np.int64)))
             ranks = rank.cpu().numpy().astype(np.int64)
         else:  # ragged candidate lists (e.g. a popular sampler that ran out of items): generic API path
             w = np.asarray(torch.as_tensor(test_batch["masked_lm_weights"]).cpu()) != 0

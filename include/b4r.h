@@ -142,6 +142,31 @@ const int32_t* b4r_shard_counts(b4r_shard* s);     /* int32[2] = {n_valid, n_row
  * {n, NDCG@k..., HR@k..., MAP}; ks: device int32 [nk]. */
 int b4r_metrics_from_hist(const uint64_t* hist, int max_rank, const int32_t* ks, int nk, double* out, void* stream);
 
+/* ---- host data path (no GPU involved, n_threads <= 0: all hardware threads).  Bit-exact with the reference's
+ * Python given the same seeds: CPython `random` (MT19937, init_by_array seeding, _randbelow rejection) for the masking, numpy's
+ * legacy RandomState (np.random.seed / np.random.choice) for the samplers.  Ragged inputs are CSR: values + offsets [n+1]. */
+/* apply_dynamic_masking_task (dataloader_utils.py:186-261) + the padded layout of BERT4RecPreprocessor.process_element
+ * (bert4rec_preprocessor.py:94-114) for n already tokenised / windowed sequences (each <= max_seq_len tokens).
+ * seeds[i] = the `seed` argument of sequence i.  Outputs int64: labels, input_word_ids, input_mask [n][max_seq_len];
+ * masked_lm_ids, masked_lm_positions, masked_lm_weights [n][max_pred]; padding value pad_id everywhere. */
+int b4r_host_cloze_mask_batch(const int64_t* tokens, const int64_t* offsets, const uint64_t* seeds, int n, int max_seq_len,
+                              int max_pred, int64_t mask_id, int64_t pad_id, const int64_t* special_ids, int n_special,
+                              int64_t vocab_size, double selection_rate, double mask_token_rate, double random_token_rate,
+                              int64_t* labels, int64_t* input_word_ids, int64_t* input_mask, int64_t* masked_lm_ids,
+                              int64_t* masked_lm_positions, int64_t* masked_lm_weights, int n_threads);
+/* RandomSampler.sample(seed=seeds[i], without=without_i) (random_sampler.py:63-79): out int64 [n][sample_size] */
+int b4r_host_sample_random_batch(const int64_t* vocab, int64_t n_vocab, const int64_t* without, const int64_t* without_off,
+                                 const uint32_t* seeds, int n, int sample_size, int allow_duplicates, int64_t* out, int n_threads);
+/* PopularSampler.sample(without=without_i) over an already popularity-ranked source (popular_sampler.py:53-71):
+ * out int64 [n][sample_size] (zero-filled tail), out_len int32 [n] */
+int b4r_host_sample_popular_batch(const int64_t* ranked, int64_t n_ranked, const int64_t* without, const int64_t* without_off, int n,
+                                  int sample_size, int64_t* out, int32_t* out_len, int n_threads);
+/* PopularRandomSampler.sample(seed=seeds[i], without=without_i) (popular_random_sampler.py:77-117); p = the sampler's
+ * probability_distribution, float64 [n_vocab]: out int64 [n][sample_size] (zero-filled tail), out_len int32 [n] */
+int b4r_host_sample_pop_random_batch(const int64_t* vocab, const double* p, int64_t n_vocab, const int64_t* without,
+                                     const int64_t* without_off, const uint32_t* seeds, int n, int sample_size, int allow_duplicates,
+                                     int64_t* out, int32_t* out_len, int n_threads);
+
 /* ---- introspection (device pointers into the workspace; valid for the session lifetime) ------------------ */
 const void* b4r_sequence_output(b4r_session* s, int layer);  /* bf16 [batch*seq_len, hidden]; layer -1 = last */
 const void* b4r_mlm_hidden(b4r_session* s);                  /* bf16 [n_rows, hidden] transformed rows */
