@@ -336,7 +336,7 @@ def host_path_block(w, model, eval_batch):
     """Host data path of the loop: Cloze masking and negative sampling on the C++ threads of libb4r.so, timed
     on this box's cores next to the per-sequence Python (the product's restatement of the reference functions; the
     reference's own list-scan versions are slower still), and the 100-negative evaluation INCLUDING the host sampling."""
-    import time
+    import torch
     from bert4rec_b200.dataloaders import host_native as hn, dataloader_utils as du, samplers
     from bert4rec_b200.evaluation import BERT4RecEvaluator
     V, S, P, B = w["vocab_size"], w["seq_len"], w["max_pred"], w["batch"]
