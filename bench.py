@@ -405,6 +405,8 @@ def kernel_work(tag, w, n_rows):
         # recompute passes: only the useful GEMM (dT = dl E, dE = dl^T t) is counted, not the recomputed logits
         "ce_bwd_umma:dT": (2 * M * H * V, M * H * e + V * H * e + V * 4 + M * H * 4, "tensor"),
         "ce_bwd_umma:dE": (2 * M * H * V, M * H * e + V * H * e + V * H * 4 + V * 4, "tensor"),
+        # one-pass generation: both useful GEMMs from one recompute
+        "ce_bwd_fused": (4 * M * H * V, M * H * e + V * H * e + V * 4 + M * H * 4 + V * H * 4, "tensor"),
         "sqnorm+adamw": (0, 32 * (V * H + 64 * H + L * (4 * H * H + 2 * H * I) + H * H + V), "hbm"),
         "embed_ln_fwd": (0, T * (8 + 2 * H * e), "hbm"),
         "embed_bwd": (0, T * (8 + H * e + H * 4) + T * H * 4, "hbm"),

@@ -219,6 +219,7 @@ struct b4r_session {
   bf16* dlogits; int dl_rows;
   float* dt_part; int dt_splits, dt_max_splits;
   float *p_dE, *p_dbias2; int me_splits;
+  bool ce_fused_ok = false, ce_fused_default = false, use_ce_fused = false; int cf_vranges = 0; float *cf_dt = nullptr, *cf_dE = nullptr, *cf_db = nullptr;   // generation-3 CE backward
   ReduceJob* d_ce_jobs;
   bf16* d_tpre;
   float *p_head_ln, *p_wt, *p_vbias; int s_wt, vb_splits;
@@ -369,6 +370,21 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
   s->p_dE = b.take<float>(bwd_umma ? (size_t)s->me_splits * V * H : 8);
   s->p_dbias2 = b.take<float>(bwd_umma ? (size_t)s->me_splits * V : 8);
   s->d_ce_jobs = b.take<ReduceJob>(2);
+  {
+    // generation-3 CE backward (one pass): partial buffers, used when they stay within 1 GB
+    const int nvr = ce_bwd_fused_vranges(V), nch = ce_bwd_fused_max_chunks(Mcap);
+    const size_t bytes = ((size_t)nvr * Mcap * H + (size_t)nch * V * (H + 1)) * sizeof(float);
+    // every vocabulary range is a dT partial slot that the MLM-transform backward has to sum: beyond ~64 ranges (V > 16k) that sum
+    // costs more than the second recompute pass saves (measured at V = 26.7k), so large catalogues keep the two-pass generation
+    s->ce_fused_ok = bwd_umma && ce_bwd_fused_supported(H) && head_bwd_fused_supported(H) && bytes <= ((size_t)1 << 30);
+    s->ce_fused_default = nvr <= 64;   // (session flag 5 still forces it: parity tests cover the many-range case)
+    s->cf_vranges = nvr;
+    if (s->ce_fused_ok) {
+      s->cf_dt = b.take<float>((size_t)nvr * Mcap * H);
+      s->cf_dE = b.take<float>((size_t)nch * V * H);
+      s->cf_db = b.take<float>((size_t)nch * V);
+    }
+  }
   s->d_tpre = b.take<bf16>((size_t)Mcap * H);
   const bool head_fused = head_bwd_fused_supported(H);
   const int head_parts = head_fused ? head_bwd_fused_ctas() : ln_bwd_parts(Mcap);
@@ -477,6 +493,7 @@ extern "C" int b4r_session_create(const b4r_config* cfg, int batch, int seq_len,
   CK(cudaMemset(s->ticket, 0, 4 * sizeof(int)));
   s->use_umma = ce_umma_make_maps(&s->umaps, s->t, s->Mcap, s->shadow + s->lay.find("word_embeddings"), s->V, s->H) &&
                 getenv("B4R_DISABLE_UMMA") == nullptr;
+  s->use_ce_fused = s->use_umma && s->ce_fused_ok && s->ce_fused_default && s->grads != nullptr;
   CK(cudaMemset(s->counts, 0, 8 * sizeof(int)));
   CK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
@@ -683,7 +700,27 @@ static int backward_impl(b4r_session* s, uint64_t seed, uint32_t step, const int
   CeArgs c = ce_args(s);
   bool head_done = false;
   if (join_select(s, st)) return 1;
-  if (bwd_umma) {
+  if (bwd_umma && s->use_ce_fused) {
+    // ---- CE backward, generation 3: ONE tcgen05 pass for dT and dE (hidden 64)
+    CeBwdFusedArgs fa{};
+    fa.vbias = c.vbias; fa.lse = s->lse; fa.row_w = s->row_w; fa.labels = s->labels; fa.d_counts = s->counts;
+    fa.M_cap = Mcap; fa.V = V; fa.ctas = 148; fa.dt_part = s->cf_dt; fa.dE_part = s->cf_dE; fa.db_part = s->cf_db;
+    KL("ce_bwd_fused", launch_ce_bwd_fused(s->umaps, fa, st));
+    // the MLM-transform backward needs dT only: it runs as a branch beside the reduction of the dE partials
+    CK(cudaEventRecord(s->ev_fork, st));
+    CK(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
+    {
+      cudaStream_t st_main = st; (void)st_main;
+      cudaStream_t st = s->side;
+      KL("head_bwd_fused", launch_head_bwd_fused(s->cf_dt, s->cf_vranges, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
+                               P + s->lay.find("head/ln/gamma"), W + s->lay.find("head/wt"), s->layers.back().out, s->rows, s->counts,
+                               Mcap, s->dxa, s->p_head_ln, s->p_wt, st, 0, 0, 0));
+    }
+    CK(cudaEventRecord(s->ev_join, s->side));
+    head_done = true;
+    KL("grad_reduce:ce", launch_ce_bwd_fused_reduce(fa, G + oE, G + s->lay.find("head/output_bias"), st));
+    CK(cudaStreamWaitEvent(st, s->ev_join, 0));
+  } else if (bwd_umma) {
     // ---- CE backward, generation 2: two tcgen05 passes that recompute the logits tile, nothing [M,V]-sized in memory
     CeBwdArgs ba{};
     ba.vbias = c.vbias; ba.lse = s->lse; ba.row_w = s->row_w; ba.labels = s->labels; ba.d_counts = s->counts;
@@ -1159,6 +1196,11 @@ extern "C" int b4r_session_set_flag(b4r_session* s, int flag, int value) {
   if (!s) return fail("null session");
   if (flag == 1) { s->use_umma = value != 0; return 0; }
   if (flag == 4) { s->overlap_select = value != 0; return 0; }
+  if (flag == 5) {
+    if (value && !s->ce_fused_ok) return fail("one-pass CE backward unavailable for this shape");
+    s->use_ce_fused = value != 0;
+    return 0;
+  }
   if (flag == 3) {
     if (value && !s->fused_bwd_ok) return fail("fused encoder backward unavailable for this shape");
     s->use_fused_bwd = value != 0;

@@ -1,0 +1,351 @@
+// Generation 3 of the tied-projection / softmax-CE BACKWARD (hidden 64): ONE tcgen05 pass produces both dT and dE.
+//
+// The two-pass generation (k_ce_bwd_umma.cu) recomputes every [128 x 128] logits tile twice (once per operand role) and is
+// bound by the per-tile epilogue (exp, one-hot, bf16 pack: ~2 us per tile per SM), not by the tensor pipe.  Here a work item
+// is (vocabulary range of VR = 2 tiles) x (row chunk of <= MR_MAX = 5 tiles), all of whose operand tiles are resident in
+// shared memory (TMA, 7 x 16 KB).  For every pair (row tile i, vocabulary tile j):
+//
+//   MMA1 :  S[128 m x 128 v]  = T_i . E_j^T                       (double-buffered in TMEM, overlaps the previous epilogue)
+//   epilogue (16 warps, one TMEM lane = one row m, 32 columns per thread):
+//           dl = (exp2(S*log2e + bias_v*log2e - lse_m*log2e) - [v == label_m]) * [w_m > 0]  -> bf16 tile in shared memory
+//   MMA2a:  dT_i[128 m x 64] += dl     . E_j     (A = dl K-major,  B = E_j read MN-major)
+//   MMA2b:  dE_j[128 v x 80] += dl^T   . [T_i|1] (A = the SAME dl tile read MN-major, B = T_i read MN-major with a second
+//           64-column block pointed at a tile of ONES: accumulator column 64 = sum_m dl[m, v] = the output-bias gradient)
+//
+// dT_i is drained after the last j of a row tile (partial slot = vocabulary range), the dE_j after the item (partial slot =
+// row chunk); head_bwd_fused sums the dT partials, ce_bwd_fused_reduce_kernel the dE / bias partials.  Deterministic.
+// Gradient of the SUM loss, like the other generations (bert4rec_model.py:166-167).
+#include <cstdlib>
+#include "common.cuh"
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace b4r {
+namespace {
+
+constexpr int FT = 128, FH = 64, MR_MAX = 5, VR = 2;
+constexpr int TILE = FT * 128;      // [128 rows][64 bf16], 128-byte swizzled rows
+constexpr int DL_BYTES = 2 * TILE;  // [128 m][128 v] as two [128][64] sub-tiles
+constexpr int OFF_T = 0, OFF_E = MR_MAX * TILE, OFF_DL = OFF_E + VR * TILE, OFF_ONES = OFF_DL + 2 * DL_BYTES, ONES_BYTES = 2048;
+constexpr int OFF_VEC = OFF_ONES + ONES_BYTES;   // bias [VR*128] | lse [MR_MAX*128] | w [MR_MAX*128] | label [MR_MAX*128]
+constexpr int VEC_WORDS = VR * FT + 3 * MR_MAX * FT;
+constexpr int OFF_BAR = OFF_VEC + VEC_WORDS * 4;
+constexpr int SMEM = OFF_BAR + 256 + 1024;
+constexpr int NTHR = 64 + 512;
+constexpr uint32_t C_S = 0, C_DT = 256, C_DE = 320, DE_COLS = 80;   // TMEM columns: S0, S1 | dT | dE_0, dE_1 (64 + 16 ones columns)
+
+struct Split { int mt, vt, nvr, nch, MR; };
+__host__ __device__ inline Split cf_split(int n_valid, int V) {
+  Split s;
+  s.mt = (n_valid + FT - 1) / FT; s.vt = (V + FT - 1) / FT;
+  s.nvr = (s.vt + VR - 1) / VR;
+  s.nch = (s.mt + MR_MAX - 1) / MR_MAX;
+  s.MR = s.nch ? (s.mt + s.nch - 1) / s.nch : 0;   // balanced chunks, every chunk non-empty
+  return s;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// MN-major operand: [k rows of 128 B (64 mn elements)], 16 k-rows per MMA, LBO = distance to the next 64-element mn block
+__device__ __forceinline__ uint64_t desc_mn(uint32_t byte_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((byte_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+struct Dev {
+  const float* vbias; const float* lse; const float* row_w; const int* labels; const int* d_counts;
+  int M_cap, V;
+  float* dt_part;   // [nvr][M_cap][64]
+  float* dE_part;   // [nch][V][64]
+  float* db_part;   // [nch][V]
+};
+
+__global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmE,
+                                                               Dev a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* sBias = reinterpret_cast<float*>(smem + OFF_VEC);
+  float* sLse = sBias + VR * FT;
+  float* sW = sLse + MR_MAX * FT;
+  int* sLab = reinterpret_cast<int*>(sW + MR_MAX * FT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* tiles_full = bars;         // TMA landed the item's tiles
+  uint64_t* tiles_free = bars + 1;     // every MMA of the item has read them
+  uint64_t* s_full = bars + 2;         // [2] MMA1 done
+  uint64_t* s_empty = bars + 4;        // [2] epilogue read S
+  uint64_t* dl_full = bars + 6;        // [2] epilogue wrote dl
+  uint64_t* dl_empty = bars + 8;       // [2] MMA2a/b consumed dl
+  uint64_t* acc_done = bars + 10;      // all MMAs of the item complete
+  uint64_t* drained = bars + 11;       // epilogue drained the item's dE accumulators
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int n_valid = min(a.M_cap, a.d_counts[0]);
+  const Split sp = cf_split(n_valid, a.V);
+  const int items = sp.nvr * sp.nch;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    umma::mbar_init(tiles_full, 1); umma::mbar_init(tiles_free, 1);
+    for (int b = 0; b < 2; ++b) {
+      umma::mbar_init(s_full + b, 1); umma::mbar_init(s_empty + b, 16);
+      umma::mbar_init(dl_full + b, 16); umma::mbar_init(dl_empty + b, 1);
+    }
+    umma::mbar_init(acc_done, 1); umma::mbar_init(drained, 16);
+    umma::fence_barrier_init();
+    umma::prefetch_tensormap(&tmT);
+    umma::prefetch_tensormap(&tmE);
+  }
+  for (int i = threadIdx.x; i < ONES_BYTES / 4; i += NTHR) reinterpret_cast<uint32_t*>(smem + OFF_ONES)[i] = 0x3F803F80u;   // bf16 1.0
+  umma::fence_proxy_async();
+  if (warp == 1) umma::tmem_alloc<512>(tmem_holder);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        const int jr = item % sp.nvr, c = item / sp.nvr;
+        const int i0 = c * sp.MR, mrc = min(sp.MR, sp.mt - i0), j0 = jr * VR, vrc = min(VR, sp.vt - j0);
+        if (it > 0) umma::mbar_wait(tiles_free, (it - 1) & 1);
+        umma::mbar_expect_tx(tiles_full, (uint32_t)(mrc + vrc) * TILE);
+        for (int j = 0; j < vrc; ++j) umma::tma_load_2d(smem + OFF_E + j * TILE, &tmE, 0, (j0 + j) * FT, tiles_full);
+        for (int i = 0; i < mrc; ++i) umma::tma_load_2d(smem + OFF_T + i * TILE, &tmT, 0, (i0 + i) * FT, tiles_full);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t id1 = idesc(FT, FT, 0, 0);          // S   = T_i (K-major) . E_j (K-major)
+      constexpr uint32_t id2a = idesc(FT, FH, 0, 1);         // dT += dl (K-major) . E_j (MN-major)
+      constexpr uint32_t id2b = idesc(FT, DE_COLS, 1, 1);    // dE += dl^T (MN-major) . [T_i | ones] (MN-major)
+      const uint32_t t_base = umma::smem_addr(smem + OFF_T), e_base = umma::smem_addr(smem + OFF_E);
+      const uint32_t dl_base = umma::smem_addr(smem + OFF_DL), ones = umma::smem_addr(smem + OFF_ONES);
+      uint32_t g = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        const int jr = item % sp.nvr, c = item / sp.nvr;
+        const int i0 = c * sp.MR, mrc = min(sp.MR, sp.mt - i0), j0 = jr * VR, vrc = min(VR, sp.vt - j0);
+        const int np = mrc * vrc;
+        umma::mbar_wait(tiles_full, it & 1);
+        if (it > 0) umma::mbar_wait(drained, (it - 1) & 1);
+        umma::fence_after_sync();
+        auto mma1 = [&](int p, uint32_t gp) {
+          const int i = p / vrc, j = p - i * vrc;
+          const uint32_t buf = gp & 1;
+          umma::mbar_wait(s_empty + buf, ((gp >> 1) & 1) ^ 1);
+          umma::fence_after_sync();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma::mma_bf16_ss(tmem + C_S + buf * FT, umma::make_desc_k_sw128(t_base + i * TILE + k * 32),
+                              umma::make_desc_k_sw128(e_base + j * TILE + k * 32), id1, k ? 1u : 0u);
+          umma::mma_commit(s_full + buf);
+        };
+        mma1(0, g);
+        for (int p = 0; p < np; ++p) {
+          const uint32_t gp = g + p, buf = gp & 1;
+          const int i = p / vrc, j = p - i * vrc;
+          if (p + 1 < np) mma1(p + 1, gp + 1);
+          umma::mbar_wait(dl_full + buf, (gp >> 1) & 1);   // (the epilogue drains dT of row tile i-1 before it arrives here for j = 0)
+          umma::fence_after_sync();
+          const uint32_t dl = dl_base + buf * DL_BYTES, tt = t_base + i * TILE, ee = e_base + j * TILE;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma::mma_bf16_ss(tmem + C_DT, umma::make_desc_k_sw128(dl + (kk >> 2) * TILE + (kk & 3) * 32), desc_mn(ee + kk * 2048, TILE),
+                              id2a, (j | kk) ? 1u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma::mma_bf16_ss(tmem + C_DE + j * DE_COLS, desc_mn(dl + kk * 2048, TILE), desc_mn(tt + kk * 2048, ones - (tt + kk * 2048)),
+                              id2b, (i | kk) ? 1u : 0u);
+          umma::mma_commit(dl_empty + buf);
+        }
+        g += np;
+        umma::mma_commit(tiles_free);
+        umma::mma_commit(acc_done);
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..17)
+    const int quad = warp & 3, cq = (warp - 2) >> 2;   // TMEM lane quadrant, column quarter
+    const int row_in_tile = quad * 32 + lane;
+    const int e = threadIdx.x - 64;                     // 0..511
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    constexpr float LOG2E = 1.4426950408889634f;
+    uint32_t g = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const int jr = item % sp.nvr, c = item / sp.nvr;
+      const int i0 = c * sp.MR, mrc = min(sp.MR, sp.mt - i0), j0 = jr * VR, vrc = min(VR, sp.vt - j0);
+      const int np = mrc * vrc;
+      auto drain_dt = [&](int i) {
+        uint32_t r[16];
+        umma::tmem_ld16(tmem + C_DT + lane_off + cq * 16, r);
+        umma::tmem_ld_wait();
+        const int m = (i0 + i) * FT + row_in_tile;
+        if (m < n_valid) {
+          float* dst = a.dt_part + ((size_t)jr * a.M_cap + m) * FH + cq * 16;
+#pragma unroll
+          for (int q = 0; q < 16; q += 4)
+            *reinterpret_cast<float4*>(dst + q) =
+                make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
+        }
+      };
+      asm volatile("bar.sync 1, 512;\n" ::: "memory");   // the previous item's vectors are no longer read
+      for (int x = e; x < vrc * FT; x += 512) {
+        const int v = j0 * FT + x;
+        sBias[x] = v < a.V ? a.vbias[v] * LOG2E : -INFINITY;
+      }
+      for (int x = e; x < mrc * FT; x += 512) {
+        const int m = i0 * FT + x;
+        const bool ok = m < n_valid;
+        sLse[x] = ok ? a.lse[m] * LOG2E : 0.f;
+        sW[x] = ok ? a.row_w[m] : 0.f;
+        sLab[x] = ok ? a.labels[m] : -1;
+      }
+      asm volatile("bar.sync 1, 512;\n" ::: "memory");
+      for (int p = 0; p < np; ++p) {
+        const uint32_t gp = g + p, buf = gp & 1;
+        const int i = p / vrc, j = p - i * vrc;
+        const int lrow = i * FT + row_in_tile;
+        const float row_a = sLse[lrow];
+        const bool row_on = sW[lrow] > 0.f;
+        const int rel_label = sLab[lrow] - ((j0 + j) * FT + cq * 32);   // label column relative to this thread's 32 columns
+        const float* vec = sBias + j * FT + cq * 32;
+        umma::mbar_wait(s_full + buf, (gp >> 1) & 1);
+        umma::fence_after_sync();
+        uint32_t r[32];
+        umma::tmem_ld32(tmem + C_S + buf * FT + lane_off + cq * 32, r);
+        umma::tmem_ld_wait();
+        umma::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(s_empty + buf);   // S buffer free: MMA1 of pair gp+2 may overwrite it
+        uint32_t pk[16];
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) {
+          const float2 b2 = *reinterpret_cast<const float2*>(vec + q);
+          float p0 = ex2_approx(fmaf(__uint_as_float(r[q]), LOG2E, b2.x) - row_a);
+          float p1 = ex2_approx(fmaf(__uint_as_float(r[q + 1]), LOG2E, b2.y) - row_a);
+          if (q == rel_label) p0 -= 1.f;
+          if (q + 1 == rel_label) p1 -= 1.f;
+          pk[q >> 1] = row_on ? pack_bf162(p0, p1) : 0u;
+        }
+        umma::mbar_wait(dl_empty + buf, ((gp >> 1) & 1) ^ 1);   // MMA2 of pair gp-2 has consumed this dl buffer
+        unsigned char* rowp = smem + OFF_DL + buf * DL_BYTES + (cq >> 1) * TILE + row_in_tile * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((cq & 1) * 4 + q) ^ (row_in_tile & 7);
+          *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+        if (j == 0 && i > 0) {
+          // dT of the previous row tile is final once the MMAs of pair gp-1 have completed; drain it before MMA2a of this pair
+          // (accumulate = 0) may overwrite it -- that MMA waits for this warp's dl_full arrival below
+          umma::mbar_wait(dl_empty + ((gp - 1) & 1), ((gp - 1) >> 1) & 1);
+          umma::fence_after_sync();
+          drain_dt(i - 1);
+        }
+        umma::fence_before_sync();
+        umma::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(dl_full + buf);
+      }
+      g += np;
+      // ---- item tail: last dT tile, the dE accumulators and the bias column
+      umma::mbar_wait(acc_done, it & 1);
+      umma::fence_after_sync();
+      drain_dt(mrc - 1);
+      for (int j = 0; j < vrc; ++j) {
+        const int v = (j0 + j) * FT + row_in_tile;
+        uint32_t r[16];
+        umma::tmem_ld16(tmem + C_DE + j * DE_COLS + lane_off + cq * 16, r);
+        umma::tmem_ld_wait();
+        if (v < a.V) {
+          float* dst = a.dE_part + ((size_t)c * a.V + v) * FH + cq * 16;
+#pragma unroll
+          for (int q = 0; q < 16; q += 4)
+            *reinterpret_cast<float4*>(dst + q) =
+                make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
+        }
+        if (cq == 0) {
+          umma::tmem_ld16(tmem + C_DE + j * DE_COLS + lane_off + FH, r);
+          umma::tmem_ld_wait();
+          if (v < a.V) a.db_part[(size_t)c * a.V + v] = __uint_as_float(r[0]);
+        }
+      }
+      umma::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(drained);
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    umma::fence_after_sync();
+    umma::tmem_dealloc<512>(tmem);
+  }
+}
+
+// table / output-bias gradient = sum of the row-chunk partials (chunk count from the device-side row count)
+__global__ void __launch_bounds__(256) ce_bwd_fused_reduce_kernel(const float* __restrict__ dE_part, const float* __restrict__ db_part,
+                                                                  const int* __restrict__ d_counts, int M_cap, int V,
+                                                                  float* __restrict__ g_table, float* __restrict__ g_bias) {
+  const int nch = cf_split(min(M_cap, d_counts[0]), V).nch;
+  const long long n4 = (long long)V * FH / 4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < nch; ++k) {
+      const float4 v = reinterpret_cast<const float4*>(dE_part + (size_t)k * V * FH)[idx];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(g_table)[idx] = acc;
+  }
+  if (idx < V) {
+    float s = 0.f;
+    for (int k = 0; k < nch; ++k) s += db_part[(size_t)k * V + idx];
+    g_bias[idx] = s;
+  }
+}
+
+}  // namespace
+
+bool ce_bwd_fused_supported(int H) { return H == FH && getenv("B4R_DISABLE_CE_FUSED") == nullptr; }
+int ce_bwd_fused_vranges(int V) { return cf_split(0, V).nvr; }
+int ce_bwd_fused_max_chunks(int M_cap) { return cf_split(M_cap, 1).nch; }
+
+cudaError_t launch_ce_bwd_fused(const CeUmmaMaps& maps, const CeBwdFusedArgs& a, cudaStream_t st) {
+  static bool done = false;
+  if (!done) {
+    cudaFuncSetAttribute(ce_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    done = true;
+  }
+  Dev d;
+  d.vbias = a.vbias; d.lse = a.lse; d.row_w = a.row_w; d.labels = a.labels; d.d_counts = a.d_counts; d.M_cap = a.M_cap; d.V = a.V;
+  d.dt_part = a.dt_part; d.dE_part = a.dE_part; d.db_part = a.db_part;
+  const CUtensorMap& tmT = *reinterpret_cast<const CUtensorMap*>(maps.a);
+  const CUtensorMap& tmE = *reinterpret_cast<const CUtensorMap*>(maps.b);
+  ce_bwd_fused_kernel<<<a.ctas > 0 ? a.ctas : 148, NTHR, SMEM, st>>>(tmT, tmE, d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ce_bwd_fused_reduce(const CeBwdFusedArgs& a, float* g_table, float* g_bias, cudaStream_t st) {
+  const long long n4 = (long long)a.V * FH / 4;
+  ce_bwd_fused_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(a.dE_part, a.db_part, a.d_counts, a.M_cap, a.V, g_table, g_bias);
+  return cudaGetLastError();
+}
+
+}  // namespace b4r

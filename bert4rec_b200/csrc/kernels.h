@@ -249,6 +249,18 @@ struct CeBwdArgs {
 bool ce_bwd_umma_supported(int H);
 int ce_bwd_umma_xtile(int H);   // rows of a streamed tile (128, or 64 for hidden 256): the unit of the vocabulary split count
 cudaError_t launch_ce_bwd_umma(const CeUmmaMaps& maps, const CeBwdArgs& a, bool row_is_m, cudaStream_t st);
+// generation 3 (k_ce_bwd_fused.cu, hidden 64): dT and dE from ONE recompute pass; partial slots: dT per vocabulary range
+// (ce_bwd_fused_vranges(V), static), dE / bias per row chunk (<= ce_bwd_fused_max_chunks(M_cap), count chosen on the device)
+struct CeBwdFusedArgs {
+  const float* vbias; const float* lse; const float* row_w; const int* labels; const int* d_counts;
+  int M_cap, V, ctas;
+  float* dt_part; float* dE_part; float* db_part;
+};
+bool ce_bwd_fused_supported(int H);
+int ce_bwd_fused_vranges(int V);
+int ce_bwd_fused_max_chunks(int M_cap);
+cudaError_t launch_ce_bwd_fused(const CeUmmaMaps& maps, const CeBwdFusedArgs& a, cudaStream_t st);
+cudaError_t launch_ce_bwd_fused_reduce(const CeBwdFusedArgs& a, float* g_table, float* g_bias, cudaStream_t st);
 // split count the generation-2 CE passes choose on the device (row tiles of 128): (row tiles x splits) fits one wave of target_ctas
 __host__ __device__ inline int ce_dyn_splits128(int n_rows, int ntiles, int target_ctas, int max_splits) {
   int mt = (n_rows + 127) / 128;

@@ -190,3 +190,44 @@ def test_fused_edge_cases_match_layered(kind, B, S, P):
     gmax = max(float(v.norm()) for v in g0.values())
     for k in g0:
         assert float((g0[k] - g1[k]).norm()) <= 2e-2 * float(g0[k].norm()) + 1e-5 * gmax + 1e-7, k
+
+
+@pytest.mark.parametrize("case", ["one_tile", "two_row_tiles", "many_items_two_chunks"])
+def test_one_pass_ce_backward_matches_two_pass(case):
+    """Generation 3 of the CE backward (k_ce_bwd_fused.cu: dT and dE from one recompute pass, session flag 5) against the
+    two-pass tcgen05 generation on the same forward state: same dl tiles, different summation order only."""
+    from bert4rec_b200.engine import ParamStore
+    from tests.helpers import make_batch, to_cuda
+    shape = {"one_tile": (1203, 24, 50, 8, 0.2), "two_row_tiles": (3709, 6, 200, 40, 0.2),
+             "many_items_two_chunks": (40013, 64, 50, 20, 0.6)}[case]
+    V, B, S, P, pm = shape
+    store = ParamStore(device="cuda:0", vocab_size=V, hidden_size=64, num_layers=1, num_attention_heads=2, max_sequence_length=S,
+                       inner_dim=64, output_dropout=0.0, attention_dropout=0.0)
+    store.init_weights(0)
+    with torch.no_grad():
+        store.seg("head/output_bias").normal_(0, 0.5, generator=None)
+    store.sync_shadow()
+    store.ensure_training_buffers()
+    cb = to_cuda(make_batch(B, S, P, V, p_mask=pm, seed=21))
+    sess = store.session(B, S, P)
+    grads = {}
+    for gen3 in (0, 1):
+        sess.set_flag(5, gen3)
+        store.grads.zero_()
+        sess.select(cb["masked_lm_positions"], cb["masked_lm_ids"], cb["masked_lm_weights"], mode=0, want_aux=True)
+        sess.encode(cb["input_word_ids"], cb["input_mask"], training=True)
+        sess.transform()
+        sess.loss()
+        sess.backward()
+        torch.cuda.synchronize()
+        grads[gen3] = {k: v.clone() for k, v in store.tf_views(store.grads).items()}
+    n_valid = int(sess.counts()[0])
+    if case == "many_items_two_chunks":
+        assert n_valid > 5 * 128 and (V + 127) // 128 // 2 > 148
+    bad = []
+    gmax = max(float(g.norm()) for g in grads[0].values())
+    for k, g in grads[0].items():
+        err = float((grads[1][k].double() - g.double()).norm())
+        if not err <= 2e-3 * float(g.norm()) + 1e-6 * gmax:
+            bad.append((k, err, float(g.norm())))
+    assert not bad, f"one-pass vs two-pass CE backward (name, l2 err, ref norm): {bad}"
