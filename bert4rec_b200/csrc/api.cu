@@ -185,6 +185,8 @@ struct Bump {
 };
 }  // namespace
 
+static const int kCeFusedCtas = 148;   // one persistent CTA per SM (k_ce_bwd_fused.cu)
+
 struct b4r_session {
   b4r_config cfg;
   int B, S, P, T, Mcap, H, I, V, N, Vp;
@@ -372,13 +374,11 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
   s->d_ce_jobs = b.take<ReduceJob>(2);
   {
     // generation-3 CE backward (one pass): partial buffers, used when they stay within 1 GB
-    const int nvr = ce_bwd_fused_vranges(V), nch = ce_bwd_fused_max_chunks(Mcap);
+    const int nvr = ce_bwd_fused_dt_slot_cap(V, kCeFusedCtas), nch = ce_bwd_fused_max_chunks(Mcap);
     const size_t bytes = ((size_t)nvr * Mcap * H + (size_t)nch * V * (H + 1)) * sizeof(float);
-    // every vocabulary range is a dT partial slot that the MLM-transform backward has to sum: beyond ~64 ranges (V > 16k) that sum
-    // costs more than the second recompute pass saves (measured at V = 26.7k), so large catalogues keep the two-pass generation
     s->ce_fused_ok = bwd_umma && ce_bwd_fused_supported(H) && head_bwd_fused_supported(H) && bytes <= ((size_t)1 << 30);
-    s->ce_fused_default = nvr <= 64;   // (session flag 5 still forces it: parity tests cover the many-range case)
-    s->cf_vranges = nvr;
+    s->ce_fused_default = true;
+    s->cf_vranges = nvr;   // capacity of the dT partial buffer (slots)
     if (s->ce_fused_ok) {
       s->cf_dt = b.take<float>((size_t)nvr * Mcap * H);
       s->cf_dE = b.take<float>((size_t)nch * V * H);
@@ -704,7 +704,7 @@ static int backward_impl(b4r_session* s, uint64_t seed, uint32_t step, const int
     // ---- CE backward, generation 3: ONE tcgen05 pass for dT and dE (hidden 64)
     CeBwdFusedArgs fa{};
     fa.vbias = c.vbias; fa.lse = s->lse; fa.row_w = s->row_w; fa.labels = s->labels; fa.d_counts = s->counts;
-    fa.M_cap = Mcap; fa.V = V; fa.ctas = 148; fa.dt_part = s->cf_dt; fa.dE_part = s->cf_dE; fa.db_part = s->cf_db;
+    fa.M_cap = Mcap; fa.V = V; fa.ctas = kCeFusedCtas; fa.dt_part = s->cf_dt; fa.dE_part = s->cf_dE; fa.db_part = s->cf_db;
     KL("ce_bwd_fused", launch_ce_bwd_fused(s->umaps, fa, st));
     // the MLM-transform backward needs dT only: it runs as a branch beside the reduction of the dE partials
     CK(cudaEventRecord(s->ev_fork, st));
@@ -714,7 +714,7 @@ static int backward_impl(b4r_session* s, uint64_t seed, uint32_t step, const int
       cudaStream_t st = s->side;
       KL("head_bwd_fused", launch_head_bwd_fused(s->cf_dt, s->cf_vranges, (size_t)Mcap * H, s->t_pre, s->t_act, s->hmean, s->hrstd,
                                P + s->lay.find("head/ln/gamma"), W + s->lay.find("head/wt"), s->layers.back().out, s->rows, s->counts,
-                               Mcap, s->dxa, s->p_head_ln, s->p_wt, st, 0, 0, 0));
+                               Mcap, s->dxa, s->p_head_ln, s->p_wt, st, V, kCeFusedCtas, -1));
     }
     CK(cudaEventRecord(s->ev_join, s->side));
     head_done = true;

@@ -6,7 +6,7 @@
 // shared memory (TMA, 7 x 16 KB).  For every pair (row tile i, vocabulary tile j):
 //
 //   MMA1 :  S[128 m x 128 v]  = T_i . E_j^T                       (double-buffered in TMEM, overlaps the previous epilogue)
-//   epilogue (16 warps, one TMEM lane = one row m, 32 columns per thread):
+//   epilogue (two groups of 8 warps on alternate pairs; one TMEM lane = one row m, 64 columns per thread):
 //           dl = (exp2(S*log2e + bias_v*log2e - lse_m*log2e) - [v == label_m]) * [w_m > 0]  -> bf16 tile in shared memory
 //   MMA2a:  dT_i[128 m x 64] += dl     . E_j     (A = dl K-major,  B = E_j read MN-major)
 //   MMA2b:  dE_j[128 v x 80] += dl^T   . [T_i|1] (A = the SAME dl tile read MN-major, B = T_i read MN-major with a second
@@ -23,31 +23,51 @@
 namespace b4r {
 namespace {
 
-constexpr int FT = 128, FH = 64, MR_MAX = 5, VR = 2;
+constexpr int FT = 128, FH = 64, MR_MAX = CF_MR_MAX, VR = CF_VR;
 constexpr int TILE = FT * 128;      // [128 rows][64 bf16], 128-byte swizzled rows
 constexpr int DL_BYTES = 2 * TILE;  // [128 m][128 v] as two [128][64] sub-tiles
-constexpr int OFF_T = 0, OFF_E = MR_MAX * TILE, OFF_DL = OFF_E + VR * TILE, OFF_ONES = OFF_DL + 2 * DL_BYTES, ONES_BYTES = 2048;
+constexpr int E_STAGE = VR * TILE;  // the vocabulary tiles of one item; two stages (the next item is prefetched)
+constexpr int OFF_T = 0, OFF_E = MR_MAX * TILE, OFF_DL = OFF_E + 2 * E_STAGE, OFF_ONES = OFF_DL + 2 * DL_BYTES, ONES_BYTES = 2048;
 constexpr int OFF_VEC = OFF_ONES + ONES_BYTES;   // bias [VR*128] | lse [MR_MAX*128] | w [MR_MAX*128] | label [MR_MAX*128]
 constexpr int VEC_WORDS = VR * FT + 3 * MR_MAX * FT;
 constexpr int OFF_BAR = OFF_VEC + VEC_WORDS * 4;
 constexpr int SMEM = OFF_BAR + 256 + 1024;
+static_assert(SMEM <= 232448, "shared memory");
 constexpr int NTHR = 64 + 512;
 constexpr uint32_t C_S = 0, C_DT = 256, C_DE = 320, DE_COLS = 80;   // TMEM columns: S0, S1 | dT | dE_0, dE_1 (64 + 16 ones columns)
 
-struct Split { int mt, vt, nvr, nch, MR; };
-__host__ __device__ inline Split cf_split(int n_valid, int V) {
-  Split s;
-  s.mt = (n_valid + FT - 1) / FT; s.vt = (V + FT - 1) / FT;
-  s.nvr = (s.vt + VR - 1) / VR;
-  s.nch = (s.mt + MR_MAX - 1) / MR_MAX;
-  s.MR = s.nch ? (s.mt + s.nch - 1) / s.nch : 0;   // balanced chunks, every chunk non-empty
-  return s;
-}
+// Work of one CTA: super-items (row chunk c, vocabulary group q) strided by the grid; inside, the group's vocabulary ranges in
+// order (an "item").  All three warp roles walk the same sequence.
+struct Walk {
+  int G, nch, b, per, nvr, si, jr, jr_hi;
+  bool valid, first;
+  __device__ void start() {
+    valid = si < nch * b;
+    if (valid) { jr = (si % b) * per; jr_hi = min(nvr, jr + per); first = true; }
+  }
+  __device__ void init(const CfSplit& sp, int bid, int grid) {
+    G = grid; nch = sp.nch; b = sp.b; per = sp.per; nvr = sp.nvr; si = bid;
+    start();
+  }
+  __device__ void next() {
+    ++jr; first = false;
+    if (jr >= jr_hi) { si += G; start(); }
+  }
+  __device__ int c() const { return si / b; }
+  __device__ int q() const { return si % b; }
+};
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// dT slot update: the first vocabulary range of a super-item stores, the later ones ADD with a fire-and-forget reduction (no
+// read round trip in the drain).  Only this thread ever touches the address and its operations apply in program order, so the
+// summation order is fixed (deterministic).
+__device__ __forceinline__ void put4(float* dst, bool first, float x, float y, float z, float w) {
+  if (first) *reinterpret_cast<float4*>(dst) = make_float4(x, y, z, w);
+  else asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(dst), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 // MN-major operand: [k rows of 128 B (64 mn elements)], 16 k-rows per MMA, LBO = distance to the next 64-element mn block
 __device__ __forceinline__ uint64_t desc_mn(uint32_t byte_addr, uint32_t lbo_bytes) {
@@ -67,7 +87,7 @@ __host__ __device__ constexpr uint32_t idesc(int M, int N, int a_mn, int b_mn) {
 struct Dev {
   const float* vbias; const float* lse; const float* row_w; const int* labels; const int* d_counts;
   int M_cap, V;
-  float* dt_part;   // [nvr][M_cap][64]
+  float* dt_part;   // [vocabulary groups][M_cap][64]
   float* dE_part;   // [nch][V][64]
   float* db_part;   // [nch][V]
 };
@@ -81,26 +101,25 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
   float* sW = sLse + MR_MAX * FT;
   int* sLab = reinterpret_cast<int*>(sW + MR_MAX * FT);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* tiles_full = bars;         // TMA landed the item's tiles
-  uint64_t* tiles_free = bars + 1;     // every MMA of the item has read them
-  uint64_t* s_full = bars + 2;         // [2] MMA1 done
-  uint64_t* s_empty = bars + 4;        // [2] epilogue read S
-  uint64_t* dl_full = bars + 6;        // [2] epilogue wrote dl
-  uint64_t* dl_empty = bars + 8;       // [2] MMA2a/b consumed dl
-  uint64_t* acc_done = bars + 10;      // all MMAs of the item complete
-  uint64_t* drained = bars + 11;       // epilogue drained the item's dE accumulators
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* e_full = bars;             // [2] TMA landed the item's vocabulary tiles (+ the row tiles for the first item of a super-item)
+  uint64_t* e_free = bars + 2;         // [2] every MMA of the item has completed
+  uint64_t* s_full = bars + 4;         // [2] MMA1 done
+  uint64_t* s_empty = bars + 6;        // [2] epilogue read S
+  uint64_t* dl_full = bars + 8;        // [2] epilogue wrote dl
+  uint64_t* dl_empty = bars + 10;      // [2] MMA2a/b consumed dl
+  uint64_t* acc_done = bars + 12;      // all MMAs of the item complete
+  uint64_t* drained = bars + 13;       // epilogue drained the item's dE accumulators
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int n_valid = min(a.M_cap, a.d_counts[0]);
-  const Split sp = cf_split(n_valid, a.V);
-  const int items = sp.nvr * sp.nch;
+  const CfSplit sp = cf_split(n_valid, a.V, (int)gridDim.x);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    umma::mbar_init(tiles_full, 1); umma::mbar_init(tiles_free, 1);
     for (int b = 0; b < 2; ++b) {
-      umma::mbar_init(s_full + b, 1); umma::mbar_init(s_empty + b, 16);
-      umma::mbar_init(dl_full + b, 16); umma::mbar_init(dl_empty + b, 1);
+      umma::mbar_init(e_full + b, 1); umma::mbar_init(e_free + b, 1);
+      umma::mbar_init(s_full + b, 1); umma::mbar_init(s_empty + b, 8);
+      umma::mbar_init(dl_full + b, 8); umma::mbar_init(dl_empty + b, 1);
     }
     umma::mbar_init(acc_done, 1); umma::mbar_init(drained, 16);
     umma::fence_barrier_init();
@@ -118,14 +137,17 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      int it = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-        const int jr = item % sp.nvr, c = item / sp.nvr;
-        const int i0 = c * sp.MR, mrc = min(sp.MR, sp.mt - i0), j0 = jr * VR, vrc = min(VR, sp.vt - j0);
-        if (it > 0) umma::mbar_wait(tiles_free, (it - 1) & 1);
-        umma::mbar_expect_tx(tiles_full, (uint32_t)(mrc + vrc) * TILE);
-        for (int j = 0; j < vrc; ++j) umma::tma_load_2d(smem + OFF_E + j * TILE, &tmE, 0, (j0 + j) * FT, tiles_full);
-        for (int i = 0; i < mrc; ++i) umma::tma_load_2d(smem + OFF_T + i * TILE, &tmT, 0, (i0 + i) * FT, tiles_full);
+      Walk w;
+      w.init(sp, blockIdx.x, gridDim.x);
+      for (int it = 0; w.valid; w.next(), ++it) {
+        const int st = it & 1;
+        const int i0 = w.c() * sp.MR, mrc = min(sp.MR, sp.mt - i0), j0 = w.jr * VR, vrc = min(VR, sp.vt - j0);
+        if (it >= 2) umma::mbar_wait(e_free + st, ((it - 2) >> 1) & 1);                 // stage free: MMAs of item it-2 done
+        if (w.first && it > 0) umma::mbar_wait(e_free + ((it - 1) & 1), ((it - 1) >> 1) & 1);   // row tiles free: previous super-item done
+        umma::mbar_expect_tx(e_full + st, (uint32_t)(vrc + (w.first ? mrc : 0)) * TILE);
+        for (int j = 0; j < vrc; ++j) umma::tma_load_2d(smem + OFF_E + st * E_STAGE + j * TILE, &tmE, 0, (j0 + j) * FT, e_full + st);
+        if (w.first)
+          for (int i = 0; i < mrc; ++i) umma::tma_load_2d(smem + OFF_T + i * TILE, &tmT, 0, (i0 + i) * FT, e_full + st);
       }
     }
   } else if (warp == 1) {
@@ -134,15 +156,17 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
       constexpr uint32_t id1 = idesc(FT, FT, 0, 0);          // S   = T_i (K-major) . E_j (K-major)
       constexpr uint32_t id2a = idesc(FT, FH, 0, 1);         // dT += dl (K-major) . E_j (MN-major)
       constexpr uint32_t id2b = idesc(FT, DE_COLS, 1, 1);    // dE += dl^T (MN-major) . [T_i | ones] (MN-major)
-      const uint32_t t_base = umma::smem_addr(smem + OFF_T), e_base = umma::smem_addr(smem + OFF_E);
+      const uint32_t t_base = umma::smem_addr(smem + OFF_T), e_base0 = umma::smem_addr(smem + OFF_E);
       const uint32_t dl_base = umma::smem_addr(smem + OFF_DL), ones = umma::smem_addr(smem + OFF_ONES);
       uint32_t g = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-        const int jr = item % sp.nvr, c = item / sp.nvr;
-        const int i0 = c * sp.MR, mrc = min(sp.MR, sp.mt - i0), j0 = jr * VR, vrc = min(VR, sp.vt - j0);
+      Walk w;
+      w.init(sp, blockIdx.x, gridDim.x);
+      for (int it = 0; w.valid; w.next(), ++it) {
+        const int st = it & 1;
+        const int i0 = w.c() * sp.MR, mrc = min(sp.MR, sp.mt - i0), j0 = w.jr * VR, vrc = min(VR, sp.vt - j0);
         const int np = mrc * vrc;
-        umma::mbar_wait(tiles_full, it & 1);
+        const uint32_t e_base = e_base0 + st * E_STAGE;
+        umma::mbar_wait(e_full + st, (it >> 1) & 1);
         if (it > 0) umma::mbar_wait(drained, (it - 1) & 1);
         umma::fence_after_sync();
         auto mma1 = [&](int p, uint32_t gp) {
@@ -156,11 +180,14 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
                               umma::make_desc_k_sw128(e_base + j * TILE + k * 32), id1, k ? 1u : 0u);
           umma::mma_commit(s_full + buf);
         };
+        // MMA1 runs two pairs ahead: S[buf] is refilled as soon as the epilogue of pair p has READ it (s_empty, early in that
+        // epilogue), not after its dl tile is complete -- a group stalled in a dT drain does not starve the other group
         mma1(0, g);
+        if (np > 1) mma1(1, g + 1);
         for (int p = 0; p < np; ++p) {
           const uint32_t gp = g + p, buf = gp & 1;
           const int i = p / vrc, j = p - i * vrc;
-          if (p + 1 < np) mma1(p + 1, gp + 1);
+          if (p + 2 < np) mma1(p + 2, gp + 2);
           umma::mbar_wait(dl_full + buf, (gp >> 1) & 1);   // (the epilogue drains dT of row tile i-1 before it arrives here for j = 0)
           umma::fence_after_sync();
           const uint32_t dl = dl_base + buf * DL_BYTES, tt = t_base + i * TILE, ee = e_base + j * TILE;
@@ -175,22 +202,28 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
           umma::mma_commit(dl_empty + buf);
         }
         g += np;
-        umma::mma_commit(tiles_free);
+        umma::mma_commit(e_free + st);
         umma::mma_commit(acc_done);
       }
     }
   } else {
     // ===================================================================== epilogue (warps 2..17)
+    // Two groups of 8 warps take alternate pairs (group = S / dl buffer index), so that one group's TMEM-load, barrier and
+    // fence latencies overlap the other's arithmetic; inside a group a thread owns one row and 64 columns (`half`).
+    // The item tail (accumulator drains) uses all 16 warps: quadrant x column quarter `cq`.
     const int quad = warp & 3, cq = (warp - 2) >> 2;   // TMEM lane quadrant, column quarter
+    const int grp = (warp - 2) >> 3, half = cq & 1;
     const int row_in_tile = quad * 32 + lane;
     const int e = threadIdx.x - 64;                     // 0..511
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     constexpr float LOG2E = 1.4426950408889634f;
     uint32_t g = 0;
-    int it = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
-      const int jr = item % sp.nvr, c = item / sp.nvr;
-      const int i0 = c * sp.MR, mrc = min(sp.MR, sp.mt - i0), j0 = jr * VR, vrc = min(VR, sp.vt - j0);
+    Walk w;
+    w.init(sp, blockIdx.x, gridDim.x);
+    for (int it = 0; w.valid; w.next(), ++it) {
+      const int c = w.c(), slot = w.q();
+      const bool first = w.first;   // first vocabulary range of the super-item: the dT slot is written, afterwards added to
+      const int i0 = c * sp.MR, mrc = min(sp.MR, sp.mt - i0), j0 = w.jr * VR, vrc = min(VR, sp.vt - j0);
       const int np = mrc * vrc;
       auto drain_dt = [&](int i) {
         uint32_t r[16];
@@ -198,11 +231,10 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
         umma::tmem_ld_wait();
         const int m = (i0 + i) * FT + row_in_tile;
         if (m < n_valid) {
-          float* dst = a.dt_part + ((size_t)jr * a.M_cap + m) * FH + cq * 16;
+          float* dst = a.dt_part + ((size_t)slot * a.M_cap + m) * FH + cq * 16;
 #pragma unroll
           for (int q = 0; q < 16; q += 4)
-            *reinterpret_cast<float4*>(dst + q) =
-                make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
+            put4(dst + q, first, __uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
         }
       };
       asm volatile("bar.sync 1, 512;\n" ::: "memory");   // the previous item's vectors are no longer read
@@ -210,7 +242,7 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
         const int v = j0 * FT + x;
         sBias[x] = v < a.V ? a.vbias[v] * LOG2E : -INFINITY;
       }
-      for (int x = e; x < mrc * FT; x += 512) {
+      for (int x = e; first && x < mrc * FT; x += 512) {
         const int m = i0 * FT + x;
         const bool ok = m < n_valid;
         sLse[x] = ok ? a.lse[m] * LOG2E : 0.f;
@@ -220,43 +252,59 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
       asm volatile("bar.sync 1, 512;\n" ::: "memory");
       for (int p = 0; p < np; ++p) {
         const uint32_t gp = g + p, buf = gp & 1;
+        if ((int)buf != grp) continue;
         const int i = p / vrc, j = p - i * vrc;
         const int lrow = i * FT + row_in_tile;
         const float row_a = sLse[lrow];
         const bool row_on = sW[lrow] > 0.f;
-        const int rel_label = sLab[lrow] - ((j0 + j) * FT + cq * 32);   // label column relative to this thread's 32 columns
-        const float* vec = sBias + j * FT + cq * 32;
+        const int rel_label = sLab[lrow] - ((j0 + j) * FT + half * 64);   // label column relative to this thread's 64 columns
+        const float* vec = sBias + j * FT + half * 64;
+        unsigned char* rowp = smem + OFF_DL + buf * DL_BYTES + half * TILE + row_in_tile * 128;
         umma::mbar_wait(s_full + buf, (gp >> 1) & 1);
         umma::fence_after_sync();
-        uint32_t r[32];
-        umma::tmem_ld32(tmem + C_S + buf * FT + lane_off + cq * 32, r);
-        umma::tmem_ld_wait();
-        umma::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) umma::mbar_arrive(s_empty + buf);   // S buffer free: MMA1 of pair gp+2 may overwrite it
-        uint32_t pk[16];
+#pragma unroll 1
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t r[32];
+          umma::tmem_ld32(tmem + C_S + buf * FT + lane_off + half * 64 + c2 * 32, r);
+          umma::tmem_ld_wait();
+          if (c2 == 1) {
+            umma::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(s_empty + buf);   // S buffer free: MMA1 of pair gp+2 may overwrite it
+          }
+          uint32_t pk[16];
+          const int rl = rel_label - c2 * 32;
 #pragma unroll
-        for (int q = 0; q < 32; q += 2) {
-          const float2 b2 = *reinterpret_cast<const float2*>(vec + q);
-          float p0 = ex2_approx(fmaf(__uint_as_float(r[q]), LOG2E, b2.x) - row_a);
-          float p1 = ex2_approx(fmaf(__uint_as_float(r[q + 1]), LOG2E, b2.y) - row_a);
-          if (q == rel_label) p0 -= 1.f;
-          if (q + 1 == rel_label) p1 -= 1.f;
-          pk[q >> 1] = row_on ? pack_bf162(p0, p1) : 0u;
-        }
-        umma::mbar_wait(dl_empty + buf, ((gp >> 1) & 1) ^ 1);   // MMA2 of pair gp-2 has consumed this dl buffer
-        unsigned char* rowp = smem + OFF_DL + buf * DL_BYTES + (cq >> 1) * TILE + row_in_tile * 128;
+          for (int q = 0; q < 32; q += 2) {
+            const float2 b2 = *reinterpret_cast<const float2*>(vec + c2 * 32 + q);
+            float p0 = ex2_approx(fmaf(__uint_as_float(r[q]), LOG2E, b2.x) - row_a);
+            float p1 = ex2_approx(fmaf(__uint_as_float(r[q + 1]), LOG2E, b2.y) - row_a);
+            if (q == rl) p0 -= 1.f;
+            if (q + 1 == rl) p1 -= 1.f;
+            pk[q >> 1] = row_on ? pack_bf162(p0, p1) : 0u;
+          }
+          if (c2 == 0) umma::mbar_wait(dl_empty + buf, ((gp >> 1) & 1) ^ 1);   // MMA2 of pair gp-2 has consumed this dl buffer
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = ((cq & 1) * 4 + q) ^ (row_in_tile & 7);
-          *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = (c2 * 4 + q) ^ (row_in_tile & 7);
+            *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          }
         }
         if (j == 0 && i > 0) {
-          // dT of the previous row tile is final once the MMAs of pair gp-1 have completed; drain it before MMA2a of this pair
-          // (accumulate = 0) may overwrite it -- that MMA waits for this warp's dl_full arrival below
+          // dT of the previous row tile is final once the MMAs of pair gp-1 (the other group's) have completed; drain it before
+          // MMA2a of this pair (accumulate = 0) may overwrite it -- that MMA waits for this group's dl_full arrivals below
           umma::mbar_wait(dl_empty + ((gp - 1) & 1), ((gp - 1) >> 1) & 1);
           umma::fence_after_sync();
-          drain_dt(i - 1);
+          uint32_t r[32];
+          umma::tmem_ld32(tmem + C_DT + lane_off + half * 32, r);
+          umma::tmem_ld_wait();
+          const int m = (i0 + i - 1) * FT + row_in_tile;
+          if (m < n_valid) {
+            float* dst = a.dt_part + ((size_t)slot * a.M_cap + m) * FH + half * 32;
+#pragma unroll
+            for (int q = 0; q < 32; q += 4)
+              put4(dst + q, first, __uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
+          }
         }
         umma::fence_before_sync();
         umma::fence_proxy_async();
@@ -303,7 +351,7 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
 __global__ void __launch_bounds__(256) ce_bwd_fused_reduce_kernel(const float* __restrict__ dE_part, const float* __restrict__ db_part,
                                                                   const int* __restrict__ d_counts, int M_cap, int V,
                                                                   float* __restrict__ g_table, float* __restrict__ g_bias) {
-  const int nch = cf_split(min(M_cap, d_counts[0]), V).nch;
+  const int nch = cf_split(min(M_cap, d_counts[0]), V, 1).nch;
   const long long n4 = (long long)V * FH / 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n4) {
@@ -324,8 +372,7 @@ __global__ void __launch_bounds__(256) ce_bwd_fused_reduce_kernel(const float* _
 }  // namespace
 
 bool ce_bwd_fused_supported(int H) { return H == FH && getenv("B4R_DISABLE_CE_FUSED") == nullptr; }
-int ce_bwd_fused_vranges(int V) { return cf_split(0, V).nvr; }
-int ce_bwd_fused_max_chunks(int M_cap) { return cf_split(M_cap, 1).nch; }
+int ce_bwd_fused_max_chunks(int M_cap) { return cf_split(M_cap, 1, 1).nch; }
 
 cudaError_t launch_ce_bwd_fused(const CeUmmaMaps& maps, const CeBwdFusedArgs& a, cudaStream_t st) {
   static bool done = false;

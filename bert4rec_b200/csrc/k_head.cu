@@ -26,7 +26,9 @@ __global__ void __launch_bounds__(256) head_bwd_fused_kernel(const float* __rest
   __shared__ float sLn[3][HF_H];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = min(M_cap, d_counts[0]);    // valid masked slots only: aux rows carry no gradient
-  if (dyn_max > 0) {                        // split count chosen on the device by the generation-2 dT pass
+  if (dyn_max < 0) {                        // one-pass CE backward: slots = vocabulary groups (dyn_vtiles = V, dyn_target = its CTAs)
+    nsplit = cf_split(M, dyn_vtiles, dyn_target).b;
+  } else if (dyn_max > 0) {                 // split count chosen on the device by the generation-2 dT pass
     int mt = (M + 127) / 128; if (mt < 1) mt = 1;
     int vs = dyn_target / mt;
     if (vs > dyn_vtiles) vs = dyn_vtiles;

@@ -257,8 +257,26 @@ struct CeBwdFusedArgs {
   float* dt_part; float* dE_part; float* db_part;
 };
 bool ce_bwd_fused_supported(int H);
-int ce_bwd_fused_vranges(int V);
 int ce_bwd_fused_max_chunks(int M_cap);
+// decomposition shared by the kernel and its consumers: row chunks of <= 5 tiles, vocabulary ranges of 2 tiles; the `ctas`
+// resident CTAs are split into nch (row chunks) x b (groups of consecutive vocabulary ranges); one dT partial slot per group
+constexpr int CF_MR_MAX = 5, CF_VR = 2;
+struct CfSplit { int mt, vt, nvr, nch, MR, b, per; };
+__host__ __device__ inline CfSplit cf_split(int n_valid, int V, int ctas) {
+  CfSplit s;
+  s.mt = (n_valid + 127) / 128; s.vt = (V + 127) / 128;
+  s.nvr = (s.vt + CF_VR - 1) / CF_VR;
+  s.nch = (s.mt + CF_MR_MAX - 1) / CF_MR_MAX;
+  s.MR = s.nch ? (s.mt + s.nch - 1) / s.nch : 0;   // balanced chunks, every chunk non-empty
+  int b = s.nch ? ctas / s.nch : 0;
+  if (b < 1) b = 1;
+  if (b > s.nvr) b = s.nvr;
+  s.per = b ? (s.nvr + b - 1) / b : 0;
+  s.b = s.per ? (s.nvr + s.per - 1) / s.per : 0;   // every group non-empty
+  if (s.nch == 0) s.b = 0;
+  return s;
+}
+inline int ce_bwd_fused_dt_slot_cap(int V, int ctas) { const int nvr = ((V + 127) / 128 + CF_VR - 1) / CF_VR; return nvr < ctas ? nvr : ctas; }
 cudaError_t launch_ce_bwd_fused(const CeUmmaMaps& maps, const CeBwdFusedArgs& a, cudaStream_t st);
 cudaError_t launch_ce_bwd_fused_reduce(const CeBwdFusedArgs& a, float* g_table, float* g_bias, cudaStream_t st);
 // split count the generation-2 CE passes choose on the device (row tiles of 128): (row tiles x splits) fits one wave of target_ctas
