@@ -12,6 +12,8 @@
 namespace b4r {
 
 constexpr int HF_H = 64;
+constexpr int HF_LD = HF_H + 1;   // odd row stride: the transposing read of the final sum is conflict-free
+constexpr int HF_SMEM = (8 * HF_H * HF_LD + 8 * 3 * HF_H) * 4;
 
 __global__ void __launch_bounds__(256) head_bwd_fused_kernel(const float* __restrict__ dt_part, int nsplit, size_t split_stride,
                                                              const bf16* __restrict__ t_pre, const bf16* __restrict__ t_act,
@@ -22,8 +24,9 @@ __global__ void __launch_bounds__(256) head_bwd_fused_kernel(const float* __rest
                                                              float* __restrict__ p_ln, float* __restrict__ p_wt, int dyn_vtiles,
                                                              int dyn_target, int dyn_max) {
   __shared__ float sW[HF_H][HF_H + 1];      // Wt[in][out] as fp32
-  __shared__ float sAcc[HF_H][HF_H + 2];    // CTA accumulator of dWt, TRANSPOSED: [out][in] (lanes own consecutive in-columns)
-  __shared__ float sLn[3][HF_H];
+  extern __shared__ float sAccW[];          // [8 warps][out][HF_LD]: every warp's dWt accumulator, TRANSPOSED ([out][in]); then
+                                            // [8][3][HF_H]: its LayerNorm / bias sums -- summed over the warps in fixed order
+  float* sLnW = sAccW + 8 * HF_H * HF_LD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = min(M_cap, d_counts[0]);    // valid masked slots only: aux rows carry no gradient
   if (dyn_max < 0) {                        // one-pass CE backward: slots = vocabulary groups (dyn_vtiles = V, dyn_target = its CTAs)
@@ -43,8 +46,6 @@ __global__ void __launch_bounds__(256) head_bwd_fused_kernel(const float* __rest
 #pragma unroll
     for (int k = 0; k < 4; ++k) { const float2 f = unpack_bf162(w4[k]); sW[r][c + 2 * k] = f.x; sW[r][c + 2 * k + 1] = f.y; }
   }
-  for (int i = tid; i < HF_H * (HF_H + 2); i += 256) (&sAcc[0][0])[i] = 0.f;
-  if (tid < 3 * HF_H) sLn[tid / HF_H][tid % HF_H] = 0.f;
   __syncthreads();
   const int c0 = 2 * lane;
   const float g0 = gamma[c0], g1 = gamma[c0 + 1];
@@ -60,13 +61,13 @@ __global__ void __launch_bounds__(256) head_bwd_fused_kernel(const float* __rest
     const uint32_t act_u = *reinterpret_cast<const uint32_t*>(t_act + (size_t)m * HF_H + c0);
     const uint32_t tp_u = *reinterpret_cast<const uint32_t*>(t_pre + (size_t)m * HF_H + c0);
     const float mu = mean[m], rs = rstd[m];
-    for (int s0 = 0; s0 < nsplit; s0 += 8) {
-      float2 v[8];
+    for (int s0 = 0; s0 < nsplit; s0 += 16) {   // 16 independent loads in flight per lane
+      float2 v[16];
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
+      for (int k = 0; k < 16; ++k)
         v[k] = s0 + k < nsplit ? *reinterpret_cast<const float2*>(dt_part + (s0 + k) * split_stride + (size_t)m * HF_H + c0) : make_float2(0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { d0 += v[k].x; d1 += v[k].y; }
+      for (int k = 0; k < 16; ++k) { d0 += v[k].x; d1 += v[k].y; }
     }
     const uint32_t x_u = *reinterpret_cast<const uint32_t*>(x + (size_t)rm * HF_H + c0);
     const float2 act = unpack_bf162(act_u), tp = unpack_bf162(tp_u), xv = unpack_bf162(x_u);
@@ -91,23 +92,30 @@ __global__ void __launch_bounds__(256) head_bwd_fused_kernel(const float* __rest
     }
     *reinterpret_cast<float2*>(dx_out + (size_t)rm * HF_H + c0) = make_float2(dx0, dx1);
   }
-  // CTA reduction, warp after warp (fixed order -> deterministic)
+  // CTA reduction: every warp parks its accumulators in its own shared-memory slab, then all threads sum the slabs of the warps
+  // that had rows, in warp order (fixed order -> deterministic)
   const bool had_rows = blockIdx.x * 8 + warp < M;
-  for (int w = 0; w < 8; ++w) {
-    if (warp == w && had_rows) {
+  if (had_rows) {
+    float* slab = sAccW + warp * HF_H * HF_LD;
 #pragma unroll
-      for (int o = 0; o < HF_H; ++o) {
-        float2* p = reinterpret_cast<float2*>(&sAcc[o][c0]);
-        float2 v = *p;
-        v.x += acc0[o]; v.y += acc1[o];
-        *p = v;
-      }
-      sLn[0][c0] += a_g0; sLn[0][c0 + 1] += a_g1; sLn[1][c0] += a_b0; sLn[1][c0 + 1] += a_b1; sLn[2][c0] += a_c0; sLn[2][c0 + 1] += a_c1;
-    }
-    __syncthreads();
+    for (int o = 0; o < HF_H; ++o) { slab[o * HF_LD + c0] = acc0[o]; slab[o * HF_LD + c0 + 1] = acc1[o]; }
+    float* ln = sLnW + warp * 3 * HF_H;
+    ln[c0] = a_g0; ln[c0 + 1] = a_g1; ln[HF_H + c0] = a_b0; ln[HF_H + c0 + 1] = a_b1; ln[2 * HF_H + c0] = a_c0; ln[2 * HF_H + c0 + 1] = a_c1;
   }
-  for (int i = tid; i < HF_H * HF_H; i += 256) p_wt[(size_t)blockIdx.x * HF_H * HF_H + i] = sAcc[i % HF_H][i / HF_H];   // [in][out]
-  if (tid < 3 * HF_H) p_ln[(size_t)blockIdx.x * 3 * HF_H + tid] = sLn[tid / HF_H][tid % HF_H];
+  __syncthreads();
+  int nwarps = M - (int)blockIdx.x * 8;
+  nwarps = nwarps < 0 ? 0 : (nwarps > 8 ? 8 : nwarps);
+  for (int i = tid; i < HF_H * HF_H; i += 256) {   // i = in * 64 + out; slab index [out][in]
+    const int in = i / HF_H, out = i % HF_H;
+    float v = 0.f;
+    for (int w = 0; w < nwarps; ++w) v += sAccW[w * HF_H * HF_LD + out * HF_LD + in];
+    p_wt[(size_t)blockIdx.x * HF_H * HF_H + i] = v;
+  }
+  if (tid < 3 * HF_H) {
+    float v = 0.f;
+    for (int w = 0; w < nwarps; ++w) v += sLnW[w * 3 * HF_H + tid];
+    p_ln[(size_t)blockIdx.x * 3 * HF_H + tid] = v;
+  }
 }
 
 int head_bwd_fused_ctas() { return 148; }
@@ -117,7 +125,12 @@ cudaError_t launch_head_bwd_fused(const float* dt_part, int nsplit, size_t split
                                   const float* mean, const float* rstd, const float* gamma, const bf16* wt, const bf16* x,
                                   const int* rows, const int* d_counts, int M_cap, float* dx_out, float* p_ln, float* p_wt,
                                   cudaStream_t st, int dyn_vtiles, int dyn_target, int dyn_max) {
-  head_bwd_fused_kernel<<<head_bwd_fused_ctas(), 256, 0, st>>>(dt_part, nsplit, split_stride, t_pre, t_act, mean, rstd, gamma, wt, x, rows,
+  static bool done = false;
+  if (!done) {
+    cudaFuncSetAttribute(head_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HF_SMEM);
+    done = true;
+  }
+  head_bwd_fused_kernel<<<head_bwd_fused_ctas(), 256, HF_SMEM, st>>>(dt_part, nsplit, split_stride, t_pre, t_act, mean, rstd, gamma, wt, x, rows,
                                                               d_counts, M_cap, dx_out, p_ln, p_wt, dyn_vtiles, dyn_target, dyn_max);
   return cudaGetLastError();
 }
