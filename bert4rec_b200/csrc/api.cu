@@ -705,6 +705,7 @@ static int backward_impl(b4r_session* s, uint64_t seed, uint32_t step, const int
     CeBwdFusedArgs fa{};
     fa.vbias = c.vbias; fa.lse = s->lse; fa.row_w = s->row_w; fa.labels = s->labels; fa.d_counts = s->counts;
     fa.M_cap = Mcap; fa.V = V; fa.ctas = kCeFusedCtas; fa.dt_part = s->cf_dt; fa.dE_part = s->cf_dE; fa.db_part = s->cf_db;
+    fa.dbg = getenv("B4R_CF_DEBUG") ? s->dbg_buf : nullptr;
     KL("ce_bwd_fused", launch_ce_bwd_fused(s->umaps, fa, st));
     // the MLM-transform backward needs dT only: it runs as a branch beside the reduction of the dE partials
     CK(cudaEventRecord(s->ev_fork, st));

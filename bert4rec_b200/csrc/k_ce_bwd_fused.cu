@@ -28,12 +28,12 @@ constexpr int TILE = FT * 128;      // [128 rows][64 bf16], 128-byte swizzled ro
 constexpr int DL_BYTES = 2 * TILE;  // [128 m][128 v] as two [128][64] sub-tiles
 constexpr int E_STAGE = VR * TILE;  // the vocabulary tiles of one item; two stages (the next item is prefetched)
 constexpr int OFF_T = 0, OFF_E = MR_MAX * TILE, OFF_DL = OFF_E + 2 * E_STAGE, OFF_ONES = OFF_DL + 2 * DL_BYTES, ONES_BYTES = 2048;
-constexpr int OFF_VEC = OFF_ONES + ONES_BYTES;   // bias [VR*128] | lse [MR_MAX*128] | w [MR_MAX*128] | label [MR_MAX*128]
-constexpr int VEC_WORDS = VR * FT + 3 * MR_MAX * FT;
+constexpr int OFF_VEC = OFF_ONES + ONES_BYTES;   // bias [2 items][VR*128] | lse [MR_MAX*128] | label [MR_MAX*128]
+constexpr int VEC_WORDS = 2 * VR * FT + 2 * MR_MAX * FT;
 constexpr int OFF_BAR = OFF_VEC + VEC_WORDS * 4;
 constexpr int SMEM = OFF_BAR + 256 + 1024;
 static_assert(SMEM <= 232448, "shared memory");
-constexpr int NTHR = 64 + 512;
+constexpr int NTHR = 128 + 512;   // warp 0: TMA, warps 1-3: MMA issuers, warps 4-19: epilogue
 constexpr uint32_t C_S = 0, C_DT = 256, C_DE = 320, DE_COLS = 80;   // TMEM columns: S0, S1 | dT | dE_0, dE_1 (64 + 16 ones columns)
 
 // Work of one CTA: super-items (row chunk c, vocabulary group q) strided by the grid; inside, the group's vocabulary ranges in
@@ -69,6 +69,33 @@ __device__ __forceinline__ void put4(float* dst, bool first, float x, float y, f
   if (first) *reinterpret_cast<float4*>(dst) = make_float4(x, y, z, w);
   else asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(dst), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// packed fp32 pair arithmetic (sm_100 f32x2): {o0, o1} = {x0, x1} * l2 + ({b0, b1} + nra2)
+__device__ __forceinline__ void fma2_bias(float& o0, float& o1, float x0, float x1, uint64_t l2, float b0, float b1, uint64_t nra2) {
+  asm("{\n"
+      ".reg .b64 x, b, t;\n"
+      "mov.b64 x, {%2, %3};\n"
+      "mov.b64 b, {%5, %6};\n"
+      "add.rn.f32x2 t, b, %7;\n"
+      "fma.rn.f32x2 t, x, %4, t;\n"
+      "mov.b64 {%0, %1}, t;\n"
+      "}\n"
+      : "=f"(o0), "=f"(o1)
+      : "f"(x0), "f"(x1), "l"(l2), "f"(b0), "f"(b1), "l"(nra2));
+}
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+#define CF_STAMP(role, pair, k)                                                                    \
+  do {                                                                                             \
+    if (a.dbg && blockIdx.x == 0 && (pair) < 32u && lane == 0) a.dbg[(role) * 128 + (pair) * 4 + (k)] = gtime(); \
+  } while (0)
 // MN-major operand: [k rows of 128 B (64 mn elements)], 16 k-rows per MMA, LBO = distance to the next 64-element mn block
 __device__ __forceinline__ uint64_t desc_mn(uint32_t byte_addr, uint32_t lbo_bytes) {
   uint64_t d = 0;
@@ -90,6 +117,7 @@ struct Dev {
   float* dt_part;   // [vocabulary groups][M_cap][64]
   float* dE_part;   // [nch][V][64]
   float* db_part;   // [nch][V]
+  unsigned long long* dbg;   // development aid (B4R_CF_DEBUG): %globaltimer stamps of CTA 0, [4 roles][32 pairs][4]
 };
 
 __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmE,
@@ -97,9 +125,8 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* sBias = reinterpret_cast<float*>(smem + OFF_VEC);
-  float* sLse = sBias + VR * FT;
-  float* sW = sLse + MR_MAX * FT;
-  int* sLab = reinterpret_cast<int*>(sW + MR_MAX * FT);
+  float* sLse = sBias + 2 * VR * FT;   // lse * log2e of the row, +inf for rows without a gradient (their dl is exp2(-inf) = 0)
+  int* sLab = reinterpret_cast<int*>(sLse + MR_MAX * FT);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* e_full = bars;             // [2] TMA landed the item's vocabulary tiles (+ the row tiles for the first item of a super-item)
   uint64_t* e_free = bars + 2;         // [2] every MMA of the item has completed
@@ -117,11 +144,11 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
-      umma::mbar_init(e_full + b, 1); umma::mbar_init(e_free + b, 1);
+      umma::mbar_init(e_full + b, 1); umma::mbar_init(e_free + b, 3);
       umma::mbar_init(s_full + b, 1); umma::mbar_init(s_empty + b, 8);
-      umma::mbar_init(dl_full + b, 8); umma::mbar_init(dl_empty + b, 1);
+      umma::mbar_init(dl_full + b, 8); umma::mbar_init(dl_empty + b, 2);
     }
-    umma::mbar_init(acc_done, 1); umma::mbar_init(drained, 16);
+    umma::mbar_init(acc_done, 2); umma::mbar_init(drained, 16);
     umma::fence_barrier_init();
     umma::prefetch_tensormap(&tmT);
     umma::prefetch_tensormap(&tmE);
@@ -150,8 +177,10 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
           for (int i = 0; i < mrc; ++i) umma::tma_load_2d(smem + OFF_T + i * TILE, &tmT, 0, (i0 + i) * FT, e_full + st);
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
+  } else if (warp <= 3) {
+    // ===================================================================== MMA issuers: three single threads, one per accumulator
+    // chain -- warp 1: S = T_i . E_j^T, warp 2: dT += dl . E_j, warp 3: dE += dl^T . [T_i | 1].  A single thread issuing all 20
+    // MMAs of a pair was the bottleneck of the kernel (ncu: tensor pipe 18 % active, epilogue warps waiting on barriers).
     if (lane == 0) {
       constexpr uint32_t id1 = idesc(FT, FT, 0, 0);          // S   = T_i (K-major) . E_j (K-major)
       constexpr uint32_t id2a = idesc(FT, FH, 0, 1);         // dT += dl (K-major) . E_j (MN-major)
@@ -167,54 +196,61 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
         const int np = mrc * vrc;
         const uint32_t e_base = e_base0 + st * E_STAGE;
         umma::mbar_wait(e_full + st, (it >> 1) & 1);
-        if (it > 0) umma::mbar_wait(drained, (it - 1) & 1);
+        if (warp != 1 && it > 0) umma::mbar_wait(drained, (it - 1) & 1);   // all 16 epilogue warps have read the previous item's dT / dE
         umma::fence_after_sync();
-        auto mma1 = [&](int p, uint32_t gp) {
-          const int i = p / vrc, j = p - i * vrc;
-          const uint32_t buf = gp & 1;
-          umma::mbar_wait(s_empty + buf, ((gp >> 1) & 1) ^ 1);
-          umma::fence_after_sync();
+        if (warp == 1) {
+          // S[buf] is refilled as soon as the epilogue of pair p-2 has READ it (s_empty, early in that epilogue)
+          for (int p = 0; p < np; ++p) {
+            const uint32_t gp = g + p, buf = gp & 1;
+            const int i = p / vrc, j = p - i * vrc;
+            umma::mbar_wait(s_empty + buf, ((gp >> 1) & 1) ^ 1);
+            umma::fence_after_sync();
+            CF_STAMP(3, gp, 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma::mma_bf16_ss(tmem + C_S + buf * FT, umma::make_desc_k_sw128(t_base + i * TILE + k * 32),
-                              umma::make_desc_k_sw128(e_base + j * TILE + k * 32), id1, k ? 1u : 0u);
-          umma::mma_commit(s_full + buf);
-        };
-        // MMA1 runs two pairs ahead: S[buf] is refilled as soon as the epilogue of pair p has READ it (s_empty, early in that
-        // epilogue), not after its dl tile is complete -- a group stalled in a dT drain does not starve the other group
-        mma1(0, g);
-        if (np > 1) mma1(1, g + 1);
-        for (int p = 0; p < np; ++p) {
-          const uint32_t gp = g + p, buf = gp & 1;
-          const int i = p / vrc, j = p - i * vrc;
-          if (p + 2 < np) mma1(p + 2, gp + 2);
-          umma::mbar_wait(dl_full + buf, (gp >> 1) & 1);   // (the epilogue drains dT of row tile i-1 before it arrives here for j = 0)
-          umma::fence_after_sync();
-          const uint32_t dl = dl_base + buf * DL_BYTES, tt = t_base + i * TILE, ee = e_base + j * TILE;
+            for (int k = 0; k < 4; ++k)
+              umma::mma_bf16_ss(tmem + C_S + buf * FT, umma::make_desc_k_sw128(t_base + i * TILE + k * 32),
+                                umma::make_desc_k_sw128(e_base + j * TILE + k * 32), id1, k ? 1u : 0u);
+            umma::mma_commit(s_full + buf);
+            CF_STAMP(3, gp, 1);
+          }
+        } else {
+          for (int p = 0; p < np; ++p) {
+            const uint32_t gp = g + p, buf = gp & 1;
+            const int i = p / vrc, j = p - i * vrc;
+            umma::mbar_wait(dl_full + buf, (gp >> 1) & 1);   // (the epilogue drains dT of row tile i-1 before it arrives here for j = 0)
+            umma::fence_after_sync();
+            const uint32_t dl = dl_base + buf * DL_BYTES, tt = t_base + i * TILE, ee = e_base + j * TILE;
+            if (warp == 2) CF_STAMP(2, gp, 0);
+            if (warp == 2) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma::mma_bf16_ss(tmem + C_DT, umma::make_desc_k_sw128(dl + (kk >> 2) * TILE + (kk & 3) * 32), desc_mn(ee + kk * 2048, TILE),
-                              id2a, (j | kk) ? 1u : 0u);
+              for (int kk = 0; kk < 8; ++kk)
+                umma::mma_bf16_ss(tmem + C_DT, umma::make_desc_k_sw128(dl + (kk >> 2) * TILE + (kk & 3) * 32), desc_mn(ee + kk * 2048, TILE),
+                                  id2a, (j | kk) ? 1u : 0u);
+            } else {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma::mma_bf16_ss(tmem + C_DE + j * DE_COLS, desc_mn(dl + kk * 2048, TILE), desc_mn(tt + kk * 2048, ones - (tt + kk * 2048)),
-                              id2b, (i | kk) ? 1u : 0u);
-          umma::mma_commit(dl_empty + buf);
+              for (int kk = 0; kk < 8; ++kk)
+                umma::mma_bf16_ss(tmem + C_DE + j * DE_COLS, desc_mn(dl + kk * 2048, TILE),
+                                  desc_mn(tt + kk * 2048, ones - (tt + kk * 2048)), id2b, (i | kk) ? 1u : 0u);
+            }
+            if (warp == 2) CF_STAMP(2, gp, 1);
+            umma::mma_commit(dl_empty + buf);   // two arrivals: the dT and the dE chain
+            if (warp == 2) CF_STAMP(2, gp, 2);
+          }
         }
         g += np;
-        umma::mma_commit(e_free + st);
-        umma::mma_commit(acc_done);
+        umma::mma_commit(e_free + st);          // three arrivals
+        if (warp != 1) umma::mma_commit(acc_done);   // two arrivals
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..17)
+    // ===================================================================== epilogue (warps 4..19)
     // Two groups of 8 warps take alternate pairs (group = S / dl buffer index), so that one group's TMEM-load, barrier and
     // fence latencies overlap the other's arithmetic; inside a group a thread owns one row and 64 columns (`half`).
     // The item tail (accumulator drains) uses all 16 warps: quadrant x column quarter `cq`.
-    const int quad = warp & 3, cq = (warp - 2) >> 2;   // TMEM lane quadrant, column quarter
-    const int grp = (warp - 2) >> 3, half = cq & 1;
+    const int quad = warp & 3, cq = (warp - 4) >> 2;   // TMEM lane quadrant, column quarter
+    const int grp = (warp - 4) >> 3, half = cq & 1;
     const int row_in_tile = quad * 32 + lane;
-    const int e = threadIdx.x - 64;                     // 0..511
+    const int e = threadIdx.x - 128;                    // 0..511
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     constexpr float LOG2E = 1.4426950408889634f;
     uint32_t g = 0;
@@ -237,31 +273,47 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
             put4(dst + q, first, __uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
         }
       };
-      asm volatile("bar.sync 1, 512;\n" ::: "memory");   // the previous item's vectors are no longer read
-      for (int x = e; x < vrc * FT; x += 512) {
-        const int v = j0 * FT + x;
-        sBias[x] = v < a.V ? a.vbias[v] * LOG2E : -INFINITY;
+      // bias of this item: written into buffer it & 1 by the previous item's tail (prefetched a whole item ahead), directly for
+      // the first item; row vectors once per super-item
+      if (it == 0)
+        for (int x = e; x < vrc * FT; x += 512) {
+          const int v = j0 * FT + x;
+          sBias[x] = v < a.V ? a.vbias[v] * LOG2E : -INFINITY;
+        }
+      asm volatile("bar.sync 1, 512;\n" ::: "memory");   // bias visible; the previous super-item's row vectors are no longer read
+      if (first) {
+        for (int x = e; x < mrc * FT; x += 512) {
+          const int m = i0 * FT + x;
+          const bool on = m < n_valid && a.row_w[m] > 0.f;
+          sLse[x] = on ? a.lse[m] * LOG2E : INFINITY;
+          sLab[x] = on ? a.labels[m] : -1;
+        }
+        asm volatile("bar.sync 1, 512;\n" ::: "memory");
       }
-      for (int x = e; first && x < mrc * FT; x += 512) {
-        const int m = i0 * FT + x;
-        const bool ok = m < n_valid;
-        sLse[x] = ok ? a.lse[m] * LOG2E : 0.f;
-        sW[x] = ok ? a.row_w[m] : 0.f;
-        sLab[x] = ok ? a.labels[m] : -1;
+      float next_bias = 0.f;   // the next item's bias value of column e (threads 0..255), in flight during this item's pairs
+      {
+        Walk wn = w;
+        wn.next();
+        if (wn.valid && e < VR * FT) {
+          const int v = wn.jr * VR * FT + e;
+          next_bias = v < a.V ? a.vbias[v] * LOG2E : -INFINITY;
+        }
       }
-      asm volatile("bar.sync 1, 512;\n" ::: "memory");
+      const float* bias_it = sBias + (it & 1) * VR * FT;
+      if (warp == 4) CF_STAMP(3, (uint32_t)it + 16, 3);
       for (int p = 0; p < np; ++p) {
         const uint32_t gp = g + p, buf = gp & 1;
         if ((int)buf != grp) continue;
         const int i = p / vrc, j = p - i * vrc;
         const int lrow = i * FT + row_in_tile;
-        const float row_a = sLse[lrow];
-        const bool row_on = sW[lrow] > 0.f;
+        const uint64_t nra2 = pack2(-sLse[lrow], -sLse[lrow]), l2 = pack2(LOG2E, LOG2E);
         const int rel_label = sLab[lrow] - ((j0 + j) * FT + half * 64);   // label column relative to this thread's 64 columns
-        const float* vec = sBias + j * FT + half * 64;
+        const float* vec = bias_it + j * FT + half * 64;
         unsigned char* rowp = smem + OFF_DL + buf * DL_BYTES + half * TILE + row_in_tile * 128;
         umma::mbar_wait(s_full + buf, (gp >> 1) & 1);
         umma::fence_after_sync();
+        const bool stamp = ((warp - 4) & 7) == 0;
+        if (stamp) CF_STAMP(grp, gp, 0);
 #pragma unroll 1
         for (int c2 = 0; c2 < 2; ++c2) {
           uint32_t r[32];
@@ -273,22 +325,29 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
             if (lane == 0) umma::mbar_arrive(s_empty + buf);   // S buffer free: MMA1 of pair gp+2 may overwrite it
           }
           uint32_t pk[16];
-          const int rl = rel_label - c2 * 32;
 #pragma unroll
           for (int q = 0; q < 32; q += 2) {
             const float2 b2 = *reinterpret_cast<const float2*>(vec + c2 * 32 + q);
-            float p0 = ex2_approx(fmaf(__uint_as_float(r[q]), LOG2E, b2.x) - row_a);
-            float p1 = ex2_approx(fmaf(__uint_as_float(r[q + 1]), LOG2E, b2.y) - row_a);
-            if (q == rl) p0 -= 1.f;
-            if (q + 1 == rl) p1 -= 1.f;
-            pk[q >> 1] = row_on ? pack_bf162(p0, p1) : 0u;
+            float x0, x1;
+            fma2_bias(x0, x1, __uint_as_float(r[q]), __uint_as_float(r[q + 1]), l2, b2.x, b2.y, nra2);
+            pk[q >> 1] = pack_bf162(ex2_approx(x0), ex2_approx(x1));
           }
-          if (c2 == 0) umma::mbar_wait(dl_empty + buf, ((gp >> 1) & 1) ^ 1);   // MMA2 of pair gp-2 has consumed this dl buffer
+          if (c2 == 0) {
+            if (stamp) CF_STAMP(grp, gp, 1);
+            umma::mbar_wait(dl_empty + buf, ((gp >> 1) & 1) ^ 1);   // MMA2 of pair gp-2 has consumed this dl buffer
+            if (stamp) CF_STAMP(grp, gp, 2);
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int chunk = (c2 * 4 + q) ^ (row_in_tile & 7);
             *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           }
+        }
+        if (rel_label >= 0 && rel_label < 64) {
+          // the one-hot term: the label column lives in this thread's row segment (written just above): p -> p - 1 in place
+          const int chunk = (rel_label >> 3) ^ (row_in_tile & 7);
+          __nv_bfloat16* el = reinterpret_cast<__nv_bfloat16*>(rowp + chunk * 16) + (rel_label & 7);
+          *el = __float2bfloat16_rn(__bfloat162float(*el) - 1.f);
         }
         if (j == 0 && i > 0) {
           // dT of the previous row tile is final once the MMAs of pair gp-1 (the other group's) have completed; drain it before
@@ -310,12 +369,16 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
         umma::fence_proxy_async();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(dl_full + buf);
+        if (stamp) CF_STAMP(grp, gp, 3);
       }
       g += np;
       // ---- item tail: last dT tile, the dE accumulators and the bias column
+      if (warp == 4) CF_STAMP(3, (uint32_t)it, 2);
       umma::mbar_wait(acc_done, it & 1);
       umma::fence_after_sync();
+      if (warp == 4) CF_STAMP(3, (uint32_t)it, 3);
       drain_dt(mrc - 1);
+      if (warp == 4) CF_STAMP(2, (uint32_t)it, 3);
       for (int j = 0; j < vrc; ++j) {
         const int v = (j0 + j) * FT + row_in_tile;
         uint32_t r[16];
@@ -337,6 +400,8 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
       umma::fence_before_sync();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(drained);
+      if (e < VR * FT) sBias[((it + 1) & 1) * VR * FT + e] = next_bias;   // (buffer (it+1)&1 was last read in item it-1)
+      if (warp == 4) CF_STAMP(3, (uint32_t)it + 16, 2);
     }
   }
   umma::fence_before_sync();
@@ -382,7 +447,7 @@ cudaError_t launch_ce_bwd_fused(const CeUmmaMaps& maps, const CeBwdFusedArgs& a,
   }
   Dev d;
   d.vbias = a.vbias; d.lse = a.lse; d.row_w = a.row_w; d.labels = a.labels; d.d_counts = a.d_counts; d.M_cap = a.M_cap; d.V = a.V;
-  d.dt_part = a.dt_part; d.dE_part = a.dE_part; d.db_part = a.db_part;
+  d.dt_part = a.dt_part; d.dE_part = a.dE_part; d.db_part = a.db_part; d.dbg = a.dbg;
   const CUtensorMap& tmT = *reinterpret_cast<const CUtensorMap*>(maps.a);
   const CUtensorMap& tmE = *reinterpret_cast<const CUtensorMap*>(maps.b);
   ce_bwd_fused_kernel<<<a.ctas > 0 ? a.ctas : 148, NTHR, SMEM, st>>>(tmT, tmE, d);

@@ -255,6 +255,7 @@ struct CeBwdFusedArgs {
   const float* vbias; const float* lse; const float* row_w; const int* labels; const int* d_counts;
   int M_cap, V, ctas;
   float* dt_part; float* dE_part; float* db_part;
+  unsigned long long* dbg;   // optional timestamps (development aid)
 };
 bool ce_bwd_fused_supported(int H);
 int ce_bwd_fused_max_chunks(int M_cap);
