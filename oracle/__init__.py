@@ -17,5 +17,9 @@ Pinning status (see DESIGN.md "Oracle"):
   the arithmetic lives in tensorflow==2.10.0, keras==2.10.0 and
   tf-models-official==2.10.1, none of which is present under /root/reference
   or installable here; the restatement follows the published layer semantics
-   and the reference's call sites.
+   and the reference's call sites.  It IS cross-checked
+  against an independent implementation of the same architecture (Hugging Face
+  ``BertForMaskedLM`` with the oracle's weights: outputs, loss and gradients,
+  ``tests/test_oracle_vs_hf_bert.py``); parity with TensorFlow itself remains
+  unpinned.
 """
