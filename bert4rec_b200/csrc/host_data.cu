@@ -294,6 +294,71 @@ extern "C" int b4r_host_sample_random_batch(const int64_t* vocab, int64_t n_voca
     if (i == 0 || vocab[i] > vmax) vmax = vocab[i];
   }
   const bool dense = n_vocab > 0 && vmin >= 0 && vmax < (1ll << 26);
+  // Fast path (the reproducible-evaluation case: one fixed seed for every call, no duplicates, unique small ids): the legacy
+  // permutation depends on (seed, pool size) only, so it is shuffled ONCE per distinct pool size of the batch and its first
+  // sample_size entries are mapped through each request's pool by rank-select over the excluded positions -- the same draws as the
+  // per-request full shuffle, O(|without| + sample_size * |without|) instead of O(V) per request.
+  bool same_seed = n > 0 && !allow_duplicates && dense && sample_size > 0;
+  for (int b = 1; same_seed && b < n; ++b) same_seed = seeds[b] == seeds[0];
+  if (same_seed) {
+    std::vector<int32_t> pos_of((size_t)vmax + 1, -1);
+    bool unique = true;
+    for (int64_t i = 0; i < n_vocab && unique; ++i) {
+      if (pos_of[(size_t)vocab[i]] >= 0) unique = false;
+      pos_of[(size_t)vocab[i]] = (int32_t)i;
+    }
+    if (unique && n_vocab < (1ll << 31)) {
+      const int64_t tot_wo = without ? without_off[n] - without_off[0] : 0;
+      std::vector<int32_t> ex_pos((size_t)tot_wo);   // per request: sorted unique excluded vocab positions, at without_off[b] - without_off[0]
+      std::vector<int32_t> ex_cnt((size_t)n, 0);
+      int rc = run_parallel(n, n_threads, [&](int b) -> int {
+        int32_t* e = ex_pos.data() + (without ? without_off[b] - without_off[0] : 0);
+        int m = 0;
+        if (without)
+          for (int64_t k = without_off[b]; k < without_off[b + 1]; ++k) {
+            const int64_t wv = without[k];
+            if (wv >= 0 && wv <= vmax && pos_of[(size_t)wv] >= 0) e[m++] = pos_of[(size_t)wv];
+          }
+        std::sort(e, e + m);
+        m = (int)(std::unique(e, e + m) - e);
+        ex_cnt[(size_t)b] = m;
+        if (sample_size > n_vocab - m) return err.fail("Cannot take a larger sample than population when 'replace=False'");
+        return 0;
+      });
+      if (rc) return err.finish(rc);
+      // distinct pool sizes -> shuffled prefixes
+      std::vector<int64_t> sizes;
+      for (int b = 0; b < n; ++b) sizes.push_back(n_vocab - ex_cnt[(size_t)b]);
+      std::sort(sizes.begin(), sizes.end());
+      sizes.erase(std::unique(sizes.begin(), sizes.end()), sizes.end());
+      std::vector<std::vector<int64_t>> prefix(sizes.size());
+      rc = run_parallel((int)sizes.size(), n_threads, [&](int si) -> int {
+        thread_local std::vector<int64_t> ident, perm;
+        const int64_t m = sizes[(size_t)si];
+        ident.resize((size_t)m);
+        for (int64_t i = 0; i < m; ++i) ident[(size_t)i] = i;
+        MT19937 g;
+        g.init_genrand(seeds[0]);
+        prefix[(size_t)si].resize((size_t)sample_size);
+        return np_choice_uniform(err, g, ident, sample_size, false, prefix[(size_t)si].data(), perm);
+      });
+      if (rc) return err.finish(rc);
+      rc = run_parallel(n, n_threads, [&](int b) -> int {
+        const int m = ex_cnt[(size_t)b];
+        const int32_t* e = ex_pos.data() + (without ? without_off[b] - without_off[0] : 0);
+        const size_t si = (size_t)(std::lower_bound(sizes.begin(), sizes.end(), n_vocab - m) - sizes.begin());
+        const int64_t* pf = prefix[si].data();
+        int64_t* o = out + (size_t)b * sample_size;
+        for (int k = 0; k < sample_size; ++k) {
+          int64_t pos = pf[k];   // index into the pool -> position in the vocab: skip the excluded positions at or below it
+          for (int q = 0; q < m && e[q] <= pos; ++q) ++pos;
+          o[k] = vocab[(size_t)pos];
+        }
+        return 0;
+      });
+      return err.finish(rc);
+    }
+  }
   const int rc = run_parallel(n, n_threads, [&](int b) -> int {
     thread_local std::vector<int64_t> pool, perm;
     thread_local std::unordered_set<int64_t> ex;
@@ -367,20 +432,13 @@ extern "C" int b4r_host_sample_pop_random_batch(const int64_t* vocab, const doub
   }
   int64_t nonzero = 0;
   for (int64_t i = 0; i < n_vocab; ++i) nonzero += p[i] > 0.0;
-  const int rc = run_parallel(n, n_threads, [&](int b) -> int {
-    thread_local std::unordered_set<int64_t> ex;
+  // one weighted legacy draw of `size` indices: np.random.choice(n_vocab, size, replace, p) after np.random.seed(seed)
+  auto draw = [&](uint32_t seed, int64_t size, std::vector<int64_t>& found) -> int {
     thread_local std::vector<double> pw, cdf, x;
-    thread_local std::vector<int64_t> found;
     thread_local std::vector<std::pair<int64_t, int>> uniq;
     thread_local std::vector<std::pair<int, int64_t>> byidx;
-    ex.clear();
-    if (without) ex.insert(without + without_off[b], without + without_off[b + 1]);
-    const int64_t size = sample_size + (without ? (int64_t)ex.size() : 0);
-    if (!allow_duplicates && size > n_vocab)
-      return err.fail("The given without list (length: %d reduces the vocab (length: %lld) too much to take a sample of size %d "
-                       "(since no duplicates are allowed).", (int)ex.size(), (long long)n_vocab, sample_size);
     MT19937 g;
-    g.init_genrand(seeds[b]);
+    g.init_genrand(seed);
     found.assign((size_t)size, 0);
     cdf.resize((size_t)n_vocab);
     auto make_cdf = [&](const double* q) {
@@ -418,11 +476,56 @@ extern "C" int b4r_host_sample_pop_random_batch(const int64_t* vocab, const doub
         for (auto& e : byidx) found[(size_t)n_uniq++] = e.second;
       }
     }
+    for (int64_t i = 0; i < size; ++i)
+      if (found[(size_t)i] >= n_vocab) return err.fail("internal: sampled index out of range");
+    return 0;
+  };
+  // the draw depends on (seed, sample_size + |set(without)|) only -- `without` just filters it afterwards: with one seed for the
+  // whole batch (reproducible evaluation) it is computed once per distinct draw size and shared by the requests
+  bool same_seed = n > 0;
+  for (int b = 1; same_seed && b < n; ++b) same_seed = seeds[b] == seeds[0];
+  std::vector<int64_t> draw_sizes;
+  std::vector<std::vector<int64_t>> shared;
+  if (same_seed) {
+    std::vector<int64_t> dsz((size_t)n);
+    int rc0 = run_parallel(n, n_threads, [&](int b) -> int {
+      thread_local std::vector<int64_t> w;
+      w.clear();
+      if (without) w.assign(without + without_off[b], without + without_off[b + 1]);
+      std::sort(w.begin(), w.end());
+      dsz[(size_t)b] = sample_size + (int64_t)(std::unique(w.begin(), w.end()) - w.begin());
+      return 0;
+    });
+    if (rc0) return err.finish(rc0);
+    draw_sizes = dsz;
+    std::sort(draw_sizes.begin(), draw_sizes.end());
+    draw_sizes.erase(std::unique(draw_sizes.begin(), draw_sizes.end()), draw_sizes.end());
+    shared.resize(draw_sizes.size());
+    rc0 = run_parallel((int)draw_sizes.size(), n_threads, [&](int si) -> int {
+      if (!allow_duplicates && draw_sizes[(size_t)si] > n_vocab) return 0;   // reported per request below, with its own message
+      return draw(seeds[0], draw_sizes[(size_t)si], shared[(size_t)si]);
+    });
+    if (rc0) return err.finish(rc0);
+  }
+  const int rc = run_parallel(n, n_threads, [&](int b) -> int {
+    thread_local std::unordered_set<int64_t> ex;
+    thread_local std::vector<int64_t> own;
+    ex.clear();
+    if (without) ex.insert(without + without_off[b], without + without_off[b + 1]);
+    const int64_t size = sample_size + (without ? (int64_t)ex.size() : 0);
+    if (!allow_duplicates && size > n_vocab)
+      return err.fail("The given without list (length: %d reduces the vocab (length: %lld) too much to take a sample of size %d "
+                       "(since no duplicates are allowed).", (int)ex.size(), (long long)n_vocab, sample_size);
+    const std::vector<int64_t>* found = &own;
+    if (same_seed) {
+      found = &shared[(size_t)(std::lower_bound(draw_sizes.begin(), draw_sizes.end(), size) - draw_sizes.begin())];
+    } else if (draw(seeds[b], size, own)) {
+      return 1;
+    }
     int k = 0;
     int64_t* o = out + (size_t)b * sample_size;
     for (int64_t i = 0; i < size && k < sample_size; ++i) {
-      if (found[(size_t)i] >= n_vocab) return err.fail("internal: sampled index out of range");
-      const int64_t v = vocab[(size_t)found[(size_t)i]];
+      const int64_t v = vocab[(size_t)(*found)[(size_t)i]];
       if (!ex.count(v)) o[k++] = v;
     }
     out_len[b] = k;

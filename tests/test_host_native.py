@@ -192,3 +192,29 @@ def test_random_sampler_batch_sparse_ids_use_the_hash_path():
         for i, w in enumerate(withouts):
             np.random.seed(seed)
             assert got[i].tolist() == np.random.choice([v for v in vocab if v not in w], size=3, replace=False).tolist()
+
+
+def test_sampler_batch_per_request_seeds_take_the_general_path():
+    """Different seeds per request (what seed=None means: fresh entropy per call) cannot share a shuffle: every request does its
+    own full legacy permutation / weighted draw -- still the numpy streams, checked against numpy."""
+    rng = np.random.RandomState(5)
+    vocab = list(range(3, 900)); rng.shuffle(vocab)
+    src = (rng.zipf(1.3, size=4000) % 897 + 3).tolist() + vocab
+    p = [src.count(v) / len(src) for v in vocab]
+    withouts = [rng.randint(3, 900, size=rng.randint(0, 60)).tolist() for _ in range(12)]
+    seeds = rng.randint(0, 2**32 - 1, size=len(withouts)).astype(np.uint32)
+    got = hn.sample_random_batch(vocab, withouts, 50, False, seeds)
+    gp, lens = hn.sample_pop_random_batch(vocab, p, withouts, 50, False, seeds)
+    for i, w in enumerate(withouts):
+        np.random.seed(int(seeds[i]))
+        ex = set(w)
+        assert got[i].tolist() == np.random.choice([v for v in vocab if v not in ex], size=50, replace=False).tolist()
+        np.random.seed(int(seeds[i]))
+        drawn = np.random.choice(vocab, 50 + len(ex), False, p).tolist()
+        assert gp[i, :lens[i]].tolist() == [v for v in drawn if v not in ex][:50]
+    # a vocabulary with a repeated id is not eligible for the shared-shuffle path either
+    dup_vocab = vocab + [vocab[0]]
+    got = hn.sample_random_batch(dup_vocab, withouts, 20, False, 9)
+    for i, w in enumerate(withouts):
+        np.random.seed(9)
+        assert got[i].tolist() == np.random.choice([v for v in dup_vocab if v not in set(w)], size=20, replace=False).tolist()
