@@ -14,6 +14,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <string>
 #include <thread>
 #include <unordered_set>
@@ -116,9 +119,10 @@ inline uint64_t np_interval(MT19937& g, uint64_t max) {   // random_interval: un
 }
 
 template <class F>
-int run_parallel(int n, int n_threads, F&& body) {   // body(i) -> 0 or error; first error wins
+int run_parallel(int n, int n_threads, F&& body, int grain = 1) {   // body(i) -> 0 or error; first error wins
   if (n_threads < 1) n_threads = (int)std::thread::hardware_concurrency();
   if (n_threads < 1) n_threads = 1;
+  if (grain > 1 && n_threads > (n + grain - 1) / grain) n_threads = (n + grain - 1) / grain;   // cheap items: a thread per `grain` of them
   if (n_threads > n) n_threads = n > 0 ? n : 1;
   std::atomic<int> next(0), err(0);
   auto worker = [&]() {
@@ -311,6 +315,7 @@ extern "C" int b4r_host_sample_random_batch(const int64_t* vocab, int64_t n_voca
       const int64_t tot_wo = without ? without_off[n] - without_off[0] : 0;
       std::vector<int32_t> ex_pos((size_t)tot_wo);   // per request: sorted unique excluded vocab positions, at without_off[b] - without_off[0]
       std::vector<int32_t> ex_cnt((size_t)n, 0);
+      const int kGrain = 128;   // requests per thread for the cheap per-request phases (a std::thread start costs ~20-50 us)
       int rc = run_parallel(n, n_threads, [&](int b) -> int {
         int32_t* e = ex_pos.data() + (without ? without_off[b] - without_off[0] : 0);
         int m = 0;
@@ -322,41 +327,63 @@ extern "C" int b4r_host_sample_random_batch(const int64_t* vocab, int64_t n_voca
         std::sort(e, e + m);
         m = (int)(std::unique(e, e + m) - e);
         ex_cnt[(size_t)b] = m;
+        for (int q = 0; q < m; ++q) e[q] -= q;   // thresholds thr[q] = e[q] - q (see the mapping below)
         if (sample_size > n_vocab - m) return err.fail("Cannot take a larger sample than population when 'replace=False'");
         return 0;
-      });
+      }, kGrain);
       if (rc) return err.finish(rc);
-      // distinct pool sizes -> shuffled prefixes
+        // distinct pool sizes -> shuffled prefixes
       std::vector<int64_t> sizes;
       for (int b = 0; b < n; ++b) sizes.push_back(n_vocab - ex_cnt[(size_t)b]);
       std::sort(sizes.begin(), sizes.end());
       sizes.erase(std::unique(sizes.begin(), sizes.end()), sizes.end());
+      // process-wide cache of the shuffled prefixes, keyed by (seed, pool size, sample size): an evaluation loop calls this once
+      // per batch with the same sampler, so after the first batches no shuffle is left to do
+      static std::mutex cache_mu;
+      static std::map<std::tuple<uint32_t, int64_t, int>, std::vector<int64_t>> cache;
       std::vector<std::vector<int64_t>> prefix(sizes.size());
-      rc = run_parallel((int)sizes.size(), n_threads, [&](int si) -> int {
+      std::vector<int> todo;
+      {
+        std::lock_guard<std::mutex> lk(cache_mu);
+        for (size_t si = 0; si < sizes.size(); ++si) {
+          auto it = cache.find(std::make_tuple(seeds[0], sizes[si], sample_size));
+          if (it != cache.end()) prefix[si] = it->second; else todo.push_back((int)si);
+        }
+      }
+        rc = run_parallel((int)todo.size(), n_threads, [&](int ti) -> int {
         thread_local std::vector<int64_t> ident, perm;
-        const int64_t m = sizes[(size_t)si];
+        const size_t si = (size_t)todo[(size_t)ti];
+        const int64_t m = sizes[si];
         ident.resize((size_t)m);
         for (int64_t i = 0; i < m; ++i) ident[(size_t)i] = i;
         MT19937 g;
         g.init_genrand(seeds[0]);
-        prefix[(size_t)si].resize((size_t)sample_size);
-        return np_choice_uniform(err, g, ident, sample_size, false, prefix[(size_t)si].data(), perm);
+        prefix[si].resize((size_t)sample_size);
+        return np_choice_uniform(err, g, ident, sample_size, false, prefix[si].data(), perm);
       });
       if (rc) return err.finish(rc);
-      rc = run_parallel(n, n_threads, [&](int b) -> int {
+      if (!todo.empty()) {
+        std::lock_guard<std::mutex> lk(cache_mu);
+        if (cache.size() > 8192) cache.clear();
+        for (int si : todo) cache[std::make_tuple(seeds[0], sizes[(size_t)si], sample_size)] = prefix[(size_t)si];
+      }
+        rc = run_parallel(n, n_threads, [&](int b) -> int {
         const int m = ex_cnt[(size_t)b];
         const int32_t* e = ex_pos.data() + (without ? without_off[b] - without_off[0] : 0);
         const size_t si = (size_t)(std::lower_bound(sizes.begin(), sizes.end(), n_vocab - m) - sizes.begin());
         const int64_t* pf = prefix[si].data();
         int64_t* o = out + (size_t)b * sample_size;
         for (int k = 0; k < sample_size; ++k) {
-          int64_t pos = pf[k];   // index into the pool -> position in the vocab: skip the excluded positions at or below it
-          for (int q = 0; q < m && e[q] <= pos; ++q) ++pos;
-          o[k] = vocab[(size_t)pos];
+          // index into the pool -> position in the vocab: the q-th excluded position e[q] precedes pool index i iff e[q] - q <= i
+          // (thr[q] = e[q] - q is non-decreasing), so position = i + #{q : thr[q] <= i}
+          const int64_t i = pf[k];
+          int cnt = 0;
+          for (int q = 0; q < m; ++q) cnt += e[q] <= (int32_t)i;   // branch-free (vectorised) count over <= a few dozen thresholds
+          o[k] = vocab[(size_t)(i + cnt)];
         }
         return 0;
-      });
-      return err.finish(rc);
+      }, kGrain);
+        return err.finish(rc);
     }
   }
   const int rc = run_parallel(n, n_threads, [&](int b) -> int {
