@@ -1142,6 +1142,14 @@ extern "C" int b4r_rank_full_ext(b4r_session* s, const void* t_rows, const int32
   return 0;
 }
 
+// n host->device copies enqueued back to back (pinned sources: true DMA, the host returns at once).  The step's five int64 inputs
+// go to their persistent device views with ~2 us of host time each instead of a packing pass over the batch on the host.
+extern "C" int b4r_h2d_copy_many(void* const* dst, const void* const* src, const size_t* nbytes, int n, void* stream) {
+  if (!dst || !src || !nbytes || n < 0) return fail("bad argument");
+  for (int i = 0; i < n; ++i) CK(cudaMemcpyAsync(dst[i], src[i], nbytes[i], cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
 extern "C" int b4r_metrics_from_hist(const uint64_t* hist, int max_rank, const int32_t* ks, int nk, double* out, void* stream) {
   if (!hist || !ks || !out || nk < 0 || nk > 16) return fail("bad argument");
   CK(launch_metrics_from_hist(reinterpret_cast<const unsigned long long*>(hist), max_rank, ks, nk, out, (cudaStream_t)stream));

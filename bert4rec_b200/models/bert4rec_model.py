@@ -102,6 +102,7 @@ class BERT4RecModel:
         self._want_sca = False
         self._stats = {}
         self._staging = {}
+        self._pinned_plans = {}
         self._seed = 0x5EEDB4A7
         self._host_step = 0
         self.stop_training = False
@@ -147,6 +148,23 @@ class BERT4RecModel:
                 off += n
             st = self._staging[key] = (host, dev, views)
         host, dev, views = st
+        if not all_cuda and all(v.dtype == torch.int64 and v.is_contiguous() and not v.is_cuda for v in vals):
+            # pinned host tensors: straight DMA of every tensor into its device view (no packing pass over the batch)
+            ptrs = tuple(v.data_ptr() for v in vals)
+            plan = self._pinned_plans.get((key, ptrs))
+            if plan is None and all(v.is_pinned() for v in vals):
+                import ctypes as C
+                n = len(vals)
+                plan = ((C.c_void_p * n)(*[views[k].data_ptr() for k in keys]), (C.c_void_p * n)(*ptrs),
+                        (C.c_size_t * n)(*[8 * s_ for s_ in sizes]), n, vals)   # (vals kept alive: the plan is keyed by their addresses)
+                if len(self._pinned_plans) > 64:
+                    self._pinned_plans.clear()
+                self._pinned_plans[(key, ptrs)] = plan
+            if plan is not None:
+                from bert4rec_b200 import _lib
+                _lib.check(self.store.lib.b4r_h2d_copy_many(plan[0], plan[1], plan[2], plan[3],
+                                                            torch.cuda.current_stream(self.device).cuda_stream))
+                return views
         if all_cuda:
             torch.cat([v.reshape(-1).to(torch.int64) for v in vals], out=dev)
         else:

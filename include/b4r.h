@@ -138,6 +138,10 @@ const float* b4r_shard_step_stats(b4r_shard* s);   /* float[8], layout of b4r_st
 const float* b4r_shard_lse(b4r_shard* s);          /* fp32 [n_ranks*rows_per_rank] packed row order */
 const int32_t* b4r_shard_counts(b4r_shard* s);     /* int32[2] = {n_valid, n_rows} over all ranks */
 
+/* n host->device copies enqueued back to back on `stream` (dst[i] device, src[i] host -- pinned for a true asynchronous DMA).
+ * Host inputs of a step (the reference feeds host tensors through tf.data, dataloader_utils.py:306-346) reach the persistent
+ * device buffers of the captured step without a packing pass on the host. */
+int b4r_h2d_copy_many(void* const* dst, const void* const* src, const size_t* nbytes, int n, void* stream);
 /* HR@k / NDCG@k / MAP from a rank histogram (evaluation_metrics.py:47-112): out fp64 [2 + 2*nk] =
  * {n, NDCG@k..., HR@k..., MAP}; ks: device int32 [nk]. */
 int b4r_metrics_from_hist(const uint64_t* hist, int max_rank, const int32_t* ks, int nk, double* out, void* stream);

@@ -497,3 +497,27 @@ def test_full_catalogue_ranks_api_and_shard_additivity():
         sess.rank_full_ext(t, lab, score.view(-1).contiguous(), cnt, lo, hi, parts)
     assert torch.equal(whole, parts)
     assert torch.equal(whole.cpu() + 1, ranks.to(torch.int32))
+
+
+def test_train_step_input_paths_agree():
+    """The same batches fed as pageable host tensors (packed staging copy), pinned host tensors (direct DMA into the step's
+    device views, b4r_h2d_copy_many) and device-resident tensors (consumed in place) give identical training trajectories."""
+    from bert4rec_b200 import trainers
+    from bert4rec_b200.models import BERT4RecModel
+    from bert4rec_b200.models.components import networks
+    kw = dict(vocab_size=703, hidden_size=64, num_layers=2, num_attention_heads=2, max_sequence_length=30,
+              inner_dim=64, output_dropout=0.1, attention_dropout=0.1)
+    base = [make_batch(16, 30, 6, 703, seed=s) for s in range(3)]
+    feeds = {"pageable": base, "pinned": [{k: v.pin_memory() for k, v in b.items()} for b in base],
+             "device": [to_cuda(b) for b in base]}
+    out = {}
+    for name, batches in feeds.items():
+        model = BERT4RecModel(networks.Bert4RecEncoder(**kw, device="cuda:0", seed=4))
+        trainers.get("bert4rec", model=model).initialize_model(
+            optimizer=trainers.optimizers.get("adamw", init_lr=5e-3, num_warmup_steps=2, num_train_steps=1000))
+        losses = []
+        for i in range(9):
+            model.reset_metrics("train")
+            losses.append(model.train_step(batches[i % 3])["loss"])
+        out[name] = losses
+    assert out["pageable"] == out["pinned"] == out["device"]
