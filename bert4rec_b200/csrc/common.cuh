@@ -1,5 +1,7 @@
 // Shared device helpers for the bert4rec_b200 kernels (sm_100a only).
 #pragma once
+#include <cstdlib>
+#include <utility>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -145,6 +147,32 @@ __device__ __forceinline__ void load_b_frag(uint32_t (&b)[4], const bf16* s, int
     const bf16* p = s + (size_t)(k0 + ((j & 1) << 3) + r) * ld + n0 + ((j >> 1) << 3);
     ldsm_x4_t(b, smem_u32(p));
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): a kernel launched through launch_pdl() may be SCHEDULED while its predecessor in
+// the stream is still running -- its grid launch, CTA placement and parameter fetch overlap the predecessor's tail -- and
+// blocks at pdl_grid_sync() until the predecessor has completed and flushed its memory.  Every kernel on the step's path
+// starts with pdl_grid_sync() (wait for the predecessor, then allow the successor to be scheduled), so the dependency
+// chain is unchanged; only the ~2-3 us of launch latency between dependent kernels of the captured step is hidden.
+// Without the launch attribute both instructions are no-ops.  B4R_DISABLE_PDL=1 launches without the attribute.
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+inline bool pdl_enabled() {
+  static const bool on = getenv("B4R_DISABLE_PDL") == nullptr;
+  return on;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 
 // C-fragment coordinates: element e of acc[4] -> (row, col) inside a 16x8 tile.

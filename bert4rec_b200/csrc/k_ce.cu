@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(1024) mlm_select_kernel(const int64_t* __restr
                                                           int P, int want_aux, int* __restrict__ rows, int* __restrict__ labels,
                                                           float* __restrict__ row_w, int* __restrict__ row_mult,
                                                           int* __restrict__ counts) {
+  pdl_grid_sync();
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -109,7 +110,8 @@ __global__ void __launch_bounds__(1024) mlm_select_kernel(const int64_t* __restr
 cudaError_t launch_mlm_select(const int64_t* positions, const int64_t* ids, const int64_t* weights, int use_weights,
                               int B, int S, int P, int want_aux, int* rows, int* labels, float* row_w, int* row_mult,
                               int* counts, cudaStream_t st) {
-  mlm_select_kernel<<<1, 1024, 0, st>>>(positions, ids, weights, use_weights, B, S, P, want_aux, rows, labels, row_w, row_mult, counts);
+  launch_pdl(mlm_select_kernel, dim3(1), dim3(1024), (size_t)0, st, positions, ids, weights, use_weights, B, S, P, want_aux, rows, labels, row_w,
+             row_mult, counts);
   return cudaGetLastError();
 }
 
@@ -282,6 +284,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(CeDev a) {
 // Multi-CTA: merge the vsplits partials per row, emit lse; per-CTA partial statistics; the LAST CTA to finish (atomic
 // ticket) sums them in CTA-index order (deterministic) and accumulates the step / running statistics.
 __global__ void __launch_bounds__(256) ce_finalize_kernel(CeDev a, float* __restrict__ fin_part, int* __restrict__ ticket) {
+  pdl_grid_sync();
   __shared__ float s_red[8][5];
   __shared__ int s_last;
   const int n_rows = min(a.M_cap, a.d_counts[1]);
@@ -588,7 +591,7 @@ cudaError_t launch_ce_count(const CeArgs& a, const float* s_gt, int* beat, cudaS
 cudaError_t launch_ce_finalize(const CeArgs& a, cudaStream_t st) {
   int blocks = (a.M_cap + 31) / 32;
   if (blocks > 64) blocks = 64;
-  ce_finalize_kernel<<<blocks, 256, 0, st>>>(to_dev(a), a.fin_part, a.ticket);
+  launch_pdl(ce_finalize_kernel, dim3(blocks), dim3(256), (size_t)0, st, to_dev(a), a.fin_part, a.ticket);
   return cudaGetLastError();
 }
 

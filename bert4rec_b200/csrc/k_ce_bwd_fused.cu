@@ -122,6 +122,7 @@ struct Dev {
 
 __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmE,
                                                                Dev a) {
+  pdl_grid_sync();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* sBias = reinterpret_cast<float*>(smem + OFF_VEC);
@@ -416,6 +417,7 @@ __global__ void __launch_bounds__(NTHR, 1) ce_bwd_fused_kernel(const __grid_cons
 __global__ void __launch_bounds__(256) ce_bwd_fused_reduce_kernel(const float* __restrict__ dE_part, const float* __restrict__ db_part,
                                                                   const int* __restrict__ d_counts, int M_cap, int V,
                                                                   float* __restrict__ g_table, float* __restrict__ g_bias) {
+  pdl_grid_sync();
   const int nch = cf_split(min(M_cap, d_counts[0]), V, 1).nch;
   const long long n4 = (long long)V * FH / 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -450,14 +452,13 @@ cudaError_t launch_ce_bwd_fused(const CeUmmaMaps& maps, const CeBwdFusedArgs& a,
   d.dt_part = a.dt_part; d.dE_part = a.dE_part; d.db_part = a.db_part; d.dbg = a.dbg;
   const CUtensorMap& tmT = *reinterpret_cast<const CUtensorMap*>(maps.a);
   const CUtensorMap& tmE = *reinterpret_cast<const CUtensorMap*>(maps.b);
-  ce_bwd_fused_kernel<<<a.ctas > 0 ? a.ctas : 148, NTHR, SMEM, st>>>(tmT, tmE, d);
-  return cudaGetLastError();
+  return launch_pdl(ce_bwd_fused_kernel, dim3(a.ctas > 0 ? a.ctas : 148), dim3(NTHR), (size_t)SMEM, st, tmT, tmE, d);
 }
 
 cudaError_t launch_ce_bwd_fused_reduce(const CeBwdFusedArgs& a, float* g_table, float* g_bias, cudaStream_t st) {
   const long long n4 = (long long)a.V * FH / 4;
-  ce_bwd_fused_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(a.dE_part, a.db_part, a.d_counts, a.M_cap, a.V, g_table, g_bias);
-  return cudaGetLastError();
+  return launch_pdl(ce_bwd_fused_reduce_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), (size_t)0, st, a.dE_part, a.db_part, a.d_counts,
+                    a.M_cap, a.V, g_table, g_bias);
 }
 
 }  // namespace b4r

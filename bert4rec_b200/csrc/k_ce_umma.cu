@@ -52,6 +52,7 @@ __host__ __device__ inline int ce_umma_dyn_splits(int n_rows, int ntiles, int ta
 template <int H>
 __global__ void __launch_bounds__(320, 2) ce_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, CeUmmaDev a) {
+  pdl_grid_sync();
   using Cfg = CeUmmaCfg<H>;
   constexpr int KB = Cfg::KB, STAGES = Cfg::STAGES;
   extern __shared__ unsigned char smem_raw[];
@@ -278,7 +279,7 @@ cudaError_t launch_ce_fwd_umma(const CeUmmaMaps& maps, const CeArgs& a, cudaStre
       cudaFuncSetAttribute(ce_fwd_umma_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, CeUmmaCfg<HH>::SMEM); \
       done_##HH = true;                                                                                             \
     }                                                                                                               \
-    ce_fwd_umma_kernel<HH><<<grid, 320, CeUmmaCfg<HH>::SMEM, st>>>(tmA, tmB, d);                                    \
+    launch_pdl(ce_fwd_umma_kernel<HH>, grid, dim3(320), (size_t)CeUmmaCfg<HH>::SMEM, st, tmA, tmB, d);              \
     break;                                                                                                          \
   }
   switch (a.H) {

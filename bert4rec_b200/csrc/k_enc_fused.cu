@@ -40,6 +40,7 @@ struct EncFusedDev {
 };
 
 __global__ void __launch_bounds__(NTHR, 1) enc_fwd_fused_kernel(EncFusedDev a) {
+  pdl_grid_sync();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sX = smem + OFF_X;
@@ -537,8 +538,7 @@ cudaError_t launch_enc_fwd_fused(const EncFusedArgs& a, cudaStream_t st) {
   }
   const int G = FT / d.slot;
   const int grid = (a.B + G - 1) / G;
-  enc_fwd_fused_kernel<<<grid, NTHR, smem, st>>>(d);
-  return cudaGetLastError();
+  return launch_pdl(enc_fwd_fused_kernel, dim3(grid), dim3(NTHR), smem, st, d);
 }
 
 }  // namespace b4r

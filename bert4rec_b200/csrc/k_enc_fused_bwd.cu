@@ -101,6 +101,7 @@ struct EncBwdDev {
 };
 
 __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
+  pdl_grid_sync();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   auto tile = [&](int i) -> unsigned char* { return smem + i * TILE_B; };
@@ -780,8 +781,7 @@ cudaError_t launch_enc_bwd_fused(const EncBwdArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     cap = smem;
   }
-  enc_bwd_fused_kernel<<<enc_fused_ctas(a.B, a.S), NTHR, smem, st>>>(d);
-  return cudaGetLastError();
+  return launch_pdl(enc_bwd_fused_kernel, dim3(enc_fused_ctas(a.B, a.S)), dim3(NTHR), smem, st, d);
 }
 
 }  // namespace b4r

@@ -194,6 +194,7 @@ struct RowLnDev {
 
 template <int H, int MODE>
 __global__ void __launch_bounds__(256) gemm_rowln_kernel(GemmOperands op, RowLnDev ep, const int* d_M) {
+  pdl_grid_sync();
   typedef typename RowTile<H>::T T;
   constexpr int LDS = RowTile<H>::LDS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -317,7 +318,7 @@ static cudaError_t launch_rowln_t(const RowLnArgs& a, cudaStream_t st) {
     cudaFuncSetAttribute(gemm_rowln_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  gemm_rowln_kernel<H, MODE><<<(a.M + T::BM - 1) / T::BM, 256, smem, st>>>(op, ep, a.d_M);
+  launch_pdl(gemm_rowln_kernel<H, MODE>, dim3((a.M + T::BM - 1) / T::BM), dim3(256), (size_t)smem, st, op, ep, a.d_M);
   return cudaGetLastError();
 }
 

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(256) head_bwd_fused_kernel(const float* __rest
                                                              const int* __restrict__ d_counts, int M_cap, float* __restrict__ dx_out,
                                                              float* __restrict__ p_ln, float* __restrict__ p_wt, int dyn_vtiles,
                                                              int dyn_target, int dyn_max) {
+  pdl_grid_sync();
   __shared__ float sW[HF_H][HF_H + 1];      // Wt[in][out] as fp32
   extern __shared__ float sAccW[];          // [8 warps][out][HF_LD]: every warp's dWt accumulator, TRANSPOSED ([out][in]); then
                                             // [8][3][HF_H]: its LayerNorm / bias sums -- summed over the warps in fixed order
@@ -130,9 +131,8 @@ cudaError_t launch_head_bwd_fused(const float* dt_part, int nsplit, size_t split
     cudaFuncSetAttribute(head_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HF_SMEM);
     done = true;
   }
-  head_bwd_fused_kernel<<<head_bwd_fused_ctas(), 256, HF_SMEM, st>>>(dt_part, nsplit, split_stride, t_pre, t_act, mean, rstd, gamma, wt, x, rows,
-                                                              d_counts, M_cap, dx_out, p_ln, p_wt, dyn_vtiles, dyn_target, dyn_max);
-  return cudaGetLastError();
+  return launch_pdl(head_bwd_fused_kernel, dim3(head_bwd_fused_ctas()), dim3(256), (size_t)HF_SMEM, st, dt_part, nsplit, split_stride, t_pre, t_act,
+                    mean, rstd, gamma, wt, x, rows, d_counts, M_cap, dx_out, p_ln, p_wt, dyn_vtiles, dyn_target, dyn_max);
 }
 
 }  // namespace b4r

@@ -157,6 +157,7 @@ cudaError_t launch_head_bwd_rows(const float* dt_part, int nsplit, size_t split_
 // One launch reduces every parameter-gradient partial buffer of the step (fixed summation order -> deterministic).
 // block = 32 columns x 8 part-lanes; grid = (ceil(max_len/32), njobs).
 __global__ void __launch_bounds__(256) grad_reduce_kernel(const ReduceJob* __restrict__ jobs) {
+  pdl_grid_sync();
   __shared__ float s[8][33];
   const ReduceJob job = jobs[blockIdx.y];
   if (job.nparts <= 8) {
@@ -208,8 +209,7 @@ int grad_reduce_blocks(int nparts, int len) { return nparts <= 8 ? (len + 1023) 
 cudaError_t launch_grad_reduce(const ReduceJob* d_jobs, int njobs, int max_blocks, cudaStream_t st) {
   if (njobs <= 0) return cudaSuccess;
   dim3 grid(max_blocks, njobs);
-  grad_reduce_kernel<<<grid, 256, 0, st>>>(d_jobs);
-  return cudaGetLastError();
+  return launch_pdl(grad_reduce_kernel, grid, dim3(256), (size_t)0, st, d_jobs);
 }
 
 // ------------------------------------------------------------------------------------------------ column sums
@@ -293,6 +293,7 @@ struct AdamWDev {
 // advances optimizer.iterations and evaluates the step coefficients ONCE (global-norm clip scale, warm-up / decayed
 // learning rate, Adam bias correction in double precision) -- not per block of the update kernel.
 __global__ void __launch_bounds__(256) sqnorm_kernel(AdamWDev a, int with_coef) {
+  pdl_grid_sync();
   __shared__ float s[8];
   __shared__ int s_last;
   float acc = 0.f;
@@ -358,6 +359,7 @@ cudaError_t launch_sqnorm(const float* g, long long n, float* out_part, int nblo
 }
 
 __global__ void __launch_bounds__(256) adamw_kernel(AdamWDev a) {
+  pdl_grid_sync();
   const float* coef = a.sq_part + a.n_sq_part;
   const float gs = coef[0], lr = coef[1], alpha = coef[2];
   const float ob1 = 1.0f - a.beta1, ob2 = 1.0f - a.beta2;
@@ -394,13 +396,12 @@ cudaError_t launch_adamw(const AdamWArgs& a, cudaStream_t st) {
   d.num_train_steps = (float)a.num_train_steps; d.num_warmup_steps = (float)a.num_warmup_steps;
   d.wd = a.wd; d.beta1 = a.beta1; d.beta2 = a.beta2; d.eps = a.eps; d.clip = a.clip; d.d_lr_out = a.d_lr_out;
   // stage 1: squared-norm partials + (last block) step counter and coefficients ; stage 2: update
-  sqnorm_kernel<<<a.n_sq_part, 256, 0, st>>>(d, 1);
+  launch_pdl(sqnorm_kernel, dim3(a.n_sq_part), dim3(256), (size_t)0, st, d, 1);
   long long n4 = a.n >> 2;
   int blocks = (int)((n4 + 1023) / 1024);   // 4 float4 per thread
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  adamw_kernel<<<blocks, 256, 0, st>>>(d);
-  return cudaGetLastError();
+  return launch_pdl(adamw_kernel, dim3(blocks), dim3(256), (size_t)0, st, d);
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
