@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(128) rank_candidates_kernel(const bf16* __rest
                                                               const int64_t* __restrict__ gt, int M, int C,
                                                               int64_t* __restrict__ ranking, float* __restrict__ scores,
                                                               int* __restrict__ rank, unsigned long long* __restrict__ hist) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x * 4 + warp;
@@ -81,7 +82,7 @@ cudaError_t launch_rank_candidates(const bf16* t, int ldt, const bf16* E, const 
 #define B4R_RK(HH)                                                                                            \
   case HH:                                                                                                    \
     { static size_t cap_##HH = 0; if (smem > cap_##HH) { cudaFuncSetAttribute(rank_candidates_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cap_##HH = smem; } } \
-    rank_candidates_kernel<HH><<<grid, 128, smem, st>>>(t, ldt, E, vbias, cand, gt, M, C, ranking, scores, rank, hist); \
+    launch_pdl(rank_candidates_kernel<HH>, dim3(grid), dim3(128), smem, st, t, ldt, E, vbias, cand, gt, M, C, ranking, scores, rank, hist); \
     break;
   switch (H) {
     B4R_RK(64)
