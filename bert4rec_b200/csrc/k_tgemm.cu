@@ -242,7 +242,9 @@ bool tgemm_supported(int epi, const GemmArgs& a) {
   if (getenv("B4R_DISABLE_TGEMM")) return false;
   if (!(epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU || epi == EPI_GELU_GRAD || epi == EPI_BF16 || epi == EPI_F32_RES)) return false;
   if (a.a_trans || a.a_rows || a.d_M || a.splits > 1) return false;
-  if (a.K % TG_BK || a.N % 64 || a.K < 128 || a.M < 256) return false;   // small / narrow problems stay on the portable kernel
+  // one 64-wide k-block is enough for the TMA ring (hidden-64 FFN1: 36 -> 30 us at C1); B4R_TGEMM_MINK raises the threshold
+  static const int min_k = getenv("B4R_TGEMM_MINK") ? atoi(getenv("B4R_TGEMM_MINK")) : 64;
+  if (a.K % TG_BK || a.N % 64 || a.K < min_k || a.M < 256) return false;   // small / narrow problems stay on the portable kernel
   if ((a.a_kmax && a.a_kmax != a.K) || (a.b_kmax && a.b_kmax != a.K)) return false;
   if (a.lda % 8 || a.ldb % 8 || ((uintptr_t)a.A & 15) || ((uintptr_t)a.B & 15)) return false;
   return true;
