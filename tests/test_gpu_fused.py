@@ -231,3 +231,34 @@ def test_one_pass_ce_backward_matches_two_pass(case):
         if not err <= 2e-3 * float(g.norm()) + 1e-6 * gmax:
             bad.append((k, err, float(g.norm())))
     assert not bad, f"one-pass vs two-pass CE backward (name, l2 err, ref norm): {bad}"
+
+
+def test_backward_with_no_valid_slot_is_finite_and_zero():
+    """A batch whose masked_lm_weights are all zero (no item to predict): no gradient anywhere, nothing NaN, and the one-pass CE
+    backward (zero work items, partial slots never written) agrees with the two-pass generation."""
+    from bert4rec_b200.engine import ParamStore
+    from tests.helpers import make_batch, to_cuda
+    V, B, S, P = 1203, 16, 50, 8
+    store = ParamStore(device="cuda:0", vocab_size=V, hidden_size=64, num_layers=2, num_attention_heads=2, max_sequence_length=S,
+                       inner_dim=64, output_dropout=0.0, attention_dropout=0.0)
+    store.init_weights(0)
+    store.ensure_training_buffers()
+    batch = make_batch(B, S, P, V, seed=3)
+    batch["masked_lm_weights"].zero_(); batch["masked_lm_ids"].zero_()
+    cb = to_cuda(batch)
+    sess = store.session(B, S, P)
+    for gen3 in (1, 0):
+        sess.set_flag(5, gen3)
+        store.grads.normal_()                       # stale garbage must be overwritten, not accumulated
+        sess.select(cb["masked_lm_positions"], cb["masked_lm_ids"], cb["masked_lm_weights"], mode=0, want_aux=True)
+        sess.encode(cb["input_word_ids"], cb["input_mask"], training=True)
+        sess.transform()
+        sess.loss()
+        sess.backward()
+        torch.cuda.synchronize()
+        st = sess.step_stats().cpu()
+        assert int(sess.counts()[0]) == 0 and float(st[0]) == 0.0 and float(st[1]) == 0.0
+        for k, g in store.tf_views(store.grads).items():      # (the flat buffer's padding between segments is never written)
+            if not k.startswith("pooler_transform"):
+                assert bool(torch.isfinite(g).all()) and float(g.abs().max()) == 0.0, (gen3, k)
+    sess.set_flag(5, 1)
