@@ -160,6 +160,9 @@ __device__ __forceinline__ void pdl_grid_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+// multi-wave kernels: wait only -- the successor is released when this grid's CTAs exit (an explicit early trigger lets the
+// successor's CTAs take SM slots from this grid's later waves: measured slower)
+__device__ __forceinline__ void pdl_grid_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 inline bool pdl_enabled() {
   static const bool on = getenv("B4R_DISABLE_PDL") == nullptr;
   return on;

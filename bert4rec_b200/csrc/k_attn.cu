@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
                                                        uint64_t* __restrict__ keep_bits, int S, int H, int N,
                                                        uint32_t thr16, float inv_keep, uint64_t seed, uint32_t site,
                                                        uint32_t step, const long long* __restrict__ d_step) {
+  pdl_grid_wait();
   if (d_step) step += (uint32_t)(*d_step);
   constexpr int LD = D + 8;
   constexpr int KD = D / 16;  // k-steps over the head dim
@@ -202,10 +203,10 @@ cudaError_t launch_attn_fwd(const AttnArgs& a, cudaStream_t st) {
   static size_t cap32 = 0, cap64 = 0;
   if (D == 32) {
     if (smem > cap32) { cudaFuncSetAttribute(attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cap32 = smem; }
-    attn_fwd_kernel<32><<<grid, 128, smem, st>>>(a.qkv, a.mask, a.ctx, a.lse, a.keep_bits, a.S, a.H, a.N, thr, inv_keep, a.seed, a.site, a.step, a.d_step);
+    launch_pdl(attn_fwd_kernel<32>, dim3(grid), dim3(128), (size_t)(smem), st, a.qkv, a.mask, a.ctx, a.lse, a.keep_bits, a.S, a.H, a.N, thr, inv_keep, a.seed, a.site, a.step, a.d_step);
   } else {
     if (smem > cap64) { cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cap64 = smem; }
-    attn_fwd_kernel<64><<<grid, 128, smem, st>>>(a.qkv, a.mask, a.ctx, a.lse, a.keep_bits, a.S, a.H, a.N, thr, inv_keep, a.seed, a.site, a.step, a.d_step);
+    launch_pdl(attn_fwd_kernel<64>, dim3(grid), dim3(128), (size_t)(smem), st, a.qkv, a.mask, a.ctx, a.lse, a.keep_bits, a.S, a.H, a.N, thr, inv_keep, a.seed, a.site, a.step, a.d_step);
   }
   return cudaGetLastError();
 }
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const bf16* __restrict__ 
                                                        const float* __restrict__ lse, const uint64_t* __restrict__ keep_bits,
                                                        bf16* __restrict__ dqkv, int S, int H, int N, uint32_t thr16,
                                                        float inv_keep) {
+  pdl_grid_wait();
   constexpr int LD = D + 8;
   constexpr int KD = D / 16, ND = D / 8;
   constexpr int LDS = 72;  // dS^T tile row stride (64 queries + 8)
@@ -453,10 +455,10 @@ cudaError_t launch_attn_bwd(const AttnArgs& a, cudaStream_t st) {
   static size_t cap32 = 0, cap64 = 0;
   if (D == 32) {
     if (smem > cap32) { cudaFuncSetAttribute(attn_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cap32 = smem; }
-    attn_bwd_kernel<32><<<a.B * a.N, 128, smem, st>>>(a.qkv, a.mask, a.ctx, a.dctx, a.lse, a.keep_bits, a.dqkv, a.S, a.H, a.N, thr, inv_keep);
+    launch_pdl(attn_bwd_kernel<32>, dim3(a.B * a.N), dim3(128), (size_t)(smem), st, a.qkv, a.mask, a.ctx, a.dctx, a.lse, a.keep_bits, a.dqkv, a.S, a.H, a.N, thr, inv_keep);
   } else {
     if (smem > cap64) { cudaFuncSetAttribute(attn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cap64 = smem; }
-    attn_bwd_kernel<64><<<a.B * a.N, 128, smem, st>>>(a.qkv, a.mask, a.ctx, a.dctx, a.lse, a.keep_bits, a.dqkv, a.S, a.H, a.N, thr, inv_keep);
+    launch_pdl(attn_bwd_kernel<64>, dim3(a.B * a.N), dim3(128), (size_t)(smem), st, a.qkv, a.mask, a.ctx, a.dctx, a.lse, a.keep_bits, a.dqkv, a.S, a.H, a.N, thr, inv_keep);
   }
   return cudaGetLastError();
 }

@@ -165,6 +165,7 @@ __device__ __forceinline__ void ce_tile_mma(const bf16* sA, const bf16* sB, int 
 // grid = (vsplits, ceil(M_cap/64)); 256 threads = 4 (M) x 2 (N) warps, warp tile 16 x 64.
 template <int H>
 __global__ void __launch_bounds__(256) ce_fwd_kernel(CeDev a) {
+  pdl_grid_wait();
   constexpr int LD = H + 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* sA = reinterpret_cast<bf16*>(smem_raw);
@@ -383,6 +384,7 @@ __global__ void __launch_bounds__(256) ce_finalize_kernel(CeDev a, float* __rest
 // optimizer's gradient scale).  grid = (ceil(Vshard/128), ceil(row_count/64)).
 template <int H>
 __global__ void __launch_bounds__(256) ce_dlogits_kernel(CeDev a) {
+  pdl_grid_wait();
   constexpr int LD = H + 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* sA = reinterpret_cast<bf16*>(smem_raw);
@@ -458,6 +460,7 @@ __global__ void __launch_bounds__(256) ce_dlogits_kernel(CeDev a) {
 // s_gt comes from the label-logit of ce_fwd (same MMA order -> identical bits for the gt column itself).
 template <int H>
 __global__ void __launch_bounds__(256) ce_count_kernel(CeDev a, const float* __restrict__ s_gt, int* __restrict__ beat) {
+  pdl_grid_wait();
   constexpr int LD = H + 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* sA = reinterpret_cast<bf16*>(smem_raw);
@@ -554,7 +557,7 @@ cudaError_t launch_ce_fwd(const CeArgs& a, cudaStream_t st) {
     size_t smem = ce_fwd_smem<HH>();                                                                       \
     static bool done_##HH = false;                                                                         \
     if (!done_##HH) { cudaFuncSetAttribute(ce_fwd_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done_##HH = true; }        \
-    ce_fwd_kernel<HH><<<grid, 256, smem, st>>>(d);                                                         \
+    launch_pdl(ce_fwd_kernel<HH>, dim3(grid), dim3(256), (size_t)(smem), st, d);                                                         \
     break;                                                                                                 \
   }
   switch (a.H) {
@@ -575,7 +578,7 @@ cudaError_t launch_ce_count(const CeArgs& a, const float* s_gt, int* beat, cudaS
     size_t smem = ce_fwd_smem<HH>();                                                                       \
     static bool done_##HH = false;                                                                         \
     if (!done_##HH) { cudaFuncSetAttribute(ce_count_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done_##HH = true; }      \
-    ce_count_kernel<HH><<<grid, 256, smem, st>>>(d, s_gt, beat);                                           \
+    launch_pdl(ce_count_kernel<HH>, dim3(grid), dim3(256), (size_t)(smem), st, d, s_gt, beat);                                           \
     break;                                                                                                 \
   }
   switch (a.H) {
@@ -603,7 +606,7 @@ cudaError_t launch_ce_dlogits(const CeArgs& a, cudaStream_t st) {
     size_t smem = ce_dl_smem<HH>();                                                                        \
     static bool done_##HH = false;                                                                         \
     if (!done_##HH) { cudaFuncSetAttribute(ce_dlogits_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); done_##HH = true; }    \
-    ce_dlogits_kernel<HH><<<grid, 256, smem, st>>>(d);                                                     \
+    launch_pdl(ce_dlogits_kernel<HH>, dim3(grid), dim3(256), (size_t)(smem), st, d);                                                     \
     break;                                                                                                 \
   }
   switch (a.H) {

@@ -80,6 +80,7 @@ __host__ __device__ inline int ce_bwd_dyn_splits(int n_rows, int ntiles, int tar
 template <int H, bool ROW_IS_M>
 __global__ void __launch_bounds__(320, CeBwdCfg<H>::CTAS_PER_SM) ce_bwd_umma_kernel(const __grid_constant__ CUtensorMap tmT,
                                                              const __grid_constant__ CUtensorMap tmE, CeBwdDev a) {
+  pdl_grid_wait();
   using Cfg = CeBwdCfg<H>;
   constexpr int KB = Cfg::KB, XS = Cfg::XSTAGES, XT = Cfg::XT;
   extern __shared__ unsigned char smem_raw[];
@@ -352,7 +353,7 @@ static cudaError_t launch_ce_bwd_t(const CUtensorMap& tmT, const CUtensorMap& tm
     cudaFuncSetAttribute(ce_bwd_umma_kernel<H, ROW_IS_M>, cudaFuncAttributeMaxDynamicSharedMemorySize, CeBwdCfg<H>::SMEM);
     done = true;
   }
-  ce_bwd_umma_kernel<H, ROW_IS_M><<<grid, 320, CeBwdCfg<H>::SMEM, st>>>(tmT, tmE, d);
+  launch_pdl(ce_bwd_umma_kernel<H, ROW_IS_M>, dim3(grid), dim3(320), (size_t)(CeBwdCfg<H>::SMEM), st, tmT, tmE, d);
   return cudaGetLastError();
 }
 

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restric
                                                         float* __restrict__ dpos_part, float* __restrict__ dln_part, int B,
                                                         int S, int V, uint32_t thr16, float inv_keep, uint64_t seed,
                                                         uint32_t step, const long long* __restrict__ d_step) {
+  pdl_grid_wait();
   if (d_step) step += (uint32_t)(*d_step);
   constexpr int LPR = H / 8, RPW = 32 / LPR, RPC = 8 * RPW;  // rows per CTA pass
   __shared__ float s_red[3][RPC][H + 1];
@@ -226,9 +227,9 @@ cudaError_t launch_embed_bwd(const int64_t* ids, const bf16* table, const bf16* 
   float inv_keep = 1.0f / (1.0f - (float)thr / 65536.0f);
   dim3 grid(S, bsplits);
   switch (H) {
-    case 64: embed_bwd_kernel<64><<<grid, 256, 0, st>>>(ids, table, pos, gamma, d_out, grad_table, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
-    case 128: embed_bwd_kernel<128><<<grid, 256, 0, st>>>(ids, table, pos, gamma, d_out, grad_table, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
-    case 256: embed_bwd_kernel<256><<<grid, 256, 0, st>>>(ids, table, pos, gamma, d_out, grad_table, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
+    case 64: launch_pdl(embed_bwd_kernel<64>, dim3(grid), dim3(256), (size_t)(0), st, ids, table, pos, gamma, d_out, grad_table, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
+    case 128: launch_pdl(embed_bwd_kernel<128>, dim3(grid), dim3(256), (size_t)(0), st, ids, table, pos, gamma, d_out, grad_table, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
+    case 256: launch_pdl(embed_bwd_kernel<256>, dim3(grid), dim3(256), (size_t)(0), st, ids, table, pos, gamma, d_out, grad_table, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

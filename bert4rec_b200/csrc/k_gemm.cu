@@ -6,6 +6,7 @@
 // tfm.nlp.layers.TransformerEncoderBlock (bert4rec_encoder.py:136-147) and tfm MaskedLM dense+LN
 // (bert4rec_model.py:76-81); see SURVEY.md 2b rows K3-K5, K7.
 #include "gemm.cuh"
+#include "common.cuh"
 #include "kernels.h"
 
 namespace b4r {
@@ -31,6 +32,7 @@ struct EpiDev {
 
 template <class T, int EPI>
 __global__ void __launch_bounds__(T::THREADS) gemm_kernel(GemmOperands op, EpiDev ep, const int* d_M, int d_M_off, int k_per_split) {
+  pdl_grid_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* smem = reinterpret_cast<bf16*>(smem_raw);
   int M = ep.M;
@@ -151,7 +153,7 @@ static cudaError_t launch_gemm_t(const GemmArgs& a, cudaStream_t st) {
     cudaFuncSetAttribute(gemm_kernel<T, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  gemm_kernel<T, EPI><<<grid, T::THREADS, smem, st>>>(op, ep, a.d_M, a.d_M_off, kps);
+  launch_pdl(gemm_kernel<T, EPI>, dim3(grid), dim3(T::THREADS), (size_t)(smem), st, op, ep, a.d_M, a.d_M_off, kps);
   return cudaGetLastError();
 }
 
@@ -342,6 +344,7 @@ typedef GemmTile<64, 64, 32, 2, 2, true, true, 4> TileWG;  // A = X^T ([t][m]), 
 __global__ void __launch_bounds__(TileWG::THREADS) wgrad_kernel(GemmOperands op, float* out, size_t split_stride,
                                                                 int ld_out, int M, int N, int accumulate,
                                                                 const int* d_T, int d_T_off, int t_per_split) {
+  pdl_grid_wait();
   typedef TileWG T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* smem = reinterpret_cast<bf16*>(smem_raw);
@@ -392,7 +395,7 @@ cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t st) {
     cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  wgrad_kernel<<<grid, T::THREADS, smem, st>>>(op, a.out, a.split_stride, a.ld_out, a.M, a.N, a.accumulate, a.d_T, a.d_T_off, tps);
+  launch_pdl(wgrad_kernel, dim3(grid), dim3(T::THREADS), (size_t)(smem), st, op, a.out, a.split_stride, a.ld_out, a.M, a.N, a.accumulate, a.d_T, a.d_T_off, tps);
   return cudaGetLastError();
 }
 

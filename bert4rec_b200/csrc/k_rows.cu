@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      const bf16* __restrict__ t_pre, const int* __restrict__ d_M,
                                                      const long long* __restrict__ d_step, int dyn_vtiles = 0,
                                                      int dyn_target = 0, int dyn_max = 0) {
+  pdl_grid_wait();
   if (d_M) M = min(M, *d_M);
   if (HEAD && dyn_max > 0) {  // split count chosen on the device by the generation-2 dT pass (same formula)
     int mt = (M + 127) / 128; if (mt < 1) mt = 1;
@@ -130,9 +131,9 @@ cudaError_t launch_ln_bwd(const float* d_out, const bf16* pre, const float* mean
   float inv_keep = 1.0f / (1.0f - (float)thr / 65536.0f);
   int grid = ln_bwd_parts(M);
   switch (H) {
-    case 64: ln_bwd_kernel<64, false><<<grid, 256, 0, st>>>(d_out, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr, d_step); break;
-    case 128: ln_bwd_kernel<128, false><<<grid, 256, 0, st>>>(d_out, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr, d_step); break;
-    case 256: ln_bwd_kernel<256, false><<<grid, 256, 0, st>>>(d_out, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr, d_step); break;
+    case 64: launch_pdl(ln_bwd_kernel<64, false>, dim3(grid), dim3(256), (size_t)(0), st, d_out, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr, d_step, 0, 0, 0); break;
+    case 128: launch_pdl(ln_bwd_kernel<128, false>, dim3(grid), dim3(256), (size_t)(0), st, d_out, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr, d_step, 0, 0, 0); break;
+    case 256: launch_pdl(ln_bwd_kernel<256, false>, dim3(grid), dim3(256), (size_t)(0), st, d_out, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr, d_step, 0, 0, 0); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -145,9 +146,9 @@ cudaError_t launch_head_bwd_rows(const float* dt_part, int nsplit, size_t split_
   int grid = ln_bwd_parts(M_cap);
   const int* d_M = d_counts;   // n_valid: aux rows carry no gradient
   switch (H) {
-    case 64: ln_bwd_kernel<64, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
-    case 128: ln_bwd_kernel<128, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
-    case 256: ln_bwd_kernel<256, true><<<grid, 256, 0, st>>>(dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
+    case 64: launch_pdl(ln_bwd_kernel<64, true>, dim3(grid), dim3(256), (size_t)(0), st, dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
+    case 128: launch_pdl(ln_bwd_kernel<128, true>, dim3(grid), dim3(256), (size_t)(0), st, dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
+    case 256: launch_pdl(ln_bwd_kernel<256, true>, dim3(grid), dim3(256), (size_t)(0), st, dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -216,6 +217,7 @@ cudaError_t launch_grad_reduce(const ReduceJob* d_jobs, int njobs, int max_block
 // partials[z][n] = sum over rows r = z*8+ty, step 8*gridDim.y of src[r][n]
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ src, int ld, int M, int N,
                                                           const int* __restrict__ d_M, int d_M_off, float* __restrict__ part) {
+  pdl_grid_wait();
   __shared__ float s[8][65];
   if (d_M) M = min(M, *d_M - d_M_off);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
 // N <= 2048, N % 8 == 0: one thread per 8 consecutive columns (16-byte loads), RL row lanes per block
 __global__ void __launch_bounds__(256) colsum8_bf16_kernel(const bf16* __restrict__ src, int ld, int M, int N,
                                                            const int* __restrict__ d_M, int d_M_off, float* __restrict__ part) {
+  pdl_grid_wait();
   extern __shared__ float s_cs[];   // [RL][N]
   if (d_M) M = min(M, *d_M - d_M_off);
   const int groups = N >> 3, RL = 256 / groups;
@@ -269,11 +272,11 @@ cudaError_t launch_colsum_bf16(const bf16* src, int ld, int M, int N, const int*
                                int splits, cudaStream_t st) {
   if (N % 8 == 0 && N <= 2048 && ld % 8 == 0) {
     const int groups = N / 8, RL = 256 / groups;
-    colsum8_bf16_kernel<<<dim3(1, splits), 256, (size_t)RL * N * sizeof(float), st>>>(src, ld, M, N, d_M, d_M_off, part);
+    launch_pdl(colsum8_bf16_kernel, dim3(dim3(1, splits)), dim3(256), (size_t)((size_t)RL * N * sizeof(float)), st, src, ld, M, N, d_M, d_M_off, part);
     return cudaGetLastError();
   }
   dim3 grid((N + 63) / 64, splits);
-  colsum_bf16_kernel<<<grid, 256, 0, st>>>(src, ld, M, N, d_M, d_M_off, part);
+  launch_pdl(colsum_bf16_kernel, dim3(grid), dim3(256), (size_t)(0), st, src, ld, M, N, d_M, d_M_off, part);
   return cudaGetLastError();
 }
 

@@ -31,6 +31,7 @@ struct TAttnDev {
 
 template <int D>
 __global__ void __launch_bounds__(TA_THREADS, 1) tattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, TAttnDev a) {
+  pdl_grid_wait();
   constexpr int NHG = 64 / D;   // heads per 64-column group
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -234,10 +235,10 @@ cudaError_t launch_tattn_fwd(const AttnArgs& a, cudaStream_t st) {
   static bool done32 = false, done64 = false;
   if (D == 32) {
     if (!done32) { cudaError_t e = cudaFuncSetAttribute(tattn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM); if (e != cudaSuccess) return e; done32 = true; }
-    tattn_fwd_kernel<32><<<grid, TA_THREADS, TA_SMEM, st>>>(tm, d);
+    launch_pdl(tattn_fwd_kernel<32>, dim3(grid), dim3(TA_THREADS), (size_t)(TA_SMEM), st, tm, d);
   } else {
     if (!done64) { cudaError_t e = cudaFuncSetAttribute(tattn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM); if (e != cudaSuccess) return e; done64 = true; }
-    tattn_fwd_kernel<64><<<grid, TA_THREADS, TA_SMEM, st>>>(tm, d);
+    launch_pdl(tattn_fwd_kernel<64>, dim3(grid), dim3(TA_THREADS), (size_t)(TA_SMEM), st, tm, d);
   }
   return cudaGetLastError();
 }

@@ -40,6 +40,7 @@ struct TGemmDev {
 template <int EPI, bool B_MN>
 __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                        TGemmDev a) {
+  pdl_grid_wait();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* sCol = reinterpret_cast<float*>(smem + TG_STAGES * TG_STAGE);   // [2 acc][4 quads][128] column-sum partials
@@ -258,7 +259,7 @@ static cudaError_t launch_tgemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB
     if (e != cudaSuccess) return e;
     done = true;
   }
-  tgemm_kernel<EPI, B_MN><<<grid, TG_THREADS, TG_SMEM, st>>>(tmA, tmB, d);
+  launch_pdl(tgemm_kernel<EPI, B_MN>, dim3(grid), dim3(TG_THREADS), (size_t)(TG_SMEM), st, tmA, tmB, d);
   return cudaGetLastError();
 }
 
@@ -306,6 +307,7 @@ struct TWgradDev { int M, N, T, t_per_split, tiles_n; float* out; size_t split_s
 
 __global__ void __launch_bounds__(320, 1) twgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                                                         TWgradDev a) {
+  pdl_grid_wait();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TW_STAGES * TW_STAGE);
@@ -425,7 +427,7 @@ cudaError_t launch_twgrad(const WgradArgs& a, cudaStream_t st) {
     done = true;
   }
   dim3 grid((a.M / 256) * (a.N / 256), a.splits);
-  twgrad_kernel<<<grid, 320, TW_SMEM, st>>>(tmX, tmY, d);
+  launch_pdl(twgrad_kernel, dim3(grid), dim3(320), (size_t)(TW_SMEM), st, tmX, tmY, d);
   return cudaGetLastError();
 }
 }  // namespace b4r
