@@ -78,6 +78,8 @@ _SIGNATURES = {
     "b4r_host_sample_random_batch": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
     "b4r_host_sample_popular_batch": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int]),
     "b4r_host_sample_pop_random_batch": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int]),
+    "b4r_packed_inputs_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "b4r_unpack_inputs": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "b4r_h2d_copy_many": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "b4r_metrics_from_hist": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P]),
     "b4r_sequence_output": (_P, [_P, C.c_int]),

@@ -1142,6 +1142,34 @@ extern "C" int b4r_rank_full_ext(b4r_session* s, const void* t_rows, const int32
   return 0;
 }
 
+// The step's five int64 inputs travel host -> device in a compact form (ids / positions / labels as int32, the two 0/1 arrays as
+// bytes: 2.9x fewer PCIe bytes than the int64 tensors of the reference's batch dict) and are widened on the device into the
+// persistent int64 buffers the captured step reads.  packed = [int32 ids n_tok][int32 positions n_pred][int32 mlm_ids n_pred]
+// [uint8 mask n_tok][uint8 weights n_pred].
+__global__ void __launch_bounds__(256) unpack_inputs_kernel(const int* __restrict__ p32, const unsigned char* __restrict__ p8, int n_tok,
+                                                            int n_pred, long long* __restrict__ ids, long long* __restrict__ mask,
+                                                            long long* __restrict__ pos, long long* __restrict__ mlm,
+                                                            long long* __restrict__ w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_tok) { ids[i] = p32[i]; mask[i] = p8[i]; }
+  if (i < n_pred) { pos[i] = p32[n_tok + i]; mlm[i] = p32[n_tok + n_pred + i]; w[i] = p8[n_tok + i]; }
+}
+extern "C" size_t b4r_packed_inputs_bytes(int n_tok, int n_pred) { return (size_t)4 * ((size_t)n_tok + 2 * (size_t)n_pred) + n_tok + n_pred; }
+extern "C" int b4r_unpack_inputs(const void* packed, int n_tok, int n_pred, int64_t* input_word_ids, int64_t* input_mask,
+                                 int64_t* masked_lm_positions, int64_t* masked_lm_ids, int64_t* masked_lm_weights, void* stream) {
+  if (!packed || n_tok < 1 || n_pred < 0 || !input_word_ids || !input_mask || (n_pred && (!masked_lm_positions || !masked_lm_ids || !masked_lm_weights)))
+    return fail("bad argument");
+  const int* p32 = reinterpret_cast<const int*>(packed);
+  const unsigned char* p8 = reinterpret_cast<const unsigned char*>(packed) + (size_t)4 * ((size_t)n_tok + 2 * (size_t)n_pred);
+  const int n = n_tok > n_pred ? n_tok : n_pred;
+  unpack_inputs_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      p32, p8, n_tok, n_pred, reinterpret_cast<long long*>(input_word_ids), reinterpret_cast<long long*>(input_mask),
+      reinterpret_cast<long long*>(masked_lm_positions), reinterpret_cast<long long*>(masked_lm_ids),
+      reinterpret_cast<long long*>(masked_lm_weights));
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // n host->device copies enqueued back to back (pinned sources: true DMA, the host returns at once).  The step's five int64 inputs
 // go to their persistent device views with ~2 us of host time each instead of a packing pass over the batch on the host.
 extern "C" int b4r_h2d_copy_many(void* const* dst, const void* const* src, const size_t* nbytes, int n, void* stream) {

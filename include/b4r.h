@@ -138,6 +138,13 @@ const float* b4r_shard_step_stats(b4r_shard* s);   /* float[8], layout of b4r_st
 const float* b4r_shard_lse(b4r_shard* s);          /* fp32 [n_ranks*rows_per_rank] packed row order */
 const int32_t* b4r_shard_counts(b4r_shard* s);     /* int32[2] = {n_valid, n_rows} over all ranks */
 
+/* Compact host->device transfer of a step's inputs (the reference's batch dict holds int64 tensors, bert4rec_model.py:15-22):
+ * packed = [int32 input_word_ids n_tok][int32 masked_lm_positions n_pred][int32 masked_lm_ids n_pred][uint8 input_mask n_tok]
+ * [uint8 masked_lm_weights n_pred] (b4r_packed_inputs_bytes), copied with ONE H2D copy and widened on the device into the int64
+ * buffers the step reads.  n_tok = batch*seq_len, n_pred = batch*max_pred. */
+size_t b4r_packed_inputs_bytes(int n_tok, int n_pred);
+int b4r_unpack_inputs(const void* packed, int n_tok, int n_pred, int64_t* input_word_ids, int64_t* input_mask,
+                      int64_t* masked_lm_positions, int64_t* masked_lm_ids, int64_t* masked_lm_weights, void* stream);
 /* n host->device copies enqueued back to back on `stream` (dst[i] device, src[i] host -- pinned for a true asynchronous DMA).
  * Host inputs of a step (the reference feeds host tensors through tf.data, dataloader_utils.py:306-346) reach the persistent
  * device buffers of the captured step without a packing pass on the host. */
