@@ -510,10 +510,10 @@ def roofline_block(model, sess, w, dev_batches, args, hbm, tf_burst, src):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
 NCU_TRAFFIC = {   # bytes per launch at C2, profiles/r01_ncu_full_c2.md (cold-cache capture; the step itself runs L2-warm)
-    "enc_bwd_fused": 39_321_088 + 249_856,
-    "enc_fwd_fused": 1_028_864 + 124_928,
-    "ce_fwd_umma": 1_878_528,
-    "ce_bwd_fused": 2_033_664 + 959_232,
+    "enc_bwd_fused": 39_311_872 + 396_288,
+    "enc_fwd_fused": 1_029_376 + 227_328,
+    "ce_fwd_umma": 1_879_040,
+    "ce_bwd_fused": 1_999_616 + 809_472,
 }
 
 
