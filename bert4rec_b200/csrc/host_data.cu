@@ -14,6 +14,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <unistd.h>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -118,28 +121,91 @@ inline uint64_t np_interval(MT19937& g, uint64_t max) {   // random_interval: un
   return v;
 }
 
+// Persistent worker pool: a batch call is a few hundred microseconds of work, a std::thread start costs tens of microseconds, so
+// the workers are created once (lazily, re-created in a forked child) and woken per job.  One job at a time (callers serialise on
+// `run_mu`); the calling thread works too.  The pool is never destroyed (detached workers die with the process).
+class Pool {
+ public:
+  static Pool& get() {
+    static std::mutex mu;
+    static Pool* pool = nullptr;
+    static pid_t owner = 0;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pool || owner != getpid()) {   // first use, or a fork()ed child (threads do not survive fork)
+      pool = new Pool();
+      owner = getpid();
+    }
+    return *pool;
+  }
+  // runs job() on up to `threads` threads (including the caller) and returns when all of them are done
+  void run(int threads, const std::function<void()>& job) {
+    std::lock_guard<std::mutex> serial(run_mu_);
+    const int helpers = std::min(threads - 1, (int)workers_);
+    if (helpers <= 0) { job(); return; }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = &job; wanted_ = helpers; running_ = helpers; ++gen_;
+    }
+    cv_.notify_all();
+    job();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&] { return running_ == 0; });
+    job_ = nullptr;
+  }
+  int size() const { return (int)workers_ + 1; }
+
+ private:
+  Pool() {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw < 1) hw = 1;
+    if (hw > 64) hw = 64;
+    workers_ = hw - 1;
+    for (unsigned i = 0; i < workers_; ++i) std::thread([this] { loop(); }).detach();
+  }
+  void loop() {
+    unsigned long seen = 0;
+    for (;;) {
+      const std::function<void()>* job = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (wanted_ > 0) { --wanted_; job = job_; }   // only `helpers` workers take part in this job
+      }
+      if (!job) continue;
+      (*job)();
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--running_ == 0) done_.notify_all();
+    }
+  }
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void()>* job_ = nullptr;
+  unsigned long gen_ = 0;
+  int wanted_ = 0, running_ = 0;
+  unsigned workers_ = 0;
+};
+
 template <class F>
 int run_parallel(int n, int n_threads, F&& body, int grain = 1) {   // body(i) -> 0 or error; first error wins
-  if (n_threads < 1) n_threads = (int)std::thread::hardware_concurrency();
-  if (n_threads < 1) n_threads = 1;
+  if (n_threads < 1) n_threads = Pool::get().size();
   if (grain > 1 && n_threads > (n + grain - 1) / grain) n_threads = (n + grain - 1) / grain;   // cheap items: a thread per `grain` of them
   if (n_threads > n) n_threads = n > 0 ? n : 1;
   std::atomic<int> next(0), err(0);
+  const int chunk = n >= 16 * n_threads ? 16 : (n + n_threads - 1) / n_threads > 0 ? (n + n_threads - 1) / n_threads : 1;
   auto worker = [&]() {
     for (;;) {
-      const int i0 = next.fetch_add(16);
+      const int i0 = next.fetch_add(chunk);
       if (i0 >= n || err.load()) return;
-      const int i1 = i0 + 16 < n ? i0 + 16 : n;
+      const int i1 = i0 + chunk < n ? i0 + chunk : n;
       for (int i = i0; i < i1; ++i) {
         const int e = body(i);
         if (e) { err.store(e); return; }
       }
     }
   };
-  if (n_threads == 1) { worker(); return err.load(); }
-  std::vector<std::thread> th;
-  for (int t = 0; t < n_threads; ++t) th.emplace_back(worker);
-  for (auto& t : th) t.join();
+  if (n_threads <= 1) { worker(); return err.load(); }
+  Pool::get().run(n_threads, worker);
   return err.load();
 }
 
@@ -315,7 +381,7 @@ extern "C" int b4r_host_sample_random_batch(const int64_t* vocab, int64_t n_voca
       const int64_t tot_wo = without ? without_off[n] - without_off[0] : 0;
       std::vector<int32_t> ex_pos((size_t)tot_wo);   // per request: sorted unique excluded vocab positions, at without_off[b] - without_off[0]
       std::vector<int32_t> ex_cnt((size_t)n, 0);
-      const int kGrain = 128;   // requests per thread for the cheap per-request phases (a std::thread start costs ~20-50 us)
+      const int kGrain = 32;   // requests per thread for the cheap per-request phases
       int rc = run_parallel(n, n_threads, [&](int b) -> int {
         int32_t* e = ex_pos.data() + (without ? without_off[b] - without_off[0] : 0);
         int m = 0;
