@@ -218,3 +218,38 @@ def test_sampler_batch_per_request_seeds_take_the_general_path():
     for i, w in enumerate(withouts):
         np.random.seed(9)
         assert got[i].tolist() == np.random.choice([v for v in dup_vocab if v not in set(w)], size=20, replace=False).tolist()
+
+
+def test_host_path_is_safe_under_concurrent_callers_and_after_fork():
+    """The worker pool serialises jobs of concurrent callers, and a fork()ed child gets its own workers."""
+    import multiprocessing as mp
+    import threading
+    rng = np.random.RandomState(4)
+    V, S, P, n = 997, 32, 8, 600
+    seqs = [rng.randint(3, V, size=rng.randint(1, S + 1)).astype(np.int64) for _ in range(n)]
+    seeds = np.arange(n, dtype=np.uint64)
+    ref = hn.cloze_mask_batch(seqs, S, P, 1, [2, 0], V, 0.3, 0.8, 0.1, seeds=seeds, n_threads=1)
+    outs = [None] * 4
+
+    def work(i):
+        for _ in range(5):
+            outs[i] = hn.cloze_mask_batch(seqs, S, P, 1, [2, 0], V, 0.3, 0.8, 0.1, seeds=seeds, n_threads=0)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join(60) for t in ts]
+    assert not any(t.is_alive() for t in ts)
+    for o in outs:
+        assert all(np.array_equal(o[k], ref[k]) for k in ref)
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+
+    def child():
+        o = hn.cloze_mask_batch(seqs, S, P, 1, [2, 0], V, 0.3, 0.8, 0.1, seeds=seeds, n_threads=0)
+        q.put(all(np.array_equal(o[k], ref[k]) for k in ref))
+
+    p = ctx.Process(target=child)
+    p.start()
+    assert q.get(timeout=60) is True
+    p.join(30)
+    assert p.exitcode == 0
