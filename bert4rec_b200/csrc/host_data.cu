@@ -40,7 +40,8 @@ struct MT19937 {
     pos = 624;
   }
   void init_by_array(const uint32_t* key, int len) {   // CPython random_seed for an int
-    init_genrand(19650218u);
+    static const MT19937 base = [] { MT19937 b; b.init_genrand(19650218u); return b; }();   // constant first stage: computed once
+    memcpy(mt, base.mt, sizeof(mt));
     int i = 1, j = 0;
     for (int k = 624 > len ? 624 : len; k; --k) {
       mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
@@ -56,24 +57,16 @@ struct MT19937 {
     mt[0] = 0x80000000u;
     pos = 624;
   }
-  void refill() {
-    static const uint32_t mag[2] = {0u, 0x9908b0dfu};
-    int kk = 0;
-    for (; kk < 624 - 397; ++kk) {
-      const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
-      mt[kk] = mt[kk + 397] ^ (y >> 1) ^ mag[y & 1u];
-    }
-    for (; kk < 623; ++kk) {
-      const uint32_t y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
-      mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ mag[y & 1u];
-    }
-    const uint32_t y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
-    mt[623] = mt[396] ^ (y >> 1) ^ mag[y & 1u];
-    pos = 0;
-  }
+  // The state is twisted LAZILY, one word per draw, in place and in index order: word k of the next generation depends on the old
+  // words k, k+1 and on word k+397 (old for k < 227, already new for k >= 227), exactly the values the block refill of the
+  // reference implementation sees when it reaches k.  A masked sequence draws ~100 numbers, not 624: most of the twist is never done.
   uint32_t next32() {
-    if (pos >= 624) refill();
-    uint32_t y = mt[pos++];
+    static const uint32_t mag[2] = {0u, 0x9908b0dfu};
+    if (pos >= 624) pos = 0;
+    const int k = pos, k1 = k == 623 ? 0 : k + 1, km = k < 227 ? k + 397 : k - 227;
+    const uint32_t t = (mt[k] & 0x80000000u) | (mt[k1] & 0x7fffffffu);
+    uint32_t y = mt[k] = mt[km] ^ (t >> 1) ^ mag[t & 1u];
+    ++pos;
     y ^= y >> 11;
     y ^= (y << 7) & 0x9d2c5680u;
     y ^= (y << 15) & 0xefc60000u;
