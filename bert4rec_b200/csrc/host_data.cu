@@ -84,6 +84,40 @@ inline void py_seed(MT19937& g, uint64_t seed) {
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   g.init_by_array(key, key[1] ? 2 : 1);
 }
+// Four generators seeded in lockstep: init_by_array is a chain of ~1250 dependent multiply-xor steps (the whole cost of masking a
+// short sequence is this latency chain); four independent chains interleaved in one loop keep the multiplier busy.
+inline void py_seed4(MT19937* g, const uint64_t* seed, int count) {
+  static const MT19937 base = [] { MT19937 b; b.init_genrand(19650218u); return b; }();
+  uint32_t key[4][2];
+  int len[4], j[4];
+  for (int q = 0; q < 4; ++q) {
+    const uint64_t sd = seed[q < count ? q : 0];
+    key[q][0] = (uint32_t)sd; key[q][1] = (uint32_t)(sd >> 32);
+    len[q] = key[q][1] ? 2 : 1; j[q] = 0;
+    memcpy(g[q].mt, base.mt, sizeof(base.mt));
+  }
+  uint32_t* __restrict__ m0 = g[0].mt; uint32_t* __restrict__ m1 = g[1].mt;
+  uint32_t* __restrict__ m2 = g[2].mt; uint32_t* __restrict__ m3 = g[3].mt;
+  uint32_t p0 = m0[0], p1 = m1[0], p2 = m2[0], p3 = m3[0];   // mt[i-1] of every chain, carried in registers
+  int i = 1;
+  for (int k = 624; k; --k) {
+    p0 = m0[i] = (m0[i] ^ ((p0 ^ (p0 >> 30)) * 1664525u)) + key[0][j[0]] + (uint32_t)j[0];
+    p1 = m1[i] = (m1[i] ^ ((p1 ^ (p1 >> 30)) * 1664525u)) + key[1][j[1]] + (uint32_t)j[1];
+    p2 = m2[i] = (m2[i] ^ ((p2 ^ (p2 >> 30)) * 1664525u)) + key[2][j[2]] + (uint32_t)j[2];
+    p3 = m3[i] = (m3[i] ^ ((p3 ^ (p3 >> 30)) * 1664525u)) + key[3][j[3]] + (uint32_t)j[3];
+    for (int q = 0; q < 4; ++q)
+      if (++j[q] >= len[q]) j[q] = 0;
+    if (++i >= 624) { m0[0] = p0; m1[0] = p1; m2[0] = p2; m3[0] = p3; i = 1; }
+  }
+  for (int k = 623; k; --k) {
+    p0 = m0[i] = (m0[i] ^ ((p0 ^ (p0 >> 30)) * 1566083941u)) - (uint32_t)i;
+    p1 = m1[i] = (m1[i] ^ ((p1 ^ (p1 >> 30)) * 1566083941u)) - (uint32_t)i;
+    p2 = m2[i] = (m2[i] ^ ((p2 ^ (p2 >> 30)) * 1566083941u)) - (uint32_t)i;
+    p3 = m3[i] = (m3[i] ^ ((p3 ^ (p3 >> 30)) * 1566083941u)) - (uint32_t)i;
+    if (++i >= 624) { m0[0] = p0; m1[0] = p1; m2[0] = p2; m3[0] = p3; i = 1; }
+  }
+  for (int q = 0; q < 4; ++q) { g[q].mt[0] = 0x80000000u; g[q].pos = 624; }
+}
 inline int bit_length(uint64_t n) { return n ? 64 - __builtin_clzll(n) : 0; }
 inline uint64_t py_randbelow(MT19937& g, uint64_t n) {   // n >= 1, n < 2^32 here
   const int k = bit_length(n);
@@ -249,7 +283,13 @@ extern "C" int b4r_host_cloze_mask_batch(const int64_t* tokens, const int64_t* o
       if (special_ids[i] == v) return true;
     return false;
   };
-  const int rc = run_parallel(n, n_threads, [&](int b) -> int {
+  const int rc = run_parallel((n + 3) / 4, n_threads, [&](int grp) -> int {
+   MT19937 gens[4];
+   const int b0 = grp * 4, cnt = n - b0 < 4 ? n - b0 : 4;
+   py_seed4(gens, seeds + b0, cnt);
+   for (int bq = 0; bq < cnt; ++bq) {
+    const int b = b0 + bq;
+    MT19937& g = gens[bq];
     const int64_t* seq = tokens + offsets[b];
     const int64_t len64 = offsets[b + 1] - offsets[b];
     if (len64 < 0 || len64 > S) return err.fail("sequence %d has %lld tokens, more than max_seq_len %d", b, (long long)len64, S);
@@ -262,8 +302,6 @@ extern "C" int b4r_host_cloze_mask_batch(const int64_t* tokens, const int64_t* o
       lab[i] = in ? seq[i] : pad_id; ids[i] = in ? seq[i] : pad_id; msk[i] = in ? 1 : pad_id;
     }
     for (int i = 0; i < P; ++i) { mid[i] = pad_id; mpos[i] = pad_id; mw[i] = pad_id; }
-    MT19937 g;
-    py_seed(g, seeds[b]);
     int n_plain = 0;
     for (int i = 0; i < len; ++i) n_plain += is_special(seq[i]) ? 0 : 1;
     int n_pred = (int)((double)n_plain * selection_rate);   // int(len * rate): truncation of the double product
@@ -297,6 +335,7 @@ extern "C" int b4r_host_cloze_mask_batch(const int64_t* tokens, const int64_t* o
       ids[idx] = token;
       mid[k] = seq[idx]; mpos[k] = idx; mw[k] = 1;
     }
+   }
     return 0;
   });
   return err.finish(rc);
