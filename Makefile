@@ -1,7 +1,7 @@
 # Builds libb4r.so (sm_100a only) in-tree and the oracle helpers.  `make -j` ; `make clean`.
 NVCC ?= nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v $(EXTRA)
 SRC_DIR := bert4rec_b200/csrc
 SRCS := $(wildcard $(SRC_DIR)/*.cu)
 OBJS := $(patsubst $(SRC_DIR)/%.cu,build/%.o,$(SRCS))

@@ -201,6 +201,7 @@ struct b4r_session {
   int vsplits, vsplits_umma;
   bool use_umma = false;
   CeUmmaMaps umaps;
+  bool use_fattn = true;    // tcgen05 attention of the layered path (k_fattn.cu); false: mma.sync generation (k_attn.cu)
   bool use_fused = false;   // whole-encoder forward in one tcgen05 launch (k_enc_fused.cu)
   bool use_fused_bwd = false, fused_bwd_ok = false;   // ... and the backward (k_enc_fused_bwd.cu)
   float *enc_wpart = nullptr, *enc_bpart = nullptr, *enc_dpos = nullptr, *enc_embln = nullptr;
@@ -564,6 +565,7 @@ extern "C" int b4r_encode(b4r_session* s, const int64_t* ids, const int64_t* mas
     AttnArgs a{};
     a.qkv = L.qkv; a.mask = mask; a.ctx = L.ctx; a.lse = L.lse; a.keep_bits = L.keep; a.B = s->B; a.S = s->S; a.H = H; a.N = s->N;
     a.drop_rate = ad; a.seed = seed; a.site = site_id(SITE_ATTN_PROBS, l); a.step = step; a.d_step = d_step;
+    a.no_tcgen05 = !s->use_fattn;
     KL("attn_fwd", launch_attn_fwd(a, st));
     RowLnArgs r{};
     r.A = L.ctx; r.lda = H; r.W = W + L.wo; r.M = T; r.K = H; r.H = H; r.bias = P + L.bo; r.gamma = P + L.g1; r.beta = P + L.be1;
@@ -851,7 +853,7 @@ static int backward_impl(b4r_session* s, uint64_t seed, uint32_t step, const int
     {
       AttnArgs a{};
       a.qkv = L.qkv; a.mask = s->mask; a.ctx = L.ctx; a.lse = L.lse; a.keep_bits = L.keep; a.B = s->B; a.S = s->S; a.H = H; a.N = s->N;
-      a.drop_rate = s->cfg.attention_dropout; a.dctx = s->dctx; a.dqkv = s->dqkv;
+      a.drop_rate = s->cfg.attention_dropout; a.dctx = s->dctx; a.dqkv = s->dqkv; a.no_tcgen05 = !s->use_fattn;
       KL("attn_bwd", launch_attn_bwd(a, st));
     }
     KL("colsum:bqkv", launch_colsum_bf16(s->dqkv, 3 * H, T, 3 * H, nullptr, 0, L.p_bqkv, kColsumSplits, st));
@@ -1233,6 +1235,7 @@ extern "C" int b4r_session_set_flag(b4r_session* s, int flag, int value) {
   if (!s) return fail("null session");
   if (flag == 1) { s->use_umma = value != 0; return 0; }
   if (flag == 4) { s->overlap_select = value != 0; return 0; }
+  if (flag == 6) { s->use_fattn = value != 0; return 0; }
   if (flag == 5) {
     if (value && !s->ce_fused_ok) return fail("one-pass CE backward unavailable for this shape");
     s->use_ce_fused = value != 0;

@@ -5,6 +5,7 @@
 // degenerates to uniform attention, exactly as in the reference), attention-prob dropout keep bits are written
 // bit-packed (1 bit / prob) in forward and re-read in backward.
 // Generation 1: mma.sync m16n8k16 with flash-style online softmax.  S <= 256, D in {32, 64}.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -193,7 +194,8 @@ static size_t attn_fwd_smem(int S, int D) {
 }
 
 cudaError_t launch_attn_fwd(const AttnArgs& a, cudaStream_t st) {
-  if (tattn_fwd_supported(a)) return launch_tattn_fwd(a, st);   // generation 2: tcgen05 + TMEM + TMA
+  if (!a.no_tcgen05 && fattn_supported(a) && !getenv("B4R_FATTN_NO_FWD")) return launch_fattn_fwd(a, st);   // generation 2: tcgen05 + TMEM + TMA
+  if (tattn_fwd_supported(a)) return launch_tattn_fwd(a, st);                 // first tcgen05 forward (opt-in)
   const int D = a.H / a.N;
   if (a.S > 256 || (D != 32 && D != 64)) return cudaErrorInvalidValue;
   uint32_t thr = drop_threshold16(a.drop_rate);
@@ -447,6 +449,7 @@ static size_t attn_bwd_smem(int S, int D) {
 }
 
 cudaError_t launch_attn_bwd(const AttnArgs& a, cudaStream_t st) {
+  if (!a.no_tcgen05 && fattn_supported(a) && !getenv("B4R_FATTN_NO_BWD")) return launch_fattn_bwd(a, st);   // generation 2: tcgen05 + TMEM + TMA
   const int D = a.H / a.N;
   if (a.S > 256 || (D != 32 && D != 64)) return cudaErrorInvalidValue;
   uint32_t thr = drop_threshold16(a.drop_rate);

@@ -113,11 +113,17 @@ struct AttnArgs {
   // backward
   const bf16* dctx;       // [B*S][H]
   bf16* dqkv;             // [B*S][3H]
+  bool no_tcgen05;        // force the mma.sync generation (session flag 6 = 0; parity partner of k_fattn.cu)
 };
 cudaError_t launch_attn_fwd(const AttnArgs& a, cudaStream_t st);
 cudaError_t launch_attn_bwd(const AttnArgs& a, cudaStream_t st);
 int attn_mask_words(int S);
-// generation 2 forward (k_tattn.cu): tcgen05 + TMEM + TMA, seq_len <= 256; launch_attn_fwd dispatches to it
+// generation 2 (k_fattn.cu): tcgen05 + TMEM + TMA, persistent warp-specialised CTAs, seq_len <= 256, head dim 32 / 64;
+// launch_attn_fwd / launch_attn_bwd dispatch to it unless no_tcgen05
+bool fattn_supported(const AttnArgs& a);
+cudaError_t launch_fattn_fwd(const AttnArgs& a, cudaStream_t st);
+cudaError_t launch_fattn_bwd(const AttnArgs& a, cudaStream_t st);
+// first tcgen05 forward (k_tattn.cu, opt-in B4R_ENABLE_TATTN): one serial chain per CTA, kept for comparison
 bool tattn_fwd_supported(const AttnArgs& a);
 cudaError_t launch_tattn_fwd(const AttnArgs& a, cudaStream_t st);
 

@@ -196,7 +196,9 @@ int b4r_launch_count(b4r_session* s);   /* kernels launched through this session
  * flag 2: whole-encoder fused tcgen05 forward (1, default where the shape allows) or the layered kernels (0);
  * flag 3: whole-encoder fused tcgen05 backward (needs flag 2) or the layered backward kernels (0);
  * flag 4: while set, b4r_mlm_select runs as a parallel branch (internal side stream, joined by the next consumer of the
- *         selection) so that it overlaps whatever the caller enqueues next, e.g. b4r_encode (default 0) */
+ *         selection) so that it overlaps whatever the caller enqueues next, e.g. b4r_encode (default 0);
+ * flag 5: one-pass tcgen05 CE backward (1, default at hidden 64) or the two recompute passes (0);
+ * flag 6: tcgen05 attention kernels of the layered encoder path (1, default) or the mma.sync generation (0) */
 int b4r_session_set_flag(b4r_session* s, int flag, int value);
 const void* b4r_debug_buffer(b4r_session* s);
 const void* b4r_debug_buffer2(b4r_session* s); /* uint64[512]: fused-kernel phase timestamps (ns) when B4R_FUSED_DEBUG is set */  /* kernel-internal timestamps when B4R_CE_DEBUG&8 (development aid) */

@@ -155,3 +155,65 @@ def test_c2_full_size_ranking_properties():
     a = sess.rank_full(n, 0, 5000)
     b = sess.rank_full(n, 5000, V)
     assert torch.equal(whole, a + b) and int(whole.min()) >= 0 and int(whole.max()) < V
+
+
+def _oracle_step_parity(wl, B, seed, ragged=True):
+    """One training forward + backward at the workload's REAL shape (all of V, S, H, L, N, I, P; batch ``B``) against the fp32
+    CPU oracle: logits of all P slots (rel-L2 1e-2), loss (1e-3 relative), counts, every gradient tensor (4e-2 rel-L2)."""
+    from oracle import model as om
+    store, kw, w = _store(wl)
+    S, P, V = w["seq_len"], w["max_pred"], w["vocab_size"]
+    batch = make_batch(B, S, P, V, p_mask=w["mask_prob"], ragged=ragged, seed=seed)
+    cb = to_cuda(batch)
+    sess = store.session(B, S, P)
+    # forward: logits over ALL P slots (BERT4RecModel.call semantics)
+    sess.encode(cb["input_word_ids"], cb["input_mask"], training=False)
+    sess.select(cb["masked_lm_positions"], cb["masked_lm_ids"], cb["masked_lm_weights"], mode=2)
+    sess.transform()
+    logits = sess.logits(B * P).cpu().reshape(B, P, V)
+    seq = sess.sequence_output().float().cpu()
+    got, st = _grads(store, sess, cb)
+    sd = {k: v.to(torch.bfloat16).float() if k.endswith(("kernel", "embeddings")) else v for k, v in store.state_dict().items()}
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = om.model_forward(leaves, oracle_cfg(kw), batch, training=False)
+    y = batch["masked_lm_ids"]
+    loss = om.masked_sparse_ce(y, out["mlm_logits"])
+    names = list(leaves)
+    gs = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    n_valid = int((y != 0).sum())
+    assert int(st[1]) == n_valid and int(st[4]) == B * P
+    loss = loss.detach()
+    assert abs(float(st[0]) / n_valid - float(loss)) < 1e-3 * float(loss), (float(st[0]) / n_valid, float(loss))
+    err = (seq - out["sequence_output"].detach()).abs().max().item()
+    assert err < 8e-2, f"{wl}: sequence_output max abs err {err}"
+    rl = rel_l2(logits, out["mlm_logits"].detach())
+    assert rl < 1e-2, f"{wl}: logits rel l2 {rl}"                                  # north_star: logits within 1e-2 relative
+    gd = store.tf_views(got)
+    ref = {k: g for k, g in zip(names, gs) if g is not None}
+    gmax = max(float(g.norm()) for g in ref.values())
+    bad = []
+    for k, g in ref.items():
+        e = float((gd[k].cpu().double() / n_valid - g.double()).norm())
+        if not e < 4e-2 * float(g.norm()) + 1e-5 * gmax:
+            bad.append((k, e, float(g.norm())))
+    assert not bad, f"{wl}: gradient mismatches (name, l2 err, ref norm): {bad}"
+
+
+def test_c1_full_size_train_step_against_oracle():
+    """BASELINE config 1 (ML-1m shape) at its full size, B = 256 (152 MB of oracle logits)."""
+    _oracle_step_parity("c1", 256, seed=71)
+
+
+def test_c3_shape_train_step_against_oracle():
+    """BASELINE config 3 (ML-20m shape: V 26 732, S 200, H 64) on a 48-sequence slice of the per-GPU batch."""
+    _oracle_step_parity("c3", 48, seed=73)
+
+
+def test_c4_shape_train_step_against_oracle():
+    """BASELINE config 4 at its real shape (H 256, 4 layers x 4 heads of 64, S 200, I 1024, V 13 047), 24 sequences."""
+    _oracle_step_parity("c4", 24, seed=79)
+
+
+def test_c4_shape_dense_sequences_against_oracle():
+    """The same with full-length sequences (the bench's shape: no padded keys, every 128-row tile full)."""
+    _oracle_step_parity("c4", 8, seed=83, ragged=False)
