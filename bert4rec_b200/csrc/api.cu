@@ -1113,7 +1113,7 @@ extern "C" int b4r_rank_candidates(b4r_session* s, const int64_t* cand, const in
   if (n_slots > s->Mcap) return fail("n_slots %d exceeds session capacity %d", n_slots, s->Mcap);
   if (join_select(s, st)) return 1;
   KL("rank_candidates", launch_rank_candidates(s->t, s->H, s->shadow + s->lay.find("word_embeddings"), s->params + s->lay.find("head/output_bias"),
-                            cand, gt, n_slots, C, s->H, reinterpret_cast<int64_t*>(ranking_out), scores_out, rank_out,
+                            cand, gt, n_slots, C, s->H, s->V, s->counts, reinterpret_cast<int64_t*>(ranking_out), scores_out, rank_out,
                             reinterpret_cast<unsigned long long*>(hist), st));
   return 0;
 }

@@ -22,14 +22,15 @@ constexpr float kLnEps = 1e-12f;  // reference: bert4rec_encoder.py:116-117
 enum DropSite : uint32_t { SITE_EMB = 1, SITE_ATTN_OUT = 2, SITE_FFN_OUT = 3, SITE_ATTN_PROBS = 4 };
 __host__ __device__ inline uint32_t site_id(uint32_t site, uint32_t layer) { return site | (layer << 8); }
 
-// ---------------------------------------------------------------- Philox4x32-10
+// ---------------------------------------------------------------- Philox4x32-7 (the Crush-resistant round count of the Random123 paper; 10 is its
+// safety-margin default): the dropout masks cost 13 of the ~23 instructions per attention probability at 10 rounds
 struct Philox {
   uint32_t k0, k1;
   __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
   __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
     uint32_t ka = k0, kb = k1;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < 7; ++r) {
       uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
       uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
       uint32_t n0 = hi1 ^ c1 ^ ka, n2 = hi0 ^ c3 ^ kb;
@@ -61,9 +62,31 @@ __device__ __forceinline__ uint32_t keep_bits8(const Philox& ph, uint32_t row, u
 }
 
 // ---------------------------------------------------------------- math
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (keras.activations.gelu(approximate=False), bert4rec_encoder.py:96) and its derivative, branch-free:
+// Phi(x) = 1/2 erfc(-x / sqrt 2) with erfc from Abramowitz & Stegun 7.1.26 (|error| < 1.5e-7, i.e. fp32 round-off level),
+// whose exponential exp(-x^2 / 2) is also the density term of the derivative.  ~15 instructions instead of erff's ~35: the
+// GELU epilogues of the FFN GEMMs were instruction-bound on erff (profiles/r01_ncu_tgemm_c4.md).
+__device__ __forceinline__ void gelu_terms(float x, float& Phi, float& dens) {
+  const float t = __fdividef(1.0f, fmaf(0.23164189f, fabsf(x), 1.0f));     // 1 / (1 + p |x| / sqrt 2), p = 0.3275911
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));   // exp(-x^2 / 2)
+  float q = fmaf(1.061405429f, t, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  const float hc = 0.5f * q * t * e;                                         // 1/2 erfc(|x| / sqrt 2)
+  Phi = x >= 0.f ? 1.0f - hc : hc;
+  dens = e * 0.3989422804014327f;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float Phi, dens;
+  gelu_terms(x, Phi, dens);
+  return x * Phi;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  float Phi, dens;
+  gelu_terms(x, Phi, dens);
+  return fmaf(x, dens, Phi);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

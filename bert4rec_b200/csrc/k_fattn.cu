@@ -37,6 +37,8 @@ __device__ __forceinline__ float ex2(float x) {
 }
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[32]) { umma::tmem_ld32(taddr, r); }
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[16]) { umma::tmem_ld16(taddr, r); }
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[8]) { umma::tmem_ld8(taddr, r); }
+constexpr int FA_NG = 2;                 // column groups of the compute threads: 128 * FA_NG threads = TMEM lane quadrant x column group
 // 32 score columns, or (last chunk of a sequence whose padded length is an odd multiple of 16) 16 columns + zeros: columns past
 // the score MMA's N were never written and may hold NaN bit patterns
 __device__ __forceinline__ void ld_chunk(uint32_t taddr, bool full, uint32_t (&r)[32]) {
@@ -65,12 +67,16 @@ __device__ __noinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, int i
   if ((threadIdx.x & 31) == 0) printf("TIMEOUT cta %d warp %d barrier %d parity %u\n", blockIdx.x, threadIdx.x >> 5, id, parity);
 }
 #define MBAR_WAIT(bar, par, id) mbar_wait_dbg(bar, par, id)
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ unsigned long long g_fattn_ts[128];
+#define FTS(cond, id) do { if (cond) g_fattn_ts[id] = gtimer(); } while (0)
 #else
+#define FTS(cond, id) do { } while (0)
 #define MBAR_WAIT(bar, par, id) umma::mbar_wait(bar, par)
 #endif
 
 // ------------------------------------------------------------------------------------------------ backward
-constexpr int FB_CT = 256;               // compute threads
+constexpr int FB_CT = 128 * FA_NG;       // compute threads
 constexpr int FB_THREADS = FB_CT + 32;   // + control warp
 constexpr int FB_Q = 0, FB_K = 2, FB_V = 4, FB_DO = 6, FB_P = 8, FB_DS = 10, FB_TILES = 12;
 constexpr int FB_OFF_LD = FB_TILES * TILE_B;            // float2 [2][256]  (lse * log2e, delta)
@@ -92,7 +98,9 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
                  const __grid_constant__ CUtensorMap tmO, FAttnBwdDev a) {
   pdl_grid_wait();
   constexpr int NHG = 64 / D;      // heads per 64-column group
-  constexpr int CPT = D / 2;       // accumulator columns drained per thread
+  constexpr int CPT = D / FA_NG;   // accumulator columns drained per thread
+  constexpr int QPT = 128 / FA_NG; // query columns of a score tile per thread
+  constexpr int NCH = QPT / 16;    // in 16-column chunks
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float2* sLD = reinterpret_cast<float2*>(smem + FB_OFF_LD);
@@ -149,7 +157,10 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++nitem) {
       const int b = item / G, g = item % G;
+      const bool tsk = blockIdx.x == 0 && nitem == 2 && lane == 0;
+      FTS(tsk, 64);
       if (git > 0) umma::mbar_wait(barG, (git - 1) & 1);     // every MMA of the previous item has completed: tiles are free
+      FTS(tsk, 65);
       if (elect_one()) {
         umma::mbar_expect_tx(barL, (uint32_t)(5 * MT * TILE_B));
         for (int mt = 0; mt < MT; ++mt) {
@@ -162,16 +173,21 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         }
       }
       __syncwarp();
+      FTS(tsk, 66);
       umma::mbar_wait(barL, nitem & 1);
+      FTS(tsk, 67);
       if (git > 0) umma::mbar_wait(barSF, (git - 1) & 1);    // score accumulators of the previous iteration were read
       issue_scores(0);
+      FTS(tsk, 68);
       for (int i = 0; i < n_it; ++i, ++git) {
         const int h = i / (MT * MT), kt = (i / MT) % MT, qt = i % MT;
         if (i + 1 < n_it) {
           umma::mbar_wait(barSF, git & 1);
+          FTS(tsk, 70 + i * 4);
           issue_scores(i + 1);
         }
-        umma::mbar_wait(barPD, git & 1);                      // Pd^T / dS^T tiles of iteration i are in shared memory
+        umma::mbar_wait(barPD, git & 1);
+        FTS(tsk, 71 + i * 4);                      // Pd^T / dS^T tiles of iteration i are in shared memory
         if (qt == 0) {
           if (gblk > 0) umma::mbar_wait(barAF, (gblk - 1) & 1);   // the accumulators of the previous block were drained
           ++gblk;
@@ -189,6 +205,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           umma::mma_commit(barG);
         }
         __syncwarp();
+        FTS(tsk, 72 + i * 4);
         (void)h;
       }
     }
@@ -205,9 +222,12 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++nitem) {
       const int b = item / G, g = item % G;
+      const bool tsc = blockIdx.x == 0 && nitem == 2 && tid == 0;
+      FTS(tsc, 0);
       umma::mbar_wait(barL, nitem & 1);
+      FTS(tsc, 1);
       // ---- per-item vectors: key mask, lse (log2 units), delta = rowsum(dO * O), keep bits
-      sMask[tid] = tid < S ? (a.mask[(size_t)b * S + tid] != 0 ? 0.f : -1e9f * kLog2e) : -INFINITY;
+      if (tid < 256) sMask[tid] = tid < S ? (a.mask[(size_t)b * S + tid] != 0 ? 0.f : -1e9f * kLog2e) : -INFINITY;
 #pragma unroll
       for (int h = 0; h < NHG; ++h) {
         const int bn = b * a.N + g * NHG + h;
@@ -219,13 +239,14 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 #pragma unroll
           for (int i = 0; i < D; ++i) dl += dv[i] * ov[i];
         }
-        sLD[h * 256 + tid] = make_float2(tid < S ? a.lse[(size_t)bn * S + tid] * kLog2e : INFINITY, dl);
+        if (tid < 256) sLD[h * 256 + tid] = make_float2(tid < S ? a.lse[(size_t)bn * S + tid] * kLog2e : INFINITY, dl);
         if (drop) {
           const unsigned long long* src = a.keep + (size_t)bn * S * W;
           for (int i = tid; i < S * W; i += FB_CT) sKeep[h * 1024 + i] = src[i];
         }
       }
       named_bar_sync(1, FB_CT);
+      FTS(tsc, 2);
       for (int i = 0; i < n_it; ++i, ++git) {
         const int h = i / (MT * MT), kt = (i / MT) % MT, qt = i % MT;
         const int qext = min(128, S16 - qt * 128);
@@ -236,11 +257,12 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         const int kbit = key & 63;
         // ---- phase A: scores -> Pd^T, dS^T packed in registers
         umma::mbar_wait(barS, git & 1);
+        FTS(tsc, 4 + i * 6);
         umma::fence_after_sync();
-        uint32_t pkp[4][8], pkd[4][8];
+        uint32_t pkp[NCH][8], pkd[NCH][8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int q0 = wg * 64 + c * 16;
+        for (int c = 0; c < NCH; ++c) {
+          const int q0 = wg * QPT + c * 16;
           if (q0 < qext) {
             float s[16], dp[16];
             {
@@ -270,11 +292,13 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         }
         umma::fence_before_sync();
         umma::mbar_arrive(barSF);
+        FTS(tsc, 5 + i * 6);
         // ---- phase B: registers -> swizzled tiles [key][query] (free once the gradient MMAs of the previous iteration are done)
         need_g(git);
+        FTS(tsc, 6 + i * 6);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int q0 = wg * 64 + c * 16;
+        for (int c = 0; c < NCH; ++c) {
+          const int q0 = wg * QPT + c * 16;
           if (q0 < qext) {
             st_tile<2>(tile(FB_P + (q0 >> 6)), r, (q0 & 63) >> 3, pkp[c]);
             st_tile<2>(tile(FB_DS + (q0 >> 6)), r, (q0 & 63) >> 3, pkd[c]);
@@ -282,9 +306,11 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         }
         umma::fence_proxy_async();
         umma::mbar_arrive(barPD);
+        FTS(tsc, 7 + i * 6);
         // ---- end of a (head, key tile) block: drain dK / dV (and dQ after the head's last key tile)
         if (qt == MT - 1) {
           need_g(git + 1);
+          FTS(tsc, 8 + i * 6);
           const int col0 = h * D + wg * CPT;
           {
             uint32_t rv[CPT], rk[CPT];
@@ -321,6 +347,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
           }
           umma::fence_before_sync();
           umma::mbar_arrive(barAF);
+          FTS(tsc, 9 + i * 6);
         }
       }
     }
@@ -341,12 +368,12 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 // TMEM is double buffered (2 x 256 columns): the control warp issues the score MMA of tile t+1 while the threads work on tile t,
 // and the epilogue of tile t-1 (which waits for its PV MMA) runs between the two passes of tile t.
 namespace {
-constexpr int FF_CT = 256, FF_THREADS = FF_CT + 32;
+constexpr int FF_CT = 128 * FA_NG, FF_THREADS = FF_CT + 32;
 constexpr int FF_Q = 0, FF_K = 2, FF_V = 4, FF_P = 6, FF_TILES = 10;
 constexpr int FF_OFF_MASK = FF_TILES * TILE_B;           // float [2][256]  (item parity)
-constexpr int FF_OFF_REDM = FF_OFF_MASK + 2 * 256 * 4;   // float [2 tile parity][2 halves][128]
-constexpr int FF_OFF_REDL = FF_OFF_REDM + 2 * 2 * 128 * 4;
-constexpr int FF_OFF_BAR = FF_OFF_REDL + 2 * 2 * 128 * 4;
+constexpr int FF_OFF_REDM = FF_OFF_MASK + 2 * 256 * 4;   // float [2 tile parity][FA_NG column groups][128]
+constexpr int FF_OFF_REDL = FF_OFF_REDM + 2 * FA_NG * 128 * 4;
+constexpr int FF_OFF_BAR = FF_OFF_REDL + 2 * FA_NG * 128 * 4;
 constexpr int FF_SMEM = FF_OFF_BAR + 128 + 1024;
 
 struct FAttnFwdDev {
@@ -359,7 +386,7 @@ struct FAttnFwdDev {
 template <int D>
 __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, FAttnFwdDev a) {
   pdl_grid_wait();
-  constexpr int NHG = 64 / D, CPT = D / 2;
+  constexpr int NHG = 64 / D, CPT = D / FA_NG;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* sMask = reinterpret_cast<float*>(smem + FF_OFF_MASK);
@@ -467,15 +494,17 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_c
     const uint32_t step = a.step + (a.d_step ? (uint32_t)(*a.d_step) : 0u);
     const Philox ph(a.seed);
     const int NC = (S16 + 31) >> 5;                  // 32-key chunks
-    const int c_lo = wg ? (NC + 1) / 2 : 0, c_hi = wg ? NC : (NC + 1) / 2;
+    const int c_lo = (wg * NC) / FA_NG, c_hi = ((wg + 1) * NC) / FA_NG;   // this thread's chunks (column group wg)
     uint32_t gt = 0, nitem = 0;
     // state of the previous tile (its epilogue runs inside the next tile's iteration)
     float prev_m = 0.f; int prev_qi = 0, prev_b = 0, prev_col = 0, prev_bn = 0; bool have_prev = false;
     auto epilogue = [&](uint32_t gtile) {
       MBAR_WAIT(barO, gtile & 1, 4);
       umma::fence_after_sync();
-      const float* rl = sRedL + (gtile & 1) * 256;
-      const float l = rl[row] + rl[128 + row];
+      const float* rl = sRedL + (gtile & 1) * (FA_NG * 128);
+      float l = 0.f;
+#pragma unroll
+      for (int q = 0; q < FA_NG; ++q) l += rl[q * 128 + row];
       uint32_t ro[CPT];
       tmem_ld_n(tlane + (gtile & 1) * 256 + (prev_col & 63), ro);
       umma::tmem_ld_wait();
@@ -495,7 +524,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_c
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++nitem) {
       const int b = item / G, g = item % G;
       float* mk = sMask + (nitem & 1) * 256;
-      mk[tid] = tid < S ? (a.mask[(size_t)b * S + tid] != 0 ? 0.f : -1e9f * kLog2e) : -INFINITY;
+      if (tid < 256) mk[tid] = tid < S ? (a.mask[(size_t)b * S + tid] != 0 ? 0.f : -1e9f * kLog2e) : -INFINITY;
       // (made visible by the named barrier of the first tile's max exchange)
       for (int t = 0; t < n_t; ++t, ++gt) {
         const int h = t / MT, mt = t % MT;
@@ -515,10 +544,12 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) mloc = fmaxf(mloc, fmaf(__uint_as_float(rs[j]), c1, mk[c * 32 + j]));
         }
-        float* rm = sRedM + (gt & 1) * 256;
+        float* rm = sRedM + (gt & 1) * (FA_NG * 128);
         rm[wg * 128 + row] = mloc;
         named_bar_sync(1, FF_CT);
-        const float m = fmaxf(rm[row], rm[128 + row]);
+        float m = rm[row];
+#pragma unroll
+        for (int q = 1; q < FA_NG; ++q) m = fmaxf(m, rm[q * 128 + row]);
         // ---- epilogue of the previous tile (its PV MMA ran during pass 1)
         if (have_prev) epilogue(gt - 1);
         // ---- pass 2: probabilities -> P tiles
@@ -558,7 +589,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_c
           pack_n<32>(p, pk);
           st_tile<4>(tile(FF_P + (key0 >> 6)), row, (key0 & 63) >> 3, pk);
         }
-        sRedL[(gt & 1) * 256 + wg * 128 + row] = lsum;
+        sRedL[(gt & 1) * (FA_NG * 128) + wg * 128 + row] = lsum;
         umma::fence_before_sync();
         umma::fence_proxy_async();
         umma::mbar_arrive(barP);
@@ -650,5 +681,15 @@ cudaError_t launch_fattn_fwd(const AttnArgs& a, cudaStream_t st) {
   }
   return cudaGetLastError();
 }
+
+#ifdef FATTN_DEBUG
+extern "C" void b4r_fattn_dump_ts() {
+  unsigned long long h[128];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, g_fattn_ts, sizeof(h));
+  unsigned long long t0 = h[0];
+  for (int i = 0; i < 128; ++i) if (h[i]) printf("ts %3d %8.2f us\n", i, (double)((long long)(h[i] - t0)) / 1e3);
+}
+#endif
 
 }  // namespace b4r

@@ -13,7 +13,8 @@ namespace b4r {
 template <int H>
 __global__ void __launch_bounds__(128) rank_candidates_kernel(const bf16* __restrict__ t, int ldt, const bf16* __restrict__ E,
                                                               const float* __restrict__ vbias, const int64_t* __restrict__ cand,
-                                                              const int64_t* __restrict__ gt, int M, int C,
+                                                              const int64_t* __restrict__ gt, int M, int C, int V,
+                                                              const int* __restrict__ d_counts,
                                                               int64_t* __restrict__ ranking, float* __restrict__ scores,
                                                               int* __restrict__ rank, unsigned long long* __restrict__ hist) {
   pdl_grid_sync();
@@ -21,6 +22,10 @@ __global__ void __launch_bounds__(128) rank_candidates_kernel(const bf16* __rest
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x * 4 + warp;
   if (m >= M) return;
+  if (d_counts && m >= d_counts[0]) {   // no selected slot behind this row (caller passed more candidate lists than slots): rank 0
+    if (lane == 0 && rank) rank[m] = 0;
+    return;
+  }
   long long* s_id = reinterpret_cast<long long*>(smem_raw) + (size_t)warp * C;
   float* s_sc = reinterpret_cast<float*>(reinterpret_cast<long long*>(smem_raw) + (size_t)4 * C) + (size_t)warp * C;
   // the slot's hidden row, fp32, in shared memory (read as a broadcast by every lane)
@@ -34,6 +39,11 @@ __global__ void __launch_bounds__(128) rank_candidates_kernel(const bf16* __rest
   // gathers of the slot in flight at once)
   for (int c = lane; c < C; c += 32) {
     const long long id = cand[(size_t)m * C + c];
+    if (id < 0 || id >= V) {   // not an item of this model's catalogue (e.g. a sampler built over a larger vocabulary): ranked last
+      s_sc[c] = -INFINITY;
+      s_id[c] = id;
+      continue;
+    }
     const uint4* row = reinterpret_cast<const uint4*>(E + (size_t)id * H);
     float a4[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains; summed in a fixed order
 #pragma unroll
@@ -74,15 +84,15 @@ __global__ void __launch_bounds__(128) rank_candidates_kernel(const bf16* __rest
 }
 
 cudaError_t launch_rank_candidates(const bf16* t, int ldt, const bf16* E, const float* vbias, const int64_t* cand,
-                                   const int64_t* gt, int M, int C, int H, int64_t* ranking, float* scores,
-                                   int* rank, unsigned long long* hist, cudaStream_t st) {
+                                   const int64_t* gt, int M, int C, int H, int V, const int* d_counts, int64_t* ranking,
+                                   float* scores, int* rank, unsigned long long* hist, cudaStream_t st) {
   if (M <= 0) return cudaSuccess;
   size_t smem = (size_t)4 * C * (sizeof(long long) + sizeof(float)) + (size_t)4 * H * sizeof(float);
   int grid = (M + 3) / 4;
 #define B4R_RK(HH)                                                                                            \
   case HH:                                                                                                    \
     { static size_t cap_##HH = 0; if (smem > cap_##HH) { cudaFuncSetAttribute(rank_candidates_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cap_##HH = smem; } } \
-    launch_pdl(rank_candidates_kernel<HH>, dim3(grid), dim3(128), smem, st, t, ldt, E, vbias, cand, gt, M, C, ranking, scores, rank, hist); \
+    launch_pdl(rank_candidates_kernel<HH>, dim3(grid), dim3(128), smem, st, t, ldt, E, vbias, cand, gt, M, C, V, d_counts, ranking, scores, rank, hist); \
     break;
   switch (H) {
     B4R_RK(64)

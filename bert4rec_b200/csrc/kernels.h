@@ -321,10 +321,11 @@ cudaError_t launch_head_bwd_fused(const float* dt_part, int nsplit, size_t split
 
 // ------------------------------------------------------------------ ranking (k_rank.cu)
 // scores[m][c] = t[m] . E[cand[m][c]] + vbias[cand[m][c]] ; ranking = stable descending order (lower index first on ties)
-// rank[m] = 1 + position of the first candidate equal to gt[m] ; hist[r] += 1
+// rank[m] = 1 + position of the first candidate equal to gt[m] ; hist[r] += 1.  Candidate ids outside [0, V) score -inf (ranked
+// last); rows at or beyond d_counts[0] (the number of selected slots, device side; optional) get rank 0 and are not scored.
 cudaError_t launch_rank_candidates(const bf16* t, int ldt, const bf16* E, const float* vbias, const int64_t* cand,
-                                   const int64_t* gt, int M, int C, int H, int64_t* ranking, float* scores,
-                                   int* rank, unsigned long long* hist, cudaStream_t st);
+                                   const int64_t* gt, int M, int C, int H, int V, const int* d_counts, int64_t* ranking,
+                                   float* scores, int* rank, unsigned long long* hist, cudaStream_t st);
 // metric sums from a rank histogram: out = {n, ndcg@k.., hr@k.., map} in fp64
 cudaError_t launch_metrics_from_hist(const unsigned long long* hist, int max_rank, const int* ks, int nk,
                                      double* out, cudaStream_t st);

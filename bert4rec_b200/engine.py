@@ -34,6 +34,11 @@ def dl_view(t):
     return v
 
 
+def _dl_ptr(t):
+    """Device pointer of an input tensor handed over as a DLPack capsule (checked by the C ABI's adapter: CUDA, row-major)."""
+    return C.c_void_p(dl_view(t).data) if t is not None else C.c_void_p(0)
+
+
 class ParamStore:
     """Flat fp32 master parameters + bf16 shadow + (optionally) gradient / Adam moment buffers on one device."""
 
@@ -62,6 +67,7 @@ class ParamStore:
         self.m = self.v = None
         self.step_counter = None
         self.sessions = {}
+        self.generation = 0     # bumped whenever sessions (and their workspaces) are re-created: captured graphs are stale
 
     # ---- hyper-parameters
     @property
@@ -83,9 +89,11 @@ class ParamStore:
             self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
             self.adam_scratch = torch.zeros(self.lib.b4r_adamw_scratch_floats(), dtype=torch.float32, device=self.device)
             self.lr_out = torch.zeros(2, dtype=torch.float32, device=self.device)
-            for s in self.sessions.values():
-                s.close()
-            self.sessions = {}
+            if self.sessions:
+                for s in self.sessions.values():
+                    s.close()
+                self.sessions = {}
+                self.generation += 1
 
     # ---- views
     def seg(self, name, buf=None):
@@ -220,12 +228,12 @@ class Session:
         assert ids.dtype == torch.int64 and mask.dtype == torch.int64 and ids.is_contiguous() and mask.is_contiguous()
         assert tuple(ids.shape) == (self.B, self.S), (ids.shape, self.B, self.S)
         self._keep = [ids, mask]
-        check(self.lib.b4r_encode(self.h, _ptr(ids), _ptr(mask), int(bool(training)), int(seed), int(step),
+        check(self.lib.b4r_encode(self.h, _dl_ptr(ids), _dl_ptr(mask), int(bool(training)), int(seed), int(step),
                                   _ptr(step_counter), _stream()))
 
     def select(self, positions, ids=None, weights=None, mode=0, want_aux=False):
         self._keep += [positions, ids, weights]
-        check(self.lib.b4r_mlm_select(self.h, _ptr(positions), _ptr(ids), _ptr(weights), mode, int(want_aux), _stream()))
+        check(self.lib.b4r_mlm_select(self.h, _dl_ptr(positions), _dl_ptr(ids), _dl_ptr(weights), mode, int(want_aux), _stream()))
 
     def transform(self):
         check(self.lib.b4r_mlm_transform(self.h, _stream()))
@@ -257,7 +265,7 @@ class Session:
         ranking = torch.empty(n, Cn, dtype=torch.int64, device=dev) if want_ranking else None
         scores = torch.empty(n, Cn, dtype=torch.float32, device=dev) if want_scores else None
         rank = torch.zeros(n, dtype=torch.int32, device=dev)
-        check(self.lib.b4r_rank_candidates(self.h, _ptr(cand), _ptr(gt), n, Cn, _ptr(ranking), _ptr(scores), _ptr(rank),
+        check(self.lib.b4r_rank_candidates(self.h, _dl_ptr(cand), _dl_ptr(gt), n, Cn, _ptr(ranking), _ptr(scores), _ptr(rank),
                                            _ptr(hist), _stream()))
         return ranking, scores, rank
 

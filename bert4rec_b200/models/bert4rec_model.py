@@ -45,6 +45,31 @@ class History:
             self.history.setdefault(k, []).append(v)
 
 
+class _PinnedRing:
+    """A few pinned host buffers used round-robin as the source of asynchronous H2D copies.  A buffer is only rewritten after
+    the copy that last read it has completed (CUDA event recorded behind that copy): the host may run many steps ahead of
+    the stream (lazy metrics, graph replays), and a single staging buffer would be overwritten while its copy is pending."""
+
+    def __init__(self, make, depth=3):
+        self._make, self._depth, self._slots, self._next = make, depth, [], 0
+
+    def acquire(self):
+        """-> (buffer(s), release): fill the buffers, enqueue the copy, then call release() on the copy's stream."""
+        if len(self._slots) < self._depth:
+            slot = [self._make(), None]
+            self._slots.append(slot)
+        else:
+            slot = self._slots[self._next]
+            self._next = (self._next + 1) % self._depth
+            if slot[1] is not None:
+                slot[1].synchronize()
+        def release(slot=slot):
+            if slot[1] is None:
+                slot[1] = torch.cuda.Event()
+            slot[1].record()
+        return slot[0], release
+
+
 class StepMetrics(collections.abc.Mapping):
     """Lazy view of the device-side running metrics (Keras ``{m.name: m.result()}``, bert4rec_model.py:173).
     Values are read from the device (one small D2H copy, synchronising) on first access."""
@@ -120,6 +145,7 @@ class BERT4RecModel:
         self._shards = {}
         self.use_cuda_graph = True
         self._graphs = {}
+        self._store_gen = self.store.generation
         # data-parallel step as ONE graph with the NCCL all-reduce captured inside: opt-in only (B4R_DP_SINGLE_GRAPH=1).  Measured
         # 308 vs 316 us at N=2, but a live graph holding NCCL work hung the process at teardown on this stack.
         self._dp_single_graph = None if os.environ.get("B4R_DP_SINGLE_GRAPH") else False
@@ -149,14 +175,14 @@ class BERT4RecModel:
         key = (keys, tuple(shapes))
         st = self._staging.get(key)
         if st is None:
-            host = torch.empty(total, dtype=torch.int64).pin_memory()
+            host = _PinnedRing(lambda: torch.empty(total, dtype=torch.int64).pin_memory())
             dev = torch.empty(total, dtype=torch.int64, device=self.device)
             views, off = {}, 0
             for k, shp, n in zip(keys, shapes, sizes):   # the per-key device views are fixed: built once
                 views[k] = dev[off:off + n].view(shp)
                 off += n
             st = self._staging[key] = (host, dev, views)
-        host, dev, views = st
+        host_ring, dev, views = st
         if keys == _STAGED_KEYS and not any(v.is_cuda for v in vals) and os.environ.get("B4R_NO_PACKED_H2D") is None:
             # host batch of a train / test step: compact transfer (ids / positions / labels as int32, the 0/1 arrays as bytes: 2.9x
             # fewer PCIe bytes than the int64 tensors), ONE H2D copy, widened on the device into the persistent int64 views
@@ -164,16 +190,20 @@ class BERT4RecModel:
             pk = self._packed.get(key)
             if pk is None:
                 nbytes = self.store.lib.b4r_packed_inputs_bytes(n_tok, n_pred)
-                hp = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
                 n32 = n_tok + 2 * n_pred
-                h32 = hp[: 4 * n32].view(torch.int32)
-                pk = self._packed[key] = (hp, torch.empty(nbytes, dtype=torch.uint8, device=self.device),
-                                          (h32[:n_tok], h32[n_tok:n_tok + n_pred], h32[n_tok + n_pred:]),
-                                          (hp[4 * n32: 4 * n32 + n_tok], hp[4 * n32 + n_tok:]))
-            hp, dp, (h_ids, h_pos, h_mlm), (h_mask, h_w) = pk
+
+                def make():
+                    hp = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+                    h32 = hp[: 4 * n32].view(torch.int32)
+                    return (hp, (h32[:n_tok], h32[n_tok:n_tok + n_pred], h32[n_tok + n_pred:]),
+                            (hp[4 * n32: 4 * n32 + n_tok], hp[4 * n32 + n_tok:]))
+                pk = self._packed[key] = (_PinnedRing(make), torch.empty(nbytes, dtype=torch.uint8, device=self.device))
+            ring, dp = pk
+            (hp, (h_ids, h_pos, h_mlm), (h_mask, h_w)), release = ring.acquire()   # waits for the copy that last read this buffer
             h_ids.copy_(vals[0].reshape(-1)); h_mask.copy_(vals[1].reshape(-1))
             h_pos.copy_(vals[2].reshape(-1)); h_mlm.copy_(vals[3].reshape(-1)); h_w.copy_(vals[4].reshape(-1))
             dp.copy_(hp, non_blocking=True)
+            release()
             from bert4rec_b200 import _lib
             import ctypes as C
             _lib.check(self.store.lib.b4r_unpack_inputs(
@@ -200,6 +230,7 @@ class BERT4RecModel:
         if all_cuda:
             torch.cat([v.reshape(-1).to(torch.int64) for v in vals], out=dev)
         else:
+            host, release = host_ring.acquire()
             if all(v.dtype == torch.int64 for v in vals):
                 torch.cat([v.reshape(-1) for v in vals], out=host)   # one packed host copy into the pinned buffer
             else:
@@ -208,6 +239,7 @@ class BERT4RecModel:
                     host[off:off + n].copy_(v.reshape(-1))           # dtype-converting host copy
                     off += n
             dev.copy_(host, non_blocking=True)   # ONE H2D copy (five separate small copies measured slower)
+            release()
         return views
 
     @staticmethod
@@ -295,10 +327,19 @@ class BERT4RecModel:
             if phase is None or k == phase:
                 b.zero_()
 
+    def _check_graphs(self):
+        """Captured graphs reference session workspaces: drop them when the store re-created its sessions (compile() after an
+        evaluation allocates the gradient buffers and rebuilds every session)."""
+        if self._store_gen != self.store.generation:
+            self._graphs.clear()
+            self._graph_inputs = {}
+            self._store_gen = self.store.generation
+
     def train_step(self, inputs):
         """fwd(training) -> fused CE -> backward -> [NCCL allreduce] -> clip + AdamW (bert4rec_model.py:151-173)."""
         if self.optimizer is None:
             raise RuntimeError("compile() the model (or trainer.initialize_model()) before train_step")
+        self._check_graphs()
         # Device-resident int64 inputs are consumed IN PLACE: the captured graph is keyed by their addresses (a training
         # loop cycling over a cached, device-resident dataset replays with no copy at all).  Host inputs, and device
         # inputs once more than 8 address sets have been seen, go through the persistent staging buffer.
@@ -540,11 +581,14 @@ class BERT4RecModel:
         key = (name, tuple(t.shape))
         st = self._staging.get(key)
         if st is None:
-            st = self._staging[key] = (torch.empty(tuple(t.shape), dtype=torch.int64).pin_memory(),
-                                       torch.empty(tuple(t.shape), dtype=torch.int64, device=self.device))
-        host, dev = st
+            shape = tuple(t.shape)
+            st = self._staging[key] = (_PinnedRing(lambda: torch.empty(shape, dtype=torch.int64).pin_memory()),
+                                       torch.empty(shape, dtype=torch.int64, device=self.device))
+        ring, dev = st
+        host, release = ring.acquire()
         host.copy_(t)
         dev.copy_(host, non_blocking=True)
+        release()
         return dev
 
     def rank_candidates(self, encoder_input, candidates, ground_truth=None, want_ranking=False, hist=None):
@@ -553,6 +597,7 @@ class BERT4RecModel:
         ranks int32 [n_slots]) as device tensors.  The launch sequence (encoder forward, slot selection, MLM
         transform, fused gather-dot + rank) is captured per set of input buffers and replayed; the returned tensors
         are the graph's output buffers, valid until the next call with the same buffers."""
+        self._check_graphs()
         keys = ("input_word_ids", "input_mask", "masked_lm_positions") + \
                (("masked_lm_weights",) if "masked_lm_weights" in encoder_input else ())
         d = self._stage(encoder_input, keys)

@@ -98,7 +98,9 @@ int b4r_adamw_step(float* params, void* shadow_bf16, const float* grads, float* 
 /* BERT4RecModel.rank_items with per-slot candidate lists (bert4rec_model.py:224-234) + rank lookup
  * (bert4rec_evaluator.py:112-117).  cand: int64 [n_slots, C]; gt: int64 [n_slots] or NULL.
  * ranking_out int64 [n_slots, C] (optional), scores_out fp32 [n_slots, C] (optional), rank_out int32 [n_slots]
- * (1-based, 0 if gt absent), hist: uint64 [C+1] rank histogram, accumulated (optional). */
+ * (1-based, 0 if gt absent), hist: uint64 [C+1] rank histogram, accumulated (optional).
+ * Candidate ids outside [0, vocab_size) are scored -inf (ranked last, never dereferenced); rows at or beyond the number of
+ * slots the last b4r_mlm_select selected get rank 0 and are not scored. */
 int b4r_rank_candidates(b4r_session* s, const int64_t* cand, const int64_t* gt, int n_slots, int C,
                         int64_t* ranking_out, float* scores_out, int32_t* rank_out, uint64_t* hist, void* stream);
 /* rank_items(items=None) for evaluation: 1-based rank of the label of every selected row over the vocabulary shard
