@@ -147,6 +147,14 @@ def train_flops(w, m_valid):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_sample_batch(w):
+    """Bounded CPU sample of the workload: whole batches of the small configs, a slice of the big ones (seconds per step)."""
+    tok = w["batch"] * w["seq_len"] * w["hidden_size"] * w["num_layers"]
+    if tok <= 256 * 50 * 64 * 2:
+        return w["batch"]
+    return 32 if w["hidden_size"] >= 256 else 64
+
+
 def cpu_reference(w, steps, warmup, sample_batch=None):
     """The reference's TF2 path restated on the CPU (oracle/model.py), fp32, all host threads."""
     import torch
@@ -170,12 +178,36 @@ def cpu_reference(w, steps, warmup, sample_batch=None):
     return b["batch"] / (ms / 1e3), ms, b["batch"]
 
 
+def cpu_eval_reference(w, sample_batch, reps=2):
+    """The reference's evaluation path on the CPU: BERT4RecModel.rank_items (full [B,P,V] logits, gather of the 101 candidates,
+    stable descending sort per slot) + the rank lookup of BERT4RecEvaluator.evaluate_batch; prebuilt candidates."""
+    import torch
+    from oracle import model as om, host_ops
+    torch.set_num_threads(os.cpu_count())
+    b = dict(w); b["batch"] = sample_batch
+    cfg = om.Config(**{k: w[k] for k in ENC_KEYS})
+    params = om.init_params(cfg, 0)
+    batch = synth_batches(b, 1, seed=1000, eval_mode=True)[0]
+    gt = batch["masked_lm_ids"][:, 0].numpy()
+    cand = np.random.RandomState(5).randint(3, w["vocab_size"], size=(sample_batch, 101)).astype(np.int64)
+    cand[:, 100] = gt
+    items = [[cand[i].tolist()] for i in range(sample_batch)]
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        rk = om.rank_items(params, cfg, batch, items)
+        _ = [host_ops.rank_of(rk[i][0].numpy(), int(gt[i])) for i in range(sample_batch)]
+        ts.append(time.perf_counter() - t0)
+    t = float(np.min(ts))
+    return sample_batch / t, t * 1e3
+
+
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count()
-    sample = min(w["batch"], 64) if w["seq_len"] >= 200 else w["batch"]
+    sample = cpu_sample_batch(w)
     value, ms, bs = cpu_reference(w, args.steps, args.warmup, sample_batch=sample)
     line = {"impl": "reference", "metric": "train masked-seq/s", "value": value, "unit": "seq/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -188,26 +220,30 @@ def run_reference(args, w):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
-def run_b200(args, w):
-    import torch
-    import torch.distributed as dist
+def build_model(w, dev, dropout=None):
     from bert4rec_b200 import trainers
     from bert4rec_b200.models import BERT4RecModel
     from bert4rec_b200.models.components import networks
-    from bert4rec_b200.evaluation import BERT4RecEvaluator
-    from bert4rec_b200.dataloaders import samplers
+    kw = {k: w[k] for k in ENC_KEYS}
+    if dropout is not None:
+        kw.update(output_dropout=dropout, attention_dropout=dropout)
+    model = BERT4RecModel(networks.Bert4RecEncoder(**kw, device=dev, seed=0))
+    trainers.get("bert4rec", model=model).initialize_model()  # AdamW defaults, masked CE, [sparse_categorical_accuracy, masked_accuracy]
+    return model
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = f"cuda:{local}"
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
-    enc = networks.Bert4RecEncoder(**{k: w[k] for k in ENC_KEYS}, device=dev, seed=0)
-    model = BERT4RecModel(enc)
-    trainer = trainers.get("bert4rec", model=model)
-    trainer.initialize_model()  # AdamW defaults, masked CE, [sparse_categorical_accuracy, masked_accuracy]
+
+def working_set_bytes(model, sess):
+    return int(sess.ws.numel()) + int(model.store.params.numel()) * 18
+
+
+def measure(args, w, dev, world, rank, min_seconds, with_eval=True, clocks=None):
+    """Timed train steps (device-resident inputs -> `value`; pinned host inputs + D2H loss read, wall clock -> `e2e`) and the
+    100-negative evaluation of one workload.  Every rank runs this; numbers are the max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from bert4rec_b200.models import BERT4RecModel
+    model = build_model(w, dev)
+    B, S, P = w["batch"], w["seq_len"], w["max_pred"]
     n_b = 4
     host_batches = synth_batches(w, n_b, seed=rank)
     for b in host_batches:
@@ -215,15 +251,22 @@ def run_b200(args, w):
             b[k] = b[k].pin_memory()
     dev_batches = [{k: v.to(dev) for k, v in b.items()} for b in host_batches]
     m_valid = int((host_batches[0]["masked_lm_ids"] != 0).sum())
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    B, S, P = w["batch"], w["seq_len"], w["max_pred"]
     sess = model.store.session(B, S, P)
+    l2_bytes = 126 << 20
+    big = working_set_bytes(model, sess) > 4 * l2_bytes       # the step's working set dwarfs L2: nothing to flush
+    flush = None if big else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def rmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # launches per step: counted once on an eager (non-graph) step; a graph replay re-issues the same kernels
     model.use_cuda_graph = False
@@ -233,102 +276,293 @@ def run_b200(args, w):
     launches_per_step = sess.launch_count() - l_a + 2   # + sqnorm and adamw kernels
     model.use_cuda_graph = not args.no_graph
 
-    def timed(batches, read_loss):
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for i in range(args.warmup):
-            r = model.train_step(batches[i % n_b])
-            if read_loss:
-                _ = r["loss"]
-        barrier()
-        for i in range(args.steps):
-            flush.fill_(i & 0xFF)  # L2 flush between timed steps (untimed)
-            ev[i][0].record()
-            r = model.train_step(batches[i % n_b])
-            if read_loss:
-                _ = r["loss"]  # D2H read of the running loss (synchronises)
-            ev[i][1].record()
-        barrier()
-        launches = launches_per_step * args.steps
-        total_ms = sum(a.elapsed_time(b) for a, b in ev)
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), launches
+    for i in range(args.warmup):
+        model.train_step(dev_batches[i % n_b])
+    barrier()
+    # pilot: how many passes of --steps make the timed region at least `min_seconds`
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(3):
+        model.train_step(dev_batches[i % n_b])
+    e1.record(); torch.cuda.synchronize()
+    est = max(e0.elapsed_time(e1) / 3e3, 1e-6)
+    reps = int(rmax(max(1.0, np.ceil(min_seconds / (est * args.steps)))))
+    n_timed = reps * args.steps
 
-    clocks = ClockSampler(local)
-    if rank == 0:
+    # ---- device-resident inputs: CUDA events per step on the launching stream (the L2 flush, where used, is outside them)
+    if clocks is not None:
         clocks.start()
-    total_ms, launches = timed(dev_batches, read_loss=False)
-    clk = clocks.stop() if rank == 0 else None
-    e2e_ms, _ = timed(host_batches, read_loss=True)
-    value = world * B * args.steps / (total_ms / 1e3)
-    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_timed)]
+    barrier()
+    for i in range(n_timed):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        ev[i][0].record()
+        model.train_step(dev_batches[i % n_b])
+        ev[i][1].record()
+    barrier()
+    clk = clocks.stop() if clocks is not None else None
+    total_ms = rmax(sum(a.elapsed_time(b) for a, b in ev))
 
-    # ---- 100-negative evaluation (leave-one-out, RandomSampler negatives built once on the host)
+    # ---- end to end: pinned host batches through BERT4RecModel.train_step, H2D copy + D2H loss read inside; host wall clock,
+    # started after the (untimed) flush has completed
+    for i in range(3):
+        _ = model.train_step(host_batches[i % n_b])["loss"]
+    barrier()
+    wall = 0.0
+    for i in range(n_timed):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _ = model.train_step(host_batches[i % n_b])["loss"]     # D2H read of the running loss (synchronises)
+        wall += time.perf_counter() - t0
+    e2e_ms = rmax(wall * 1e3)
+    res = {"model": model, "sess": sess, "dev_batches": dev_batches, "host_batches": host_batches, "m_valid": m_valid,
+           "ms_per_step": total_ms / n_timed, "value": world * B * n_timed / (total_ms / 1e3),
+           "e2e_value": world * B * n_timed / (e2e_ms / 1e3), "e2e_ms_per_step": e2e_ms / n_timed, "timed_steps": n_timed,
+           "launches": launches_per_step * n_timed, "launches_per_step": launches_per_step, "clocks": clk,
+           "l2": ("working set %.1f GB per step >> 126 MB L2: no flush" % (working_set_bytes(model, sess) / 1e9)) if big
+                 else "256 MiB buffer written between timed steps (untimed)",
+           "h2d": BERT4RecModel._bytes_of(("input_word_ids", "input_mask", "masked_lm_positions", "masked_lm_ids", "masked_lm_weights"), host_batches[0])}
+    if with_eval:
+        res["eval"] = measure_eval(args, w, model, dev, world, rank, flush, barrier, rmax, min_seconds / 4)
+    return res
+
+
+def measure_eval(args, w, model, dev, world, rank, flush, barrier, rmax, min_seconds):
+    """100-negative evaluation (leave-one-out, prebuilt [B,101] candidates, ground truth last): sequences ranked per second."""
+    import torch
+    B, V = w["batch"], w["vocab_size"]
     eval_batches = synth_batches(w, 2, seed=1000 + rank, eval_mode=True)
-    V = w["vocab_size"]
     rng = np.random.RandomState(5)
-    ev_items = []
+    items = []
     for b in eval_batches:
         gt = b["masked_lm_ids"][:, 0].numpy()
         cand = rng.randint(3, V, size=(B, 101)).astype(np.int64)
         cand[:, 100] = gt
-        ev_items.append((b, {k: v.to(dev) for k, v in b.items()}, torch.from_numpy(cand).pin_memory(),
-                         torch.from_numpy(cand).to(dev), torch.from_numpy(gt.astype(np.int64)).pin_memory(),
-                         torch.from_numpy(gt.astype(np.int64)).to(dev)))
-    def eval_timed(use_dev):
-        for i in range(args.warmup):
-            hb, db, hc, dc, hg, dg = ev_items[i % 2]
-            model.rank_candidates(db if use_dev else hb, dc if use_dev else hc, dg if use_dev else hg)[1].cpu()
-        barrier()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for i in range(args.steps):
-            hb, db, hc, dc, hg, dg = ev_items[i % 2]
+        items.append((b, {k: v.to(dev) for k, v in b.items()}, torch.from_numpy(cand).pin_memory(), torch.from_numpy(cand).to(dev),
+                      torch.from_numpy(gt.astype(np.int64)).pin_memory(), torch.from_numpy(gt.astype(np.int64)).to(dev)))
+    for i in range(max(args.warmup, 3)):
+        hb, db, hc, dc, hg, dg = items[i % 2]
+        model.rank_candidates(db, dc, dg)[1].cpu()
+        model.rank_candidates(hb, hc, hg)[1].cpu()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(3):
+        model.rank_candidates(items[i % 2][1], items[i % 2][3], items[i % 2][5])
+    e1.record(); torch.cuda.synchronize()
+    est = max(e0.elapsed_time(e1) / 3e3, 1e-6)
+    n = int(rmax(max(args.steps, np.ceil(min_seconds / est))))
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    barrier()
+    for i in range(n):
+        hb, db, hc, dc, hg, dg = items[i % 2]
+        if flush is not None:
             flush.fill_(i & 0xFF)
-            ev[i][0].record()
-            _, rk = model.rank_candidates(db if use_dev else hb, dc if use_dev else hc, dg if use_dev else hg)
-            if not use_dev:
-                rk.cpu()
-            ev[i][1].record()
-        barrier()
-        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return world * B * args.steps / (float(t.item()) / 1e3)
-    eval_value = eval_timed(True)
-    eval_e2e = eval_timed(False)
+        ev[i][0].record()
+        model.rank_candidates(db, dc, dg)
+        ev[i][1].record()
+    barrier()
+    dev_ms = rmax(sum(a.elapsed_time(b) for a, b in ev))
+    wall = 0.0
+    for i in range(n):
+        hb, db, hc, dc, hg, dg = items[i % 2]
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.rank_candidates(hb, hc, hg)[1].cpu()          # ranks back on the host (synchronises)
+        wall += time.perf_counter() - t0
+    e2e_ms = rmax(wall * 1e3)
+    return {"metric": "100-neg eval seq/s", "unit": "seq/s", "value": world * B * n / (dev_ms / 1e3),
+            "e2e": {"value": world * B * n / (e2e_ms / 1e3), "unit": "seq/s",
+                    "h2d_bytes_per_step": int(8 * (2 * B * w["seq_len"] + 2 * B * w["max_pred"] + B * 101 + B)),
+                    "d2h_bytes_per_step": 4 * B},
+            "ms_per_batch": dev_ms / n, "batches_timed": n, "items": items}
 
+
+def eval_roofline(model, w, items, hbm, tf_burst, src, n=10):
+    """Per-kernel event times of the captured ranking pass; the roofline entry is its dominant kernel."""
+    import torch
+    sess = model.store.session(w["batch"], w["seq_len"], w["max_pred"])
+    model._graphs.clear()
+    sess.profile(True)
+    hb, db, hc, dc, hg, dg = items[0]
+    model.rank_candidates(db, dc, dg)         # eager pass + capture (with event nodes)
+    torch.cuda.synchronize()
+    sess.profile_report()
+    agg = {}
+    for _ in range(n):
+        model.rank_candidates(db, dc, dg)
+        for tag, (cnt, ms) in sess.profile_report().items():
+            c0, m0 = agg.get(tag, (0, 0.0))
+            agg[tag] = (c0 + cnt, m0 + ms)
+    sess.profile(False)
+    model._graphs.clear()
+    return roofline_from(agg, w, w["batch"], n, hbm, tf_burst, src, eval_mode=True)
+
+
+def dp_parity_probe(w, dev, world, rank, main_model):
+    """Untimed hardware check of the data-parallel step (N > 1): the flat gradient AFTER BERT4RecModel._all_reduce (NCCL, SUM over
+    ranks, valid-slot count riding along) against rank 0 recomputing the GLOBAL batch on one GPU.  Dropout off (the keep masks are
+    keyed by the row index inside a rank's batch), same weights everywhere."""
+    import torch
+    import torch.distributed as dist
+    B, S, P = w["batch"], w["seq_len"], w["max_pred"]
+    probe = build_model(w, dev, dropout=0.0)
+    probe.load_state_dict(main_model.state_dict())
+    batch = {k: v.to(dev) for k, v in synth_batches(w, 1, seed=500 + rank)[0].items()}
+    sess = probe.store.session(B, S, P)
+    probe.store.grads.zero_()
+    probe._fwd_bwd(sess, batch, probe._stats_buf("train"))
+    probe._all_reduce(sess)
+    torch.cuda.synchronize()
+    nt = probe.store.n_trainable
+    g_dp = probe.store.grads[: nt + 1].clone()
+    keys = ("input_word_ids", "input_mask", "masked_lm_positions", "masked_lm_ids", "masked_lm_weights")
+    gathered = {}
+    for k in keys:
+        buf = [torch.empty_like(batch[k]) for _ in range(world)] if rank == 0 else None
+        dist.gather(batch[k], buf, dst=0)
+        if rank == 0:
+            gathered[k] = torch.cat(buf, 0).contiguous()
+    out = None
+    if rank == 0:
+        single = build_model(w, dev, dropout=0.0)
+        single.distributed = False
+        single.load_state_dict(main_model.state_dict())
+        s1 = single.store.session(B * world, S, P)
+        single.store.grads.zero_()
+        single._fwd_bwd(s1, gathered, single._stats_buf("train"))
+        torch.cuda.synchronize()
+        g1 = single.store.grads[:nt]
+        n1 = float(s1.step_stats()[1])
+        views_dp, views_1 = single.store.tf_views(torch.cat([g_dp[:nt], single.store.grads[nt:]])), single.store.tf_views(single.store.grads)
+        worst, worst_name = 0.0, ""
+        gmax = max(float(v.norm()) for v in views_1.values())
+        for k, v in views_1.items():
+            if k.startswith("pooler"):
+                continue
+            err = float((views_dp[k].double() - v.double()).norm()) / (float(v.norm()) + 1e-5 * gmax)
+            if err > worst:
+                worst, worst_name = err, k
+        out = {"max_rel_l2_over_tensors": worst, "worst_tensor": worst_name, "global_rel_l2": float((g_dp[:nt].double() - g1.double()).norm() / g1.double().norm()),
+               "valid_slots_dp": float(g_dp[nt]), "valid_slots_single": n1, "global_batch": B * world,
+               "what": "flat gradient after the NCCL all-reduce vs rank 0 recomputing the global batch on one GPU (dropout off)"}
+        del single
+    del probe
+    torch.cuda.empty_cache()
+    return out
+
+
+def allreduce_time_us(model, dev, n=30):
+    """Device time of the step's gradient all-reduce alone (it is issued between the two graphs of a data-parallel step and is not
+    overlapped with compute, so this is the communication time a step exposes)."""
+    import torch
+    sess = None
+    for _ in range(5):
+        model._all_reduce(sess)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        model._all_reduce(sess)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+def run_b200(args, w, secondary):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    clocks = ClockSampler(local) if rank == 0 else None
+    r = measure(args, w, dev, world, rank, args.min_seconds, with_eval=True, clocks=clocks)
+    model, sess = r["model"], r["sess"]
+    comm = None
+    if world > 1:
+        comm = {"allreduce_floats": int(model.store.n_trainable + 1), "exposed_allreduce_us_per_step": allreduce_time_us(model, dev),
+                "note": "one NCCL all-reduce of the flat fp32 gradient (+ valid-slot count) between the forward/backward graph and the optimizer graph"}
+        t = torch.tensor([comm["exposed_allreduce_us_per_step"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        comm["exposed_allreduce_us_per_step"] = float(t.item())
+        parity = dp_parity_probe(w, dev, world, rank, model)
+    line = None
     if rank == 0:
         hbm, tf_burst, tf_sus, src = peaks()
-        flops = train_flops(w, m_valid)
-        step_ms = total_ms / args.steps
+        flops = train_flops(w, r["m_valid"])
+        step_ms = r["ms_per_step"]
         achieved_tf = flops / (step_ms / 1e3) / 1e12
+        ev = r["eval"]
         line = {
-            "metric": "train masked-seq/s", "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
+            "metric": "train masked-seq/s", "value": r["value"], "unit": "seq/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {**workload_config(w, world, m_valid),
-                       "l2": "256 MiB buffer written between timed steps (untimed); per-step CUDA events summed",
-                       "cuda_graph": not args.no_graph},
-            "e2e": {"value": e2e_value, "unit": "seq/s",
-                    "h2d_bytes_per_step": BERT4RecModel._bytes_of(("input_word_ids", "input_mask", "masked_lm_positions", "masked_lm_ids", "masked_lm_weights"), host_batches[0]),
-                    "d2h_bytes_per_step": 64},
-            "gpu_launches": launches,
-            "clocks": clk,
-            "eval": {"metric": "100-neg eval seq/s", "value": eval_value, "e2e": eval_e2e, "unit": "seq/s"},
+            "config": {**workload_config(w, world, r["m_valid"]), "l2": r["l2"], "cuda_graph": not args.no_graph,
+                       "timed_steps": r["timed_steps"],
+                       "timing": "CUDA events per step on the launching stream, %d passes of --steps (timed region >= %.1f s); e2e by host wall clock" % (r["timed_steps"] // args.steps, args.min_seconds)},
+            "e2e": {"value": r["e2e_value"], "unit": "seq/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": 64,
+                    "ms_per_step": r["e2e_ms_per_step"], "clock": "host wall clock around BERT4RecModel.train_step + loss read"},
+            "gpu_launches": r["launches"],
+            "clocks": r["clocks"],
             "step_flops": {"algorithmic_flops_per_step": flops, "achieved_tflops": achieved_tf,
                            "frac_of_bf16_sustained": achieved_tf / tf_sus, "peak_source": src},
         }
-        line["roofline"] = roofline_block(model, sess, w, dev_batches, args, hbm, tf_burst, src)
-        if world == 1:
-            line["host_path"] = host_path_block(w, model, eval_batches[0])
+    # rank-0-only passes below: no collective may be issued from here on (the other ranks are not stepping)
+    model.distributed = False
+    if rank == 0:
+        line["roofline"] = roofline_block(model, sess, w, r["dev_batches"], args, hbm, tf_burst, src)
+        ev_items = ev.pop("items")
+        ev["roofline"] = eval_roofline(model, w, ev_items, hbm, tf_burst, src)
         if world == 1 and not args.no_cpu_baseline:
-            sample = min(B, 64) if S >= 200 else B
+            sample = cpu_sample_batch(w)
+            v, ms = cpu_eval_reference(w, min(sample, 32))
+            ev["cpu_baseline"] = {"value": v, "unit": "seq/s", "cores": os.cpu_count(), "kind": "port",
+                                  "sample": f"rank_items + rank lookup of {min(sample, 32)} sequences x 101 candidates (CPU restatement: full [B,P,V] logits, stable sort), {ms:.0f} ms"}
+        line["eval"] = ev
+        if comm is not None:
+            line["comm"] = comm
+            line["dp_parity"] = parity
+        if world == 1:
+            line["host_path"] = host_path_block(w, model, synth_batches(w, 1, seed=1000, eval_mode=True)[0])
+        if world == 1 and not args.no_cpu_baseline:
+            sample = cpu_sample_batch(w)
             v, ms, bs = cpu_reference(w, 3, 1, sample_batch=sample)
             line["cpu_baseline"] = {"value": v, "unit": "seq/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"3 train steps of batch {bs} after 1 warm-up (CPU restatement of the TF2 path, torch fp32, {os.cpu_count()} threads), {ms:.0f} ms/step"}
+    else:
+        r["eval"].pop("items", None)
+    del model, sess, r
+    torch.cuda.empty_cache()
+    # ---- the other single-GPU BASELINE configurations, same method, shorter timed regions (N = 1 only)
+    if world == 1 and secondary:
+        line["configs"] = []
+        for name in secondary:
+            w2 = WORKLOADS[name]
+            r2 = measure(args, w2, dev, 1, 0, min(args.min_seconds, 0.25), with_eval=True)
+            hbm, tf_burst, tf_sus, src = peaks()
+            fl = train_flops(w2, r2["m_valid"])
+            r2["model"].distributed = False
+            e2 = r2["eval"]; e2.pop("items")
+            line["configs"].append({"workload": w2["name"], "value": r2["value"], "unit": "seq/s", "ms_per_step": r2["ms_per_step"],
+                                    "e2e": r2["e2e_value"], "timed_steps": r2["timed_steps"], "gpu_launches_per_step": r2["launches_per_step"],
+                                    "achieved_tflops": fl / (r2["ms_per_step"] / 1e3) / 1e12, "l2": r2["l2"],
+                                    "eval": {"value": e2["value"], "e2e": e2["e2e"]["value"], "unit": "seq/s"},
+                                    "roofline": roofline_block(r2["model"], r2["sess"], w2, r2["dev_batches"], args, hbm, tf_burst, src, brief=True)})
+            del r2
+            torch.cuda.empty_cache()
+    if rank == 0:
         emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -396,36 +630,27 @@ def host_path_block(w, model, eval_batch):
             "note": "bit-exact with the reference's python `random` / np.random streams (tests/test_host_native.py)"}
 
 
-def enc_ctas(w):
-    """CTAs of the fused encoder kernels: 128-row tiles of whole sequences in 32/64/128-row slots."""
-    S = w["seq_len"]
-    slot = 32 if S <= 32 else (64 if S <= 64 else 128)
-    g = 128 // slot
-    return (w["batch"] + g - 1) // g
-
-
-def kernel_work(tag, w, n_rows):
-    """Algorithmic (flops, bytes, bound) of ONE launch of the kernel behind a profile tag."""
+def kernel_work(tag, w, n_rows, eval_mode=False):
+    """Algorithmic (flops, bytes, bound) of ONE launch of the kernel behind a profile tag.
+    Bytes are the COMPULSORY traffic only: inputs read once + outputs written once; per-CTA partial buffers a kernel creates for
+    its own reductions are not algorithmic work and are not counted."""
     B, S, H, I, V, N = w["batch"], w["seq_len"], w["hidden_size"], w["inner_dim"], w["vocab_size"], w["num_attention_heads"]
     T, M, Vp, e = B * S, n_rows, (V + 127) // 128 * 128, 2
     L = w["num_layers"]
     saved = T * e * (H + L * (3 * H + 5 * H + 2 * I))   # activations the fused forward writes for backward
+    enc = L * T * (8 * H * H + 4 * S * H + 4 * H * I)
     t = {
-        # fused encoder forward: FLOPs of SURVEY 8d's encoder formula; bytes = ids + every saved activation once
-        "enc_fwd_fused": (L * T * (8 * H * H + 4 * S * H + 4 * H * I), T * 8 + saved + L * 4 * T * 4, "hbm"),
-        # fused encoder backward (+ embedding backward): 2x the forward FLOPs; bytes = saved activations read once +
-        # d(out) in + per-CTA weight/bias gradient partials out + item-table reduction
-        "enc_bwd_fused": (2 * L * T * (8 * H * H + 4 * S * H + 4 * H * I),
-                          saved + 2 * T * H * 4 + L * enc_ctas(w) * (4 * H * H + 2 * H * I + 9 * H + I) * 4 + L * 4 * T * 4, "hbm"),
+        # fused whole-encoder kernels: FLOPs of SURVEY 8d's encoder formula; bytes = ids + saved activations once (+ d(out) in the backward)
+        "enc_fwd_fused": (enc, T * 8 + (saved if not eval_mode else T * H * e * L) + L * 4 * T * 4, "hbm"),
+        "enc_bwd_fused": (2 * enc, saved + 2 * T * H * 4 + L * 4 * T * 4, "hbm"),
         "ce_fwd_umma": (2 * M * H * V, M * H * e + V * H * e + V * 4 + 3 * M * 4, "tensor"),
         # recompute passes: only the useful GEMM (dT = dl E, dE = dl^T t) is counted, not the recomputed logits
         "ce_bwd_umma:dT": (2 * M * H * V, M * H * e + V * H * e + V * 4 + M * H * 4, "tensor"),
         "ce_bwd_umma:dE": (2 * M * H * V, M * H * e + V * H * e + V * H * 4 + V * 4, "tensor"),
-        # one-pass generation: both useful GEMMs from one recompute
         "ce_bwd_fused": (4 * M * H * V, M * H * e + V * H * e + V * 4 + M * H * 4 + V * H * 4, "tensor"),
         "sqnorm+adamw": (0, 32 * (V * H + 64 * H + L * (4 * H * H + 2 * H * I) + H * H + V), "hbm"),
         "embed_ln_fwd": (0, T * (8 + 2 * H * e), "hbm"),
-        "embed_bwd": (0, T * (8 + H * e + H * 4) + T * H * 4, "hbm"),
+        "embed_bwd": (0, T * (8 + H * e + H * 4) + V * H * 4, "hbm"),
         "gemm:qkv": (2 * T * H * 3 * H, T * H * e + 3 * H * H * e + T * 3 * H * e, "tensor"),
         "attn_fwd": (4 * T * S * H, T * 3 * H * e + T * H * e + T * N * 4, "tensor"),
         "rowln:attn_out": (2 * T * H * H, 3 * T * H * e + H * H * e + T * H * e, "tensor"),
@@ -435,19 +660,21 @@ def kernel_work(tag, w, n_rows):
         "ce_fwd": (2 * M * H * V, M * H * e + V * H * e + V * 4 + 3 * M * 4, "tensor"),
         "ce_dlogits": (2 * M * H * V, M * H * e + V * H * e + V * 4 + M * Vp * e, "hbm"),
         "gemm:ce_dT": (2 * M * V * H, M * Vp * e + V * H * e + M * H * 4, "hbm"),
-        "wgrad:ce_dE": (2 * M * V * H, M * Vp * e + M * H * e + 2 * V * H * 4, "hbm"),
+        "wgrad:ce_dE": (2 * M * V * H, M * Vp * e + M * H * e + V * H * 4, "hbm"),
         "colsum:vbias": (0, M * Vp * e + V * 4, "hbm"),
         "ln_bwd": (0, T * H * (4 + e + 4 + e), "hbm"),
         "attn_bwd": (10 * T * S * H, T * 3 * H * e * 2 + 2 * T * H * e, "tensor"),
-        "wgrad:w2": (2 * T * I * H, T * I * e + T * H * e, "hbm"),
-        "wgrad:w1": (2 * T * I * H, T * I * e + T * H * e, "hbm"),
-        "wgrad:wo": (2 * T * H * H, 2 * T * H * e, "hbm"),
-        "wgrad:wqkv": (2 * T * H * 3 * H, T * H * e + T * 3 * H * e, "hbm"),
+        "wgrad:w2": (2 * T * I * H, T * I * e + T * H * e + I * H * 4, "tensor"),
+        "wgrad:w1": (2 * T * I * H, T * I * e + T * H * e + I * H * 4, "tensor"),
+        "wgrad:wo": (2 * T * H * H, 2 * T * H * e + H * H * 4, "tensor"),
+        "wgrad:wqkv": (2 * T * H * 3 * H, T * H * e + T * 3 * H * e + 3 * H * H * 4, "tensor"),
         "gemm:ffn2_dgrad_gelu": (2 * T * H * I, T * H * e + 2 * T * I * e + I * H * e, "tensor"),
         "gemm:ffn1_dgrad": (2 * T * I * H, T * I * e + 2 * T * H * 4, "tensor"),
         "gemm:attn_out_dgrad": (2 * T * H * H, 2 * T * H * e, "tensor"),
         "gemm:qkv_dgrad": (2 * T * 3 * H * H, T * 3 * H * e + 2 * T * H * 4, "tensor"),
         "colsum:bqkv": (0, T * 3 * H * e, "hbm"),
+        # evaluation: fused gather-dot over 101 candidates + stable rank (101 H e + 101 * 4 + H e per sequence + ids)
+        "rank_candidates": (2 * M * 101 * H, M * (101 * H * e + 101 * 4 + H * e + 101 * 8 + 4), "hbm"),
     }
     return t.get(tag, (0, 0, "hbm"))
 
@@ -476,44 +703,49 @@ def profile_steps(model, sess, batches, n, flush=None):
     return agg
 
 
-def roofline_block(model, sess, w, dev_batches, args, hbm, tf_burst, src):
-    """Per-kernel CUDA-event timing inside graph replays (profile_steps); the roofline entry is the kernel with the
-    largest share of the step among those with a stated algorithmic workload (kernel_work), + the breakdown."""
-    import torch
-    n = max(args.steps, 10)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_batches[0]["input_word_ids"].device)
-    model.distributed = False      # rank-0-only profiling pass: no collective (the other ranks are not stepping)
-    rep = profile_steps(model, sess, dev_batches, n, flush)
-    n_rows = int(sess.counts()[1])
+def roofline_from(rep, w, n_rows, n, hbm, tf_burst, src, eval_mode=False, brief=False):
+    """Roofline entry = the kernel with the largest share of the pass among those with a stated algorithmic workload; every
+    kernel of the breakdown carries BOTH fractions (tensor and HBM) of the measured peaks."""
     rows = sorted(((tag, cnt, tot) for tag, (cnt, tot) in rep.items()), key=lambda r: -r[2])
     total = sum(r[2] for r in rows)
     breakdown = []
-    for tag, cnt, tot in rows[:14]:
-        fl, by, bound = kernel_work(tag, w, n_rows)
+    for tag, cnt, tot in rows[:(6 if brief else 16)]:
+        fl, by, bound = kernel_work(tag, w, n_rows, eval_mode)
         ms = tot / cnt
-        breakdown.append({"kernel": tag, "launches_per_step": cnt / n, "avg_ms": ms, "share": tot / total,
-                          "tflops": fl / (ms / 1e3) / 1e12 if fl else 0.0, "gbs": by / (ms / 1e3) / 1e9 if by else 0.0})
-    known = [r for r in rows if kernel_work(r[0], w, n_rows)[0] or kernel_work(r[0], w, n_rows)[1]]
+        tf, gb = (fl / (ms / 1e3) / 1e12 if fl else 0.0), (by / (ms / 1e3) / 1e9 if by else 0.0)
+        breakdown.append({"kernel": tag, "launches_per_step": cnt / n, "avg_ms": ms, "share": tot / total, "bound": bound,
+                          "tflops": tf, "gbs": gb, "frac_tensor": tf / tf_burst, "frac_hbm": gb / hbm})
+    known = [r for r in rows if any(kernel_work(r[0], w, n_rows, eval_mode)[:2])]
     tag, cnt, tot = (known or rows)[0]
-    fl, by, bound = kernel_work(tag, w, n_rows)
+    fl, by, bound = kernel_work(tag, w, n_rows, eval_mode)
     ms = tot / cnt
-    if bound == "tensor":
-        ach, peak, unit = fl / (ms / 1e3) / 1e12, tf_burst, "TFLOP/s"
-    else:
-        ach, peak, unit = by / (ms / 1e3) / 1e9, hbm, "GB/s"
+    tf, gb = fl / (ms / 1e3) / 1e12, by / (ms / 1e3) / 1e9
+    ach, peak, unit = (tf, tf_burst, "TFLOP/s") if bound == "tensor" else (gb, hbm, "GB/s")
+    traffic = NCU_TRAFFIC.get((w["name"][:2], tag))
     return {"kernel": tag, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-            "traffic": NCU_TRAFFIC.get(tag) if w["name"].startswith("C2") else None, "peak_source": src, "launch_ms": ms, "share_of_step": tot / total,
-            "algorithmic_flops": fl, "algorithmic_bytes": by, "kernel_ms_per_step": total / n,
+            "frac_tensor": tf / tf_burst, "frac_hbm": gb / hbm, "traffic": traffic, "peak_source": src, "launch_ms": ms,
+            "share_of_step": tot / total, "algorithmic_flops": fl, "algorithmic_bytes": by, "kernel_ms_per_step": total / n,
             "timing": "CUDA events recorded as graph nodes around every launch, averaged over %d replays" % n,
             "breakdown": breakdown}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {   # bytes per launch at C2, profiles/r01_ncu_full_c2.md (cold-cache capture; the step itself runs L2-warm)
-    "enc_bwd_fused": 39_311_872 + 396_288,
-    "enc_fwd_fused": 1_029_376 + 227_328,
-    "ce_fwd_umma": 1_879_040,
-    "ce_bwd_fused": 1_999_616 + 809_472,
+def roofline_block(model, sess, w, dev_batches, args, hbm, tf_burst, src, brief=False):
+    """Per-kernel CUDA-event timing inside graph replays of the train step (profile_steps)."""
+    n = 10
+    model.distributed = False      # rank-0-only profiling pass: no collective (the other ranks are not stepping)
+    rep = profile_steps(model, sess, dev_batches, n)
+    return roofline_from(rep, w, int(sess.counts()[1]), n, hbm, tf_burst, src, brief=brief)
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), keyed by
+# (config, kernel tag); cold-cache captures
+NCU_TRAFFIC = {
+    ("C2", "enc_bwd_fused"): 39_311_872 + 396_288,       # profiles/r01_ncu_full_c2.md
+    ("C2", "enc_fwd_fused"): 1_029_376 + 227_328,
+    ("C2", "ce_fwd_umma"): 1_879_040,
+    ("C2", "ce_bwd_fused"): 1_999_616 + 809_472,
+    ("C4", "attn_bwd"): 555_940_864 + 279_664_128,       # profiles/r02_ncu_fattn_c4.md
+    ("C4", "attn_fwd"): 336_830_208 + 109_373_952,
 }
 
 
@@ -542,17 +774,23 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: c4 (the largest single-GPU BASELINE configuration) on 1 GPU, c3 (the data-parallel one) on N > 1")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="lower bound of the timed region (passes of --steps are repeated)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C1 / C2 entries of the `configs` array (N = 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
-    w = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    name = args.workload or ("c4" if max(world, args.gpus) == 1 else "c3")
+    w = WORKLOADS[name]
     if args.impl == "reference":
         run_reference(args, w)
     else:
-        run_b200(args, w)
+        secondary = [] if (args.no_secondary or args.workload) else [c for c in ("c1", "c2") if c != name]
+        run_b200(args, w, secondary)
 
 
 if __name__ == "__main__":
