@@ -1144,6 +1144,40 @@ extern "C" int b4r_rank_full_ext(b4r_session* s, const void* t_rows, const int32
   return 0;
 }
 
+// Full-catalogue top-k (rank_items(items=None) / apps.Recommender, bert4rec_model.py:235-236, apps/recommender.py:14-63): the K best
+// items of every row over the vocabulary shard [v_begin, v_end) as order-preserving keys (see k_ce.cu), best first.
+extern "C" size_t b4r_topk_scratch_bytes(int n_rows, int v_begin, int v_end, int K) {
+  if (n_rows < 1 || v_end <= v_begin || K < 1) return 0;
+  return topk_scratch_bytes(n_rows, v_end - v_begin, K);
+}
+extern "C" int b4r_topk_full(b4r_session* s, const void* t_rows, int n_rows, int v_begin, int v_end, int K, void* scratch,
+                             uint64_t* keys_out, int64_t* ids_out, float* scores_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!s || !scratch) return fail("null argument");
+  if (v_begin < 0 || v_end > s->V || v_begin >= v_end) return fail("bad vocabulary shard [%d, %d)", v_begin, v_end);
+  if (K < 1 || K > 128) return fail("K %d unsupported (1..128)", K);
+  if (n_rows < 1 || (!t_rows && n_rows > s->Mcap)) return fail("n_rows %d", n_rows);
+  if (!t_rows && join_select(s, st)) return 1;
+  CeArgs c = ce_args(s);
+  c.v_begin = v_begin; c.v_end = v_end;
+  if (t_rows) { c.t = reinterpret_cast<const bf16*>(t_rows); c.d_counts = nullptr; }
+  else c.d_counts = s->counts;
+  cudaError_t e = launch_topk_full(c, n_rows, K, reinterpret_cast<unsigned long long*>(scratch), reinterpret_cast<unsigned long long*>(keys_out),
+                                   reinterpret_cast<long long*>(ids_out), scores_out, st);
+  if (e != cudaSuccess) return fail("topk_full: %s (K %d may not fit shared memory at hidden %d)", cudaGetErrorString(e), K, s->H);
+  s->launches += 2;
+  return 0;
+}
+extern "C" int b4r_topk_merge(const uint64_t* keys_in, int nlists, int n_rows, int K, uint64_t* keys_out, int64_t* ids_out,
+                              float* scores_out, void* stream) {
+  if (!keys_in || nlists < 1 || n_rows < 1 || K < 1 || (long long)nlists * K > 8192) return fail("bad argument");
+  cudaError_t e = launch_topk_merge(reinterpret_cast<const unsigned long long*>(keys_in), nlists, n_rows, K, nullptr,
+                                    reinterpret_cast<unsigned long long*>(keys_out), reinterpret_cast<long long*>(ids_out), scores_out,
+                                    (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail("topk_merge: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 // The step's five int64 inputs travel host -> device in a compact form (ids / positions / labels as int32, the two 0/1 arrays as
 // bytes: 2.9x fewer PCIe bytes than the int64 tensors of the reference's batch dict) and are widened on the device into the
 // persistent int64 buffers the captured step reads.  packed = [int32 ids n_tok][int32 positions n_pred][int32 mlm_ids n_pred]

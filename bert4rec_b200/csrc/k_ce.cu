@@ -3,6 +3,7 @@
 // (tfm MaskedLM, bert4rec_model.py:76-81,143; MaskedSparseCategoricalCrossentropy / masked_accuracy,
 // trainer_utils.py:12-23,49-60) is never materialised in forward.
 // Generation 1: mma.sync tiles, A tile (64 rows of t) resident in smem, E streamed in 128-row tiles.
+#include <cstring>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -528,6 +529,161 @@ __global__ void __launch_bounds__(256) ce_count_kernel(CeDev a, const float* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------ full-catalogue top-k
+// rank_items(items=None) for serving / full-catalogue evaluation (bert4rec_model.py:235-236: tf.argsort over the vocabulary,
+// DESCENDING, stable = lower item id first among equal logits; apps/recommender.py:14-63): the K best items of every selected row
+// over the vocabulary shard [v_begin, v_end), without materialising any logits.  A (score, id) pair is ONE unsigned 64-bit key,
+//   key = order_preserving_bits(score) << 32 | (0xFFFFFFFF - id),
+// so "larger key" == "ranks earlier" (higher score, then lower id) and every selection / merge below is a plain integer maximum:
+// exact, order independent and therefore deterministic.
+//   topk_partial_kernel: grid (vocabulary splits, 64-row tiles); the score tiles of ce_fwd_kernel (mma.sync, E streamed through a
+//     double-buffered tile); each CTA keeps, per row, the K largest keys of its vocabulary range in shared memory (replace-the-minimum
+//     under a per-row lock; after the first few tiles almost every score fails the racy threshold pre-check and costs one compare).
+//   topk_merge_kernel: one CTA per row, bitonic sort of the nlists x K partial keys, first K -> sorted keys.  The same kernel merges
+//     the per-rank lists after the NCCL all-gather of a vocabulary-sharded catalogue.
+__host__ __device__ inline unsigned long long topk_key(float score, int id) {
+#ifdef __CUDA_ARCH__
+  unsigned u = __float_as_uint(score);
+#else
+  unsigned u; memcpy(&u, &score, 4);
+#endif
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)id);
+}
+constexpr int TOPK_MAX = 128;
+
+template <int H>
+__global__ void __launch_bounds__(256) topk_partial_kernel(CeDev a, int K, int n_rows_static, unsigned long long* __restrict__ part) {
+  pdl_grid_wait();
+  constexpr int LD = H + 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf16* sA = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sB0 = sA + CE_BM * LD;
+  bf16* sB1 = sB0 + CE_BN * LD;
+  float* sBias0 = reinterpret_cast<float*>(sB1 + CE_BN * LD);
+  float* sBias1 = sBias0 + CE_BN;
+  unsigned long long* sList = reinterpret_cast<unsigned long long*>(sBias1 + CE_BN);   // [64][K]
+  unsigned long long* sThr = sList + (size_t)CE_BM * K;                                  // [64] current minimum of a full list (0 until full)
+  int* sCnt = reinterpret_cast<int*>(sThr + CE_BM);                                      // [64]
+  int* sMinPos = sCnt + CE_BM;                                                           // [64]
+  int* sLock = sMinPos + CE_BM;                                                          // [64]
+  const int n_rows = a.d_counts ? min(n_rows_static, a.d_counts[0]) : n_rows_static;
+  const int m0 = blockIdx.y * CE_BM;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_m = warp & 3, warp_n = warp >> 2;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int ntiles = (a.v_end - a.v_begin + CE_BN - 1) / CE_BN;
+  const int tps = (ntiles + a.vsplits - 1) / a.vsplits;
+  const int tile_lo = blockIdx.x * tps, tile_hi = min(ntiles, tile_lo + tps);
+  unsigned long long* out = part + ((size_t)blockIdx.x * n_rows_static + m0) * K;        // [split][row][K]
+  if (m0 >= n_rows) return;
+  for (int i = tid; i < CE_BM; i += 256) { sThr[i] = 0ull; sCnt[i] = 0; sMinPos[i] = 0; sLock[i] = 0; }
+  constexpr int CH = H / 8;
+  for (int c = tid; c < CE_BM * CH; c += 256) {
+    const int r = c / CH, cc = (c % CH) * 8;
+    const bool ok = m0 + r < n_rows;
+    cp_async16(sA + r * LD + cc, a.t + (size_t)(ok ? m0 + r : 0) * a.ldt + cc, ok);
+  }
+  if (tile_lo < tile_hi) ce_load_b_tile<H>(a, a.v_begin + tile_lo * CE_BN, sB0, sBias0);
+  cp_async_commit();
+  for (int tile = tile_lo; tile < tile_hi; ++tile) {
+    const int buf = (tile - tile_lo) & 1;
+    bf16* sB = buf ? sB1 : sB0;
+    float* sBias = buf ? sBias1 : sBias0;
+    cp_async_wait<0>();
+    __syncthreads();
+    if (tile + 1 < tile_hi) ce_load_b_tile<H>(a, a.v_begin + (tile + 1) * CE_BN, buf ? sB0 : sB1, buf ? sBias0 : sBias1);
+    cp_async_commit();
+    float acc[8][4];
+    ce_tile_mma<H>(sA, sB, warp_m, warp_n, lane, acc);
+    const int v0 = a.v_begin + tile * CE_BN + warp_n * 64;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int cl = warp_n * 64 + nt * 8 + 2 * t4 + (e & 1);
+        const int col = v0 + nt * 8 + 2 * t4 + (e & 1);
+        const int rl = warp_m * 16 + g + (e >> 1) * 8;
+        if (col < a.v_end && m0 + rl < n_rows) {
+          const unsigned long long key = topk_key(acc[nt][e] + sBias[cl], col);
+          if (key > *reinterpret_cast<volatile unsigned long long*>(sThr + rl)) {
+            bool done = false;
+            while (!done) {                       // (lock taken and released inside one iteration: lanes of a warp may share a row)
+              if (atomicCAS(sLock + rl, 0, 1) == 0) {
+                __threadfence_block();
+                volatile unsigned long long* lst = sList + (size_t)rl * K;
+                const int cnt = *reinterpret_cast<volatile int*>(sCnt + rl);
+                bool rescan = false;
+                if (cnt < K) {
+                  lst[cnt] = key;
+                  *reinterpret_cast<volatile int*>(sCnt + rl) = cnt + 1;
+                  rescan = cnt + 1 == K;
+                } else if (key > *reinterpret_cast<volatile unsigned long long*>(sThr + rl)) {
+                  lst[*reinterpret_cast<volatile int*>(sMinPos + rl)] = key;
+                  rescan = true;
+                }
+                if (rescan) {
+                  unsigned long long mn = lst[0]; int mp = 0;
+                  for (int i = 1; i < K; ++i) { const unsigned long long x = lst[i]; if (x < mn) { mn = x; mp = i; } }
+                  *reinterpret_cast<volatile int*>(sMinPos + rl) = mp;
+                  *reinterpret_cast<volatile unsigned long long*>(sThr + rl) = mn;
+                }
+                __threadfence_block();
+                atomicExch(sLock + rl, 0);
+                done = true;
+              }
+            }
+          }
+        }
+      }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  for (int i = tid; i < CE_BM * K; i += 256) {
+    const int r = i / K, j = i % K;
+    if (m0 + r < n_rows) out[(size_t)r * K + j] = j < sCnt[r] ? sList[(size_t)r * K + j] : 0ull;
+  }
+}
+
+// keys_in: [nlists][n_rows][K] (0 = empty slot); one CTA per row: bitonic sort (descending) of the nlists*K keys padded to a power of
+// two, the first K -> keys_out [n_rows][K] and, if requested, ids_out int64 / scores_out fp32 (-1 / -inf for empty slots)
+__global__ void __launch_bounds__(256) topk_merge_kernel(const unsigned long long* __restrict__ keys_in, int nlists, int n_rows, int K,
+                                                         const int* __restrict__ d_counts, unsigned long long* __restrict__ keys_out,
+                                                         long long* __restrict__ ids_out, float* __restrict__ scores_out, int npow2) {
+  pdl_grid_wait();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* s = reinterpret_cast<unsigned long long*>(smem_raw);
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const bool live = !d_counts || row < d_counts[0];
+  const int total = nlists * K;
+  for (int i = tid; i < npow2; i += 256) {
+    unsigned long long k = 0ull;
+    if (live && i < total) k = keys_in[((size_t)(i / K) * n_rows + row) * K + (i % K)];
+    s[i] = k;
+  }
+  __syncthreads();
+  for (int size = 2; size <= npow2; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < npow2 / 2; i += 256) {
+        const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long x = s[lo], y = s[hi];
+        if (desc ? x < y : x > y) { s[lo] = y; s[hi] = x; }
+      }
+      __syncthreads();
+    }
+  for (int j = tid; j < K; j += 256) {
+    const unsigned long long k = s[j];
+    if (keys_out) keys_out[(size_t)row * K + j] = k;
+    if (ids_out) ids_out[(size_t)row * K + j] = k ? (long long)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull)) : -1ll;
+    if (scores_out) {
+      unsigned u = (unsigned)(k >> 32);
+      u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+      scores_out[(size_t)row * K + j] = k ? __uint_as_float(u) : -INFINITY;
+    }
+  }
+}
+
 static CeDev to_dev(const CeArgs& a) {
   CeDev d;
   d.t = a.t; d.ldt = a.ldt; d.E = a.E; d.vbias = a.vbias; d.labels = a.labels; d.row_w = a.row_w; d.row_mult = a.row_mult;
@@ -589,6 +745,55 @@ cudaError_t launch_ce_count(const CeArgs& a, const float* s_gt, int* beat, cudaS
   }
 #undef B4R_CC
   return cudaGetLastError();
+}
+
+
+int topk_splits(int n_rows, int v_len, int K) {
+  const int mt = (n_rows + CE_BM - 1) / CE_BM, ntiles = (v_len + CE_BN - 1) / CE_BN;
+  int vs = (2 * 148 + mt - 1) / mt;                 // about two waves of CTAs
+  if (vs > ntiles) vs = ntiles;
+  while (vs > 1 && (long long)vs * K > 4096) --vs;  // the merge sorts vs * K keys per row in shared memory
+  return vs < 1 ? 1 : vs;
+}
+size_t topk_scratch_bytes(int n_rows, int v_len, int K) { return (size_t)topk_splits(n_rows, v_len, K) * n_rows * K * sizeof(unsigned long long); }
+
+cudaError_t launch_topk_merge(const unsigned long long* keys_in, int nlists, int n_rows, int K, const int* d_counts,
+                              unsigned long long* keys_out, long long* ids_out, float* scores_out, cudaStream_t st) {
+  if (n_rows <= 0) return cudaSuccess;
+  int np2 = 2;
+  while (np2 < nlists * K) np2 <<= 1;
+  if (np2 > 8192) return cudaErrorInvalidValue;
+  static bool done = false;
+  if (!done) { cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8); done = true; }
+  launch_pdl(topk_merge_kernel, dim3(n_rows), dim3(256), (size_t)np2 * 8, st, keys_in, nlists, n_rows, K, d_counts, keys_out, ids_out, scores_out, np2);
+  return cudaGetLastError();
+}
+
+// keys_out [n_rows][K] sorted (best first) over [a.v_begin, a.v_end); scratch: topk_scratch_bytes(n_rows, v_len, K)
+cudaError_t launch_topk_full(const CeArgs& a, int n_rows, int K, unsigned long long* scratch, unsigned long long* keys_out,
+                             long long* ids_out, float* scores_out, cudaStream_t st) {
+  if (K < 1 || K > TOPK_MAX || n_rows < 1) return cudaErrorInvalidValue;
+  CeDev d = to_dev(a);
+  d.vsplits = topk_splits(n_rows, a.v_end - a.v_begin, K);
+  dim3 grid(d.vsplits, (n_rows + CE_BM - 1) / CE_BM);
+#define B4R_TK(HH)                                                                                         \
+  case HH: {                                                                                               \
+    size_t smem = (size_t)(CE_BM + 2 * CE_BN) * (HH + 8) * sizeof(bf16) + 2 * CE_BN * sizeof(float) + (size_t)CE_BM * K * 8 + CE_BM * (8 + 12); \
+    static size_t cap_##HH = 0;                                                                            \
+    if (smem > cap_##HH) { cudaError_t e = cudaFuncSetAttribute(topk_partial_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; cap_##HH = smem; } \
+    launch_pdl(topk_partial_kernel<HH>, dim3(grid), dim3(256), smem, st, d, K, n_rows, scratch);          \
+    break;                                                                                                 \
+  }
+  switch (a.H) {
+    B4R_TK(64)
+    B4R_TK(128)
+    B4R_TK(256)
+    default: return cudaErrorInvalidValue;
+  }
+#undef B4R_TK
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return launch_topk_merge(scratch, d.vsplits, n_rows, K, a.d_counts, keys_out, ids_out, scores_out, st);
 }
 
 cudaError_t launch_ce_finalize(const CeArgs& a, cudaStream_t st) {

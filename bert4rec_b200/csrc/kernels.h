@@ -237,6 +237,15 @@ cudaError_t launch_ce_dlogits(const CeArgs& a, cudaStream_t st);
 // full-catalogue rank counting (see k_ce.cu): beat[m] += #items of the shard that rank ahead of the ground truth
 cudaError_t launch_ce_count(const CeArgs& a, const float* s_gt, int* beat, cudaStream_t st);
 int ce_block_m();
+// full-catalogue top-k (k_ce.cu): the K best (score, id) of every row over [a.v_begin, a.v_end) as order-preserving u64 keys
+// (larger = ranks earlier: higher score, then lower id), sorted best first; K <= 128.  d_counts[0] (optional) bounds the live rows.
+int topk_splits(int n_rows, int v_len, int K);
+size_t topk_scratch_bytes(int n_rows, int v_len, int K);
+cudaError_t launch_topk_full(const CeArgs& a, int n_rows, int K, unsigned long long* scratch, unsigned long long* keys_out,
+                             long long* ids_out, float* scores_out, cudaStream_t st);
+// merge nlists sorted or unsorted key lists [nlists][n_rows][K] -> the K best per row (also the cross-rank merge of a sharded catalogue)
+cudaError_t launch_topk_merge(const unsigned long long* keys_in, int nlists, int n_rows, int K, const int* d_counts,
+                              unsigned long long* keys_out, long long* ids_out, float* scores_out, cudaStream_t st);
 // generation 2 (tcgen05 + TMA) forward; maps are created once per session on the host
 struct CeUmmaMaps {   // a: t rows, b: E rows (128-row boxes); a64 / b64: 64-row boxes (streamed operand of the hidden-256 backward)
   alignas(64) unsigned char a[128]; alignas(64) unsigned char b[128]; alignas(64) unsigned char a64[128]; alignas(64) unsigned char b64[128];

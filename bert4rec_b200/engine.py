@@ -269,6 +269,25 @@ class Session:
                                            _ptr(hist), _stream()))
         return ranking, scores, rank
 
+    def topk_full(self, k, v_begin=0, v_end=None, t_rows=None, n_rows=None, want_keys=False):
+        """The k best catalogue items of every selected row (or of the external bf16 rows ``t_rows``) over the vocabulary shard
+        [v_begin, v_end): (ids int64 [n, k], scores fp32 [n, k][, keys uint64-as-int64 [n, k]]), best first, lower id first among
+        equal scores; no logits are materialised (b4r_topk_full)."""
+        dev = self.store.device
+        v_end = self.store.V if v_end is None else v_end
+        n = int(n_rows if n_rows is not None else (t_rows.shape[0] if t_rows is not None else self.Mcap))
+        if t_rows is not None:
+            assert t_rows.dtype == torch.bfloat16 and t_rows.is_contiguous() and t_rows.shape[1] == self.store.H
+        nbytes = self.lib.b4r_topk_scratch_bytes(n, int(v_begin), int(v_end), int(k))
+        scratch = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
+        ids = torch.empty(n, k, dtype=torch.int64, device=dev)
+        scores = torch.empty(n, k, dtype=torch.float32, device=dev)
+        keys = torch.empty(n, k, dtype=torch.int64, device=dev) if want_keys else None
+        check(self.lib.b4r_topk_full(self.h, _ptr(t_rows), n, int(v_begin), int(v_end), int(k), _ptr(scratch), _ptr(keys), _ptr(ids),
+                                     _ptr(scores), _stream()))
+        self._keep_topk = scratch
+        return (ids, scores, keys) if want_keys else (ids, scores)
+
     def rank_full(self, n_rows, v_begin=0, v_end=None):
         beat = torch.zeros(max(n_rows, 1), dtype=torch.int32, device=self.store.device)
         check(self.lib.b4r_rank_full(self.h, v_begin, self.store.V if v_end is None else v_end, _ptr(beat), _stream()))
@@ -352,6 +371,16 @@ class Session:
             tag, cnt, ms = line.rsplit(" ", 2)
             out[tag] = (int(cnt), float(ms))
         return out
+
+
+def topk_merge(keys):
+    """keys: int64 view of the uint64 keys [nlists, n_rows, k] (per shard / per rank) -> (ids, scores) of the k best per row."""
+    assert keys.dtype == torch.int64 and keys.is_contiguous() and keys.dim() == 3
+    nl, n, k = keys.shape
+    ids = torch.empty(n, k, dtype=torch.int64, device=keys.device)
+    scores = torch.empty(n, k, dtype=torch.float32, device=keys.device)
+    check(_lib.load().b4r_topk_merge(_ptr(keys), nl, n, k, None, _ptr(ids), _ptr(scores), _stream()))
+    return ids, scores
 
 
 def shard_range(vocab, world, rank):

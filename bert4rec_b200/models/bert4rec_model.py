@@ -682,6 +682,52 @@ class BERT4RecModel:
         dist.all_reduce(beat, group=group)
         return beat[me, :n] + 1
 
+    def top_k_items(self, encoder_input, k, group=None, exclude=None):
+        """The ``k`` most probable catalogue items of every prediction slot: ``rank_items(items=None)[...][:k]`` of the reference
+        (bert4rec_model.py:235-236: argsort over the whole vocabulary, descending, lower id first among equal logits) without
+        materialising logits.  Returns (ids int64 [n_slots, k], scores fp32 [n_slots, k]) on the device, best first.
+        ``exclude``: optional list (per slot) of item ids never to return (apps.Recommender masks the user's history): the kernel is
+        asked for k + max(len) items and the excluded ones are dropped on the host side of the ranking.
+        With an initialised process group the catalogue is SHARDED over the ranks: the hidden rows of all ranks are
+        all-gathered, every rank selects the k best of its vocabulary slice for every row (``b4r_topk_full``), the per-rank lists
+        are all-gathered and merged (``b4r_topk_merge``: a key comparison, exact, lowest id first)."""
+        import torch.distributed as dist
+        from bert4rec_b200.engine import shard_range, topk_merge
+        sess, _ = self._encode_for_ranking(encoder_input)
+        n = int(sess.counts()[0])
+        extra = max((len(set(e)) for e in exclude), default=0) if exclude is not None else 0
+        kk = min(k + extra, self.store.V)
+        if kk > 128:
+            raise ValueError(f"top_k_items: k + excluded items = {kk} exceeds the kernel's limit of 128")
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if world == 1:
+            ids, scores = sess.topk_full(kk, n_rows=n)
+        else:
+            me = dist.get_rank(group)
+            cap, H = sess.Mcap, self.store.H
+            rows = torch.empty(world, cap, H, dtype=torch.bfloat16, device=self.device)
+            dist.all_gather_into_tensor(rows, sess.mlm_hidden().contiguous(), group=group)
+            lo, hi = shard_range(self.store.V, world, me)
+            if lo < hi:
+                _, _, keys = sess.topk_full(kk, lo, hi, t_rows=rows.view(world * cap, H), want_keys=True)
+            else:
+                keys = torch.zeros(world * cap, kk, dtype=torch.int64, device=self.device)
+            allk = torch.empty(world, world * cap, kk, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(allk, keys, group=group)
+            ids, scores = topk_merge(allk)
+            ids, scores = ids[me * cap: me * cap + n], scores[me * cap: me * cap + n]
+        if exclude is None:
+            return ids[:, :k], scores[:, :k]
+        ids_h, sc_h = ids.cpu(), scores.cpu()
+        out_i = torch.full((n, k), -1, dtype=torch.int64)
+        out_s = torch.full((n, k), -float("inf"))
+        for r in range(n):
+            ban = set(int(x) for x in exclude[r])
+            keep = [j for j in range(kk) if int(ids_h[r, j]) not in ban and int(ids_h[r, j]) >= 0][:k]
+            out_i[r, :len(keep)] = ids_h[r, keep]
+            out_s[r, :len(keep)] = sc_h[r, keep]
+        return out_i.to(self.device), out_s.to(self.device)
+
     def rank_items(self, encoder_input: dict, items: list = None):
         """Reference semantics (bert4rec_model.py:203-240): one ranking per slot whose ``masked_lm_weights`` is 1;
         with ``items`` (list per sequence of list per slot of candidate ids) the candidates sorted by descending

@@ -103,6 +103,19 @@ int b4r_adamw_step(float* params, void* shadow_bf16, const float* grads, float* 
  * slots the last b4r_mlm_select selected get rank 0 and are not scored. */
 int b4r_rank_candidates(b4r_session* s, const int64_t* cand, const int64_t* gt, int n_slots, int C,
                         int64_t* ranking_out, float* scores_out, int32_t* rank_out, uint64_t* hist, void* stream);
+/* rank_items(items=None) for serving (bert4rec_model.py:235-236: tf.argsort(DESCENDING) over the vocabulary, lower id first among
+ * equal logits; apps/recommender.py:14-63): the K (<= 128) best items of every row over the vocabulary shard [v_begin, v_end), no
+ * logits materialised.  t_rows: bf16 [n_rows, hidden] external hidden rows (e.g. all-gathered from other ranks) or NULL = the rows of
+ * the last b4r_mlm_select + b4r_mlm_transform.  keys_out uint64 [n_rows, K] (optional): (score, id) packed so that a LARGER key ranks
+ * EARLIER (order-preserving score bits << 32 | 0xFFFFFFFF - id; 0 = empty), best first -- lists of different shards / ranks are
+ * merged with b4r_topk_merge after an all-gather.  ids_out int64 [n_rows, K] / scores_out fp32 [n_rows, K] (optional; -1 / -inf = empty).
+ * scratch: b4r_topk_scratch_bytes(n_rows, v_begin, v_end, K) bytes of device memory. */
+size_t b4r_topk_scratch_bytes(int n_rows, int v_begin, int v_end, int K);
+int b4r_topk_full(b4r_session* s, const void* t_rows, int n_rows, int v_begin, int v_end, int K, void* scratch,
+                  uint64_t* keys_out, int64_t* ids_out, float* scores_out, void* stream);
+/* keys_in uint64 [nlists, n_rows, K] -> the K best keys per row, best first (nlists * K <= 8192) */
+int b4r_topk_merge(const uint64_t* keys_in, int nlists, int n_rows, int K, uint64_t* keys_out, int64_t* ids_out,
+                   float* scores_out, void* stream);
 /* rank_items(items=None) for evaluation: 1-based rank of the label of every selected row over the vocabulary shard
  * [v_begin, v_end): beat_out[i] += #items ranking ahead (caller zeroes; sum over shards + 1 = rank). */
 int b4r_rank_full(b4r_session* s, int v_begin, int v_end, int32_t* beat_out, void* stream);

@@ -229,3 +229,80 @@ def test_dlpack_capsule_through_the_c_abi():
     sess = model.store.session(4, 32, 6)
     with pytest.raises((_lib.B4RError, AssertionError)):
         sess.encode(b["input_word_ids"].t(), b["input_mask"])
+
+
+@pytest.mark.parametrize("H,N,V,k", [(64, 2, 1203, 10), (128, 4, 5003, 100), (256, 4, 2001, 37), (64, 2, 40007, 128)])
+def test_full_catalogue_top_k_is_the_head_of_the_stable_argsort(H, N, V, k):
+    """b4r_topk_full: ids / scores of the k best items per slot == the first k of the stable descending argsort of the kernel's own
+    logits (tf.argsort(DESCENDING) semantics: lower id first among equal logits, bert4rec_model.py:235-236); duplicate table rows
+    force exact ties; vocabulary shards merged with b4r_topk_merge give the same lists (the multi-GPU path)."""
+    from bert4rec_b200.engine import ParamStore, topk_merge
+    kw = dict(vocab_size=V, hidden_size=H, num_layers=1, num_attention_heads=N, max_sequence_length=24, inner_dim=2 * H)
+    store = ParamStore(device="cuda:0", **kw)
+    store.init_weights(5)
+    with torch.no_grad():
+        tv = store.tf_views()
+        E, vb = tv["word_embeddings/embeddings"], tv["cls/predictions/output_bias/bias"]
+        E.mul_(20.0)
+        vb.copy_((torch.randn(V, generator=torch.Generator().manual_seed(3)) * 0.1).cuda())
+        for a, b in ((7, 700), (8, 9), (V - 1, 11), (500, 501), (500, 502)):      # exact ties (same row, same bias)
+            E[b] = E[a]; vb[b] = vb[a]
+    store.sync_shadow()
+    B, S, P = 70, 24, 3
+    batch = make_batch(B, S, P, V, seed=4)
+    cb = to_cuda(batch)
+    sess = store.session(B, S, P)
+    sess.encode(cb["input_word_ids"], cb["input_mask"], training=False)
+    sess.select(cb["masked_lm_positions"], None, cb["masked_lm_weights"], mode=1)
+    sess.transform()
+    n = int(sess.counts()[0])
+    ids, scores = sess.topk_full(k, n_rows=n)
+    logits = sess.logits(n)
+    order = torch.sort(logits, dim=-1, descending=True, stable=True)
+    # the GEMM that materialises the test's logits and the top-k kernel round identically only up to fp32 summation order:
+    # compare the ORDER through the kernel's own scores, and the scores against the logits
+    got_s = scores.cpu()
+    assert float((got_s - torch.gather(logits, 1, ids).cpu()).abs().max()) < 2e-3
+    assert bool((got_s[:, :-1] >= got_s[:, 1:]).all())
+    tie = got_s[:, :-1] == got_s[:, 1:]
+    assert bool((ids.cpu()[:, :-1][tie] < ids.cpu()[:, 1:][tie]).all())                      # lower id first among equal scores
+    # membership: everything left out scores no better than the k-th entry
+    kth = got_s[:, -1:]
+    mask = torch.ones_like(logits, dtype=torch.bool).scatter_(1, ids, False).cpu()
+    assert float((logits.cpu()[mask].view(n, V - k) - kth).max()) < 2e-3
+    agree = (order.indices[:, :k].cpu() == ids.cpu()).float().mean()
+    assert float(agree) > 0.97, float(agree)                                                 # identical up to near-ties of two kernels
+    for r in range(n):
+        assert len(set(ids[r].tolist())) == k
+    # shards + merge == whole
+    cuts = [0, V // 3, V // 3 + 1, V]
+    keys = torch.stack([sess.topk_full(k, lo, hi, n_rows=n, want_keys=True)[2] for lo, hi in zip(cuts[:-1], cuts[1:])])
+    m_ids, m_sc = topk_merge(keys.contiguous())
+    assert torch.equal(m_ids, ids) and torch.equal(m_sc, scores)
+    # external rows (the all-gathered rows of other ranks) give the same lists
+    e_ids, e_sc = sess.topk_full(k, t_rows=sess.mlm_hidden()[:n].clone().contiguous())
+    assert torch.equal(e_ids, ids) and torch.equal(e_sc, scores)
+
+
+def test_top_k_items_api_and_recommender_exclusion():
+    from bert4rec_b200.apps import Recommender, InferenceDataloader
+    model, _ = _model(seed=6)
+    V = KW["vocab_size"]
+    ev = make_batch(5, 32, 6, V, seed=12, eval_mode=True)
+    ids, sc = model.top_k_items(ev, 7)
+    assert tuple(ids.shape) == (5, 7)
+    own = model(ev, training=False)["mlm_logits"][:, 0]                      # slot 0 is the only weighted slot of an eval batch
+    ref = torch.sort(own, dim=-1, descending=True, stable=True).indices[:, :7]
+    assert float((ref == ids).float().mean()) > 0.9
+    ban = [ids[r, :3].tolist() for r in range(5)]
+    ids2, _ = model.top_k_items(ev, 4, exclude=ban)
+    assert torch.equal(ids2, ids[:, 3:7])
+    dl = InferenceDataloader(max_seq_len=32)
+    dl.tokenizer.tokenize([f"item{j}" for j in range(V - 3)])
+    hist = [f"item{j}" for j in (5, 17, 33, 120, 64)]
+    got = Recommender(model, dl)(list(hist))
+    assert got not in hist
+    inp = dl.prepare_inference(list(hist))
+    logits = model(inp, training=False)["mlm_logits"][0, 0].clone()
+    logits[torch.tensor(dl.tokenizer.tokenize(hist), device=logits.device)] = -float("inf")
+    assert float(logits.max() - logits[dl.tokenizer.tokenize(got)]) < 2e-2
