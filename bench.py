@@ -40,6 +40,10 @@ WORKLOADS = {
     "c4": dict(name="C4 scaled H256 L4", vocab_size=13047, hidden_size=256, num_layers=4, num_attention_heads=4,
                max_sequence_length=200, inner_dim=1024, output_dropout=0.1, attention_dropout=0.1,
                batch=1024, seq_len=200, max_pred=40, mask_prob=0.2),
+    # C5: 1M-item synthetic catalogue, tied output embedding vocabulary-sharded over the ranks (C4's encoder)
+    "c5": dict(name="C5 1M-item catalogue, vocab-sharded", vocab_size=1000003, hidden_size=256, num_layers=4, num_attention_heads=4,
+               max_sequence_length=200, inner_dim=1024, output_dropout=0.1, attention_dropout=0.1,
+               batch=1024, seq_len=200, max_pred=40, mask_prob=0.2),
 }
 ENC_KEYS = ("vocab_size", "hidden_size", "num_layers", "num_attention_heads", "max_sequence_length", "inner_dim",
             "output_dropout", "attention_dropout")
@@ -473,6 +477,55 @@ def allreduce_time_us(model, dev, n=30):
     return e0.elapsed_time(e1) / n * 1e3
 
 
+def measure_c5(args, dev, world, rank, steps=5, warmup=2):
+    """BASELINE config 5: V = 1 000 003, hidden 256; train step with the tied projection SHARDED by vocabulary rows over the ranks
+    (softmax-CE max / sum merged over NCCL) and full-catalogue top-10 ranking with the per-shard lists merged over NCCL."""
+    import torch
+    import torch.distributed as dist
+    w = WORKLOADS["c5"]
+    model = build_model(w, dev)
+    model.vocab_sharded = world > 1
+    B = w["batch"]
+    batches = [{k: v.to(dev) for k, v in b.items()} for b in synth_batches(w, 2, seed=rank)]
+    m_valid = int((batches[0]["masked_lm_ids"] != 0).sum())
+    for i in range(warmup):
+        model.train_step(batches[i % 2])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        model.train_step(batches[i % 2])
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    loss = float(model.train_step(batches[0])["loss"])
+    ev = {k: v.to(dev) for k, v in synth_batches(w, 1, seed=1000 + rank, eval_mode=True)[0].items()}
+    ids, _ = model.top_k_items(ev, 10)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(3):
+        ids, _ = model.top_k_items(ev, 10)
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ems = float(t.item()) / 3
+    fl = train_flops(w, m_valid)
+    out = {"workload": w["name"], "value": world * B / (ms / 1e3), "unit": "seq/s", "ms_per_step": ms, "steps": steps, "n_gpus": world,
+           "vocab_sharded": bool(model.vocab_sharded), "loss_after_warmup": loss, "ln_vocab": float(np.log(w["vocab_size"])),
+           "achieved_tflops_per_gpu": fl / (ms / 1e3) / 1e12,
+           "full_catalogue_top10": {"value": world * B / (ems / 1e3), "unit": "seq/s", "ms_per_batch": ems,
+                                    "what": "encoder forward + per-shard top-10 over the 1M-item catalogue + NCCL all-gather + key merge"},
+           "config": {k: w[k] for k in ENC_KEYS}, "batch_per_gpu": B}
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args, w, secondary):
     import torch
     import torch.distributed as dist
@@ -559,6 +612,10 @@ def run_b200(args, w, secondary):
                                     "roofline": roofline_block(r2["model"], r2["sess"], w2, r2["dev_batches"], args, hbm, tf_burst, src, brief=True)})
             del r2
             torch.cuda.empty_cache()
+    if world > 1 and (world == 8 or os.environ.get("B4R_BENCH_C5")) and not args.workload:
+        c5 = measure_c5(args, dev, world, rank)     # every rank takes part (collectives inside)
+        if rank == 0:
+            line["c5"] = c5
     if rank == 0:
         emit(line)
     if world > 1:

@@ -704,9 +704,14 @@ class BERT4RecModel:
             ids, scores = sess.topk_full(kk, n_rows=n)
         else:
             me = dist.get_rank(group)
-            cap, H = sess.Mcap, self.store.H
+            H = self.store.H
+            nmax = torch.tensor([n], dtype=torch.int64, device=self.device)
+            dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=group)
+            cap = int(nmax.item())                       # live rows of the fullest rank: only those travel and are scored
+            mine = torch.zeros(cap, H, dtype=torch.bfloat16, device=self.device)
+            mine[:n] = sess.mlm_hidden()[:n]
             rows = torch.empty(world, cap, H, dtype=torch.bfloat16, device=self.device)
-            dist.all_gather_into_tensor(rows, sess.mlm_hidden().contiguous(), group=group)
+            dist.all_gather_into_tensor(rows, mine, group=group)
             lo, hi = shard_range(self.store.V, world, me)
             if lo < hi:
                 _, _, keys = sess.topk_full(kk, lo, hi, t_rows=rows.view(world * cap, H), want_keys=True)
