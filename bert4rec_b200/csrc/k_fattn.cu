@@ -50,6 +50,16 @@ __device__ __forceinline__ void ld_chunk(uint32_t taddr, bool full, uint32_t (&r
     for (int j = 16; j < 32; ++j) r[j] = 0u;
   }
 }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 
@@ -95,7 +105,7 @@ struct FAttnBwdDev {
 template <int D>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                 const __grid_constant__ CUtensorMap tmO, FAttnBwdDev a) {
+                 const __grid_constant__ CUtensorMap tmO, FAttnBwdDev a, uint32_t stagger_ns) {
   pdl_grid_wait();
   constexpr int NHG = 64 / D;      // heads per 64-column group
   constexpr int CPT = D / FA_NG;   // accumulator columns drained per thread
@@ -155,6 +165,9 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       }
       __syncwarp();
     };
+    // every CTA takes the same time per item: without a stagger all 148 CTAs issue their item loads in the same microsecond and
+    // then leave the memory system idle; a one-off start offset spreads the bursts
+    if (n_items > (int)gridDim.x && stagger_ns) __nanosleep((blockIdx.x % 8) * stagger_ns);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++nitem) {
       const int b = item / G, g = item % G;
       const bool tsk = blockIdx.x == 0 && nitem == 2 && lane == 0;
@@ -216,6 +229,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
     const float scale = rsqrtf((float)D), c1 = scale * kLog2e;
     uint32_t git = 0, g_waited = 0, nitem = 0;
+    const uint32_t sLD_a = umma::smem_addr(sLD), sKeep_a = umma::smem_addr(sKeep);
     auto need_g = [&](uint32_t upto) {     // gradient MMAs of global iterations < upto have completed
       while (g_waited < upto) { umma::mbar_wait(barG, g_waited & 1); ++g_waited; }
       umma::fence_after_sync();
@@ -224,25 +238,39 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       const int b = item / G, g = item % G;
       const bool tsc = blockIdx.x == 0 && nitem == 2 && tid == 0;
       FTS(tsc, 0);
-      umma::mbar_wait(barL, nitem & 1);
-      FTS(tsc, 1);
-      // ---- per-item vectors: key mask, lse (log2 units), delta = rowsum(dO * O), keep bits
+      // ---- per-item vectors that do not depend on the tiles (issued before the wait: their latency hides behind the TMA loads).
+      // Every thread is past its last read of these arrays (phase A of the previous item's last iteration) by the time any
+      // thread gets here: the final drain waits for the gradient MMAs, which wait for every thread's phase B.
       if (tid < 256) sMask[tid] = tid < S ? (a.mask[(size_t)b * S + tid] != 0 ? 0.f : -1e9f * kLog2e) : -INFINITY;
 #pragma unroll
       for (int h = 0; h < NHG; ++h) {
         const int bn = b * a.N + g * NHG + h;
-        float dl = 0.f;
+        if (tid < 256) sLD[h * 256 + tid].x = tid < S ? a.lse[(size_t)bn * S + tid] * kLog2e : INFINITY;
+        if (drop) {
+          // (all loads first, then the stores: one round trip instead of one per loop iteration)
+          const unsigned long long* src = a.keep + (size_t)bn * S * W;
+          constexpr int KPT = (1024 + FB_CT - 1) / FB_CT;
+          unsigned long long kv[KPT];
+#pragma unroll
+          for (int q = 0; q < KPT; ++q) { const int i = tid + q * FB_CT; kv[q] = i < S * W ? src[i] : 0ull; }
+#pragma unroll
+          for (int q = 0; q < KPT; ++q) { const int i = tid + q * FB_CT; if (i < S * W) sKeep[h * 1024 + i] = kv[q]; }
+        }
+      }
+      umma::mbar_wait(barL, nitem & 1);
+      FTS(tsc, 1);
+      // ---- delta = rowsum(dO * O) per (head, query)
+#pragma unroll
+      for (int h = 0; h < NHG; ++h) {
         if (tid < MT * 128) {
-          float dv[D], ov[D];
+          float dv[D], ov[D], dl = 0.f;
           ld_tile<D / 8>(tile(FB_DO + (tid >> 7)), tid & 127, h * (D / 8), dv);
           ld_tile<D / 8>(tile(FB_P + (tid >> 7)), tid & 127, h * (D / 8), ov);
 #pragma unroll
           for (int i = 0; i < D; ++i) dl += dv[i] * ov[i];
-        }
-        if (tid < 256) sLD[h * 256 + tid] = make_float2(tid < S ? a.lse[(size_t)bn * S + tid] * kLog2e : INFINITY, dl);
-        if (drop) {
-          const unsigned long long* src = a.keep + (size_t)bn * S * W;
-          for (int i = tid; i < S * W; i += FB_CT) sKeep[h * 1024 + i] = src[i];
+          sLD[h * 256 + tid].y = dl;
+        } else if (tid < 256) {
+          sLD[h * 256 + tid].y = 0.f;
         }
       }
       named_bar_sync(1, FB_CT);
@@ -251,10 +279,13 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         const int h = i / (MT * MT), kt = (i / MT) % MT, qt = i % MT;
         const int qext = min(128, S16 - qt * 128);
         const int key = kt * 128 + r;
+        // a warp whose 32 key rows all lie past the padded sequence contributes nothing: its rows of P^T / dS^T are never read by
+        // the dQ MMA (K extent = padded keys) and only feed rows of dK / dV that are not stored
+        const bool warp_live = kt * 128 + quad * 32 < S16;
         const float mk = sMask[key];
-        const float2* ld = sLD + h * 256 + qt * 128;
-        const unsigned long long* kp = sKeep + h * 1024 + (size_t)(qt * 128) * W + (key >> 6);
-        const int kbit = key & 63;
+        const uint32_t ld_a = sLD_a + (uint32_t)(h * 256 + qt * 128) * 8;
+        const uint32_t kp_a = sKeep_a + (uint32_t)(h * 1024 + (qt * 128) * W + (key >> 6)) * 8 + ((key & 32) ? 4u : 0u);
+        const uint32_t kbit = key & 31;
         // ---- phase A: scores -> Pd^T, dS^T packed in registers
         umma::mbar_wait(barS, git & 1);
         FTS(tsc, 4 + i * 6);
@@ -263,7 +294,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           const int q0 = wg * QPT + c * 16;
-          if (q0 < qext) {
+          if (q0 < qext && warp_live) {
             float s[16], dp[16];
             {
               uint32_t rs[16], rd[16];
@@ -273,18 +304,24 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 16; ++j) { s[j] = __uint_as_float(rs[j]); dp[j] = __uint_as_float(rd[j]); }
             }
+            if (drop) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 l2 = ld[q0 + j];
-              const float p = ex2(fmaf(s[j], c1, mk) - l2.x);
-              float pd = p, dpj = dp[j];
-              if (drop) {
-                const bool keep = (kp[(size_t)(q0 + j) * W] >> kbit) & 1ull;
-                pd = keep ? p * a.inv_keep : 0.f;
-                dpj = keep ? dpj * a.inv_keep : 0.f;
+              for (int j = 0; j < 16; j += 2) {
+                const float4 l4 = lds_f4(ld_a + (uint32_t)(q0 + j) * 8);         // (lse, delta) of two queries
+                const uint32_t w0 = lds_u32(kp_a + (uint32_t)((q0 + j) * W) * 8), w1 = lds_u32(kp_a + (uint32_t)((q0 + j + 1) * W) * 8);
+                const float p0 = ex2(fmaf(s[j], c1, mk) - l4.x), p1 = ex2(fmaf(s[j + 1], c1, mk) - l4.z);
+                const float t0 = ((w0 >> kbit) & 1u) ? a.inv_keep : 0.f, t1 = ((w1 >> kbit) & 1u) ? a.inv_keep : 0.f;
+                s[j] = p0 * t0; s[j + 1] = p1 * t1;
+                dp[j] = p0 * fmaf(dp[j], t0, -l4.y); dp[j + 1] = p1 * fmaf(dp[j + 1], t1, -l4.w);
               }
-              s[j] = pd;
-              dp[j] = p * (dpj - l2.y);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const float4 l4 = lds_f4(ld_a + (uint32_t)(q0 + j) * 8);
+                const float p0 = ex2(fmaf(s[j], c1, mk) - l4.x), p1 = ex2(fmaf(s[j + 1], c1, mk) - l4.z);
+                s[j] = p0; s[j + 1] = p1;
+                dp[j] = p0 * (dp[j] - l4.y); dp[j + 1] = p1 * (dp[j + 1] - l4.w);
+              }
             }
             pack_n<16>(s, pkp[c]);
             pack_n<16>(dp, pkd[c]);
@@ -299,7 +336,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           const int q0 = wg * QPT + c * 16;
-          if (q0 < qext) {
+          if (q0 < qext && warp_live) {
             st_tile<2>(tile(FB_P + (q0 >> 6)), r, (q0 & 63) >> 3, pkp[c]);
             st_tile<2>(tile(FB_DS + (q0 >> 6)), r, (q0 & 63) >> 3, pkd[c]);
           }
@@ -307,46 +344,54 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         umma::fence_proxy_async();
         umma::mbar_arrive(barPD);
         FTS(tsc, 7 + i * 6);
-        // ---- end of a (head, key tile) block: drain dK / dV (and dQ after the head's last key tile)
+        // ---- end of a (head, key tile) block: drain dK / dV (and dQ after the head's last key tile).  The accumulators go through
+        // the (now idle) dS^T tiles so that the global stores are row-contiguous: 8 (4) lanes x 16 bytes cover the 128 (64) bytes
+        // of one row; one thread per row writing its own 64 bytes made every store instruction touch 32 half-used sectors.
         if (qt == MT - 1) {
           need_g(git + 1);
           FTS(tsc, 8 + i * 6);
           const int col0 = h * D + wg * CPT;
-          {
-            uint32_t rv[CPT], rk[CPT];
-            tmem_ld_n(tlane + TC_DV + col0, rv);
-            tmem_ld_n(tlane + TC_DK + col0, rk);
-            umma::tmem_ld_wait();
-            if (key < S) {
-              float fv[CPT], fk[CPT];
-#pragma unroll
-              for (int j = 0; j < CPT; ++j) { fv[j] = __uint_as_float(rv[j]); fk[j] = __uint_as_float(rk[j]) * scale; }
-              uint32_t pv[CPT / 2], pk2[CPT / 2];
-              pack_n<CPT>(fv, pv);
-              pack_n<CPT>(fk, pk2);
-              bf16* dst = a.dqkv + ((size_t)b * S + key) * 3 * H + g * 64 + col0;
-              st_global<CPT / 2>(dst + H, pk2);
-              st_global<CPT / 2>(dst + 2 * H, pv);
-            }
-          }
-          if (kt == MT - 1) {
-            for (int t = 0; t < MT; ++t) {
-              uint32_t rq[CPT];
-              tmem_ld_n(tlane + TC_DQ + t * 64 + col0, rq);
+          const bool last_kt = kt == MT - 1;
+          auto stage = [&](uint32_t tcol, int t, float mul, bool rows_live) {
+            if (rows_live) {
+              uint32_t rr[CPT];
+              tmem_ld_n(tlane + tcol + col0, rr);
               umma::tmem_ld_wait();
-              const int qi = t * 128 + r;
-              if (qi < S) {
-                float fq[CPT];
+              float f[CPT];
 #pragma unroll
-                for (int j = 0; j < CPT; ++j) fq[j] = __uint_as_float(rq[j]) * scale;
-                uint32_t pq[CPT / 2];
-                pack_n<CPT>(fq, pq);
-                st_global<CPT / 2>(a.dqkv + ((size_t)b * S + qi) * 3 * H + g * 64 + col0, pq);
+              for (int j = 0; j < CPT; ++j) f[j] = __uint_as_float(rr[j]) * mul;
+              uint32_t pk[CPT / 2];
+              pack_n<CPT>(f, pk);
+              st_tile<CPT / 8>(tile(FB_DS + t), r, col0 >> 3, pk);
+            }
+          };
+          auto flush_tile = [&](int t, int row0, int col_off) {     // staged tile t -> dqkv rows [row0, row0 + 128) of this sequence
+            constexpr int LPR = D / 8, RPP = FB_CT / LPR;            // lanes per row, rows per pass
+            const int li = tid % LPR;
+            for (int rr = tid / LPR; rr < 128; rr += RPP) {
+              if (row0 + rr < S) {
+                const int chunk = (h * D) / 8 + li;
+                const uint4 v = *reinterpret_cast<const uint4*>(tile(FB_DS + t) + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+                *reinterpret_cast<uint4*>(a.dqkv + ((size_t)b * S + row0 + rr) * 3 * H + col_off + g * 64 + h * D + li * 8) = v;
               }
             }
+          };
+          const bool krows = kt * 128 + quad * 32 < S;
+          stage(TC_DV, 0, 1.0f, krows);
+          stage(TC_DK, 1, scale, krows);
+          if (!last_kt) { umma::fence_before_sync(); umma::mbar_arrive(barAF); }
+          named_bar_sync(1, FB_CT);
+          flush_tile(0, kt * 128, 2 * H);
+          flush_tile(1, kt * 128, H);
+          named_bar_sync(1, FB_CT);
+          if (last_kt) {
+            for (int t = 0; t < MT; ++t) stage(TC_DQ + t * 64, t, scale, t * 128 + quad * 32 < S);
+            umma::fence_before_sync();
+            umma::mbar_arrive(barAF);
+            named_bar_sync(1, FB_CT);
+            for (int t = 0; t < MT; ++t) flush_tile(t, t * 128, 0);
+            named_bar_sync(1, FB_CT);
           }
-          umma::fence_before_sync();
-          umma::mbar_arrive(barAF);
           FTS(tsc, 9 + i * 6);
         }
       }
@@ -646,13 +691,14 @@ cudaError_t launch_fattn_bwd(const AttnArgs& a, cudaStream_t st) {
   const int D = a.H / a.N;
   const int items = a.B * (a.H / 64);
   dim3 grid(items < sm_count() ? items : sm_count());
+  static const uint32_t stagger = getenv("B4R_FATTN_STAGGER_NS") ? (uint32_t)atoi(getenv("B4R_FATTN_STAGGER_NS")) : 2000u;
   static bool done32 = false, done64 = false;
   if (D == 32) {
     if (!done32) { cudaError_t e = cudaFuncSetAttribute(fattn_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM); if (e != cudaSuccess) return e; done32 = true; }
-    launch_pdl(fattn_bwd_kernel<32>, grid, dim3(FB_THREADS), (size_t)FB_SMEM, st, tq, tdo, to, d);
+    launch_pdl(fattn_bwd_kernel<32>, grid, dim3(FB_THREADS), (size_t)FB_SMEM, st, tq, tdo, to, d, stagger);
   } else {
     if (!done64) { cudaError_t e = cudaFuncSetAttribute(fattn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM); if (e != cudaSuccess) return e; done64 = true; }
-    launch_pdl(fattn_bwd_kernel<64>, grid, dim3(FB_THREADS), (size_t)FB_SMEM, st, tq, tdo, to, d);
+    launch_pdl(fattn_bwd_kernel<64>, grid, dim3(FB_THREADS), (size_t)FB_SMEM, st, tq, tdo, to, d, stagger);
   }
   return cudaGetLastError();
 }
