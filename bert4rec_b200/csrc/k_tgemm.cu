@@ -4,7 +4,10 @@
 //   warp 1    : MMA issuer (one elected lane): 4 x (M128 N128 K16) per k-block into one of TWO 128-column fp32
 //               accumulators in TMEM, so the epilogue of tile i overlaps the main loop of tile i+1
 //   warps 2-17: epilogue, thread = (accumulator row, 32-column part): one tcgen05.ld of 32 columns -> bias / GELU /
-//               GELU' (+ per-tile column sums = bias gradient) / fp32 residual -> global
+//               GELU' (+ per-tile column sums = bias gradient) / fp32 residual -> global.  bf16 outputs leave through a
+//               swizzled shared-memory staging tile and TMA stores (cp.async.bulk.tensor): one thread writing the 64 bytes
+//               of its own row made every store instruction touch 32 half-used sectors -- the stores, not the MMAs or the
+//               math, were 55-70 % of these kernels (FFN1 + GELU at C4: 371 us with, 112 us without its stores)
 // B is consumed in place in either layout: [K,N] row-major (forward: TF kernels are [in,out]) as an MN-major operand,
 // [N,K] row-major (data gradients read the SAME weights transposed) as a K-major operand -- no transposed copies.
 // Used for hidden sizes whose GEMMs are real GEMMs (K, N multiples of 64; e.g. C4: M = 204 800 tokens, K/N in
@@ -20,10 +23,15 @@ namespace b4r {
 using namespace encf;
 
 namespace {
-constexpr int TG_BM = 128, TG_BN = 128, TG_BK = 64, TG_STAGES = 4;
+constexpr int TG_BM = 128, TG_BN = 128, TG_BK = 64, TG_STAGES = 4;   // (4 ring stages allocated for the barrier arrays; see tg_stages)
 constexpr int TG_EPI_WARPS = 16, TG_THREADS = 64 + 32 * TG_EPI_WARPS;   // producer + issuer + 16 epilogue warps
 constexpr int TG_A_BYTES = TG_BM * 128, TG_B_BYTES = TG_BN * 128, TG_STAGE = TG_A_BYTES + TG_B_BYTES;
-constexpr int TG_SMEM = TG_STAGES * TG_STAGE + 2 * 4 * TG_BN * 4 + 256 + 1024;   // ring + column-sum scratch + barriers + align
+constexpr int TG_OUT_BYTES = TG_BM * TG_BN * 2;            // bf16 staging of one output tile: two [128][64] swizzled halves
+__host__ __device__ constexpr int tg_nout(int epi) { return epi == EPI_BIAS_GELU ? 2 : (epi == EPI_F32_RES ? 0 : 1); }
+// GELU' reads its second operand (the saved pre-activation tile) through TMA as well: two 32 KB landing buffers, paid for with one ring stage
+__host__ __device__ constexpr int tg_naux(int epi) { return epi == EPI_GELU_GRAD ? 2 : 0; }
+__host__ __device__ constexpr int tg_stages(int epi) { return epi == EPI_GELU_GRAD ? 3 : 4; }
+__host__ __device__ constexpr int tg_smem(int epi) { return tg_stages(epi) * TG_STAGE + (tg_nout(epi) + tg_naux(epi)) * TG_OUT_BYTES + 2 * 4 * TG_BN * 4 + 256 + 1024; }   // ring + staging + column sums + barriers + align
 
 struct TGemmDev {
   int M, N, K;
@@ -39,17 +47,22 @@ struct TGemmDev {
 
 template <int EPI, bool B_MN>
 __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                       const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
                                                        TGemmDev a) {
   pdl_grid_wait();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* sCol = reinterpret_cast<float*>(smem + TG_STAGES * TG_STAGE);   // [2 acc][4 quads][128] column-sum partials
+  constexpr int NST = tg_stages(EPI);
+  unsigned char* sOut = smem + NST * TG_STAGE;                            // [NOUT][2 halves][128][64] bf16, 128-byte swizzle
+  unsigned char* sAux = sOut + tg_nout(EPI) * TG_OUT_BYTES;               // [2 acc][2 halves][128][64] bf16 (GELU' only)
+  float* sCol = reinterpret_cast<float*>(sAux + tg_naux(EPI) * TG_OUT_BYTES);   // [2 acc][4 quads][128] column-sum partials
   uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + 2 * 4 * TG_BN);
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = bars + TG_STAGES;          // [STAGES]
   uint64_t* tfull = bars + 2 * TG_STAGES;      // [2]
   uint64_t* tempty = tfull + 2;                // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* auxfull = tempty + 2;              // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(auxfull + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (a.M + TG_BM - 1) / TG_BM, tiles_n = (a.N + TG_BN - 1) / TG_BN;
@@ -57,10 +70,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TG_STAGES; ++i) { umma::mbar_init(full + i, 1); umma::mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(tfull + i, 1); umma::mbar_init(tempty + i, TG_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(tfull + i, 1); umma::mbar_init(tempty + i, TG_EPI_WARPS); umma::mbar_init(auxfull + i, 1); }
     umma::fence_barrier_init();
     umma::prefetch_tensormap(&tmA);
     umma::prefetch_tensormap(&tmB);
+    if (tg_nout(EPI) > 0) umma::prefetch_tensormap(&tmO);
+    if (tg_nout(EPI) > 1 || tg_naux(EPI) > 0) umma::prefetch_tensormap(&tmO2);
   }
   if (warp == 1) umma::tmem_alloc<256>(tmem_holder);
   umma::fence_before_sync();
@@ -75,8 +90,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int m0 = (t / tiles_n) * TG_BM, n0 = (t % tiles_n) * TG_BN;
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int st = it % TG_STAGES;
-          umma::mbar_wait(empty + st, ((it / TG_STAGES) & 1) ^ 1);
+          const int st = it % NST;
+          umma::mbar_wait(empty + st, ((it / NST) & 1) ^ 1);
           umma::mbar_expect_tx(full + st, TG_STAGE);
           unsigned char* sA = smem + st * TG_STAGE;
           unsigned char* sB = sA + TG_A_BYTES;
@@ -102,8 +117,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
         umma::mbar_wait(tempty + acc, ((ti >> 1) & 1) ^ 1);
         umma::fence_after_sync();
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int st = it % TG_STAGES;
-          umma::mbar_wait(full + st, (it / TG_STAGES) & 1);
+          const int st = it % NST;
+          umma::mbar_wait(full + st, (it / NST) & 1);
           umma::fence_after_sync();
           const uint32_t offA = st * TG_STAGE, offB = offA + TG_A_BYTES;
 #pragma unroll
@@ -122,10 +137,44 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
     // ===================================================================== epilogue (warps 2..17): (lane quadrant, 32-column part)
     const int quad = warp & 3, cpart = (warp - 2) >> 2;
     const int row_in_tile = quad * 32 + lane;
+    const bool store_leader = threadIdx.x == 64;     // first epilogue thread: issues and tracks the bulk stores
     int ti = 0;
+    // staging protocol per tile: [leader: earlier bulk stores have read the staging tiles] -> bar -> st_tile -> proxy fence -> bar ->
+    // [leader: TMA stores + commit]
+    auto stage_begin = [&]() {
+      if (store_leader) umma::tma_store_wait_read<0>();
+      asm volatile("bar.sync 2, 512;\n" ::: "memory");
+    };
+    auto stage_put = [&](int which, const uint32_t (&pk)[16]) {
+      st_tile<4>(sOut + which * TG_OUT_BYTES + (cpart >> 1) * TILE_B, row_in_tile, (cpart & 1) * 4, pk);
+    };
+    auto stage_commit = [&](int m0, int n0) {
+      umma::fence_proxy_async();
+      asm volatile("bar.sync 2, 512;\n" ::: "memory");
+      if (store_leader) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+          if (n0 + hh * 64 < a.N) {
+            umma::tma_store_2d(&tmO, sOut + hh * TILE_B, n0 + hh * 64, m0);
+            if (tg_nout(EPI) > 1) umma::tma_store_2d(&tmO2, sOut + TG_OUT_BYTES + hh * TILE_B, n0 + hh * 64, m0);
+          }
+        umma::tma_store_commit();
+      }
+    };
+    auto aux_load = [&](int tt, int tti) {       // the pre-activation tile of output tile tt -> landing buffer tti & 1
+      if (EPI == EPI_GELU_GRAD && store_leader && tt < n_tiles) {
+        const int am0 = (tt / tiles_n) * TG_BM, an0 = (tt % tiles_n) * TG_BN;
+        unsigned char* dst = sAux + (tti & 1) * TG_OUT_BYTES;
+        umma::mbar_expect_tx(auxfull + (tti & 1), TG_OUT_BYTES);
+        umma::tma_load_2d(dst, &tmO2, an0, am0, auxfull + (tti & 1));
+        umma::tma_load_2d(dst + TILE_B, &tmO2, an0 + 64, am0, auxfull + (tti & 1));
+      }
+    };
+    aux_load(blockIdx.x, 0);
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
       const int acc = ti & 1;
       const int mt = t / tiles_n, m0 = mt * TG_BM, n0 = (t % tiles_n) * TG_BN;
+      aux_load(t + gridDim.x, ti + 1);           // (its buffer was last read two tiles ago: every thread has passed that tile's staging barrier)
       const int m = m0 + row_in_tile;
       const bool mok = m < a.M;
       umma::mbar_wait(tfull + acc, (ti >> 1) & 1);
@@ -147,35 +196,35 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
         if (EPI == EPI_BIAS_BF16 || EPI == EPI_BF16) {
           uint32_t pk[16];
           pack_n<32>(v, pk);
-          if (mok && nok) st_global<16>(a.out_bf16 + (size_t)m * a.ld_out + n, pk);
+          stage_begin();
+          stage_put(0, pk);
+          stage_commit(m0, n0);
         } else if (EPI == EPI_BIAS_GELU) {
-          uint32_t pk[16];
+          uint32_t pk[16], pk2[16];
           round_n<32>(v, pk);   // GELU of the bf16-rounded pre-activation backward re-reads
-          if (mok && nok) st_global<16>(a.out_bf16 + (size_t)m * a.ld_out + n, pk);
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-          pack_n<32>(v, pk);
-          if (mok && nok) st_global<16>(a.out2_bf16 + (size_t)m * a.ld_out + n, pk);
+          pack_n<32>(v, pk2);
+          stage_begin();
+          stage_put(0, pk);
+          stage_put(1, pk2);
+          stage_commit(m0, n0);
         } else if (EPI == EPI_GELU_GRAD) {
           uint32_t pk[16];
+          umma::mbar_wait(auxfull + acc, (ti >> 1) & 1);
           if (mok && nok) {
-            const bf16* ap = a.aux_bf16 + (size_t)m * a.ld_aux + n;
+            float x[32];
+            ld_tile<4>(sAux + acc * TG_OUT_BYTES + (cpart >> 1) * TILE_B, row_in_tile, (cpart & 1) * 4, x);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(ap + 8 * q));
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_bf162(w[i]);
-                v[8 * q + 2 * i] *= gelu_erf_grad(f.x); v[8 * q + 2 * i + 1] *= gelu_erf_grad(f.y);
-              }
-            }
+            for (int i = 0; i < 32; ++i) v[i] *= gelu_erf_grad(x[i]);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
           round_n<32>(v, pk);   // the bias gradient sums what the weight-gradient GEMM will see
-          if (mok && nok) st_global<16>(a.out_bf16 + (size_t)m * a.ld_out + n, pk);
+          stage_begin();
+          stage_put(0, pk);
+          stage_commit(m0, n0);
           if (a.colsum_part) {
             // column sums over the 32 rows of this warp (recursive halving: 31 shuffles for 32 columns), then over the 4
             // lane quadrants through smem
@@ -230,6 +279,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(tempty + acc);
     }
+    if (tg_nout(EPI) > 0 && store_leader) umma::tma_store_wait<0>();   // every bulk store has completed before the CTA retires
   }
   umma::fence_before_sync();
   __syncthreads();
@@ -248,18 +298,21 @@ bool tgemm_supported(int epi, const GemmArgs& a) {
   if (a.K % TG_BK || a.N % 64 || a.K < min_k || a.M < 256) return false;   // small / narrow problems stay on the portable kernel
   if ((a.a_kmax && a.a_kmax != a.K) || (a.b_kmax && a.b_kmax != a.K)) return false;
   if (a.lda % 8 || a.ldb % 8 || ((uintptr_t)a.A & 15) || ((uintptr_t)a.B & 15)) return false;
+  if (tg_naux(epi) > 0 && (a.ld_aux % 8 || ((uintptr_t)a.aux_bf16 & 15))) return false;
+  if (tg_nout(epi) > 0 && (a.ld_out % 8 || ((uintptr_t)a.out_bf16 & 15) || (tg_nout(epi) > 1 && ((uintptr_t)a.out2_bf16 & 15)))) return false;   // TMA stores
   return true;
 }
 
 template <int EPI, bool B_MN>
-static cudaError_t launch_tgemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const TGemmDev& d, int grid, cudaStream_t st) {
+static cudaError_t launch_tgemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmO2,
+                                  const TGemmDev& d, int grid, cudaStream_t st) {
   static bool done = false;
   if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(tgemm_kernel<EPI, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(tgemm_kernel<EPI, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem(EPI));
     if (e != cudaSuccess) return e;
     done = true;
   }
-  launch_pdl(tgemm_kernel<EPI, B_MN>, dim3(grid), dim3(TG_THREADS), (size_t)(TG_SMEM), st, tmA, tmB, d);
+  launch_pdl(tgemm_kernel<EPI, B_MN>, dim3(grid), dim3(TG_THREADS), (size_t)(tg_smem(EPI)), st, tmA, tmB, tmO, tmO2, d);
   return cudaGetLastError();
 }
 
@@ -270,6 +323,10 @@ cudaError_t launch_tgemm(int epi, const GemmArgs& a, cudaStream_t st) {
   if (bmn ? !make_tmap_bf16_sw128(&tmB, a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb, 64)
           : !make_tmap_bf16_sw128(&tmB, a.B, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb, TG_BN))
     return cudaErrorInvalidValue;
+  CUtensorMap tmO = tmA, tmO2 = tmA;   // (placeholders when the epilogue has no bf16 output)
+  if (tg_nout(epi) > 0 && !make_tmap_bf16_sw128(&tmO, a.out_bf16, (uint64_t)a.M, (uint64_t)a.N, (uint64_t)a.ld_out, TG_BM)) return cudaErrorInvalidValue;
+  if (tg_nout(epi) > 1 && !make_tmap_bf16_sw128(&tmO2, a.out2_bf16, (uint64_t)a.M, (uint64_t)a.N, (uint64_t)a.ld_out, TG_BM)) return cudaErrorInvalidValue;
+  if (tg_naux(epi) > 0 && !make_tmap_bf16_sw128(&tmO2, a.aux_bf16, (uint64_t)a.M, (uint64_t)a.N, (uint64_t)a.ld_aux, TG_BM)) return cudaErrorInvalidValue;
   TGemmDev d;
   d.M = a.M; d.N = a.N; d.K = a.K; d.bias = a.bias; d.out_bf16 = a.out_bf16; d.ld_out = a.ld_out; d.out2_bf16 = a.out2_bf16;
   d.aux_bf16 = a.aux_bf16; d.ld_aux = a.ld_aux; d.out_f32 = a.out_f32; d.ld_f32 = a.ld_f32; d.res_f32 = a.res_f32;
@@ -278,7 +335,7 @@ cudaError_t launch_tgemm(int epi, const GemmArgs& a, cudaStream_t st) {
   const int grid = tiles < 148 ? tiles : 148;
 #define B4R_TG(E)                                                                                              \
   case E:                                                                                                      \
-    return bmn ? launch_tgemm_t<E, true>(tmA, tmB, d, grid, st) : launch_tgemm_t<E, false>(tmA, tmB, d, grid, st);
+    return bmn ? launch_tgemm_t<E, true>(tmA, tmB, tmO, tmO2, d, grid, st) : launch_tgemm_t<E, false>(tmA, tmB, tmO, tmO2, d, grid, st);
   switch (epi) {
     B4R_TG(EPI_BIAS_BF16)
     B4R_TG(EPI_BIAS_GELU)

@@ -1,4 +1,2 @@
-for ns in 0 1000 2000 4000; do
-B4R_FATTN_STAGGER_NS=$ns timeout 100 python scripts/profile_step.py c4 5 2>&1 | grep -E "attn_bwd|us/step" > gpurun_out/r2w_c4_$ns.log
-done
-timeout 200 python -m pytest tests/test_gpu_fattn.py -x -q 2>&1 | tail -n 3 > gpurun_out/r2w_fattn.log
+timeout 300 python -m pytest tests/test_gpu_tgemm.py tests/test_gpu_engine.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -n 3 > gpurun_out/r3a_tests.log
+timeout 100 python scripts/profile_step.py c4 5 2>&1 | head -n 24 > gpurun_out/r3a_c4.log
