@@ -492,14 +492,17 @@ cudaError_t launch_twgrad(const WgradArgs& a, cudaStream_t st) {
 // ======================================================================================= GEMM + full-row epilogue (generation 2)
 // y = LayerNorm(drop(A W + bias) + residual) for hidden 256 (ROW_RES_DROP_LN of k_gemm.cu): one CTA tile = 128 whole
 // rows x 256 columns (a 256-column TMEM accumulator, double-buffered = all 512 columns), so the row statistics never
-// leave the CTA.  Epilogue thread = (row, 128-column half): pass 1 writes the bf16 pre-LN value and accumulates sum and
-// sum of squares, the two halves exchange them through shared memory, pass 2 re-reads the (L2-hot) pre-LN value and
-// normalises.  Same persistent producer / issuer / epilogue split as tgemm_kernel.
+// leave the CTA.  Epilogue thread = (row, 128-column half).  The tile's residual rows arrive by TMA in a 64 KB swizzled buffer;
+// pass 1 turns them IN PLACE into the bf16 pre-LN value (accumulating sum and sum of squares, exchanged between the two halves
+// through shared memory) which leaves by TMA store; pass 2 normalises in place and the LN output leaves by TMA store.  No
+// per-thread global row accesses remain (they touched 32 half-used sectors per instruction and cost ~17 us per tile).
+// Same persistent producer / issuer / epilogue split as tgemm_kernel.
 namespace b4r {
 using namespace encf;
 namespace {
-constexpr int TR_STAGES = 4, TR_STAGE = 128 * 128 + 64 * 256 * 2;   // 16 KB of A + 32 KB of W per 64-wide k-block
-constexpr int TR_SMEM = TR_STAGES * TR_STAGE + 2 * 2 * 128 * 2 * 4 + 256 + 1024;
+constexpr int TR_STAGES = 3, TR_STAGE = 128 * 128 + 64 * 256 * 2;   // 16 KB of A + 32 KB of W per 64-wide k-block
+constexpr int TR_BUF = 4 * 128 * 128;                                 // residual -> pre-LN -> LN output tile: 4 x [128][64] bf16
+constexpr int TR_SMEM = TR_STAGES * TR_STAGE + TR_BUF + 2 * 2 * 128 * 2 * 4 + 256 + 1024;
 struct TRowDev {
   int M, K;
   const float* bias; const float* gamma; const float* beta;
@@ -509,17 +512,20 @@ struct TRowDev {
 }  // namespace
 
 __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                                                        TRowDev a) {
+                                                        const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmP,
+                                                        const __grid_constant__ CUtensorMap tmY, TRowDev a) {
   constexpr int H = 256;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* sStat = reinterpret_cast<float*>(smem + TR_STAGES * TR_STAGE);   // [2 acc][2 halves][128 rows][2]
+  unsigned char* sBuf = smem + TR_STAGES * TR_STAGE;
+  float* sStat = reinterpret_cast<float*>(sBuf + TR_BUF);   // [2 acc][2 halves][128 rows][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * 2 * 128 * 2);
   uint64_t* full = bars;
   uint64_t* empty = bars + TR_STAGES;
   uint64_t* tfull = bars + 2 * TR_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* resfull = tempty + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(resfull + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (a.M + 127) / 128, kblocks = a.K / 64;
   const uint32_t step = a.step + (a.d_step ? (uint32_t)(*a.d_step) : 0u);
@@ -527,9 +533,11 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TR_STAGES; ++i) { umma::mbar_init(full + i, 1); umma::mbar_init(empty + i, 1); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(tfull + i, 1); umma::mbar_init(tempty + i, 8); }
+    umma::mbar_init(resfull, 1);
     umma::fence_barrier_init();
     umma::prefetch_tensormap(&tmA);
     umma::prefetch_tensormap(&tmW);
+    umma::prefetch_tensormap(&tmR); umma::prefetch_tensormap(&tmP); umma::prefetch_tensormap(&tmY);
   }
   if (warp == 1) umma::tmem_alloc<512>(tmem_holder);
   umma::fence_before_sync();
@@ -581,6 +589,13 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row_in_tile = quad * 32 + lane;
     const Philox ph(a.seed);
+    const bool leader = threadIdx.x == 64;
+    auto load_residual = [&](int tt) {
+      umma::mbar_expect_tx(resfull, TR_BUF);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) umma::tma_load_2d(sBuf + j * TILE_B, &tmR, j * 64, tt * 128, resfull);
+    };
+    if (leader && (int)blockIdx.x < n_tiles) load_residual(blockIdx.x);
     int ti = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
       const int acc = ti & 1;
@@ -588,10 +603,12 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
       const bool mok = m < a.M;
       umma::mbar_wait(tfull + acc, (ti >> 1) & 1);
       umma::fence_after_sync();
+      umma::mbar_wait(resfull, ti & 1);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int n = half * 128 + c * 32;
+        unsigned char* bt = sBuf + (n >> 6) * TILE_B;
         float v[32];
         tmem_ld_f32(tmem + ((uint32_t)(quad * 32) << 16) + acc * 256 + n, v);
 #pragma unroll
@@ -607,21 +624,15 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
             for (int i = 0; i < 8; ++i) v[8 * q + i] = ((bits >> i) & 1u) ? v[8 * q + i] * a.inv_keep : 0.f;
           }
         }
-        if (mok) {
-          const bf16* rp = a.residual + (size_t)m * H + n;
+        float res[32];
+        ld_tile<4>(bt, row_in_tile, (c & 1) * 4, res);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + 8 * q));
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        for (int i = 0; i < 32; ++i) v[i] += res[i];
+        uint32_t pk[16];
+        round_n<32>(v, pk);   // LN statistics are taken on the bf16-rounded value that backward will re-read
+        st_tile<4>(bt, row_in_tile, (c & 1) * 4, pk);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf162(w[i]); v[8 * q + 2 * i] += f.x; v[8 * q + 2 * i + 1] += f.y; }
-          }
-          uint32_t pk[16];
-          round_n<32>(v, pk);   // LN statistics are taken on the bf16-rounded value that backward will re-read
-          st_global<16>(a.pre + (size_t)m * H + n, pk);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 += v[i] * v[i]; }
-        }
+        for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 += v[i] * v[i]; }
       }
       // the accumulator has been read completely: hand it back to the MMA warp before the second pass
       umma::fence_before_sync();
@@ -629,39 +640,49 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
       if (lane == 0) umma::mbar_arrive(tempty + acc);
       float* st = sStat + ((acc * 2 + half) * 128 + row_in_tile) * 2;
       st[0] = s1; st[1] = s2;
+      umma::fence_proxy_async();
       asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      if (leader) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma::tma_store_2d(&tmP, sBuf + j * TILE_B, j * 64, t * 128);
+        umma::tma_store_commit();
+      }
       const float* so = sStat + ((acc * 2 + (half ^ 1)) * 128 + row_in_tile) * 2;
       const float t1 = half == 0 ? s1 + so[0] : so[0] + s1, t2 = half == 0 ? s2 + so[1] : so[1] + s2;
       const float mean = t1 * (1.0f / H);
       const float var = fmaxf(t2 * (1.0f / H) - mean * mean, 0.f);
       const float rstd = rsqrtf(var + kLnEps);
-      if (mok) {
+      if (leader) umma::tma_store_wait_read<0>();
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");     // the pre-LN store has read the buffer: normalise in place
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int n = half * 128 + c * 32;
-          const bf16* pp = a.pre + (size_t)m * H + n;
-          float v[32];
+      for (int c = 0; c < 4; ++c) {
+        const int n = half * 128 + c * 32;
+        unsigned char* bt = sBuf + (n >> 6) * TILE_B;
+        float v[32];
+        ld_tile<4>(bt, row_in_tile, (c & 1) * 4, v);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 u = *reinterpret_cast<const uint4*>(pp + 8 * q);
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf162(w[i]); v[8 * q + 2 * i] = f.x; v[8 * q + 2 * i + 1] = f.y; }
-          }
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma + n + i));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(a.beta + n + i));
-            v[i] = (v[i] - mean) * rstd * g.x + b.x; v[i + 1] = (v[i + 1] - mean) * rstd * g.y + b.y;
-            v[i + 2] = (v[i + 2] - mean) * rstd * g.z + b.z; v[i + 3] = (v[i + 3] - mean) * rstd * g.w + b.w;
-          }
-          uint32_t pk[16];
-          pack_n<32>(v, pk);
-          st_global<16>(a.y + (size_t)m * H + n, pk);
+        for (int i = 0; i < 32; i += 4) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma + n + i));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(a.beta + n + i));
+          v[i] = (v[i] - mean) * rstd * g.x + b.x; v[i + 1] = (v[i + 1] - mean) * rstd * g.y + b.y;
+          v[i + 2] = (v[i + 2] - mean) * rstd * g.z + b.z; v[i + 3] = (v[i + 3] - mean) * rstd * g.w + b.w;
         }
-        if (half == 0) { a.mean[m] = mean; a.rstd[m] = rstd; }
+        uint32_t pk[16];
+        pack_n<32>(v, pk);
+        st_tile<4>(bt, row_in_tile, (c & 1) * 4, pk);
+      }
+      if (mok && half == 0) { a.mean[m] = mean; a.rstd[m] = rstd; }
+      umma::fence_proxy_async();
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      if (leader) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma::tma_store_2d(&tmY, sBuf + j * TILE_B, j * 64, t * 128);
+        umma::tma_store_commit();
+        umma::tma_store_wait_read<0>();
+        if (t + (int)gridDim.x < n_tiles) load_residual(t + gridDim.x);
       }
     }
+    if (leader) umma::tma_store_wait<0>();
   }
   umma::fence_before_sync();
   __syncthreads();
@@ -675,12 +696,17 @@ bool trowln_supported(int mode, const RowLnArgs& a) {
   if (getenv("B4R_DISABLE_TGEMM")) return false;
   if (mode != ROW_RES_DROP_LN || a.H != 256 || a.a_rows || a.d_M) return false;
   if (a.K % 64 || a.K < 128 || a.M < 256 || a.lda % 8 || ((uintptr_t)a.A & 15) || ((uintptr_t)a.W & 15)) return false;
+  if (((uintptr_t)a.residual & 15) || ((uintptr_t)a.pre & 15) || ((uintptr_t)a.y & 15)) return false;   // TMA tiles
   return true;
 }
 cudaError_t launch_trowln(const RowLnArgs& a, cudaStream_t st) {
   CUtensorMap tmA, tmW;
   if (!make_tmap_bf16_sw128(&tmA, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, 128)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16_sw128(&tmW, a.W, (uint64_t)a.K, 256, 256, 64)) return cudaErrorInvalidValue;
+  CUtensorMap tmR, tmP, tmY;
+  if (!make_tmap_bf16_sw128(&tmR, a.residual, (uint64_t)a.M, 256, 256, 128) || !make_tmap_bf16_sw128(&tmP, a.pre, (uint64_t)a.M, 256, 256, 128) ||
+      !make_tmap_bf16_sw128(&tmY, a.y, (uint64_t)a.M, 256, 256, 128))
+    return cudaErrorInvalidValue;
   TRowDev d;
   d.M = a.M; d.K = a.K; d.bias = a.bias; d.gamma = a.gamma; d.beta = a.beta; d.residual = a.residual; d.pre = a.pre; d.y = a.y;
   d.mean = a.mean; d.rstd = a.rstd;
@@ -694,7 +720,7 @@ cudaError_t launch_trowln(const RowLnArgs& a, cudaStream_t st) {
     done = true;
   }
   const int tiles = (a.M + 127) / 128;
-  trowln_kernel<<<tiles < 148 ? tiles : 148, 320, TR_SMEM, st>>>(tmA, tmW, d);
+  trowln_kernel<<<tiles < 148 ? tiles : 148, 320, TR_SMEM, st>>>(tmA, tmW, tmR, tmP, tmY, d);
   return cudaGetLastError();
 }
 }  // namespace b4r
