@@ -159,49 +159,78 @@ cudaError_t launch_head_bwd_rows(const float* dt_part, int nsplit, size_t split_
 // block = 32 columns x 8 part-lanes; grid = (ceil(max_len/32), njobs).
 __global__ void __launch_bounds__(256) grad_reduce_kernel(const ReduceJob* __restrict__ jobs) {
   pdl_grid_sync();
-  __shared__ float s[8][33];
+  __shared__ float4 s[8][33];
   const ReduceJob job = jobs[blockIdx.y];
+  // grid.x is capped (launch_grad_reduce): every block strides over the job's column blocks.  A grid sized for the LONGEST job
+  // of the launch made the short jobs (biases, LayerNorm vectors) launch thousands of blocks that exited at once -- at C4
+  // (70 jobs x 8192 column blocks) the empty blocks, not the 0.6 GB of partials, were most of this kernel's 555 us.
   if (job.nparts <= 8) {
     // few, long partials (split-K weight gradients, vocabulary-sized buffers): 1024 columns per block, one thread per
     // column, coalesced
-    const int c0 = blockIdx.x * 1024;
-    if (c0 >= job.len) return;
+    for (int c0 = blockIdx.x * 1024; c0 < job.len; c0 += gridDim.x * 1024) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int col = c0 + k * 256 + threadIdx.x;
-      if (col < job.len) {
-        float v = 0.f;
-        for (int p = 0; p < job.nparts; ++p) v += job.src[(size_t)p * job.part_stride + col];
-        if (job.accumulate) v += job.dst[col];
-        job.dst[col] = v;
+      for (int k = 0; k < 4; ++k) {
+        const int col = c0 + k * 256 + threadIdx.x;
+        if (col < job.len) {
+          float v = 0.f;
+          for (int p = 0; p < job.nparts; ++p) v += job.src[(size_t)p * job.part_stride + col];
+          if (job.accumulate) v += job.dst[col];
+          job.dst[col] = v;
+        }
       }
     }
     return;
   }
-  // many partials (per-CTA bias / LayerNorm sums, token-split weight gradients): 32 columns x 8 part-lanes per block
-  const int cb = blockIdx.x * 32;
-  if (cb >= job.len) return;
+  // many partials (per-CTA bias / LayerNorm sums, token-split weight gradients): 32 column groups x 8 part-lanes per block; a
+  // column group is 4 consecutive columns (one 16-byte load) when the job's layout allows it, else 1 column
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int col = cb + tx;
-  float acc = 0.f;
-  if (col < job.len) {
-    const float* p = job.src + col;
-    int k = ty;
-    for (; k + 24 < job.nparts; k += 32) {
-      float a = p[(size_t)k * job.part_stride], b = p[(size_t)(k + 8) * job.part_stride];
-      float c = p[(size_t)(k + 16) * job.part_stride], d = p[(size_t)(k + 24) * job.part_stride];
-      acc += a; acc += b; acc += c; acc += d;
+  const bool wide = (job.len & 3) == 0 && (job.part_stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(job.src) | reinterpret_cast<uintptr_t>(job.dst)) & 15) == 0;
+  const int cw = wide ? 4 : 1;
+  for (int cb = blockIdx.x * 32 * cw; cb < job.len; cb += gridDim.x * 32 * cw) {
+    const int col = cb + tx * cw;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < job.len) {
+      const float* p = job.src + col;
+      if (wide) {
+        int k = ty;
+        for (; k + 24 < job.nparts; k += 32) {
+          const float4 a = *reinterpret_cast<const float4*>(p + (size_t)k * job.part_stride), b = *reinterpret_cast<const float4*>(p + (size_t)(k + 8) * job.part_stride);
+          const float4 c = *reinterpret_cast<const float4*>(p + (size_t)(k + 16) * job.part_stride), d = *reinterpret_cast<const float4*>(p + (size_t)(k + 24) * job.part_stride);
+          acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+          acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+          acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+          acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+        }
+        for (; k < job.nparts; k += 8) {
+          const float4 a = *reinterpret_cast<const float4*>(p + (size_t)k * job.part_stride);
+          acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        }
+      } else {
+        int k = ty;
+        for (; k + 24 < job.nparts; k += 32) {
+          float a = p[(size_t)k * job.part_stride], b = p[(size_t)(k + 8) * job.part_stride];
+          float c = p[(size_t)(k + 16) * job.part_stride], d = p[(size_t)(k + 24) * job.part_stride];
+          acc.x += a; acc.x += b; acc.x += c; acc.x += d;
+        }
+        for (; k < job.nparts; k += 8) acc.x += p[(size_t)k * job.part_stride];
+      }
     }
-    for (; k < job.nparts; k += 8) acc += p[(size_t)k * job.part_stride];
-  }
-  s[ty][tx] = acc;
-  __syncthreads();
-  if (ty == 0 && col < job.len) {
-    float v = 0.f;
+    __syncthreads();            // (the previous round's readers are done with s)
+    s[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && col < job.len) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v += s[r][tx];
-    if (job.accumulate) v += job.dst[col];
-    job.dst[col] = v;
+      for (int r = 0; r < 8; ++r) { v.x += s[r][tx].x; v.y += s[r][tx].y; v.z += s[r][tx].z; v.w += s[r][tx].w; }
+      if (wide) {
+        float4* d = reinterpret_cast<float4*>(job.dst + col);
+        if (job.accumulate) { const float4 o = *d; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        *d = v;
+      } else {
+        if (job.accumulate) v.x += job.dst[col];
+        job.dst[col] = v.x;
+      }
+    }
   }
 }
 
@@ -209,7 +238,7 @@ int grad_reduce_blocks(int nparts, int len) { return nparts <= 8 ? (len + 1023) 
 
 cudaError_t launch_grad_reduce(const ReduceJob* d_jobs, int njobs, int max_blocks, cudaStream_t st) {
   if (njobs <= 0) return cudaSuccess;
-  dim3 grid(max_blocks, njobs);
+  dim3 grid(max_blocks < 96 ? max_blocks : 96, njobs);   // blocks stride over the job's column blocks
   return launch_pdl(grad_reduce_kernel, grid, dim3(256), (size_t)0, st, d_jobs);
 }
 
