@@ -27,11 +27,12 @@ constexpr int TG_BM = 128, TG_BN = 128, TG_BK = 64, TG_STAGES = 4;   // (4 ring 
 constexpr int TG_EPI_WARPS = 16, TG_THREADS = 64 + 32 * TG_EPI_WARPS;   // producer + issuer + 16 epilogue warps
 constexpr int TG_A_BYTES = TG_BM * 128, TG_B_BYTES = TG_BN * 128, TG_STAGE = TG_A_BYTES + TG_B_BYTES;
 constexpr int TG_OUT_BYTES = TG_BM * TG_BN * 2;            // bf16 staging of one output tile: two [128][64] swizzled halves
-__host__ __device__ constexpr int tg_nout(int epi) { return epi == EPI_BIAS_GELU ? 2 : (epi == EPI_F32_RES ? 0 : 1); }
+__host__ __device__ constexpr int tg_nout(int epi) { return epi == EPI_BIAS_GELU ? 2 : (epi == EPI_F32_RES ? 0 : 1); }   // bf16 output tiles staged
+__host__ __device__ constexpr int tg_nf32(int epi) { return epi == EPI_F32_RES ? 2 : 0; }   // fp32 residual -> output tile, in place: 4 x [128][32] fp32 = 64 KB
 // GELU' reads its second operand (the saved pre-activation tile) through TMA as well: two 32 KB landing buffers, paid for with one ring stage
 __host__ __device__ constexpr int tg_naux(int epi) { return epi == EPI_GELU_GRAD ? 2 : 0; }
 __host__ __device__ constexpr int tg_stages(int epi) { return epi == EPI_GELU_GRAD ? 3 : 4; }
-__host__ __device__ constexpr int tg_smem(int epi) { return tg_stages(epi) * TG_STAGE + (tg_nout(epi) + tg_naux(epi)) * TG_OUT_BYTES + 2 * 4 * TG_BN * 4 + 256 + 1024; }   // ring + staging + column sums + barriers + align
+__host__ __device__ constexpr int tg_smem(int epi) { return tg_stages(epi) * TG_STAGE + (tg_nout(epi) + tg_naux(epi) + tg_nf32(epi)) * TG_OUT_BYTES + 2 * 4 * TG_BN * 4 + 256 + 1024; }   // ring + staging + column sums + barriers + align
 
 struct TGemmDev {
   int M, N, K;
@@ -55,14 +56,16 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
   constexpr int NST = tg_stages(EPI);
   unsigned char* sOut = smem + NST * TG_STAGE;                            // [NOUT][2 halves][128][64] bf16, 128-byte swizzle
   unsigned char* sAux = sOut + tg_nout(EPI) * TG_OUT_BYTES;               // [2 acc][2 halves][128][64] bf16 (GELU' only)
-  float* sCol = reinterpret_cast<float*>(sAux + tg_naux(EPI) * TG_OUT_BYTES);   // [2 acc][4 quads][128] column-sum partials
+  unsigned char* sF32 = sAux + tg_naux(EPI) * TG_OUT_BYTES;               // [4 column blocks][128][32] fp32 (F32_RES only)
+  float* sCol = reinterpret_cast<float*>(sF32 + tg_nf32(EPI) * TG_OUT_BYTES);   // [2 acc][4 quads][128] column-sum partials
   uint64_t* bars = reinterpret_cast<uint64_t*>(sCol + 2 * 4 * TG_BN);
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = bars + TG_STAGES;          // [STAGES]
   uint64_t* tfull = bars + 2 * TG_STAGES;      // [2]
   uint64_t* tempty = tfull + 2;                // [2]
   uint64_t* auxfull = tempty + 2;              // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(auxfull + 2);
+  uint64_t* resfull = auxfull + 2;             // [1]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(resfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (a.M + TG_BM - 1) / TG_BM, tiles_n = (a.N + TG_BN - 1) / TG_BN;
@@ -71,11 +74,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < TG_STAGES; ++i) { umma::mbar_init(full + i, 1); umma::mbar_init(empty + i, 1); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(tfull + i, 1); umma::mbar_init(tempty + i, TG_EPI_WARPS); umma::mbar_init(auxfull + i, 1); }
+    umma::mbar_init(resfull, 1);
     umma::fence_barrier_init();
     umma::prefetch_tensormap(&tmA);
     umma::prefetch_tensormap(&tmB);
-    if (tg_nout(EPI) > 0) umma::prefetch_tensormap(&tmO);
-    if (tg_nout(EPI) > 1 || tg_naux(EPI) > 0) umma::prefetch_tensormap(&tmO2);
+    if (tg_nout(EPI) > 0 || tg_nf32(EPI) > 0) umma::prefetch_tensormap(&tmO);
+    if (tg_nout(EPI) > 1 || tg_naux(EPI) > 0 || tg_nf32(EPI) > 0) umma::prefetch_tensormap(&tmO2);
   }
   if (warp == 1) umma::tmem_alloc<256>(tmem_holder);
   umma::fence_before_sync();
@@ -170,7 +174,16 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
         umma::tma_load_2d(dst + TILE_B, &tmO2, an0 + 64, am0, auxfull + (tti & 1));
       }
     };
+    auto res_load = [&](int tt) {                // fp32 residual tile of output tile tt -> the in-place buffer (tmO2 = residual map)
+      if (EPI == EPI_F32_RES && store_leader && tt < n_tiles) {
+        const int am0 = (tt / tiles_n) * TG_BM, an0 = (tt % tiles_n) * TG_BN;
+        umma::mbar_expect_tx(resfull, 2 * TG_OUT_BYTES);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma::tma_load_2d(sF32 + j * TILE_B, &tmO2, an0 + j * 32, am0, resfull);
+      }
+    };
     aux_load(blockIdx.x, 0);
+    res_load(blockIdx.x);
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
       const int acc = ti & 1;
       const int mt = t / tiles_n, m0 = mt * TG_BM, n0 = (t % tiles_n) * TG_BN;
@@ -256,14 +269,29 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
             sCol[(acc * 4 + quad) * TG_BN + cpart * 32 + col] = tot;
           }
         } else if (EPI == EPI_F32_RES) {
-          if (mok && nok) {
-            const float* rp = a.res_f32 + (size_t)m * a.ld_f32 + n;
-            float* op = a.out_f32 + (size_t)m * a.ld_f32 + n;
+          // out = acc + residual, fp32: the residual tile came in by TMA; add in place, TMA store, then fetch the next tile's residual
+          umma::mbar_wait(resfull, ti & 1);
+          unsigned char* bt = sF32 + cpart * TILE_B;       // this thread's 32 columns = one 128-byte row of column block cpart
+          {
+            const unsigned char* rp = bt + row_in_tile * 128;
+            uint32_t o[32];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 r = *reinterpret_cast<const float4*>(rp + i);
-              *reinterpret_cast<float4*>(op + i) = make_float4(v[i] + r.x, v[i + 1] + r.y, v[i + 2] + r.z, v[i + 3] + r.w);
+            for (int q = 0; q < 8; ++q) {
+              const float4 r4 = *reinterpret_cast<const float4*>(rp + ((q ^ (row_in_tile & 7)) << 4));
+              o[4 * q] = __float_as_uint(v[4 * q] + r4.x); o[4 * q + 1] = __float_as_uint(v[4 * q + 1] + r4.y);
+              o[4 * q + 2] = __float_as_uint(v[4 * q + 2] + r4.z); o[4 * q + 3] = __float_as_uint(v[4 * q + 3] + r4.w);
             }
+            st_tile<8>(bt, row_in_tile, 0, o);
+          }
+          umma::fence_proxy_async();
+          asm volatile("bar.sync 2, 512;\n" ::: "memory");
+          if (store_leader) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n0 + j * 32 < a.N) umma::tma_store_2d(&tmO, sF32 + j * TILE_B, n0 + j * 32, m0);
+            umma::tma_store_commit();
+            umma::tma_store_wait_read<0>();
+            res_load(t + gridDim.x);
           }
         }
       }
@@ -279,7 +307,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(tempty + acc);
     }
-    if (tg_nout(EPI) > 0 && store_leader) umma::tma_store_wait<0>();   // every bulk store has completed before the CTA retires
+    if ((tg_nout(EPI) > 0 || tg_nf32(EPI) > 0) && store_leader) umma::tma_store_wait<0>();   // every bulk store has completed before the CTA retires
   }
   umma::fence_before_sync();
   __syncthreads();
@@ -298,6 +326,7 @@ bool tgemm_supported(int epi, const GemmArgs& a) {
   if (a.K % TG_BK || a.N % 64 || a.K < min_k || a.M < 256) return false;   // small / narrow problems stay on the portable kernel
   if ((a.a_kmax && a.a_kmax != a.K) || (a.b_kmax && a.b_kmax != a.K)) return false;
   if (a.lda % 8 || a.ldb % 8 || ((uintptr_t)a.A & 15) || ((uintptr_t)a.B & 15)) return false;
+  if (tg_nf32(epi) > 0 && (a.ld_f32 % 4 || ((uintptr_t)a.out_f32 & 15) || ((uintptr_t)a.res_f32 & 15) || a.N % 32)) return false;
   if (tg_naux(epi) > 0 && (a.ld_aux % 8 || ((uintptr_t)a.aux_bf16 & 15))) return false;
   if (tg_nout(epi) > 0 && (a.ld_out % 8 || ((uintptr_t)a.out_bf16 & 15) || (tg_nout(epi) > 1 && ((uintptr_t)a.out2_bf16 & 15)))) return false;   // TMA stores
   return true;
@@ -326,6 +355,9 @@ cudaError_t launch_tgemm(int epi, const GemmArgs& a, cudaStream_t st) {
   CUtensorMap tmO = tmA, tmO2 = tmA;   // (placeholders when the epilogue has no bf16 output)
   if (tg_nout(epi) > 0 && !make_tmap_bf16_sw128(&tmO, a.out_bf16, (uint64_t)a.M, (uint64_t)a.N, (uint64_t)a.ld_out, TG_BM)) return cudaErrorInvalidValue;
   if (tg_nout(epi) > 1 && !make_tmap_bf16_sw128(&tmO2, a.out2_bf16, (uint64_t)a.M, (uint64_t)a.N, (uint64_t)a.ld_out, TG_BM)) return cudaErrorInvalidValue;
+  if (tg_nf32(epi) > 0 && (!make_tmap_f32_sw128(&tmO, a.out_f32, (uint64_t)a.M, (uint64_t)a.N, (uint64_t)a.ld_f32, TG_BM) ||
+                           !make_tmap_f32_sw128(&tmO2, a.res_f32, (uint64_t)a.M, (uint64_t)a.N, (uint64_t)a.ld_f32, TG_BM)))
+    return cudaErrorInvalidValue;
   if (tg_naux(epi) > 0 && !make_tmap_bf16_sw128(&tmO2, a.aux_bf16, (uint64_t)a.M, (uint64_t)a.N, (uint64_t)a.ld_aux, TG_BM)) return cudaErrorInvalidValue;
   TGemmDev d;
   d.M = a.M; d.N = a.N; d.K = a.K; d.bias = a.bias; d.out_bf16 = a.out_bf16; d.ld_out = a.ld_out; d.out2_bf16 = a.out2_bf16;

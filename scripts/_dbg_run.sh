@@ -1,4 +1,2 @@
-timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 3 > gpurun_out/r3b_tests.log
-timeout 100 python scripts/profile_step.py c4 5 2>&1 | grep -E "us/step|grad_reduce|embed|colsum" > gpurun_out/r3b_c4.log
-timeout 100 python scripts/profile_step.py c3 10 2>&1 | grep -E "us/step|grad_reduce" > gpurun_out/r3b_c3.log
-timeout 100 python scripts/profile_step.py c2 20 2>&1 | grep -E "us/step|grad_reduce" > gpurun_out/r3b_c2.log
+timeout 300 python -m pytest tests/test_gpu_tgemm.py tests/test_gpu_engine.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -n 3 > gpurun_out/r3c_tests.log
+timeout 100 python scripts/profile_step.py c4 5 2>&1 | head -n 14 > gpurun_out/r3c_c4.log
