@@ -1,2 +1,7 @@
-timeout 300 python -m pytest tests/test_gpu_tgemm.py tests/test_gpu_engine.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -n 3 > gpurun_out/r3c_tests.log
-timeout 100 python scripts/profile_step.py c4 5 2>&1 | head -n 14 > gpurun_out/r3c_c4.log
+set -e
+for w in c4 c3 c1; do
+  python scripts/ncu_step.py $w 3 > gpurun_out/plain_$w.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_$w.csv python scripts/ncu_step.py $w 3 > gpurun_out/ncu_$w.log 2>&1
+done
+python scripts/ncu_step.py c4 2 > gpurun_out/plain.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"fattn_bwd|fattn_fwd" -s 8 -c 2 -o gpurun_out/r02_fattn_c4 python scripts/ncu_step.py c4 2 > gpurun_out/ncu.log 2>&1
