@@ -9,7 +9,7 @@ LIB := bert4rec_b200/libb4r.so
 
 all: $(LIB)
 
-build/%.o: $(SRC_DIR)/%.cu $(wildcard $(SRC_DIR)/*.cuh) $(SRC_DIR)/kernels.h include/b4r.h
+build/%.o: $(SRC_DIR)/%.cu $(wildcard $(SRC_DIR)/*.cuh) $(SRC_DIR)/kernels.h include/b4r.h include/b4r_debug.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 

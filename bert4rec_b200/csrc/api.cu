@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/b4r.h"
+#include "../../include/b4r_debug.h"
 #include "common.cuh"
 #include "kernels.h"
 

@@ -215,22 +215,9 @@ int b4r_launch_count(b4r_session* s);   /* kernels launched through this session
  * flag 5: one-pass tcgen05 CE backward (1, default at hidden 64) or the two recompute passes (0);
  * flag 6: tcgen05 attention kernels of the layered encoder path (1, default) or the mma.sync generation (0) */
 int b4r_session_set_flag(b4r_session* s, int flag, int value);
-const void* b4r_debug_buffer(b4r_session* s);
-const void* b4r_debug_buffer2(b4r_session* s); /* uint64[512]: fused-kernel phase timestamps (ns) when B4R_FUSED_DEBUG is set */  /* kernel-internal timestamps when B4R_CE_DEBUG&8 (development aid) */
-/* per-kernel CUDA-event timing of everything launched through the session (events on the launching stream);
- * report: lines "tag count total_ms", synchronises, clears the records. */
-int b4r_profile_enable(b4r_session* s, int on);
-int b4r_profile_report(b4r_session* s, char* buf, int cap);
-
-/* ---- test helpers ------------------------------------------------------------------------------------------ */
-/* keep mask (1 byte / element) of an elementwise dropout site: site 1 = embedding, 2 = attention output, 3 = FFN output */
-int b4r_dropout_keep_mask(uint8_t* out, int rows, int cols, float rate, uint64_t seed, int site, int layer, uint32_t step,
-                          void* stream);
-/* standalone kernels for unit parity tests */
-int b4r_embed_ln_fwd(const int64_t* ids, const void* table_bf16, const void* pos_bf16, const float* gamma,
-                     const float* beta, void* out_bf16, int batch, int seq_len, int hidden, int vocab, void* stream);
-
-/* ---- optional DLPack adapter: validates a (borrowed) DLManagedTensor and returns its device pointer ---------- */
+/* ---- DLPack adapter: validates a (borrowed) DLManagedTensor (CUDA device, row-major contiguous, scalar dtype) and returns its
+ * device pointer; the Python host hands every int64 input of b4r_encode / b4r_mlm_select / b4r_rank_candidates over through it.
+ * Development / test helpers (profiling, debug buffers, standalone kernels) are declared in include/b4r_debug.h. */
 typedef struct b4r_dl_view { void* data; int32_t device_type, device_id, ndim, dtype_code, dtype_bits; int64_t shape[4]; } b4r_dl_view;
 int b4r_dl_view_of(const void* dl_managed_tensor, b4r_dl_view* out);
 

@@ -1,4 +1,4 @@
-"""CPU suite: the C-ABI library loads and exports every symbol include/b4r.h declares (no compute calls), the flat
+"""CPU suite: the C-ABI library loads and exports every symbol include/*.h declares (b4r.h = product ABI, b4r_debug.h = test helpers) (no compute calls), the flat
 parameter layout is sane, and the reference-facing factories keep their contract."""
 import ctypes as C
 import os
@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _header_functions():
-    src = open(os.path.join(ROOT, "include", "b4r.h")).read()
+    src = "".join(open(os.path.join(ROOT, "include", f)).read() for f in sorted(os.listdir(os.path.join(ROOT, "include"))) if f.endswith(".h"))
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(b4r_[a-z0-9_]+)\s*\(", src)))
 
@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     names = _header_functions()
     assert len(names) >= 25
     for n in names:
-        assert hasattr(lib, n), f"{n} declared in include/b4r.h but not exported by libb4r.so"
+        assert hasattr(lib, n), f"{n} declared in include/*.h but not exported by libb4r.so"
     assert set(names) == set(_lib.EXPORTED_SYMBOLS), set(names) ^ set(_lib.EXPORTED_SYMBOLS)
     assert lib.b4r_version() == 100
 
