@@ -413,12 +413,14 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 // TMEM is double buffered (2 x 256 columns): the control warp issues the score MMA of tile t+1 while the threads work on tile t,
 // and the epilogue of tile t-1 (which waits for its PV MMA) runs between the two passes of tile t.
 namespace {
-constexpr int FF_CT = 128 * FA_NG, FF_THREADS = FF_CT + 32;
+constexpr int FF_NG = 3;                              // column groups of the two score passes (the phases are dependency-latency bound:
+                                                      // 12 warps hide more of it than 8; 16 do not fit the register file)
+constexpr int FF_CT = 128 * FF_NG, FF_THREADS = FF_CT + 32;
 constexpr int FF_Q = 0, FF_K = 2, FF_V = 4, FF_P = 6, FF_TILES = 10;
 constexpr int FF_OFF_MASK = FF_TILES * TILE_B;           // float [2][256]  (item parity)
-constexpr int FF_OFF_REDM = FF_OFF_MASK + 2 * 256 * 4;   // float [2 tile parity][FA_NG column groups][128]
-constexpr int FF_OFF_REDL = FF_OFF_REDM + 2 * FA_NG * 128 * 4;
-constexpr int FF_OFF_BAR = FF_OFF_REDL + 2 * FA_NG * 128 * 4;
+constexpr int FF_OFF_REDM = FF_OFF_MASK + 2 * 256 * 4;   // float [2 tile parity][FF_NG column groups][128]
+constexpr int FF_OFF_REDL = FF_OFF_REDM + 2 * FF_NG * 128 * 4;
+constexpr int FF_OFF_BAR = FF_OFF_REDL + 2 * FF_NG * 128 * 4;
 constexpr int FF_SMEM = FF_OFF_BAR + 128 + 1024;
 
 struct FAttnFwdDev {
@@ -431,7 +433,7 @@ struct FAttnFwdDev {
 template <int D>
 __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, FAttnFwdDev a) {
   pdl_grid_wait();
-  constexpr int NHG = 64 / D, CPT = D / FA_NG;
+  constexpr int NHG = 64 / D, CPT = D / 2;          // the accumulator is drained by column groups 0 and 1
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* sMask = reinterpret_cast<float*>(smem + FF_OFF_MASK);
@@ -539,23 +541,25 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_c
     const uint32_t step = a.step + (a.d_step ? (uint32_t)(*a.d_step) : 0u);
     const Philox ph(a.seed);
     const int NC = (S16 + 31) >> 5;                  // 32-key chunks
-    const int c_lo = (wg * NC) / FA_NG, c_hi = ((wg + 1) * NC) / FA_NG;   // this thread's chunks (column group wg)
+    const int c_lo = (wg * NC) / FF_NG, c_hi = ((wg + 1) * NC) / FF_NG;   // this thread's chunks (column group wg)
     uint32_t gt = 0, nitem = 0;
     // state of the previous tile (its epilogue runs inside the next tile's iteration)
     float prev_m = 0.f; int prev_qi = 0, prev_b = 0, prev_col = 0, prev_bn = 0; bool have_prev = false;
     auto epilogue = [&](uint32_t gtile) {
       MBAR_WAIT(barO, gtile & 1, 4);
       umma::fence_after_sync();
-      const float* rl = sRedL + (gtile & 1) * (FA_NG * 128);
+      const float* rl = sRedL + (gtile & 1) * (FF_NG * 128);
       float l = 0.f;
 #pragma unroll
-      for (int q = 0; q < FA_NG; ++q) l += rl[q * 128 + row];
+      for (int q = 0; q < FF_NG; ++q) l += rl[q * 128 + row];
       uint32_t ro[CPT];
-      tmem_ld_n(tlane + (gtile & 1) * 256 + (prev_col & 63), ro);
-      umma::tmem_ld_wait();
+      if (wg < 2) {
+        tmem_ld_n(tlane + (gtile & 1) * 256 + (prev_col & 63), ro);
+        umma::tmem_ld_wait();
+      }
       umma::fence_before_sync();
       umma::mbar_arrive(barOF);
-      if (prev_qi < S) {
+      if (wg < 2 && prev_qi < S) {
         const float inv = 1.0f / l;
         float fo[CPT];
 #pragma unroll
@@ -589,12 +593,12 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) mloc = fmaxf(mloc, fmaf(__uint_as_float(rs[j]), c1, mk[c * 32 + j]));
         }
-        float* rm = sRedM + (gt & 1) * (FA_NG * 128);
+        float* rm = sRedM + (gt & 1) * (FF_NG * 128);
         rm[wg * 128 + row] = mloc;
         named_bar_sync(1, FF_CT);
         float m = rm[row];
 #pragma unroll
-        for (int q = 1; q < FA_NG; ++q) m = fmaxf(m, rm[q * 128 + row]);
+        for (int q = 1; q < FF_NG; ++q) m = fmaxf(m, rm[q * 128 + row]);
         // ---- epilogue of the previous tile (its PV MMA ran during pass 1)
         if (have_prev) epilogue(gt - 1);
         // ---- pass 2: probabilities -> P tiles
@@ -634,11 +638,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_c
           pack_n<32>(p, pk);
           st_tile<4>(tile(FF_P + (key0 >> 6)), row, (key0 & 63) >> 3, pk);
         }
-        sRedL[(gt & 1) * (FA_NG * 128) + wg * 128 + row] = lsum;
+        sRedL[(gt & 1) * (FF_NG * 128) + wg * 128 + row] = lsum;
         umma::fence_before_sync();
         umma::fence_proxy_async();
         umma::mbar_arrive(barP);
-        prev_m = m; prev_qi = qi; prev_b = b; prev_col = g * 64 + h * D + wg * CPT; prev_bn = bn; have_prev = true;
+        prev_m = m; prev_qi = qi; prev_b = b; prev_col = g * 64 + h * D + (wg & 1) * CPT; prev_bn = bn; have_prev = true;
       }
     }
     if (have_prev) {
