@@ -249,6 +249,19 @@ static int wgrad_splits(int M, int N, int T) {
   return s;
 }
 
+// Row splits of the dE pass of the tcgen05 CE backward: its grid is (vocabulary tiles x splits) CTAs of equal work, `ctas` resident at a
+// time, so the pass takes ceil(tiles * splits / ctas) / splits of the unsplit time -- choose the split count (<= 8, partial buffers grow with
+// it) that minimises that; e.g. 102 tiles on 148 resident CTAs: 1 split = one 69 %-full wave, 7 splits = 5 waves of 1/7 = 0.71.
+static int choose_me_splits(int vtiles, int ctas) {
+  int best = 1;
+  double best_t = 1e30;
+  for (int ms = 1; ms <= 8; ++ms) {
+    const double t = (double)((vtiles * ms + ctas - 1) / ctas) / ms;
+    if (t < best_t - 1e-9) { best_t = t; best = ms; }
+  }
+  return best;
+}
+
 static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<ReduceJob>* jobs, std::vector<ReduceJob>* jobs_f = nullptr) {
   Bump b{reinterpret_cast<char*>(ws), 0, cap, dry};
   const int T = s->T, H = s->H, I = s->I, V = s->V, N = s->N, B = s->B, S = s->S, Mcap = s->Mcap;
@@ -364,10 +377,7 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
     int vtiles = (V + 127) / 128;
     const int xtiles = (V + ce_bwd_umma_xtile(H) - 1) / ce_bwd_umma_xtile(H);
     s->dt_max_splits = xtiles < 24 ? xtiles : 24;
-    int ms = (ce_bwd_umma_xtile(H) == 64 ? 148 : 2 * 148) / vtiles;   // resident CTAs: two per SM, one at hidden 256
-    if (ms < 1) ms = 1;
-    if (ms > 8) ms = 8;
-    s->me_splits = ms;
+    s->me_splits = choose_me_splits(vtiles, ce_bwd_umma_xtile(H) == 64 ? 148 : 2 * 148);   // resident CTAs: two per SM, one at hidden 256
   }
   const bool bwd_umma = ce_bwd_umma_supported(H);
   s->dt_part = b.take<float>((size_t)(bwd_umma && s->dt_max_splits > s->dt_splits ? s->dt_max_splits : s->dt_splits) * Mcap * H);
@@ -928,10 +938,7 @@ static size_t shard_carve(b4r_shard* s, void* ws, size_t ws_bytes, bool dry) {
     int vs = xtiles < 24 ? xtiles : 24;
     if ((size_t)vs > ms) vs = (int)ms;
     s->dt_max_splits = vs < 1 ? 1 : vs;
-    int me = (xt == 64 ? 148 : 2 * 148) / vtiles;
-    if (me < 1) me = 1;
-    if (me > 8) me = 8;
-    s->me_splits = me;
+    s->me_splits = choose_me_splits(vtiles, xt == 64 ? 148 : 2 * 148);
   }
   s->dt_part = b.take<float>((size_t)s->dt_max_splits * cap * H);
   s->p_dE = b.take<float>((size_t)s->me_splits * Vs * H);

@@ -238,7 +238,8 @@ int grad_reduce_blocks(int nparts, int len) { return nparts <= 8 ? (len + 1023) 
 
 cudaError_t launch_grad_reduce(const ReduceJob* d_jobs, int njobs, int max_blocks, cudaStream_t st) {
   if (njobs <= 0) return cudaSuccess;
-  dim3 grid(max_blocks < 96 ? max_blocks : 96, njobs);   // blocks stride over the job's column blocks
+  const int cap = njobs > 8 ? 96 : 1184;                 // many jobs of very different lengths: few blocks per job, striding
+  dim3 grid(max_blocks < cap ? max_blocks : cap, njobs);
   return launch_pdl(grad_reduce_kernel, grid, dim3(256), (size_t)0, st, d_jobs);
 }
 
