@@ -293,12 +293,7 @@ __global__ void __launch_bounds__(256) ce_finalize_kernel(CeDev a, float* __rest
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (a.vsplits < 0) {  // generation-2 forward: same device-side split formula as ce_fwd_umma_kernel (128-row tiles)
     const int ntiles = (a.v_end - a.v_begin + 127) / 128;
-    int mt = (n_rows + 127) / 128; if (mt < 1) mt = 1;
-    int vs = a.target_ctas / mt;
-    if (vs > ntiles) vs = ntiles;
-    if (vs > a.max_splits) vs = a.max_splits;
-    if (vs < 1) vs = 1;
-    a.vsplits = vs;
+    a.vsplits = ce_dyn_splits128(n_rows, ntiles, a.target_ctas, a.max_splits);
   }
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // loss_sum, n_valid, correct_masked, correct_all, n_all
   // 8 lanes per row: lane q merges splits q, q+8, ...; the 8 lanes are then merged by an xor butterfly (fixed order)

@@ -68,13 +68,8 @@ struct CeBwdCfg {
 };
 
 __host__ __device__ inline int ce_bwd_dyn_splits(int n_rows, int ntiles, int target_ctas, int max_splits) {
-  int mt = (n_rows + CB_T - 1) / CB_T;
-  if (mt < 1) mt = 1;
-  int vs = target_ctas / mt;
-  if (vs > ntiles) vs = ntiles;
-  if (vs > max_splits) vs = max_splits;
-  if (vs < 1) vs = 1;
-  return vs;
+  static_assert(CB_T == 128, "ce_dyn_splits128 assumes 128-row tiles");
+  return ce_dyn_splits128(n_rows, ntiles, target_ctas, max_splits);
 }
 
 template <int H, bool ROW_IS_M>
@@ -367,7 +362,8 @@ cudaError_t launch_ce_bwd_umma(const CeUmmaMaps& maps, const CeBwdArgs& a, bool 
   const CUtensorMap& tmT = *reinterpret_cast<const CUtensorMap*>(row_is_m || !x64 ? maps.a : maps.a64);
   const CUtensorMap& tmE = *reinterpret_cast<const CUtensorMap*>(!row_is_m || !x64 ? maps.b : maps.b64);
   const int mtiles_cap = (a.M_cap + CB_T - 1) / CB_T, vtiles = (a.V + CB_T - 1) / CB_T;
-  const int grid = row_is_m ? a.target_ctas + mtiles_cap : vtiles * a.msplits;
+  const int xtiles = (a.V + ce_bwd_umma_xtile(a.H) - 1) / ce_bwd_umma_xtile(a.H);
+  const int grid = row_is_m ? ce_dyn_grid(a.target_ctas, mtiles_cap, xtiles, a.max_splits) : vtiles * a.msplits;
   if (a.H == 64) return row_is_m ? launch_ce_bwd_t<64, true>(tmT, tmE, d, grid, st) : launch_ce_bwd_t<64, false>(tmT, tmE, d, grid, st);
   if (a.H == 128) return row_is_m ? launch_ce_bwd_t<128, true>(tmT, tmE, d, grid, st) : launch_ce_bwd_t<128, false>(tmT, tmE, d, grid, st);
   if (a.H == 256) return row_is_m ? launch_ce_bwd_t<256, true>(tmT, tmE, d, grid, st) : launch_ce_bwd_t<256, false>(tmT, tmE, d, grid, st);

@@ -40,13 +40,8 @@ struct CeUmmaCfg {
 //   mtiles = ceil(n_rows/128), vsplits = clamp(ceil(target_ctas / mtiles), 1, min(max_splits, ntiles)),
 //   CTA id -> (m-tile = id / vsplits, split = id % vsplits).  ce_finalize uses the same formula.
 __host__ __device__ inline int ce_umma_dyn_splits(int n_rows, int ntiles, int target_ctas, int max_splits) {
-  int mt = (n_rows + UM_BM - 1) / UM_BM;
-  if (mt < 1) mt = 1;
-  int vs = target_ctas / mt;   // floor: (m-tiles x splits) fits in one wave of target_ctas resident CTAs
-  if (vs > ntiles) vs = ntiles;
-  if (vs > max_splits) vs = max_splits;
-  if (vs < 1) vs = 1;
-  return vs;
+  static_assert(UM_BM == 128, "ce_dyn_splits128 assumes 128-row tiles");
+  return ce_dyn_splits128(n_rows, ntiles, target_ctas, max_splits);
 }
 
 template <int H>
@@ -269,7 +264,7 @@ cudaError_t launch_ce_fwd_umma(const CeUmmaMaps& maps, const CeArgs& a, cudaStre
   d.target_ctas = a.target_ctas; d.max_splits = a.max_splits; d.part = a.part;
   { const char* e = getenv("B4R_CE_DEBUG"); d.debug = e ? atoi(e) : 0; }
   // capacity grid: enough CTAs for every (m-tile, split) pair any row count can produce
-  dim3 grid(a.target_ctas + (a.M_cap + UM_BM - 1) / UM_BM);
+  dim3 grid(ce_dyn_grid(a.target_ctas, (a.M_cap + UM_BM - 1) / UM_BM, (a.v_end - a.v_begin + UM_BN - 1) / UM_BN, a.max_splits));
   const CUtensorMap& tmA = *reinterpret_cast<const CUtensorMap*>(maps.a);
   const CUtensorMap& tmB = *reinterpret_cast<const CUtensorMap*>(maps.b);
 #define B4R_UM(HH)                                                                                                  \

@@ -33,12 +33,7 @@ __global__ void __launch_bounds__(256) head_bwd_fused_kernel(const float* __rest
   if (dyn_max < 0) {                        // one-pass CE backward: slots = vocabulary groups (dyn_vtiles = V, dyn_target = its CTAs)
     nsplit = cf_split(M, dyn_vtiles, dyn_target).b;
   } else if (dyn_max > 0) {                 // split count chosen on the device by the generation-2 dT pass
-    int mt = (M + 127) / 128; if (mt < 1) mt = 1;
-    int vs = dyn_target / mt;
-    if (vs > dyn_vtiles) vs = dyn_vtiles;
-    if (vs > dyn_max) vs = dyn_max;
-    if (vs < 1) vs = 1;
-    nsplit = vs;
+    nsplit = ce_dyn_splits128(M, dyn_vtiles, dyn_target, dyn_max);
   }
   for (int i = tid; i < HF_H * HF_H / 8; i += 256) {   // 8 bf16 per 16-byte load
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(wt) + i);

@@ -28,12 +28,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   pdl_grid_wait();
   if (d_M) M = min(M, *d_M);
   if (HEAD && dyn_max > 0) {  // split count chosen on the device by the generation-2 dT pass (same formula)
-    int mt = (M + 127) / 128; if (mt < 1) mt = 1;
-    int vs = dyn_target / mt;
-    if (vs > dyn_vtiles) vs = dyn_vtiles;
-    if (vs > dyn_max) vs = dyn_max;
-    if (vs < 1) vs = 1;
-    nsplit = vs;
+    nsplit = ce_dyn_splits128(M, dyn_vtiles, dyn_target, dyn_max);
   }
   if (d_step) step += (uint32_t)(*d_step);
   constexpr int LPR = H / 8, RPW = 32 / LPR, RPC = 8 * RPW;

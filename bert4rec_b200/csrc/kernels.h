@@ -295,15 +295,42 @@ __host__ __device__ inline CfSplit cf_split(int n_valid, int V, int ctas) {
 inline int ce_bwd_fused_dt_slot_cap(int V, int ctas) { const int nvr = ((V + 127) / 128 + CF_VR - 1) / CF_VR; return nvr < ctas ? nvr : ctas; }
 cudaError_t launch_ce_bwd_fused(const CeUmmaMaps& maps, const CeBwdFusedArgs& a, cudaStream_t st);
 cudaError_t launch_ce_bwd_fused_reduce(const CeBwdFusedArgs& a, float* g_table, float* g_bias, cudaStream_t st);
-// split count the generation-2 CE passes choose on the device (row tiles of 128): (row tiles x splits) fits one wave of target_ctas
+// Split count the generation-2 CE passes choose on the device from the number of live rows (row tiles of 128).  The grid is
+// (row tiles x splits) CTAs of equal work with `target_ctas` resident at a time.
+//  * mt <= target: floor(target / mt) splits = one wave (a launch grid of target + mtiles_cap covers it; CTAs without work exit at
+//    once, but every launched CTA of these kernels costs ~75 ns of scheduling, so the grid must stay close to the work).
+//  * mt > target (C4 / C5: more row tiles than resident CTAs): one split would be ceil(mt / target) FULL passes over the vocabulary
+//    (2.0 at C4's 320 tiles on 296 CTAs); with vs splits the pass takes ceil(mt * vs / target) / vs -- the vs <= 8 minimising that
+//    is taken (C4 forward: 7 splits = 8 waves of 1/7 = 1.14).
+// Every producer and consumer of the split partials calls this one function.
 __host__ __device__ inline int ce_dyn_splits128(int n_rows, int ntiles, int target_ctas, int max_splits) {
   int mt = (n_rows + 127) / 128;
   if (mt < 1) mt = 1;
-  int vs = target_ctas / mt;
-  if (vs > ntiles) vs = ntiles;
-  if (vs > max_splits) vs = max_splits;
-  if (vs < 1) vs = 1;
-  return vs;
+  int lim = max_splits < ntiles ? max_splits : ntiles;
+  if (lim < 1) lim = 1;
+  if (mt <= target_ctas) {
+    int vs = target_ctas / mt;
+    if (vs > lim) vs = lim;
+    return vs < 1 ? 1 : vs;
+  }
+  if (lim > 8) lim = 8;
+  int best = 1;
+  float best_t = 3.0e38f;
+  for (int vs = 1; vs <= lim; ++vs) {
+    const int waves = (mt * vs + target_ctas - 1) / target_ctas;
+    const float t = (float)waves / (float)vs + 0.002f * (float)vs;
+    if (t < best_t) { best_t = t; best = vs; }
+  }
+  return best;
+}
+// launch grid that covers every live-row count up to mtiles_cap row tiles
+inline int ce_dyn_grid(int target_ctas, int mtiles_cap, int ntiles, int max_splits) {
+  int g = target_ctas + mtiles_cap;
+  for (int mt = target_ctas + 1; mt <= mtiles_cap; ++mt) {
+    const int need = mt * ce_dyn_splits128(mt * 128, ntiles, target_ctas, max_splits);
+    if (need > g) g = need;
+  }
+  return g;
 }
 
 // ------------------------------------------------------------------ vocabulary-sharded projection, row-side helpers (k_shard.cu)
