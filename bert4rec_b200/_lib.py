@@ -97,6 +97,8 @@ _SIGNATURES = {
     "b4r_profile_report": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "b4r_dropout_keep_mask": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_int, C.c_int, C.c_uint32, _P]),
     "b4r_embed_ln_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "b4r_table_grad_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "b4r_table_grad": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "b4r_dl_view_of": (C.c_int, [_P, C.POINTER(DLView)]),
     "b4r_topk_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "b4r_topk_full": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),

@@ -213,7 +213,14 @@ struct b4r_session {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sel = nullptr;
   bool sel_pending = false, overlap_select = false;
+  // deterministic item-table gradient (k_tablegrad.cu): the token sort runs on its own branch beside the whole backward
+  cudaStream_t side_sort = nullptr;
+  cudaEvent_t ev_sort_fork = nullptr, ev_sort = nullptr;
+  TableGradArgs tg{};
   ~b4r_session() {
+    if (ev_sort_fork) cudaEventDestroy(ev_sort_fork);
+    if (ev_sort) cudaEventDestroy(ev_sort);
+    if (side_sort) cudaStreamDestroy(side_sort);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (ev_sel) cudaEventDestroy(ev_sel);
@@ -416,6 +423,11 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
   s->emb_bsplits = embed_bwd_bsplits(B);
   s->p_dpos = b.take<float>((size_t)s->emb_bsplits * S * H);
   s->p_embln = b.take<float>((size_t)s->emb_bsplits * S * 2 * H);
+  s->tg.T = T; s->tg.V = V; s->tg.H = H;
+  for (int i = 0; i < 2; ++i) { s->tg.keys[i] = b.take<uint32_t>((size_t)T); s->tg.vals[i] = b.take<uint32_t>((size_t)T); }
+  s->tg.hist = b.take<uint32_t>((size_t)256 * table_grad_sort_blocks(T));
+  s->tg.long_runs = b.take<int>((size_t)1 + 4 * table_grad_max_long_runs(T));
+  s->tg.carry = b.take<float>((size_t)table_grad_chunks(T) * 2 * H);
   in_layers = true;   // the fused backward reduces its own embedding partials (below)
   job(s->p_dpos, off("position_embedding"), s->emb_bsplits, S * H, (long long)S * H);
   job(s->p_embln, off("emb_ln/gamma"), s->emb_bsplits * S, H, 2 * H);
@@ -511,6 +523,9 @@ extern "C" int b4r_session_create(const b4r_config* cfg, int batch, int seq_len,
   CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&s->ev_sel, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&s->side_sort, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&s->ev_sort_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&s->ev_sort, cudaEventDisableTiming));
   if (enc_fused_supported(s->H, s->N, s->S, s->I)) {
     const int Ln = s->cfg.num_layers;
     std::vector<EncFusedLayerHost> lh(Ln);
@@ -710,6 +725,16 @@ static int backward_impl(b4r_session* s, uint64_t seed, uint32_t step, const int
   // gradient accumulators that are scatter / accumulate targets
   if (!bwd_umma && !ext_dt) CK(cudaMemsetAsync(G + oE, 0, (size_t)V * H * sizeof(float), st));
   CK(cudaMemsetAsync(s->dxa, 0, (size_t)T * H * sizeof(float), st));
+  // token sort of the embedding gradient: depends on the ids only, its own branch until the end of the backward
+  s->tg.ids = s->ids; s->tg.dx = s->dxa; s->tg.grad_table = G + oE;
+  CK(cudaEventRecord(s->ev_sort_fork, st));
+  CK(cudaStreamWaitEvent(s->side_sort, s->ev_sort_fork, 0));
+  {
+    cudaStream_t st_main = st; (void)st_main;
+    cudaStream_t st = s->side_sort;
+    KL("token_sort", launch_token_sort(s->tg, st));
+  }
+  CK(cudaEventRecord(s->ev_sort, s->side_sort));
   CeArgs c = ce_args(s);
   bool head_done = false;
   if (join_select(s, st)) return 1;
@@ -815,7 +840,7 @@ static int backward_impl(b4r_session* s, uint64_t seed, uint32_t step, const int
     f.out_drop = od; f.attn_drop = s->cfg.attention_dropout; f.seed = seed; f.step = step; f.d_step = d_step;
     f.dbg = getenv("B4R_FUSED_DEBUG") ? (void*)s->dbg_buf : nullptr;
     f.ids = s->ids; f.table = W + oE; f.pos = W + s->lay.find("position_embedding"); f.emb_g = P + s->lay.find("emb_ln/gamma");
-    f.grad_table = G + oE; f.dpos_part = s->enc_dpos; f.embln_part = s->enc_embln; f.V = V;
+    f.dx_rows = s->dxa; f.dpos_part = s->enc_dpos; f.embln_part = s->enc_embln; f.V = V;
     KL("enc_bwd_fused", launch_enc_bwd_fused(f, st));
   }
   for (int l = s->cfg.num_layers - 1; l >= 0 && !fbwd; --l) {
@@ -882,9 +907,20 @@ static int backward_impl(b4r_session* s, uint64_t seed, uint32_t step, const int
     }
   }
   if (!fbwd) KL("embed_bwd", launch_embed_bwd(s->ids, W + oE, W + s->lay.find("position_embedding"), P + s->lay.find("emb_ln/gamma"), s->dxa,
-                      G + oE, s->p_dpos, s->p_embln, s->B, s->S, H, V, od, seed, step, d_step, s->emb_bsplits, st));
+                      s->dxa, s->p_dpos, s->p_embln, s->B, s->S, H, V, od, seed, step, d_step, s->emb_bsplits, st));
+  // item-table gradient of the gather: fixed-order per-item sums of the dx rows on top of the tied-projection part.  It touches the
+  // table only, the final reduction everything else: the two run as parallel branches.
+  CK(cudaEventRecord(s->ev_sort_fork, st));
+  CK(cudaStreamWaitEvent(s->side_sort, s->ev_sort_fork, 0));
+  {
+    cudaStream_t st_main = st; (void)st_main;
+    cudaStream_t st = s->side_sort;
+    KL("table_grad", launch_table_grad(s->tg, st));
+  }
+  CK(cudaEventRecord(s->ev_sort, s->side_sort));
   if (fbwd) KL("grad_reduce:all", launch_grad_reduce(s->d_jobs_f, s->n_jobs_f, s->jobs_f_blocks, st));
   else KL("grad_reduce:all", launch_grad_reduce(s->d_jobs, s->n_jobs, s->jobs_max_len, st));
+  CK(cudaStreamWaitEvent(st, s->ev_sort, 0));
   return 0;
 }
 
@@ -1348,6 +1384,27 @@ extern "C" int b4r_embed_ln_fwd(const int64_t* ids, const void* table, const voi
   if (!ids || !table || !pos || !gamma || !beta || !out) return fail("null argument");
   CK(launch_embed_ln_fwd(ids, (const bf16*)table, (const bf16*)pos, gamma, beta, (bf16*)out, batch, seq_len, hidden, vocab,
                          0.f, 0, 0, nullptr, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" size_t b4r_table_grad_workspace_bytes(int tokens, int hidden) {
+  return (size_t)4 * 4 * tokens + 4 * 256 * (size_t)table_grad_sort_blocks(tokens) + 4 * (1 + 4 * (size_t)table_grad_max_long_runs(tokens)) +
+         4 * (size_t)table_grad_chunks(tokens) * 2 * hidden + 8 * 256;
+}
+extern "C" int b4r_table_grad(const int64_t* ids, const float* dx, float* grad_table, int tokens, int vocab, int hidden,
+                              void* workspace, void* stream) {
+  if (!ids || !dx || !grad_table || !workspace) return fail("null argument");
+  if (tokens < 1 || vocab < 1) return fail("empty problem");
+  TableGradArgs a{};
+  a.ids = ids; a.T = tokens; a.V = vocab; a.H = hidden; a.dx = dx; a.grad_table = grad_table;
+  char* w = reinterpret_cast<char*>(workspace);
+  auto take = [&](size_t bytes) { char* p = w; w += (bytes + 255) / 256 * 256; return p; };
+  for (int i = 0; i < 2; ++i) { a.keys[i] = (uint32_t*)take(4 * (size_t)tokens); a.vals[i] = (uint32_t*)take(4 * (size_t)tokens); }
+  a.hist = (uint32_t*)take(4 * 256 * (size_t)table_grad_sort_blocks(tokens));
+  a.long_runs = (int*)take(4 * (1 + 4 * (size_t)table_grad_max_long_runs(tokens)));
+  a.carry = (float*)take(4 * (size_t)table_grad_chunks(tokens) * 2 * hidden);
+  CK(launch_token_sort(a, (cudaStream_t)stream));
+  CK(launch_table_grad(a, (cudaStream_t)stream));
   return 0;
 }
 

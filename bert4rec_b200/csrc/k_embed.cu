@@ -86,14 +86,15 @@ cudaError_t launch_embed_ln_fwd(const int64_t* ids, const bf16* table, const bf1
 
 // ------------------------------------------------------------------------------------------------ backward
 // grid = (S, bsplits).  CTA (s, z) walks batch rows b = z, z+bsplits, ... for position s: recomputes the LN input
-// (gather again - cheaper than saving it), applies dropout' and LN backward, scatter-adds the row into the item
-// table gradient (red.global.add.f32) and accumulates the position gradient / LN parameter gradients locally.
+// (gather again - cheaper than saving it), applies dropout' and LN backward, writes the row's dx (dx_rows may alias d_out:
+// in place) and accumulates the position gradient / LN parameter gradients locally.  The item-table gradient is NOT
+// scattered here: k_tablegrad.cu sums the dx rows per item in a fixed order (bit-reproducible, no hot-row atomics).
 int embed_bwd_bsplits(int B) { return B >= 64 ? 4 : 1; }
 
 template <int H>
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ table,
                                                         const bf16* __restrict__ pos, const float* __restrict__ gamma,
-                                                        const float* __restrict__ d_out, float* __restrict__ grad_table,
+                                                        const float* d_out, float* dx_rows,
                                                         float* __restrict__ dpos_part, float* __restrict__ dln_part, int B,
                                                         int S, int V, uint32_t thr16, float inv_keep, uint64_t seed,
                                                         uint32_t step, const long long* __restrict__ d_step) {
@@ -101,8 +102,6 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restric
   if (d_step) step += (uint32_t)(*d_step);
   constexpr int LPR = H / 8, RPW = 32 / LPR, RPC = 8 * RPW;  // rows per CTA pass
   __shared__ float s_red[3][RPC][H + 1];
-  __shared__ float s_dx[RPC][H];   // dx rows of one pass, for the in-CTA aggregation of repeated items
-  __shared__ int s_id[RPC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, l = lane % LPR, c0 = l * 8;
   const int s = blockIdx.x, z = blockIdx.y, nz = gridDim.y;
@@ -177,30 +176,12 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restric
         a_b[i] += dy[i];
       }
     }
-    // Rows of this pass that gather the same item (popular items repeat) are summed in shared memory first; one vector
-    // reduction per distinct item of the pass goes to the table (the hot rows otherwise serialise in L2).
-    *reinterpret_cast<float4*>(&s_dx[slot][c0]) = make_float4(dx[0], dx[1], dx[2], dx[3]);
-    *reinterpret_cast<float4*>(&s_dx[slot][c0 + 4]) = make_float4(dx[4], dx[5], dx[6], dx[7]);
-    if (l == 0) s_id[slot] = ok ? (int)id : -1;
-    __syncthreads();
+    // dx of the gathered row replaces d_out in place (same thread, same addresses); the item-table gradient is the
+    // fixed-order segmented sum of these rows over the id-sorted token list (k_tablegrad.cu)
     if (ok) {
-      const int my = (int)id;
-      bool leader = true;
-      for (int r = 0; r < slot && leader; ++r) leader = s_id[r] != my;
-      if (leader) {
-        for (int r = slot + 1; r < RPC; ++r) {
-          if (s_id[r] == my) {
-            const float4 o0 = *reinterpret_cast<const float4*>(&s_dx[r][c0]);
-            const float4 o1 = *reinterpret_cast<const float4*>(&s_dx[r][c0 + 4]);
-            dx[0] += o0.x; dx[1] += o0.y; dx[2] += o0.z; dx[3] += o0.w; dx[4] += o1.x; dx[5] += o1.y; dx[6] += o1.z; dx[7] += o1.w;
-          }
-        }
-        float* g = grad_table + (size_t)id * H + c0;
-        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(g), "f"(dx[0]), "f"(dx[1]), "f"(dx[2]), "f"(dx[3]) : "memory");
-        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(g + 4), "f"(dx[4]), "f"(dx[5]), "f"(dx[6]), "f"(dx[7]) : "memory");
-      }
+      *reinterpret_cast<float4*>(dx_rows + (size_t)t * H + c0) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+      *reinterpret_cast<float4*>(dx_rows + (size_t)t * H + c0 + 4) = make_float4(dx[4], dx[5], dx[6], dx[7]);
     }
-    __syncthreads();
   }
   // CTA reduction over the RPC row slots (fixed order -> deterministic for dpos / dgamma / dbeta)
 #pragma unroll
@@ -220,16 +201,16 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restric
 }
 
 cudaError_t launch_embed_bwd(const int64_t* ids, const bf16* table, const bf16* pos, const float* gamma,
-                             const float* d_out, float* grad_table, float* dpos_part, float* dln_part, int B, int S,
+                             const float* d_out, float* dx_rows, float* dpos_part, float* dln_part, int B, int S,
                              int H, int V, float drop_rate, uint64_t seed, uint32_t step, const long long* d_step,
                              int bsplits, cudaStream_t st) {
   uint32_t thr = drop_threshold16(drop_rate);
   float inv_keep = 1.0f / (1.0f - (float)thr / 65536.0f);
   dim3 grid(S, bsplits);
   switch (H) {
-    case 64: launch_pdl(embed_bwd_kernel<64>, dim3(grid), dim3(256), (size_t)(0), st, ids, table, pos, gamma, d_out, grad_table, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
-    case 128: launch_pdl(embed_bwd_kernel<128>, dim3(grid), dim3(256), (size_t)(0), st, ids, table, pos, gamma, d_out, grad_table, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
-    case 256: launch_pdl(embed_bwd_kernel<256>, dim3(grid), dim3(256), (size_t)(0), st, ids, table, pos, gamma, d_out, grad_table, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
+    case 64: launch_pdl(embed_bwd_kernel<64>, dim3(grid), dim3(256), (size_t)(0), st, ids, table, pos, gamma, d_out, dx_rows, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
+    case 128: launch_pdl(embed_bwd_kernel<128>, dim3(grid), dim3(256), (size_t)(0), st, ids, table, pos, gamma, d_out, dx_rows, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
+    case 256: launch_pdl(embed_bwd_kernel<256>, dim3(grid), dim3(256), (size_t)(0), st, ids, table, pos, gamma, d_out, dx_rows, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

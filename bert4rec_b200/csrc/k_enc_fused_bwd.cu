@@ -90,7 +90,7 @@ struct EncBwdDev {
   float* bpart;              // [L][nCTA][PF] bias / LayerNorm gradient partials, laid out like the parameter block
   // embedding stage backward (fused tail): LN backward + dropout', scatter-add into the item-table gradient
   const int64_t* ids; const bf16* table; const bf16* pos; const float* emb_g;
-  float* grad_table;         // [V][64] fp32 (already holds the tied-projection part)
+  float* dx_rows;            // [T][64] fp32: gradient of the gathered table rows (may alias dx: each CTA overwrites its own rows)
   float* dpos_part;          // [nCTA][S][64]
   float* embln_part;         // [nCTA][128] gamma | beta
   int V;
@@ -694,34 +694,17 @@ __global__ void __launch_bounds__(NTHR, 1) enc_bwd_fused_kernel(EncBwdDev a) {
     for (int i = 0; i < 16; ++i) dO[i] = rstd * (dO[i] - s1 - x[i] * s2);
     // stage dx rows (fp32) and the item ids of the tile in the (dead) arena
     float* sDx = reinterpret_cast<float*>(smem);                 // [128 rows][64]
-    int* sIds = reinterpret_cast<int*>(smem + 2 * TILE_B);       // [128]
     umma::fence_before_sync();
     __syncthreads();                                             // every MMA / tile read of the last layer is complete
 #pragma unroll
     for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(sDx + row * FH + cq + i) = make_float4(dO[i], dO[i + 1], dO[i + 2], dO[i + 3]);
-    if (part == 0) sIds[row] = valid ? (int)id : -1;
     __syncthreads();
-    // item-table gradient: rows of the tile with the same item are summed here first (popular items repeat), then ONE
-    // vector reduction per distinct item of the tile goes to the table
-    {
-      const int my = valid ? (int)id : -2;
-      bool leader = valid;
-      for (int r = 0; r < row && leader; ++r) leader = sIds[r] != my;
-      if (leader) {
-        for (int r = row + 1; r < FT; ++r) {
-          if (sIds[r] == my) {
+    // item-table gradient: the dx rows go to memory (in place over the incoming gradient of the tile's own rows); their per-item
+    // sums are taken in a fixed order over the id-sorted token list (k_tablegrad.cu) -- no floating-point atomics
+    if (valid) {
+      float* gr = a.dx_rows + (size_t)t * FH + cq;
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 o = *reinterpret_cast<const float4*>(sDx + r * FH + cq + i);
-              dO[i] += o.x; dO[i + 1] += o.y; dO[i + 2] += o.z; dO[i + 3] += o.w;
-            }
-          }
-        }
-        float* gt = a.grad_table + (size_t)id * FH + cq;
-#pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(gt + i), "f"(dO[i]), "f"(dO[i + 1]), "f"(dO[i + 2]), "f"(dO[i + 3]) : "memory");
-      }
+      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(gr + i) = make_float4(dO[i], dO[i + 1], dO[i + 2], dO[i + 3]);
     }
     // position gradient: sum over the G sequences of the tile (fixed order), one partial per CTA
     float* dp = a.dpos_part + (size_t)blockIdx.x * S * FH;
@@ -767,7 +750,7 @@ cudaError_t launch_enc_bwd_fused(const EncBwdArgs& a, cudaStream_t st) {
   size_t moff = ((size_t)a.L * sizeof(LayerDev) + 127) / 128 * 128;
   d.maps = reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const char*>(a.dev_tables) + moff);
   d.dx = a.dx; d.wpart = a.wpart; d.bpart = a.bpart;
-  d.ids = a.ids; d.table = a.table; d.pos = a.pos; d.emb_g = a.emb_g; d.grad_table = a.grad_table; d.dpos_part = a.dpos_part;
+  d.ids = a.ids; d.table = a.table; d.pos = a.pos; d.emb_g = a.emb_g; d.dx_rows = a.dx_rows; d.dpos_part = a.dpos_part;
   d.embln_part = a.embln_part; d.V = a.V;
   d.B = a.B; d.S = a.S; d.L = a.L; d.slot = a.S <= 32 ? 32 : (a.S <= 64 ? 64 : 128); d.I = a.I;
   d.thr_out = drop_threshold16(a.out_drop); d.thr_attn = drop_threshold16(a.attn_drop);

@@ -93,13 +93,37 @@ cudaError_t launch_twgrad(const WgradArgs& a, cudaStream_t st);
 cudaError_t launch_embed_ln_fwd(const int64_t* ids, const bf16* table, const bf16* pos, const float* gamma,
                                 const float* beta, bf16* out, int B, int S, int H, int V, float drop_rate,
                                 uint64_t seed, uint32_t step, const long long* d_step, cudaStream_t st);
-// d_out fp32 [T][H] -> dE (atomic scatter-add into grad_table fp32 [V][H]), dpos partials [bsplits][S*H],
-// dgamma/dbeta partials [nparts][2H]
+// d_out fp32 [T][H] -> dx rows (fp32 [T][H], may alias d_out), dpos partials [bsplits][S*H], dgamma/dbeta partials [nparts][2H].
+// The item-table gradient is the per-item sum of the dx rows: launch_table_grad (k_tablegrad.cu).
 cudaError_t launch_embed_bwd(const int64_t* ids, const bf16* table, const bf16* pos, const float* gamma,
-                             const float* d_out, float* grad_table, float* dpos_part, float* dln_part, int B, int S,
+                             const float* d_out, float* dx_rows, float* dpos_part, float* dln_part, int B, int S,
                              int H, int V, float drop_rate, uint64_t seed, uint32_t step, const long long* d_step,
                              int bsplits, cudaStream_t st);
 int embed_bwd_bsplits(int B);
+
+// ------------------------------------------------------------------ deterministic item-table gradient (k_tablegrad.cu)
+// grad_table[id] += sum over the tokens t with ids[t] == id of dx[t], in a FIXED order: the tokens are sorted by (id, t) with a
+// stable LSD radix sort (integer work, depends on the batch only: runs on a side branch of the step), the sorted list is cut
+// into chunks of 64 (16 for small batches) tokens that are summed run by run, and runs that cross chunk boundaries are finished from per-chunk
+// carries in chunk order.  No floating-point atomics: the result is bit-reproducible and popular items do not serialise.
+struct TableGradArgs {
+  const int64_t* ids;     // [T] token ids (clamped to [0, V) like the gather)
+  int T, V, H;
+  uint32_t* keys[2];      // [T] each: sort ping-pong (item ids)
+  uint32_t* vals[2];      // [T] each: sort ping-pong (token indices)
+  uint32_t* hist;         // [256 * table_grad_sort_blocks(T)] digit-major block histograms
+  int* long_runs;         // [1 + 4 * table_grad_max_long_runs(T)]: count, then {first token, end token, id, -} per long run
+  float* carry;           // [table_grad_chunks(T)][2][H] head / tail partial rows of every chunk
+  const float* dx;        // [T][H] fp32 rows to sum
+  float* grad_table;      // [V][H] fp32, accumulated into (one read-modify-write per item, by one thread per column)
+};
+int table_grad_sort_blocks(int T);
+int table_grad_chunk_tokens(int T);   // 16 (small batches) or 64
+int table_grad_chunks(int T);
+int table_grad_max_long_runs(int T);
+cudaError_t launch_token_sort(const TableGradArgs& a, cudaStream_t st);    // keys/vals[table_grad_sorted_buf(V)] = sorted (id, t)
+int table_grad_sorted_buf(int V);
+cudaError_t launch_table_grad(const TableGradArgs& a, cudaStream_t st);    // 2 launches: chunk sums, boundary runs
 
 // ------------------------------------------------------------------ attention (k_attn.cu)
 struct AttnArgs {
@@ -159,7 +183,7 @@ struct EncBwdArgs {
   float* wpart; float* bpart;
   // embedding stage backward (fused tail)
   const int64_t* ids; const bf16* table; const bf16* pos; const float* emb_g;
-  float* grad_table; float* dpos_part; float* embln_part; int V;
+  float* dx_rows; float* dpos_part; float* embln_part; int V;
   int B, S, L, I;
   float out_drop, attn_drop; uint64_t seed; uint32_t step; const long long* d_step;
   void* dbg;

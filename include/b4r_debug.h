@@ -22,6 +22,11 @@ int b4r_dropout_keep_mask(uint8_t* out, int rows, int cols, float rate, uint64_t
 /* standalone kernels for unit parity tests */
 int b4r_embed_ln_fwd(const int64_t* ids, const void* table_bf16, const void* pos_bf16, const float* gamma,
                      const float* beta, void* out_bf16, int batch, int seq_len, int hidden, int vocab, void* stream);
+/* deterministic item-table gradient of the embedding gather, standalone: grad_table[ids[t]] += dx[t] (fp32 rows of `hidden`
+ * columns, hidden in {64, 128, 256}) in a fixed summation order; workspace of b4r_table_grad_workspace_bytes() device bytes */
+size_t b4r_table_grad_workspace_bytes(int tokens, int hidden);
+int b4r_table_grad(const int64_t* ids, const float* dx, float* grad_table, int tokens, int vocab, int hidden, void* workspace,
+                   void* stream);
 
 #ifdef __cplusplus
 }
