@@ -322,7 +322,8 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
     job(L.p_ln1 + H, L.be1, ln_parts, H, 3 * H);
     job(L.p_ln1 + 2 * H, L.bo, ln_parts, H, 3 * H);
     job(L.p_b1, L.b1, mt128, I, I);
-    job(L.p_bqkv, L.bqkv, kColsumSplits, 3 * H, 3 * H);
+    // hidden 256: the tcgen05 weight-gradient kernel of Wqkv also sums the columns of dQKV (one partial row per token split)
+    job(L.p_bqkv, L.bqkv, twgrad_shape_ok(H, 3 * H, T) ? L.s_wqkv : kColsumSplits, 3 * H, 3 * H);
   }
   in_layers = false;
   s->fused_bwd_ok = enc_bwd_fused_supported(H, N, S, I);
@@ -892,11 +893,16 @@ static int backward_impl(b4r_session* s, uint64_t seed, uint32_t step, const int
       a.drop_rate = s->cfg.attention_dropout; a.dctx = s->dctx; a.dqkv = s->dqkv; a.no_tcgen05 = !s->use_fattn;
       KL("attn_bwd", launch_attn_bwd(a, st));
     }
-    KL("colsum:bqkv", launch_colsum_bf16(s->dqkv, 3 * H, T, 3 * H, nullptr, 0, L.p_bqkv, kColsumSplits, st));
+    const bool bias_in_wgrad = twgrad_shape_ok(H, 3 * H, T);
+    if (!bias_in_wgrad) KL("colsum:bqkv", launch_colsum_bf16(s->dqkv, 3 * H, T, 3 * H, nullptr, 0, L.p_bqkv, kColsumSplits, st));
     {
       WgradArgs w{};
       w.X = x_in; w.ldx = H; w.dY = s->dqkv; w.ldy = 3 * H; w.M = H; w.N = 3 * H; w.T = T; w.splits = L.s_wqkv;
       w.out = L.p_wqkv; w.split_stride = (size_t)H * 3 * H; w.ld_out = 3 * H;
+      if (bias_in_wgrad) {
+        w.colsum_part = L.p_bqkv;
+        if (!twgrad_supported(w)) return fail("the tcgen05 weight-gradient kernel rejected the Wqkv problem it was planned for");
+      }
       KL("wgrad:wqkv", launch_wgrad(w, st));
     }
     {

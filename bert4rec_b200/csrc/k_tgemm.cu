@@ -391,7 +391,7 @@ using namespace encf;
 namespace {
 constexpr int TW_STAGES = 3, TW_STAGE = 2 * 64 * 256 * 2;   // 32 KB of X + 32 KB of dY per 64-token k-block
 constexpr int TW_SMEM = TW_STAGES * TW_STAGE + 256 + 1024;
-struct TWgradDev { int M, N, T, t_per_split, tiles_n; float* out; size_t split_stride; int ld_out; };
+struct TWgradDev { int M, N, T, t_per_split, tiles_n; float* out; size_t split_stride; int ld_out; float* colsum; };
 }  // namespace
 
 __global__ void __launch_bounds__(320, 1) twgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
@@ -409,9 +409,12 @@ __global__ void __launch_bounds__(320, 1) twgrad_kernel(const __grid_constant__ 
   const int m0 = (tile / a.tiles_n) * 256, n0 = (tile % a.tiles_n) * 256;
   const int t_begin = z * a.t_per_split, t_end = min(a.T, t_begin + a.t_per_split);
   const int kblocks = t_end > t_begin ? (t_end - t_begin + 63) / 64 : 0;
+  // column sums of dY (= the bias gradient of the layer that produced it) ride along: the eight epilogue warps are idle during
+  // the main loop and read every dY stage from shared memory before it is released (one more arrival per warp on `empty`)
+  const bool do_colsum = a.colsum != nullptr && m0 == 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TW_STAGES; ++i) { umma::mbar_init(full + i, 1); umma::mbar_init(empty + i, 1); }
+    for (int i = 0; i < TW_STAGES; ++i) { umma::mbar_init(full + i, 1); umma::mbar_init(empty + i, do_colsum ? 9 : 1); }
     umma::mbar_init(tfull, 1);
     umma::fence_barrier_init();
     umma::prefetch_tensormap(&tmX);
@@ -464,6 +467,36 @@ __global__ void __launch_bounds__(320, 1) twgrad_kernel(const __grid_constant__ 
     const int quad = warp & 3, h = (warp - 2) >> 2;
     const int m = m0 + h * 128 + quad * 32 + lane;
     float* dst = a.out + (size_t)z * a.split_stride + (size_t)m * a.ld_out + n0;
+    if (do_colsum) {
+      // thread = (feature pair p of the 256 columns, half of the 64 token rows of a stage); tiles are [64 rows][64 features] boxes,
+      // 128-byte rows, 16-byte chunks XOR-swizzled with the row
+      const int et = threadIdx.x - 64, p = et & 127, rh = et >> 7;
+      const uint32_t box = (uint32_t)(p >> 5) * 8192u, chunk = (uint32_t)(p & 31) >> 2, inner = (uint32_t)(p & 3) * 4u;
+      float c0 = 0.f, c1 = 0.f;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int st = kb % TW_STAGES;
+        umma::mbar_wait(full + st, (kb / TW_STAGES) & 1);
+        const uint32_t sB = umma::smem_addr(smem + st * TW_STAGE + TW_STAGE / 2) + box + inner;
+#pragma unroll 8
+        for (int r = rh * 32; r < rh * 32 + 32; ++r) {
+          uint32_t w;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sB + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4)));
+          const float2 f = unpack_bf162(w);
+          c0 += f.x; c1 += f.y;
+        }
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(empty + st);
+      }
+      // the two row halves meet in the (now idle) first stage buffer; fixed order: rows 0-31 of every stage first
+      if (kblocks > 0) umma::mbar_wait(tfull, 0);       // every MMA has read its operands: the ring is free
+      float2* sx = reinterpret_cast<float2*>(smem);
+      if (rh == 1) sx[p] = make_float2(c0, c1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (rh == 0) {
+        const float2 o = sx[p];
+        *reinterpret_cast<float2*>(a.colsum + (size_t)z * a.N + n0 + 2 * p) = make_float2(kblocks > 0 ? c0 + o.x : 0.f, kblocks > 0 ? c1 + o.y : 0.f);
+      }
+    }
     if (kblocks > 0) {
       umma::mbar_wait(tfull, 0);
       umma::fence_after_sync();
@@ -507,7 +540,7 @@ cudaError_t launch_twgrad(const WgradArgs& a, cudaStream_t st) {
   if (!make_tmap_bf16_sw128(&tmX, a.X, (uint64_t)a.T, (uint64_t)a.M, (uint64_t)a.ldx, 64)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16_sw128(&tmY, a.dY, (uint64_t)a.T, (uint64_t)a.N, (uint64_t)a.ldy, 64)) return cudaErrorInvalidValue;
   TWgradDev d;
-  d.M = a.M; d.N = a.N; d.T = a.T; d.tiles_n = a.N / 256; d.out = a.out; d.split_stride = a.split_stride; d.ld_out = a.ld_out;
+  d.M = a.M; d.N = a.N; d.T = a.T; d.tiles_n = a.N / 256; d.out = a.out; d.split_stride = a.split_stride; d.ld_out = a.ld_out; d.colsum = a.colsum_part;
   d.t_per_split = ((a.T + a.splits - 1) / a.splits + 63) / 64 * 64;
   static bool done = false;
   if (!done) {

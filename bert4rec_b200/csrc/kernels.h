@@ -81,6 +81,7 @@ struct WgradArgs {
   float* out; size_t split_stride;             // partials (accumulate==0) or final (splits==1, accumulate==1: out += )
   int ld_out; int accumulate;
   int x_mmax;                                  // valid columns of X (multiple of 8; defaults to M rounded up)
+  float* colsum_part;                          // optional (tcgen05 kernel only): column sums of dY per token split, [splits][N]
 };
 cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t st);
 // generation 2 (k_tgemm.cu): tcgen05 weight gradient for M, N multiples of 256; launch_wgrad dispatches to it
