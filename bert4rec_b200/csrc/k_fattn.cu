@@ -420,7 +420,8 @@ constexpr int FF_Q = 0, FF_K = 2, FF_V = 4, FF_P = 6, FF_TILES = 10;
 constexpr int FF_OFF_MASK = FF_TILES * TILE_B;           // float [2][256]  (item parity)
 constexpr int FF_OFF_REDM = FF_OFF_MASK + 2 * 256 * 4;   // float [2 tile parity][FF_NG column groups][128]
 constexpr int FF_OFF_REDL = FF_OFF_REDM + 2 * FF_NG * 128 * 4;
-constexpr int FF_OFF_BAR = FF_OFF_REDL + 2 * FF_NG * 128 * 4;
+constexpr int FF_OFF_PAD = FF_OFF_REDL + 2 * FF_NG * 128 * 4;   // int [2] (item parity): != 0 when the sequence has padded keys
+constexpr int FF_OFF_BAR = FF_OFF_PAD + 16;
 constexpr int FF_SMEM = FF_OFF_BAR + 128 + 1024;
 
 struct FAttnFwdDev {
@@ -439,6 +440,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_c
   float* sMask = reinterpret_cast<float*>(smem + FF_OFF_MASK);
   float* sRedM = reinterpret_cast<float*>(smem + FF_OFF_REDM);
   float* sRedL = reinterpret_cast<float*>(smem + FF_OFF_REDL);
+  int* sPad = reinterpret_cast<int*>(smem + FF_OFF_PAD);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FF_OFF_BAR);
   // barS is per TMEM buffer: the score MMAs of tiles t and t+1 need nothing from the compute threads, so a single barrier could
   // complete two phases before a thread polls the first one (and a parity wait cannot tell phase t from phase t+2)
@@ -455,6 +457,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_c
     umma::mbar_init(barLQ, 1); umma::mbar_init(barLV, 1); umma::mbar_init(barS, 1); umma::mbar_init(barS + 1, 1); umma::mbar_init(barP, FF_CT);
     umma::mbar_init(barO, 1); umma::mbar_init(barOF, FF_CT);
     umma::fence_barrier_init();
+    sPad[0] = 0; sPad[1] = 0;
   }
   if (warp == FF_CT / 32) {
     umma::tmem_alloc<512>(tmem_holder);
@@ -540,6 +543,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_c
     const float c1 = rsqrtf((float)D) * kLog2e;
     const uint32_t step = a.step + (a.d_step ? (uint32_t)(*a.d_step) : 0u);
     const Philox ph(a.seed);
+    const float log2_inv_keep = __log2f(a.inv_keep), keep_prob = 1.0f / a.inv_keep;
     const int NC = (S16 + 31) >> 5;                  // 32-key chunks
     const int c_lo = (wg * NC) / FF_NG, c_hi = ((wg + 1) * NC) / FF_NG;   // this thread's chunks (column group wg)
     uint32_t gt = 0, nitem = 0;
@@ -573,25 +577,46 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_c
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++nitem) {
       const int b = item / G, g = item % G;
       float* mk = sMask + (nitem & 1) * 256;
-      if (tid < 256) mk[tid] = tid < S ? (a.mask[(size_t)b * S + tid] != 0 ? 0.f : -1e9f * kLog2e) : -INFINITY;
+      if (tid < 256) {
+        const bool padded = tid < S && a.mask[(size_t)b * S + tid] == 0;
+        mk[tid] = tid < S ? (padded ? -1e9f * kLog2e : 0.f) : -INFINITY;
+        if (padded) atomicOr(sPad + (nitem & 1), 1);
+      }
       // (made visible by the named barrier of the first tile's max exchange)
+      bool dense = false;      // no padded key in this sequence: chunks that lie inside the sequence need no mask term
       for (int t = 0; t < n_t; ++t, ++gt) {
         const int h = t / MT, mt = t % MT;
         const int head = g * NHG + h, bn = b * a.N + head;
         const int qi = mt * 128 + row;
         const bool valid = qi < S;
+        // a warp whose 32 query rows all lie past the sequence end has nothing to compute: its rows of P only feed rows of O that
+        // are never stored (the MMA keeps rows independent), whatever the tile holds
+        const bool warp_live = mt * 128 + quad * 32 < S;
         const uint32_t tS = tlane + (gt & 1) * 256;
         MBAR_WAIT(barS + (gt & 1), (gt >> 1) & 1, 2);
         umma::fence_after_sync();
-        if (t == 0) named_bar_sync(1, FF_CT);
+        if (t == 0) {
+          named_bar_sync(1, FF_CT);
+          dense = sPad[nitem & 1] == 0;
+          if (tid == 0) sPad[(nitem + 1) & 1] = 0;   // next item's flag: its writers are behind this tile's max exchange barrier
+        }
         // ---- pass 1: row maximum (log2 units)
         float mloc = -INFINITY;
-        for (int c = c_lo; c < c_hi; ++c) {
-          uint32_t rs[32];
-          ld_chunk(tS + c * 32, c * 32 + 32 <= S16, rs);
-          umma::tmem_ld_wait();
+        if (warp_live) {
+          for (int c = c_lo; c < c_hi; ++c) {
+            uint32_t rs[32];
+            ld_chunk(tS + c * 32, c * 32 + 32 <= S16, rs);
+            umma::tmem_ld_wait();
+            if (dense && c * 32 + 32 <= S) {
+              float mx = __uint_as_float(rs[0]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mloc = fmaxf(mloc, fmaf(__uint_as_float(rs[j]), c1, mk[c * 32 + j]));
+              for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(rs[j]));
+              mloc = fmaxf(mloc, mx * c1);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) mloc = fmaxf(mloc, fmaf(__uint_as_float(rs[j]), c1, mk[c * 32 + j]));
+            }
+          }
         }
         float* rm = sRedM + (gt & 1) * (FF_NG * 128);
         rm[wg * 128 + row] = mloc;
@@ -601,9 +626,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_c
         for (int q = 1; q < FF_NG; ++q) m = fmaxf(m, rm[q * 128 + row]);
         // ---- epilogue of the previous tile (its PV MMA ran during pass 1)
         if (have_prev) epilogue(gt - 1);
-        // ---- pass 2: probabilities -> P tiles
+        // ---- pass 2: probabilities -> P tiles.  With dropout the kept values are p / (1 - r): the factor rides in the exponent
+        // (mo = m - log2(1 / (1 - r))), the row sum is taken on the scaled values and scaled back once.
         float lsum = 0.f;
-        for (int c = c_lo; c < c_hi; ++c) {
+        const float mo = drop ? m - log2_inv_keep : m;
+        for (int c = c_lo; c < c_hi && warp_live; ++c) {
           const int key0 = c * 32;
           uint32_t rs[32];
           ld_chunk(tS + key0, key0 + 32 <= S16, rs);
@@ -627,17 +654,26 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_c
           }
           umma::tmem_ld_wait();
           float p[32];
+          if (dense && key0 + 32 <= S) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = ex2(fmaf(__uint_as_float(rs[j]), c1, mk[key0 + j]) - m);
-            lsum += v;
-            if (drop) v = ((bits >> j) & 1u) ? v * a.inv_keep : 0.f;
-            p[j] = v;
+            for (int j = 0; j < 32; ++j) {
+              const float v = ex2(fmaf(__uint_as_float(rs[j]), c1, -mo));
+              lsum += v;
+              p[j] = ((bits >> j) & 1u) ? v : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = ex2(fmaf(__uint_as_float(rs[j]), c1, mk[key0 + j]) - mo);
+              lsum += v;
+              p[j] = ((bits >> j) & 1u) ? v : 0.f;
+            }
           }
           uint32_t pk[16];
           pack_n<32>(p, pk);
           st_tile<4>(tile(FF_P + (key0 >> 6)), row, (key0 & 63) >> 3, pk);
         }
+        if (drop) lsum *= keep_prob;
         sRedL[(gt & 1) * (FF_NG * 128) + wg * 128 + row] = lsum;
         umma::fence_before_sync();
         umma::fence_proxy_async();
