@@ -94,7 +94,7 @@ int embed_bwd_bsplits(int B) { return B >= 64 ? 4 : 1; }
 template <int H>
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ table,
                                                         const bf16* __restrict__ pos, const float* __restrict__ gamma,
-                                                        const float* d_out, float* dx_rows,
+                                                        const float* d_out, const bf16* __restrict__ d_branch, float* dx_rows,
                                                         float* __restrict__ dpos_part, float* __restrict__ dln_part, int B,
                                                         int S, int V, uint32_t thr16, float inv_keep, uint64_t seed,
                                                         uint32_t step, const long long* __restrict__ d_step) {
@@ -139,6 +139,12 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restric
       const float4 d0 = *reinterpret_cast<const float4*>(d_out + (size_t)t * H + c0);
       const float4 d1 = *reinterpret_cast<const float4*>(d_out + (size_t)t * H + c0 + 4);
       dy[0] = d0.x; dy[1] = d0.y; dy[2] = d0.z; dy[3] = d0.w; dy[4] = d1.x; dy[5] = d1.y; dy[6] = d1.z; dy[7] = d1.w;
+      if (d_branch) {   // + the bf16 output of the first layer's QKV data-gradient GEMM
+        const uint4 bv = *reinterpret_cast<const uint4*>(d_branch + (size_t)t * H + c0);
+        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 f = unpack_bf162(bw[i]); dy[2 * i] += f.x; dy[2 * i + 1] += f.y; }
+      }
       if (thr16 > 0) {
         uint32_t bits = keep_bits8(ph, (uint32_t)t, (uint32_t)l, site_id(SITE_EMB, 0), step, thr16);
 #pragma unroll
@@ -201,16 +207,16 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restric
 }
 
 cudaError_t launch_embed_bwd(const int64_t* ids, const bf16* table, const bf16* pos, const float* gamma,
-                             const float* d_out, float* dx_rows, float* dpos_part, float* dln_part, int B, int S,
+                             const float* d_out, const bf16* d_branch, float* dx_rows, float* dpos_part, float* dln_part, int B, int S,
                              int H, int V, float drop_rate, uint64_t seed, uint32_t step, const long long* d_step,
                              int bsplits, cudaStream_t st) {
   uint32_t thr = drop_threshold16(drop_rate);
   float inv_keep = 1.0f / (1.0f - (float)thr / 65536.0f);
   dim3 grid(S, bsplits);
   switch (H) {
-    case 64: launch_pdl(embed_bwd_kernel<64>, dim3(grid), dim3(256), (size_t)(0), st, ids, table, pos, gamma, d_out, dx_rows, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
-    case 128: launch_pdl(embed_bwd_kernel<128>, dim3(grid), dim3(256), (size_t)(0), st, ids, table, pos, gamma, d_out, dx_rows, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
-    case 256: launch_pdl(embed_bwd_kernel<256>, dim3(grid), dim3(256), (size_t)(0), st, ids, table, pos, gamma, d_out, dx_rows, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
+    case 64: launch_pdl(embed_bwd_kernel<64>, dim3(grid), dim3(256), (size_t)(0), st, ids, table, pos, gamma, d_out, d_branch, dx_rows, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
+    case 128: launch_pdl(embed_bwd_kernel<128>, dim3(grid), dim3(256), (size_t)(0), st, ids, table, pos, gamma, d_out, d_branch, dx_rows, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
+    case 256: launch_pdl(embed_bwd_kernel<256>, dim3(grid), dim3(256), (size_t)(0), st, ids, table, pos, gamma, d_out, d_branch, dx_rows, dpos_part, dln_part, B, S, V, thr, inv_keep, seed, step, d_step); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

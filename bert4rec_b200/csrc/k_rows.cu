@@ -16,9 +16,9 @@ int ln_bwd_parts(int M) { return (M + 63) / 64; }
 // HEAD=true : MLM transform LayerNorm: d_out = sum of nsplit split-K partials, the LN input is gelu(t_pre) so the
 //             branch gradient is additionally multiplied by gelu'(t_pre); no d_pre output.
 template <int H, bool HEAD>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d_out, const bf16* __restrict__ pre,
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* d_out, const bf16* __restrict__ branch, const bf16* __restrict__ pre,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                     const float* __restrict__ gamma, float* __restrict__ d_pre,
+                                                     const float* __restrict__ gamma, float* d_pre,
                                                      bf16* __restrict__ d_branch, float* __restrict__ partials, int M,
                                                      uint32_t thr16, float inv_keep, uint64_t seed, uint32_t site,
                                                      uint32_t step, int nsplit, size_t split_stride,
@@ -54,6 +54,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
         const float4 d0 = *reinterpret_cast<const float4*>(src);
         const float4 d1 = *reinterpret_cast<const float4*>(src + 4);
         dy[0] += d0.x; dy[1] += d0.y; dy[2] += d0.z; dy[3] += d0.w; dy[4] += d1.x; dy[5] += d1.y; dy[6] += d1.z; dy[7] += d1.w;
+      }
+      if (!HEAD && branch) {   // gradient that arrived through the sublayer above (bf16 output of its data-gradient GEMM)
+        const uint4 bv = *reinterpret_cast<const uint4*>(branch + (size_t)m * H + c0);
+        const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 f = unpack_bf162(bw[i]); dy[2 * i] += f.x; dy[2 * i + 1] += f.y; }
       }
       const uint4 pv = *reinterpret_cast<const uint4*>(pre + (size_t)m * H + c0);
       const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
@@ -118,7 +124,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   }
 }
 
-cudaError_t launch_ln_bwd(const float* d_out, const bf16* pre, const float* mean, const float* rstd,
+cudaError_t launch_ln_bwd(const float* d_out, const bf16* branch, const bf16* pre, const float* mean, const float* rstd,
                           const float* gamma, float* d_pre, bf16* d_branch, float* partials, int M, int H,
                           float drop_rate, uint64_t seed, uint32_t site, uint32_t step, const long long* d_step,
                           cudaStream_t st) {
@@ -126,9 +132,9 @@ cudaError_t launch_ln_bwd(const float* d_out, const bf16* pre, const float* mean
   float inv_keep = 1.0f / (1.0f - (float)thr / 65536.0f);
   int grid = ln_bwd_parts(M);
   switch (H) {
-    case 64: launch_pdl(ln_bwd_kernel<64, false>, dim3(grid), dim3(256), (size_t)(0), st, d_out, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr, d_step, 0, 0, 0); break;
-    case 128: launch_pdl(ln_bwd_kernel<128, false>, dim3(grid), dim3(256), (size_t)(0), st, d_out, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr, d_step, 0, 0, 0); break;
-    case 256: launch_pdl(ln_bwd_kernel<256, false>, dim3(grid), dim3(256), (size_t)(0), st, d_out, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr, d_step, 0, 0, 0); break;
+    case 64: launch_pdl(ln_bwd_kernel<64, false>, dim3(grid), dim3(256), (size_t)(0), st, d_out, branch, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr, d_step, 0, 0, 0); break;
+    case 128: launch_pdl(ln_bwd_kernel<128, false>, dim3(grid), dim3(256), (size_t)(0), st, d_out, branch, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr, d_step, 0, 0, 0); break;
+    case 256: launch_pdl(ln_bwd_kernel<256, false>, dim3(grid), dim3(256), (size_t)(0), st, d_out, branch, pre, mean, rstd, gamma, d_pre, d_branch, partials, M, thr, inv_keep, seed, site, step, 1, 0, nullptr, nullptr, d_step, 0, 0, 0); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -141,9 +147,9 @@ cudaError_t launch_head_bwd_rows(const float* dt_part, int nsplit, size_t split_
   int grid = ln_bwd_parts(M_cap);
   const int* d_M = d_counts;   // n_valid: aux rows carry no gradient
   switch (H) {
-    case 64: launch_pdl(ln_bwd_kernel<64, true>, dim3(grid), dim3(256), (size_t)(0), st, dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
-    case 128: launch_pdl(ln_bwd_kernel<128, true>, dim3(grid), dim3(256), (size_t)(0), st, dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
-    case 256: launch_pdl(ln_bwd_kernel<256, true>, dim3(grid), dim3(256), (size_t)(0), st, dt_part, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
+    case 64: launch_pdl(ln_bwd_kernel<64, true>, dim3(grid), dim3(256), (size_t)(0), st, dt_part, nullptr, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
+    case 128: launch_pdl(ln_bwd_kernel<128, true>, dim3(grid), dim3(256), (size_t)(0), st, dt_part, nullptr, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
+    case 256: launch_pdl(ln_bwd_kernel<256, true>, dim3(grid), dim3(256), (size_t)(0), st, dt_part, nullptr, act, mean, rstd, gamma, nullptr, d_tpre, partials, M_cap, 0, 1.f, 0, 0, 0, nsplit, split_stride, t_pre, d_M, nullptr, dyn_vtiles, dyn_target, dyn_max); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

@@ -97,7 +97,7 @@ cudaError_t launch_embed_ln_fwd(const int64_t* ids, const bf16* table, const bf1
 // d_out fp32 [T][H] -> dx rows (fp32 [T][H], may alias d_out), dpos partials [bsplits][S*H], dgamma/dbeta partials [nparts][2H].
 // The item-table gradient is the per-item sum of the dx rows: launch_table_grad (k_tablegrad.cu).
 cudaError_t launch_embed_bwd(const int64_t* ids, const bf16* table, const bf16* pos, const float* gamma,
-                             const float* d_out, float* dx_rows, float* dpos_part, float* dln_part, int B, int S,
+                             const float* d_out, const bf16* d_branch /* optional bf16 addend of d_out */, float* dx_rows, float* dpos_part, float* dln_part, int B, int S,
                              int H, int V, float drop_rate, uint64_t seed, uint32_t step, const long long* d_step,
                              int bsplits, cudaStream_t st);
 int embed_bwd_bsplits(int B);
@@ -197,8 +197,10 @@ cudaError_t launch_enc_bwd_fused(const EncBwdArgs& a, cudaStream_t st);
 
 // ------------------------------------------------------------------ row kernels (k_rows.cu)
 // LayerNorm backward over rows (+ dropout of the branch gradient):
-//   d_pre = LNbwd(d_out) ; d_branch = drop(d_pre) (bf16) ; partials[cta] = {dgamma[H], dbeta[H], dbranch_colsum[H]}
-cudaError_t launch_ln_bwd(const float* d_out, const bf16* pre, const float* mean, const float* rstd,
+//   d_pre = LNbwd(d_out + branch) ; d_branch = drop(d_pre) (bf16) ; partials[cta] = {dgamma[H], dbeta[H], dbranch_colsum[H]}
+// d_out is the fp32 gradient of the residual stream, `branch` (optional) the bf16 gradient that the data-gradient GEMM of the
+// sublayer above produced; d_pre may alias d_out (the residual-stream gradient is updated in place).
+cudaError_t launch_ln_bwd(const float* d_out, const bf16* branch, const bf16* pre, const float* mean, const float* rstd,
                           const float* gamma, float* d_pre, bf16* d_branch, float* partials, int M, int H,
                           float drop_rate, uint64_t seed, uint32_t site, uint32_t step, const long long* d_step,
                           cudaStream_t st);
