@@ -382,10 +382,12 @@ cudaError_t launch_tgemm(int epi, const GemmArgs& a, cudaStream_t st) {
 }  // namespace b4r
 
 // ======================================================================================= weight gradient (generation 2)
-// dW[M,N] = X^T dY, contraction over the T token rows, for M, N multiples of 256 (hidden 256 models).  Both operands are
-// read in place as MN-major tiles ([64 token rows][64 features] TMA boxes); one CTA owns a 256 x 256 output tile (two
-// M = 128 accumulators of 256 TMEM columns each) and a contiguous range of token rows (split over T, deterministic fp32
-// partials summed by grad_reduce_kernel).  256 x 256 tiles read X N/256 times and dY M/256 times: HBM-bound by design.
+// dW[M,N] = X^T dY, contraction over the T token rows.  Both operands are read in place as MN-major tiles ([64 token rows][64
+// features] TMA boxes); one CTA owns a 256 x 256 output tile (two M = 128 accumulators of 256 TMEM columns each) and a contiguous
+// range of token rows (split over T, deterministic fp32 partials summed by grad_reduce_kernel).  256 x 256 tiles read X N/256 times
+// and dY M/256 times: HBM-bound by design.  M and N need not fill the tile (hidden 64 / 128 models: 64 x 192, 64 x 256, 256 x 64 ...):
+// feature boxes that lie completely outside the matrix are not loaded, the second accumulator is skipped when M <= 128 and the
+// MMA's N shrinks to the valid columns; a partly valid box is zero-filled by TMA.  Rows / columns past M / N are never stored.
 namespace b4r {
 using namespace encf;
 namespace {
@@ -409,6 +411,9 @@ __global__ void __launch_bounds__(320, 1) twgrad_kernel(const __grid_constant__ 
   const int m0 = (tile / a.tiles_n) * 256, n0 = (tile % a.tiles_n) * 256;
   const int t_begin = z * a.t_per_split, t_end = min(a.T, t_begin + a.t_per_split);
   const int kblocks = t_end > t_begin ? (t_end - t_begin + 63) / 64 : 0;
+  const int m_ext = min(256, a.M - m0), n_ext = min(256, a.N - n0);      // valid part of this CTA's 256 x 256 tile
+  const int nbA = (m_ext + 63) / 64, nbB = (n_ext + 63) / 64;            // 64-feature boxes to load per k-block
+  const int nh = m_ext > 128 ? 2 : 1;                                    // M = 128 accumulators in use
   // column sums of dY (= the bias gradient of the layer that produced it) ride along: the eight epilogue warps are idle during
   // the main loop and read every dY stage from shared memory before it is released (one more arrival per warp on `empty`)
   const bool do_colsum = a.colsum != nullptr && m0 == 0;
@@ -431,21 +436,20 @@ __global__ void __launch_bounds__(320, 1) twgrad_kernel(const __grid_constant__ 
       for (int kb = 0; kb < kblocks; ++kb) {
         const int st = kb % TW_STAGES;
         umma::mbar_wait(empty + st, ((kb / TW_STAGES) & 1) ^ 1);
-        umma::mbar_expect_tx(full + st, TW_STAGE);
+        umma::mbar_expect_tx(full + st, (uint32_t)((nbA + nbB) * 8192));
         unsigned char* sA = smem + st * TW_STAGE;
         unsigned char* sB = sA + TW_STAGE / 2;
         const int t0 = t_begin + kb * 64;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          umma::tma_load_2d(sA + j * 8192, &tmX, m0 + j * 64, t0, full + st);
-          umma::tma_load_2d(sB + j * 8192, &tmY, n0 + j * 64, t0, full + st);
-        }
+        for (int j = 0; j < nbA; ++j) umma::tma_load_2d(sA + j * 8192, &tmX, m0 + j * 64, t0, full + st);
+        for (int j = 0; j < nbB; ++j) umma::tma_load_2d(sB + j * 8192, &tmY, n0 + j * 64, t0, full + st);
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       const uint64_t DMN0 = desc_mn_sw128(umma::smem_addr(smem), 8192);
-      constexpr uint32_t idesc = idesc_gen(128, 256, 1, 1);
+      // (rows of an accumulator that come from boxes that were not loaded hold whatever the ring held: the MMA keeps rows
+      // independent and those rows are not stored)
+      const uint32_t idesc = idesc_gen(128, (n_ext + 15) & ~15, 1, 1);
       for (int kb = 0; kb < kblocks; ++kb) {
         const int st = kb % TW_STAGES;
         umma::mbar_wait(full + st, (kb / TW_STAGES) & 1);
@@ -453,8 +457,7 @@ __global__ void __launch_bounds__(320, 1) twgrad_kernel(const __grid_constant__ 
         const uint32_t offA = st * TW_STAGE, offB = offA + TW_STAGE / 2;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
+          for (int h = 0; h < nh; ++h)
             umma::mma_bf16_ss(tmem + h * 256, desc_at(DMN0, offA + h * 16384 + k * 2048), desc_at(DMN0, offB + k * 2048), idesc,
                               (kb | k) ? 1u : 0u);
         umma::mma_commit(empty + st);
@@ -494,7 +497,8 @@ __global__ void __launch_bounds__(320, 1) twgrad_kernel(const __grid_constant__ 
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (rh == 0) {
         const float2 o = sx[p];
-        *reinterpret_cast<float2*>(a.colsum + (size_t)z * a.N + n0 + 2 * p) = make_float2(kblocks > 0 ? c0 + o.x : 0.f, kblocks > 0 ? c1 + o.y : 0.f);
+        if (2 * p < n_ext)
+          *reinterpret_cast<float2*>(a.colsum + (size_t)z * a.N + n0 + 2 * p) = make_float2(kblocks > 0 ? c0 + o.x : 0.f, kblocks > 0 ? c1 + o.y : 0.f);
       }
     }
     if (kblocks > 0) {
@@ -502,15 +506,18 @@ __global__ void __launch_bounds__(320, 1) twgrad_kernel(const __grid_constant__ 
       umma::fence_after_sync();
     }
 #pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 8 && c * 32 < n_ext && h < nh; ++c) {
       float v[32];
-      if (kblocks > 0) tmem_ld_f32(tmem + ((uint32_t)(quad * 32) << 16) + h * 256 + c * 32, v);
+      if (kblocks > 0) tmem_ld_f32(tmem + ((uint32_t)(quad * 32) << 16) + h * 256 + c * 32, v);   // (warp-uniform: every lane takes part)
       else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
       }
+      if (m < a.M) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + c * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < 32; i += 4)
+          if (c * 32 + i < n_ext) *reinterpret_cast<float4*>(dst + c * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
     }
   }
   umma::fence_before_sync();
@@ -521,9 +528,9 @@ __global__ void __launch_bounds__(320, 1) twgrad_kernel(const __grid_constant__ 
   }
 }
 
-bool twgrad_shape_ok(int M, int N, int T) { return !getenv("B4R_DISABLE_TGEMM") && M % 256 == 0 && N % 256 == 0 && T >= 4096; }
+bool twgrad_shape_ok(int M, int N, int T) { return !getenv("B4R_DISABLE_TGEMM") && M % 8 == 0 && N % 8 == 0 && M >= 64 && N >= 64 && T >= 4096; }
 int twgrad_splits(int M, int N, int T) {
-  const int tiles = (M / 256) * (N / 256);
+  const int tiles = ((M + 255) / 256) * ((N + 255) / 256);
   int s = 148 / tiles;
   const int cap = T / 512;   // at least 8 k-blocks per CTA
   if (s > cap) s = cap;
@@ -540,7 +547,7 @@ cudaError_t launch_twgrad(const WgradArgs& a, cudaStream_t st) {
   if (!make_tmap_bf16_sw128(&tmX, a.X, (uint64_t)a.T, (uint64_t)a.M, (uint64_t)a.ldx, 64)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16_sw128(&tmY, a.dY, (uint64_t)a.T, (uint64_t)a.N, (uint64_t)a.ldy, 64)) return cudaErrorInvalidValue;
   TWgradDev d;
-  d.M = a.M; d.N = a.N; d.T = a.T; d.tiles_n = a.N / 256; d.out = a.out; d.split_stride = a.split_stride; d.ld_out = a.ld_out; d.colsum = a.colsum_part;
+  d.M = a.M; d.N = a.N; d.T = a.T; d.tiles_n = (a.N + 255) / 256; d.out = a.out; d.split_stride = a.split_stride; d.ld_out = a.ld_out; d.colsum = a.colsum_part;
   d.t_per_split = ((a.T + a.splits - 1) / a.splits + 63) / 64 * 64;
   static bool done = false;
   if (!done) {
@@ -548,16 +555,16 @@ cudaError_t launch_twgrad(const WgradArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     done = true;
   }
-  dim3 grid((a.M / 256) * (a.N / 256), a.splits);
+  dim3 grid(((a.M + 255) / 256) * ((a.N + 255) / 256), a.splits);
   launch_pdl(twgrad_kernel, dim3(grid), dim3(320), (size_t)(TW_SMEM), st, tmX, tmY, d);
   return cudaGetLastError();
 }
 }  // namespace b4r
 
 // ======================================================================================= GEMM + full-row epilogue (generation 2)
-// y = LayerNorm(drop(A W + bias) + residual) for hidden 256 (ROW_RES_DROP_LN of k_gemm.cu): one CTA tile = 128 whole
-// rows x 256 columns (a 256-column TMEM accumulator, double-buffered = all 512 columns), so the row statistics never
-// leave the CTA.  Epilogue thread = (row, 128-column half).  The tile's residual rows arrive by TMA in a 64 KB swizzled buffer;
+// y = LayerNorm(drop(A W + bias) + residual) for hidden 256 and 64 (ROW_RES_DROP_LN of k_gemm.cu): one CTA tile = 128 whole
+// rows x H columns (an H-column TMEM accumulator, double-buffered: all 512 columns at hidden 256), so the row statistics never
+// leave the CTA.  Epilogue thread = (row, H/2-column half).  The tile's residual rows arrive by TMA in a 64 KB swizzled buffer;
 // pass 1 turns them IN PLACE into the bf16 pre-LN value (accumulating sum and sum of squares, exchanged between the two halves
 // through shared memory) which leaves by TMA store; pass 2 normalises in place and the LN output leaves by TMA store.  No
 // per-thread global row accesses remain (they touched 32 half-used sectors per instruction and cost ~17 us per tile).
@@ -565,9 +572,10 @@ cudaError_t launch_twgrad(const WgradArgs& a, cudaStream_t st) {
 namespace b4r {
 using namespace encf;
 namespace {
-constexpr int TR_STAGES = 3, TR_STAGE = 128 * 128 + 64 * 256 * 2;   // 16 KB of A + 32 KB of W per 64-wide k-block
-constexpr int TR_BUF = 4 * 128 * 128;                                 // residual -> pre-LN -> LN output tile: 4 x [128][64] bf16
-constexpr int TR_SMEM = TR_STAGES * TR_STAGE + TR_BUF + 2 * 2 * 128 * 2 * 4 + 256 + 1024;
+constexpr int TR_STAGES = 3;
+__host__ __device__ constexpr int tr_stage(int H) { return 128 * 128 + 64 * H * 2; }   // 16 KB of A + 64 x H of W per 64-wide k-block
+__host__ __device__ constexpr int tr_buf(int H) { return (H / 64) * 128 * 128; }        // residual -> pre-LN -> LN output tile: H/64 x [128][64] bf16
+__host__ __device__ constexpr int tr_smem(int H) { return TR_STAGES * tr_stage(H) + tr_buf(H) + 2 * 2 * 128 * 2 * 4 + 256 + 1024; }
 struct TRowDev {
   int M, K;
   const float* bias; const float* gamma; const float* beta;
@@ -576,10 +584,12 @@ struct TRowDev {
 };
 }  // namespace
 
+template <int H>
 __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                                                         const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmP,
                                                         const __grid_constant__ CUtensorMap tmY, TRowDev a) {
-  constexpr int H = 256;
+  constexpr int TR_STAGE = tr_stage(H), TR_BUF = tr_buf(H), NB = H / 64, HC = H / 2, NCH = HC / 32;   // column blocks, columns / chunks per half
+  constexpr int TCOLS = 2 * H < 32 ? 32 : 2 * H;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sBuf = smem + TR_STAGES * TR_STAGE;
@@ -604,7 +614,7 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
     umma::prefetch_tensormap(&tmW);
     umma::prefetch_tensormap(&tmR); umma::prefetch_tensormap(&tmP); umma::prefetch_tensormap(&tmY);
   }
-  if (warp == 1) umma::tmem_alloc<512>(tmem_holder);
+  if (warp == 1) umma::tmem_alloc<TCOLS>(tmem_holder);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
@@ -622,7 +632,7 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
           unsigned char* sB = sA + 128 * 128;
           umma::tma_load_2d(sA, &tmA, kb * 64, t * 128, full + st);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) umma::tma_load_2d(sB + j * 8192, &tmW, j * 64, kb * 64, full + st);
+          for (int j = 0; j < NB; ++j) umma::tma_load_2d(sB + j * 8192, &tmW, j * 64, kb * 64, full + st);
         }
       }
     }
@@ -630,7 +640,7 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
     if (elect_one()) {
       const uint64_t DK0 = umma::make_desc_k_sw128(umma::smem_addr(smem));
       const uint64_t DMN0 = desc_mn_sw128(umma::smem_addr(smem), 8192);
-      constexpr uint32_t idesc = idesc_gen(128, 256, 0, 1);
+      constexpr uint32_t idesc = idesc_gen(128, H, 0, 1);
       int it = 0, ti = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
         const int acc = ti & 1;
@@ -643,7 +653,7 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
           const uint32_t offA = st * TR_STAGE, offB = offA + 128 * 128;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma::mma_bf16_ss(tmem + acc * 256, desc_at(DK0, offA + k * 32), desc_at(DMN0, offB + k * 2048), idesc, (kb | k) ? 1u : 0u);
+            umma::mma_bf16_ss(tmem + acc * H, desc_at(DK0, offA + k * 32), desc_at(DMN0, offB + k * 2048), idesc, (kb | k) ? 1u : 0u);
           umma::mma_commit(empty + st);
         }
         umma::mma_commit(tfull + acc);
@@ -658,7 +668,7 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
     auto load_residual = [&](int tt) {
       umma::mbar_expect_tx(resfull, TR_BUF);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) umma::tma_load_2d(sBuf + j * TILE_B, &tmR, j * 64, tt * 128, resfull);
+      for (int j = 0; j < NB; ++j) umma::tma_load_2d(sBuf + j * TILE_B, &tmR, j * 64, tt * 128, resfull);
     };
     if (leader && (int)blockIdx.x < n_tiles) load_residual(blockIdx.x);
     int ti = 0;
@@ -671,11 +681,12 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
       umma::mbar_wait(resfull, ti & 1);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int n = half * 128 + c * 32;
+      for (int c = 0; c < NCH; ++c) {
+        const int n = half * HC + c * 32;
         unsigned char* bt = sBuf + (n >> 6) * TILE_B;
+        const int ch = (n & 63) >> 3;        // first 16-byte chunk of these 32 columns inside the [128][64] block
         float v[32];
-        tmem_ld_f32(tmem + ((uint32_t)(quad * 32) << 16) + acc * 256 + n, v);
+        tmem_ld_f32(tmem + ((uint32_t)(quad * 32) << 16) + acc * H + n, v);
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n + i));
@@ -690,12 +701,12 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
           }
         }
         float res[32];
-        ld_tile<4>(bt, row_in_tile, (c & 1) * 4, res);
+        ld_tile<4>(bt, row_in_tile, ch, res);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += res[i];
         uint32_t pk[16];
         round_n<32>(v, pk);   // LN statistics are taken on the bf16-rounded value that backward will re-read
-        st_tile<4>(bt, row_in_tile, (c & 1) * 4, pk);
+        st_tile<4>(bt, row_in_tile, ch, pk);
 #pragma unroll
         for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 += v[i] * v[i]; }
       }
@@ -709,7 +720,7 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
       asm volatile("bar.sync 1, 256;\n" ::: "memory");
       if (leader) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) umma::tma_store_2d(&tmP, sBuf + j * TILE_B, j * 64, t * 128);
+        for (int j = 0; j < NB; ++j) umma::tma_store_2d(&tmP, sBuf + j * TILE_B, j * 64, t * 128);
         umma::tma_store_commit();
       }
       const float* so = sStat + ((acc * 2 + (half ^ 1)) * 128 + row_in_tile) * 2;
@@ -720,11 +731,12 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
       if (leader) umma::tma_store_wait_read<0>();
       asm volatile("bar.sync 1, 256;\n" ::: "memory");     // the pre-LN store has read the buffer: normalise in place
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int n = half * 128 + c * 32;
+      for (int c = 0; c < NCH; ++c) {
+        const int n = half * HC + c * 32;
         unsigned char* bt = sBuf + (n >> 6) * TILE_B;
+        const int ch = (n & 63) >> 3;
         float v[32];
-        ld_tile<4>(bt, row_in_tile, (c & 1) * 4, v);
+        ld_tile<4>(bt, row_in_tile, ch, v);
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma + n + i));
@@ -734,14 +746,14 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
         }
         uint32_t pk[16];
         pack_n<32>(v, pk);
-        st_tile<4>(bt, row_in_tile, (c & 1) * 4, pk);
+        st_tile<4>(bt, row_in_tile, ch, pk);
       }
       if (mok && half == 0) { a.mean[m] = mean; a.rstd[m] = rstd; }
       umma::fence_proxy_async();
       asm volatile("bar.sync 1, 256;\n" ::: "memory");
       if (leader) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) umma::tma_store_2d(&tmY, sBuf + j * TILE_B, j * 64, t * 128);
+        for (int j = 0; j < NB; ++j) umma::tma_store_2d(&tmY, sBuf + j * TILE_B, j * 64, t * 128);
         umma::tma_store_commit();
         umma::tma_store_wait_read<0>();
         if (t + (int)gridDim.x < n_tiles) load_residual(t + gridDim.x);
@@ -753,24 +765,25 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     umma::fence_after_sync();
-    umma::tmem_dealloc<512>(tmem);
+    umma::tmem_dealloc<TCOLS>(tmem);
   }
 }
 
 bool trowln_supported(int mode, const RowLnArgs& a) {
   if (getenv("B4R_DISABLE_TGEMM")) return false;
-  if (mode != ROW_RES_DROP_LN || a.H != 256 || a.a_rows || a.d_M) return false;
-  if (a.K % 64 || a.K < 128 || a.M < 256 || a.lda % 8 || ((uintptr_t)a.A & 15) || ((uintptr_t)a.W & 15)) return false;
+  if (mode != ROW_RES_DROP_LN || (a.H != 256 && a.H != 64) || a.a_rows || a.d_M) return false;
+  if (a.K % 64 || a.K < 64 || a.M < 256 || a.lda % 8 || ((uintptr_t)a.A & 15) || ((uintptr_t)a.W & 15)) return false;
   if (((uintptr_t)a.residual & 15) || ((uintptr_t)a.pre & 15) || ((uintptr_t)a.y & 15)) return false;   // TMA tiles
   return true;
 }
 cudaError_t launch_trowln(const RowLnArgs& a, cudaStream_t st) {
   CUtensorMap tmA, tmW;
   if (!make_tmap_bf16_sw128(&tmA, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda, 128)) return cudaErrorInvalidValue;
-  if (!make_tmap_bf16_sw128(&tmW, a.W, (uint64_t)a.K, 256, 256, 64)) return cudaErrorInvalidValue;
+  const uint64_t HH = (uint64_t)a.H;
+  if (!make_tmap_bf16_sw128(&tmW, a.W, (uint64_t)a.K, HH, HH, 64)) return cudaErrorInvalidValue;
   CUtensorMap tmR, tmP, tmY;
-  if (!make_tmap_bf16_sw128(&tmR, a.residual, (uint64_t)a.M, 256, 256, 128) || !make_tmap_bf16_sw128(&tmP, a.pre, (uint64_t)a.M, 256, 256, 128) ||
-      !make_tmap_bf16_sw128(&tmY, a.y, (uint64_t)a.M, 256, 256, 128))
+  if (!make_tmap_bf16_sw128(&tmR, a.residual, (uint64_t)a.M, HH, HH, 128) || !make_tmap_bf16_sw128(&tmP, a.pre, (uint64_t)a.M, HH, HH, 128) ||
+      !make_tmap_bf16_sw128(&tmY, a.y, (uint64_t)a.M, HH, HH, 128))
     return cudaErrorInvalidValue;
   TRowDev d;
   d.M = a.M; d.K = a.K; d.bias = a.bias; d.gamma = a.gamma; d.beta = a.beta; d.residual = a.residual; d.pre = a.pre; d.y = a.y;
@@ -778,14 +791,24 @@ cudaError_t launch_trowln(const RowLnArgs& a, cudaStream_t st) {
   d.thr16 = drop_threshold16(a.drop_rate);
   d.inv_keep = 1.0f / (1.0f - (float)d.thr16 / 65536.0f);
   d.seed = a.seed; d.site = a.site; d.step = a.step; d.d_step = a.d_step;
-  static bool done = false;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(trowln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM);
-    if (e != cudaSuccess) return e;
-    done = true;
-  }
   const int tiles = (a.M + 127) / 128;
-  trowln_kernel<<<tiles < 148 ? tiles : 148, 320, TR_SMEM, st>>>(tmA, tmW, tmR, tmP, tmY, d);
+  if (a.H == 256) {
+    static bool done = false;
+    if (!done) {
+      cudaError_t e = cudaFuncSetAttribute(trowln_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem(256));
+      if (e != cudaSuccess) return e;
+      done = true;
+    }
+    trowln_kernel<256><<<tiles < 148 ? tiles : 148, 320, tr_smem(256), st>>>(tmA, tmW, tmR, tmP, tmY, d);
+  } else {
+    static bool done = false;
+    if (!done) {
+      cudaError_t e = cudaFuncSetAttribute(trowln_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem(64));
+      if (e != cudaSuccess) return e;
+      done = true;
+    }
+    trowln_kernel<64><<<tiles < 148 ? tiles : 148, 320, tr_smem(64), st>>>(tmA, tmW, tmR, tmP, tmY, d);
+  }
   return cudaGetLastError();
 }
 }  // namespace b4r

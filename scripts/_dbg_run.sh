@@ -1,4 +1,4 @@
-timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 15 > gpurun_out/r4e_tests.log
-timeout 100 python scripts/profile_step.py c4 8 > gpurun_out/r4e_c4.log 2>&1
-timeout 100 python scripts/profile_step.py c3 10 > gpurun_out/r4e_c3.log 2>&1
-timeout 100 python scripts/profile_step.py c1 10 > gpurun_out/r4e_c1.log 2>&1
+timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 15 > gpurun_out/r4f_tests.log
+timeout 100 python scripts/profile_step.py c1 10 > gpurun_out/r4f_c1.log 2>&1
+timeout 100 python scripts/profile_step.py c3 10 > gpurun_out/r4f_c3.log 2>&1
+timeout 100 python scripts/profile_step.py c4 8 > gpurun_out/r4f_c4.log 2>&1
