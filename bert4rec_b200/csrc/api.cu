@@ -734,6 +734,7 @@ static int backward_impl(b4r_session* s, uint64_t seed, uint32_t step, const int
     cudaStream_t st_main = st; (void)st_main;
     cudaStream_t st = s->side_sort;
     KL("token_sort", launch_token_sort(s->tg, st));
+    s->launches += table_grad_sort_launches(s->tg.T, s->tg.V) - 1;
   }
   CK(cudaEventRecord(s->ev_sort, s->side_sort));
   CeArgs c = ce_args(s);
@@ -925,6 +926,7 @@ static int backward_impl(b4r_session* s, uint64_t seed, uint32_t step, const int
     cudaStream_t st_main = st; (void)st_main;
     cudaStream_t st = s->side_sort;
     KL("table_grad", launch_table_grad(s->tg, st));
+    s->launches += 1;
   }
   CK(cudaEventRecord(s->ev_sort, s->side_sort));
   if (fbwd) KL("grad_reduce:all", launch_grad_reduce(s->d_jobs_f, s->n_jobs_f, s->jobs_f_blocks, st));

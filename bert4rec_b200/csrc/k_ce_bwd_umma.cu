@@ -57,13 +57,18 @@ template <int H>
 struct CeBwdCfg {
   static constexpr int KB = H / 64;
   static constexpr int XT = H <= 128 ? 128 : 64;           // rows of a streamed X tile (= columns of the S / dl tile)
-  static constexpr int XSTAGES = H == 64 ? 3 : 2;
+  // Hidden 256 runs ONE CTA per SM (TMEM: 320 of 512 columns, 200 KB of shared memory), so nothing overlaps a tile's epilogue
+  // with the next tile's first MMA unless the CTA does it itself: the S accumulator and the dl tile are double-buffered (SB = 2)
+  // and MMA1 of tile i+1 is issued BEFORE the issuer waits for the dl tile of tile i.  Hidden <= 128 runs two CTAs per SM that
+  // overlap each other; they keep single buffers (256 TMEM columns each).
+  static constexpr int SB = H == 256 ? 2 : 1;
+  static constexpr int XSTAGES = H == 128 ? 2 : 3;
   static constexpr int R_BYTES = KB * CB_T * 128;
   static constexpr int X_BYTES = KB * XT * 128;
   static constexpr int DL_BYTES = (XT / 64) * CB_T * 128;  // [128][XT] bf16 as [128][64] sub-tiles
   static constexpr int VEC_BYTES = 2 * 3 * CB_T * 4;       // double-buffered per-column vectors (3 x 128 x 4 B)
-  static constexpr int SMEM = R_BYTES + XSTAGES * X_BYTES + DL_BYTES + VEC_BYTES + 256 + 1024;
-  static constexpr int TMEM_COLS = XT + H <= 256 ? 256 : 512;   // S (XT) + ACC (H)
+  static constexpr int SMEM = R_BYTES + XSTAGES * X_BYTES + SB * DL_BYTES + VEC_BYTES + 256 + 1024;
+  static constexpr int TMEM_COLS = SB * XT + H <= 256 ? 256 : 512;   // S (SB x XT) + ACC (H)
   static constexpr int CTAS_PER_SM = TMEM_COLS == 256 ? 2 : 1;
 };
 
@@ -77,22 +82,22 @@ __global__ void __launch_bounds__(320, CeBwdCfg<H>::CTAS_PER_SM) ce_bwd_umma_ker
                                                              const __grid_constant__ CUtensorMap tmE, CeBwdDev a) {
   pdl_grid_wait();
   using Cfg = CeBwdCfg<H>;
-  constexpr int KB = Cfg::KB, XS = Cfg::XSTAGES, XT = Cfg::XT;
+  constexpr int KB = Cfg::KB, XS = Cfg::XSTAGES, XT = Cfg::XT, SB = Cfg::SB;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sR = smem;
   unsigned char* sX = sR + Cfg::R_BYTES;
   unsigned char* sDl = sX + XS * Cfg::X_BYTES;
-  float* sVec = reinterpret_cast<float*>(sDl + Cfg::DL_BYTES);  // [2][3][128]
+  float* sVec = reinterpret_cast<float*>(sDl + SB * Cfg::DL_BYTES);  // [2][3][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sVec + 2 * 3 * CB_T);
   uint64_t* xfull = bars;             // [XS]
   uint64_t* xempty = bars + XS;       // [XS]
   uint64_t* rfull = bars + 2 * XS;    // R tile landed
-  uint64_t* s_full = rfull + 1;       // MMA1 done -> epilogue may read S
-  uint64_t* s_empty = s_full + 1;     // epilogue done reading S
-  uint64_t* dl_full = s_empty + 1;    // epilogue wrote the dl tile
-  uint64_t* dl_empty = dl_full + 1;   // MMA2 done reading the dl tile
-  uint64_t* acc_full = dl_empty + 1;  // all MMA2 done
+  uint64_t* s_full = rfull + 1;       // [2] MMA1 done -> epilogue may read S (per S buffer)
+  uint64_t* s_empty = s_full + 2;     // [2] epilogue done reading S
+  uint64_t* dl_full = s_empty + 2;    // [2] epilogue wrote the dl tile (per dl buffer)
+  uint64_t* dl_empty = dl_full + 2;   // [2] MMA2 done reading the dl tile
+  uint64_t* acc_full = dl_empty + 2;  // all MMA2 done
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   // rows with a gradient = the valid masked slots; the zero-weight aux rows behind them (metric parity only) are skipped
@@ -140,10 +145,12 @@ __global__ void __launch_bounds__(320, CeBwdCfg<H>::CTAS_PER_SM) ce_bwd_umma_ker
   if (threadIdx.x == 0) {
     for (int i = 0; i < XS; ++i) { umma::mbar_init(xfull + i, 1); umma::mbar_init(xempty + i, 1); }
     umma::mbar_init(rfull, 1);
-    umma::mbar_init(s_full, 1);
-    umma::mbar_init(s_empty, 8);
-    umma::mbar_init(dl_full, 8);
-    umma::mbar_init(dl_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(s_full + i, 1);
+      umma::mbar_init(s_empty + i, 8);
+      umma::mbar_init(dl_full + i, 8);
+      umma::mbar_init(dl_empty + i, 1);
+    }
     umma::mbar_init(acc_full, 1);
     umma::fence_barrier_init();
     umma::prefetch_tensormap(mapR);
@@ -154,7 +161,10 @@ __global__ void __launch_bounds__(320, CeBwdCfg<H>::CTAS_PER_SM) ce_bwd_umma_ker
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem_base = *tmem_holder;
-  const uint32_t tmem_s = tmem_base, tmem_acc = tmem_base + XT;
+  const uint32_t tmem_s = tmem_base, tmem_acc = tmem_base + SB * XT;
+  // buffer / phase of tile i: one S and dl buffer -> (0, i & 1); two -> (i & 1, (i >> 1) & 1)
+  auto bsel = [](int i) { return SB == 2 ? (i & 1) : 0; };
+  auto bpar = [](int i) { return (uint32_t)(SB == 2 ? ((i >> 1) & 1) : (i & 1)); };
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -175,31 +185,38 @@ __global__ void __launch_bounds__(320, CeBwdCfg<H>::CTAS_PER_SM) ce_bwd_umma_ker
       constexpr uint32_t idesc1 = umma::make_idesc_bf16(CB_T, XT);
       constexpr uint32_t idesc2 = make_idesc_bf16_bmn(CB_T, H);
       umma::mbar_wait(rfull, 0);
-      for (int i = 0; i < my_tiles; ++i) {
+      auto issue_mma1 = [&](int i) {      // S[buffer of i] = R . X_i^T
         const int st = i % XS;
         const uint32_t x_addr = umma::smem_addr(sX + st * Cfg::X_BYTES);
         umma::mbar_wait(xfull + st, (i / XS) & 1);
-        umma::mbar_wait(s_empty, (i & 1) ^ 1);
+        umma::mbar_wait(s_empty + bsel(i), bpar(i) ^ 1);     // the epilogue that last used this S buffer has read it
         umma::fence_after_sync();
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           const uint32_t r_addr = umma::smem_addr(sR + kb * CB_T * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma::mma_bf16_ss(tmem_s, umma::make_desc_k_sw128(r_addr + k * 32),
+            umma::mma_bf16_ss(tmem_s + bsel(i) * XT, umma::make_desc_k_sw128(r_addr + k * 32),
                               umma::make_desc_k_sw128(x_addr + kb * XT * 128 + k * 32), idesc1, (kb | k) ? 1u : 0u);
         }
-        umma::mma_commit(s_full);
+        umma::mma_commit(s_full + bsel(i));
+      };
+      if (SB == 2) issue_mma1(0);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int st = i % XS;
+        const uint32_t x_addr = umma::smem_addr(sX + st * Cfg::X_BYTES);
+        if (SB == 2) { if (i + 1 < my_tiles) issue_mma1(i + 1); }   // runs on the tensor pipe while the epilogue works on tile i
+        else issue_mma1(i);
         // second MMA: ACC += dl (K-major, K = the 128 streamed rows) . X (MN-major: N = H feature columns)
-        umma::mbar_wait(dl_full, i & 1);
+        umma::mbar_wait(dl_full + bsel(i), bpar(i));
         umma::fence_after_sync();
-        const uint32_t dl_addr = umma::smem_addr(sDl);
+        const uint32_t dl_addr = umma::smem_addr(sDl + bsel(i) * Cfg::DL_BYTES);
 #pragma unroll
         for (int kk = 0; kk < XT / 16; ++kk)
           umma::mma_bf16_ss(tmem_acc, umma::make_desc_k_sw128(dl_addr + (kk >> 2) * CB_T * 128 + (kk & 3) * 32),
                             make_desc_mn_sw128(x_addr + kk * 16 * 128, XT * 128), idesc2, (i | kk) ? 1u : 0u);
         umma::mma_commit(xempty + st);
-        umma::mma_commit(dl_empty);
+        umma::mma_commit(dl_empty + bsel(i));
       }
       umma::mma_commit(acc_full);
     }
@@ -245,15 +262,15 @@ __global__ void __launch_bounds__(320, CeBwdCfg<H>::CTAS_PER_SM) ce_bwd_umma_ker
       const int buf = i & 1;
       if (et < XT && i + 1 < my_tiles) fetch(i + 1);
       asm volatile("bar.sync 1, 256;\n" ::: "memory");  // vectors of tile i visible; buffer buf^1 free
-      umma::mbar_wait(s_full, i & 1);
+      umma::mbar_wait(s_full + bsel(i), bpar(i));
       umma::fence_after_sync();
-      umma::mbar_wait(dl_empty, (i & 1) ^ 1);           // MMA2 of the previous tile has consumed the dl tile
+      umma::mbar_wait(dl_empty + bsel(i), bpar(i) ^ 1);   // the MMA2 that last read this dl buffer is done
       const float* vec = sVec + buf * 3 * CB_T + half * (XT / 2);
       const int x0 = (x_lo + i) * XT + half * (XT / 2);   // first streamed row (= S column) of this thread's half
 #pragma unroll 1
       for (int c = 0; c < XT / 64; ++c) {
         uint32_t r[32];
-        umma::tmem_ld32(tmem_s + ((uint32_t)(quad * 32) << 16) + half * (XT / 2) + c * 32, r);
+        umma::tmem_ld32(tmem_s + ((uint32_t)(quad * 32) << 16) + bsel(i) * XT + half * (XT / 2) + c * 32, r);
         umma::tmem_ld_wait();
         uint32_t pk[16];
         if (ROW_IS_M) {
@@ -287,7 +304,7 @@ __global__ void __launch_bounds__(320, CeBwdCfg<H>::CTAS_PER_SM) ce_bwd_umma_ker
         }
         // row-contiguous store into the 128B-swizzled K-major sub-tile `half`: 16-byte chunk q -> q ^ (row & 7)
         const int dcol = half * (XT / 2) + c * 32;   // first dl column of this chunk: sub-tile dcol / 64, 16-byte chunk (dcol % 64) / 8
-        unsigned char* rowp = sDl + (dcol >> 6) * (CB_T * 128) + row_in_tile * 128;
+        unsigned char* rowp = sDl + bsel(i) * Cfg::DL_BYTES + (dcol >> 6) * (CB_T * 128) + row_in_tile * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int chunk = (((dcol & 63) >> 3) + q) ^ (row_in_tile & 7);
@@ -297,7 +314,7 @@ __global__ void __launch_bounds__(320, CeBwdCfg<H>::CTAS_PER_SM) ce_bwd_umma_ker
       umma::fence_before_sync();
       umma::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       __syncwarp();
-      if (lane == 0) { umma::mbar_arrive(s_empty); umma::mbar_arrive(dl_full); }
+      if (lane == 0) { umma::mbar_arrive(s_empty + bsel(i)); umma::mbar_arrive(dl_full + bsel(i)); }
       if (et < XT && i + 1 < my_tiles) stash(buf ^ 1);
     }
     // ---- accumulator -> global partial

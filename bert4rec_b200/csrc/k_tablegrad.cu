@@ -374,6 +374,7 @@ int table_grad_chunk_tokens(int T) { return T < 65536 ? 16 : 64; }
 int table_grad_chunks(int T) { const int c = table_grad_chunk_tokens(T); return (T + c - 1) / c; }
 int table_grad_max_long_runs(int T) { return T / (kMaxParts * table_grad_chunk_tokens(T)) + 1; }
 int table_grad_sorted_buf(int V) { return sort_passes(V) & 1; }
+int table_grad_sort_launches(int T, int V) { return T <= kSmallSortTokens ? 1 : 3 * sort_passes(V) + 1; }
 
 cudaError_t launch_token_sort(const TableGradArgs& a, cudaStream_t st) {
   const int nblk = table_grad_sort_blocks(a.T);

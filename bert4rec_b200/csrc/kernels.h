@@ -124,6 +124,7 @@ int table_grad_chunks(int T);
 int table_grad_max_long_runs(int T);
 cudaError_t launch_token_sort(const TableGradArgs& a, cudaStream_t st);    // keys/vals[table_grad_sorted_buf(V)] = sorted (id, t)
 int table_grad_sorted_buf(int V);
+int table_grad_sort_launches(int T, int V);   // kernels launch_token_sort enqueues (launch_table_grad: always 2)
 cudaError_t launch_table_grad(const TableGradArgs& a, cudaStream_t st);    // 2 launches: chunk sums, boundary runs
 
 // ------------------------------------------------------------------ attention (k_attn.cu)
