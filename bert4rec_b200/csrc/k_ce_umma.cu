@@ -2,7 +2,7 @@
 // tcgen05.mma (bf16 -> fp32 accumulators in TMEM) fed by TMA (128-byte-swizzled K-major tiles), warp-specialised:
 //   warp 0    : TMA producer (t tile once, then the stream of E tiles through a STAGES-deep smem ring)
 //   warp 1    : TMEM allocator + single-thread MMA issuer (double-buffered 128x128 fp32 accumulators)
-//   warps 2-5 : epilogue, one thread per accumulator row: tcgen05.ld 32 columns at a time, + bias, online
+//   warps 2-17: epilogue, thread = (accumulator row, 32-column quarter of the tile): one tcgen05.ld of 32 columns, + bias, online
 //               (max, sum-exp, label logit, first arg-max) entirely thread-local -- no shuffles, logits never leave chip.
 // Same partial format / finalize kernel as generation 1 (k_ce.cu); reference ops replaced: tfm MaskedLM projection +
 // SparseSoftmaxCrossEntropyWithLogits + argmax metrics (bert4rec_model.py:143, trainer_utils.py:12-23,49-60).
@@ -33,7 +33,10 @@ struct CeUmmaCfg {
   static constexpr int STAGES = H == 64 ? 4 : (H == 128 ? 3 : 2);
   static constexpr int A_BYTES = KB * UM_BM * 128;
   static constexpr int B_STAGE_BYTES = KB * UM_BN * 128;
-  static constexpr int SMEM = A_BYTES + STAGES * B_STAGE_BYTES + 2 * UM_BN * 4 + 128 * 5 * 4 + 8 + 256 + 1024;  // + bias x2, merge, barriers, align slack
+  // epilogue column parts per tile: hidden 64 runs two CTAs per SM (2 x 8 epilogue warps); one CTA per SM gets 16 warps itself
+  static constexpr int NP = H == 64 ? 2 : 4;
+  static constexpr int THREADS = 64 + 128 * NP;
+  static constexpr int SMEM = A_BYTES + STAGES * B_STAGE_BYTES + 2 * UM_BN * 4 + 3 * 128 * 5 * 4 + 8 + 256 + 1024;  // + bias x2, merge, barriers, align slack
 };
 
 // Work decomposition is decided ON THE DEVICE from the actual row count (the grid is sized for the capacity):
@@ -45,19 +48,19 @@ __host__ __device__ inline int ce_umma_dyn_splits(int n_rows, int ntiles, int ta
 }
 
 template <int H>
-__global__ void __launch_bounds__(320, 2) ce_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(CeUmmaCfg<H>::THREADS, H == 64 ? 2 : 1) ce_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, CeUmmaDev a) {
   pdl_grid_sync();
   using Cfg = CeUmmaCfg<H>;
-  constexpr int KB = Cfg::KB, STAGES = Cfg::STAGES;
+  constexpr int KB = Cfg::KB, STAGES = Cfg::STAGES, NP = Cfg::NP, CW = UM_BN / NP;   // CW = columns of a tile per epilogue thread
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment for the 128B-swizzled tiles
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;
   unsigned char* sB = smem + Cfg::A_BYTES;
   float* sBias = reinterpret_cast<float*>(sB + STAGES * Cfg::B_STAGE_BYTES);  // [2][UM_BN]
-  float* sMerge = sBias + 2 * UM_BN;                                          // [128][5] second column half's result
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMerge + 128 * 5 + 2);
+  float* sMerge = sBias + 2 * UM_BN;                                          // [3][128][5] results of column quarters 1..3
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMerge + 3 * 128 * 5 + 2);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + STAGES;       // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;   // [2]
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(320, 2) ce_fwd_umma_kernel(const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { umma::mbar_init(full + i, 1); umma::mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(tfull + i, 1); umma::mbar_init(tempty + i, 8); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(tfull + i, 1); umma::mbar_init(tempty + i, 4 * NP); }
     umma::mbar_init(afull, 1);
     umma::fence_barrier_init();
     umma::prefetch_tensormap(&tmA);
@@ -139,42 +142,48 @@ __global__ void __launch_bounds__(320, 2) ce_fwd_umma_kernel(const __grid_consta
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..9)
-    // 2 warps per TMEM lane quadrant; warp pair member `half` owns columns [half*64, half*64+64) of every tile
+    // ===================================================================== epilogue (warps 2..17)
+    // NP warps per TMEM lane quadrant; member `part` owns columns [part*CW, part*CW+CW) of every tile.  With one CTA per SM sixteen
+    // warps (four per scheduler) hide the tcgen05.ld / MUFU latencies that eight left exposed.
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;
     const int row_in_tile = quad * 32 + lane;
     const int row = m0 + row_in_tile;
-    const int et = threadIdx.x - 64;           // 0..255 index among the epilogue threads
+    const int et = threadIdx.x - 64;           // index among the 128 * NP epilogue threads
     const int label = row < n_rows ? a.labels[row] : -1;
     float run_max = -INFINITY, run_sum = 0.f, lab_logit = -INFINITY, best_v = -INFINITY;
     int best_i = 0x7fffffff;
     constexpr float LOG2E = 1.4426950408889634f;
-    // bias of tile 0 -> smem; later tiles are prefetched one tile ahead into a register
-    float bias_next = 0.f;
-    if (et < UM_BN && my_tiles > 0) {
-      const int v = a.v_begin + tile_lo * UM_BN + et;
-      sBias[et] = v < a.v_end ? a.vbias[v] : -INFINITY;  // -inf masks the out-of-range columns
-    }
+    // The bias of the thread's columns comes straight from global memory (L1: every row of the tile reads the same 128 values),
+    // issued before the wait for the accumulator.  No shared staging and therefore no CTA-wide barrier per tile: the epilogue warps
+    // drift apart instead of hitting the tcgen05.ld and the MUFU in the same cycles.
+    const bool bias_vec = (reinterpret_cast<uintptr_t>(a.vbias) & 15) == 0 && (a.v_begin & 3) == 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int acc = i & 1;
       const int v0 = a.v_begin + (tile_lo + i) * UM_BN;
-      if (et < UM_BN && i + 1 < my_tiles) {
-        const int v = v0 + UM_BN + et;
-        bias_next = v < a.v_end ? a.vbias[v] : -INFINITY;
-      }
-      if (et == 0) DBG_T(2, i, 0);
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");  // bias of tile i visible; buffer (i+1)&1 no longer read
-      if (et == 0) DBG_T(2, i, 1);
-      umma::mbar_wait(tfull + acc, (i >> 1) & 1);
-      if (et == 0) DBG_T(2, i, 2);
-      umma::fence_after_sync();
-      const float* bias = sBias + acc * UM_BN + half * 64;
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < CW / 32; ++c) {
+        const int col0 = v0 + part * CW + c * 32;
+        float bias[32];
+        if (bias_vec && col0 + 32 <= a.v_end) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.vbias + col0 + j));
+            bias[j] = b4.x; bias[j + 1] = b4.y; bias[j + 2] = b4.z; bias[j + 3] = b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) bias[j] = col0 + j < a.v_end ? __ldg(a.vbias + col0 + j) : -INFINITY;   // -inf masks the out-of-range columns
+        }
+        if (c == 0) {
+          if (et == 0) DBG_T(2, i, 1);
+          umma::mbar_wait(tfull + acc, (i >> 1) & 1);
+          if (et == 0) DBG_T(2, i, 2);
+          umma::fence_after_sync();
+        }
         uint32_t r[32];
         if (!(a.debug & 2)) {
-          umma::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * UM_BN + half * 64 + c * 32, r);
+          umma::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * UM_BN + part * CW + c * 32, r);
           umma::tmem_ld_wait();
         } else {
 #pragma unroll
@@ -184,13 +193,11 @@ __global__ void __launch_bounds__(320, 2) ce_fwd_umma_kernel(const __grid_consta
         float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 32 + j);
-          v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+          v[j] = __uint_as_float(r[j]) + bias[j]; v[j + 1] = __uint_as_float(r[j + 1]) + bias[j + 1];
+          v[j + 2] = __uint_as_float(r[j + 2]) + bias[j + 2]; v[j + 3] = __uint_as_float(r[j + 3]) + bias[j + 3];
           cm[0] = fmaxf(cm[0], v[j]); cm[1] = fmaxf(cm[1], v[j + 1]); cm[2] = fmaxf(cm[2], v[j + 2]); cm[3] = fmaxf(cm[3], v[j + 3]);
         }
         const float cmax = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
-        const int col0 = v0 + half * 64 + c * 32;
         if (cmax > best_v) {  // first maximum wins (columns are visited in increasing order)
           best_v = cmax;
 #pragma unroll
@@ -219,23 +226,27 @@ __global__ void __launch_bounds__(320, 2) ce_fwd_umma_kernel(const __grid_consta
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(tempty + acc);
       if (et == 0) DBG_T(2, i, 4);
-      if (et < UM_BN && i + 1 < my_tiles) sBias[((i + 1) & 1) * UM_BN + et] = bias_next;
     }
-    // merge the two column halves of each row (half 1 -> smem -> half 0)
-    if (half == 1) {
-      float* d = sMerge + row_in_tile * 5;
+    // merge the column parts of each row (parts 1.. -> smem -> part 0, fixed order)
+    if (part > 0) {
+      float* d = sMerge + ((part - 1) * 128 + row_in_tile) * 5;
       d[0] = run_max; d[1] = run_sum; d[2] = lab_logit; d[3] = best_v; d[4] = __int_as_float(best_i);
     }
-    asm volatile("bar.sync 1, 256;\n" ::: "memory");
-    if (half == 0 && row < n_rows) {
-      const float* o = sMerge + row_in_tile * 5;
-      const float mn = fmaxf(run_max, o[0]);
-      float l = 0.f;
-      if (mn != -INFINITY) l = run_sum * ex2_approx((run_max - mn) * LOG2E) + o[1] * ex2_approx((o[0] - mn) * LOG2E);
-      const int bi1 = __float_as_int(o[4]);
-      if (o[3] > best_v || (o[3] == best_v && bi1 < best_i)) { best_v = o[3]; best_i = bi1; }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(128 * NP) : "memory");
+    if (part == 0 && row < n_rows) {
+      float mn = run_max, l = run_sum;
+#pragma unroll
+      for (int q = 0; q < NP - 1; ++q) {
+        const float* o = sMerge + (q * 128 + row_in_tile) * 5;
+        const float m2 = fmaxf(mn, o[0]);
+        if (m2 != -INFINITY) l = l * ex2_approx((mn - m2) * LOG2E) + o[1] * ex2_approx((o[0] - m2) * LOG2E);
+        mn = m2;
+        const int bi1 = __float_as_int(o[4]);
+        if (o[3] > best_v || (o[3] == best_v && bi1 < best_i)) { best_v = o[3]; best_i = bi1; }
+        lab_logit = fmaxf(lab_logit, o[2]);
+      }
       float* out = a.part + ((size_t)split * a.M_cap + row) * 6;
-      out[0] = mn; out[1] = l; out[2] = fmaxf(lab_logit, o[2]); out[3] = best_v; out[4] = __int_as_float(best_i); out[5] = 0.f;
+      out[0] = mn; out[1] = l; out[2] = lab_logit; out[3] = best_v; out[4] = __int_as_float(best_i); out[5] = 0.f;
     }
   }
   umma::fence_before_sync();
@@ -274,7 +285,7 @@ cudaError_t launch_ce_fwd_umma(const CeUmmaMaps& maps, const CeArgs& a, cudaStre
       cudaFuncSetAttribute(ce_fwd_umma_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, CeUmmaCfg<HH>::SMEM); \
       done_##HH = true;                                                                                             \
     }                                                                                                               \
-    launch_pdl(ce_fwd_umma_kernel<HH>, grid, dim3(320), (size_t)CeUmmaCfg<HH>::SMEM, st, tmA, tmB, d);              \
+    launch_pdl(ce_fwd_umma_kernel<HH>, grid, dim3(CeUmmaCfg<HH>::THREADS), (size_t)CeUmmaCfg<HH>::SMEM, st, tmA, tmB, d);              \
     break;                                                                                                          \
   }
   switch (a.H) {
