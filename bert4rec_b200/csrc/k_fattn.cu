@@ -117,7 +117,9 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
   float* sMask = reinterpret_cast<float*>(smem + FB_OFF_MASK);
   unsigned long long* sKeep = reinterpret_cast<unsigned long long*>(smem + FB_OFF_KEEP);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FB_OFF_BAR);
-  uint64_t *barL = bars, *barS = bars + 1, *barSF = bars + 2, *barPD = bars + 3, *barG = bars + 4, *barAF = bars + 5;
+  // item loads arrive in three groups: barL (Q0 K0 V0 dO0 -- with two row tiles these are prefetched while the previous item's last
+  // iteration runs, see the control warp), barLb (O0 O1 dO1: what the delta pass needs) and barLc (Q1 K1 V1)
+  uint64_t *barL = bars, *barS = bars + 1, *barSF = bars + 2, *barPD = bars + 3, *barG = bars + 4, *barAF = bars + 5, *barLb = bars + 6, *barLc = bars + 7;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
   auto tile = [&](int i) -> unsigned char* { return smem + i * TILE_B; };
 
@@ -129,7 +131,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 
   if (tid == 0) {
     umma::mbar_init(barL, 1); umma::mbar_init(barS, 1); umma::mbar_init(barSF, FB_CT); umma::mbar_init(barPD, FB_CT);
-    umma::mbar_init(barG, 1); umma::mbar_init(barAF, FB_CT);
+    umma::mbar_init(barG, 1); umma::mbar_init(barAF, FB_CT); umma::mbar_init(barLb, 1); umma::mbar_init(barLc, 1);
     umma::fence_barrier_init();
   }
   if (warp == FB_CT / 32) {
@@ -168,21 +170,40 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
     // every CTA takes the same time per item: without a stagger all 148 CTAs issue their item loads in the same microsecond and
     // then leave the memory system idle; a one-off start offset spreads the bursts
     if (n_items > (int)gridDim.x && stagger_ns) __nanosleep((blockIdx.x % 8) * stagger_ns);
+    // first row tile of an item: Q0 K0 V0 dO0.  With two row tiles the LAST iteration of an item (key tile 1 x query tile 1) touches
+    // none of them, so the next item's copies are requested at the top of that iteration -- once the gradient MMAs of the iteration
+    // before it have completed -- and are in place when the next item starts: its first score MMAs are issued at once and the
+    // compute threads wait only for O0 O1 dO1 (48 KB instead of 160 KB).
+    auto load_first = [&](int it) {
+      if (elect_one()) {
+        const int bb = it / G, gg = it % G, r0 = bb * S;
+        umma::mbar_expect_tx(barL, (uint32_t)(4 * TILE_B));
+        umma::tma_load_2d(tile(FB_Q), &tmQKV, gg * 64, r0, barL);
+        umma::tma_load_2d(tile(FB_K), &tmQKV, H + gg * 64, r0, barL);
+        umma::tma_load_2d(tile(FB_V), &tmQKV, 2 * H + gg * 64, r0, barL);
+        umma::tma_load_2d(tile(FB_DO), &tmDO, gg * 64, r0, barL);
+      }
+      __syncwarp();
+    };
+    bool prefetched = false;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++nitem) {
       const int b = item / G, g = item % G;
       const bool tsk = blockIdx.x == 0 && nitem == 2 && lane == 0;
       FTS(tsk, 64);
       if (git > 0) umma::mbar_wait(barG, (git - 1) & 1);     // every MMA of the previous item has completed: tiles are free
       FTS(tsk, 65);
+      if (!prefetched) load_first(item);
       if (elect_one()) {
-        umma::mbar_expect_tx(barL, (uint32_t)(5 * MT * TILE_B));
-        for (int mt = 0; mt < MT; ++mt) {
-          const int r0 = b * S + mt * 128;
-          umma::tma_load_2d(tile(FB_Q + mt), &tmQKV, g * 64, r0, barL);
-          umma::tma_load_2d(tile(FB_K + mt), &tmQKV, H + g * 64, r0, barL);
-          umma::tma_load_2d(tile(FB_V + mt), &tmQKV, 2 * H + g * 64, r0, barL);
-          umma::tma_load_2d(tile(FB_DO + mt), &tmDO, g * 64, r0, barL);
-          umma::tma_load_2d(tile(FB_P + mt), &tmO, g * 64, r0, barL);
+        const int r0 = b * S;
+        umma::mbar_expect_tx(barLb, (uint32_t)((MT == 2 ? 3 : 1) * TILE_B));
+        umma::tma_load_2d(tile(FB_P), &tmO, g * 64, r0, barLb);
+        if (MT == 2) {
+          umma::tma_load_2d(tile(FB_P + 1), &tmO, g * 64, r0 + 128, barLb);
+          umma::tma_load_2d(tile(FB_DO + 1), &tmDO, g * 64, r0 + 128, barLb);
+          umma::mbar_expect_tx(barLc, (uint32_t)(3 * TILE_B));
+          umma::tma_load_2d(tile(FB_Q + 1), &tmQKV, g * 64, r0 + 128, barLc);
+          umma::tma_load_2d(tile(FB_K + 1), &tmQKV, H + g * 64, r0 + 128, barLc);
+          umma::tma_load_2d(tile(FB_V + 1), &tmQKV, 2 * H + g * 64, r0 + 128, barLc);
         }
       }
       __syncwarp();
@@ -197,7 +218,15 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         if (i + 1 < n_it) {
           umma::mbar_wait(barSF, git & 1);
           FTS(tsk, 70 + i * 4);
+          if (i == 0 && MT == 2) { umma::mbar_wait(barLb, nitem & 1); umma::mbar_wait(barLc, nitem & 1); }   // iteration 1 is the first to read row tile 1
           issue_scores(i + 1);
+        }
+        if (i == n_it - 1) {
+          prefetched = MT == 2 && item + (int)gridDim.x < n_items;
+          if (prefetched) {
+            umma::mbar_wait(barG, (git - 1) & 1);    // gradient MMAs of every earlier iteration are done: Q0 K0 V0 dO0 are free
+            load_first(item + gridDim.x);
+          }
         }
         umma::mbar_wait(barPD, git & 1);
         FTS(tsk, 71 + i * 4);                      // Pd^T / dS^T tiles of iteration i are in shared memory
@@ -258,6 +287,7 @@ fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         }
       }
       umma::mbar_wait(barL, nitem & 1);
+      umma::mbar_wait(barLb, nitem & 1);
       FTS(tsc, 1);
       // ---- delta = rowsum(dO * O) per (head, query)
 #pragma unroll
