@@ -363,7 +363,7 @@ static size_t carve(b4r_session* s, void* ws, size_t cap, bool dry, std::vector<
   s->ce_part = b.take<float>((size_t)(s->vsplits > s->vsplits_umma ? s->vsplits : s->vsplits_umma) * Mcap * 6);
   s->lse = b.take<float>(Mcap); s->lab = b.take<float>(Mcap);
   s->stats = b.take<float>(8); s->step_stats = b.take<float>(8);
-  s->fin_part = b.take<float>(64 * 5); s->ticket = b.take<int>(4);
+  s->fin_part = b.take<float>(kCeFinalizeMaxBlocks * 5); s->ticket = b.take<int>(4);
   {
     // dlogits chunk: at most ~256 MB so that it stays close to the L2 / small in HBM
     size_t max_rows = ((size_t)256 << 20) / ((size_t)s->Vp * 2);
@@ -978,7 +978,7 @@ static size_t shard_carve(b4r_shard* s, void* ws, size_t ws_bytes, bool dry) {
   }
   s->ce_part = b.take<float>((size_t)s->fwd_max_splits * cap * 6);
   s->lse = b.take<float>(cap); s->lab = b.take<float>(cap);
-  s->step_stats = b.take<float>(8); s->fin_part = b.take<float>(64 * 5); s->ticket = b.take<int>(4);
+  s->step_stats = b.take<float>(8); s->fin_part = b.take<float>(kCeFinalizeMaxBlocks * 5); s->ticket = b.take<int>(4);
   {
     const int xt = ce_bwd_umma_xtile(H), xtiles = (Vs + xt - 1) / xt;
     size_t ms = budget / ((size_t)cap * H * sizeof(float));

@@ -302,6 +302,9 @@ __global__ void __launch_bounds__(256) ce_finalize_kernel(CeDev a, float* __rest
     const int r = r0 + warp * 4 + rsub;
     float mn = -INFINITY, l = 0.f, lab = -INFINITY, bv = -INFINITY;
     int bi = 0x7fffffff;
+    // the row's weight / multiplicity / label do not depend on the merge: requested up front, one round trip instead of two
+    float w = 0.f; int mult = 0, label_r = -1;
+    if (q == 0 && r < n_rows) { w = a.row_w[r]; mult = a.row_mult[r]; label_r = a.labels[r]; }
     if (r < n_rows) {
       for (int s = q; s < a.vsplits; s += 8) {
         const float2* p = reinterpret_cast<const float2*>(a.part + ((size_t)s * a.M_cap + r) * 6);
@@ -329,9 +332,7 @@ __global__ void __launch_bounds__(256) ce_finalize_kernel(CeDev a, float* __rest
       const float lse = mn + logf(l);
       a.lse[r] = lse;
       if (a.lab_out) a.lab_out[r] = lab;
-      const float w = a.row_w[r];
-      const int mult = a.row_mult[r];
-      const int correct = (bi == a.labels[r]);
+      const int correct = (bi == label_r);
       if (w > 0.f) acc[0] += (lse - lab);
       acc[1] += w;
       acc[2] += (w > 0.f && correct) ? 1.f : 0.f;
@@ -357,12 +358,24 @@ __global__ void __launch_bounds__(256) ce_finalize_kernel(CeDev a, float* __rest
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (tid < 5) {
-    float v = 0.f;
-    for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(fin_part + b * 5 + tid);
-    s_tot[tid] = v;
-    a.step_stats[tid] = v;
-    if (a.stats) a.stats[tid] += v;
+  {
+    // fixed-order sum of the per-CTA statistics: thread t takes CTAs t, t + 256, ...; the 256 partial sums are added in index order
+    __shared__ float s_fin[256][5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      float v = 0.f;
+      for (unsigned b = tid; b < gridDim.x; b += 256) v += __ldcg(fin_part + b * 5 + k);
+      s_fin[tid][k] = v;
+    }
+    __syncthreads();
+    if (tid < 5) {
+      float v = 0.f;
+      const int n = gridDim.x < 256 ? gridDim.x : 256;
+      for (int t = 0; t < n; ++t) v += s_fin[t][tid];
+      s_tot[tid] = v;
+      a.step_stats[tid] = v;
+      if (a.stats) a.stats[tid] += v;
+    }
   }
   if (tid == 0) *ticket = 0;
   __syncthreads();
@@ -793,7 +806,7 @@ cudaError_t launch_topk_full(const CeArgs& a, int n_rows, int K, unsigned long l
 
 cudaError_t launch_ce_finalize(const CeArgs& a, cudaStream_t st) {
   int blocks = (a.M_cap + 31) / 32;
-  if (blocks > 64) blocks = 64;
+  if (blocks > kCeFinalizeMaxBlocks) blocks = kCeFinalizeMaxBlocks;   // one 32-row pass per CTA up to four CTAs per SM
   launch_pdl(ce_finalize_kernel, dim3(blocks), dim3(256), (size_t)0, st, to_dev(a), a.fin_part, a.ticket);
   return cudaGetLastError();
 }

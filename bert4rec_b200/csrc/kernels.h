@@ -260,6 +260,7 @@ struct CeArgs {
   int row_begin, row_count;          // chunk of rows for dlogits
 };
 cudaError_t launch_ce_fwd(const CeArgs& a, cudaStream_t st);
+constexpr int kCeFinalizeMaxBlocks = 4 * 148;   // fin_part holds 5 floats per CTA
 cudaError_t launch_ce_finalize(const CeArgs& a, cudaStream_t st);
 cudaError_t launch_ce_dlogits(const CeArgs& a, cudaStream_t st);
 // full-catalogue rank counting (see k_ce.cu): beat[m] += #items of the shard that rank ahead of the ground truth
