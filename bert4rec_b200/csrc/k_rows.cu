@@ -173,8 +173,12 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const ReduceJob* __res
       for (int k = 0; k < 4; ++k) {
         const int col = c0 + k * 256 + threadIdx.x;
         if (col < job.len) {
+          float x[8];
+#pragma unroll
+          for (int p = 0; p < 8; ++p) x[p] = p < job.nparts ? job.src[(size_t)p * job.part_stride + col] : 0.f;   // all in flight
           float v = 0.f;
-          for (int p = 0; p < job.nparts; ++p) v += job.src[(size_t)p * job.part_stride + col];
+#pragma unroll
+          for (int p = 0; p < 8; ++p) v += x[p];
           if (job.accumulate) v += job.dst[col];
           job.dst[col] = v;
         }
@@ -193,18 +197,16 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const ReduceJob* __res
     if (col < job.len) {
       const float* p = job.src + col;
       if (wide) {
-        int k = ty;
-        for (; k + 24 < job.nparts; k += 32) {
-          const float4 a = *reinterpret_cast<const float4*>(p + (size_t)k * job.part_stride), b = *reinterpret_cast<const float4*>(p + (size_t)(k + 8) * job.part_stride);
-          const float4 c = *reinterpret_cast<const float4*>(p + (size_t)(k + 16) * job.part_stride), d = *reinterpret_cast<const float4*>(p + (size_t)(k + 24) * job.part_stride);
-          acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
-          acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
-          acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
-          acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
-        }
-        for (; k < job.nparts; k += 8) {
-          const float4 a = *reinterpret_cast<const float4*>(p + (size_t)k * job.part_stride);
-          acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        // eight (predicated) loads in flight per thread: a lane's share of up to 64 partials costs one memory round trip
+        for (int k = ty; k < job.nparts; k += 64) {
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k + 8 * u < job.nparts) v[u] = *reinterpret_cast<const float4*>(p + (size_t)(k + 8 * u) * job.part_stride);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
         }
       } else {
         int k = ty;
