@@ -186,6 +186,13 @@ __device__ __forceinline__ void pdl_grid_sync() {
 // multi-wave kernels: wait only -- the successor is released when this grid's CTAs exit (an explicit early trigger lets the
 // successor's CTAs take SM slots from this grid's later waves: measured slower)
 __device__ __forceinline__ void pdl_grid_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// persistent kernels whose whole grid is resident at once (at most one CTA per SM): there are no later waves the successor's CTAs
+// could displace, so the successor is released at once and its launch latency hides behind this kernel; a larger grid only waits
+constexpr int kNumSMs = 148;
+__device__ __forceinline__ void pdl_grid_wait_single_wave() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (gridDim.x * gridDim.y * gridDim.z <= (unsigned)kNumSMs) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 inline bool pdl_enabled() {
   static const bool on = getenv("B4R_DISABLE_PDL") == nullptr;
   return on;

@@ -106,7 +106,7 @@ template <int D>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 fattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                  const __grid_constant__ CUtensorMap tmO, FAttnBwdDev a, uint32_t stagger_ns) {
-  pdl_grid_wait();
+  pdl_grid_wait_single_wave();
   constexpr int NHG = 64 / D;      // heads per 64-column group
   constexpr int CPT = D / FA_NG;   // accumulator columns drained per thread
   constexpr int QPT = 128 / FA_NG; // query columns of a score tile per thread
@@ -463,7 +463,7 @@ struct FAttnFwdDev {
 
 template <int D>
 __global__ void __launch_bounds__(FF_THREADS, 1) fattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, FAttnFwdDev a) {
-  pdl_grid_wait();
+  pdl_grid_wait_single_wave();
   constexpr int NHG = 64 / D, CPT = D / 2;          // the accumulator is drained by column groups 0 and 1
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);

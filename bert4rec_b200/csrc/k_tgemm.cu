@@ -50,7 +50,7 @@ template <int EPI, bool B_MN>
 __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                        const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
                                                        TGemmDev a) {
-  pdl_grid_wait();
+  pdl_grid_wait_single_wave();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int NST = tg_stages(EPI);
@@ -398,7 +398,7 @@ struct TWgradDev { int M, N, T, t_per_split, tiles_n; float* out; size_t split_s
 
 __global__ void __launch_bounds__(320, 1) twgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                                                         TWgradDev a) {
-  pdl_grid_wait();
+  pdl_grid_wait_single_wave();
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TW_STAGES * TW_STAGE);
@@ -588,6 +588,7 @@ template <int H>
 __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                                                         const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmP,
                                                         const __grid_constant__ CUtensorMap tmY, TRowDev a) {
+  pdl_grid_wait_single_wave();
   constexpr int TR_STAGE = tr_stage(H), TR_BUF = tr_buf(H), NB = H / 64, HC = H / 2, NCH = HC / 32;   // column blocks, columns / chunks per half
   constexpr int TCOLS = 2 * H < 32 ? 32 : 2 * H;
   extern __shared__ unsigned char smem_raw[];
@@ -799,7 +800,7 @@ cudaError_t launch_trowln(const RowLnArgs& a, cudaStream_t st) {
       if (e != cudaSuccess) return e;
       done = true;
     }
-    trowln_kernel<256><<<tiles < 148 ? tiles : 148, 320, tr_smem(256), st>>>(tmA, tmW, tmR, tmP, tmY, d);
+    launch_pdl(trowln_kernel<256>, dim3(tiles < 148 ? tiles : 148), dim3(320), (size_t)tr_smem(256), st, tmA, tmW, tmR, tmP, tmY, d);
   } else {
     static bool done = false;
     if (!done) {
@@ -807,7 +808,7 @@ cudaError_t launch_trowln(const RowLnArgs& a, cudaStream_t st) {
       if (e != cudaSuccess) return e;
       done = true;
     }
-    trowln_kernel<64><<<tiles < 148 ? tiles : 148, 320, tr_smem(64), st>>>(tmA, tmW, tmR, tmP, tmY, d);
+    launch_pdl(trowln_kernel<64>, dim3(tiles < 148 ? tiles : 148), dim3(320), (size_t)tr_smem(64), st, tmA, tmW, tmR, tmP, tmY, d);
   }
   return cudaGetLastError();
 }
