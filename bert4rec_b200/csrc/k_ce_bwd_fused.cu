@@ -423,9 +423,15 @@ __global__ void __launch_bounds__(256) ce_bwd_fused_reduce_kernel(const float* _
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n4) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < nch; ++k) {
-      const float4 v = reinterpret_cast<const float4*>(dE_part + (size_t)k * V * FH)[idx];
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    for (int k0 = 0; k0 < nch; k0 += 8) {      // eight chunk partials in flight per thread (the chunk count is a run-time value)
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + u < nch) v[u] = __ldcs(reinterpret_cast<const float4*>(dE_part + (size_t)(k0 + u) * V * FH) + idx);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
     }
     reinterpret_cast<float4*>(g_table)[idx] = acc;
   }
