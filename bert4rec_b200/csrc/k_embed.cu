@@ -7,6 +7,8 @@
 
 namespace b4r {
 
+constexpr int kEmbedRowsPerGroup = 4;
+
 template <int H>
 __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ table,
                                                            const bf16* __restrict__ pos, const float* __restrict__ gamma,
@@ -15,50 +17,65 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const int64_t* __rest
                                                            uint32_t step, const long long* __restrict__ d_step) {
   if (d_step) step += (uint32_t)(*d_step);
   constexpr int LPR = H / 8;       // lanes per row (16 B each)
-  constexpr int RPW = 32 / LPR;    // rows per warp
+  constexpr int RPW = 32 / LPR;    // rows per warp and pass
+  constexpr int R = kEmbedRowsPerGroup;   // passes per CTA: the ids and the gathered rows of all passes are requested before any is used
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, l = lane % LPR;
-  const int t = (blockIdx.x * 8 + warp) * RPW + sub;
-  const bool ok = t < T;
   const int c0 = l * 8;
-  float v[8];
+  const int t0 = blockIdx.x * (8 * RPW * R) + warp * RPW + sub;
+  long long id[R];
+  uint4 e[R], p[R];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = 0.f;
-  if (ok) {
-    long long id = ids[t];
-    id = id < 0 ? 0 : (id >= V ? V - 1 : id);  // clamp like a GPU gather; the reference would raise on CPU
-    const uint4 e = __ldg(reinterpret_cast<const uint4*>(table + (size_t)id * H + c0));
-    const uint4 p = __ldg(reinterpret_cast<const uint4*>(pos + (size_t)(t % S) * H + c0));
-    const uint32_t ew[4] = {e.x, e.y, e.z, e.w}, pw[4] = {p.x, p.y, p.z, p.w};
+  for (int r = 0; r < R; ++r) {
+    const int t = t0 + r * 8 * RPW;
+    id[r] = t < T ? ids[t] : 0;
+    id[r] = id[r] < 0 ? 0 : (id[r] >= V ? V - 1 : id[r]);  // clamp like a GPU gather; the reference would raise on CPU
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int t = t0 + r * 8 * RPW;
+    e[r] = __ldg(reinterpret_cast<const uint4*>(table + (size_t)id[r] * H + c0));
+    p[r] = __ldg(reinterpret_cast<const uint4*>(pos + (size_t)((t < T ? t : 0) % S) * H + c0));
+  }
+  float gm[8], bt[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { gm[i] = gamma[c0 + i]; bt[i] = beta[c0 + i]; }
+  const Philox ph(seed);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int t = t0 + r * 8 * RPW;
+    const bool ok = t < T;
+    float v[8];
+    const uint32_t ew[4] = {e[r].x, e[r].y, e[r].z, e[r].w}, pw[4] = {p[r].x, p[r].y, p[r].z, p[r].w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float2 a = unpack_bf162(ew[i]), b = unpack_bf162(pw[i]);
       v[2 * i] = a.x + b.x; v[2 * i + 1] = a.y + b.y;
     }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    s = group_sum<LPR>(s);
+    const float mean = s * (1.0f / H);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { float d = v[i] - mean; q += d * d; }
+    q = group_sum<LPR>(q);
+    const float rstd = rsqrtf(q * (1.0f / H) + kLnEps);
+    if (ok) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (v[i] - mean) * rstd * gm[i] + bt[i];
+      if (thr16 > 0) {
+        uint32_t bits = keep_bits8(ph, (uint32_t)t, (uint32_t)l, site_id(SITE_EMB, 0), step, thr16);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = ((bits >> i) & 1u) ? o[i] * inv_keep : 0.f;
+      }
+      uint4 ov;
+      ov.x = pack_bf162(o[0], o[1]); ov.y = pack_bf162(o[2], o[3]); ov.z = pack_bf162(o[4], o[5]); ov.w = pack_bf162(o[6], o[7]);
+      *reinterpret_cast<uint4*>(out + (size_t)t * H + c0) = ov;
+    }
   }
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s += v[i];
-  s = group_sum<LPR>(s);
-  const float mean = s * (1.0f / H);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { float d = v[i] - mean; q += d * d; }
-  q = group_sum<LPR>(q);
-  const float rstd = rsqrtf(q * (1.0f / H) + kLnEps);
-  if (!ok) return;
-  float o[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = (v[i] - mean) * rstd * gamma[c0 + i] + beta[c0 + i];
-  if (thr16 > 0) {
-    const Philox ph(seed);
-    uint32_t bits = keep_bits8(ph, (uint32_t)t, (uint32_t)l, site_id(SITE_EMB, 0), step, thr16);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = ((bits >> i) & 1u) ? o[i] * inv_keep : 0.f;
-  }
-  uint4 ov;
-  ov.x = pack_bf162(o[0], o[1]); ov.y = pack_bf162(o[2], o[3]); ov.z = pack_bf162(o[4], o[5]); ov.w = pack_bf162(o[6], o[7]);
-  *reinterpret_cast<uint4*>(out + (size_t)t * H + c0) = ov;
 }
 
 cudaError_t launch_embed_ln_fwd(const int64_t* ids, const bf16* table, const bf16* pos, const float* gamma,
@@ -69,7 +86,7 @@ cudaError_t launch_embed_ln_fwd(const int64_t* ids, const bf16* table, const bf1
   float inv_keep = 1.0f / (1.0f - (float)thr / 65536.0f);
 #define B4R_E(HH)                                                                                              \
   case HH: {                                                                                                   \
-    int rows_per_cta = 8 * (32 / (HH / 8));                                                                    \
+    int rows_per_cta = 8 * (32 / (HH / 8)) * kEmbedRowsPerGroup;                                               \
     embed_ln_fwd_kernel<HH><<<(T + rows_per_cta - 1) / rows_per_cta, 256, 0, st>>>(ids, table, pos, gamma, beta, out, T, S, \
                                                                                    V, thr, inv_keep, seed, step, d_step);  \
     break;                                                                                                     \

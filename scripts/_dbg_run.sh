@@ -1,2 +1,4 @@
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r02f_bench_n2.json 2> gpurun_out/r02f_bench_n2.err
-timeout 600 python bench.py --gpus 1 --workload c3 --no-secondary --steps 20 --warmup 5 > gpurun_out/r02f_bench_c3_n1.json 2> gpurun_out/r02f_bench_c3_n1.err
+timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 4 > gpurun_out/r4x_tests.log
+timeout 100 python scripts/profile_step.py c4 8 > gpurun_out/r4x_c4.log 2>&1
+timeout 100 python scripts/profile_step.py c3 10 > gpurun_out/r4x_c3.log 2>&1
+timeout 100 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r4x_smoke.log 2>&1
