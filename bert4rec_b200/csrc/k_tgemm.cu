@@ -564,7 +564,8 @@ cudaError_t launch_twgrad(const WgradArgs& a, cudaStream_t st) {
 // ======================================================================================= GEMM + full-row epilogue (generation 2)
 // y = LayerNorm(drop(A W + bias) + residual) for hidden 256 and 64 (ROW_RES_DROP_LN of k_gemm.cu): one CTA tile = 128 whole
 // rows x H columns (an H-column TMEM accumulator, double-buffered: all 512 columns at hidden 256), so the row statistics never
-// leave the CTA.  Epilogue thread = (row, H/2-column half).  The tile's residual rows arrive by TMA in a 64 KB swizzled buffer;
+// leave the CTA.  Epilogue thread = (row, H/4-column quarter): sixteen epilogue warps (four per scheduler) -- with eight the two
+// passes over the tile were paced by the latency of each warp's own tcgen05.ld / Philox / shared-memory chain.  The tile's residual rows arrive by TMA in a 64 KB swizzled buffer;
 // pass 1 turns them IN PLACE into the bf16 pre-LN value (accumulating sum and sum of squares, exchanged between the two halves
 // through shared memory) which leaves by TMA store; pass 2 normalises in place and the LN output leaves by TMA store.  No
 // per-thread global row accesses remain (they touched 32 half-used sectors per instruction and cost ~17 us per tile).
@@ -575,7 +576,8 @@ namespace {
 constexpr int TR_STAGES = 3;
 __host__ __device__ constexpr int tr_stage(int H) { return 128 * 128 + 64 * H * 2; }   // 16 KB of A + 64 x H of W per 64-wide k-block
 __host__ __device__ constexpr int tr_buf(int H) { return (H / 64) * 128 * 128; }        // residual -> pre-LN -> LN output tile: H/64 x [128][64] bf16
-__host__ __device__ constexpr int tr_smem(int H) { return TR_STAGES * tr_stage(H) + tr_buf(H) + 2 * 2 * 128 * 2 * 4 + 256 + 1024; }
+constexpr int TR_PARTS = 4, TR_THREADS = 64 + 128 * TR_PARTS;
+__host__ __device__ constexpr int tr_smem(int H) { return TR_STAGES * tr_stage(H) + tr_buf(H) + 2 * TR_PARTS * 128 * 2 * 4 + 256 + 1024; }
 struct TRowDev {
   int M, K;
   const float* bias; const float* gamma; const float* beta;
@@ -585,17 +587,17 @@ struct TRowDev {
 }  // namespace
 
 template <int H>
-__global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+__global__ void __launch_bounds__(TR_THREADS, 1) trowln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                                                         const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmP,
                                                         const __grid_constant__ CUtensorMap tmY, TRowDev a) {
   pdl_grid_wait_single_wave();
-  constexpr int TR_STAGE = tr_stage(H), TR_BUF = tr_buf(H), NB = H / 64, HC = H / 2, NCH = HC / 32;   // column blocks, columns / chunks per half
+  constexpr int TR_STAGE = tr_stage(H), TR_BUF = tr_buf(H), NB = H / 64, HC = H / TR_PARTS, NCH = HC / 16;   // column blocks, columns / 16-column chunks per part
   constexpr int TCOLS = 2 * H < 32 ? 32 : 2 * H;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sBuf = smem + TR_STAGES * TR_STAGE;
-  float* sStat = reinterpret_cast<float*>(sBuf + TR_BUF);   // [2 acc][2 halves][128 rows][2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * 2 * 128 * 2);
+  float* sStat = reinterpret_cast<float*>(sBuf + TR_BUF);   // [2 acc][TR_PARTS][128 rows][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * TR_PARTS * 128 * 2);
   uint64_t* full = bars;
   uint64_t* empty = bars + TR_STAGES;
   uint64_t* tfull = bars + 2 * TR_STAGES;
@@ -608,7 +610,7 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TR_STAGES; ++i) { umma::mbar_init(full + i, 1); umma::mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(tfull + i, 1); umma::mbar_init(tempty + i, 8); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(tfull + i, 1); umma::mbar_init(tempty + i, 4 * TR_PARTS); }
     umma::mbar_init(resfull, 1);
     umma::fence_barrier_init();
     umma::prefetch_tensormap(&tmA);
@@ -662,7 +664,7 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
     }
     __syncwarp();
   } else {
-    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int quad = warp & 3, part = (warp - 2) >> 2;
     const int row_in_tile = quad * 32 + lane;
     const Philox ph(a.seed);
     const bool leader = threadIdx.x == 64;
@@ -683,75 +685,79 @@ __global__ void __launch_bounds__(320, 1) trowln_kernel(const __grid_constant__ 
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
-        const int n = half * HC + c * 32;
+        const int n = part * HC + c * 16;
         unsigned char* bt = sBuf + (n >> 6) * TILE_B;
-        const int ch = (n & 63) >> 3;        // first 16-byte chunk of these 32 columns inside the [128][64] block
-        float v[32];
-        tmem_ld_f32(tmem + ((uint32_t)(quad * 32) << 16) + acc * H + n, v);
+        const int ch = (n & 63) >> 3;        // first 16-byte chunk of these 16 columns inside the [128][64] block
+        float v[16];
+        tmem_ld_f16(tmem + ((uint32_t)(quad * 32) << 16) + acc * H + n, v);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < 16; i += 4) {
           const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n + i));
           v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
         }
         if (a.thr16 > 0 && mok) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 2; ++q) {
             const uint32_t bits = keep_bits8(ph, (uint32_t)m, (uint32_t)(n / 8 + q), a.site, step, a.thr16);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[8 * q + i] = ((bits >> i) & 1u) ? v[8 * q + i] * a.inv_keep : 0.f;
           }
         }
-        float res[32];
-        ld_tile<4>(bt, row_in_tile, ch, res);
+        float res[16];
+        ld_tile<2>(bt, row_in_tile, ch, res);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += res[i];
-        uint32_t pk[16];
-        round_n<32>(v, pk);   // LN statistics are taken on the bf16-rounded value that backward will re-read
-        st_tile<4>(bt, row_in_tile, ch, pk);
+        for (int i = 0; i < 16; ++i) v[i] += res[i];
+        uint32_t pk[8];
+        round_n<16>(v, pk);   // LN statistics are taken on the bf16-rounded value that backward will re-read
+        st_tile<2>(bt, row_in_tile, ch, pk);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 += v[i] * v[i]; }
+        for (int i = 0; i < 16; ++i) { s1 += v[i]; s2 += v[i] * v[i]; }
       }
       // the accumulator has been read completely: hand it back to the MMA warp before the second pass
       umma::fence_before_sync();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(tempty + acc);
-      float* st = sStat + ((acc * 2 + half) * 128 + row_in_tile) * 2;
+      float* st = sStat + ((acc * TR_PARTS + part) * 128 + row_in_tile) * 2;
       st[0] = s1; st[1] = s2;
       umma::fence_proxy_async();
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      asm volatile("bar.sync 1, %0;\n" ::"n"(128 * TR_PARTS) : "memory");
       if (leader) {
 #pragma unroll
         for (int j = 0; j < NB; ++j) umma::tma_store_2d(&tmP, sBuf + j * TILE_B, j * 64, t * 128);
         umma::tma_store_commit();
       }
-      const float* so = sStat + ((acc * 2 + (half ^ 1)) * 128 + row_in_tile) * 2;
-      const float t1 = half == 0 ? s1 + so[0] : so[0] + s1, t2 = half == 0 ? s2 + so[1] : so[1] + s2;
+      float t1 = 0.f, t2 = 0.f;       // the four parts of a row in part order: every thread of the row gets the same statistics
+#pragma unroll
+      for (int q = 0; q < TR_PARTS; ++q) {
+        const float* so = sStat + ((acc * TR_PARTS + q) * 128 + row_in_tile) * 2;
+        t1 += so[0]; t2 += so[1];
+      }
       const float mean = t1 * (1.0f / H);
       const float var = fmaxf(t2 * (1.0f / H) - mean * mean, 0.f);
       const float rstd = rsqrtf(var + kLnEps);
       if (leader) umma::tma_store_wait_read<0>();
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");     // the pre-LN store has read the buffer: normalise in place
+      asm volatile("bar.sync 1, %0;\n" ::"n"(128 * TR_PARTS) : "memory");     // the pre-LN store has read the buffer: normalise in place
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
-        const int n = half * HC + c * 32;
+        const int n = part * HC + c * 16;
         unsigned char* bt = sBuf + (n >> 6) * TILE_B;
         const int ch = (n & 63) >> 3;
-        float v[32];
-        ld_tile<4>(bt, row_in_tile, ch, v);
+        float v[16];
+        ld_tile<2>(bt, row_in_tile, ch, v);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < 16; i += 4) {
           const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma + n + i));
           const float4 b = __ldg(reinterpret_cast<const float4*>(a.beta + n + i));
           v[i] = (v[i] - mean) * rstd * g.x + b.x; v[i + 1] = (v[i + 1] - mean) * rstd * g.y + b.y;
           v[i + 2] = (v[i + 2] - mean) * rstd * g.z + b.z; v[i + 3] = (v[i + 3] - mean) * rstd * g.w + b.w;
         }
-        uint32_t pk[16];
-        pack_n<32>(v, pk);
-        st_tile<4>(bt, row_in_tile, ch, pk);
+        uint32_t pk[8];
+        pack_n<16>(v, pk);
+        st_tile<2>(bt, row_in_tile, ch, pk);
       }
-      if (mok && half == 0) { a.mean[m] = mean; a.rstd[m] = rstd; }
+      if (mok && part == 0) { a.mean[m] = mean; a.rstd[m] = rstd; }
       umma::fence_proxy_async();
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      asm volatile("bar.sync 1, %0;\n" ::"n"(128 * TR_PARTS) : "memory");
       if (leader) {
 #pragma unroll
         for (int j = 0; j < NB; ++j) umma::tma_store_2d(&tmY, sBuf + j * TILE_B, j * 64, t * 128);
@@ -800,7 +806,7 @@ cudaError_t launch_trowln(const RowLnArgs& a, cudaStream_t st) {
       if (e != cudaSuccess) return e;
       done = true;
     }
-    launch_pdl(trowln_kernel<256>, dim3(tiles < 148 ? tiles : 148), dim3(320), (size_t)tr_smem(256), st, tmA, tmW, tmR, tmP, tmY, d);
+    launch_pdl(trowln_kernel<256>, dim3(tiles < 148 ? tiles : 148), dim3(TR_THREADS), (size_t)tr_smem(256), st, tmA, tmW, tmR, tmP, tmY, d);
   } else {
     static bool done = false;
     if (!done) {
@@ -808,7 +814,7 @@ cudaError_t launch_trowln(const RowLnArgs& a, cudaStream_t st) {
       if (e != cudaSuccess) return e;
       done = true;
     }
-    launch_pdl(trowln_kernel<64>, dim3(tiles < 148 ? tiles : 148), dim3(320), (size_t)tr_smem(64), st, tmA, tmW, tmR, tmP, tmY, d);
+    launch_pdl(trowln_kernel<64>, dim3(tiles < 148 ? tiles : 148), dim3(TR_THREADS), (size_t)tr_smem(64), st, tmA, tmW, tmR, tmP, tmY, d);
   }
   return cudaGetLastError();
 }
