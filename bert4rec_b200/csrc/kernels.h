@@ -102,6 +102,13 @@ cudaError_t launch_embed_bwd(const int64_t* ids, const bf16* table, const bf16* 
                              int bsplits, cudaStream_t st);
 int embed_bwd_bsplits(int B);
 
+// ------------------------------------------------------------------ peer-memory gradient all-reduce (k_p2p.cu)
+// bufs / flags: device arrays of `world` peer-mapped pointers (this rank's own included) to the fp32 buffer and to a zeroed u32 flag
+// array of >= 3 * p2p_allreduce_max_world() entries on every rank; state: local zeroed u32[8]
+int p2p_allreduce_max_world();
+cudaError_t launch_p2p_allreduce(float* const* bufs, uint32_t* const* flags, size_t off, size_t n, int rank, int world,
+                                 uint32_t* state, cudaStream_t st);
+
 // ------------------------------------------------------------------ deterministic item-table gradient (k_tablegrad.cu)
 // grad_table[id] += sum over the tokens t with ids[t] == id of dx[t], in a FIXED order: the tokens are sorted by (id, t) with a
 // stable LSD radix sort (integer work, depends on the batch only: runs on a side branch of the step), the sorted list is cut

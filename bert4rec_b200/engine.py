@@ -5,6 +5,7 @@ launched through the C ABI (include/b4r.h).  Nothing here falls back to torch op
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -64,6 +65,7 @@ class ParamStore:
             self.params = torch.zeros(self.n_total, dtype=torch.float32, device=self.device)
             self.shadow = torch.zeros(self.n_total, dtype=torch.bfloat16, device=self.device)
         self.grads = None
+        self.p2p = None      # symmetric-memory handles of the peer-memory gradient all-reduce (data-parallel NCCL worlds)
         self.m = self.v = None
         self.step_counter = None
         self.sessions = {}
@@ -81,9 +83,53 @@ class ParamStore:
     @property
     def I(self): return self.cfg.inner_dim
 
+    def _alloc_grads(self):
+        """The flat gradient buffer.  In a NCCL world of 2..16 ranks it is allocated in symmetric memory and exchanged with the other
+        ranks (a collective: every rank creates its training buffers at the same point), so that the data-parallel all-reduce can be
+        the library's own peer-memory kernel (csrc/k_p2p.cu); otherwise (single process, gloo, B4R_DISABLE_P2P_ALLREDUCE=1, or a
+        platform without peer access) a plain tensor, reduced by torch.distributed.all_reduce."""
+        self.p2p = None
+        import torch.distributed as dist
+        if (dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
+                and 2 <= dist.get_world_size() <= self.lib.b4r_p2p_allreduce_max_world()
+                and not os.environ.get("B4R_DISABLE_P2P_ALLREDUCE")):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                with torch.cuda.device(self.device):
+                    grads = symm.empty(self.n_total, dtype=torch.float32, device=self.device)
+                    flags = symm.empty(3 * self.lib.b4r_p2p_allreduce_max_world(), dtype=torch.int32, device=self.device)
+                    grads.zero_(); flags.zero_()
+                    torch.cuda.synchronize(self.device)
+                    hg = symm.rendezvous(grads, dist.group.WORLD)
+                    hf = symm.rendezvous(flags, dist.group.WORLD)
+                    state = torch.zeros(8, dtype=torch.int32, device=self.device)
+                    torch.cuda.synchronize(self.device)
+                dist.barrier()     # every rank's flags are zero before anyone signals
+                self.p2p = dict(hg=hg, hf=hf, flags=flags, state=state, rank=dist.get_rank(), world=dist.get_world_size())
+                return grads
+            except Exception as e:   # noqa: BLE001
+                import warnings
+                warnings.warn(f"peer-memory all-reduce unavailable ({type(e).__name__}: {e}); using torch.distributed.all_reduce")
+                self.p2p = None
+        return torch.zeros(self.n_total, dtype=torch.float32, device=self.device)
+
+    def all_reduce_grads(self, n_floats, stream=None):
+        """SUM over ranks of grads[:n_floats], in place, on the current stream (capturable when the peer-memory kernel is in use)."""
+        if self.p2p is None:
+            torch.distributed.all_reduce(self.grads[:n_floats])
+            return
+        p = self.p2p
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        check(self.lib.b4r_p2p_allreduce_f32(C.c_void_p(p["hg"].buffer_ptrs_dev), C.c_void_p(p["hf"].buffer_ptrs_dev), 0, int(n_floats),
+                                             p["rank"], p["world"], _ptr(p["state"]), C.c_void_p(st)))
+
+    def p2p_error(self):
+        """0, or the code a peer-memory all-reduce left behind when a rank did not arrive within its bounded wait (synchronises)."""
+        return 0 if self.p2p is None else int(self.p2p["state"][7].item())
+
     def ensure_training_buffers(self):
         if self.grads is None:
-            self.grads = torch.zeros(self.n_total, dtype=torch.float32, device=self.device)
+            self.grads = self._alloc_grads()
             self.m = torch.zeros(self.n_trainable, dtype=torch.float32, device=self.device)
             self.v = torch.zeros(self.n_trainable, dtype=torch.float32, device=self.device)
             self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.device)

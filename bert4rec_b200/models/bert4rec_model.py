@@ -380,7 +380,7 @@ class BERT4RecModel:
                 self._reduce_and_update(sess)
                 torch.cuda.synchronize(self.device)
                 g1, g2 = None, None
-                if self.distributed and self._dp_single_graph is not False:
+                if self.distributed and (self._dp_single_graph is not False or self.store.p2p is not None):
                     # data-parallel: try ONE graph for the whole step with the NCCL all-reduce captured inside it
                     # (NCCL collectives are capturable); on any failure fall back to graph / eager all-reduce / graph
                     try:
@@ -417,7 +417,9 @@ class BERT4RecModel:
     def _all_reduce(self, sess):
         # batch data-parallel: SUM gradients of the SUM loss and the valid-slot counts over ranks (NCCL), so that
         # the normaliser is the GLOBAL number of valid masked slots (trainer_utils.py:22)
-        torch.distributed.all_reduce(self.store.grads[: self.store.n_trainable + 1])
+        # the library's own two-shot kernel over NVLink peer mappings when the gradient buffer lives in symmetric memory
+        # (engine.ParamStore._alloc_grads), else one NCCL all-reduce
+        self.store.all_reduce_grads(self.store.n_trainable + 1)
 
     def _update(self, count):
         self.store.adamw_step(self._hp, count=count, grad_scale=1.0)

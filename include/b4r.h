@@ -86,6 +86,19 @@ int b4r_backward_from_dt(b4r_session* s, const float* dt, uint64_t seed, uint32_
 /* tanh pooler on token 0 (bert4rec_encoder.py:224-226) -> out fp32 [batch, hidden] */
 int b4r_pooled_output(b4r_session* s, float* out, void* stream);
 
+/* Batch data-parallel training (one process per GPU; reference: the loss of a step is normalised by the number of valid masked
+ * slots, trainer_utils.py:22 -- summed over ranks here): SUM-all-reduce of an fp32 range [offset, offset + n) of a buffer that
+ * lives in SYMMETRIC memory, in place, by this library's own two-shot kernel over NVLink peer mappings (rank r adds slice r of all
+ * ranks in rank order, then everyone gathers; deterministic, no NCCL launch, CUDA-graph capturable).  buffer_ptrs_dev /
+ * flag_ptrs_dev: DEVICE arrays of `world` pointers (this rank's own included) to the buffer and to a zero-initialised uint32 flag
+ * array of >= 3 * b4r_p2p_allreduce_max_world() entries on every rank, each valid for peer access from this device (what
+ * torch.distributed._symmetric_memory.rendezvous(...).buffer_ptrs_dev holds); state: this rank's own zero-initialised device
+ * uint32[8] (call counter; state[7] != 0 after a call = a peer never arrived within the bounded wait).  Every rank must enqueue the
+ * same sequence of calls. */
+int b4r_p2p_allreduce_max_world(void);
+int b4r_p2p_allreduce_f32(const void* buffer_ptrs_dev, const void* flag_ptrs_dev, size_t offset_floats, size_t n_floats, int rank,
+                          int world, void* state, void* stream);
+
 /* AdamWeightDecay.apply_gradients (adam_w_optimizer.py:100-136): clip_by_global_norm, WarmUp/PolynomialDecay lr,
  * decoupled decay, Adam; also refreshes shadow_bf16.  The gradient is first multiplied by grad_scale / max(*count,1)
  * (count = number of valid masked slots, the loss normaliser of trainer_utils.py:22).  step_counter: device int64

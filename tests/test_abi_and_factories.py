@@ -115,3 +115,19 @@ def test_bench_reference_arm_prints_one_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["metric"] == "train masked-seq/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+def test_p2p_allreduce_entry_validates_its_arguments_without_a_gpu():
+    """b4r_p2p_allreduce_f32 (the data-parallel gradient all-reduce over NVLink peer memory) rejects worlds it does not support and
+    null buffers before touching the device; its exchange needs >= 2 GPUs and is checked by scripts/p2p_allreduce_check.py and the
+    `dp_parity` entry of the multi-GPU bench line."""
+    import ctypes as C
+    from bert4rec_b200 import _lib
+    lib = _lib.load()
+    assert lib.b4r_p2p_allreduce_max_world() >= 8
+    one = C.c_void_p(16)
+    assert lib.b4r_p2p_allreduce_f32(None, one, 0, 4, 0, 2, one, None) != 0
+    assert lib.b4r_p2p_allreduce_f32(one, one, 0, 4, 0, 1, one, None) != 0
+    assert lib.b4r_p2p_allreduce_f32(one, one, 0, 4, 5, 4, one, None) != 0
+    assert lib.b4r_p2p_allreduce_f32(one, one, 2, 4, 0, 2, one, None) != 0
+    assert b"16-byte" in lib.b4r_last_error()
