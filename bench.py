@@ -458,7 +458,7 @@ def dp_parity_probe(w, dev, world, rank, main_model):
                 worst, worst_name = err, k
         out = {"max_rel_l2_over_tensors": worst, "worst_tensor": worst_name, "global_rel_l2": float((g_dp[:nt].double() - g1.double()).norm() / g1.double().norm()),
                "valid_slots_dp": float(g_dp[nt]), "valid_slots_single": n1, "global_batch": B * world,
-               "what": "flat gradient after the data-parallel all-reduce (%s) vs rank 0 recomputing the global batch on one GPU (dropout off)" % ("own two-shot kernel over NVLink peer memory" if probe.store.p2p is not None else "NCCL")}
+               "what": "flat gradient after the data-parallel all-reduce (%s) vs rank 0 recomputing the global batch on one GPU (dropout off)" % (("own NVLS multimem kernel" if probe.store.p2p.get("mc") else "own two-shot kernel over NVLink peer memory") if probe.store.p2p is not None else "NCCL")}
         del single
     del probe
     torch.cuda.empty_cache()
@@ -547,7 +547,7 @@ def run_b200(args, w, secondary):
     comm = None
     if world > 1:
         comm = {"allreduce_floats": int(model.store.n_trainable + 1), "exposed_allreduce_us_per_step": allreduce_time_us(model, dev),
-                "kernel": "b4r p2p_allreduce_kernel (two-shot over NVLink peer memory, inside the step graph)" if model.store.p2p is not None else "NCCL all-reduce between the forward/backward graph and the optimizer graph", "note": "one all-reduce of the flat fp32 gradient (+ valid-slot count) per step, timed alone (back to back)"}
+                "kernel": (("b4r p2p_allreduce_nvls_kernel (one pass of multimem.ld_reduce / multimem.st through the NVSwitch multicast mapping, inside the step graph)" if model.store.p2p.get("mc") else "b4r p2p_allreduce_kernel (two-shot over NVLink peer memory, inside the step graph)") if model.store.p2p is not None else "NCCL all-reduce between the forward/backward graph and the optimizer graph"), "note": "one all-reduce of the flat fp32 gradient (+ valid-slot count) per step, timed alone (back to back)"}
         comm["p2p_error"] = model.store.p2p_error()
         t = torch.tensor([comm["exposed_allreduce_us_per_step"]], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -55,7 +55,7 @@ _SIGNATURES = {
     "b4r_backward": (C.c_int, [_P, C.c_uint64, C.c_uint32, _P, _P]),
     "b4r_pooled_output": (C.c_int, [_P, _P, _P]),
     "b4r_p2p_allreduce_max_world": (C.c_int, []),
-    "b4r_p2p_allreduce_f32": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.c_int, C.c_int, _P, _P]),
+    "b4r_p2p_allreduce_f32": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_size_t, C.c_int, C.c_int, _P, _P]),
     "b4r_adamw_scratch_floats": (C.c_size_t, []),
     "b4r_adamw_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.POINTER(AdamWHParams), _P, C.c_float, _P, _P, _P, _P]),
     "b4r_rank_candidates": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),

@@ -1421,14 +1421,15 @@ extern "C" int b4r_table_grad(const int64_t* ids, const float* dx, float* grad_t
 
 // ------------------------------------------------------------------------------------------------ data-parallel all-reduce
 extern "C" int b4r_p2p_allreduce_max_world(void) { return p2p_allreduce_max_world(); }
-extern "C" int b4r_p2p_allreduce_f32(const void* buffer_ptrs_dev, const void* flag_ptrs_dev, size_t offset_floats, size_t n_floats,
-                                     int rank, int world, void* state, void* stream) {
+extern "C" int b4r_p2p_allreduce_f32(const void* buffer_ptrs_dev, const void* flag_ptrs_dev, void* multicast_ptr, size_t offset_floats,
+                                     size_t n_floats, int rank, int world, void* state, void* stream) {
   if (!buffer_ptrs_dev || !flag_ptrs_dev || !state) return fail("null argument");
   if (world < 2 || world > p2p_allreduce_max_world()) return fail("world size %d unsupported by the peer-memory all-reduce (2..%d)", world, p2p_allreduce_max_world());
   if (rank < 0 || rank >= world) return fail("rank %d outside the world of %d", rank, world);
   if (offset_floats % 4) return fail("the buffer range must start on a 16-byte boundary");
-  CK(launch_p2p_allreduce(reinterpret_cast<float* const*>(buffer_ptrs_dev), reinterpret_cast<uint32_t* const*>(flag_ptrs_dev), offset_floats,
-                          n_floats, rank, world, reinterpret_cast<uint32_t*>(state), (cudaStream_t)stream));
+  CK(launch_p2p_allreduce(reinterpret_cast<float* const*>(buffer_ptrs_dev), reinterpret_cast<uint32_t* const*>(flag_ptrs_dev),
+                          reinterpret_cast<float*>(multicast_ptr), offset_floats, n_floats, rank, world, reinterpret_cast<uint32_t*>(state),
+                          (cudaStream_t)stream));
   return 0;
 }
 

@@ -161,11 +161,60 @@ __global__ void __launch_bounds__(kP2PThreads, 1) p2p_allreduce_kernel(P2PDev a)
   if (blockIdx.x == 0 && threadIdx.x == 0) a.state[0] = epoch;
 }
 
+// ---- variant for NVSwitch systems with multicast (NVLS): `mc` is the multicast mapping of the same buffer.  One pass: a lane reads
+// the element of ALL ranks with one multimem.ld_reduce (the switch adds the ranks' values) and writes the sum to ALL ranks with one
+// multimem.st -- each GPU moves 1/world of the buffer in and 1/world out, and there is no gather phase: two barriers instead of three.
+// The same lane reads and then overwrites an element, and nothing else touches the slice, so the operation stays in place.  The sum
+// is taken once per element (every rank receives the same bits); its association order is the switch's, not rank order.
+__device__ __forceinline__ float4 mm_ld_reduce(const float4* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st(float4* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float mm_ld_reduce1(const float* p) {
+  float v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st1(float* p, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kP2PThreads, 1) p2p_allreduce_nvls_kernel(P2PDev a, float* mc) {
+  pdl_grid_wait();
+  const uint32_t epoch = a.state[0] + 1u;
+  const int R = a.rank, W = a.world;
+  const size_t n4 = a.n / 4, per4 = (n4 + W - 1) / W;
+  const size_t gtid = (size_t)blockIdx.x * kP2PThreads + threadIdx.x, gstride = (size_t)gridDim.x * kP2PThreads;
+  float4* mc4 = reinterpret_cast<float4*>(mc + a.off);
+  grid_then_world_barrier(a, 0, epoch, 0u, false);
+  const size_t lo = min(n4, (size_t)R * per4), hi = min(n4, lo + per4);
+  for (size_t i = lo + gtid; i < hi; i += 4 * gstride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * gstride < hi) v[u] = mm_ld_reduce(mc4 + i + u * gstride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * gstride < hi) mm_st(mc4 + i + u * gstride, v[u]);
+  }
+  if (R == W - 1 && gtid < (a.n & 3)) {
+    float* pe = mc + a.off + n4 * 4 + gtid;
+    mm_st1(pe, mm_ld_reduce1(pe));
+  }
+  grid_then_world_barrier(a, 1, epoch, epoch * gridDim.x, true);
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.state[0] = epoch;
+}
+
 }  // namespace
 
 int p2p_allreduce_max_world() { return kP2PMaxWorld; }
 
-cudaError_t launch_p2p_allreduce(float* const* bufs, uint32_t* const* flags, size_t off, size_t n, int rank, int world,
+cudaError_t launch_p2p_allreduce(float* const* bufs, uint32_t* const* flags, float* multicast, size_t off, size_t n, int rank, int world,
                                  uint32_t* state, cudaStream_t st) {
   if (world < 2 || world > kP2PMaxWorld || rank < 0 || rank >= world) return cudaErrorInvalidValue;
   P2PDev a;
@@ -173,6 +222,7 @@ cudaError_t launch_p2p_allreduce(float* const* bufs, uint32_t* const* flags, siz
   // 96 of the 148 SMs (measured at 7.4 MB, 2 ranks: 16 CTAs 59 us, 32: 44, 64: 39, 96: 41, 128: 39): enough lanes to keep the NVLink
   // loads in flight, and every CTA becomes resident whatever little else the device runs (the CTAs meet at a counter)
   static const int ctas = getenv("B4R_P2P_CTAS") ? atoi(getenv("B4R_P2P_CTAS")) : 96;   // (development aid; must be the same on every call)
+  if (multicast) return launch_pdl(p2p_allreduce_nvls_kernel, dim3(ctas), dim3(kP2PThreads), (size_t)0, st, a, multicast);
   return launch_pdl(p2p_allreduce_kernel, dim3(ctas), dim3(kP2PThreads), (size_t)0, st, a);
 }
 

@@ -106,7 +106,9 @@ int embed_bwd_bsplits(int B);
 // bufs / flags: device arrays of `world` peer-mapped pointers (this rank's own included) to the fp32 buffer and to a zeroed u32 flag
 // array of >= 3 * p2p_allreduce_max_world() entries on every rank; state: local zeroed u32[8]
 int p2p_allreduce_max_world();
-cudaError_t launch_p2p_allreduce(float* const* bufs, uint32_t* const* flags, size_t off, size_t n, int rank, int world,
+// multicast (optional): NVLS multicast mapping of the same buffer -> one-pass multimem.ld_reduce / multimem.st variant.  A buffer must
+// always be reduced by the same variant (the two keep different arrival counts in `state`).
+cudaError_t launch_p2p_allreduce(float* const* bufs, uint32_t* const* flags, float* multicast, size_t off, size_t n, int rank, int world,
                                  uint32_t* state, cudaStream_t st);
 
 // ------------------------------------------------------------------ deterministic item-table gradient (k_tablegrad.cu)

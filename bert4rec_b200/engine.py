@@ -105,7 +105,9 @@ class ParamStore:
                     state = torch.zeros(8, dtype=torch.int32, device=self.device)
                     torch.cuda.synchronize(self.device)
                 dist.barrier()     # every rank's flags are zero before anyone signals
-                self.p2p = dict(hg=hg, hf=hf, flags=flags, state=state, rank=dist.get_rank(), world=dist.get_world_size())
+                # NVSwitch multicast mapping of the gradient buffer (0 when the platform has none): the one-pass NVLS variant
+                mc = 0 if os.environ.get("B4R_DISABLE_NVLS") else int(getattr(hg, "multicast_ptr", 0) or 0)
+                self.p2p = dict(hg=hg, hf=hf, flags=flags, state=state, rank=dist.get_rank(), world=dist.get_world_size(), mc=mc)
                 return grads
             except Exception as e:   # noqa: BLE001
                 import warnings
@@ -120,8 +122,8 @@ class ParamStore:
             return
         p = self.p2p
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
-        check(self.lib.b4r_p2p_allreduce_f32(C.c_void_p(p["hg"].buffer_ptrs_dev), C.c_void_p(p["hf"].buffer_ptrs_dev), 0, int(n_floats),
-                                             p["rank"], p["world"], _ptr(p["state"]), C.c_void_p(st)))
+        check(self.lib.b4r_p2p_allreduce_f32(C.c_void_p(p["hg"].buffer_ptrs_dev), C.c_void_p(p["hf"].buffer_ptrs_dev), C.c_void_p(p["mc"]), 0,
+                                             int(n_floats), p["rank"], p["world"], _ptr(p["state"]), C.c_void_p(st)))
 
     def p2p_error(self):
         """0, or the code a peer-memory all-reduce left behind when a rank did not arrive within its bounded wait (synchronises)."""

@@ -93,11 +93,13 @@ int b4r_pooled_output(b4r_session* s, float* out, void* stream);
  * flag_ptrs_dev: DEVICE arrays of `world` pointers (this rank's own included) to the buffer and to a zero-initialised uint32 flag
  * array of >= 3 * b4r_p2p_allreduce_max_world() entries on every rank, each valid for peer access from this device (what
  * torch.distributed._symmetric_memory.rendezvous(...).buffer_ptrs_dev holds); state: this rank's own zero-initialised device
- * uint32[8] (call counter; state[7] != 0 after a call = a peer never arrived within the bounded wait).  Every rank must enqueue the
- * same sequence of calls. */
+ * uint32[8] (call counter; state[7] != 0 after a call = a peer never arrived within the bounded wait).  multicast_ptr (optional, may
+ * be NULL): the NVSwitch multicast mapping of the same buffer (symmetric-memory handle's multicast_ptr); with it the reduction is one
+ * pass of multimem.ld_reduce / multimem.st -- the switch adds the ranks' values -- and two barriers.  A buffer must always be reduced
+ * with the same choice.  Every rank must enqueue the same sequence of calls. */
 int b4r_p2p_allreduce_max_world(void);
-int b4r_p2p_allreduce_f32(const void* buffer_ptrs_dev, const void* flag_ptrs_dev, size_t offset_floats, size_t n_floats, int rank,
-                          int world, void* state, void* stream);
+int b4r_p2p_allreduce_f32(const void* buffer_ptrs_dev, const void* flag_ptrs_dev, void* multicast_ptr, size_t offset_floats,
+                          size_t n_floats, int rank, int world, void* state, void* stream);
 
 /* AdamWeightDecay.apply_gradients (adam_w_optimizer.py:100-136): clip_by_global_norm, WarmUp/PolynomialDecay lr,
  * decoupled decay, Adam; also refreshes shadow_bf16.  The gradient is first multiplied by grad_scale / max(*count,1)

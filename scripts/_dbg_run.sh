@@ -1,1 +1,2 @@
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r02g_bench_n2.json 2> gpurun_out/r02g_bench_n2.err
+timeout 500 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 3 > gpurun_out/r5j_tests.log
+timeout 100 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r5j_smoke.log 2>&1

@@ -126,8 +126,8 @@ def test_p2p_allreduce_entry_validates_its_arguments_without_a_gpu():
     lib = _lib.load()
     assert lib.b4r_p2p_allreduce_max_world() >= 8
     one = C.c_void_p(16)
-    assert lib.b4r_p2p_allreduce_f32(None, one, 0, 4, 0, 2, one, None) != 0
-    assert lib.b4r_p2p_allreduce_f32(one, one, 0, 4, 0, 1, one, None) != 0
-    assert lib.b4r_p2p_allreduce_f32(one, one, 0, 4, 5, 4, one, None) != 0
-    assert lib.b4r_p2p_allreduce_f32(one, one, 2, 4, 0, 2, one, None) != 0
+    assert lib.b4r_p2p_allreduce_f32(None, one, None, 0, 4, 0, 2, one, None) != 0
+    assert lib.b4r_p2p_allreduce_f32(one, one, None, 0, 4, 0, 1, one, None) != 0
+    assert lib.b4r_p2p_allreduce_f32(one, one, None, 0, 4, 5, 4, one, None) != 0
+    assert lib.b4r_p2p_allreduce_f32(one, one, None, 2, 4, 0, 2, one, None) != 0
     assert b"16-byte" in lib.b4r_last_error()
