@@ -59,8 +59,8 @@ class Bert4RecEncoder:
             unsupported.append("norm_first=True (pre-LN)")
         if with_dense_inputs:
             unsupported.append("with_dense_inputs=True")
-        if output_range is not None:
-            unsupported.append("output_range")
+        if output_range is not None and (int(output_range) < 1 or int(output_range) > max_sequence_length):
+            raise ValueError(f"output_range must lie in [1, max_sequence_length], got {output_range}")
         if unsupported:
             raise NotImplementedError("Bert4RecEncoder (B200 path) does not implement: " + "; ".join(unsupported))
         self._config = {
@@ -97,6 +97,11 @@ class Bert4RecEncoder:
         sess.encode(ids, mask, training=bool(training), seed=torch.seed() & 0x7FFFFFFFFFFF if training else 0)
         L = self._config["num_layers"]
         outs = [sess.sequence_output(l).float() for l in range(L)]
+        # output_range (bert4rec_encoder.py:45-48,144): the LAST layer's target sequence is sliced to [0, output_range).  The kernels
+        # compute the whole layer (the slice only saves work in the reference); the values of the kept positions are the same.
+        k = self._config["output_range"]
+        if k is not None:
+            outs[-1] = outs[-1][:, :int(k)].contiguous()
         return dict(sequence_output=outs[-1], pooled_output=sess.pooled_output(), encoder_outputs=outs)
 
     # ------------------------------------------------------------------ accessors

@@ -1,1 +1,3 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r02h_bench_n2.json 2> gpurun_out/r02h_bench_n2.err
+# scratch driver for `gpurun -- 'bash scripts/_dbg_run.sh'`: GPU test suite + smoke
+timeout 500 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 3 > gpurun_out/last_gpu_tests.log
+timeout 100 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/last_smoke.log 2>&1

@@ -409,6 +409,25 @@ def test_model_call_output_contract():
         model.encoder("not a dict")
 
 
+def test_encoder_output_range_slices_the_last_layer():
+    """output_range (reference bert4rec_encoder.py:45-48,144 and its test bert4rec_encoder_tests.py:124-194): the last layer's target
+    sequence is [0, output_range); earlier layers keep the whole sequence; the kept values equal the unsliced encoder's."""
+    from bert4rec_b200.models.components import networks
+    kw = dict(vocab_size=203, hidden_size=64, num_layers=2, num_attention_heads=2, max_sequence_length=21, inner_dim=64)
+    full = networks.Bert4RecEncoder(**kw, device="cuda:0", seed=3)
+    part = networks.Bert4RecEncoder(**kw, output_range=1, device="cuda:0", seed=3)
+    assert part.get_config()["output_range"] == 1
+    batch = make_batch(3, 21, 4, 203, seed=1)
+    x = {k: batch[k] for k in ("input_word_ids", "input_mask")}
+    a, b = full(x), part(x)
+    assert tuple(b["sequence_output"].shape) == (3, 1, 64) and tuple(b["pooled_output"].shape) == (3, 64)
+    assert tuple(b["encoder_outputs"][0].shape) == (3, 21, 64) and tuple(b["encoder_outputs"][1].shape) == (3, 1, 64)
+    assert torch.equal(b["sequence_output"], a["sequence_output"][:, :1]) and torch.equal(b["pooled_output"], a["pooled_output"])
+    assert torch.equal(b["encoder_outputs"][0], a["encoder_outputs"][0])
+    with pytest.raises(ValueError):
+        networks.Bert4RecEncoder(**kw, output_range=0, device="cuda:0")
+
+
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_ce_forward_tcgen05_matches_mma_sync_generation(name):
     """Generation 2 (tcgen05 + TMEM + TMA) of the fused projection/CE forward against generation 1 (mma.sync) on the
