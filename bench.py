@@ -811,8 +811,10 @@ NCU_TRAFFIC = {
     ("C2", "enc_fwd_fused"): 1_029_376 + 227_328,
     ("C2", "ce_fwd_umma"): 1_879_040,
     ("C2", "ce_bwd_fused"): 1_999_616 + 809_472,
-    ("C4", "attn_bwd"): 555_940_864 + 279_664_128,       # profiles/r02_ncu_fattn_c4.md
-    ("C4", "attn_fwd"): 336_830_208 + 109_373_952,
+    ("C4", "attn_bwd"): 555_666_432 + 280_639_232,       # profiles/r02_ncu_c4_backward.md (final kernel)
+    ("C4", "attn_fwd"): 336_830_208 + 109_373_952,       # profiles/r02_ncu_fattn_c4.md
+    ("C4", "ln_bwd"): 421_081_344 + 273_888_000,         # profiles/r02_ncu_c4_backward.md
+    ("C4", "ce_fwd_umma"): 27_901_696 + 6_400,           # profiles/r02_ncu_ce_fwd_c4.md
 }
 
 
