@@ -541,7 +541,11 @@ class BERT4RecModel:
                     break
                 last = self.train_step(batch)
                 n += 1
-            logs = dict(last) if last is not None else {}
+            logs = dict(last) if last is not None else {}     # (reads the metrics: the device has finished the epoch)
+            err = self.store.p2p_error()
+            if err:
+                raise RuntimeError(f"data-parallel all-reduce: a rank did not arrive within the bounded wait (code {err}); "
+                                   "the gradients of this epoch are not trustworthy")
             if validation_data is not None:
                 val = self.evaluate(validation_data, steps=validation_steps)
                 logs.update({f"val_{k}": v for k, v in val.items()})
