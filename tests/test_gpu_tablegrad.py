@@ -44,7 +44,7 @@ def _ids(kind, T, V, rng):
 
 @pytest.mark.parametrize("kind", ["uniform", "zipf", "one_item", "chunk_aligned", "out_of_range"])
 @pytest.mark.parametrize("T,V,H", [(1, 7, 64), (63, 100, 64), (64, 5, 128), (4097, 300, 256), (12800, 12004, 64), (51200, 70000, 128),
-                                   (204800, 13047, 256), (40000, 1000003, 256)])
+                                   (204800, 13047, 256), (40000, 1000003, 256), (600000, 5003, 64)])
 def test_table_grad_is_exact_on_integer_rows(kind, T, V, H):
     rng = np.random.RandomState(T + V + H)
     ids_np = _ids(kind, T, V, rng).astype(np.int64)
