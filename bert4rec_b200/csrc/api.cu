@@ -217,6 +217,7 @@ struct b4r_session {
   cudaStream_t side_sort = nullptr;
   cudaEvent_t ev_sort_fork = nullptr, ev_sort = nullptr;
   TableGradArgs tg{};
+  bool sort_pending = false;   // the token sort of the current ids was enqueued by b4r_encode(training) and is not joined yet
   ~b4r_session() {
     if (ev_sort_fork) cudaEventDestroy(ev_sort_fork);
     if (ev_sort) cudaEventDestroy(ev_sort);
@@ -558,6 +559,25 @@ extern "C" int b4r_sync_shadow(b4r_session* s, void* stream) {
   return 0;
 }
 
+// The token sort of the embedding gradient (k_tablegrad.cu) depends on the ids only.  It is enqueued on its own stream branch as early
+// as possible -- by the training-mode encode, so that the small sort CTAs run beside the forward (the fused forward leaves 20 SMs
+// idle) instead of taking an SM from the persistent 148-CTA kernels at the start of the backward -- and joined right before the
+// table gradient needs it.
+static int launch_sort_branch(b4r_session* s, cudaStream_t st) {
+  s->tg.ids = s->ids;
+  CK(cudaEventRecord(s->ev_sort_fork, st));
+  CK(cudaStreamWaitEvent(s->side_sort, s->ev_sort_fork, 0));
+  {
+    cudaStream_t st_main = st; (void)st_main;
+    cudaStream_t st = s->side_sort;
+    KL("token_sort", launch_token_sort(s->tg, st));
+    s->launches += table_grad_sort_launches(s->tg.T, s->tg.V) - 1;
+  }
+  CK(cudaEventRecord(s->ev_sort, s->side_sort));
+  s->sort_pending = true;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 extern "C" int b4r_encode(b4r_session* s, const int64_t* ids, const int64_t* mask, int training, uint64_t seed,
                           uint32_t step, const int64_t* step_counter, void* stream) {
@@ -569,6 +589,8 @@ extern "C" int b4r_encode(b4r_session* s, const int64_t* ids, const int64_t* mas
   const float* P = s->params;
   const bf16* W = s->shadow;
   s->ids = ids; s->mask = mask;
+  s->sort_pending = false;
+  if (training && s->grads && launch_sort_branch(s, st)) return 1;
   if (s->use_fused) {
     EncFusedArgs f{};
     f.ids = ids; f.mask = mask; f.table = W + s->lay.find("word_embeddings"); f.pos = W + s->lay.find("position_embedding");
@@ -726,17 +748,9 @@ static int backward_impl(b4r_session* s, uint64_t seed, uint32_t step, const int
   // gradient accumulators that are scatter / accumulate targets
   if (!bwd_umma && !ext_dt) CK(cudaMemsetAsync(G + oE, 0, (size_t)V * H * sizeof(float), st));
   CK(cudaMemsetAsync(s->dxa, 0, (size_t)T * H * sizeof(float), st));
-  // token sort of the embedding gradient: depends on the ids only, its own branch until the end of the backward
-  s->tg.ids = s->ids; s->tg.dx = s->dxa; s->tg.grad_table = G + oE;
-  CK(cudaEventRecord(s->ev_sort_fork, st));
-  CK(cudaStreamWaitEvent(s->side_sort, s->ev_sort_fork, 0));
-  {
-    cudaStream_t st_main = st; (void)st_main;
-    cudaStream_t st = s->side_sort;
-    KL("token_sort", launch_token_sort(s->tg, st));
-    s->launches += table_grad_sort_launches(s->tg.T, s->tg.V) - 1;
-  }
-  CK(cudaEventRecord(s->ev_sort, s->side_sort));
+  // token sort of the embedding gradient: already on its branch when the forward ran in training mode (launch_sort_branch)
+  s->tg.dx = s->dxa; s->tg.grad_table = G + oE;
+  if (!s->sort_pending && launch_sort_branch(s, st)) return 1;
   CeArgs c = ce_args(s);
   bool head_done = false;
   if (join_select(s, st)) return 1;
@@ -929,6 +943,7 @@ static int backward_impl(b4r_session* s, uint64_t seed, uint32_t step, const int
     s->launches += 1;
   }
   CK(cudaEventRecord(s->ev_sort, s->side_sort));
+  s->sort_pending = false;
   if (fbwd) KL("grad_reduce:all", launch_grad_reduce(s->d_jobs_f, s->n_jobs_f, s->jobs_f_blocks, st));
   else KL("grad_reduce:all", launch_grad_reduce(s->d_jobs, s->n_jobs, s->jobs_max_len, st));
   CK(cudaStreamWaitEvent(st, s->ev_sort, 0));
