@@ -58,7 +58,9 @@ int b4r_session_create(const b4r_config* cfg, int batch, int seq_len, int max_pr
 void b4r_session_destroy(b4r_session* s);
 int b4r_sync_shadow(b4r_session* s, void* stream);   /* shadow_bf16 = bf16(params) after a host-side weight load */
 
-/* Bert4RecEncoder.call, bert4rec_encoder.py:186-231.  ids/mask: int64 [batch, seq_len]. */
+/* Bert4RecEncoder.call, bert4rec_encoder.py:186-231.  ids/mask: int64 [batch, seq_len].  With training != 0 on a session that has a
+ * gradient buffer the call also enqueues the token sort of the embedding gradient on an internal stream branch (forked from `stream`
+ * here, joined back inside b4r_backward): a stream capture must therefore contain the matching b4r_backward. */
 int b4r_encode(b4r_session* s, const int64_t* input_word_ids, const int64_t* input_mask, int training, uint64_t seed,
                uint32_t step, const int64_t* step_counter, void* stream);
 /* Dropout masks are Philox(seed; row, col, site, step + *step_counter): step_counter (optional device int64, e.g. the
